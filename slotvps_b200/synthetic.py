@@ -1,0 +1,179 @@
+"""Seeded synthetic weights and inputs for the retriever hot path.
+
+Checkpoints and datasets are unavailable offline (reference README.md:24), so every run uses
+random-init weights of the architecture named by configs/cityscapes/r50_fpn_slotvps.py and
+synthetic Cityscapes-VPS-shaped features at the head boundary.
+
+The state_dict produced here has the reference's exact key names and shapes
+(``head_series_{l}.{j}.*`` / ``conv_trans.conv.*``, dynamic_mask_head.py:72-113), so it loads
+strictly into the reference head, the oracle and ``B200DynamicMaskHead`` alike.  It is produced
+by a CPU ``torch.Generator`` so tests regenerate it from the seed instead of storing 62 MB.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+
+C = 256
+
+
+def _uniform(g, shape, bound):
+    return (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
+
+
+def _linear(g, sd, name, out_f, in_f, bias=True, gain=1.0):
+    bound = gain * math.sqrt(6.0 / (in_f + out_f))       # xavier-uniform, as _reset_parameters (:127-131)
+    sd[name + ".weight"] = _uniform(g, (out_f, in_f), bound)
+    if bias:
+        sd[name + ".bias"] = _uniform(g, (out_f,), 0.05)
+
+
+def _norm(g, sd, name, dim=C):
+    sd[name + ".weight"] = 1.0 + _uniform(g, (dim,), 0.1)
+    sd[name + ".bias"] = _uniform(g, (dim,), 0.05)
+
+
+def _retriever(g, sd, pre):
+    for n in ("to_q", "to_k", "to_v"):
+        _linear(g, sd, pre + n, C, C)
+    for n in ("norm_q", "norm_k", "norm_v", "norm1"):
+        _norm(g, sd, pre + n)
+
+
+def make_head_state_dict(seed: int = 0, per_dh_num_heads: Sequence[int] = (1, 2, 2, 2),
+                         temporal_stages: Sequence[int] = (3, 4, 5, 6), num_classes: int = 20,
+                         dim_feedforward: int = 2048, temporal_dim_feedforward: int = 1024,
+                         trans_in_dim: int = 384, num_cls: int = 2, num_reg: int = 2
+                         ) -> Dict[str, torch.Tensor]:
+    """Random-init parameters of MultiScaleDynamicMaskHead, reference key names and order."""
+    g = torch.Generator().manual_seed(10_000 + seed)
+    sd: Dict[str, torch.Tensor] = {}
+    stage = 0
+    for l, nh in enumerate(per_dh_num_heads):
+        # the reference decides per LEVEL whether its stages own a temporal head (:89)
+        level_temporal = stage in temporal_stages
+        for j in range(nh):
+            pre = f"head_series_{l}.{j}."
+            sd[pre + "self_attn.in_proj_weight"] = _uniform(g, (3 * C, C), math.sqrt(6.0 / (4 * C)))
+            sd[pre + "self_attn.in_proj_bias"] = _uniform(g, (3 * C,), 0.05)
+            _linear(g, sd, pre + "self_attn.out_proj", C, C)
+            _retriever(g, sd, pre + "inst_interact.")
+            _linear(g, sd, pre + "linear1", dim_feedforward, C)
+            _linear(g, sd, pre + "linear2", C, dim_feedforward)
+            for n in ("norm1", "norm2", "norm3"):
+                _norm(g, sd, pre + n)
+            if level_temporal:
+                tp = pre + "temporal_query_head."
+                _retriever(g, sd, tp + "inst_interact.")
+                _linear(g, sd, tp + "linear1", temporal_dim_feedforward, C)
+                _linear(g, sd, tp + "linear2", C, temporal_dim_feedforward)
+                for n in ("norm1", "norm2", "norm3"):
+                    _norm(g, sd, tp + n)
+            for i in range(num_cls):
+                _linear(g, sd, pre + f"cls_module.{3 * i}", C, C, bias=False)
+                _norm(g, sd, pre + f"cls_module.{3 * i + 1}")
+            for i in range(num_reg):
+                _linear(g, sd, pre + f"reg_module.{3 * i}", C, C, bias=False)
+                _norm(g, sd, pre + f"reg_module.{3 * i + 1}")
+            _linear(g, sd, pre + "class_logits", num_classes, C)
+            stage += 1
+    sd["conv_trans.conv.weight"] = _uniform(g, (C, trans_in_dim, 1, 1), math.sqrt(6.0 / (trans_in_dim + C)))
+    sd["conv_trans.conv.bias"] = _uniform(g, (C,), 0.05)
+    return sd
+
+
+def make_capsule_params(seed: int = 0, n_slots: int = 100) -> Dict[str, torch.Tensor]:
+    """Parameters the retriever borrows from VPS_Capsule (vps_capsule.py:71-72, 96-97):
+    init_mask_query.weight [N,256], feat_bn (BatchNorm2d(256) eval), fg_bn (BatchNorm2d(1) eval)."""
+    g = torch.Generator().manual_seed(20_000 + seed)
+    p = {"init_mask_query.weight": _uniform(g, (n_slots, C), math.sqrt(6.0 / (n_slots + C)))}
+    p["feat_bn.weight"] = 1.0 + _uniform(g, (C,), 0.1)
+    p["feat_bn.bias"] = _uniform(g, (C,), 0.05)
+    p["feat_bn.running_mean"] = _uniform(g, (C,), 0.1)
+    p["feat_bn.running_var"] = 1.0 + _uniform(g, (C,), 0.2)
+    p["fg_bn.weight"] = torch.tensor([0.1]) + _uniform(g, (1,), 0.01)
+    p["fg_bn.bias"] = _uniform(g, (1,), 0.05)
+    p["fg_bn.running_mean"] = _uniform(g, (1,), 0.05)
+    p["fg_bn.running_var"] = 1.0 + _uniform(g, (1,), 0.2)
+    return p
+
+
+def level_shapes(H: int, W: int, n_levels: int = 4) -> List[Tuple[int, int]]:
+    """Feature sizes at strides 32,16,8,4 (coarse -> fine) of an HxW input padded to /32."""
+    Hp, Wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
+    return [(Hp // s, Wp // s) for s in (32, 16, 8, 4)][:n_levels]
+
+
+def make_features(H: int, W: int, T: int = 2, video: int = 0, frame: int = 0,
+                  shapes: Sequence[Tuple[int, int]] = None) -> List[List[torch.Tensor]]:
+    """T x 4 x [1,128,h_l,w_l] N(0,1) features (the 128-ch output of semantic_trans_ins),
+    seeded by 1000*video + frame (+ frame offset inside the clip)."""
+    shapes = shapes or level_shapes(H, W)
+    out = []
+    for t in range(T):
+        g = torch.Generator().manual_seed(1000 * video + frame + 7919 * t + 1)
+        out.append([torch.randn((1, 128, h, w), generator=g, dtype=torch.float32) for (h, w) in shapes])
+    return out
+
+
+def make_fusion_case(seed: int, n_slots: int, h: int, w: int, n_stuff: int = 11, n_things: int = 12,
+                     dup_stuff: int = 2, near_dup_things: int = 3, tiny: int = 2,
+                     num_classes: int = 20, stuff_num: int = 11):
+    """A designed (pred_logits [N,20], pred_masks [N,h,w]) pair for the fusion stage.
+
+    Random-init heads rarely keep any thing slot, so the fusion
+    parity cases are built at the fusion boundary: blobby low-frequency mask logits, ``n_stuff``
+    stuff slots (``dup_stuff`` of them repeating a class), ``n_things`` confident thing slots of
+    which ``near_dup_things`` overlap an earlier same-class thing, ``tiny`` slots whose region is a
+    few pixels, and the rest below the 0.85 score threshold or predicted no-object.
+    """
+    g = torch.Generator().manual_seed(30_000 + seed)
+    N = n_slots
+    # low-frequency fields: coarse noise upsampled bilinearly
+    ch, cw = max(2, h // 8), max(2, w // 8)
+    coarse = torch.randn((N, 1, ch, cw), generator=g)
+    masks = torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=False)[:, 0]
+    masks = masks * 6.0 + torch.randn((N, h, w), generator=g) * 0.3
+    logits = torch.randn((N, num_classes), generator=g) * 0.5
+    logits[:, num_classes - 1] += 3.0                     # default: no-object
+    perm = torch.randperm(N, generator=g)
+    k = 0
+    roles = {}
+    for i in range(n_stuff):
+        s = int(perm[k]); k += 1
+        cls = i % stuff_num if i < n_stuff - dup_stuff else int(torch.randint(0, max(1, n_stuff - dup_stuff), (1,), generator=g))
+        logits[s] = -4.0
+        logits[s, cls] = 4.0 + float(torch.rand(1, generator=g)) * 3
+        roles[s] = ("stuff", cls)
+    things = []
+    for i in range(n_things):
+        s = int(perm[k]); k += 1
+        cls = stuff_num + int(torch.randint(0, num_classes - 1 - stuff_num, (1,), generator=g))
+        logits[s] = -4.0
+        logits[s, cls] = 4.0 + float(torch.rand(1, generator=g)) * 3
+        # give things a compact blob so that prob >= 0.4 somewhere
+        cy, cx = int(torch.randint(0, h, (1,), generator=g)), int(torch.randint(0, w, (1,), generator=g))
+        yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        r = 2.0 + float(torch.rand(1, generator=g)) * min(h, w) / 6
+        masks[s] = masks[s] * 0.3 + 14.0 * torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * r * r)) - 2.0
+        things.append((s, cls))
+        roles[s] = ("thing", cls)
+    for i in range(min(near_dup_things, len(things))):
+        s = int(perm[k]); k += 1
+        src, cls = things[i]
+        logits[s] = -4.0
+        logits[s, cls] = 3.5 + float(torch.rand(1, generator=g)) * 2
+        masks[s] = masks[src] * (0.9 + 0.2 * float(torch.rand(1, generator=g))) + torch.randn((h, w), generator=g) * 0.5
+        roles[s] = ("dup", cls)
+    for i in range(tiny):
+        s = int(perm[k]); k += 1
+        cls = stuff_num + int(torch.randint(0, num_classes - 1 - stuff_num, (1,), generator=g))
+        logits[s] = -4.0
+        logits[s, cls] = 5.0
+        masks[s] = -8.0
+        cy, cx = int(torch.randint(0, h, (1,), generator=g)), int(torch.randint(0, w, (1,), generator=g))
+        masks[s, cy, cx] = 30.0
+        roles[s] = ("tiny", cls)
+    return logits.contiguous(), masks.contiguous(), roles

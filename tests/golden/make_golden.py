@@ -1,0 +1,160 @@
+"""Generate the committed golden fixtures from the UNMODIFIED reference (run in the build container).
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests / golden vectors for the retriever path, so
+the oracle is pinned against the reference's own modules, imported in place from
+/root/reference by oracle/ref_import.py (nothing of the reference is copied).  Inputs and weights
+are regenerated from seeds by slotvps_b200.synthetic, so only OUTPUTS are stored:
+
+  head_*.npz     MultiScaleDynamicMaskHead.forward  (dynamic_mask_head.py:138) cls / emb of all
+                 7 stages for every frame + a strided sample of the fused features
+  pos_*.npz      PositionEmbeddingSine              (position_encoding.py:236)
+  masklogit.npz  generate_final_outputs             (vps_temporal_slots.py:144)
+  fusion_*.npz   PostProcessPanopticInstances.forward (:659) + the inline fusion of simple_test
+                 (:411-435), obtained by running the reference's simple_test with its
+                 backbone / semantic head / retriever head replaced by tensor sources.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_import  # noqa: E402
+from slotvps_b200 import synthetic  # noqa: E402
+
+HEAD_CASES = {
+    # name: (T, n_slots, level shapes coarse->fine, weight seed, per_dh_num_heads, temporal stages)
+    "head_t2_n100": dict(T=2, N=100, shapes=[(2, 4), (4, 8), (8, 16), (16, 32)], seed=0),
+    "head_t1_n50": dict(T=1, N=50, shapes=[(3, 5), (6, 10), (12, 20), (24, 40)], seed=1),
+    "head_t3_n128": dict(T=3, N=128, shapes=[(2, 3), (4, 6), (8, 12), (16, 24)], seed=2),
+}
+POS_SHAPES = [(2, 4), (16, 32), (34, 60), (7, 5)]
+FUSION_CASES = {
+    "fusion_a": dict(seed=0, N=100, h=24, w=40, n_things=12, dup_stuff=2, near_dup_things=3, tiny=2),
+    "fusion_b": dict(seed=1, N=100, h=16, w=32, n_things=5, dup_stuff=0, near_dup_things=1, tiny=0),
+    "fusion_c": dict(seed=2, N=60, h=32, w=24, n_things=20, dup_stuff=4, near_dup_things=6, tiny=3),
+    "fusion_d": dict(seed=3, N=100, h=20, w=20, n_things=0, dup_stuff=3, near_dup_things=0, tiny=1),
+    "fusion_e": dict(seed=4, N=100, h=12, w=28, n_things=30, dup_stuff=1, near_dup_things=8, tiny=4),
+}
+
+
+def ref_pos(model, feat):
+    from mmdet.core.utils.misc import nested_tensor_from_tensor_list
+    return model.image_model.position_embedding(nested_tensor_from_tensor_list(feat))
+
+
+def gen_head(model, name, T, N, shapes, seed):
+    head = model.image_model.dynamic_mask_head
+    head.load_state_dict(synthetic.make_head_state_dict(seed), strict=True)
+    cap = synthetic.make_capsule_params(seed, N)
+    feats = synthetic.make_features(0, 0, T=T, video=seed, frame=0, shapes=shapes)
+    pos = [[ref_pos(model, f) for f in feats[t]] for t in range(T)]
+    q = cap["init_mask_query.weight"]
+    with torch.no_grad():
+        cls, emb, fused = head(features=[list(f) for f in feats], init_masks=[q.clone() for _ in range(T)],
+                               pad_mask=None, pos=pos, query_pos=None, gt_non_void_mask=None)
+    out = {}
+    for t in range(T):
+        out[f"cls{t}"] = cls[t].numpy()
+        out[f"emb{t}"] = emb[t].numpy()
+        for l in range(4):
+            f = fused[t][l][0]
+            out[f"fused{t}_{l}_sample"] = f[::7, ::3, ::5].contiguous().numpy()
+            out[f"fused{t}_{l}_sum"] = np.float64(f.double().sum().item())
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    return fused, emb, cap
+
+
+def gen_masklogit(model, fused, emb, cap):
+    im = model.image_model
+    for k in ("weight", "bias", "running_mean", "running_var"):
+        getattr(im.feat_bn, k).data.copy_(cap["feat_bn." + k])
+        getattr(im.fg_bn, k).data.copy_(cap["fg_bn." + k])
+    with torch.no_grad():
+        _, mask_output, _ = model.generate_final_outputs([f.clone() for f in fused[-1]], emb[-1], generate_aux_output=False)
+    np.savez_compressed(os.path.join(HERE, "masklogit.npz"), pred_masks=mask_output[0].numpy())
+
+
+class _Fn(torch.nn.Module):
+    """nn.Module shell so a tensor source can replace a child module of the reference model."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def forward(self, *a, **k):
+        return self.fn(*a, **k)
+
+
+def gen_fusion(model, name, seed, N, h, w, **kw):
+    """Drive the reference's simple_test with tensor sources in place of backbone/head."""
+    logits, masks, _ = synthetic.make_fusion_case(seed, N, h, w, **kw)
+    H, W = 4 * h, 4 * w
+    im = model.image_model
+    im.backbone = _Fn(lambda x: x)
+    im.neck = None
+    model.extract_semantic_feats = lambda x: (torch.zeros(1, 19, H, W), None, [torch.zeros(1, 128, 1, 1)] * 4)
+    model.semantic_trans_ins = lambda f: f
+    model.generate_position_embedding = lambda f: None
+    emb = torch.zeros(7, 1, N, 256)
+    cls = logits[None, None].repeat(7, 1, 1, 1)
+    im.dynamic_mask_head = _Fn(lambda **k: ([cls, cls], [emb, emb], [[None] * 4, [None] * 4]))
+    model.generate_final_outputs = lambda feats, om, generate_aux_output=False: (feats, masks[None], [])
+    im.init_mask_query = torch.nn.Embedding(N, 256)
+    captured = {}
+    pp = model.postprocess_panoptic
+    orig_forward = pp.forward
+
+    def spy(outputs, sizes, target_sizes=None, id=None):
+        res = orig_forward(outputs, sizes, target_sizes, id=id)
+        captured["masks"] = res.masks.clone()
+        captured["labels"] = res.labels.clone()
+        captured["probs"] = res.probs.clone()
+        return res
+    pp.forward = spy
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    img = torch.zeros(1, 3, H, W)
+    meta = [dict(iid=10001, filename="synthetic", ori_shape=(H, W, 3), img_shape=(H, W, 3))]
+    with torch.no_grad():
+        res = model.simple_test(img, meta, rescale=True, ref_img=[img])
+    pp.forward = orig_forward
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        panoptic=res["panoptic_outputs"][0].numpy().astype(np.int64),
+        cls_inds=res["panoptic_cls_inds"].numpy(), cls_prob=res["panoptic_cls_prob"].numpy(),
+        labels=captured["labels"].numpy(), probs=captured["probs"].numpy(),
+        masks_sum=captured["masks"].double().sum((1, 2)).numpy(),
+        masks_nnz=(captured["masks"] != 0).sum((1, 2)).numpy())
+
+
+def main():
+    torch.set_num_threads(8)
+    model, _ = ref_import.build_model(0)
+    for shp in POS_SHAPES:
+        p = ref_pos(model, torch.zeros(1, 128, *shp))
+        np.savez_compressed(os.path.join(HERE, "pos_%dx%d.npz" % shp), pos=p.numpy())
+    fused = emb = cap = None
+    for name, c in HEAD_CASES.items():
+        if c["N"] != 100:
+            m2, _ = ref_import.build_model(0, **{"other_config.proposal_num": c["N"]})
+        else:
+            m2 = model
+        f, e, cp = gen_head(m2, name, **c)
+        if name == "head_t2_n100":
+            fused, emb, cap = f, e, cp
+    gen_masklogit(model, fused, emb, cap)
+    for name, c in FUSION_CASES.items():
+        kw = dict(c)
+        m3, _ = ref_import.build_model(0, **{"other_config.proposal_num": kw["N"]})
+        gen_fusion(m3, name, kw.pop("seed"), kw.pop("N"), kw.pop("h"), kw.pop("w"), **kw)
+        print(name, "done")
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""Pin the oracle against the golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  CPU only."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import slotvps_oracle as O
+from slotvps_b200 import synthetic
+
+spec = importlib.util.spec_from_file_location(
+    "make_golden_cases", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+
+
+def _cases():
+    # read the case tables without importing the reference
+    src = open(spec.origin).read()
+    ns = {}
+    start = src.index("HEAD_CASES = {")
+    end = src.index("def ref_pos")
+    exec(src[start:end], ns)
+    return ns["HEAD_CASES"], ns["POS_SHAPES"], ns["FUSION_CASES"]
+
+
+HEAD_CASES, POS_SHAPES, FUSION_CASES = _cases()
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+@pytest.mark.parametrize("shape", POS_SHAPES)
+def test_sine_position_embedding(golden_dir, shape):
+    g = np.load(os.path.join(golden_dir, "pos_%dx%d.npz" % shape))["pos"]
+    p = O.sine_position_embedding(*shape).numpy()
+    assert p.shape == g.shape
+    np.testing.assert_allclose(p, g, rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", list(HEAD_CASES))
+def test_head_forward(golden_dir, name):
+    c = HEAD_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    P = synthetic.make_head_state_dict(c["seed"])
+    cap = synthetic.make_capsule_params(c["seed"], c["N"])
+    feats = synthetic.make_features(0, 0, T=c["T"], video=c["seed"], frame=0, shapes=c["shapes"])
+    pos = [[O.sine_position_embedding(*s) for s in c["shapes"]] for _ in range(c["T"])]
+    cls, emb, fused = O.head_forward(P, feats, [cap["init_mask_query.weight"]] * c["T"], pos)
+    for t in range(c["T"]):
+        assert cls[t].shape == g[f"cls{t}"].shape and emb[t].shape == g[f"emb{t}"].shape
+        for l in range(4):
+            f = fused[t][l][0]
+            assert rel_l2(f[::7, ::3, ::5].numpy(), g[f"fused{t}_{l}_sample"]) < 2e-6
+        # the 7-stage chain amplifies fp32 re-association noise: per-stage outputs
+        # agree to ~1e-5 early and a few 1e-4 at the last stage
+        # (measured: 7e-7 at stage 0 growing ~3-4x per stage to 5e-4..2e-3 at stage 6, and the fp64
+        # oracle is no closer to the fp32 reference than the fp32 oracle is -> it is the
+        # reference's own rounding noise, not a restatement error)
+        for s in range(7):
+            tol = 3e-6 * 3.5 ** s
+            assert rel_l2(emb[t][s].numpy(), g[f"emb{t}"][s]) < tol, (t, s)
+            assert rel_l2(cls[t][s].numpy(), g[f"cls{t}"][s]) < tol, (t, s)
+
+
+def test_head_forward_fp64_close_to_reference(golden_dir):
+    """fp64 oracle ('truth') vs the fp32 reference: bounded by the reference's own fp32 noise."""
+    c = HEAD_CASES["head_t2_n100"]
+    g = np.load(os.path.join(golden_dir, "head_t2_n100.npz"))
+    P = {k: v.double() for k, v in synthetic.make_head_state_dict(c["seed"]).items()}
+    cap = synthetic.make_capsule_params(c["seed"], c["N"])
+    feats = [[f.double() for f in fr] for fr in synthetic.make_features(0, 0, T=2, video=c["seed"], shapes=c["shapes"])]
+    pos = [[O.sine_position_embedding(*s, dtype=torch.float64) for s in c["shapes"]] for _ in range(2)]
+    cls, emb, _ = O.head_forward(P, feats, [cap["init_mask_query.weight"].double()] * 2, pos)
+    assert rel_l2(emb[1][-1].numpy(), g["emb1"][-1]) < 5e-3
+
+
+def test_mask_logits(golden_dir):
+    c = HEAD_CASES["head_t2_n100"]
+    g = np.load(os.path.join(golden_dir, "masklogit.npz"))["pred_masks"]
+    P = synthetic.make_head_state_dict(c["seed"])
+    cap = synthetic.make_capsule_params(c["seed"], c["N"])
+    feats = synthetic.make_features(0, 0, T=2, video=c["seed"], shapes=c["shapes"])
+    pos = [[O.sine_position_embedding(*s) for s in c["shapes"]] for _ in range(2)]
+    cls, emb, fused = O.head_forward(P, feats, [cap["init_mask_query.weight"]] * 2, pos)
+    pm = O.mask_logits(fused[-1][-1][0], emb[-1][-1, 0], cap)
+    assert pm.shape == g.shape
+    assert rel_l2(pm.numpy(), g) < 5e-3     # inherits the stage-6 drift of the embedding
+    # teacher-forced (same inputs -> tight): recompute from the golden embedding is not possible
+    # without the reference features, so the tight check lives in test_oracle_vs_reference.py
+
+
+@pytest.mark.parametrize("name", list(FUSION_CASES))
+def test_panoptic_fusion_bit_exact(golden_dir, name):
+    c = dict(FUSION_CASES[name])
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    seed, N, h, w = c.pop("seed"), c.pop("N"), c.pop("h"), c.pop("w")
+    logits, masks, _ = synthetic.make_fusion_case(seed, N, h, w, **c)
+    r = O.panoptic_fuse(logits, masks, (4 * h, 4 * w), want_masks=True)
+    np.testing.assert_array_equal(r.labels, g["labels"])
+    np.testing.assert_allclose(r.probs, g["probs"], rtol=1e-6)
+    np.testing.assert_array_equal(r.cls_inds, g["cls_inds"])
+    np.testing.assert_array_equal((r.masks != 0).sum((1, 2)), g["masks_nnz"])
+    np.testing.assert_allclose(r.masks.astype(np.float64).sum((1, 2)), g["masks_sum"], rtol=1e-9, atol=1e-6)
+    np.testing.assert_array_equal(r.panoptic, g["panoptic"])       # bit-identical id map
+    assert r.panoptic.dtype == np.int64
