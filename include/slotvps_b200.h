@@ -1,0 +1,161 @@
+/*
+ * slotvps_b200 -- C ABI of the B200-native (sm_100a) Slot-VPS retriever hot path.
+ *
+ * The reference has no FFI for this path: it is PyTorch module code.  Each entry point below
+ * replaces one reference interface (cited as file:line under /root/reference) and is what a
+ * ctypes / torch-extension binding on the reference side would call (INTEGRATION.md shows the
+ * stub).  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer to fp32 unless noted;
+ *   - every function takes the CUDA stream it must enqueue on (cudaStream_t passed as void*),
+ *     never allocates, never synchronises the device unless stated; scratch memory comes from
+ *     the caller (slotvps_*_workspace_bytes);
+ *   - returns 0 on success, a negative SLOTVPS_E* code otherwise; slotvps_last_error() gives
+ *     a thread-local message.  Thread-compatible, not re-entrant on one workspace.
+ *   - tensors use the reference's own layouts: features NCHW ([C][h][w] per frame), slots
+ *     [N][C] row-major, id maps [H][W] int64.
+ */
+#ifndef SLOTVPS_B200_H_
+#define SLOTVPS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLOTVPS_MAX_LEVELS 4
+#define SLOTVPS_MAX_STAGES 8
+#define SLOTVPS_MAX_FRAMES 8
+#define SLOTVPS_C 256              /* dh_dim, fixed by the kernels */
+#define SLOTVPS_CIN 128            /* channels of the per-level input features */
+
+enum {
+  SLOTVPS_OK = 0,
+  SLOTVPS_EINVAL = -1,             /* bad argument / unsupported shape */
+  SLOTVPS_ECUDA = -2,              /* a CUDA call or launch failed */
+  SLOTVPS_EWORKSPACE = -3,         /* workspace too small */
+  SLOTVPS_EUNSUPPORTED = -4        /* device is not sm_100 */
+};
+
+/* ---- per-stage parameter table --------------------------------------------------------
+ * One entry per MaskRCNNHead stage (dynamic_mask_head.py:231-289), pointers into the module's
+ * own parameter storage (state_dict keys head_series_{l}.{j}.<name>); tq_* are the
+ * temporal_query_head.* parameters (TemporalSlotsHead, :465-492) or NULL when the stage has
+ * no Video Retriever.  Weights are row-major [out][in] as nn.Linear stores them.            */
+typedef struct slotvps_stage_params {
+  const float *in_proj_w, *in_proj_b;          /* self_attn.in_proj_{weight,bias} [768,256],[768] */
+  const float *out_proj_w, *out_proj_b;        /* self_attn.out_proj.*            [256,256],[256] */
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b, *norm3_w, *norm3_b;
+  const float *to_q_w, *to_q_b, *to_k_w, *to_k_b, *to_v_w, *to_v_b;   /* inst_interact.to_* */
+  const float *nq_w, *nq_b, *nk_w, *nk_b, *nv_w, *nv_b, *no_w, *no_b; /* inst_interact.norm_{q,k,v}, norm1 */
+  const float *lin1_w, *lin1_b, *lin2_w, *lin2_b;                     /* [F,256],[F] / [256,F],[256] */
+  const float *cls0_w, *cls0_nw, *cls0_nb, *cls1_w, *cls1_nw, *cls1_nb; /* cls_module.{0,1,3,4} */
+  const float *reg0_w, *reg0_nw, *reg0_nb, *reg1_w, *reg1_nw, *reg1_nb; /* reg_module.{0,1,3,4} */
+  const float *logit_w, *logit_b;                                      /* class_logits [K,256],[K] */
+  /* Video Retriever (NULL if absent) */
+  const float *tq_to_q_w, *tq_to_q_b, *tq_to_k_w, *tq_to_k_b, *tq_to_v_w, *tq_to_v_b;
+  const float *tq_nq_w, *tq_nq_b, *tq_nk_w, *tq_nk_b, *tq_nv_w, *tq_nv_b, *tq_no_w, *tq_no_b;
+  const float *tq_lin1_w, *tq_lin1_b, *tq_lin2_w, *tq_lin2_b;
+  const float *tq_norm2_w, *tq_norm2_b, *tq_norm3_w, *tq_norm3_b;
+} slotvps_stage_params;
+
+/* Shape of one head invocation == the kwargs of MultiScaleDynamicMaskHead.__init__
+ * (dynamic_mask_head.py:38-54) that change the computation, plus the input sizes. */
+typedef struct slotvps_head_desc {
+  int32_t n_frames;                            /* T = len(features)                         */
+  int32_t n_slots;                             /* N = proposal_num (<= 512)                 */
+  int32_t n_levels;                            /* feat_num_levels (<= 4)                    */
+  int32_t heads_per_level[SLOTVPS_MAX_LEVELS]; /* per_dh_num_heads                          */
+  int32_t h[SLOTVPS_MAX_LEVELS], w[SLOTVPS_MAX_LEVELS]; /* coarse -> fine, each 2x the previous */
+  int32_t num_classes;                         /* 20                                        */
+  int32_t dim_feedforward;                     /* 2048                                      */
+  int32_t temporal_dim_feedforward;            /* 1024                                      */
+  int32_t nhead;                               /* 8                                         */
+  int32_t temporal_mask;                       /* bit s set: stage s runs the Video Retriever */
+  int32_t pos_mode;                            /* 0: no pos, 1: pos tensors given, 2: sine embedding generated on the fly */
+  int32_t kernel_path;                         /* 0: auto (tcgen05 when shapes allow), 1: force fp32 CUDA-core path */
+} slotvps_head_desc;
+
+/* Bytes of scratch slotvps_head_forward needs for this shape. */
+int slotvps_head_workspace_bytes(const slotvps_head_desc* d, size_t* bytes);
+
+/* One-time (per weight set) preparation: folds/centres/splits the stage weights into the
+ * operand formats of the kernels.  `prepared` is a caller-owned device buffer of
+ * slotvps_prepared_bytes() bytes that must outlive the forward calls using it.             */
+int slotvps_prepared_bytes(const slotvps_head_desc* d, size_t* bytes);
+int slotvps_prepare_weights(const slotvps_head_desc* d, const slotvps_stage_params* stages /*[n_stages]*/,
+                            const float* conv_trans_w /*[256,384]*/, const float* conv_trans_b /*[256]*/,
+                            void* prepared, void* stream);
+
+/* MultiScaleDynamicMaskHead.forward (dynamic_mask_head.py:138-228), bs == 1.
+ *   feats[t*n_levels+l] : [128,h_l,w_l]     input features (the reference's features[t][l][0])
+ *   pos[t*n_levels+l]   : [256,h_l,w_l]     position embedding, or NULL array when pos_mode != 1
+ *   init_query[t]       : [N,256]
+ *   cls_out             : [T][S][N][num_classes]   (the reference's T x [S,1,N,num_classes])
+ *   emb_out             : [T][S][N][256]
+ *   fused_out[t*n_levels+l] : [256,h_l,w_l]  transformed features (third return value)      */
+int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params* stages,
+                         const void* prepared,
+                         const float* const* feats, const float* const* pos,
+                         const float* const* init_query,
+                         float* cls_out, float* emb_out, float* const* fused_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Level fusion alone (dynamic_mask_head.py:172-185): out = conv_trans(cat(up2x(prev), x)) or,
+ * prev == NULL, conv_trans(cat(x,x,x)).  prev [256,h/2,w/2], x [128,h,w], out [256,h,w];
+ * scratch: 256*max(128,(h/2)*(w/2)) floats.                                                 */
+int slotvps_level_fuse(const float* prev, const float* x, const float* conv_w, const float* conv_b,
+                       float* out, int h, int w, float* scratch, void* stream);
+
+/* Panoptic Retriever attention alone (MaskDynamicConv.forward, dynamic_mask_head.py:423-461),
+ * one frame: slots_p [N,256] (post-norm1 slots), x [256,h,w], pos [256,h,w] | NULL
+ * -> out [N,256] = ReLU(LN(sum_pixels softmax_slots(q k^T) v)).                              */
+int slotvps_slot_attention(const slotvps_stage_params* stage, const float* slots_p, const float* x,
+                           const float* pos, float* out, int n_slots, int h, int w,
+                           int kernel_path, void* workspace, size_t workspace_bytes, void* stream);
+int slotvps_slot_attention_workspace_bytes(int n_slots, int h, int w, size_t* bytes);
+
+/* Mask-logit projection (VPS_Temporal_Slots.generate_final_outputs, vps_temporal_slots.py:144-154):
+ *   feat [256,h,w] finest fused feature, emb [N,256], feat_bn_* [256] (BatchNorm2d eval),
+ *   fg_bn = {weight, bias, running_mean, running_var} of BatchNorm2d(1) -> out [N,h,w].      */
+int slotvps_mask_logits_workspace_bytes(int n_slots, int h, int w, size_t* bytes);
+int slotvps_mask_logits(const float* feat, const float* emb,
+                        const float* feat_bn_w, const float* feat_bn_b,
+                        const float* feat_bn_mean, const float* feat_bn_var,
+                        const float* fg_bn /*[4] device: weight,bias,running_mean,running_var*/, float* out,
+                        int n_slots, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Panoptic fusion: PostProcessPanopticInstances.forward (vps_temporal_slots.py:659-807, incl.
+ * mask_removal :564-657) + the inline relabel of simple_test (:411-435), entirely on device.
+ *   pred_logits [N,num_classes], pred_masks [N,h,w] (1/4 resolution), target size (H,W).
+ * Outputs (device): panoptic [H,W] int64; meta int32[4 + 3*N]:
+ *   meta[0]=K' kept slots, meta[1]=number of things, meta[2]=filter iterations, meta[3]=converged,
+ *   then keep_index[N], label[N], (float bits) prob[N] in final order (stuff..., things...).
+ *   masks_out (optional, may be NULL): [N_cap,H,W] fp32 masked logits of the kept slots
+ *   (Instances.masks), only the first K' planes are written.                                 */
+typedef struct slotvps_fusion_cfg {
+  int32_t num_classes, stuff_num, small_area, max_iters;
+  float threshold, pixel_threshold;   /* compared in fp32, as torch / numpy do (:691, :607)      */
+  double fraction_threshold;          /* compared in fp64, as numpy does (:621-622)              */
+} slotvps_fusion_cfg;
+int slotvps_fusion_workspace_bytes(int n_slots, int H, int W, size_t* bytes);
+int slotvps_panoptic_fuse(const slotvps_fusion_cfg* cfg, const float* pred_logits, const float* pred_masks,
+                          int n_slots, int h, int w, int H, int W,
+                          int64_t* panoptic, int32_t* meta, float* masks_out, int masks_cap,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Sine position embedding (PositionEmbeddingSine.forward, position_encoding.py:236-256,
+ * normalize=True, 128 feats/axis): out [256,h,w].                                           */
+int slotvps_sine_pos(float* out, int h, int w, void* stream);
+
+/* Introspection. */
+const char* slotvps_last_error(void);
+const char* slotvps_version(void);
+/* number of kernels launched by this library on the calling thread since the last reset */
+int64_t slotvps_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLOTVPS_B200_H_ */

@@ -1,0 +1,609 @@
+// C ABI of libslotvps_b200.so (see include/slotvps_b200.h) and the host-side orchestration of the
+// retriever hot path: level fusion -> per-stage slot update / pixel attention -> mask logits ->
+// panoptic fusion.  One translation unit; kernels live in the .cuh files next to it.
+#include "common.cuh"
+#include "sgemm.cuh"
+#include "rowops.cuh"
+#include "pixel_fp32.cuh"
+#include "fusion.cuh"
+#include "pixel_tc.cuh"
+
+namespace slotvps {
+thread_local char g_err[512] = "";
+thread_local int64_t g_launches = 0;
+
+static int n_stages_of(const slotvps_head_desc* d) {
+  int s = 0;
+  for (int l = 0; l < d->n_levels; ++l) s += d->heads_per_level[l];
+  return s;
+}
+
+static int validate(const slotvps_head_desc* d) {
+  SV_REQUIRE(d != nullptr, "null descriptor");
+  SV_REQUIRE(d->n_frames >= 1 && d->n_frames <= SLOTVPS_MAX_FRAMES, "n_frames out of range");
+  SV_REQUIRE(d->n_slots >= 1 && d->n_slots <= 512, "n_slots out of range (1..512)");
+  SV_REQUIRE(d->n_levels >= 1 && d->n_levels <= SLOTVPS_MAX_LEVELS, "n_levels out of range");
+  SV_REQUIRE(n_stages_of(d) >= 1 && n_stages_of(d) <= SLOTVPS_MAX_STAGES, "stage count out of range");
+  SV_REQUIRE(d->nhead * 32 == C, "nhead must be 8 (head_dim 32)");
+  SV_REQUIRE(d->num_classes >= 2 && d->num_classes <= 256, "num_classes out of range");
+  SV_REQUIRE(d->dim_feedforward > 0 && d->temporal_dim_feedforward > 0, "feed-forward widths");
+  for (int l = 0; l < d->n_levels; ++l) {
+    SV_REQUIRE(d->h[l] > 0 && d->w[l] > 0, "empty level");
+    if (l > 0) SV_REQUIRE(d->h[l] == 2 * d->h[l - 1] && d->w[l] == 2 * d->w[l - 1], "each level must be 2x the previous");
+  }
+  SV_REQUIRE(d->pos_mode >= 0 && d->pos_mode <= 2, "pos_mode");
+  return SLOTVPS_OK;
+}
+
+// ---- prepared (folded) weights --------------------------------------------------------------------
+struct PreparedStage {
+  float *Wk_c, *bk_c, *Wv_c, *bv_c;     // output-centred key/value projections
+  float *tq_qkv_w, *tq_qkv_b, *tq_ln_w, *tq_ln_b;   // Video Retriever q|k|v stacked [768,256],[768],[3,256]
+  float *tw_w, *tw_ln_w, *tw_ln_b;      // first tower layers cls|reg stacked [512,256],[2,256]
+  TcStageOperands tc;                   // tensor-core operand planes (pixel_tc.cuh)
+};
+struct Prepared {
+  float* W0;                            // level-0 folded conv weight [256,128]
+  float *conv_w, *conv_b;               // copies of conv_trans.conv.{weight [256,384], bias [256]}
+  PreparedStage st[SLOTVPS_MAX_STAGES];
+};
+
+static size_t prepared_layout(const slotvps_head_desc* d, void* base, Prepared* out) {
+  Arena a(base, (size_t)-1);
+  Prepared p;
+  p.W0 = a.take<float>((size_t)C * CIN);
+  p.conv_w = a.take<float>((size_t)C * 3 * CIN); p.conv_b = a.take<float>(C);
+  const int S = n_stages_of(d);
+  for (int s = 0; s < S; ++s) {
+    PreparedStage& ps = p.st[s];
+    ps.Wk_c = a.take<float>((size_t)C * C); ps.bk_c = a.take<float>(C);
+    ps.Wv_c = a.take<float>((size_t)C * C); ps.bv_c = a.take<float>(C);
+    ps.tq_qkv_w = a.take<float>((size_t)3 * C * C); ps.tq_qkv_b = a.take<float>(3 * C);
+    ps.tq_ln_w = a.take<float>(3 * C); ps.tq_ln_b = a.take<float>(3 * C);
+    ps.tw_w = a.take<float>((size_t)2 * C * C); ps.tw_ln_w = a.take<float>(2 * C); ps.tw_ln_b = a.take<float>(2 * C);
+    tc_stage_layout(a, &ps.tc);
+  }
+  if (out) *out = p;
+  return align_up(a.off);
+}
+
+// Wc[o][c] = W[o][c] - mean_o W[o][c] ; bc[o] = b[o] - mean(b)   (double accumulation)
+__global__ void __launch_bounds__(256) center_rows_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                                                          float* __restrict__ Wc, float* __restrict__ bc) {
+  const int c = threadIdx.x;
+  double m = 0.0;
+  for (int o = 0; o < C; ++o) m += (double)W[o * C + c];
+  m /= C;
+  for (int o = 0; o < C; ++o) Wc[o * C + c] = (float)((double)W[o * C + c] - m);
+  __shared__ double sb[C];
+  sb[c] = (double)b[c];
+  __syncthreads();
+  double mb = 0.0;
+  for (int o = 0; o < C; ++o) mb += sb[o];
+  bc[c] = (float)(sb[c] - mb / C);
+}
+__global__ void __launch_bounds__(256) fold_w0_kernel(const float* __restrict__ W, float* __restrict__ W0) {
+  int i = blockIdx.x * 256 + threadIdx.x;            // [256][128]
+  if (i >= C * CIN) return;
+  int o = i / CIN, c = i % CIN;
+  const float* r = W + (long)o * (3 * CIN);
+  W0[i] = (float)((double)r[c] + (double)r[CIN + c] + (double)r[2 * CIN + c]);
+}
+__global__ void __launch_bounds__(256) copy_kernel(const float* __restrict__ src, float* __restrict__ dst, long n) {
+  long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+static int dcopy(const float* src, float* dst, long n, cudaStream_t s) {
+  copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, n);
+  SV_CHECK_LAUNCH("copy");
+  return SLOTVPS_OK;
+}
+
+// ---- workspace of one head invocation ----------------------------------------------------------------
+struct HeadWs {
+  float *slots, *qkv, *mo, *p, *qraw, *qt, *g0, *g1, *G;
+  float *rs_k, *rs_v, *Zpart, *a0part, *a1part, *Z, *a0, *a1, *Y, *p2, *hdn, *f, *f2;
+  float *tqkv, *L, *av, *ty, *thdn, *tw, *c2, *e1;
+  float *pos[SLOTVPS_MAX_LEVELS];       // generated sine embeddings (pos_mode 2)
+  float *ybuf;                          // coarse conv_trans partial [T][256][P/4]
+  TcWorkspace tc;
+  int chunks;
+};
+static int attn_chunks(int P, int T) {
+  int tiles = ceil_div(P, ATT_PX);
+  int per = 148 / (T > 0 ? T : 1);
+  if (per < 1) per = 1;
+  return tiles < per ? tiles : per;
+}
+static size_t head_ws_layout(const slotvps_head_desc* d, void* base, size_t cap, HeadWs* out) {
+  Arena a(base, cap);
+  HeadWs w;
+  const int T = d->n_frames, N = d->n_slots, R = T * N;
+  int Pmax = 0;
+  for (int l = 0; l < d->n_levels; ++l) Pmax = max(Pmax, d->h[l] * d->w[l]);
+  const int chunks = 148;               // upper bound of attn_chunks * NB-independent
+  w.chunks = chunks;
+  w.slots = a.take<float>((size_t)R * C); w.qkv = a.take<float>((size_t)R * 3 * C); w.mo = a.take<float>((size_t)R * C);
+  w.p = a.take<float>((size_t)R * C); w.qraw = a.take<float>((size_t)R * C); w.qt = a.take<float>((size_t)R * C);
+  w.g0 = a.take<float>(R); w.g1 = a.take<float>(R); w.G = a.take<float>((size_t)R * C);
+  w.rs_k = a.take<float>((size_t)T * Pmax); w.rs_v = a.take<float>((size_t)T * Pmax);
+  w.Zpart = a.take<float>((size_t)chunks * R * C); w.a0part = a.take<float>((size_t)chunks * R); w.a1part = a.take<float>((size_t)chunks * R);
+  w.Z = a.take<float>((size_t)R * C); w.a0 = a.take<float>(R); w.a1 = a.take<float>(R);
+  w.Y = a.take<float>((size_t)R * C); w.p2 = a.take<float>((size_t)R * C);
+  w.hdn = a.take<float>((size_t)R * max(d->dim_feedforward, d->temporal_dim_feedforward));
+  w.f = a.take<float>((size_t)R * C); w.f2 = a.take<float>((size_t)R * C);
+  w.tqkv = a.take<float>((size_t)R * 3 * C); w.L = a.take<float>((size_t)R * R); w.av = a.take<float>((size_t)R * C);
+  w.ty = a.take<float>((size_t)R * C); w.thdn = w.hdn;
+  w.tw = a.take<float>((size_t)R * 2 * C); w.c2 = a.take<float>((size_t)R * C); w.e1 = a.take<float>((size_t)R * C);
+  for (int l = 0; l < SLOTVPS_MAX_LEVELS; ++l)
+    w.pos[l] = (d->pos_mode == 2 && l < d->n_levels) ? a.take<float>((size_t)C * d->h[l] * d->w[l]) : nullptr;
+  w.ybuf = a.take<float>((size_t)T * C * (Pmax / 4 + 1));
+  tc_workspace_layout(a, d, &w.tc);
+  if (out) *out = w;
+  return align_up(a.off);
+}
+
+// ---- level fusion (dynamic_mask_head.py:172-185), folded: W.cat(up(p),x) = up(Wa.p) + Wb.x ----------
+static int level_fuse_frame(const float* prev, const float* x, const float* conv_w, const float* conv_b, const float* W0,
+                            float* out, int h, int w, float* ybuf, cudaStream_t s) {
+  const int P = h * w;
+  GemmArgs g;
+  g.B = x; g.b_ks = P; g.b_ns = 1;
+  g.Cm = out; g.c_ms = P; g.c_ns = 1;
+  g.M = C; g.N = P; g.K = CIN;
+  g.bias = conv_b; g.bias_mode = 1;
+  if (!prev) {
+    g.A = W0; g.a_ms = CIN; g.a_ks = 1;
+    return sgemm(g, s);
+  }
+  const int Pc = (h / 2) * (w / 2);
+  GemmArgs gy;
+  gy.A = conv_w; gy.a_ms = 3 * CIN; gy.a_ks = 1;
+  gy.B = prev; gy.b_ks = Pc; gy.b_ns = 1;
+  gy.Cm = ybuf; gy.c_ms = Pc; gy.c_ns = 1;
+  gy.M = C; gy.N = Pc; gy.K = C;
+  SV_TRY(sgemm(gy, s));
+  g.A = conv_w + 2 * CIN; g.a_ms = 3 * CIN; g.a_ks = 1;
+  g.up = ybuf; g.up_h = h / 2; g.up_w = w / 2;
+  return sgemm(g, s);
+}
+
+// ---- pixel attention, fp32 path: rs_k, rs_v, then fused S/softmax/Z, then deterministic reduce --------
+static int pixel_attention_fp32(const float* x, long x_bs, const float* pos, long pos_bs, const PreparedStage& ps,
+                                const HeadWs& w, int T, int N, int P, cudaStream_t s) {
+  dim3 gs(ceil_div(P, 32), T);
+  proj_rstd_kernel<<<gs, 256, 0, s>>>(x, x_bs, pos, pos_bs, ps.Wk_c, ps.bk_c, w.rs_k, P);
+  SV_CHECK_LAUNCH("proj_rstd(k)");
+  proj_rstd_kernel<<<gs, 256, 0, s>>>(x, x_bs, nullptr, 0, ps.Wv_c, ps.bv_c, w.rs_v, P);
+  SV_CHECK_LAUNCH("proj_rstd(v)");
+  const int NB = ceil_div(N, 128);
+  const int chunks = attn_chunks(P, T);
+  dim3 ga(chunks, T, NB);
+  const size_t smem = att_fp32_smem_bytes();
+#define SV_ATT(NBV)                                                                                                  \
+  {                                                                                                                  \
+    static bool attr_done = false;                                                                                   \
+    if (!attr_done) {                                                                                                \
+      SV_CHECK_CUDA(cudaFuncSetAttribute(slot_attn_fp32_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_done = true;                                                                                              \
+    }                                                                                                                \
+    slot_attn_fp32_kernel<NBV><<<ga, 256, smem, s>>>(x, x_bs, pos, pos_bs, w.G, w.g0, w.g1, w.rs_k, w.rs_v, w.Zpart,  \
+                                                     w.a0part, w.a1part, N, P, T);                                   \
+  }
+  switch (NB) {
+    case 1: SV_ATT(1) break;
+    case 2: SV_ATT(2) break;
+    case 3: SV_ATT(3) break;
+    case 4: SV_ATT(4) break;
+    default: return fail(SLOTVPS_EINVAL, "n_slots > 512 unsupported%s%s");
+  }
+#undef SV_ATT
+  SV_CHECK_LAUNCH("slot_attn_fp32");
+  const long nz = (long)T * N * C, na = (long)T * N;
+  reduce_parts_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(w.Zpart, w.Z, nz, chunks);
+  SV_CHECK_LAUNCH("reduce(Z)");
+  reduce_parts_kernel<<<(unsigned)((na + 255) / 256), 256, 0, s>>>(w.a0part, w.a0, na, chunks);
+  SV_CHECK_LAUNCH("reduce(a0)");
+  reduce_parts_kernel<<<(unsigned)((na + 255) / 256), 256, 0, s>>>(w.a1part, w.a1, na, chunks);
+  SV_CHECK_LAUNCH("reduce(a1)");
+  return SLOTVPS_OK;
+}
+
+// ---- one MaskRCNNHead stage for all frames (dynamic_mask_head.py:291-400) ------------------------------
+static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp, const PreparedStage& ps, const HeadWs& w,
+                     const float* x, long x_bs, const float* pos, long pos_bs, int h, int wd, bool temporal, bool use_tc,
+                     float* cls_out /*[T][S][N][K] base at this stage*/, long cls_frame_stride,
+                     float* emb_out, long emb_frame_stride, cudaStream_t s) {
+  const int T = d->n_frames, N = d->n_slots, R = T * N, P = h * wd, F = d->dim_feedforward, TF = d->temporal_dim_feedforward;
+  // (1) slot self-attention + norm1  (:346-358)
+  SV_TRY(linear(w.slots, sp.in_proj_w, sp.in_proj_b, w.qkv, R, C, 3 * C, 0, nullptr, s));
+  {
+    size_t smem = (size_t)(2 * N * 33 + 8 * N) * sizeof(float);
+    static size_t attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+      SV_CHECK_CUDA(cudaFuncSetAttribute(mha_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
+    }
+    mha_core_kernel<<<dim3(d->nhead, T), 256, smem, s>>>(w.qkv, w.mo, N, d->nhead);
+    SV_CHECK_LAUNCH("mha_core");
+  }
+  SV_TRY(linear(w.mo, sp.out_proj_w, sp.out_proj_b, w.qraw, R, C, C, 0, w.slots, s));       // s + attn
+  SV_TRY(ln_rows(w.qraw, nullptr, sp.norm1_w, sp.norm1_b, 1, nullptr, w.p, R, 0, s));       // p
+  // (2) query side of the Panoptic Retriever (:431) + folded key operands
+  SV_TRY(linear(w.p, sp.to_q_w, sp.to_q_b, w.qraw, R, C, C, 0, nullptr, s));
+  q_post_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.qraw, sp.nq_w, sp.nq_b, sp.nk_w, sp.nk_b, ps.bk_c, w.qt, w.g0, w.g1, R);
+  SV_CHECK_LAUNCH("q_post");
+  {
+    GemmArgs g;                                         // G = qt . Wk_c   ([R,256] x [256(o),256(c)])
+    g.A = w.qt; g.a_ms = C; g.a_ks = 1;
+    g.B = ps.Wk_c; g.b_ks = C; g.b_ns = 1;
+    g.Cm = w.G; g.c_ms = C; g.c_ns = 1;
+    g.M = R; g.N = C; g.K = C;
+    SV_TRY(sgemm(g, s));
+  }
+  // (3) pixel side: Z, a0, a1
+  if (use_tc) SV_TRY(pixel_attention_tc(x, x_bs, pos, pos_bs, ps.tc, w.tc, w.G, w.g0, w.g1, w.Z, w.a0, w.a1, T, N, h, wd, s));
+  else SV_TRY(pixel_attention_fp32(x, x_bs, pos, pos_bs, ps, w, T, N, P, s));
+  // (4) value projection on the pixel-reduced slots, norm1/ReLU, residual, norm2 (:456-459, 374-376)
+  SV_TRY(linear(w.Z, ps.Wv_c, nullptr, w.Y, R, C, C, 0, nullptr, s));
+  attn_post_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.Y, w.a0, w.a1, w.p, sp.nv_w, sp.nv_b, ps.bv_c, sp.no_w, sp.no_b,
+                                                   sp.norm2_w, sp.norm2_b, nullptr, w.p2, R);
+  SV_CHECK_LAUNCH("attn_post");
+  // (5) FFN + norm3 (:379-385), exact GELU
+  SV_TRY(linear(w.p2, sp.lin1_w, sp.lin1_b, w.hdn, R, C, F, 2, nullptr, s));
+  SV_TRY(linear(w.hdn, sp.lin2_w, sp.lin2_b, w.qraw, R, F, C, 0, w.p2, s));
+  SV_TRY(ln_rows(w.qraw, nullptr, sp.norm3_w, sp.norm3_b, 1, nullptr, w.f, R, 0, s));
+  // (6) Video Retriever over the T*N slots of all frames (:308-322, 494-527, 550-572)
+  const float* fcur = w.f;
+  if (temporal) {
+    SV_REQUIRE(sp.tq_to_q_w != nullptr, "temporal stage without temporal_query_head parameters");
+    SV_TRY(linear(w.f, ps.tq_qkv_w, ps.tq_qkv_b, w.tqkv, R, C, 3 * C, 0, nullptr, s));
+    SV_TRY(ln_rows(w.tqkv, nullptr, ps.tq_ln_w, ps.tq_ln_b, 3, nullptr, w.tqkv, 3 * R, 0, s));   // rows r*3+{q,k,v}
+    {
+      GemmArgs g;                                       // L[l,u] = q_l . k_u
+      g.A = w.tqkv; g.a_ms = 3 * C; g.a_ks = 1;
+      g.B = w.tqkv + C; g.b_ks = 1; g.b_ns = 3 * C;
+      g.Cm = w.L; g.c_ms = R; g.c_ns = 1;
+      g.M = R; g.N = R; g.K = C;
+      SV_TRY(sgemm(g, s));
+    }
+    col_softmax_kernel<<<ceil_div(R, 32), 256, 0, s>>>(w.L, R);
+    SV_CHECK_LAUNCH("col_softmax");
+    {
+      GemmArgs g;                                       // av = A . v
+      g.A = w.L; g.a_ms = R; g.a_ks = 1;
+      g.B = w.tqkv + 2 * C; g.b_ks = 3 * C; g.b_ns = 1;
+      g.Cm = w.av; g.c_ms = C; g.c_ns = 1;
+      g.M = R; g.N = C; g.K = R;
+      SV_TRY(sgemm(g, s));
+    }
+    SV_TRY(ln_rows(w.av, nullptr, sp.tq_no_w, sp.tq_no_b, 1, w.f, w.ty, R, 1, s));              // f + relu(LN(av))
+    SV_TRY(ln_rows(w.ty, nullptr, sp.tq_norm2_w, sp.tq_norm2_b, 1, nullptr, w.ty, R, 0, s));    // y
+    SV_TRY(linear(w.ty, sp.tq_lin1_w, sp.tq_lin1_b, w.thdn, R, C, TF, 1, nullptr, s));
+    SV_TRY(linear(w.thdn, sp.tq_lin2_w, sp.tq_lin2_b, w.qraw, R, TF, C, 0, w.ty, s));
+    SV_TRY(ln_rows(w.qraw, nullptr, sp.tq_norm3_w, sp.tq_norm3_b, 1, w.f, w.f2, R, 0, s));      // X + LN3(...)  (:317)
+    fcur = w.f2;
+  }
+  // (7) towers (:390-400): first layers of cls|reg share the input
+  SV_TRY(linear(fcur, ps.tw_w, nullptr, w.tw, R, C, 2 * C, 0, nullptr, s));
+  SV_TRY(ln_rows(w.tw, nullptr, ps.tw_ln_w, ps.tw_ln_b, 2, nullptr, w.tw, 2 * R, 1, s));         // rows r*2+{cls,reg}
+  SV_TRY(linear(w.tw, sp.cls1_w, nullptr, w.c2, R, C, C, 0, nullptr, s, 2 * C));
+  SV_TRY(ln_rows(w.c2, nullptr, sp.cls1_nw, sp.cls1_nb, 1, nullptr, w.c2, R, 1, s));
+  SV_TRY(linear(w.tw + C, sp.reg1_w, nullptr, w.e1, R, C, C, 0, nullptr, s, 2 * C));
+  SV_TRY(ln_rows(w.e1, nullptr, sp.reg1_nw, sp.reg1_nb, 1, nullptr, w.slots, R, 1, s));          // next-stage slots
+  for (int t = 0; t < T; ++t) {
+    SV_TRY(linear(w.c2 + (long)t * N * C, sp.logit_w, sp.logit_b, cls_out + t * cls_frame_stride, N, C, d->num_classes, 0, nullptr, s));
+    SV_TRY(dcopy(w.slots + (long)t * N * C, emb_out + t * emb_frame_stride, (long)N * C, s));
+  }
+  return SLOTVPS_OK;
+}
+
+}  // namespace slotvps
+
+using namespace slotvps;
+
+extern "C" {
+
+const char* slotvps_last_error(void) { return g_err; }
+const char* slotvps_version(void) { return "slotvps_b200 0.1 (sm_100a)"; }
+int64_t slotvps_launch_count(int reset) {
+  int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int slotvps_head_workspace_bytes(const slotvps_head_desc* d, size_t* bytes) {
+  SV_TRY(validate(d));
+  SV_REQUIRE(bytes != nullptr, "null out pointer");
+  *bytes = head_ws_layout(d, nullptr, (size_t)-1, nullptr);
+  return SLOTVPS_OK;
+}
+
+int slotvps_prepared_bytes(const slotvps_head_desc* d, size_t* bytes) {
+  SV_TRY(validate(d));
+  SV_REQUIRE(bytes != nullptr, "null out pointer");
+  *bytes = prepared_layout(d, nullptr, nullptr);
+  return SLOTVPS_OK;
+}
+
+int slotvps_prepare_weights(const slotvps_head_desc* d, const slotvps_stage_params* stages, const float* conv_w,
+                            const float* conv_b, void* prepared, void* stream) {
+  SV_TRY(validate(d));
+  SV_REQUIRE(stages && conv_w && conv_b && prepared, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  Prepared p;
+  prepared_layout(d, prepared, &p);
+  fold_w0_kernel<<<ceil_div(C * CIN, 256), 256, 0, s>>>(conv_w, p.W0);
+  SV_CHECK_LAUNCH("fold_w0");
+  SV_TRY(dcopy(conv_w, p.conv_w, (long)C * 3 * CIN, s));
+  SV_TRY(dcopy(conv_b, p.conv_b, C, s));
+  const int S = n_stages_of(d);
+  for (int i = 0; i < S; ++i) {
+    const slotvps_stage_params& sp = stages[i];
+    PreparedStage& ps = p.st[i];
+    center_rows_kernel<<<1, 256, 0, s>>>(sp.to_k_w, sp.to_k_b, ps.Wk_c, ps.bk_c);
+    SV_CHECK_LAUNCH("center(k)");
+    center_rows_kernel<<<1, 256, 0, s>>>(sp.to_v_w, sp.to_v_b, ps.Wv_c, ps.bv_c);
+    SV_CHECK_LAUNCH("center(v)");
+    if (sp.tq_to_q_w) {
+      const float* ws[3] = {sp.tq_to_q_w, sp.tq_to_k_w, sp.tq_to_v_w};
+      const float* bs[3] = {sp.tq_to_q_b, sp.tq_to_k_b, sp.tq_to_v_b};
+      const float* lw[3] = {sp.tq_nq_w, sp.tq_nk_w, sp.tq_nv_w};
+      const float* lb[3] = {sp.tq_nq_b, sp.tq_nk_b, sp.tq_nv_b};
+      for (int j = 0; j < 3; ++j) {
+        SV_TRY(dcopy(ws[j], ps.tq_qkv_w + (long)j * C * C, (long)C * C, s));
+        SV_TRY(dcopy(bs[j], ps.tq_qkv_b + j * C, C, s));
+        SV_TRY(dcopy(lw[j], ps.tq_ln_w + j * C, C, s));
+        SV_TRY(dcopy(lb[j], ps.tq_ln_b + j * C, C, s));
+      }
+    }
+    SV_TRY(dcopy(sp.cls0_w, ps.tw_w, (long)C * C, s));
+    SV_TRY(dcopy(sp.reg0_w, ps.tw_w + (long)C * C, (long)C * C, s));
+    SV_TRY(dcopy(sp.cls0_nw, ps.tw_ln_w, C, s)); SV_TRY(dcopy(sp.reg0_nw, ps.tw_ln_w + C, C, s));
+    SV_TRY(dcopy(sp.cls0_nb, ps.tw_ln_b, C, s)); SV_TRY(dcopy(sp.reg0_nb, ps.tw_ln_b + C, C, s));
+    SV_TRY(tc_prepare_stage(sp, ps.Wk_c, ps.bk_c, ps.Wv_c, ps.bv_c, ps.tc, s));
+  }
+  return SLOTVPS_OK;
+}
+
+int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params* stages, const void* prepared,
+                         const float* const* feats, const float* const* pos, const float* const* init_query,
+                         float* cls_out, float* emb_out, float* const* fused_out, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  SV_TRY(validate(d));
+  SV_REQUIRE(stages && prepared && feats && init_query && cls_out && emb_out && fused_out && workspace, "null argument");
+  SV_REQUIRE(d->pos_mode != 1 || pos != nullptr, "pos_mode 1 needs pos tensors");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int T = d->n_frames, N = d->n_slots, L = d->n_levels, S = n_stages_of(d);
+  HeadWs w;
+  if (head_ws_layout(d, workspace, workspace_bytes, &w) > workspace_bytes)
+    return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
+  Prepared pr;
+  prepared_layout(d, const_cast<void*>(prepared), &pr);
+  // frame strides of the caller's fused_out / pos tensors must be uniform per level
+  long fstride[SLOTVPS_MAX_LEVELS], pstride[SLOTVPS_MAX_LEVELS];
+  for (int l = 0; l < L; ++l) {
+    fstride[l] = T > 1 ? (long)(fused_out[1 * L + l] - fused_out[l]) : 0;
+    pstride[l] = (d->pos_mode == 1 && T > 1) ? (long)(pos[1 * L + l] - pos[l]) : 0;
+    for (int t = 0; t < T; ++t) {
+      SV_REQUIRE(fused_out[t * L + l] == fused_out[l] + t * fstride[l], "fused_out frames of a level must be equally strided");
+      if (d->pos_mode == 1) SV_REQUIRE(pos[t * L + l] == pos[l] + t * pstride[l], "pos frames of a level must be equally strided");
+    }
+  }
+  for (int t = 0; t < T; ++t) SV_TRY(dcopy(init_query[t], w.slots + (long)t * N * C, (long)N * C, s));
+  const long cls_fs = (long)S * N * d->num_classes, emb_fs = (long)S * N * C;
+  int stage = 0;
+  for (int l = 0; l < L; ++l) {
+    const int h = d->h[l], wd = d->w[l], P = h * wd;
+    for (int t = 0; t < T; ++t)
+      SV_TRY(level_fuse_frame(l > 0 ? fused_out[t * L + l - 1] : nullptr, feats[t * L + l], pr.conv_w, pr.conv_b, pr.W0,
+                              fused_out[t * L + l], h, wd, w.ybuf + (long)t * C * (P / 4 + 1), s));
+    const float* pl = nullptr;
+    long pls = 0;
+    if (d->pos_mode == 1) { pl = pos[l]; pls = pstride[l]; }
+    else if (d->pos_mode == 2) {
+      sine_pos_kernel<<<(unsigned)(((long)C * P + 255) / 256), 256, 0, s>>>(w.pos[l], h, wd);
+      SV_CHECK_LAUNCH("sine_pos");
+      pl = w.pos[l]; pls = 0;
+    }
+    const bool use_tc = d->kernel_path == 0 && tc_supported(d, l);
+    for (int j = 0; j < d->heads_per_level[l]; ++j, ++stage) {
+      const bool temporal = (d->temporal_mask >> stage) & 1;
+      SV_TRY(run_stage(d, stages[stage], pr.st[stage], w, fused_out[l], fstride[l], pl, pls, h, wd, temporal, use_tc,
+                       cls_out + (long)stage * N * d->num_classes, cls_fs, emb_out + (long)stage * N * C, emb_fs, s));
+    }
+  }
+  return SLOTVPS_OK;
+}
+
+int slotvps_level_fuse(const float* prev, const float* x, const float* conv_w, const float* conv_b, float* out, int h, int w,
+                       float* scratch, void* stream) {
+  SV_REQUIRE(x && conv_w && conv_b && out && h > 0 && w > 0, "bad argument");
+  SV_REQUIRE(scratch != nullptr, "scratch of 256*max(128, (h/2)*(w/2)) floats required");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!prev) {
+    fold_w0_kernel<<<ceil_div(C * CIN, 256), 256, 0, s>>>(conv_w, scratch);
+    SV_CHECK_LAUNCH("fold_w0");
+    return level_fuse_frame(nullptr, x, conv_w, conv_b, scratch, out, h, w, nullptr, s);
+  }
+  SV_REQUIRE(h % 2 == 0 && w % 2 == 0, "level must be 2x the previous");
+  return level_fuse_frame(prev, x, conv_w, conv_b, nullptr, out, h, w, scratch, s);
+}
+
+int slotvps_sine_pos(float* out, int h, int w, void* stream) {
+  SV_REQUIRE(out && h > 0 && w > 0, "bad argument");
+  sine_pos_kernel<<<(unsigned)(((long)C * h * w + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, h, w);
+  SV_CHECK_LAUNCH("sine_pos");
+  return SLOTVPS_OK;
+}
+
+// ---- mask logits ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_prep_kernel(const float* __restrict__ emb, const float* __restrict__ bw,
+                                                        const float* __restrict__ bb, const float* __restrict__ bm,
+                                                        const float* __restrict__ bv, const float* __restrict__ fg,
+                                                        float* __restrict__ sc, float* __restrict__ sh, float* __restrict__ e2,
+                                                        float* __restrict__ dn, float* __restrict__ aff, int N) {
+  // block 0..N-1: one slot row each (warp 0 does the row dot); also (block 0) the folded BN vectors
+  const int n = blockIdx.x, c = threadIdx.x;
+  const float s = bw[c] / sqrtf(bv[c] + BN_EPS);
+  const float t = bb[c] - bm[c] * s;
+  if (n == 0) {
+    sc[c] = s; sh[c] = t;
+    if (c == 0) { float sg = fg[0] / sqrtf(fg[3] + BN_EPS); aff[0] = sg; aff[1] = fg[1] - fg[2] * sg; }
+  }
+  const float e = emb[(long)n * C + c];
+  e2[(long)n * C + c] = e * s;
+  __shared__ float red[8];
+  float v = warp_sum(e * t);
+  if ((c & 31) == 0) red[c >> 5] = v;
+  __syncthreads();
+  if (c == 0) { float a = 0.f; for (int i = 0; i < 8; ++i) a += red[i]; dn[n] = a; }
+}
+
+int slotvps_mask_logits_workspace_bytes(int n_slots, int h, int w, size_t* bytes) {
+  SV_REQUIRE(bytes && n_slots > 0 && h > 0 && w > 0, "bad argument");
+  Arena a(nullptr, (size_t)-1);
+  a.take<float>(C); a.take<float>(C); a.take<float>((size_t)n_slots * C); a.take<float>(n_slots); a.take<float>(4);
+  a.take<float>((size_t)h * w);
+  *bytes = align_up(a.off);
+  return SLOTVPS_OK;
+}
+
+int slotvps_mask_logits(const float* feat, const float* emb, const float* bw, const float* bb, const float* bm, const float* bv,
+                        const float* fg_bn, float* out, int n_slots, int h, int w, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  SV_REQUIRE(feat && emb && bw && bb && bm && bv && fg_bn && out && workspace, "null argument");
+  SV_REQUIRE(n_slots > 0 && h > 0 && w > 0, "bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int P = h * w;
+  Arena a(workspace, workspace_bytes);
+  float* sc = a.take<float>(C); float* sh = a.take<float>(C);
+  float* e2 = a.take<float>((size_t)n_slots * C); float* dn = a.take<float>(n_slots); float* aff = a.take<float>(4);
+  float* rn = a.take<float>(P);
+  if (!a.ok()) return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
+  mask_prep_kernel<<<n_slots, 256, 0, s>>>(emb, bw, bb, bm, bv, fg_bn, sc, sh, e2, dn, aff, n_slots);
+  SV_CHECK_LAUNCH("mask_prep");
+  feat_rnorm_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
+  SV_CHECK_LAUNCH("feat_rnorm");
+  GemmArgs g;
+  g.A = e2; g.a_ms = C; g.a_ks = 1;
+  g.B = feat; g.b_ks = P; g.b_ns = 1;
+  g.Cm = out; g.c_ms = P; g.c_ns = 1;
+  g.M = n_slots; g.N = P; g.K = C;
+  g.bias = dn; g.bias_mode = 1;
+  g.col_scale = rn; g.affine = aff;
+  return sgemm(g, s);
+}
+
+// ---- panoptic fusion ----------------------------------------------------------------------------------
+struct FuseWs {
+  FuseState* st;
+  unsigned int* pair;
+  unsigned short *owner, *ids;
+};
+static size_t fuse_ws_layout(int N, int H, int W, void* base, size_t cap, FuseWs* out) {
+  Arena a(base, cap);
+  FuseWs w;
+  w.st = a.take<FuseState>(1);
+  w.pair = a.take<unsigned int>((size_t)N * N);
+  w.owner = a.take<unsigned short>((size_t)H * W);
+  w.ids = a.take<unsigned short>((size_t)H * W);
+  if (out) *out = w;
+  return align_up(a.off);
+}
+int slotvps_fusion_workspace_bytes(int n_slots, int H, int W, size_t* bytes) {
+  SV_REQUIRE(bytes && n_slots > 0 && n_slots <= FUSE_MAXN && H > 0 && W > 0, "bad argument");
+  *bytes = fuse_ws_layout(n_slots, H, W, nullptr, (size_t)-1, nullptr);
+  return SLOTVPS_OK;
+}
+int slotvps_panoptic_fuse(const slotvps_fusion_cfg* cfg, const float* pred_logits, const float* pred_masks, int N, int h, int w,
+                          int H, int W, int64_t* panoptic, int32_t* meta, float* masks_out, int masks_cap, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  SV_REQUIRE(cfg && pred_logits && pred_masks && panoptic && meta && workspace, "null argument");
+  SV_REQUIRE(N > 0 && N <= FUSE_MAXN && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
+  SV_REQUIRE(cfg->num_classes >= 2 && cfg->stuff_num >= 0 && cfg->max_iters >= 1, "bad config");
+  cudaStream_t s = (cudaStream_t)stream;
+  FuseWs ws;
+  if (fuse_ws_layout(N, H, W, workspace, workspace_bytes, &ws) > workspace_bytes)
+    return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
+  const long HW = (long)H * W;
+  const int grid = (int)((HW + 255) / 256 < 148 * 16 ? (HW + 255) / 256 : 148 * 16);
+  SV_CHECK_CUDA(cudaMemsetAsync(ws.pair, 0, (size_t)N * N * sizeof(unsigned int), s));
+  SV_CHECK_CUDA(cudaMemsetAsync(meta, 0, (size_t)(4 + 3 * N) * sizeof(int32_t), s));
+  fuse_select_kernel<<<1, FUSE_MAXN, 0, s>>>(pred_logits, N, cfg->num_classes, cfg->stuff_num, cfg->threshold, ws.st);
+  SV_CHECK_LAUNCH("fuse_select");
+  fuse_count_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, cfg->pixel_threshold, ws.st, ws.pair);
+  SV_CHECK_LAUNCH("fuse_count");
+  fuse_greedy_kernel<<<1, 32, 0, s>>>(ws.st, ws.pair, HW, cfg->fraction_threshold);
+  SV_CHECK_LAUNCH("fuse_greedy");
+  fuse_owner_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, cfg->pixel_threshold, ws.st, ws.owner);
+  SV_CHECK_LAUNCH("fuse_owner");
+  for (int it = 0; it < cfg->max_iters; ++it) {
+    fuse_argmax_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, ws.st, ws.owner, ws.ids);
+    SV_CHECK_LAUNCH("fuse_argmax");
+    fuse_filter_kernel<<<1, FUSE_MAXN, 0, s>>>(ws.st, cfg->stuff_num, (unsigned)cfg->small_area, N, meta);
+    SV_CHECK_LAUNCH("fuse_filter");
+  }
+  fuse_relabel_kernel<<<grid, 256, 0, s>>>(ws.st, ws.ids, HW, (long long*)panoptic);
+  SV_CHECK_LAUNCH("fuse_relabel");
+  if (masks_out && masks_cap > 0) {
+    fuse_masks_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, ws.st, ws.owner, masks_out, masks_cap);
+    SV_CHECK_LAUNCH("fuse_masks");
+  }
+  return SLOTVPS_OK;
+}
+
+// ---- Panoptic Retriever attention alone (per-kernel parity entry point) ----------------------------------
+int slotvps_slot_attention_workspace_bytes(int n_slots, int h, int w, size_t* bytes) {
+  SV_REQUIRE(bytes && n_slots > 0 && n_slots <= 512 && h > 0 && w > 0, "bad argument");
+  slotvps_head_desc d;
+  memset(&d, 0, sizeof(d));
+  d.n_frames = 1; d.n_slots = n_slots; d.n_levels = 1; d.heads_per_level[0] = 1; d.h[0] = h; d.w[0] = w;
+  d.num_classes = 20; d.dim_feedforward = 2048; d.temporal_dim_feedforward = 1024; d.nhead = 8;
+  size_t a = head_ws_layout(&d, nullptr, (size_t)-1, nullptr), b = prepared_layout(&d, nullptr, nullptr);
+  *bytes = a + b + 4096;
+  return SLOTVPS_OK;
+}
+int slotvps_slot_attention(const slotvps_stage_params* sp, const float* slots_p, const float* x, const float* pos, float* out,
+                           int N, int h, int wd, int kernel_path, void* workspace, size_t workspace_bytes, void* stream) {
+  SV_REQUIRE(sp && slots_p && x && out && workspace, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  slotvps_head_desc d;
+  memset(&d, 0, sizeof(d));
+  d.n_frames = 1; d.n_slots = N; d.n_levels = 1; d.heads_per_level[0] = 1; d.h[0] = h; d.w[0] = wd;
+  d.num_classes = 20; d.dim_feedforward = 2048; d.temporal_dim_feedforward = 1024; d.nhead = 8;
+  d.kernel_path = kernel_path;
+  SV_TRY(validate(&d));
+  const size_t pb = prepared_layout(&d, nullptr, nullptr);
+  if (pb + head_ws_layout(&d, nullptr, (size_t)-1, nullptr) > workspace_bytes) return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
+  Prepared pr;
+  prepared_layout(&d, workspace, &pr);
+  HeadWs w;
+  head_ws_layout(&d, (char*)workspace + pb, workspace_bytes - pb, &w);
+  PreparedStage& ps = pr.st[0];
+  center_rows_kernel<<<1, 256, 0, s>>>(sp->to_k_w, sp->to_k_b, ps.Wk_c, ps.bk_c);
+  SV_CHECK_LAUNCH("center(k)");
+  center_rows_kernel<<<1, 256, 0, s>>>(sp->to_v_w, sp->to_v_b, ps.Wv_c, ps.bv_c);
+  SV_CHECK_LAUNCH("center(v)");
+  SV_TRY(tc_prepare_stage(*sp, ps.Wk_c, ps.bk_c, ps.Wv_c, ps.bv_c, ps.tc, s));
+  const int P = h * wd;
+  SV_TRY(linear(slots_p, sp->to_q_w, sp->to_q_b, w.qraw, N, C, C, 0, nullptr, s));
+  q_post_kernel<<<ceil_div(N, 8), 256, 0, s>>>(w.qraw, sp->nq_w, sp->nq_b, sp->nk_w, sp->nk_b, ps.bk_c, w.qt, w.g0, w.g1, N);
+  SV_CHECK_LAUNCH("q_post");
+  GemmArgs g;
+  g.A = w.qt; g.a_ms = C; g.a_ks = 1;
+  g.B = ps.Wk_c; g.b_ks = C; g.b_ns = 1;
+  g.Cm = w.G; g.c_ms = C; g.c_ns = 1;
+  g.M = N; g.N = C; g.K = C;
+  SV_TRY(sgemm(g, s));
+  const bool use_tc = kernel_path == 0 && tc_supported(&d, 0);
+  if (use_tc) SV_TRY(pixel_attention_tc(x, 0, pos, 0, ps.tc, w.tc, w.G, w.g0, w.g1, w.Z, w.a0, w.a1, 1, N, h, wd, s));
+  else SV_TRY(pixel_attention_fp32(x, 0, pos, 0, ps, w, 1, N, P, s));
+  SV_TRY(linear(w.Z, ps.Wv_c, nullptr, w.Y, N, C, C, 0, nullptr, s));
+  attn_post_kernel<<<ceil_div(N, 8), 256, 0, s>>>(w.Y, w.a0, w.a1, nullptr, sp->nv_w, sp->nv_b, ps.bv_c, sp->no_w, sp->no_b,
+                                                   nullptr, nullptr, out, nullptr, N);
+  SV_CHECK_LAUNCH("attn_post");
+  return SLOTVPS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// Shared helpers for the slotvps_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/slotvps_b200.h"
+
+namespace slotvps {
+
+constexpr int C = SLOTVPS_C;          // 256
+constexpr int CIN = SLOTVPS_CIN;      // 128
+constexpr float LN_EPS = 1e-5f;
+constexpr float BN_EPS = 1e-5f;
+
+extern thread_local char g_err[512];
+extern thread_local int64_t g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+#define SV_CHECK_CUDA(expr)                                                            \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) return ::slotvps::fail(SLOTVPS_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define SV_CHECK_LAUNCH(name)                                                          \
+  do {                                                                                 \
+    ++::slotvps::g_launches;                                                           \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess) return ::slotvps::fail(SLOTVPS_ECUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define SV_REQUIRE(cond, msg)                                                          \
+  do {                                                                                 \
+    if (!(cond)) return ::slotvps::fail(SLOTVPS_EINVAL, "%s (%s)", msg, #cond);        \
+  } while (0)
+
+#define SV_TRY(expr)                                                                   \
+  do {                                                                                 \
+    int _r = (expr);                                                                   \
+    if (_r != SLOTVPS_OK) return _r;                                                   \
+  } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Bump allocator over the caller-provided workspace.
+struct Arena {
+  char* base;
+  size_t cap, off;
+  Arena(void* p, size_t n) : base((char*)p), cap(n), off(0) {}
+  template <typename T>
+  T* take(size_t n) {
+    size_t o = align_up(off);
+    off = o + n * sizeof(T);
+    return (T*)(base ? base + o : nullptr);
+  }
+  bool ok() const { return off <= cap; }
+};
+
+}  // namespace slotvps

@@ -1,0 +1,362 @@
+// Panoptic fusion on device: PostProcessPanopticInstances.forward (vps_temporal_slots.py:659-807,
+// mask_removal :564-657) + the inline relabel of simple_test (:411-435), with no host round trip.
+//
+// Exact two-pass form of mask_removal: the per-pixel softmax over the K
+// kept slots sums to 1, so at most two slots can reach pixel_threshold = 0.4 at a pixel.  Hence
+//   overlap_i  = sum over earlier-kept same-class things j of |B_i & B_j|         (pair counts)
+//   A_i        = B_i minus the union of B_k of earlier-kept things                (first kept owner)
+// and one counting pass + an O(K^2) greedy + an "owner" pass reproduce the sequential NumPy loop.
+//
+// Pipeline (all on one stream):
+//   select  (1 CTA)   class softmax / keep / order            -> Sel
+//   count   (pixels)  |B_i| and pair counts of thing candidates
+//   greedy  (1 CTA)   mask_removal decisions                   -> final kept list (stuff.., things..)
+//   owner   (pixels)  owner[pixel] = first kept thing with prob >= 0.4   (uint16, 0xFFFF = none)
+//   repeat <= max_iters: argmax (pixels) -> ids + areas ; filter (1 CTA) -> drop area <= small_area
+//   relabel (pixels)  ids -> int64 panoptic labels (stuff class | 11 + thing rank), meta
+// Bilinear sampling follows F.interpolate(mode="bilinear", align_corners=False) to size (H,W).
+#pragma once
+#include "common.cuh"
+
+namespace slotvps {
+
+constexpr int FUSE_MAXN = 512;
+
+struct FuseState {                 // lives in the workspace (device)
+  int K;                           // kept by score/class filter
+  int n_stuff, n_cand;             // stuff count, thing candidates (K = n_stuff + n_cand)
+  int Kl;                          // after mask_removal: n_stuff + kept things
+  int n_things_kept;
+  int iters, converged;
+  int pad;
+  int ord[FUSE_MAXN];              // slot index per position: stuff (score desc), then thing candidates (score desc)
+  int cls[FUSE_MAXN];              // class per position (same indexing as ord)
+  float score[FUSE_MAXN];
+  int list[FUSE_MAXN];             // final list after greedy: positions into ord[] (stuff.., kept things..)
+  int thing_rank[FUSE_MAXN];       // candidate index -> rank among kept things, or -1
+  int active[FUSE_MAXN];           // per final-list entry
+  unsigned int area[FUSE_MAXN];    // per final-list entry (current iteration)
+  unsigned int cntB[FUSE_MAXN];    // per thing candidate
+  int lut[FUSE_MAXN];              // final-list entry -> panoptic label (valid once converged)
+};
+
+struct Bilin {
+  int i00, i01, i10, i11;
+  float w00, w01, w10, w11;
+};
+__device__ __forceinline__ Bilin bilin_setup(int y, int x, int h, int w, float sy_scale, float sx_scale) {
+  float sy = fmaxf(sy_scale * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(sx_scale * (x + 0.5f) - 0.5f, 0.f);
+  int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1);
+  int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  float ly = sy - y0, lx = sx - x0;
+  Bilin b;
+  b.i00 = y0 * w + x0; b.i01 = y0 * w + x1; b.i10 = y1 * w + x0; b.i11 = y1 * w + x1;
+  b.w00 = (1.f - ly) * (1.f - lx); b.w01 = (1.f - ly) * lx; b.w10 = ly * (1.f - lx); b.w11 = ly * lx;
+  return b;
+}
+// torch: h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11); evaluated with separated weights to keep
+// the same association (rounding differs by <= 1-2 ulp, inside the stated logit tolerance)
+__device__ __forceinline__ float bilin_eval(const float* __restrict__ m, const Bilin& b, float ly1, float ly0, float lx1, float lx0) {
+  return ly0 * (lx0 * __ldg(m + b.i00) + lx1 * __ldg(m + b.i01)) + ly1 * (lx0 * __ldg(m + b.i10) + lx1 * __ldg(m + b.i11));
+}
+struct Samp {
+  int i00, i01, i10, i11;
+  float ly0, ly1, lx0, lx1;
+  __device__ __forceinline__ float at(const float* __restrict__ m) const {
+    return ly0 * (lx0 * __ldg(m + i00) + lx1 * __ldg(m + i01)) + ly1 * (lx0 * __ldg(m + i10) + lx1 * __ldg(m + i11));
+  }
+};
+__device__ __forceinline__ Samp samp_setup(int y, int x, int h, int w, float sy_scale, float sx_scale, bool same) {
+  Samp s;
+  if (same) { s.i00 = s.i01 = s.i10 = s.i11 = y * w + x; s.ly0 = 1.f; s.ly1 = 0.f; s.lx0 = 1.f; s.lx1 = 0.f; return s; }
+  float sy = fmaxf(sy_scale * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(sx_scale * (x + 0.5f) - 0.5f, 0.f);
+  int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1);
+  int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  s.ly1 = sy - y0; s.ly0 = 1.f - s.ly1; s.lx1 = sx - x0; s.lx0 = 1.f - s.lx1;
+  s.i00 = y0 * w + x0; s.i01 = y0 * w + x1; s.i10 = y1 * w + x0; s.i11 = y1 * w + x1;
+  return s;
+}
+
+// ---- select: class softmax, keep filter, ordering ---------------------------------------------
+__global__ void __launch_bounds__(FUSE_MAXN) fuse_select_kernel(const float* __restrict__ logits, int N, int ncls, int stuff_num,
+                                                                float thr, FuseState* __restrict__ st) {
+  __shared__ float s_score[FUSE_MAXN];
+  __shared__ int s_cls[FUSE_MAXN];
+  __shared__ int s_keep[FUSE_MAXN];
+  __shared__ int s_cnt[2];
+  const int i = threadIdx.x;
+  if (i < 2) s_cnt[i] = 0;
+  float sc = 0.f;
+  int cl = 0, keep = 0;
+  if (i < N) {
+    const float* l = logits + (long)i * ncls;
+    float mx = l[0];
+    cl = 0;
+    for (int j = 1; j < ncls; ++j) if (l[j] > mx) { mx = l[j]; cl = j; }
+    float sum = 0.f;
+    for (int j = 0; j < ncls; ++j) sum += expf(l[j] - mx);
+    sc = 1.f / sum;                                   // softmax value of the arg-max class (exp(0)/sum)
+    keep = (cl != ncls - 1) && (sc > thr);
+  }
+  s_score[i] = sc; s_cls[i] = cl; s_keep[i] = keep;
+  __syncthreads();
+  if (keep) {
+    const bool stuff = cl <= stuff_num - 1;
+    int rank = 0;
+    for (int j = 0; j < N; ++j) {
+      if (!s_keep[j] || j == i) continue;
+      if ((s_cls[j] <= stuff_num - 1) != stuff) continue;
+      // np.argsort(score)[::-1]: descending score, equal scores -> higher index first
+      if (s_score[j] > sc || (s_score[j] == sc && j > i)) ++rank;
+    }
+    atomicAdd(&s_cnt[stuff ? 0 : 1], 1);
+    s_keep[i] = 1 + rank + (stuff ? 0 : 100000);
+  }
+  __syncthreads();
+  const int ns = s_cnt[0], nc = s_cnt[1];
+  if (keep) {
+    int code = s_keep[i] - 1;
+    int pos = code >= 100000 ? ns + (code - 100000) : code;
+    st->ord[pos] = i; st->cls[pos] = cl; st->score[pos] = sc;
+  }
+  if (i == 0) { st->K = ns + nc; st->n_stuff = ns; st->n_cand = nc; st->Kl = 0; st->n_things_kept = 0; st->iters = 0; st->converged = 0; }
+  for (int j = i; j < FUSE_MAXN; j += blockDim.x) { st->cntB[j] = 0; st->area[j] = 0; st->active[j] = 0; }
+}
+
+// ---- count: |B_i| and pair overlaps of thing candidates ------------------------------------------
+// pair [n_cand][n_cand] (global, zeroed by the caller); one thread per output pixel.
+__global__ void __launch_bounds__(256) fuse_count_kernel(const float* __restrict__ masks, int h, int w, int H, int W,
+                                                         float pix_thr, FuseState* __restrict__ st, unsigned int* __restrict__ pair) {
+  __shared__ unsigned int s_cnt[FUSE_MAXN];
+  const int K = st->K, ns = st->n_stuff, nc = st->n_cand;
+  for (int j = threadIdx.x; j < nc; j += 256) s_cnt[j] = 0;
+  __syncthreads();
+  const long P = (long)h * w;
+  const float sys = (float)h / H, sxs = (float)w / W;
+  const bool same = (h == H && w == W);
+  for (long pix = (long)blockIdx.x * 256 + threadIdx.x; pix < (long)H * W; pix += (long)gridDim.x * 256) {
+    const int y = (int)(pix / W), x = (int)(pix % W);
+    const Samp sp = samp_setup(y, x, h, w, sys, sxs, same);
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, sp.at(masks + (long)st->ord[k] * P));
+    float sum = 0.f;
+    for (int k = 0; k < K; ++k) sum += expf(sp.at(masks + (long)st->ord[k] * P) - mx);
+    int c1 = -1, c2 = -1;
+    for (int k = ns; k < K; ++k) {
+      float p = expf(sp.at(masks + (long)st->ord[k] * P) - mx) / sum;
+      if (p >= pix_thr) { if (c1 < 0) c1 = k - ns; else if (c2 < 0) c2 = k - ns; }
+    }
+    if (c1 >= 0) atomicAdd(&s_cnt[c1], 1u);
+    if (c2 >= 0) { atomicAdd(&s_cnt[c2], 1u); atomicAdd(&pair[c1 * nc + c2], 1u); atomicAdd(&pair[c2 * nc + c1], 1u); }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nc; j += 256) if (s_cnt[j]) atomicAdd(&st->cntB[j], s_cnt[j]);
+}
+
+// ---- greedy: the sequential decisions of mask_removal --------------------------------------------
+// One warp: candidate i is decided in order; lanes sum its overlaps with earlier survivors.
+__global__ void __launch_bounds__(32) fuse_greedy_kernel(FuseState* __restrict__ st, const unsigned int* __restrict__ pair, long HW, double frac_thr) {
+  __shared__ int s_rank[FUSE_MAXN];
+  __shared__ int s_cls[FUSE_MAXN];
+  const int lane = threadIdx.x;
+  const int ns = st->n_stuff, nc = st->n_cand;
+  for (int j = lane; j < nc; j += 32) { s_rank[j] = -1; s_cls[j] = st->cls[ns + j]; }
+  for (int k = lane; k < ns; k += 32) { st->list[k] = k; st->active[k] = 1; }
+  __syncwarp();
+  int nk = 0;
+  for (int i = 0; i < nc; ++i) {
+    const unsigned int b = st->cntB[i];
+    unsigned int ov = 0;
+    for (int j = lane; j < i; j += 32)
+      if (s_rank[j] >= 0 && s_cls[j] == s_cls[i]) ov += pair[i * nc + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ov += __shfl_xor_sync(0xffffffffu, ov, o);
+    bool keep = !(b == 0 || (long)b == HW);                      // constant binarisation (:620)
+    if (keep && (double)ov / (double)(float)b > frac_thr) keep = false;   // int64/float32 -> float64 (:621-622)
+    if (keep) {
+      if (lane == 0) { s_rank[i] = nk; st->list[ns + nk] = ns + i; st->active[ns + nk] = 1; }
+      ++nk;
+    }
+    __syncwarp();
+  }
+  for (int j = lane; j < nc; j += 32) st->thing_rank[j] = s_rank[j];
+  if (lane == 0) { st->Kl = ns + nk; st->n_things_kept = nk; }
+}
+
+// ---- owner: first kept thing (in order) whose softmax prob over the K kept slots is >= 0.4 --------
+__global__ void __launch_bounds__(256) fuse_owner_kernel(const float* __restrict__ masks, int h, int w, int H, int W, float pix_thr,
+                                                         const FuseState* __restrict__ st, unsigned short* __restrict__ owner) {
+  const int K = st->K, ns = st->n_stuff;
+  const long P = (long)h * w;
+  const float sys = (float)h / H, sxs = (float)w / W;
+  const bool same = (h == H && w == W);
+  for (long pix = (long)blockIdx.x * 256 + threadIdx.x; pix < (long)H * W; pix += (long)gridDim.x * 256) {
+    const int y = (int)(pix / W), x = (int)(pix % W);
+    const Samp sp = samp_setup(y, x, h, w, sys, sxs, same);
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, sp.at(masks + (long)st->ord[k] * P));
+    float sum = 0.f;
+    for (int k = 0; k < K; ++k) sum += expf(sp.at(masks + (long)st->ord[k] * P) - mx);
+    int own = 0xFFFF;
+    for (int k = ns; k < K; ++k) {
+      if (st->thing_rank[k - ns] < 0) continue;
+      float p = expf(sp.at(masks + (long)st->ord[k] * P) - mx) / sum;
+      if (p >= pix_thr) { own = st->thing_rank[k - ns]; break; }
+    }
+    owner[pix] = (unsigned short)own;
+  }
+}
+
+// ---- argmax over the active kept slots of the masked logits ---------------------------------------
+// ids[pixel] = entry of the final list (uncompacted); lowest entry wins ties (torch argmax).
+__global__ void __launch_bounds__(256) fuse_argmax_kernel(const float* __restrict__ masks, int h, int w, int H, int W,
+                                                          FuseState* __restrict__ st, const unsigned short* __restrict__ owner,
+                                                          unsigned short* __restrict__ ids) {
+  if (st->converged) return;
+  __shared__ unsigned int s_area[FUSE_MAXN];
+  __shared__ int s_first_thing, s_second_thing;
+  const int Kl = st->Kl, ns = st->n_stuff;
+  for (int j = threadIdx.x; j < Kl; j += 256) s_area[j] = 0;
+  if (threadIdx.x == 0) {
+    int f = -1, s2 = -1;
+    for (int e = ns; e < Kl; ++e) if (st->active[e]) { if (f < 0) f = e; else if (s2 < 0) { s2 = e; break; } }
+    s_first_thing = f; s_second_thing = s2;
+  }
+  __syncthreads();
+  const int first_thing = s_first_thing, second_thing = s_second_thing;
+  const long P = (long)h * w;
+  const float sys = (float)h / H, sxs = (float)w / W;
+  const bool same = (h == H && w == W);
+  for (long pix = (long)blockIdx.x * 256 + threadIdx.x; pix < (long)H * W; pix += (long)gridDim.x * 256) {
+    const int y = (int)(pix / W), x = (int)(pix % W);
+    const Samp sp = samp_setup(y, x, h, w, sys, sxs, same);
+    float best = -INFINITY;
+    int bi = -1;
+    for (int e = 0; e < ns; ++e) {
+      if (!st->active[e]) continue;
+      float v = sp.at(masks + (long)st->ord[st->list[e]] * P);
+      if (v > best) { best = v; bi = e; }
+    }
+    if (first_thing >= 0) {
+      const int own = owner[pix];
+      const int oe = own == 0xFFFF ? -1 : ns + own;            // entry of the owner (things keep their order)
+      const bool own_active = oe >= 0 && st->active[oe];
+      // all active things other than the owner carry exactly 0 here (:632-634)
+      int ze = -1;                                              // lowest active thing entry holding a zero
+      if (!own_active) ze = first_thing;
+      else ze = (first_thing != oe) ? first_thing : second_thing;
+      float tv = -INFINITY;
+      int te = -1;
+      if (own_active) { tv = sp.at(masks + (long)st->ord[st->list[oe]] * P); te = oe; }
+      if (ze >= 0 && (0.f > tv || (0.f == tv && ze < te))) { tv = 0.f; te = ze; }
+      if (tv > best) { best = tv; bi = te; }
+    }
+    ids[pix] = (unsigned short)bi;
+    if (bi >= 0) atomicAdd(&s_area[bi], 1u);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Kl; j += 256) if (s_area[j]) atomicAdd(&st->area[j], s_area[j]);
+}
+
+// ---- filter: merge duplicate stuff classes (first call only), drop area <= small_area; on
+// convergence build the label LUT of the inline fusion (vps_temporal_slots.py:420-435) and meta ----
+__global__ void __launch_bounds__(FUSE_MAXN) fuse_filter_kernel(FuseState* __restrict__ st, int stuff_num, unsigned int small_area,
+                                                                int N, int* __restrict__ meta) {
+  if (st->converged) return;
+  __shared__ unsigned int s_area[FUSE_MAXN];
+  __shared__ int s_act[FUSE_MAXN], s_cls[FUSE_MAXN], s_first[FUSE_MAXN], s_comp[FUSE_MAXN], s_lut[FUSE_MAXN];
+  __shared__ int s_removed;
+  const int e = threadIdx.x;
+  const int Kl = st->Kl, ns = st->n_stuff, it = st->iters;
+  if (e == 0) s_removed = 0;
+  if (e < Kl) { s_area[e] = st->area[e]; s_act[e] = st->active[e]; s_cls[e] = st->cls[st->list[e]]; }
+  __syncthreads();
+  if (it == 0) {                                                  // dedup=True only on the first call (:758)
+    int first = e;
+    if (e < ns && s_act[e])
+      for (int f = 0; f < e; ++f) if (s_act[f] && s_cls[f] == s_cls[e]) { first = f; break; }
+    if (e < Kl) s_first[e] = first;
+    __syncthreads();
+    if (e < ns && s_act[e] && s_first[e] == e) {
+      unsigned int a = s_area[e];
+      for (int f = e + 1; f < ns; ++f) if (s_act[f] && s_first[f] == e) a += s_area[f];
+      s_area[e] = a;
+    }
+    __syncthreads();
+    if (e < ns && s_act[e] && s_first[e] != e) s_area[e] = 0;
+    __syncthreads();
+  }
+  if (e < Kl && s_act[e] && s_area[e] <= small_area) { s_act[e] = 0; st->active[e] = 0; atomicAdd(&s_removed, 1); }
+  __syncthreads();
+  const int removed = s_removed;
+  if (removed != 0) {
+    if (e < Kl) st->area[e] = 0;
+    if (e == 0) st->iters = it + 1;
+    return;
+  }
+  // converged: every active entry is present (area > small_area) in the id map of this iteration
+  if (e == 0) {
+    int n_all = 0, n_inst = 0;
+    for (int f = 0; f < Kl; ++f) { s_comp[f] = s_act[f] ? n_all : -1; if (s_act[f]) { s_first[n_all] = f; ++n_all; if (f >= ns) ++n_inst; } }
+    // present ids ascending = compacted ids 0..n_all-1 restricted to area > 0; scan from the top
+    int npresent = 0;
+    for (int f = 0; f < Kl; ++f) if (s_act[f] && s_area[f] > 0) ++npresent;
+    int count = n_inst, i = npresent - 1;
+    for (int f = Kl - 1; f >= 0; --f) {
+      s_lut[f] = 0;
+      if (!(s_act[f] && s_area[f] > 0)) continue;
+      if (s_comp[f] >= n_all - n_inst) { s_lut[f] = stuff_num + count - 1; --count; }
+      else s_lut[f] = s_cls[s_first[i]];      // semantic_labels[i], i = position in the unique-id list (:433)
+      --i;
+    }
+    meta[0] = n_all; meta[1] = n_inst; meta[2] = it + 1; meta[3] = 1;
+    for (int c = 0; c < n_all; ++c) {
+      const int f = s_first[c];
+      meta[4 + c] = st->ord[st->list[f]];
+      meta[4 + N + c] = s_cls[f];
+      meta[4 + 2 * N + c] = __float_as_int(st->score[st->list[f]]);
+    }
+    st->iters = it + 1; st->converged = 1;
+  }
+  __syncthreads();
+  if (e < Kl) st->lut[e] = s_lut[e];
+}
+
+// ---- relabel: ids -> int64 panoptic labels -------------------------------------------------------
+__global__ void __launch_bounds__(256) fuse_relabel_kernel(const FuseState* __restrict__ st, const unsigned short* __restrict__ ids,
+                                                           long HW, long long* __restrict__ out) {
+  __shared__ int s_lut[FUSE_MAXN];
+  const int Kl = st->Kl;
+  for (int j = threadIdx.x; j < Kl; j += 256) s_lut[j] = st->lut[j];
+  __syncthreads();
+  for (long pix = (long)blockIdx.x * 256 + threadIdx.x; pix < HW; pix += (long)gridDim.x * 256) {
+    const unsigned short id = ids[pix];
+    out[pix] = id == 0xFFFF ? 0 : s_lut[id];
+  }
+}
+
+// ---- optional: materialise Instances.masks (masked logits of the final kept slots) -------------------
+__global__ void __launch_bounds__(256) fuse_masks_kernel(const float* __restrict__ masks, int h, int w, int H, int W,
+                                                         const FuseState* __restrict__ st, const unsigned short* __restrict__ owner,
+                                                         float* __restrict__ out, int cap) {
+  const int Kl = st->Kl, ns = st->n_stuff;
+  const long P = (long)h * w, HW = (long)H * W;
+  const float sys = (float)h / H, sxs = (float)w / W;
+  const bool same = (h == H && w == W);
+  for (long pix = (long)blockIdx.x * 256 + threadIdx.x; pix < HW; pix += (long)gridDim.x * 256) {
+    const int y = (int)(pix / W), x = (int)(pix % W);
+    const Samp sp = samp_setup(y, x, h, w, sys, sxs, same);
+    const int own = owner[pix];
+    int c = 0;
+    for (int e = 0; e < Kl && c < cap; ++e) {
+      if (!st->active[e]) continue;
+      float v;
+      if (e < ns) v = sp.at(masks + (long)st->ord[st->list[e]] * P);
+      else v = (own != 0xFFFF && ns + own == e) ? sp.at(masks + (long)st->ord[st->list[e]] * P) : 0.f;
+      out[(long)c * HW + pix] = v;
+      ++c;
+    }
+  }
+}
+
+}  // namespace slotvps

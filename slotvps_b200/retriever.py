@@ -1,0 +1,232 @@
+"""Mask-logit projection, panoptic fusion and the whole-clip retriever on top of the C ABI.
+
+Host-side mirrors of
+* ``VPS_Temporal_Slots.generate_final_outputs``       vps_temporal_slots.py:144-194
+* ``PostProcessPanopticInstances``                    vps_temporal_slots.py:528-807
+* the inline panoptic fusion of ``simple_test``       vps_temporal_slots.py:411-435
+All arithmetic runs in libslotvps_b200.so; nothing here falls back to torch ops or the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .head import B200DynamicMaskHead, _stream_ptr
+
+
+def _need_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (slotvps_b200 has no CPU fallback)")
+
+
+def sine_position_embedding(h: int, w: int, device) -> torch.Tensor:
+    """PositionEmbeddingSine (position_encoding.py:236-256, normalize=True) -> [1,256,h,w]."""
+    out = torch.empty((1, 256, h, w), dtype=torch.float32, device=device)
+    _lib.check(_lib.lib().slotvps_sine_pos(out.data_ptr(), h, w, _stream_ptr(out.device)), "slotvps_sine_pos")
+    return out
+
+
+def level_fuse(prev: Optional[torch.Tensor], x: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor) -> torch.Tensor:
+    """dynamic_mask_head.py:172-185 for one frame: prev [256,h/2,w/2] | None, x [128,h,w] -> [256,h,w]."""
+    _need_cuda(x, "x")
+    h, w = x.shape[-2:]
+    out = torch.empty((256, h, w), dtype=torch.float32, device=x.device)
+    scratch = torch.empty(256 * max(128, (h // 2) * (w // 2)), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().slotvps_level_fuse(None if prev is None else prev.contiguous().data_ptr(), x.contiguous().data_ptr(),
+                                             conv_w.contiguous().data_ptr(), conv_b.contiguous().data_ptr(), out.data_ptr(),
+                                             h, w, scratch.data_ptr(), _stream_ptr(x.device)), "slotvps_level_fuse")
+    return out
+
+
+def slot_attention(stage_params: Dict[str, torch.Tensor], slots_p: torch.Tensor, x: torch.Tensor,
+                   pos: Optional[torch.Tensor], kernel_path: int = 0) -> torch.Tensor:
+    """MaskDynamicConv.forward (dynamic_mask_head.py:423-461) for one frame.
+
+    stage_params: tensors keyed by the state_dict suffixes of one stage (``inst_interact.to_q.weight`` ...).
+    slots_p [N,256], x [256,h,w], pos [256,h,w] | None -> [N,256]."""
+    _need_cuda(x, "x")
+    sp = _lib.StageParams()
+    keep = []
+    for f in _lib.STAGE_FIELDS:
+        t = stage_params.get(_lib.STAGE_KEYS[f])
+        if t is not None:
+            t = t.contiguous()
+            keep.append(t)
+            setattr(sp, f, t.data_ptr())
+    N = slots_p.shape[0]
+    h, w = x.shape[-2:]
+    nbytes = C.c_size_t()
+    L = _lib.lib()
+    _lib.check(L.slotvps_slot_attention_workspace_bytes(N, h, w, C.byref(nbytes)), "slot_attention_workspace_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+    out = torch.empty((N, 256), dtype=torch.float32, device=x.device)
+    _lib.check(L.slotvps_slot_attention(C.byref(sp), slots_p.contiguous().data_ptr(), x.contiguous().data_ptr(),
+                                        None if pos is None else pos.contiguous().data_ptr(), out.data_ptr(), N, h, w,
+                                        kernel_path, ws.data_ptr(), ws.numel(), _stream_ptr(x.device)), "slotvps_slot_attention")
+    return out
+
+
+def mask_logits(feat: torch.Tensor, emb: torch.Tensor, bn: Dict[str, torch.Tensor], fg_pack: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """generate_final_outputs (vps_temporal_slots.py:145-154): feat [256,h,w], emb [N,256] -> [N,h,w].
+
+    bn: feat_bn.{weight,bias,running_mean,running_var} [256] and fg_bn.{...} [1] (BatchNorm eval)."""
+    _need_cuda(feat, "feat")
+    feat = feat.reshape(256, *feat.shape[-2:])
+    h, w = feat.shape[-2:]
+    N = emb.shape[-2]
+    if fg_pack is None:
+        fg_pack = torch.cat([bn["fg_bn.weight"].reshape(1), bn["fg_bn.bias"].reshape(1),
+                             bn["fg_bn.running_mean"].reshape(1), bn["fg_bn.running_var"].reshape(1)]).float().contiguous()
+    if out is None:
+        out = torch.empty((N, h, w), dtype=torch.float32, device=feat.device)
+    L = _lib.lib()
+    nbytes = C.c_size_t()
+    _lib.check(L.slotvps_mask_logits_workspace_bytes(N, h, w, C.byref(nbytes)), "mask_logits_workspace_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=feat.device)
+    _lib.check(L.slotvps_mask_logits(feat.contiguous().data_ptr(), emb.reshape(N, 256).contiguous().data_ptr(),
+                                     bn["feat_bn.weight"].data_ptr(), bn["feat_bn.bias"].data_ptr(),
+                                     bn["feat_bn.running_mean"].data_ptr(), bn["feat_bn.running_var"].data_ptr(),
+                                     fg_pack.data_ptr(), out.data_ptr(), N, h, w, ws.data_ptr(), ws.numel(),
+                                     _stream_ptr(feat.device)), "slotvps_mask_logits")
+    return out
+
+
+@dataclass
+class FusionOutput:
+    """Device-side result of the panoptic fusion; ``.host()`` does the one device->host read."""
+    panoptic: torch.Tensor                # [H,W] int64 (the reference's panoptic_outputs[0])
+    meta: torch.Tensor                    # int32 [4 + 3N], see include/slotvps_b200.h
+    masks: Optional[torch.Tensor]         # [cap,H,W] fp32 masked logits when requested
+    n_slots: int
+    stuff_num: int
+
+    def host(self):
+        m = self.meta.cpu().numpy()
+        k, n_things, iters, conv = int(m[0]), int(m[1]), int(m[2]), int(m[3])
+        N = self.n_slots
+        keep = m[4:4 + k].astype(np.int64)
+        labels = m[4 + N:4 + N + k].astype(np.int64)
+        probs = m[4 + 2 * N:4 + 2 * N + k].view(np.float32).copy()
+        thing = labels > self.stuff_num - 1
+        return dict(k=k, n_things=n_things, iters=iters, converged=bool(conv), keep=keep, labels=labels, probs=probs,
+                    cls_inds=labels[thing] - (self.stuff_num - 1), cls_prob=probs[thing])
+
+
+class PanopticFusion(nn.Module):
+    """PostProcessPanopticInstances (vps_temporal_slots.py:528-562 kwargs) + inline fusion (:411-435).
+
+    Only the shipped configuration is implemented on device: apply_mask_removal=True,
+    apply_mask_removal_only_ins=True, use_mask_low_constant=False, filter_small_option='4'.
+    """
+
+    def __init__(self, is_thing_map=None, threshold=0.85, output_dir="", debug=False, fraction_threshold=0.03,
+                 pixel_threshold=0.4, apply_mask_removal=True, apply_mask_removal_only_ins=True,
+                 use_mask_low_constant=False, catgories_color=None, filter_small_option='4', num_classes=20,
+                 num_stuff=11, max_iters=6):
+        super().__init__()
+        if not (apply_mask_removal and apply_mask_removal_only_ins) or use_mask_low_constant or filter_small_option != '4':
+            raise NotImplementedError("PanopticFusion implements the shipped postprocess_panoptic configuration only")
+        if is_thing_map is not None:
+            for c, t in is_thing_map.items():
+                if bool(t) != (c > num_stuff - 1):
+                    raise NotImplementedError("is_thing_map must be {c: c > num_stuff-1}")
+        self.cfg = _lib.FusionCfg(num_classes=num_classes, stuff_num=num_stuff, small_area=4, max_iters=max_iters,
+                                  threshold=threshold, pixel_threshold=pixel_threshold,
+                                  fraction_threshold=fraction_threshold)
+        self.num_stuff = num_stuff
+        self._ws = None
+
+    @torch.no_grad()
+    def fuse(self, pred_logits: torch.Tensor, pred_masks: torch.Tensor, size: Tuple[int, int],
+             want_masks: int = 0, out: Optional[torch.Tensor] = None) -> FusionOutput:
+        """pred_logits [N,num_classes], pred_masks [N,h,w] -> FusionOutput (all on device, no sync)."""
+        _need_cuda(pred_masks, "pred_masks")
+        N, h, w = pred_masks.shape
+        H, W = int(size[0]), int(size[1])
+        dev = pred_masks.device
+        L = _lib.lib()
+        nbytes = C.c_size_t()
+        _lib.check(L.slotvps_fusion_workspace_bytes(N, H, W, C.byref(nbytes)), "fusion_workspace_bytes")
+        if self._ws is None or self._ws.numel() < nbytes.value or self._ws.device != dev:
+            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        if out is None:
+            out = torch.empty((H, W), dtype=torch.int64, device=dev)
+        meta = torch.empty(4 + 3 * N, dtype=torch.int32, device=dev)
+        masks = torch.empty((want_masks, H, W), dtype=torch.float32, device=dev) if want_masks > 0 else None
+        _lib.check(L.slotvps_panoptic_fuse(C.byref(self.cfg), pred_logits.float().contiguous().data_ptr(),
+                                           pred_masks.float().contiguous().data_ptr(), N, h, w, H, W, out.data_ptr(),
+                                           meta.data_ptr(), None if masks is None else masks.data_ptr(), want_masks,
+                                           self._ws.data_ptr(), self._ws.numel(), _stream_ptr(dev)), "slotvps_panoptic_fuse")
+        return FusionOutput(out, meta, masks, N, self.num_stuff)
+
+    def forward(self, outputs, processed_sizes, target_sizes=None, id=None):
+        """Reference signature (vps_temporal_slots.py:659): ``outputs`` is an Instances-like object
+        with pred_logits [N,C] / pred_masks [N,h,w]; returns it filtered, with .masks/.probs/.labels."""
+        assert target_sizes is None or list(target_sizes) == list(processed_sizes)
+        assert len(processed_sizes) == 1
+        size = tuple(int(v) for v in processed_sizes[0])
+        N = outputs.pred_masks.shape[0]
+        fo = self.fuse(outputs.pred_logits, outputs.pred_masks, size, want_masks=N)
+        hst = fo.host()
+        if hst["k"] == 0:
+            raise ValueError("no slot survives the score/class filter (the reference raises here as well)")
+        if not hst["converged"]:
+            raise RuntimeError("small-segment filter did not converge in max_iters")
+        keep = torch.as_tensor(hst["keep"], device=outputs.pred_masks.device)
+        res = outputs[keep]
+        res.masks = fo.masks[:hst["k"]]
+        res.probs = torch.as_tensor(hst["probs"], device=keep.device)
+        res.labels = torch.as_tensor(hst["labels"], device=keep.device)
+        self.last_fusion = fo
+        return res
+
+
+class SlotVPSRetriever(nn.Module):
+    """The whole hot path for one clip: retriever head -> mask logits -> panoptic fusion.
+
+    Owns the parameters the reference keeps on VPS_Capsule for this path (vps_capsule.py:71-72,
+    96-97): ``init_mask_query``, ``feat_bn``, ``fg_bn``.
+    """
+
+    def __init__(self, head_kwargs: dict, n_slots: int = 100, fusion_kwargs: Optional[dict] = None):
+        super().__init__()
+        self.dynamic_mask_head = B200DynamicMaskHead(**head_kwargs)
+        self.init_mask_query = nn.Embedding(n_slots, 256)
+        self.feat_bn = nn.BatchNorm2d(256)
+        self.fg_bn = nn.BatchNorm2d(1)
+        self.postprocess_panoptic = PanopticFusion(**(fusion_kwargs or {}))
+        self.eval()
+
+    def load_capsule_params(self, p: Dict[str, torch.Tensor]):
+        with torch.no_grad():
+            self.init_mask_query.weight.copy_(p["init_mask_query.weight"])
+            for bn, name in ((self.feat_bn, "feat_bn"), (self.fg_bn, "fg_bn")):
+                for k in ("weight", "bias", "running_mean", "running_var"):
+                    getattr(bn, k).copy_(p[f"{name}.{k}"])
+
+    def _bn_dict(self):
+        d = {}
+        for bn, name in ((self.feat_bn, "feat_bn"), (self.fg_bn, "fg_bn")):
+            for k in ("weight", "bias", "running_mean", "running_var"):
+                d[f"{name}.{k}"] = getattr(bn, k)
+        return d
+
+    @torch.no_grad()
+    def forward(self, features: List[List[torch.Tensor]], size: Tuple[int, int], pos="sine", fuse: bool = True):
+        """features T x 4 x [1,128,h,w] (reference frame order: [ref, cur]); size = (H,W) of the image.
+        Returns dict(cls, emb, feats, pred_masks [N,h,w], fusion: FusionOutput) -- all on device."""
+        T = len(features)
+        q = self.init_mask_query.weight
+        cls, emb, feats = self.dynamic_mask_head(features, [q] * T, None, pos=pos)
+        pm = mask_logits(feats[-1][-1][0], emb[-1][-1, 0], self._bn_dict())
+        out = dict(cls=cls, emb=emb, feats=feats, pred_masks=pm)
+        if fuse:
+            out["fusion"] = self.postprocess_panoptic.fuse(cls[-1][-1, 0], pm, size)
+        return out
