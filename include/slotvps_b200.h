@@ -154,6 +154,11 @@ const char* slotvps_last_error(void);
 const char* slotvps_version(void);
 /* number of kernels launched by this library on the calling thread since the last reset */
 int64_t slotvps_launch_count(int reset);
+/* Per-launch device timing for the roofline report: between _begin and _end every kernel launch of
+ * this thread records a CUDA event on its stream; _end synchronises them and writes rows
+ * "kernel\tlaunches\ttotal_ms\n" (time between consecutive events) into buf.                  */
+int slotvps_profile_begin(void* stream);
+int slotvps_profile_end(char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

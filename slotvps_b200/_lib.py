@@ -111,6 +111,8 @@ SYMBOLS = {
     "slotvps_last_error": (C.c_char_p, []),
     "slotvps_version": (C.c_char_p, []),
     "slotvps_launch_count": (C.c_int64, [C.c_int]),
+    "slotvps_profile_begin": (C.c_int, [P]),
+    "slotvps_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
 }
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

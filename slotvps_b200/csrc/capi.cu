@@ -1,6 +1,9 @@
 // C ABI of libslotvps_b200.so (see include/slotvps_b200.h) and the host-side orchestration of the
 // retriever hot path: level fusion -> per-stage slot update / pixel attention -> mask logits ->
 // panoptic fusion.  One translation unit; kernels live in the .cuh files next to it.
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 #include "sgemm.cuh"
 #include "rowops.cuh"
@@ -11,6 +14,18 @@
 namespace slotvps {
 thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
+thread_local bool g_prof_on = false;
+
+struct ProfRec { const char* name; cudaEvent_t ev; };
+static thread_local std::vector<ProfRec> g_prof;
+static thread_local std::vector<cudaEvent_t> g_prof_pool;
+void prof_mark(const char* name, cudaStream_t s) {
+  cudaEvent_t e;
+  if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); }
+  else if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  g_prof.push_back({name, e});
+}
 
 static int n_stages_of(const slotvps_head_desc* d) {
   int s = 0;
@@ -312,6 +327,41 @@ int64_t slotvps_launch_count(int reset) {
   return v;
 }
 
+// ---- per-launch profiling (see common.cuh) ----------------------------------------------------------
+int slotvps_profile_begin(void* stream) {
+  for (auto& r : g_prof) g_prof_pool.push_back(r.ev);
+  g_prof.clear();
+  g_prof_on = true;
+  prof_mark("(begin)", (cudaStream_t)stream);
+  return SLOTVPS_OK;
+}
+// Synchronises the recorded events; writes up to `cap` rows "name\tlaunches\ttotal_ms\n" into buf.
+int slotvps_profile_end(char* buf, size_t cap) {
+  g_prof_on = false;
+  SV_REQUIRE(buf && cap > 0, "null buffer");
+  buf[0] = 0;
+  if (g_prof.empty()) return SLOTVPS_OK;
+  SV_CHECK_CUDA(cudaEventSynchronize(g_prof.back().ev));
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<int> cnt;
+  for (size_t i = 1; i < g_prof.size(); ++i) {
+    float t = 0.f;
+    SV_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof[i - 1].ev, g_prof[i].ev));
+    size_t k = 0;
+    for (; k < names.size(); ++k) if (names[k] == g_prof[i].name) break;
+    if (k == names.size()) { names.push_back(g_prof[i].name); ms.push_back(0.0); cnt.push_back(0); }
+    ms[k] += t; cnt[k] += 1;
+  }
+  size_t off = 0;
+  for (size_t k = 0; k < names.size(); ++k) {
+    int n = snprintf(buf + off, cap - off, "%s\t%d\t%.6f\n", names[k].c_str(), cnt[k], ms[k]);
+    if (n < 0 || (size_t)n >= cap - off) break;
+    off += n;
+  }
+  return SLOTVPS_OK;
+}
+
 int slotvps_head_workspace_bytes(const slotvps_head_desc* d, size_t* bytes) {
   SV_TRY(validate(d));
   SV_REQUIRE(bytes != nullptr, "null out pointer");
@@ -432,7 +482,8 @@ int slotvps_level_fuse(const float* prev, const float* x, const float* conv_w, c
 
 int slotvps_sine_pos(float* out, int h, int w, void* stream) {
   SV_REQUIRE(out && h > 0 && w > 0, "bad argument");
-  sine_pos_kernel<<<(unsigned)(((long)C * h * w + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, h, w);
+  cudaStream_t s = (cudaStream_t)stream;
+  sine_pos_kernel<<<(unsigned)(((long)C * h * w + 255) / 256), 256, 0, s>>>(out, h, w);
   SV_CHECK_LAUNCH("sine_pos");
   return SLOTVPS_OK;
 }

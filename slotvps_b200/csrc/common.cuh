@@ -18,6 +18,11 @@ constexpr float BN_EPS = 1e-5f;
 extern thread_local char g_err[512];
 extern thread_local int64_t g_launches;
 
+// Optional per-launch timing (bench.py's roofline leg): when enabled every launch records one CUDA
+// event on its stream right after the kernel; durations are differences of consecutive events.
+void prof_mark(const char* name, cudaStream_t s);
+extern thread_local bool g_prof_on;
+
 inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
   snprintf(g_err, sizeof(g_err), fmt, a, b);
   return code;
@@ -29,11 +34,13 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
     if (_e != cudaSuccess) return ::slotvps::fail(SLOTVPS_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+// requires a `cudaStream_t s` in scope (the stream the kernel was launched on)
 #define SV_CHECK_LAUNCH(name)                                                          \
   do {                                                                                 \
     ++::slotvps::g_launches;                                                           \
     cudaError_t _e = cudaGetLastError();                                               \
     if (_e != cudaSuccess) return ::slotvps::fail(SLOTVPS_ECUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+    if (::slotvps::g_prof_on) ::slotvps::prof_mark(name, s);                           \
   } while (0)
 
 #define SV_REQUIRE(cond, msg)                                                          \

@@ -219,14 +219,18 @@ class SlotVPSRetriever(nn.Module):
         return d
 
     @torch.no_grad()
-    def forward(self, features: List[List[torch.Tensor]], size: Tuple[int, int], pos="sine", fuse: bool = True):
+    def forward(self, features: List[List[torch.Tensor]], size: Tuple[int, int], pos="sine", fuse: bool = True,
+                fusion_logits: Optional[torch.Tensor] = None, panoptic_out: Optional[torch.Tensor] = None):
         """features T x 4 x [1,128,h,w] (reference frame order: [ref, cur]); size = (H,W) of the image.
-        Returns dict(cls, emb, feats, pred_masks [N,h,w], fusion: FusionOutput) -- all on device."""
+        Returns dict(cls, emb, feats, pred_masks [N,h,w], fusion: FusionOutput) -- all on device.
+        ``fusion_logits`` [N,num_classes] replaces the head's last-stage class logits at the fusion
+        input (random-init heads keep no slot; benchmarks and tests use designed ones)."""
         T = len(features)
         q = self.init_mask_query.weight
         cls, emb, feats = self.dynamic_mask_head(features, [q] * T, None, pos=pos)
         pm = mask_logits(feats[-1][-1][0], emb[-1][-1, 0], self._bn_dict())
         out = dict(cls=cls, emb=emb, feats=feats, pred_masks=pm)
         if fuse:
-            out["fusion"] = self.postprocess_panoptic.fuse(cls[-1][-1, 0], pm, size)
+            lg = cls[-1][-1, 0] if fusion_logits is None else fusion_logits
+            out["fusion"] = self.postprocess_panoptic.fuse(lg, pm, size, out=panoptic_out)
         return out

@@ -141,18 +141,22 @@ def make_fusion_case(seed: int, n_slots: int, h: int, w: int, n_stuff: int = 11,
     perm = torch.randperm(N, generator=g)
     k = 0
     roles = {}
+    # confident-class logits are all distinct and well separated so that the score ORDER (which the
+    # reference takes from np.argsort, vps_temporal_slots.py:581) is not decided by 1-ulp differences
+    n_conf = n_stuff + n_things + near_dup_things + tiny
+    strength = (2.6 + 0.06 * torch.randperm(n_conf, generator=g).float()).tolist()
     for i in range(n_stuff):
         s = int(perm[k]); k += 1
         cls = i % stuff_num if i < n_stuff - dup_stuff else int(torch.randint(0, max(1, n_stuff - dup_stuff), (1,), generator=g))
         logits[s] = -4.0
-        logits[s, cls] = 4.0 + float(torch.rand(1, generator=g)) * 3
+        logits[s, cls] = strength.pop()
         roles[s] = ("stuff", cls)
     things = []
     for i in range(n_things):
         s = int(perm[k]); k += 1
         cls = stuff_num + int(torch.randint(0, num_classes - 1 - stuff_num, (1,), generator=g))
         logits[s] = -4.0
-        logits[s, cls] = 4.0 + float(torch.rand(1, generator=g)) * 3
+        logits[s, cls] = strength.pop()
         # give things a compact blob so that prob >= 0.4 somewhere
         cy, cx = int(torch.randint(0, h, (1,), generator=g)), int(torch.randint(0, w, (1,), generator=g))
         yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
@@ -164,14 +168,14 @@ def make_fusion_case(seed: int, n_slots: int, h: int, w: int, n_stuff: int = 11,
         s = int(perm[k]); k += 1
         src, cls = things[i]
         logits[s] = -4.0
-        logits[s, cls] = 3.5 + float(torch.rand(1, generator=g)) * 2
+        logits[s, cls] = strength.pop()
         masks[s] = masks[src] * (0.9 + 0.2 * float(torch.rand(1, generator=g))) + torch.randn((h, w), generator=g) * 0.5
         roles[s] = ("dup", cls)
     for i in range(tiny):
         s = int(perm[k]); k += 1
         cls = stuff_num + int(torch.randint(0, num_classes - 1 - stuff_num, (1,), generator=g))
         logits[s] = -4.0
-        logits[s, cls] = 5.0
+        logits[s, cls] = strength.pop()
         masks[s] = -8.0
         cy, cx = int(torch.randint(0, h, (1,), generator=g)), int(torch.randint(0, w, (1,), generator=g))
         masks[s, cy, cx] = 30.0
