@@ -184,13 +184,19 @@ static int level_fuse_frame(const float* prev, const float* x, const float* conv
 }
 
 // ---- pixel attention, fp32 path: rs_k, rs_v, then fused S/softmax/Z, then deterministic reduce --------
-static int pixel_attention_fp32(const float* x, long x_bs, const float* pos, long pos_bs, const PreparedStage& ps,
-                                const HeadWs& w, int T, int N, int P, cudaStream_t s) {
-  dim3 gs(ceil_div(P, 32), T);
-  proj_rstd_kernel<<<gs, 256, 0, s>>>(x, x_bs, pos, pos_bs, ps.Wk_c, ps.bk_c, w.rs_k, P);
-  SV_CHECK_LAUNCH("proj_rstd(k)");
-  proj_rstd_kernel<<<gs, 256, 0, s>>>(x, x_bs, nullptr, 0, ps.Wv_c, ps.bv_c, w.rs_v, P);
-  SV_CHECK_LAUNCH("proj_rstd(v)");
+// (use_tc: the LayerNorm statistics -- 72 % of the contraction's FLOPs -- run on the tensor pipe from the
+//  level's bf16 operand planes, pixel_tc.cuh; the slot-softmax contraction below still runs in fp32)
+static int pixel_attention(const float* x, long x_bs, const float* pos, long pos_bs, const PreparedStage& ps,
+                           const HeadWs& w, int T, int N, int P, bool use_tc, cudaStream_t s) {
+  if (use_tc) {
+    SV_TRY(tc_stats(ps.tc, w.tc, ps.bk_c, ps.bv_c, w.rs_k, w.rs_v, T, P, s));
+  } else {
+    dim3 gs(ceil_div(P, 32), T);
+    proj_rstd_kernel<<<gs, 256, 0, s>>>(x, x_bs, pos, pos_bs, ps.Wk_c, ps.bk_c, w.rs_k, P);
+    SV_CHECK_LAUNCH("proj_rstd(k)");
+    proj_rstd_kernel<<<gs, 256, 0, s>>>(x, x_bs, nullptr, 0, ps.Wv_c, ps.bv_c, w.rs_v, P);
+    SV_CHECK_LAUNCH("proj_rstd(v)");
+  }
   const int NB = ceil_div(N, 128);
   const int chunks = attn_chunks(P, T);
   dim3 ga(chunks, T, NB);
@@ -257,8 +263,7 @@ static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp,
     SV_TRY(sgemm(g, s));
   }
   // (3) pixel side: Z, a0, a1
-  if (use_tc) SV_TRY(pixel_attention_tc(x, x_bs, pos, pos_bs, ps.tc, w.tc, w.G, w.g0, w.g1, w.Z, w.a0, w.a1, T, N, h, wd, s));
-  else SV_TRY(pixel_attention_fp32(x, x_bs, pos, pos_bs, ps, w, T, N, P, s));
+  SV_TRY(pixel_attention(x, x_bs, pos, pos_bs, ps, w, T, N, P, use_tc, s));
   // (4) value projection on the pixel-reduced slots, norm1/ReLU, residual, norm2 (:456-459, 374-376)
   SV_TRY(linear(w.Z, ps.Wv_c, nullptr, w.Y, R, C, C, 0, nullptr, s));
   attn_post_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.Y, w.a0, w.a1, w.p, sp.nv_w, sp.nv_b, ps.bv_c, sp.no_w, sp.no_b,
@@ -457,6 +462,8 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
       pl = w.pos[l]; pls = 0;
     }
     const bool use_tc = d->kernel_path == 0 && tc_supported(d, l);
+    if (use_tc && d->heads_per_level[l] > 0)
+      SV_TRY(tc_split_level(fused_out[l], fstride[l], pl, pls, false, w.tc, T, h, wd, s));
     for (int j = 0; j < d->heads_per_level[l]; ++j, ++stage) {
       const bool temporal = (d->temporal_mask >> stage) & 1;
       SV_TRY(run_stage(d, stages[stage], pr.st[stage], w, fused_out[l], fstride[l], pl, pls, h, wd, temporal, use_tc,
@@ -648,8 +655,8 @@ int slotvps_slot_attention(const slotvps_stage_params* sp, const float* slots_p,
   g.M = N; g.N = C; g.K = C;
   SV_TRY(sgemm(g, s));
   const bool use_tc = kernel_path == 0 && tc_supported(&d, 0);
-  if (use_tc) SV_TRY(pixel_attention_tc(x, 0, pos, 0, ps.tc, w.tc, w.G, w.g0, w.g1, w.Z, w.a0, w.a1, 1, N, h, wd, s));
-  else SV_TRY(pixel_attention_fp32(x, 0, pos, 0, ps, w, 1, N, P, s));
+  if (use_tc) SV_TRY(tc_split_level(x, 0, pos, 0, false, w.tc, 1, h, wd, s));
+  SV_TRY(pixel_attention(x, 0, pos, 0, ps, w, 1, N, P, use_tc, s));
   SV_TRY(linear(w.Z, ps.Wv_c, nullptr, w.Y, N, C, C, 0, nullptr, s));
   attn_post_kernel<<<ceil_div(N, 8), 256, 0, s>>>(w.Y, w.a0, w.a1, nullptr, sp->nv_w, sp->nv_b, ps.bv_c, sp->no_w, sp->no_b,
                                                    nullptr, nullptr, out, nullptr, N);
