@@ -197,29 +197,34 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
     proj_rstd_kernel<<<gs, 256, 0, s>>>(x, x_bs, nullptr, 0, ps.Wv_c, ps.bv_c, w.rs_v, P);
     SV_CHECK_LAUNCH("proj_rstd(v)");
   }
-  const int NB = ceil_div(N, 128);
-  const int chunks = attn_chunks(P, T);
-  dim3 ga(chunks, T, NB);
-  const size_t smem = att_fp32_smem_bytes();
+  int chunks = 0;
+  if (use_tc && N <= attn::NROW) {
+    SV_TRY(tc_attention(w.tc, w.tc.gplanes, w.G, w.g0, w.g1, w.rs_k, w.rs_v, w.Zpart, w.a0part, w.a1part, T, N, P, &chunks, s));
+  } else {
+    const int NB = ceil_div(N, 128);
+    chunks = attn_chunks(P, T);
+    dim3 ga(chunks, T, NB);
+    const size_t smem = att_fp32_smem_bytes();
 #define SV_ATT(NBV)                                                                                                  \
-  {                                                                                                                  \
-    static bool attr_done = false;                                                                                   \
-    if (!attr_done) {                                                                                                \
-      SV_CHECK_CUDA(cudaFuncSetAttribute(slot_attn_fp32_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_done = true;                                                                                              \
-    }                                                                                                                \
-    slot_attn_fp32_kernel<NBV><<<ga, 256, smem, s>>>(x, x_bs, pos, pos_bs, w.G, w.g0, w.g1, w.rs_k, w.rs_v, w.Zpart,  \
-                                                     w.a0part, w.a1part, N, P, T);                                   \
-  }
-  switch (NB) {
-    case 1: SV_ATT(1) break;
-    case 2: SV_ATT(2) break;
-    case 3: SV_ATT(3) break;
-    case 4: SV_ATT(4) break;
-    default: return fail(SLOTVPS_EINVAL, "n_slots > 512 unsupported%s%s");
-  }
+    {                                                                                                                  \
+      static bool attr_done = false;                                                                                   \
+      if (!attr_done) {                                                                                                \
+        SV_CHECK_CUDA(cudaFuncSetAttribute(slot_attn_fp32_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        attr_done = true;                                                                                              \
+      }                                                                                                                \
+      slot_attn_fp32_kernel<NBV><<<ga, 256, smem, s>>>(x, x_bs, pos, pos_bs, w.G, w.g0, w.g1, w.rs_k, w.rs_v, w.Zpart,  \
+                                                       w.a0part, w.a1part, N, P, T);                                   \
+    }
+    switch (NB) {
+      case 1: SV_ATT(1) break;
+      case 2: SV_ATT(2) break;
+      case 3: SV_ATT(3) break;
+      case 4: SV_ATT(4) break;
+      default: return fail(SLOTVPS_EINVAL, "n_slots > 512 unsupported%s%s");
+    }
 #undef SV_ATT
-  SV_CHECK_LAUNCH("slot_attn_fp32");
+    SV_CHECK_LAUNCH("slot_attn_fp32");
+  }
   const long nz = (long)T * N * C, na = (long)T * N;
   reduce_parts_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(w.Zpart, w.Z, nz, chunks);
   SV_CHECK_LAUNCH("reduce(Z)");
@@ -453,17 +458,18 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
     for (int t = 0; t < T; ++t)
       SV_TRY(level_fuse_frame(l > 0 ? fused_out[t * L + l - 1] : nullptr, feats[t * L + l], pr.conv_w, pr.conv_b, pr.W0,
                               fused_out[t * L + l], h, wd, w.ybuf + (long)t * C * (P / 4 + 1), s));
+    const bool use_tc = d->kernel_path == 0 && tc_supported(d, l);
+    const bool all_tc = use_tc && N <= attn::NROW;          // no fp32 kernel touches pos at this level
     const float* pl = nullptr;
     long pls = 0;
     if (d->pos_mode == 1) { pl = pos[l]; pls = pstride[l]; }
-    else if (d->pos_mode == 2) {
+    else if (d->pos_mode == 2 && !all_tc) {
       sine_pos_kernel<<<(unsigned)(((long)C * P + 255) / 256), 256, 0, s>>>(w.pos[l], h, wd);
       SV_CHECK_LAUNCH("sine_pos");
       pl = w.pos[l]; pls = 0;
     }
-    const bool use_tc = d->kernel_path == 0 && tc_supported(d, l);
     if (use_tc && d->heads_per_level[l] > 0)
-      SV_TRY(tc_split_level(fused_out[l], fstride[l], pl, pls, false, w.tc, T, h, wd, s));
+      SV_TRY(tc_split_level(fused_out[l], fstride[l], pl, pls, d->pos_mode == 2 && all_tc, w.tc, T, h, wd, s));
     for (int j = 0; j < d->heads_per_level[l]; ++j, ++stage) {
       const bool temporal = (d->temporal_mask >> stage) & 1;
       SV_TRY(run_stage(d, stages[stage], pr.st[stage], w, fused_out[l], fstride[l], pl, pls, h, wd, temporal, use_tc,

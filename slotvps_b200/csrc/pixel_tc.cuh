@@ -1,31 +1,33 @@
 // tcgen05 / TMEM / TMA implementation of the pixel-side retriever contraction (kernel_path = 0).
 //
 // Precision: the <=1e-3 per-stage tolerance rules out single-pass bf16/tf32 operands,
-// so every fp32 operand is split into bf16 hi + lo planes and each product is evaluated as
+// so every fp32 operand is split into fp16 hi + lo planes and each product is evaluated as
 // hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (error ~2^-16, measured 1.7e-5 per stage).
 //
 // Data flow per level:
-//   split_planes_kernel : x fp32 [T][256][P] (+pos) -> bf16 planes  xh, xl, (x+pos)h, (x+pos)l  [T*P][256]
+//   split_planes_kernel : x fp32 [T][256][P] (+pos) -> fp16 planes  xh, xl, (x+pos)h, (x+pos)l  [T*P][256]
 //   stats_tc_kernel     : per 128-pixel tile, D_k = (x+pos) . Wk_c^T and D_v = x . Wv_c^T on the tensor
 //                         pipe (TMA -> smem ring -> tcgen05.mma -> TMEM), epilogue reduces each pixel's
 //                         256 outputs to the LayerNorm scale rs = rsqrt(mean((D+b)^2)+eps); D never
 //                         leaves the SM.
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace slotvps {
 
 struct TcStageOperands {
-  __nv_bfloat16* wplanes = nullptr;     // [4][256][256]: Wk_c hi, Wk_c lo, Wv_c hi, Wv_c lo (row-major [out][in])
+  __half* wplanes = nullptr;     // [4][256][256]: Wk_c hi, Wk_c lo, Wv_c hi, Wv_c lo (row-major [out][in])
 };
 struct TcWorkspace {
-  __nv_bfloat16* planes = nullptr;      // [4][T*Pmax][256]: x hi, x lo, (x+pos) hi, (x+pos) lo
+  __half* planes = nullptr;      // [4][T*Pmax][256]: x hi, x lo, (x+pos) hi, (x+pos) lo
   float *ytab = nullptr, *xtab = nullptr;  // separable sine tables [128][hmax], [128][wmax]
+  __half* gplanes = nullptr;     // [T][2][112][256] folded query operand G, hi/lo
   long plane_rows = 0;                  // rows allocated per plane (T*Pmax)
 };
 
-inline void tc_stage_layout(Arena& a, TcStageOperands* o) { o->wplanes = a.take<__nv_bfloat16>((size_t)4 * C * C); }
+inline void tc_stage_layout(Arena& a, TcStageOperands* o) { o->wplanes = a.take<__half>((size_t)4 * C * C); }
 inline void tc_workspace_layout(Arena& a, const slotvps_head_desc* d, TcWorkspace* w) {
   long Pmax = 0;
   int hmax = 0, wmax = 0;
@@ -35,24 +37,29 @@ inline void tc_workspace_layout(Arena& a, const slotvps_head_desc* d, TcWorkspac
   }
   w->plane_rows = (long)d->n_frames * Pmax;
   if (d->kernel_path == 0) {
-    w->planes = a.take<__nv_bfloat16>((size_t)4 * w->plane_rows * C);
+    w->planes = a.take<__half>((size_t)4 * w->plane_rows * C);
     w->ytab = a.take<float>((size_t)128 * hmax);
     w->xtab = a.take<float>((size_t)128 * wmax);
+    w->gplanes = a.take<__half>((size_t)d->n_frames * 2 * 112 * C);
   }
 }
 // shapes the tensor-core kernels serve; everything else runs on the fp32 path
 inline bool tc_supported(const slotvps_head_desc* d, int level) { return d->h[level] * d->w[level] >= 128; }
 
 // ---- operand preparation -----------------------------------------------------------------------------
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+// fp32 -> fp16 hi + lo (22 significant bits).  tcgen05 kind::f16 requires A and B to share one 16-bit
+// format (mixing bf16 x fp16 raises an illegal-instruction fault on B200), and the softmax weights P
+// need fp16's 11-bit mantissa, so every operand plane is fp16; values are clamped to the fp16 range.
+__device__ __forceinline__ void split_bf16(float v, __half& hi, __half& lo) {
+  v = fminf(fmaxf(v, -65504.f), 65504.f);
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
 }
 __global__ void __launch_bounds__(256) weight_planes_kernel(const float* __restrict__ Wk, const float* __restrict__ Wv,
-                                                            __nv_bfloat16* __restrict__ out) {
+                                                            __half* __restrict__ out) {
   int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= C * C) return;
-  __nv_bfloat16 h, l;
+  __half h, l;
   split_bf16(Wk[i], h, l); out[i] = h; out[C * C + i] = l;
   split_bf16(Wv[i], h, l); out[2 * C * C + i] = h; out[3 * C * C + i] = l;
 }
@@ -72,7 +79,7 @@ __global__ void __launch_bounds__(256) pos_tab_kernel(float* __restrict__ ytab, 
 constexpr int SPLIT_SMEM = 2 * 256 * 33 * (int)sizeof(float);
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long x_bs, const float* __restrict__ pos, long pos_bs,
                                                            const float* __restrict__ ytab, const float* __restrict__ xtab,
-                                                           __nv_bfloat16* __restrict__ planes, long plane_rows, int P, int h, int w) {
+                                                           __half* __restrict__ planes, long plane_rows, int P, int h, int w) {
   extern __shared__ float sp_smem[];
   float* xs = sp_smem;             // [256][33]
   float* ps = sp_smem + 256 * 33;  // [256][33]  x + pos
@@ -94,20 +101,20 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
     ps[c * 33 + lane] = v + q;
   }
   __syncthreads();
-  __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(planes);
+  __half2* out = reinterpret_cast<__half2*>(planes);
   const long plane_stride2 = plane_rows * (C / 2);
 #pragma unroll 4
   for (int i = 0; i < 16; ++i) {
     int idx = tid + i * 256, pp = idx >> 7, cp = idx & 127;
     if (p0 + pp >= P) continue;
     long o = ((long)t * P + p0 + pp) * (C / 2) + cp;
-    __nv_bfloat16 h0, l0, h1, l1;
+    __half h0, l0, h1, l1;
     split_bf16(xs[(2 * cp) * 33 + pp], h0, l0); split_bf16(xs[(2 * cp + 1) * 33 + pp], h1, l1);
-    out[o] = __halves2bfloat162(h0, h1);
-    out[plane_stride2 + o] = __halves2bfloat162(l0, l1);
+    out[o] = __halves2half2(h0, h1);
+    out[plane_stride2 + o] = __halves2half2(l0, l1);
     split_bf16(ps[(2 * cp) * 33 + pp], h0, l0); split_bf16(ps[(2 * cp + 1) * 33 + pp], h1, l1);
-    out[2 * plane_stride2 + o] = __halves2bfloat162(h0, h1);
-    out[3 * plane_stride2 + o] = __halves2bfloat162(l0, l1);
+    out[2 * plane_stride2 + o] = __halves2half2(h0, h1);
+    out[3 * plane_stride2 + o] = __halves2half2(l0, l1);
   }
 }
 
@@ -115,17 +122,17 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 namespace stats {
 constexpr int TILE_M = 128;                    // pixels per tile (TMEM lanes)
 constexpr int KSUB = 64;                       // channels per k-subtile = one 128-byte swizzle row
-constexpr int A_BYTES = TILE_M * 128;          // 16 KB  [128 px][64 ch] bf16
-constexpr int B_BYTES = C * 128;               // 32 KB  [256 out][64 ch] bf16
+constexpr int A_BYTES = TILE_M * 128;          // 16 KB  [128 px][64 ch] fp16
+constexpr int B_BYTES = C * 128;               // 32 KB  [256 out][64 ch] fp16
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A hi, A lo, B hi, B lo = 96 KB
 constexpr int NSTAGE = 2;
 constexpr int AUX_BYTES = 4096;                // barriers, tmem pointer, biases
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + AUX_BYTES + 1024;   // + alignment slack
 constexpr int THREADS = 192;                   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
-constexpr uint32_t IDESC = tc::make_idesc_bf16(128, 256, 0, 0);
+constexpr uint32_t IDESC = tc::make_idesc_f16(128, 256, 0, 0);
 }  // namespace stats
 
-// planes: tensor map over [4*plane_rows][256] bf16; wplanes: tensor map over [4*256][256] bf16
+// planes: tensor map over [4*plane_rows][256] fp16; wplanes: tensor map over [4*256][256] fp16
 __global__ void __launch_bounds__(stats::THREADS, 1)
 stats_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                 const float* __restrict__ bk_c, const float* __restrict__ bv_c, float* __restrict__ rs_k,
@@ -255,6 +262,9 @@ inline int tc_split_level(const float* x, long x_bs, const float* pos, long pos_
                           cudaStream_t s) {
   const int P = h * w;
   if ((long)T * P > ws.plane_rows || !ws.planes) return fail(SLOTVPS_EWORKSPACE, "tensor-core plane workspace too small%s%s");
+  // planes of a level are packed with stride T*P rows, so a tile's rows past the end of a frame/plane are
+  // rows of the next frame/plane (finite) or beyond the tensor (TMA zero fill) -- never stale memory
+  const long rows = (long)T * P;
   static bool attr_done = false;
   if (!attr_done) {
     SV_CHECK_CUDA(cudaFuncSetAttribute(split_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_SMEM));
@@ -265,7 +275,7 @@ inline int tc_split_level(const float* x, long x_bs, const float* pos, long pos_
     SV_CHECK_LAUNCH("pos_tab");
   }
   split_planes_kernel<<<dim3(ceil_div(P, 32), T), 256, SPLIT_SMEM, s>>>(x, x_bs, pos, pos_bs, (sine && !pos) ? ws.ytab : nullptr,
-                                                                         (sine && !pos) ? ws.xtab : nullptr, ws.planes, ws.plane_rows, P, h, w);
+                                                                         (sine && !pos) ? ws.xtab : nullptr, ws.planes, rows, P, h, w);
   SV_CHECK_LAUNCH("split_planes");
   return SLOTVPS_OK;
 }
@@ -274,8 +284,9 @@ inline int tc_split_level(const float* x, long x_bs, const float* pos, long pos_
 inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const float* bk_c, const float* bv_c, float* rs_k, float* rs_v,
                     int T, int P, cudaStream_t s) {
   CUtensorMap mx, mw;
-  SV_TRY(tc::make_tmap_bf16_sw128(&mx, ws.planes, (uint64_t)4 * ws.plane_rows, C, stats::TILE_M));
-  SV_TRY(tc::make_tmap_bf16_sw128(&mw, ops.wplanes, (uint64_t)4 * C, C, C));
+  const long rows = (long)T * P;
+  SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)4 * rows, C, stats::TILE_M));
+  SV_TRY(tc::make_tmap_h16_sw128(&mw, ops.wplanes, (uint64_t)4 * C, C, C));
   static bool attr_done = false;
   if (!attr_done) {
     SV_CHECK_CUDA(cudaFuncSetAttribute(stats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stats::SMEM_BYTES));
@@ -284,8 +295,331 @@ inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const flo
   const int tiles_per_frame = ceil_div(P, stats::TILE_M);
   const int n_tiles = T * tiles_per_frame;
   const int grid = n_tiles < 148 ? n_tiles : 148;
-  stats_tc_kernel<<<grid, stats::THREADS, stats::SMEM_BYTES, s>>>(mx, mw, bk_c, bv_c, rs_k, rs_v, P, T, (int)ws.plane_rows, tiles_per_frame);
+  stats_tc_kernel<<<grid, stats::THREADS, stats::SMEM_BYTES, s>>>(mx, mw, bk_c, bv_c, rs_k, rs_v, P, T, (int)rows, tiles_per_frame);
   SV_CHECK_LAUNCH("stats_tc");
+  return SLOTVPS_OK;
+}
+
+
+// =====================================================================================================
+// Fused slot-axis-softmax attention on the tensor pipe (replaces slot_attn_fp32_kernel):
+//   S[p,n]  = (x+pos)_p . G_n                      tcgen05, M = 128 pixels (TMEM lanes), N = 112 slots
+//   A[p,:]  = softmax_n(rs_k[p] (S + g0) + g1)     thread-local: one pixel per thread, slots in registers
+//   P[n,p]  = A[p,n] * rs_v[p]            (fp16)   written to smem as the K-major B operand of the next MMA
+//   Z^T[c,n] += sum_p x[p,c] P[n,p]                tcgen05, M = 128 channels x 2, N = 112, K = 128 pixels
+//   aux[n,:] += sum_p P[n,p] (1, sigma_v[p])       tcgen05, N = 16  -> a1[n], a0[n]
+// The N x P attention matrix never leaves the SM.  x / x+pos are the fp16 hi/lo planes of the level
+// (3-product split for S; 2-product x_hi + x_lo against the fp16 P for Z, whose ~2^-12 rounding is averaged
+// over the pixel sum); accumulation is fp32 in TMEM, Z^T stays resident in TMEM across the CTA's tiles.
+namespace attn {
+constexpr int TILE_M = 128;
+constexpr int NROW = 104;                         // slot rows held in shared memory (N <= 104)
+constexpr int NPAD = 112;                         // UMMA N (multiple of 16 for M = 128); rows 104..111 over-read finite data
+constexpr int SLOT_BYTES = 16384;                 // ring slot: [128 px][64 ch] fp16, 128B swizzle
+constexpr int NSLOT = 4;
+constexpr int G_SUB = NROW * 128;                 // 13312: [104 slots][64 ch] fp16
+constexpr int G_BYTES = 2 * 4 * G_SUB;            // hi, lo planes x 4 k-subtiles = 106496
+constexpr int P_SUB = NROW * 128;                 // [104 slots][64 px] fp16
+constexpr int P_PLANE = 2 * P_SUB;                // two 64-pixel halves
+constexpr int P_BYTES = 2 * P_PLANE;              // hi, lo = 53248
+constexpr int AUX_SUB = 16 * 128;                 // [16 pseudo-channels][64 px] fp16
+constexpr int AUXT_BYTES = 2 * AUX_SUB;
+constexpr int MISC_BYTES = 2048;
+constexpr int OFF_G = NSLOT * SLOT_BYTES;
+constexpr int OFF_P = OFF_G + G_BYTES;
+constexpr int OFF_AUX = OFF_P + P_BYTES;
+constexpr int OFF_MISC = OFF_AUX + AUXT_BYTES;
+constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;      // == 232448, the sm_100 per-block maximum
+constexpr int THREADS = 192;
+constexpr uint32_t IDESC_S = tc::make_idesc_f16(128, NPAD, 0, 0);
+// Z^T: A = x tile, MN-major fp16; B = P, K-major fp16
+constexpr uint32_t IDESC_Z = tc::make_idesc_f16(128, NPAD, 1, 0);
+// aux: A = P (K-major), B = aux tile (K-major), N = 16
+constexpr uint32_t IDESC_AUX = tc::make_idesc_f16(128, 16, 0, 0);
+constexpr int TM_S = 0;                            // two S buffers of 128 columns
+constexpr int TM_Z = 256;                          // Z^T: 2 x 112 columns
+constexpr int TM_AUX = 480;                        // 16 columns
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(OFF_G % 1024 == 0 && G_SUB % 1024 == 0 && OFF_P % 1024 == 0 && P_SUB % 1024 == 0 && OFF_AUX % 1024 == 0, "swizzle atoms");
+}  // namespace attn
+
+__global__ void __launch_bounds__(256) g_planes_kernel(const float* __restrict__ G, __half* __restrict__ out, int N, int T) {
+  // out [T][2][NROW][256]; rows >= N are zero
+  long i = (long)blockIdx.x * 256 + threadIdx.x;
+  long total = (long)T * attn::NROW * C;
+  if (i >= total) return;
+  int c = (int)(i % C), n = (int)((i / C) % attn::NROW), t = (int)(i / ((long)C * attn::NROW));
+  __half h = __float2half_rn(0.f), l = h;
+  if (n < N) split_bf16(G[((long)t * N + n) * C + c], h, l);
+  long o = ((long)t * 2 * attn::NROW + n) * C + c;
+  out[o] = h;
+  out[o + (long)attn::NROW * C] = l;
+}
+
+__global__ void __launch_bounds__(attn::THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g,
+               const float* __restrict__ g0, const float* __restrict__ g1, const float* __restrict__ rs_k,
+               const float* __restrict__ rs_v, float* __restrict__ Zpart, float* __restrict__ a0part,
+               float* __restrict__ a1part, int N, int P, int T, int plane_rows, int tiles_per_frame, int dbg) {
+  using namespace attn;
+  extern __shared__ uint8_t raw_smem[];
+  const uint32_t raw = tc::smem_u32(raw_smem);
+  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
+  uint8_t* misc = smem + OFF_MISC;
+  uint64_t* full = reinterpret_cast<uint64_t*>(misc);      // [NSLOT]
+  uint64_t* empty = full + NSLOT;                          // [NSLOT]
+  uint64_t* sfull = empty + NSLOT;                         // [2]
+  uint64_t* sempty = sfull + 2;                            // [2]
+  uint64_t* pfull = sempty + 2;                            // [1]
+  uint64_t* pempty = pfull + 1;                            // [1]
+  uint64_t* gfull = pempty + 1;                            // [1]
+  uint64_t* zfull = gfull + 1;                             // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(zfull + 1);
+  float2* gc = reinterpret_cast<float2*>(misc + 256);      // [NPAD] (g0, g1)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x, chunks = gridDim.x, t = blockIdx.y;
+  const int n_my = (tiles_per_frame - chunk + chunks - 1) / chunks;       // tiles chunk, chunk+chunks, ...
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmap_x);
+    tc::tma_prefetch_desc(&tmap_g);
+    for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sfull[i], 1); tc::mbar_init(&sempty[i], 128); }
+    tc::mbar_init(pfull, 128); tc::mbar_init(pempty, 1); tc::mbar_init(gfull, 1); tc::mbar_init(zfull, 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < NPAD; i += THREADS)
+    gc[i] = i < N ? make_float2(g0[(long)t * N + i], g1[(long)t * N + i]) : make_float2(0.f, 0.f);
+  // aux tile: row 0 = 1.0 (-> a1), row 1 = sigma_v per pixel (rewritten every tile), rows 2..15 = 0.
+  // Row r lives at byte r*128 of each 64-pixel half; 16-byte chunk index is XOR-swizzled with (r & 7).
+  for (int i = threadIdx.x; i < AUXT_BYTES / 2; i += THREADS) {
+    int half = i / (AUX_SUB / 2), e = i % (AUX_SUB / 2), r = e / 64;
+    reinterpret_cast<__half*>(smem + OFF_AUX + half * AUX_SUB)[e] = __float2half(r == 0 ? 1.f : 0.f);   // constant rows: swizzle-invariant
+  }
+  for (int i = threadIdx.x; i < P_BYTES / 4; i += THREADS) reinterpret_cast<uint32_t*>(smem + OFF_P)[i] = 0u;
+  tc::fence_proxy_async();
+  if (warp == 1) { tc::tmem_alloc(tmem_ptr, 512); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tc::mbar_expect_tx(gfull, G_BYTES);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int ks = 0; ks < 4; ++ks)
+          tc::tma_load_2d(smem + OFF_G + (pl * 4 + ks) * G_SUB, &tmap_g, ks * 64, (t * 2 + pl) * NROW, gfull);
+      uint32_t it = 0;
+      auto load_slot = [&](int plane, int c0, int row) {
+        const int s = it % NSLOT;
+        tc::mbar_wait(&empty[s], ((it / NSLOT) & 1) ^ 1);
+        tc::mbar_expect_tx(&full[s], SLOT_BYTES);
+        tc::tma_load_2d(smem + s * SLOT_BYTES, &tmap_x, c0, plane * plane_rows + row, &full[s]);
+        ++it;
+      };
+      auto job_s = [&](int i) {
+        const int row = t * P + (chunk + i * chunks) * TILE_M;
+        for (int ks = 0; ks < 4; ++ks) { load_slot(2, ks * 64, row); load_slot(3, ks * 64, row); }      // (x+pos) hi, lo
+      };
+      auto job_z = [&](int i) {
+        const int row = t * P + (chunk + i * chunks) * TILE_M;
+        for (int mt = 0; mt < 2; ++mt)
+          for (int pl = 0; pl < 2; ++pl) { load_slot(pl, (2 * mt) * 64, row); load_slot(pl, (2 * mt + 1) * 64, row); }   // x hi / lo, 128 channels
+      };
+      job_s(0);
+      for (int i = 0; i < n_my; ++i) { if (i + 1 < n_my) job_s(i + 1); job_z(i); }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      tc::mbar_wait(gfull, 0);
+      tc::tc_fence_after();
+      const uint32_t g_base = tc::smem_u32(smem + OFF_G), p_base = tc::smem_u32(smem + OFF_P), x_base = tc::smem_u32(smem + OFF_AUX);
+      uint32_t it = 0;
+      auto issue_s = [&](int i) {
+        const int b = i & 1, u = i >> 1;
+        tc::mbar_wait(&sempty[b], (u & 1) ^ 1);            // softmax of tile i-2 has drained this S buffer
+        tc::tc_fence_after();
+        const uint32_t d = tmem_base + TM_S + b * 128;
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t dgh = tc::make_smem_desc_sw128(g_base + ks * G_SUB, 16, 1024);
+          const uint64_t dgl = tc::make_smem_desc_sw128(g_base + (4 + ks) * G_SUB, 16, 1024);
+          {   // (x+pos) hi against G hi and G lo
+            const int s = it % NSLOT;
+            tc::mbar_wait(&full[s], (it / NSLOT) & 1);
+            tc::tc_fence_after();
+            const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc::umma_bf16(d, da + 2 * k, dgh + 2 * k, IDESC_S, (ks | k) != 0);
+              tc::umma_bf16(d, da + 2 * k, dgl + 2 * k, IDESC_S, 1);
+            }
+            tc::umma_commit(&empty[s]);
+            ++it;
+          }
+          {   // (x+pos) lo against G hi
+            const int s = it % NSLOT;
+            tc::mbar_wait(&full[s], (it / NSLOT) & 1);
+            tc::tc_fence_after();
+            const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_bf16(d, da + 2 * k, dgh + 2 * k, IDESC_S, 1);
+            tc::umma_commit(&empty[s]);
+            ++it;
+          }
+        }
+        tc::umma_commit(&sfull[b]);
+      };
+      auto issue_z = [&](int i) {
+        tc::mbar_wait(pfull, i & 1);                        // P and the aux tile of tile i are in shared memory
+        tc::tc_fence_after();
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint32_t d = tmem_base + TM_Z + mt * NPAD;
+          for (int pl = 0; pl < 2; ++pl) {                  // pl = 0: x hi against P hi and P lo; pl = 1: x lo against P hi
+            const int s = it % NSLOT;                       // even by construction: slots (s, s+1) hold channels [128 mt, 128 mt + 128)
+            tc::mbar_wait(&full[s], (it / NSLOT) & 1);
+            tc::mbar_wait(&full[s + 1], ((it + 1) / NSLOT) & 1);
+            tc::tc_fence_after();
+            // A: x tile as MN-major operand: 64-channel groups SLOT_BYTES apart, 8-pixel groups 1024 B apart
+            const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), SLOT_BYTES, 1024);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {                   // 16 pixels per MMA: A advances 16 rows (2048 B), B 32 B inside its 64-pixel half
+              const uint32_t poff = (k >> 2) * P_SUB + (k & 3) * 32;
+              tc::umma_bf16(d, da + (uint64_t)(k * 128), tc::make_smem_desc_sw128(p_base + poff, 16, 1024), IDESC_Z, (i | pl | k) != 0);
+              if (pl == 0) tc::umma_bf16(d, da + (uint64_t)(k * 128), tc::make_smem_desc_sw128(p_base + P_PLANE + poff, 16, 1024), IDESC_Z, 1);
+            }
+            tc::umma_commit(&empty[s]);
+            tc::umma_commit(&empty[s + 1]);
+            it += 2;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                       // aux[n, :] += (P hi + P lo)[n, px] . (1, sigma_v[px], 0...)
+          const uint32_t poff = (k >> 2) * P_SUB + (k & 3) * 32;
+          const uint64_t dx = tc::make_smem_desc_sw128(x_base + (k >> 2) * AUX_SUB + (k & 3) * 32, 16, 1024);
+          tc::umma_bf16(tmem_base + TM_AUX, tc::make_smem_desc_sw128(p_base + poff, 16, 1024), dx, IDESC_AUX, (i | k) != 0);
+          tc::umma_bf16(tmem_base + TM_AUX, tc::make_smem_desc_sw128(p_base + P_PLANE + poff, 16, 1024), dx, IDESC_AUX, 1);
+        }
+        tc::umma_commit(pempty);                            // P may be overwritten once these retire
+      };
+      issue_s(0);
+      for (int i = 0; i < n_my; ++i) { if (i + 1 < n_my) issue_s(i + 1); issue_z(i); }
+      tc::umma_commit(zfull);
+    }
+  } else {
+    // ===================== softmax warps (one pixel per thread) + final epilogue =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                            // pixel row of the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint8_t* p_half = smem + OFF_P + (r >> 6) * P_SUB;      // this pixel's 64-pixel half of P
+    const int pc = (r & 63) >> 3, pe = (r & 7) * 2;         // 16-byte chunk and byte offset inside it
+    __half* aux_row1 = reinterpret_cast<__half*>(smem + OFF_AUX + (r >> 6) * AUX_SUB + 128 + ((pc ^ 1) * 16) + pe);
+    for (int i = 0; i < n_my; ++i) {
+      const int p = (chunk + i * chunks) * TILE_M + r;
+      const bool pv = p < P;
+      const float rk = pv ? __ldg(rs_k + (long)t * P + p) : 0.f;
+      const float rv = pv ? __ldg(rs_v + (long)t * P + p) : 0.f;
+      const int b = i & 1;
+      tc::mbar_wait(&sfull[b], (i >> 1) & 1);
+      tc::tc_fence_after();
+      float sv[NPAD];
+      const uint32_t ta = tmem_base + lane_addr + TM_S + b * 128;
+      tc::tmem_ld32(ta, sv);
+      tc::tmem_ld32(ta + 32, sv + 32);
+      tc::tmem_ld32(ta + 64, sv + 64);
+      {
+        float tail[32];
+        tc::tmem_ld32(ta + 96, tail);                       // columns 96..127 (only 96..111 are meaningful)
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) sv[96 + c] = tail[c];
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&sempty[b]);                          // S buffer free for tile i+2
+      float mx = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < NPAD; ++n) {
+        const float2 c = gc[n];
+        const float s = n < N ? fmaf(sv[n] + c.x, rk, c.y) : -INFINITY;
+        sv[n] = s;
+        mx = fmaxf(mx, s);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int n = 0; n < NPAD; ++n) { const float e = __expf(sv[n] - mx); sv[n] = e; sum += e; }
+      const float sc = pv ? rv / sum : 0.f;                 // A' = A * rs_v
+      tc::mbar_wait(pempty, (i & 1) ^ 1);                   // Z(i-1) has finished reading P
+#pragma unroll
+      for (int n = 0; n < NROW; ++n) {
+        const float a = pv ? sv[n] * sc : 0.f;
+        const __half hi = __float2half_rn(a);
+        const int off = n * 128 + ((pc ^ (n & 7)) * 16) + pe;
+        *reinterpret_cast<__half*>(p_half + off) = hi;
+        *reinterpret_cast<__half*>(p_half + P_PLANE + off) = __float2half_rn(a - __half2float(hi));
+      }
+      *aux_row1 = __float2half_rn(pv ? 1.f / rv : 0.f);     // sigma_v
+      tc::fence_proxy_async();
+      tc::mbar_arrive(pfull);
+    }
+    // ---- final epilogue: Z^T (lanes = channels) and aux (lanes = slots) -> per-CTA partials ----
+    tc::mbar_wait(zfull, 0);
+    tc::tc_fence_after();
+    float* Zp = Zpart + ((long)chunk * T + t) * N * C;
+    for (int mt = 0; mt < 2; ++mt) {
+      const int ch = mt * 128 + r;
+      for (int j = 0; j < 4; ++j) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + lane_addr + TM_Z + mt * NPAD + j * 32, v);   // last chunk over-reads 16 columns (ignored)
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { const int n = j * 32 + c; if (n < N) Zp[(long)n * C + ch] = v[c]; }
+      }
+    }
+    {
+      float v[32];
+      tc::tmem_ld32(tmem_base + lane_addr + TM_AUX, v);     // reads 16 columns past aux (unused)
+      tc::tmem_ld_wait();
+      if (r < N) { a1part[((long)chunk * T + t) * N + r] = v[0]; a0part[((long)chunk * T + t) * N + r] = v[1]; }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+namespace attn {
+inline int chunks_for(int P, int T) {
+  int tiles = ceil_div(P, TILE_M);
+  int per = 148 / (T > 0 ? T : 1);
+  if (per < 1) per = 1;
+  return tiles < per ? tiles : per;
+}
+}  // namespace attn
+
+// Zpart/a0part/a1part [chunks][T][N]..., returns the chunk count through *chunks_out
+inline int tc_attention(const TcWorkspace& ws, __half* gplanes, const float* G, const float* g0, const float* g1,
+                        const float* rs_k, const float* rs_v, float* Zpart, float* a0part, float* a1part, int T, int N, int P,
+                        int* chunks_out, cudaStream_t s) {
+  g_planes_kernel<<<(unsigned)(((long)T * attn::NROW * C + 255) / 256), 256, 0, s>>>(G, gplanes, N, T);
+  SV_CHECK_LAUNCH("g_planes");
+  CUtensorMap mx, mg;
+  const long rows = (long)T * P;
+  SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)4 * rows, C, attn::TILE_M));
+  SV_TRY(tc::make_tmap_h16_sw128(&mg, gplanes, (uint64_t)T * 2 * attn::NROW, C, attn::NROW));
+  static bool attr_done = false;
+  if (!attr_done) {
+    SV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles_per_frame = ceil_div(P, attn::TILE_M);
+  const int chunks = attn::chunks_for(P, T);
+  attn_tc_kernel<<<dim3(chunks, T), attn::THREADS, attn::SMEM_BYTES, s>>>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, N, P, T,
+                                                                          (int)rows, tiles_per_frame, getenv("SLOTVPS_TC_DEBUG") ? atoi(getenv("SLOTVPS_TC_DEBUG")) : 0);
+  SV_CHECK_LAUNCH("attn_tc");
+  *chunks_out = chunks;
   return SLOTVPS_OK;
 }
 

@@ -3,7 +3,7 @@
 // Descriptor bit layouts follow the PTX ISA "tcgen05 matrix / instruction descriptor" tables.
 #pragma once
 #include <cuda.h>          // CUtensorMap (types only; the encode entry point is fetched at run time)
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace slotvps {
@@ -73,11 +73,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16 with BF16 operands and FP32 accumulation.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+// Instruction descriptor for kind::f16 with FP16 operands and FP32 accumulation.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                       // D format  : F32
-         | (1u << 7)                     // A format  : BF16
-         | (1u << 10)                    // B format  : BF16
+         | (0u << 7)                     // A format  : F16 (1 = BF16; A and B must match)
+         | (0u << 10)                    // B format  : F16
          | ((uint32_t)a_mn_major << 15)  // A major   : 0 = K, 1 = MN
          | ((uint32_t)b_mn_major << 16)  // B major
          | ((uint32_t)(N >> 3) << 17)    // N / 8
@@ -142,15 +142,15 @@ inline EncodeTiledFn encode_fn() {
   }
   return fn;
 }
-// bf16 matrix [rows][cols] (row-major, cols contiguous), box = [box_rows][64 cols], 128B swizzle
-inline int make_tmap_bf16_sw128(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 16-bit matrix [rows][cols] (row-major, cols contiguous), box = [box_rows][64 cols], 128B swizzle
+inline int make_tmap_h16_sw128(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(SLOTVPS_ECUDA, "cuTensorMapEncodeTiled entry point unavailable%s%s");
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * sizeof(__nv_bfloat16)};
+  cuuint64_t strides[1] = {cols * 2};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SLOTVPS_ECUDA, "cuTensorMapEncodeTiled failed%s%s");
   return SLOTVPS_OK;
