@@ -10,6 +10,7 @@
 #include "pixel_fp32.cuh"
 #include "fusion.cuh"
 #include "pixel_tc.cuh"
+#include "fuse_tc.cuh"
 
 namespace slotvps {
 thread_local char g_err[512] = "";
@@ -53,6 +54,7 @@ static int validate(const slotvps_head_desc* d) {
 // ---- prepared (folded) weights --------------------------------------------------------------------
 struct PreparedStage {
   float *Wk_c, *bk_c, *Wv_c, *bv_c;     // output-centred key/value projections
+  float *Wk_cT;                         // Wk_c transposed [in][out] (G = qt . Wk_c as a K-contiguous linear)
   float *tq_qkv_w, *tq_qkv_b, *tq_ln_w, *tq_ln_b;   // Video Retriever q|k|v stacked [768,256],[768],[3,256]
   float *tw_w, *tw_ln_w, *tw_ln_b;      // first tower layers cls|reg stacked [512,256],[2,256]
   TcStageOperands tc;                   // tensor-core operand planes (pixel_tc.cuh)
@@ -60,6 +62,7 @@ struct PreparedStage {
 struct Prepared {
   float* W0;                            // level-0 folded conv weight [256,128]
   float *conv_w, *conv_b;               // copies of conv_trans.conv.{weight [256,384], bias [256]}
+  FuseTcWeights ftc;                    // fp16 hi/lo planes of the folded conv_trans weights
   PreparedStage st[SLOTVPS_MAX_STAGES];
 };
 
@@ -68,11 +71,13 @@ static size_t prepared_layout(const slotvps_head_desc* d, void* base, Prepared* 
   Prepared p;
   p.W0 = a.take<float>((size_t)C * CIN);
   p.conv_w = a.take<float>((size_t)C * 3 * CIN); p.conv_b = a.take<float>(C);
+  p.ftc.w0 = a.take<__half>((size_t)2 * C * CIN); p.ftc.wa = a.take<__half>((size_t)2 * C * C); p.ftc.wb = a.take<__half>((size_t)2 * C * CIN);
   const int S = n_stages_of(d);
   for (int s = 0; s < S; ++s) {
     PreparedStage& ps = p.st[s];
     ps.Wk_c = a.take<float>((size_t)C * C); ps.bk_c = a.take<float>(C);
     ps.Wv_c = a.take<float>((size_t)C * C); ps.bv_c = a.take<float>(C);
+    ps.Wk_cT = a.take<float>((size_t)C * C);
     ps.tq_qkv_w = a.take<float>((size_t)3 * C * C); ps.tq_qkv_b = a.take<float>(3 * C);
     ps.tq_ln_w = a.take<float>(3 * C); ps.tq_ln_b = a.take<float>(3 * C);
     ps.tw_w = a.take<float>((size_t)2 * C * C); ps.tw_ln_w = a.take<float>(2 * C); ps.tw_ln_b = a.take<float>(2 * C);
@@ -96,6 +101,10 @@ __global__ void __launch_bounds__(256) center_rows_kernel(const float* __restric
   double mb = 0.0;
   for (int o = 0; o < C; ++o) mb += sb[o];
   bc[c] = (float)(sb[c] - mb / C);
+}
+__global__ void __launch_bounds__(256) transpose256_kernel(const float* __restrict__ in, float* __restrict__ out) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < C * C) out[(i % C) * C + i / C] = in[i];
 }
 __global__ void __launch_bounds__(256) fold_w0_kernel(const float* __restrict__ W, float* __restrict__ W0) {
   int i = blockIdx.x * 256 + threadIdx.x;            // [256][128]
@@ -121,7 +130,9 @@ struct HeadWs {
   float *tqkv, *L, *av, *ty, *thdn, *tw, *c2, *e1;
   float *pos[SLOTVPS_MAX_LEVELS];       // generated sine embeddings (pos_mode 2)
   float *ybuf;                          // coarse conv_trans partial [T][256][P/4]
+  float *splitk;                        // split-K partials of the long-K linears [4][R][256]
   TcWorkspace tc;
+  FuseTcWorkspace ftc;
   int chunks;
 };
 static int attn_chunks(int P, int T) {
@@ -153,7 +164,12 @@ static size_t head_ws_layout(const slotvps_head_desc* d, void* base, size_t cap,
   for (int l = 0; l < SLOTVPS_MAX_LEVELS; ++l)
     w.pos[l] = (d->pos_mode == 2 && l < d->n_levels) ? a.take<float>((size_t)C * d->h[l] * d->w[l]) : nullptr;
   w.ybuf = a.take<float>((size_t)T * C * (Pmax / 4 + 1));
+  w.splitk = a.take<float>((size_t)4 * R * C);
   tc_workspace_layout(a, d, &w.tc);
+  if (d->kernel_path == 0) {
+    w.ftc.in_planes = a.take<__half>((size_t)2 * T * Pmax * CIN);
+    w.ftc.y = a.take<float>((size_t)T * (Pmax / 4 + 1) * C);
+  }
   if (out) *out = w;
   return align_up(a.off);
 }
@@ -242,7 +258,7 @@ static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp,
                      float* emb_out, long emb_frame_stride, cudaStream_t s) {
   const int T = d->n_frames, N = d->n_slots, R = T * N, P = h * wd, F = d->dim_feedforward, TF = d->temporal_dim_feedforward;
   // (1) slot self-attention + norm1  (:346-358)
-  SV_TRY(linear(w.slots, sp.in_proj_w, sp.in_proj_b, w.qkv, R, C, 3 * C, 0, nullptr, s));
+  SV_TRY(linear_fast(w.slots, sp.in_proj_w, sp.in_proj_b, w.qkv, R, C, 3 * C, 0, nullptr, s));
   {
     size_t smem = (size_t)(2 * N * 33 + 8 * N) * sizeof(float);
     static size_t attr_smem = 0;
@@ -253,36 +269,29 @@ static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp,
     mha_core_kernel<<<dim3(d->nhead, T), 256, smem, s>>>(w.qkv, w.mo, N, d->nhead);
     SV_CHECK_LAUNCH("mha_core");
   }
-  SV_TRY(linear(w.mo, sp.out_proj_w, sp.out_proj_b, w.qraw, R, C, C, 0, w.slots, s));       // s + attn
+  SV_TRY(linear_fast(w.mo, sp.out_proj_w, sp.out_proj_b, w.qraw, R, C, C, 0, w.slots, s));       // s + attn
   SV_TRY(ln_rows(w.qraw, nullptr, sp.norm1_w, sp.norm1_b, 1, nullptr, w.p, R, 0, s));       // p
   // (2) query side of the Panoptic Retriever (:431) + folded key operands
-  SV_TRY(linear(w.p, sp.to_q_w, sp.to_q_b, w.qraw, R, C, C, 0, nullptr, s));
+  SV_TRY(linear_fast(w.p, sp.to_q_w, sp.to_q_b, w.qraw, R, C, C, 0, nullptr, s));
   q_post_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.qraw, sp.nq_w, sp.nq_b, sp.nk_w, sp.nk_b, ps.bk_c, w.qt, w.g0, w.g1, R);
   SV_CHECK_LAUNCH("q_post");
-  {
-    GemmArgs g;                                         // G = qt . Wk_c   ([R,256] x [256(o),256(c)])
-    g.A = w.qt; g.a_ms = C; g.a_ks = 1;
-    g.B = ps.Wk_c; g.b_ks = C; g.b_ns = 1;
-    g.Cm = w.G; g.c_ms = C; g.c_ns = 1;
-    g.M = R; g.N = C; g.K = C;
-    SV_TRY(sgemm(g, s));
-  }
+  SV_TRY(linear_fast(w.qt, ps.Wk_cT, nullptr, w.G, R, C, C, 0, nullptr, s));     // G = qt . Wk_c  (Wk_cT = Wk_c^T, [c][o])
   // (3) pixel side: Z, a0, a1
   SV_TRY(pixel_attention(x, x_bs, pos, pos_bs, ps, w, T, N, P, use_tc, s));
   // (4) value projection on the pixel-reduced slots, norm1/ReLU, residual, norm2 (:456-459, 374-376)
-  SV_TRY(linear(w.Z, ps.Wv_c, nullptr, w.Y, R, C, C, 0, nullptr, s));
+  SV_TRY(linear_fast(w.Z, ps.Wv_c, nullptr, w.Y, R, C, C, 0, nullptr, s));
   attn_post_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.Y, w.a0, w.a1, w.p, sp.nv_w, sp.nv_b, ps.bv_c, sp.no_w, sp.no_b,
                                                    sp.norm2_w, sp.norm2_b, nullptr, w.p2, R);
   SV_CHECK_LAUNCH("attn_post");
   // (5) FFN + norm3 (:379-385), exact GELU
-  SV_TRY(linear(w.p2, sp.lin1_w, sp.lin1_b, w.hdn, R, C, F, 2, nullptr, s));
-  SV_TRY(linear(w.hdn, sp.lin2_w, sp.lin2_b, w.qraw, R, F, C, 0, w.p2, s));
+  SV_TRY(linear_fast(w.p2, sp.lin1_w, sp.lin1_b, w.hdn, R, C, F, 2, nullptr, s));
+  SV_TRY(linear_fast(w.hdn, sp.lin2_w, sp.lin2_b, w.qraw, R, F, C, 0, w.p2, s, -1, -1, w.splitk));
   SV_TRY(ln_rows(w.qraw, nullptr, sp.norm3_w, sp.norm3_b, 1, nullptr, w.f, R, 0, s));
   // (6) Video Retriever over the T*N slots of all frames (:308-322, 494-527, 550-572)
   const float* fcur = w.f;
   if (temporal) {
     SV_REQUIRE(sp.tq_to_q_w != nullptr, "temporal stage without temporal_query_head parameters");
-    SV_TRY(linear(w.f, ps.tq_qkv_w, ps.tq_qkv_b, w.tqkv, R, C, 3 * C, 0, nullptr, s));
+    SV_TRY(linear_fast(w.f, ps.tq_qkv_w, ps.tq_qkv_b, w.tqkv, R, C, 3 * C, 0, nullptr, s));
     SV_TRY(ln_rows(w.tqkv, nullptr, ps.tq_ln_w, ps.tq_ln_b, 3, nullptr, w.tqkv, 3 * R, 0, s));   // rows r*3+{q,k,v}
     {
       GemmArgs g;                                       // L[l,u] = q_l . k_u
@@ -304,20 +313,20 @@ static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp,
     }
     SV_TRY(ln_rows(w.av, nullptr, sp.tq_no_w, sp.tq_no_b, 1, w.f, w.ty, R, 1, s));              // f + relu(LN(av))
     SV_TRY(ln_rows(w.ty, nullptr, sp.tq_norm2_w, sp.tq_norm2_b, 1, nullptr, w.ty, R, 0, s));    // y
-    SV_TRY(linear(w.ty, sp.tq_lin1_w, sp.tq_lin1_b, w.thdn, R, C, TF, 1, nullptr, s));
-    SV_TRY(linear(w.thdn, sp.tq_lin2_w, sp.tq_lin2_b, w.qraw, R, TF, C, 0, w.ty, s));
+    SV_TRY(linear_fast(w.ty, sp.tq_lin1_w, sp.tq_lin1_b, w.thdn, R, C, TF, 1, nullptr, s));
+    SV_TRY(linear_fast(w.thdn, sp.tq_lin2_w, sp.tq_lin2_b, w.qraw, R, TF, C, 0, w.ty, s, -1, -1, w.splitk));
     SV_TRY(ln_rows(w.qraw, nullptr, sp.tq_norm3_w, sp.tq_norm3_b, 1, w.f, w.f2, R, 0, s));      // X + LN3(...)  (:317)
     fcur = w.f2;
   }
   // (7) towers (:390-400): first layers of cls|reg share the input
-  SV_TRY(linear(fcur, ps.tw_w, nullptr, w.tw, R, C, 2 * C, 0, nullptr, s));
+  SV_TRY(linear_fast(fcur, ps.tw_w, nullptr, w.tw, R, C, 2 * C, 0, nullptr, s));
   SV_TRY(ln_rows(w.tw, nullptr, ps.tw_ln_w, ps.tw_ln_b, 2, nullptr, w.tw, 2 * R, 1, s));         // rows r*2+{cls,reg}
-  SV_TRY(linear(w.tw, sp.cls1_w, nullptr, w.c2, R, C, C, 0, nullptr, s, 2 * C));
+  SV_TRY(linear_fast(w.tw, sp.cls1_w, nullptr, w.c2, R, C, C, 0, nullptr, s, 2 * C));
   SV_TRY(ln_rows(w.c2, nullptr, sp.cls1_nw, sp.cls1_nb, 1, nullptr, w.c2, R, 1, s));
-  SV_TRY(linear(w.tw + C, sp.reg1_w, nullptr, w.e1, R, C, C, 0, nullptr, s, 2 * C));
+  SV_TRY(linear_fast(w.tw + C, sp.reg1_w, nullptr, w.e1, R, C, C, 0, nullptr, s, 2 * C));
   SV_TRY(ln_rows(w.e1, nullptr, sp.reg1_nw, sp.reg1_nb, 1, nullptr, w.slots, R, 1, s));          // next-stage slots
   for (int t = 0; t < T; ++t) {
-    SV_TRY(linear(w.c2 + (long)t * N * C, sp.logit_w, sp.logit_b, cls_out + t * cls_frame_stride, N, C, d->num_classes, 0, nullptr, s));
+    SV_TRY(linear_fast(w.c2 + (long)t * N * C, sp.logit_w, sp.logit_b, cls_out + t * cls_frame_stride, N, C, d->num_classes, 0, nullptr, s));
     SV_TRY(dcopy(w.slots + (long)t * N * C, emb_out + t * emb_frame_stride, (long)N * C, s));
   }
   return SLOTVPS_OK;
@@ -397,6 +406,12 @@ int slotvps_prepare_weights(const slotvps_head_desc* d, const slotvps_stage_para
   SV_CHECK_LAUNCH("fold_w0");
   SV_TRY(dcopy(conv_w, p.conv_w, (long)C * 3 * CIN, s));
   SV_TRY(dcopy(conv_b, p.conv_b, C, s));
+  conv_planes_kernel<<<ceil_div(C * CIN, 256), 256, 0, s>>>(p.W0, CIN, 0, CIN, p.ftc.w0);
+  SV_CHECK_LAUNCH("conv_planes");
+  conv_planes_kernel<<<ceil_div(C * C, 256), 256, 0, s>>>(conv_w, 3 * CIN, 0, C, p.ftc.wa);
+  SV_CHECK_LAUNCH("conv_planes");
+  conv_planes_kernel<<<ceil_div(C * CIN, 256), 256, 0, s>>>(conv_w, 3 * CIN, 2 * CIN, CIN, p.ftc.wb);
+  SV_CHECK_LAUNCH("conv_planes");
   const int S = n_stages_of(d);
   for (int i = 0; i < S; ++i) {
     const slotvps_stage_params& sp = stages[i];
@@ -405,6 +420,8 @@ int slotvps_prepare_weights(const slotvps_head_desc* d, const slotvps_stage_para
     SV_CHECK_LAUNCH("center(k)");
     center_rows_kernel<<<1, 256, 0, s>>>(sp.to_v_w, sp.to_v_b, ps.Wv_c, ps.bv_c);
     SV_CHECK_LAUNCH("center(v)");
+    transpose256_kernel<<<C, 256, 0, s>>>(ps.Wk_c, ps.Wk_cT);
+    SV_CHECK_LAUNCH("transpose");
     if (sp.tq_to_q_w) {
       const float* ws[3] = {sp.tq_to_q_w, sp.tq_to_k_w, sp.tq_to_v_w};
       const float* bs[3] = {sp.tq_to_q_b, sp.tq_to_k_b, sp.tq_to_v_b};
@@ -453,13 +470,12 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
   for (int t = 0; t < T; ++t) SV_TRY(dcopy(init_query[t], w.slots + (long)t * N * C, (long)N * C, s));
   const long cls_fs = (long)S * N * d->num_classes, emb_fs = (long)S * N * C;
   int stage = 0;
+  bool prev_planes = false;
   for (int l = 0; l < L; ++l) {
     const int h = d->h[l], wd = d->w[l], P = h * wd;
-    for (int t = 0; t < T; ++t)
-      SV_TRY(level_fuse_frame(l > 0 ? fused_out[t * L + l - 1] : nullptr, feats[t * L + l], pr.conv_w, pr.conv_b, pr.W0,
-                              fused_out[t * L + l], h, wd, w.ybuf + (long)t * C * (P / 4 + 1), s));
     const bool use_tc = d->kernel_path == 0 && tc_supported(d, l);
     const bool all_tc = use_tc && N <= attn::NROW;          // no fp32 kernel touches pos at this level
+    const bool fuse_tc = use_tc && (l == 0 || prev_planes);  // the coarse GEMM reads the previous level's planes
     const float* pl = nullptr;
     long pls = 0;
     if (d->pos_mode == 1) { pl = pos[l]; pls = pstride[l]; }
@@ -468,8 +484,42 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
       SV_CHECK_LAUNCH("sine_pos");
       pl = w.pos[l]; pls = 0;
     }
-    if (use_tc && d->heads_per_level[l] > 0)
-      SV_TRY(tc_split_level(fused_out[l], fstride[l], pl, pls, d->pos_mode == 2 && all_tc, w.tc, T, h, wd, s));
+    if (fuse_tc) {
+      // ---- level fusion on the tensor pipe; the epilogue also emits the fp16 operand planes ----
+      const long rows = (long)T * P;
+      Ptr8 src;
+      for (int t = 0; t < SLOTVPS_MAX_FRAMES; ++t) src.p[t] = t < T ? feats[t * L + l] : nullptr;
+      split_in_kernel<<<dim3(ceil_div(P, 32), T), 256, 0, s>>>(src, w.ftc.in_planes, rows, P);
+      SV_CHECK_LAUNCH("split_in");
+      fuse::Params prm;
+      memset(&prm, 0, sizeof(prm));
+      if (l > 0) {
+        const int Pp = d->h[l - 1] * d->w[l - 1];
+        const long rp = (long)T * Pp;
+        prm.rows = (int)rp; prm.P = Pp; prm.w = d->w[l - 1]; prm.h = d->h[l - 1]; prm.ksub = 4; prm.a_lo_row = (int)rp;
+        prm.y_out = w.ftc.y;
+        SV_TRY(fuse_tc_launch(w.tc.planes, 2 * rp, (int)rp, C, pr.ftc.wa, prm, s));
+        memset(&prm, 0, sizeof(prm));
+      }
+      prm.rows = (int)rows; prm.P = P; prm.w = wd; prm.h = h; prm.ksub = 2; prm.a_lo_row = (int)rows;
+      prm.bias = pr.conv_b; prm.y_in = l > 0 ? w.ftc.y : nullptr;
+      prm.out = fused_out[l]; prm.out_bs = fstride[l];
+      prm.planes = w.tc.planes; prm.plane_stride = rows;
+      if (d->pos_mode == 1) { prm.pos = pos[l]; prm.pos_bs = pstride[l]; }
+      else if (d->pos_mode == 2) {
+        pos_tab_kernel<<<ceil_div(128 * (h + wd), 256), 256, 0, s>>>(w.tc.ytab, w.tc.xtab, h, wd);
+        SV_CHECK_LAUNCH("pos_tab");
+        prm.ytab = w.tc.ytab; prm.xtab = w.tc.xtab;
+      }
+      SV_TRY(fuse_tc_launch(w.ftc.in_planes, 2 * rows, (int)rows, CIN, l > 0 ? pr.ftc.wb : pr.ftc.w0, prm, s));
+    } else {
+      for (int t = 0; t < T; ++t)
+        SV_TRY(level_fuse_frame(l > 0 ? fused_out[t * L + l - 1] : nullptr, feats[t * L + l], pr.conv_w, pr.conv_b, pr.W0,
+                                fused_out[t * L + l], h, wd, w.ybuf + (long)t * C * (P / 4 + 1), s));
+      if (use_tc && d->heads_per_level[l] > 0)
+        SV_TRY(tc_split_level(fused_out[l], fstride[l], pl, pls, d->pos_mode == 2 && all_tc, w.tc, T, h, wd, s));
+    }
+    prev_planes = fuse_tc || (use_tc && d->heads_per_level[l] > 0);
     for (int j = 0; j < d->heads_per_level[l]; ++j, ++stage) {
       const bool temporal = (d->temporal_mask >> stage) & 1;
       SV_TRY(run_stage(d, stages[stage], pr.st[stage], w, fused_out[l], fstride[l], pl, pls, h, wd, temporal, use_tc,
@@ -649,17 +699,14 @@ int slotvps_slot_attention(const slotvps_stage_params* sp, const float* slots_p,
   SV_CHECK_LAUNCH("center(k)");
   center_rows_kernel<<<1, 256, 0, s>>>(sp->to_v_w, sp->to_v_b, ps.Wv_c, ps.bv_c);
   SV_CHECK_LAUNCH("center(v)");
+  transpose256_kernel<<<C, 256, 0, s>>>(ps.Wk_c, ps.Wk_cT);
+  SV_CHECK_LAUNCH("transpose");
   SV_TRY(tc_prepare_stage(*sp, ps.Wk_c, ps.bk_c, ps.Wv_c, ps.bv_c, ps.tc, s));
   const int P = h * wd;
   SV_TRY(linear(slots_p, sp->to_q_w, sp->to_q_b, w.qraw, N, C, C, 0, nullptr, s));
   q_post_kernel<<<ceil_div(N, 8), 256, 0, s>>>(w.qraw, sp->nq_w, sp->nq_b, sp->nk_w, sp->nk_b, ps.bk_c, w.qt, w.g0, w.g1, N);
   SV_CHECK_LAUNCH("q_post");
-  GemmArgs g;
-  g.A = w.qt; g.a_ms = C; g.a_ks = 1;
-  g.B = ps.Wk_c; g.b_ks = C; g.b_ns = 1;
-  g.Cm = w.G; g.c_ms = C; g.c_ns = 1;
-  g.M = N; g.N = C; g.K = C;
-  SV_TRY(sgemm(g, s));
+  SV_TRY(linear_fast(w.qt, ps.Wk_cT, nullptr, w.G, N, C, C, 0, nullptr, s));
   const bool use_tc = kernel_path == 0 && tc_supported(&d, 0);
   if (use_tc) SV_TRY(tc_split_level(x, 0, pos, 0, false, w.tc, 1, h, wd, s));
   SV_TRY(pixel_attention(x, 0, pos, 0, ps, w, 1, N, P, use_tc, s));

@@ -1,0 +1,283 @@
+// Level fusion (conv_trans over cat(up2x(prev), x), dynamic_mask_head.py:172-185) on the tensor pipe.
+//
+// Folded form (exact up to fp32 re-association):  W.cat(up(p), x) + b = up(Wa.p) + Wb.x + b,
+// and for level 0  W.cat(x,x,x) + b = (Wa0+Wa1+Wb).x + b.  Two launches of one kernel per level:
+//   "coarse"  y[p'][o]  = sum_c prev[p'][c] Wa[o][c]              (A = the previous level's fp16 planes)
+//   "main"    x[p][o]   = sum_c in[p][c] Wb[o][c] + b[o] + bilinear2x(y)[p][o]
+// GEMM shape: M = 128 pixels per tile (TMEM lanes), N = 256 outputs, K = 128 / 256, fp16 hi/lo x3 products,
+// fp32 accumulation in TMEM (two 256-column accumulators: the epilogue of tile i overlaps the MMAs of
+// tile i+1).  The "main" epilogue writes everything the rest of the path needs in one pass: the fp32 NCHW
+// feature (a required output of the head) and the four fp16 operand planes x_hi, x_lo, (x+pos)_hi, (x+pos)_lo
+// consumed by the attention kernels -- the 256-channel feature is never re-read to build them.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "pixel_tc.cuh"
+
+namespace slotvps {
+namespace fuse {
+constexpr int TILE_M = 128;
+constexpr int A_BYTES = TILE_M * 128;          // [128 px][64 ch] fp16
+constexpr int B_BYTES = C * 128;               // [256 out][64 ch] fp16
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr int NSTAGE = 2;
+constexpr int AUX_BYTES = 2048;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + AUX_BYTES + 1024;
+constexpr int THREADS = 192;
+constexpr uint32_t IDESC = tc::make_idesc_f16(128, 256, 0, 0);
+
+struct Params {
+  int rows;            // T * P pixel rows of this launch
+  int P, w;            // pixels per frame and width of THIS resolution
+  int ksub;            // K / 64
+  int a_lo_row;        // row offset of the lo plane in tmap_a (hi plane at row 0)
+  const float* bias;   // [256] or null (coarse)
+  // coarse output
+  float* y_out;        // [rows][256] or null
+  // main outputs
+  const float* y_in;   // coarse y [T * P/4][256] or null (level 0)
+  float* out;          // NCHW fp32, frame t at out + t*out_bs, or null
+  long out_bs;
+  __half* planes;      // 4 planes with stride plane_stride rows, or null
+  long plane_stride;
+  const float* pos;    // [256][P] per frame (pos_bs) or null
+  long pos_bs;
+  const float *ytab, *xtab;   // separable sine tables of this resolution or null
+  int h;
+};
+}  // namespace fuse
+
+// input features fp32 [128][P] (one pointer per frame) -> fp16 hi/lo planes [2][T*P][128]
+struct Ptr8 { const float* p[SLOTVPS_MAX_FRAMES]; };
+__global__ void __launch_bounds__(256) split_in_kernel(Ptr8 src, __half* __restrict__ planes, long rows, int P) {
+  __shared__ float xs[CIN][33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p0 = blockIdx.x * 32, t = blockIdx.y;
+  const float* __restrict__ X = src.p[t];
+  const int p = p0 + lane;
+  for (int c = warp; c < CIN; c += 8) xs[c][lane] = p < P ? __ldg(X + (long)c * P + p) : 0.f;
+  __syncthreads();
+  __half2* out = reinterpret_cast<__half2*>(planes);
+#pragma unroll 4
+  for (int i = 0; i < 8; ++i) {
+    int idx = tid + i * 256, pp = idx >> 6, cp = idx & 63;
+    if (p0 + pp >= P) continue;
+    long o = ((long)t * P + p0 + pp) * (CIN / 2) + cp;
+    __half h0, l0, h1, l1;
+    split_bf16(xs[2 * cp][pp], h0, l0); split_bf16(xs[2 * cp + 1][pp], h1, l1);
+    out[o] = __halves2half2(h0, h1);
+    out[rows * (CIN / 2) + o] = __halves2half2(l0, l1);
+  }
+}
+// fp32 weight [256][ld] columns [col0, col0+K) -> fp16 hi/lo planes [2][256][K]
+__global__ void __launch_bounds__(256) conv_planes_kernel(const float* __restrict__ W, int ld, int col0, int K, __half* __restrict__ out) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= C * K) return;
+  int o = i / K, c = i % K;
+  __half h, l;
+  split_bf16(W[(long)o * ld + col0 + c], h, l);
+  out[i] = h; out[(long)C * K + i] = l;
+}
+
+__global__ void __launch_bounds__(fuse::THREADS, 1)
+fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const fuse::Params prm) {
+  using namespace fuse;
+  extern __shared__ uint8_t raw_smem[];
+  const uint32_t raw = tc::smem_u32(raw_smem);
+  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
+  uint8_t* aux = smem + NSTAGE * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* tfull = empty + NSTAGE;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* bias = reinterpret_cast<float*>(aux + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (prm.rows + TILE_M - 1) / TILE_M;
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmap_a);
+    tc::tma_prefetch_desc(&tmap_w);
+    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 128); }
+    tc::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < C; i += THREADS) bias[i] = prm.bias ? prm.bias[i] : 0.f;
+  if (warp == 1) { tc::tmem_alloc(tmem_ptr, 512); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row = tile * TILE_M;
+        for (int ks = 0; ks < prm.ksub; ++ks, ++it) {
+          const int s = it % NSTAGE;
+          tc::mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          tc::mbar_expect_tx(&full[s], STAGE_BYTES);
+          tc::tma_load_2d(st, &tmap_a, ks * 64, row, &full[s]);
+          tc::tma_load_2d(st + A_BYTES, &tmap_a, ks * 64, prm.a_lo_row + row, &full[s]);
+          tc::tma_load_2d(st + 2 * A_BYTES, &tmap_w, ks * 64, 0, &full[s]);
+          tc::tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmap_w, ks * 64, C, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const int g = ti & 1, u = ti >> 1;
+        tc::mbar_wait(&tempty[g], (u & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + g * 256;
+        for (int ks = 0; ks < prm.ksub; ++ks, ++it) {
+          const int s = it % NSTAGE;
+          tc::mbar_wait(&full[s], (it / NSTAGE) & 1);
+          tc::tc_fence_after();
+          const uint32_t a_hi = tc::smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+          const uint64_t dah = tc::make_smem_desc_sw128(a_hi, 16, 1024), dal = tc::make_smem_desc_sw128(a_lo, 16, 1024);
+          const uint64_t dbh = tc::make_smem_desc_sw128(b_hi, 16, 1024), dbl = tc::make_smem_desc_sw128(b_lo, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc::umma_bf16(d_tmem, dah + 2 * k, dbh + 2 * k, IDESC, (ks | k) != 0);
+            tc::umma_bf16(d_tmem, dal + 2 * k, dbh + 2 * k, IDESC, 1);
+            tc::umma_bf16(d_tmem, dah + 2 * k, dbl + 2 * k, IDESC, 1);
+          }
+          tc::umma_commit(&empty[s]);
+        }
+        tc::umma_commit(&tfull[g]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int g = ti & 1, u = ti >> 1;
+      const int row = tile * TILE_M + r;
+      const bool rv = row < prm.rows;
+      const int t = rv ? row / prm.P : 0, p = rv ? row % prm.P : 0;
+      // bilinear x2 source taps (align_corners=False): coarse map is (h/2) x (w/2)
+      int i00 = 0, i01 = 0, i10 = 0, i11 = 0;
+      float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+      const int py = p / prm.w, px = p % prm.w;
+      if (prm.y_in) {
+        const int ch = prm.h / 2, cw = prm.w / 2;
+        float sy = fmaxf((py + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((px + 0.5f) * 0.5f - 0.5f, 0.f);
+        int y0 = (int)sy, x0 = (int)sx;
+        int y1 = min(y0 + 1, ch - 1), x1 = min(x0 + 1, cw - 1);
+        float ly = sy - y0, lx = sx - x0;
+        const int base = t * ch * cw;
+        i00 = base + y0 * cw + x0; i01 = base + y0 * cw + x1; i10 = base + y1 * cw + x0; i11 = base + y1 * cw + x1;
+        w00 = (1.f - ly) * (1.f - lx); w01 = (1.f - ly) * lx; w10 = ly * (1.f - lx); w11 = ly * lx;
+      }
+      tc::mbar_wait(&tfull[g], u & 1);
+      tc::tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < C / 32; ++j) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + lane_addr + g * 256 + j * 32, v);
+        tc::tmem_ld_wait();
+        if (j == C / 32 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }      // accumulator drained
+        if (!rv) continue;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] += bias[j * 32 + c];
+        if (prm.y_out) {
+          float4* dst = reinterpret_cast<float4*>(prm.y_out + (long)row * C + j * 32);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          continue;
+        }
+        if (prm.y_in) {
+          const float4* a = reinterpret_cast<const float4*>(prm.y_in + (long)i00 * C + j * 32);
+          const float4* b = reinterpret_cast<const float4*>(prm.y_in + (long)i01 * C + j * 32);
+          const float4* cc = reinterpret_cast<const float4*>(prm.y_in + (long)i10 * C + j * 32);
+          const float4* d = reinterpret_cast<const float4*>(prm.y_in + (long)i11 * C + j * 32);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 ya = __ldg(a + c), yb = __ldg(b + c), yc = __ldg(cc + c), yd = __ldg(d + c);
+            // same association as F.interpolate: (1-ly)*((1-lx)*v00 + lx*v01) + ly*((1-lx)*v10 + lx*v11), weights pre-multiplied
+            v[4 * c] += w00 * ya.x + w01 * yb.x + w10 * yc.x + w11 * yd.x;
+            v[4 * c + 1] += w00 * ya.y + w01 * yb.y + w10 * yc.y + w11 * yd.y;
+            v[4 * c + 2] += w00 * ya.z + w01 * yb.z + w10 * yc.z + w11 * yd.z;
+            v[4 * c + 3] += w00 * ya.w + w01 * yb.w + w10 * yc.w + w11 * yd.w;
+          }
+        }
+        if (prm.out) {
+          float* o = prm.out + (long)t * prm.out_bs + (long)(j * 32) * prm.P + p;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[(long)c * prm.P] = v[c];
+        }
+        if (prm.planes) {
+          uint32_t hi[16], lo[16];
+          auto pack = [&](const float* src) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              __half h0, l0, h1, l1;
+              split_bf16(src[2 * c], h0, l0); split_bf16(src[2 * c + 1], h1, l1);
+              __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+              hi[c] = *reinterpret_cast<uint32_t*>(&hh); lo[c] = *reinterpret_cast<uint32_t*>(&ll);
+            }
+          };
+          auto store = [&](int plane, const uint32_t* w) {
+            uint4* dst = reinterpret_cast<uint4*>(prm.planes + ((long)plane * prm.plane_stride + row) * C + j * 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+          };
+          pack(v); store(0, hi); store(1, lo);
+          if (prm.pos) {
+            const float* ps = prm.pos + (long)t * prm.pos_bs + (long)(j * 32) * prm.P + p;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] += __ldg(ps + (long)c * prm.P);
+          } else if (prm.ytab) {
+            if (j < 4) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] += __ldg(prm.ytab + (j * 32 + c) * prm.h + py);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] += __ldg(prm.xtab + ((j - 4) * 32 + c) * prm.w + px);
+            }
+          }
+          pack(v); store(2, hi); store(3, lo);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+struct FuseTcWeights {
+  __half *w0 = nullptr, *wa = nullptr, *wb = nullptr;   // [2][256][128], [2][256][256], [2][256][128] hi/lo planes
+};
+struct FuseTcWorkspace {
+  __half* in_planes = nullptr;   // [2][T*Pmax][128]
+  float* y = nullptr;            // [T*Pmax/4][256]
+};
+
+inline int fuse_tc_launch(const __half* a_planes, long a_rows_total, int a_lo_row, int K, const __half* w_planes, const fuse::Params& prm,
+                          cudaStream_t s) {
+  CUtensorMap ma, mw;
+  SV_TRY(tc::make_tmap_h16_sw128(&ma, a_planes, (uint64_t)a_rows_total, (uint64_t)K, fuse::TILE_M));
+  SV_TRY(tc::make_tmap_h16_sw128(&mw, w_planes, (uint64_t)2 * C, (uint64_t)K, C));
+  static bool attr_done = false;
+  if (!attr_done) {
+    SV_CHECK_CUDA(cudaFuncSetAttribute(fuse_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int n_tiles = ceil_div(prm.rows, fuse::TILE_M);
+  const int grid = n_tiles < 148 ? n_tiles : 148;
+  fuse_tc_kernel<<<grid, fuse::THREADS, fuse::SMEM_BYTES, s>>>(ma, mw, prm);
+  SV_CHECK_LAUNCH("fuse_tc");
+  return SLOTVPS_OK;
+}
+
+}  // namespace slotvps

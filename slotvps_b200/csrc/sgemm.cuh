@@ -180,3 +180,134 @@ inline int linear(const float* X, const float* W, const float* b, float* Y, int 
 }
 
 }  // namespace slotvps
+
+// ---------------------------------------------------------------------------------------------------
+// nn.Linear on row-major slots, both operands K-contiguous ("TN"): Y[R,O] = act(X[R,K] . W[O,K]^T + b + resid)
+// 32x64 tiles, BK = 32, 3-stage cp.async pipeline, float4 shared-memory reads.  Small tiles on purpose:
+// R = T*N is ~200, so parallelism has to come from the output columns (and split-K for the long-K layers).
+namespace slotvps {
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct LinArgs {
+  const float* X; long ldx;
+  const float* W;            // [O][K]
+  float* Y; long ldy;
+  const float* bias; const float* resid; long ldr;
+  int R, K, O, act;
+  int ksplit;                // > 1: blockIdx.z handles K/ksplit and writes raw partials to Y + z*R*O (ldy = O)
+};
+
+__global__ void __launch_bounds__(256) linear_tn_kernel(LinArgs g) {
+  constexpr int BM = 32, BN = 64, BK = 32, PK = BK + 4, ST = 3;
+  __shared__ __align__(16) float As[ST][BM][PK];
+  __shared__ __align__(16) float Bs[ST][BN][PK];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int klen = g.K / g.ksplit, kbeg = blockIdx.z * klen;
+  const int nk = klen / BK;
+  // loader mapping: one 16-byte chunk of A and two of B per thread and stage
+  const int lr = tid >> 3, lc = (tid & 7) * 4;
+  const float* xa = g.X + (long)min(m0 + lr, g.R - 1) * g.ldx + kbeg + lc;
+  const float* wb0 = g.W + (long)min(n0 + lr, g.O - 1) * g.K + kbeg + lc;
+  const float* wb1 = g.W + (long)min(n0 + lr + 32, g.O - 1) * g.K + kbeg + lc;
+  auto load = [&](int st, int kt) {
+    cp_async16(&As[st][lr][lc], xa + kt * BK);
+    cp_async16(&Bs[st][lr][lc], wb0 + kt * BK);
+    cp_async16(&Bs[st][lr + 32][lc], wb1 + kt * BK);
+  };
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int s = 0; s < ST - 1; ++s) { if (s < nk) load(s, s); cp_async_commit(); }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<ST - 2>();
+    __syncthreads();
+    if (kt + ST - 1 < nk) load((kt + ST - 1) % ST, kt + ST - 1);
+    cp_async_commit();
+    const int st = kt % ST;
+#pragma unroll
+    for (int k4 = 0; k4 < BK; k4 += 4) {
+      float4 a[2], b[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = *(const float4*)&As[st][ty * 2 + i][k4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = *(const float4*)&Bs[st][tx * 4 + j][k4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+          acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+          acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+        }
+    }
+  }
+  float* Y = g.Y + (g.ksplit > 1 ? (long)blockIdx.z * g.R * g.O : 0);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + ty * 2 + i;
+    if (m >= g.R) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.O) continue;
+      float v = acc[i][j];
+      if (g.ksplit == 1) {
+        if (g.bias) v += __ldg(g.bias + n);
+        if (g.resid) v += __ldg(g.resid + (long)m * g.ldr + n);
+        if (g.act == 1) v = fmaxf(v, 0.f);
+        else if (g.act == 2) v = gelu_erf(v);
+      }
+      Y[(long)m * g.ldy + n] = v;
+    }
+  }
+}
+// sums the split-K partials in a fixed order and applies the epilogue
+__global__ void __launch_bounds__(256) linear_splitk_epilogue_kernel(const float* __restrict__ part, int parts, float* __restrict__ Y, long ldy,
+                                                                     const float* __restrict__ bias, const float* __restrict__ resid, long ldr,
+                                                                     int R, int O, int act) {
+  long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (long)R * O) return;
+  int m = (int)(i / O), n = (int)(i % O);
+  float v = 0.f;
+  for (int p = 0; p < parts; ++p) v += part[(long)p * R * O + i];
+  if (bias) v += __ldg(bias + n);
+  if (resid) v += __ldg(resid + (long)m * ldr + n);
+  if (act == 1) v = fmaxf(v, 0.f);
+  else if (act == 2) v = gelu_erf(v);
+  Y[(long)m * ldy + n] = v;
+}
+
+// `scratch` (>= 4*R*O floats) enables split-K for K >= 1024
+inline int linear_fast(const float* X, const float* W, const float* b, float* Y, int R, int K, int O, int act, const float* resid,
+                       cudaStream_t s, long ldx = -1, long ldy = -1, float* scratch = nullptr) {
+  if (ldx < 0) ldx = K;
+  if (ldy < 0) ldy = O;
+  const bool ok = (K % 32 == 0) && (ldx % 4 == 0) && (((uintptr_t)X | (uintptr_t)W) % 16 == 0);
+  if (!ok) return linear(X, W, b, Y, R, K, O, act, resid, s, ldx, ldy);
+  LinArgs g{X, ldx, W, Y, ldy, b, resid, (long)O, R, K, O, act, 1};
+  dim3 grid(ceil_div(O, 64), ceil_div(R, 32), 1);
+  if (scratch && K >= 1024 && (K / 4) % 32 == 0) {
+    g.ksplit = 4; g.Y = scratch; g.ldy = O; grid.z = 4;
+    linear_tn_kernel<<<grid, 256, 0, s>>>(g);
+    SV_CHECK_LAUNCH("linear_tn(splitk)");
+    linear_splitk_epilogue_kernel<<<(unsigned)(((long)R * O + 255) / 256), 256, 0, s>>>(scratch, 4, Y, ldy, b, resid, O, R, O, act);
+    SV_CHECK_LAUNCH("linear_splitk_epilogue");
+    return SLOTVPS_OK;
+  }
+  linear_tn_kernel<<<grid, 256, 0, s>>>(g);
+  SV_CHECK_LAUNCH("linear_tn");
+  return SLOTVPS_OK;
+}
+
+}  // namespace slotvps
