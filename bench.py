@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--kernel-path", type=int, default=0, help="0 auto (tensor-core kernels), 1 force fp32 CUDA-core")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     return ap.parse_args()
 
@@ -74,7 +75,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -125,7 +126,8 @@ def kernel_flops_per_step(name, args, shapes, heads):
     table = {
         "proj_rstd(k)": 2 * C * C * px, "proj_rstd(v)": 2 * C * C * px,      # K / V projection (LayerNorm statistics)
         "slot_attn_fp32": 4 * N * C * px,                                    # slots.keys^T + attn^T.V
-        "slot_attn_tc": (4 * C * C + 4 * N * C) * px,                        # fused: projections + both contractions
+        "stats_tc": 4 * C * C * px,                                          # both projections (their LayerNorm statistics), tcgen05
+        "attn_tc": 4 * N * C * px,                                           # slots.keys^T + softmax + attn^T.V, tcgen05
     }
     return table.get(name)
 
@@ -217,13 +219,26 @@ def main():
     def step(i, feats):
         return model(feats, (H, W), pos="sine", fusion_logits=fusion_logits, panoptic_out=pan[i % K])
 
+    graphs = None
+    if not args.no_graph:
+        # one graph per resident clip (static inputs); the id map lands in the graph's static output
+        graphs = [sv.GraphedClip(model, clip, (H, W), pos="sine", fusion_logits=fusion_logits) for clip in dev_clips]
+
+    def fast_step(i):
+        if graphs is None:
+            return step(i, dev_clips[i % 2])
+        o = graphs[i % 2].replay()
+        if dist is not None:
+            pan[i % K].copy_(o["fusion"].panoptic, non_blocking=True)
+        return o
+
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
     for i in range(Wm):
-        step(i, dev_clips[i % 2])
+        fast_step(i)
     barrier()
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
     if rank == 0:
@@ -233,19 +248,18 @@ def main():
     barrier()
     e0.record()
     for i in range(K):
-        out = step(i, dev_clips[i % 2])
+        out = fast_step(i)
     if dist is not None:                                    # one all-gather of the shard's id maps
-        gathered = torch.empty((world,) + tuple(pan.shape), dtype=pan.dtype, device=dev)
+        gathered = torch.empty((world * K, H, W), dtype=pan.dtype, device=dev)
         dist.all_gather_into_tensor(gathered, pan)
     e1.record()
     barrier()
-    launches = int(L.slotvps_launch_count(0))
+    launches = int(L.slotvps_launch_count(0)) if graphs is None else K * graphs[0].launches
     ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
     value = world * K * T / (ms * 1e-3)
     meta = out["fusion"].host()
 
@@ -253,7 +267,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         pinned = [[[f.pin_memory() for f in fr] for fr in clip] for clip in host_clips]
-        stage = [[torch.empty_like(f, device=dev) for f in fr] for fr in host_clips[0]]
+        stage = dev_clips[0] if graphs is not None else [[torch.empty_like(f, device=dev) for f in fr] for fr in host_clips[0]]
         h_pan = torch.empty((H, W), dtype=torch.int64).pin_memory()
         h_meta = torch.empty(4 + 3 * N, dtype=torch.int32).pin_memory()
         h2d = sum(f.numel() * 4 for fr in host_clips[0] for f in fr)
@@ -264,7 +278,7 @@ def main():
             for t in range(T):
                 for l in range(4):
                     stage[t][l].copy_(src[t][l], non_blocking=True)
-            o = step(i, stage)
+            o = graphs[0].replay() if graphs is not None else step(i, stage)
             h_pan.copy_(o["fusion"].panoptic, non_blocking=True)
             h_meta.copy_(o["fusion"].meta, non_blocking=True)
         for i in range(max(1, Wm)):
@@ -282,6 +296,8 @@ def main():
             ms2 = float(t.item())
         e2e = dict(value=world * K * T / (ms2 * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                    ms_per_step=ms2 / K)
+
+    clocks = sampler.stop() if rank == 0 else None     # sampled over the timed region and the e2e region (both under load)
 
     # ---- per-kernel device times (CUDA events on the launching stream) -> roofline ----------------------
     roofline, breakdown = None, None
@@ -306,11 +322,12 @@ def main():
             ach = fl / (t_ms * 1e-3) / 1e12
             peak = pk["bf16_tflops_sustained"]
             roofline = dict(kernel=name, bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
+                            executed_mma_tflops=3 * ach if name.endswith("_tc") else None,   # fp16 hi/lo split: 3 MMA products per algorithmic product
                             traffic=None, peak_source=f"{pk['source']} bf16 sustained (kernel timed inside the step)",
                             algorithmic_flops_per_step=fl, ms_per_step=t_ms, share_of_step=t_ms / total,
                             launches_per_step=breakdown[name]["launches_per_step"])
             # the whole attention contraction (all its kernels) against the same peak
-            names = [k for k in breakdown if k in ("proj_rstd(k)", "proj_rstd(v)", "slot_attn_fp32", "slot_attn_tc")]
+            names = [k for k in breakdown if k in ("proj_rstd(k)", "proj_rstd(v)", "slot_attn_fp32", "stats_tc", "attn_tc")]
             tt = sum(breakdown[k]["ms_per_step"] for k in names)
             roofline["attention_contraction"] = dict(kernels=names, algorithmic_tflops=per_frame_flops * T / (tt * 1e-3) / 1e12,
                                                      ms_per_step=tt, frac_of_peak=per_frame_flops * T / (tt * 1e-3) / 1e12 / peak)
@@ -333,7 +350,7 @@ def main():
                                 frames_convention="retriever frames/s = T * clips/s; output frames/s = clips/s",
                                 l2="inputs larger than L2 (178 MB/clip), two clips alternated",
                                 fusion_logits="designed (random-init heads keep no slot)",
-                                kernel_path=args.kernel_path, sharding="clips per rank, one all_gather of id maps" if world > 1 else "single GPU",
+                                kernel_path=args.kernel_path, cuda_graph=graphs is not None, sharding="clips per rank, one all_gather of id maps" if world > 1 else "single GPU",
                                 kept_slots=meta["k"], fusion_iters=meta["iters"]),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
                     kernel_breakdown_ms_per_step=breakdown)

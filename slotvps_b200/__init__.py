@@ -9,7 +9,7 @@ All compute is hand-written CUDA behind the C ABI of include/slotvps_b200.h; the
 """
 from ._lib import build_library, lib, SlotVPSError  # noqa: F401
 from .head import B200DynamicMaskHead  # noqa: F401
-from .retriever import (PanopticFusion, SlotVPSRetriever, FusionOutput, mask_logits, level_fuse,  # noqa: F401
+from .retriever import (PanopticFusion, SlotVPSRetriever, FusionOutput, GraphedClip, mask_logits, level_fuse,  # noqa: F401
                         slot_attention, sine_position_embedding)
 
 HEAD_KWARGS = dict(  # configs/cityscapes/r50_fpn_slotvps.py:27-54

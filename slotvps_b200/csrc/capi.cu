@@ -242,12 +242,8 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
     SV_CHECK_LAUNCH("slot_attn_fp32");
   }
   const long nz = (long)T * N * C, na = (long)T * N;
-  reduce_parts_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, s>>>(w.Zpart, w.Z, nz, chunks);
-  SV_CHECK_LAUNCH("reduce(Z)");
-  reduce_parts_kernel<<<(unsigned)((na + 255) / 256), 256, 0, s>>>(w.a0part, w.a0, na, chunks);
-  SV_CHECK_LAUNCH("reduce(a0)");
-  reduce_parts_kernel<<<(unsigned)((na + 255) / 256), 256, 0, s>>>(w.a1part, w.a1, na, chunks);
-  SV_CHECK_LAUNCH("reduce(a1)");
+  reduce_attn_parts_kernel<<<(unsigned)((nz + 2 * na + 255) / 256), 256, 0, s>>>(w.Zpart, w.a0part, w.a1part, w.Z, w.a0, w.a1, nz, na, chunks);
+  SV_CHECK_LAUNCH("reduce_attn_parts");
   return SLOTVPS_OK;
 }
 
@@ -266,7 +262,7 @@ static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp,
       SV_CHECK_CUDA(cudaFuncSetAttribute(mha_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_smem = smem;
     }
-    mha_core_kernel<<<dim3(d->nhead, T), 256, smem, s>>>(w.qkv, w.mo, N, d->nhead);
+    mha_core_kernel<<<dim3(d->nhead, T, 4), 256, smem, s>>>(w.qkv, w.mo, N, d->nhead);
     SV_CHECK_LAUNCH("mha_core");
   }
   SV_TRY(linear_fast(w.mo, sp.out_proj_w, sp.out_proj_b, w.qraw, R, C, C, 0, w.slots, s));       // s + attn

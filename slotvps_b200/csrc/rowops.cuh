@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) mha_core_kernel(const float* __restrict__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* pw = ps + warp * n_slots;
   const float scale = rsqrtf((float)D);
-  for (int i = warp; i < n_slots; i += 8) {
+  // query rows are split over blockIdx.z so that (heads x frames x gridDim.z) CTAs fill the machine
+  for (int i = blockIdx.z * 8 + warp; i < n_slots; i += 8 * gridDim.z) {
     float qd = base[(long)i * 3 * C + hd * D + lane] * scale;     // lane = dim
     float mx = -INFINITY;
     for (int j0 = 0; j0 < n_slots; j0 += 32) {
@@ -184,6 +185,25 @@ __global__ void __launch_bounds__(256) reduce_parts_kernel(const float* __restri
   float s = 0.f;
   for (int k = 0; k < parts; ++k) s += part[(long)k * n + i];
   out[i] = s;
+}
+
+// Z, a0, a1 partial sums in one launch (fixed order => deterministic)
+__global__ void __launch_bounds__(256) reduce_attn_parts_kernel(const float* __restrict__ Zp, const float* __restrict__ a0p, const float* __restrict__ a1p,
+                                                                float* __restrict__ Z, float* __restrict__ a0, float* __restrict__ a1, long nz, long na, int parts) {
+  long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i < nz) {
+    float s = 0.f;
+    for (int k = 0; k < parts; ++k) s += Zp[(long)k * nz + i];
+    Z[i] = s;
+  } else if (i < nz + 2 * na) {
+    long j = i - nz;
+    const float* src = j < na ? a0p : a1p;
+    float* dst = j < na ? a0 : a1;
+    if (j >= na) j -= na;
+    float s = 0.f;
+    for (int k = 0; k < parts; ++k) s += src[(long)k * na + j];
+    dst[j] = s;
+  }
 }
 
 }  // namespace slotvps

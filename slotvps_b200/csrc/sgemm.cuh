@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) linear_tn_kernel(LinArgs g) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) a[i] = *(const float4*)&As[st][ty * 2 + i][k4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = *(const float4*)&Bs[st][tx * 4 + j][k4];
+      for (int j = 0; j < 4; ++j) b[j] = *(const float4*)&Bs[st][j * 16 + tx][k4];   // interleaved columns: conflict-free float4 reads
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) linear_tn_kernel(LinArgs g) {
     if (m >= g.R) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+      const int n = n0 + j * 16 + tx;
       if (n >= g.O) continue;
       float v = acc[i][j];
       if (g.ksplit == 1) {

@@ -234,3 +234,29 @@ class SlotVPSRetriever(nn.Module):
             lg = cls[-1][-1, 0] if fusion_logits is None else fusion_logits
             out["fusion"] = self.postprocess_panoptic.fuse(lg, pm, size, out=panoptic_out)
         return out
+
+
+class GraphedClip:
+    """One clip shape captured as a CUDA graph (the step is ~400 short kernels; replaying the graph
+    removes the per-launch host latency).  ``features`` are the STATIC input tensors: copy a new
+    clip's data into them, call ``replay()``, read the static outputs in ``self.out``."""
+
+    def __init__(self, model: "SlotVPSRetriever", features, size, **kw):
+        self.model, self.features, self.size, self.kw = model, features, size, kw
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                  # warm-up: workspaces, weight preparation, func attributes
+            for _ in range(2):
+                model(features, size, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        L = _lib.lib()
+        before = L.slotvps_launch_count(0)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = model(features, size, **kw)
+        self.launches = int(L.slotvps_launch_count(0) - before)      # kernels of this library inside the graph
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
