@@ -126,6 +126,16 @@ int slotvps_mask_logits(const float* feat, const float* emb,
                         const float* fg_bn /*[4] device: weight,bias,running_mean,running_var*/, float* out,
                         int n_slots, int h, int w, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same projection, but the contraction reads the fp16 operand planes that the immediately preceding
+ * slotvps_head_forward(d, ..., head_workspace) left for the finest level (frame = index into the clip);
+ * `feat` (the same [256,h,w] fp32 feature) is only used for the per-pixel norm.  Returns
+ * SLOTVPS_EUNSUPPORTED when that head call did not run the tensor-core path for the finest level.
+ * `workspace`: slotvps_mask_logits_workspace_bytes().                                              */
+int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, size_t head_workspace_bytes, int frame,
+                             const float* feat, const float* emb,
+                             const float* feat_bn_w, const float* feat_bn_b, const float* feat_bn_mean, const float* feat_bn_var,
+                             const float* fg_bn, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Panoptic fusion: PostProcessPanopticInstances.forward (vps_temporal_slots.py:659-807, incl.
  * mask_removal :564-657) + the inline relabel of simple_test (:411-435), entirely on device.
  *   pred_logits [N,num_classes], pred_masks [N,h,w] (1/4 resolution), target size (H,W).

@@ -104,6 +104,7 @@ SYMBOLS = {
     "slotvps_slot_attention_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "slotvps_mask_logits_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "slotvps_mask_logits": (C.c_int, [P, P, P, P, P, P, P, P, C.c_int, C.c_int, C.c_int, P, C.c_size_t, P]),
+    "slotvps_head_mask_logits": (C.c_int, [C.POINTER(HeadDesc), P, C.c_size_t, C.c_int, P, P, P, P, P, P, P, P, P, C.c_size_t, P]),
     "slotvps_fusion_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "slotvps_panoptic_fuse": (C.c_int, [C.POINTER(FusionCfg), P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P,
                                         P, C.c_int, P, C.c_size_t, P]),

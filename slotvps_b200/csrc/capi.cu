@@ -11,6 +11,7 @@
 #include "fusion.cuh"
 #include "pixel_tc.cuh"
 #include "fuse_tc.cuh"
+#include "mask_tc.cuh"
 
 namespace slotvps {
 thread_local char g_err[512] = "";
@@ -575,6 +576,7 @@ int slotvps_mask_logits_workspace_bytes(int n_slots, int h, int w, size_t* bytes
   Arena a(nullptr, (size_t)-1);
   a.take<float>(C); a.take<float>(C); a.take<float>((size_t)n_slots * C); a.take<float>(n_slots); a.take<float>(4);
   a.take<float>((size_t)h * w);
+  a.take<__half>((size_t)2 * 112 * C);
   *bytes = align_up(a.off);
   return SLOTVPS_OK;
 }
@@ -603,6 +605,36 @@ int slotvps_mask_logits(const float* feat, const float* emb, const float* bw, co
   g.bias = dn; g.bias_mode = 1;
   g.col_scale = rn; g.affine = aff;
   return sgemm(g, s);
+}
+
+// Mask logits straight from the operand planes a preceding slotvps_head_forward left in `head_workspace`
+// (finest level, frame `frame`).  Returns SLOTVPS_EUNSUPPORTED when that head call did not take the
+// tensor-core path for the finest level (caller then uses slotvps_mask_logits on the fp32 feature).
+int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, size_t head_workspace_bytes, int frame, const float* feat,
+                             const float* emb, const float* bw, const float* bb, const float* bm, const float* bv, const float* fg_bn,
+                             float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  SV_TRY(validate(d));
+  SV_REQUIRE(head_workspace && feat && emb && bw && bb && bm && bv && fg_bn && out && workspace, "null argument");
+  SV_REQUIRE(frame >= 0 && frame < d->n_frames, "frame out of range");
+  const int l = d->n_levels - 1, N = d->n_slots, h = d->h[l], w = d->w[l], P = h * w;
+  if (!(d->kernel_path == 0 && tc_supported(d, l) && N <= mask::NROW)) return fail(SLOTVPS_EUNSUPPORTED, "planes unavailable%s%s");
+  cudaStream_t s = (cudaStream_t)stream;
+  HeadWs hw;
+  if (head_ws_layout(d, head_workspace, head_workspace_bytes, &hw) > head_workspace_bytes) return fail(SLOTVPS_EWORKSPACE, "head workspace too small%s%s");
+  Arena a(workspace, workspace_bytes);
+  float* sc = a.take<float>(C); float* sh = a.take<float>(C);
+  float* e2 = a.take<float>((size_t)N * C); float* dn = a.take<float>(N); float* aff = a.take<float>(4);
+  float* rn = a.take<float>(P);
+  __half* ep = a.take<__half>((size_t)2 * mask::NROW * C);
+  if (!a.ok()) return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
+  mask_prep_kernel<<<N, 256, 0, s>>>(emb, bw, bb, bm, bv, fg_bn, sc, sh, e2, dn, aff, N);
+  SV_CHECK_LAUNCH("mask_prep");
+  feat_rnorm_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
+  SV_CHECK_LAUNCH("feat_rnorm");
+  g_planes_kernel<<<(unsigned)(((long)mask::NROW * C + 255) / 256), 256, 0, s>>>(e2, ep, N, 1);
+  SV_CHECK_LAUNCH("g_planes");
+  const long rows = (long)d->n_frames * P;
+  return mask_tc_launch(hw.tc.planes, 2 * rows, rows, (long)frame * P, ep, dn, rn, aff, out, N, P, s);
 }
 
 // ---- panoptic fusion ----------------------------------------------------------------------------------

@@ -140,6 +140,7 @@ class B200DynamicMaskHead(nn.Module):
             stage += per_dh_num_heads[i]
         self.conv_trans = _ConvParams(trans_in_dim, dh_dim)
         self._prepared = None           # (key, buffer, StageParams array)
+        self._last_call = None
         self._ws = {}
         for p in self.parameters():
             if p.dim() > 1:
@@ -257,5 +258,6 @@ class B200DynamicMaskHead(nn.Module):
             C.byref(d), table, prepared.data_ptr(), feat_ptrs, pos_ptrs, q_ptrs, cls.data_ptr(), emb.data_ptr(),
             fused_ptrs, ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "slotvps_head_forward")
         del pos_l
+        self._last_call = (d, ws)          # the finest level's operand planes stay valid in ws until the next forward
         return ([cls[t] for t in range(T)], [emb[t] for t in range(T)],
                 [[fused[l][t] for l in range(L)] for t in range(T)])

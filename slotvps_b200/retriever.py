@@ -218,6 +218,35 @@ class SlotVPSRetriever(nn.Module):
                 d[f"{name}.{k}"] = getattr(bn, k)
         return d
 
+    def _mask_logits_after_head(self, feat, emb, frame):
+        """Mask logits of clip frame ``frame`` right after the head call: the contraction runs on the tensor
+        pipe from the operand planes still resident in the head's workspace; falls back to the generic
+        entry point when the head did not take the tensor-core path for the finest level."""
+        bn = self._bn_dict()
+        last = self.dynamic_mask_head._last_call
+        if last is not None:
+            d, hws = last
+            feat = feat.reshape(256, *feat.shape[-2:])
+            h, w = feat.shape[-2:]
+            N = emb.shape[-2]
+            L = _lib.lib()
+            fg_pack = torch.cat([bn["fg_bn.weight"].reshape(1), bn["fg_bn.bias"].reshape(1),
+                                 bn["fg_bn.running_mean"].reshape(1), bn["fg_bn.running_var"].reshape(1)]).float().contiguous()
+            nbytes = C.c_size_t()
+            _lib.check(L.slotvps_mask_logits_workspace_bytes(N, h, w, C.byref(nbytes)), "mask_logits_workspace_bytes")
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=feat.device)
+            out = torch.empty((N, h, w), dtype=torch.float32, device=feat.device)
+            rc = L.slotvps_head_mask_logits(C.byref(d), hws.data_ptr(), hws.numel(), frame, feat.contiguous().data_ptr(),
+                                            emb.reshape(N, 256).contiguous().data_ptr(), bn["feat_bn.weight"].data_ptr(),
+                                            bn["feat_bn.bias"].data_ptr(), bn["feat_bn.running_mean"].data_ptr(),
+                                            bn["feat_bn.running_var"].data_ptr(), fg_pack.data_ptr(), out.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), _stream_ptr(feat.device))
+            if rc == 0:
+                return out
+            if rc != -4:
+                _lib.check(rc, "slotvps_head_mask_logits")
+        return mask_logits(feat, emb, bn)
+
     @torch.no_grad()
     def forward(self, features: List[List[torch.Tensor]], size: Tuple[int, int], pos="sine", fuse: bool = True,
                 fusion_logits: Optional[torch.Tensor] = None, panoptic_out: Optional[torch.Tensor] = None):
@@ -228,7 +257,7 @@ class SlotVPSRetriever(nn.Module):
         T = len(features)
         q = self.init_mask_query.weight
         cls, emb, feats = self.dynamic_mask_head(features, [q] * T, None, pos=pos)
-        pm = mask_logits(feats[-1][-1][0], emb[-1][-1, 0], self._bn_dict())
+        pm = self._mask_logits_after_head(feats[-1][-1][0], emb[-1][-1, 0], T - 1)
         out = dict(cls=cls, emb=emb, feats=feats, pred_masks=pm)
         if fuse:
             lg = cls[-1][-1, 0] if fusion_logits is None else fusion_logits

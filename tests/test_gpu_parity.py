@@ -252,3 +252,9 @@ def test_whole_clip_api_and_determinism(dev):
     for s in range(7):
         print(f"512x1024 stage {s}: tc-vs-fp32 path emb rel {rel(b['emb'][1][s], a['emb'][1][s]):.2e}")
     assert rel(b["emb"][1][0], a["emb"][1][0]) < TOL
+    # mask logits, teacher-forced on each path's own head outputs (tensor-core path reads the operand planes)
+    for name, o in (("fp32", a), ("tc", b)):
+        ref = O.mask_logits(o["feats"][1][3][0].double().cpu(), o["emb"][1][-1, 0].double().cpu(), {k: v.double() for k, v in cap.items()})
+        e = rel(o["pred_masks"], ref)
+        print(f"512x1024 mask logits ({name} path) vs fp64 oracle on the same inputs: rel {e:.2e}, max abs {float((o['pred_masks'].double().cpu() - ref).abs().max()):.2e}")
+        assert e < 1e-4
