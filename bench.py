@@ -273,20 +273,43 @@ def main():
         h2d = sum(f.numel() * 4 for fr in host_clips[0] for f in fr)
         d2h = h_pan.numel() * 8 + h_meta.numel() * 4
 
-        def e2e_step(i):
-            src = pinned[i % 2]
-            for t in range(T):
-                for l in range(4):
-                    stage[t][l].copy_(src[t][l], non_blocking=True)
-            o = graphs[0].replay() if graphs is not None else step(i, stage)
+        # Double-buffered upload: the copy stream moves clip i+1 into the other static input buffer while the
+        # compute stream runs clip i (both inside the timed region); results are read back every step.
+        bufs = dev_clips if graphs is not None else [stage, [[torch.empty_like(f, device=dev) for f in fr] for fr in host_clips[0]]]
+        copy_stream = torch.cuda.Stream()
+        up_done = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        main = torch.cuda.current_stream()
+
+        def upload(i):
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[b])                 # the step that last read this buffer has finished
+                for t in range(T):
+                    for l in range(4):
+                        bufs[b][t][l].copy_(pinned[i % 2][t][l], non_blocking=True)
+                up_done[b].record(copy_stream)
+
+        def e2e_step(i, last):
+            b = i % 2
+            if not last:
+                upload(i + 1)
+            main.wait_event(up_done[b])
+            o = graphs[b].replay() if graphs is not None else step(i, bufs[b])
+            free[b].record(main)
             h_pan.copy_(o["fusion"].panoptic, non_blocking=True)
             h_meta.copy_(o["fusion"].meta, non_blocking=True)
-        for i in range(max(1, Wm)):
-            e2e_step(i)
+
+        def e2e_run(n):
+            for b in range(2):
+                free[b].record(main)
+            upload(0)
+            for i in range(n):
+                e2e_step(i, i == n - 1)
+        e2e_run(max(2, Wm))
         barrier()
         e0.record()
-        for i in range(K):
-            e2e_step(i)
+        e2e_run(K)
         e1.record()
         barrier()
         ms2 = e0.elapsed_time(e1)
@@ -295,7 +318,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms2 = float(t.item())
         e2e = dict(value=world * K * T / (ms2 * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                   ms_per_step=ms2 / K)
+                   ms_per_step=ms2 / K, pipeline="upload of clip i+1 overlaps compute of clip i (2 static input buffers)")
 
     clocks = sampler.stop() if rank == 0 else None     # sampled over the timed region and the e2e region (both under load)
 

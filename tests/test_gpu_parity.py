@@ -258,3 +258,58 @@ def test_whole_clip_api_and_determinism(dev):
         e = rel(o["pred_masks"], ref)
         print(f"512x1024 mask logits ({name} path) vs fp64 oracle on the same inputs: rel {e:.2e}, max abs {float((o['pred_masks'].double().cpu() - ref).abs().max()):.2e}")
         assert e < 1e-4
+
+
+def test_fullsize_fusion_and_properties(dev):
+    """BASELINE full size (1024x2048, quarter-res masks 256x512): fusion id map vs the oracle, plus
+    size-independent properties: labels come from the kept set, areas add up, re-running is bit-identical."""
+    N, h, w = 100, 256, 512
+    H, W = 4 * h, 4 * w
+    logits, masks, _ = synthetic.make_fusion_case(21, N, h, w, n_things=15, near_dup_things=4, tiny=3)
+    fz = sv.PanopticFusion(**sv.FUSION_KWARGS)
+    fo = fz.fuse(logits.to(dev), masks.to(dev), (H, W))
+    got = fo.panoptic.cpu().numpy()
+    hst = fo.host()
+    fo2 = fz.fuse(logits.to(dev), masks.to(dev), (H, W))
+    assert np.array_equal(got, fo2.panoptic.cpu().numpy())                      # idempotent / deterministic
+    r = O.panoptic_fuse(logits, masks, (H, W))
+    np.testing.assert_array_equal(hst["keep"], r.keep)
+    np.testing.assert_array_equal(hst["labels"], r.labels)
+    diff = got != r.panoptic
+    print(f"1024x2048 fusion: kept {hst['k']} ({hst['n_things']} things), iters {hst['iters']}, id-map mismatches {int(diff.sum())} "
+          f"of {diff.size} (outside near-tie: {int((diff & ~r.near_tie).sum())}; near-tie pixels {int(r.near_tie.sum())})")
+    assert int((diff & ~r.near_tie).sum()) == 0
+    ids, counts = np.unique(got, return_counts=True)
+    n_stuff_labels = set(int(c) for c in r.labels if c <= 10)
+    assert set(ids.tolist()) <= n_stuff_labels | {11 + j for j in range(hst["n_things"])}
+    assert counts.sum() == H * W and counts.min() > 4                          # every surviving segment has area > 4
+
+
+def test_fullsize_clip_properties(dev):
+    """One 1024x2048 T=2 clip through the whole path: run-to-run bitwise determinism, identical frames give
+    identical slots on the frame-independent stages (0..2), fp32-vs-tensor-core agreement at stage 0."""
+    T, N, H, W = 2, 100, 1024, 2048
+    sd = synthetic.make_head_state_dict(0)
+    cap = synthetic.make_capsule_params(0, N)
+    one = synthetic.make_features(H, W, T=1, video=5, frame=0)[0]
+    feats = [[f.to(dev) for f in one], [f.to(dev) for f in one]]                # the same frame twice
+    lg = synthetic.make_fusion_case(0, N, 8, 8)[0].to(dev)
+    res = {}
+    for kp in (0, 1):
+        m = sv.SlotVPSRetriever({**sv.HEAD_KWARGS, "kernel_path": kp}, N, sv.FUSION_KWARGS)
+        m.dynamic_mask_head.load_state_dict(sd)
+        m.load_capsule_params(cap)
+        m = m.to(dev)
+        res[kp] = m(feats, (H, W), fusion_logits=lg)
+        if kp == 0:
+            again = m(feats, (H, W), fusion_logits=lg)
+            assert torch.equal(again["fusion"].panoptic, res[0]["fusion"].panoptic)
+            assert torch.equal(again["pred_masks"], res[0]["pred_masks"])
+    a = res[0]
+    assert a["fusion"].panoptic.shape == (H, W) and a["fusion"].panoptic.dtype == torch.int64
+    for s in range(3):                                                           # stages without the Video Retriever
+        assert torch.equal(a["emb"][0][s], a["emb"][1][s]), s
+    e0 = rel(a["emb"][1][0], res[1]["emb"][1][0])
+    e6 = rel(a["emb"][1][6], res[1]["emb"][1][6])
+    print(f"1024x2048: tensor-core vs fp32 path, stage 0 emb rel {e0:.2e}, stage 6 {e6:.2e}; kept {a['fusion'].host()['k']}")
+    assert e0 < 1e-4
