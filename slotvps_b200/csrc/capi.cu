@@ -641,14 +641,15 @@ int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, s
 struct FuseWs {
   FuseState* st;
   unsigned int* pair;
-  unsigned short *owner, *ids;
+  unsigned int* cand;        // per pixel: the (at most two) thing candidates with prob >= pixel_threshold
+  unsigned short* ids;
 };
 static size_t fuse_ws_layout(int N, int H, int W, void* base, size_t cap, FuseWs* out) {
   Arena a(base, cap);
   FuseWs w;
   w.st = a.take<FuseState>(1);
   w.pair = a.take<unsigned int>((size_t)N * N);
-  w.owner = a.take<unsigned short>((size_t)H * W);
+  w.cand = a.take<unsigned int>((size_t)H * W);
   w.ids = a.take<unsigned short>((size_t)H * W);
   if (out) *out = w;
   return align_up(a.off);
@@ -674,14 +675,17 @@ int slotvps_panoptic_fuse(const slotvps_fusion_cfg* cfg, const float* pred_logit
   SV_CHECK_CUDA(cudaMemsetAsync(meta, 0, (size_t)(4 + 3 * N) * sizeof(int32_t), s));
   fuse_select_kernel<<<1, FUSE_MAXN, 0, s>>>(pred_logits, N, cfg->num_classes, cfg->stuff_num, cfg->threshold, ws.st);
   SV_CHECK_LAUNCH("fuse_select");
-  fuse_count_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, cfg->pixel_threshold, ws.st, ws.pair);
+  const bool x4 = (H == 4 * h && W == 4 * w);              // the shipped case: 1/4-resolution masks
+  const long nblk = (long)h * w;
+  const int grid4 = (int)((nblk + 255) / 256 < 148 * 8 ? (nblk + 255) / 256 : 148 * 8);
+  if (x4) fuse_count4_kernel<<<grid4, 256, 0, s>>>(pred_masks, h, w, cfg->pixel_threshold, ws.st, ws.pair, ws.cand);
+  else fuse_count_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, cfg->pixel_threshold, ws.st, ws.pair, ws.cand);
   SV_CHECK_LAUNCH("fuse_count");
   fuse_greedy_kernel<<<1, 32, 0, s>>>(ws.st, ws.pair, HW, cfg->fraction_threshold);
   SV_CHECK_LAUNCH("fuse_greedy");
-  fuse_owner_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, cfg->pixel_threshold, ws.st, ws.owner);
-  SV_CHECK_LAUNCH("fuse_owner");
   for (int it = 0; it < cfg->max_iters; ++it) {
-    fuse_argmax_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, ws.st, ws.owner, ws.ids);
+    if (x4) fuse_argmax4_kernel<<<grid4, 256, 0, s>>>(pred_masks, h, w, ws.st, ws.cand, ws.ids);
+    else fuse_argmax_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, ws.st, ws.cand, ws.ids);
     SV_CHECK_LAUNCH("fuse_argmax");
     fuse_filter_kernel<<<1, FUSE_MAXN, 0, s>>>(ws.st, cfg->stuff_num, (unsigned)cfg->small_area, N, meta);
     SV_CHECK_LAUNCH("fuse_filter");
@@ -689,7 +693,7 @@ int slotvps_panoptic_fuse(const slotvps_fusion_cfg* cfg, const float* pred_logit
   fuse_relabel_kernel<<<grid, 256, 0, s>>>(ws.st, ws.ids, HW, (long long*)panoptic);
   SV_CHECK_LAUNCH("fuse_relabel");
   if (masks_out && masks_cap > 0) {
-    fuse_masks_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, ws.st, ws.owner, masks_out, masks_cap);
+    fuse_masks_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, ws.st, ws.cand, masks_out, masks_cap);
     SV_CHECK_LAUNCH("fuse_masks");
   }
   return SLOTVPS_OK;

@@ -23,7 +23,7 @@ constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 constexpr int NSTAGE = 2;
 constexpr int AUX_BYTES = 2048;
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + AUX_BYTES + 1024;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;                   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 constexpr uint32_t IDESC = tc::make_idesc_f16(128, 256, 0, 0);
 
 struct Params {
@@ -100,7 +100,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc::tma_prefetch_desc(&tmap_a);
     tc::tma_prefetch_desc(&tmap_w);
     for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 256); }
     tc::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < C; i += THREADS) bias[i] = prm.bias ? prm.bias[i] : 0.f;
@@ -156,6 +156,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else {
     const int q = warp & 3;
+    const int jhalf = (warp - 2) >> 2;                      // which half of the 256 output columns this warp drains
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t ti = 0;
@@ -181,11 +182,11 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc::mbar_wait(&tfull[g], u & 1);
       tc::tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < C / 32; ++j) {
+      for (int j = jhalf * 4; j < jhalf * 4 + 4; ++j) {
         float v[32];
         tc::tmem_ld32(tmem_base + lane_addr + g * 256 + j * 32, v);
         tc::tmem_ld_wait();
-        if (j == C / 32 - 1) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }      // accumulator drained
+        if (j == jhalf * 4 + 3) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }      // this warp's half is drained
         if (!rv) continue;
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] += bias[j * 32 + c];

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(FUSE_MAXN) fuse_select_kernel(const float* __r
 // ---- count: |B_i| and pair overlaps of thing candidates ------------------------------------------
 // pair [n_cand][n_cand] (global, zeroed by the caller); one thread per output pixel.
 __global__ void __launch_bounds__(256) fuse_count_kernel(const float* __restrict__ masks, int h, int w, int H, int W,
-                                                         float pix_thr, FuseState* __restrict__ st, unsigned int* __restrict__ pair) {
+                                                         float pix_thr, FuseState* __restrict__ st, unsigned int* __restrict__ pair, unsigned int* __restrict__ cand) {
   __shared__ unsigned int s_cnt[FUSE_MAXN];
   const int K = st->K, ns = st->n_stuff, nc = st->n_cand;
   for (int j = threadIdx.x; j < nc; j += 256) s_cnt[j] = 0;
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) fuse_count_kernel(const float* __restrict
     }
     if (c1 >= 0) atomicAdd(&s_cnt[c1], 1u);
     if (c2 >= 0) { atomicAdd(&s_cnt[c2], 1u); atomicAdd(&pair[c1 * nc + c2], 1u); atomicAdd(&pair[c2 * nc + c1], 1u); }
+    cand[pix] = (unsigned int)(c1 & 0xFFFF) | ((unsigned int)(c2 & 0xFFFF) << 16);
   }
   __syncthreads();
   for (int j = threadIdx.x; j < nc; j += 256) if (s_cnt[j]) atomicAdd(&st->cntB[j], s_cnt[j]);
@@ -183,38 +184,195 @@ __global__ void __launch_bounds__(32) fuse_greedy_kernel(FuseState* __restrict__
   if (lane == 0) { st->Kl = ns + nk; st->n_things_kept = nk; }
 }
 
-// ---- owner: first kept thing (in order) whose softmax prob over the K kept slots is >= 0.4 --------
-__global__ void __launch_bounds__(256) fuse_owner_kernel(const float* __restrict__ masks, int h, int w, int H, int W, float pix_thr,
-                                                         const FuseState* __restrict__ st, unsigned short* __restrict__ owner) {
-  const int K = st->K, ns = st->n_stuff;
-  const long P = (long)h * w;
-  const float sys = (float)h / H, sxs = (float)w / W;
-  const bool same = (h == H && w == W);
-  for (long pix = (long)blockIdx.x * 256 + threadIdx.x; pix < (long)H * W; pix += (long)gridDim.x * 256) {
-    const int y = (int)(pix / W), x = (int)(pix % W);
-    const Samp sp = samp_setup(y, x, h, w, sys, sxs, same);
-    float mx = -INFINITY;
-    for (int k = 0; k < K; ++k) mx = fmaxf(mx, sp.at(masks + (long)st->ord[k] * P));
-    float sum = 0.f;
-    for (int k = 0; k < K; ++k) sum += expf(sp.at(masks + (long)st->ord[k] * P) - mx);
-    int own = 0xFFFF;
-    for (int k = ns; k < K; ++k) {
-      if (st->thing_rank[k - ns] < 0) continue;
-      float p = expf(sp.at(masks + (long)st->ord[k] * P) - mx) / sum;
-      if (p >= pix_thr) { own = st->thing_rank[k - ns]; break; }
+// owner of a pixel = rank (among surviving things) of the first surviving candidate, or 0xFFFF
+__device__ __forceinline__ int owner_of(unsigned int cd, const int* __restrict__ rank) {
+  const int c1 = cd & 0xFFFF, c2 = cd >> 16;
+  if (c1 != 0xFFFF && rank[c1] >= 0) return rank[c1];
+  if (c2 != 0xFFFF && rank[c2] >= 0) return rank[c2];
+  return 0xFFFF;
+}
+
+// ---- x4 specialisation (H == 4h, W == 4w): one thread per 4x4 output block shares 3x3 source taps per slot.
+// The per-pixel arithmetic (tap indices, weights, association) is IDENTICAL to Samp::at, so results are
+// bit-identical to the generic kernels.
+struct Blk4 {
+  int r[3], c[3];            // clamped source rows / cols  (i-1, i, i+1), (j-1, j, j+1)
+  float ly0[4], ly1[4], lx0[4], lx1[4];
+  // Output row 4i+a taps source rows (i-1, i) for a < 2 and (i, i+1) for a >= 2 (same for columns).  At the
+  // borders the generic formula clamps the coordinate / the second tap; with the clamped rows r[] the static
+  // tap pairs then carry the generic weights onto the same texels, so every value is bit-identical.
+  __device__ __forceinline__ void setup(int i, int j, int h, int w) {
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { r[m] = min(max(i - 1 + m, 0), h - 1); c[m] = min(max(j - 1 + m, 0), w - 1); }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float sy = fmaxf(0.25f * (4 * i + a + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.25f * (4 * j + a + 0.5f) - 0.5f, 0.f);
+      int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1);
+      ly1[a] = sy - y0; ly0[a] = 1.f - ly1[a]; lx1[a] = sx - x0; lx0[a] = 1.f - lx1[a];
     }
-    owner[pix] = (unsigned short)own;
   }
+  // v[a*4+b] = value at output pixel (4i+a, 4j+b)
+  __device__ __forceinline__ void eval(const float* __restrict__ m, int w, float* v) const {
+    float t[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) t[a][b] = __ldg(m + r[a] * w + c[b]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int ra = a < 2 ? 0 : 1, cb = b < 2 ? 0 : 1;
+        v[a * 4 + b] = ly0[a] * (lx0[b] * t[ra][cb] + lx1[b] * t[ra][cb + 1]) + ly1[a] * (lx0[b] * t[ra + 1][cb] + lx1[b] * t[ra + 1][cb + 1]);
+      }
+  }
+  __device__ __forceinline__ float eval1(const float* __restrict__ m, int w, int a, int b) const {
+    const int ra = a < 2 ? 0 : 1, cb = b < 2 ? 0 : 1;
+    return ly0[a] * (lx0[b] * __ldg(m + r[ra] * w + c[cb]) + lx1[b] * __ldg(m + r[ra] * w + c[cb + 1])) +
+           ly1[a] * (lx0[b] * __ldg(m + r[ra + 1] * w + c[cb]) + lx1[b] * __ldg(m + r[ra + 1] * w + c[cb + 1]));
+  }
+};
+
+__global__ void __launch_bounds__(256) fuse_count4_kernel(const float* __restrict__ masks, int h, int w, float pix_thr,
+                                                          FuseState* __restrict__ st, unsigned int* __restrict__ pair,
+                                                          unsigned int* __restrict__ cand) {
+  __shared__ unsigned int s_cnt[FUSE_MAXN];
+  __shared__ int s_ord[FUSE_MAXN];
+  const int K = st->K, ns = st->n_stuff, nc = st->n_cand;
+  for (int j = threadIdx.x; j < FUSE_MAXN; j += 256) { s_cnt[j] = 0; s_ord[j] = j < K ? st->ord[j] : 0; }
+  __syncthreads();
+  const long P = (long)h * w;
+  const int W = 4 * w;
+  for (long blk = (long)blockIdx.x * 256 + threadIdx.x; blk < P; blk += (long)gridDim.x * 256) {
+    const int i = (int)(blk / w), j = (int)(blk % w);
+    Blk4 b4;
+    b4.setup(i, j, h, w);
+    float mx[16], sum[16], v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { mx[e] = -INFINITY; sum[e] = 0.f; }
+    for (int k = 0; k < K; ++k) {
+      b4.eval(masks + (long)s_ord[k] * P, w, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) mx[e] = fmaxf(mx[e], v[e]);
+    }
+    for (int k = 0; k < K; ++k) {
+      b4.eval(masks + (long)s_ord[k] * P, w, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) sum[e] += expf(v[e] - mx[e]);
+    }
+    unsigned int cd[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) cd[e] = 0xFFFFFFFFu;
+    for (int k = ns; k < K; ++k) {
+      b4.eval(masks + (long)s_ord[k] * P, w, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float p = expf(v[e] - mx[e]) / sum[e];
+        if (p >= pix_thr) {
+          const unsigned int c = (unsigned int)(k - ns);
+          if ((cd[e] & 0xFFFF) == 0xFFFF) cd[e] = (cd[e] & 0xFFFF0000u) | c;
+          else if ((cd[e] >> 16) == 0xFFFF) cd[e] = (cd[e] & 0xFFFFu) | (c << 16);
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      *reinterpret_cast<uint4*>(cand + (long)(4 * i + a) * W + 4 * j) = make_uint4(cd[a * 4], cd[a * 4 + 1], cd[a * 4 + 2], cd[a * 4 + 3]);
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const unsigned int c = cd[a * 4 + bb];
+        const int c1 = c & 0xFFFF, c2 = c >> 16;
+        if (c1 != 0xFFFF) atomicAdd(&s_cnt[c1], 1u);
+        if (c2 != 0xFFFF) { atomicAdd(&s_cnt[c2], 1u); atomicAdd(&pair[c1 * nc + c2], 1u); atomicAdd(&pair[c2 * nc + c1], 1u); }
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nc; j += 256) if (s_cnt[j]) atomicAdd(&st->cntB[j], s_cnt[j]);
+}
+
+__global__ void __launch_bounds__(256) fuse_argmax4_kernel(const float* __restrict__ masks, int h, int w, FuseState* __restrict__ st,
+                                                           const unsigned int* __restrict__ cand, unsigned short* __restrict__ ids) {
+  if (st->converged) return;
+  __shared__ unsigned int s_area[FUSE_MAXN];
+  __shared__ int s_rank[FUSE_MAXN], s_slot[FUSE_MAXN], s_act[FUSE_MAXN];
+  __shared__ int s_first_thing, s_second_thing;
+  const int Kl = st->Kl, ns = st->n_stuff, nc = st->n_cand;
+  for (int j = threadIdx.x; j < FUSE_MAXN; j += 256) {
+    s_area[j] = 0;
+    s_rank[j] = j < nc ? st->thing_rank[j] : -1;
+    s_slot[j] = j < Kl ? st->ord[st->list[j]] : 0;
+    s_act[j] = j < Kl ? st->active[j] : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int f = -1, s2 = -1;
+    for (int e = ns; e < Kl; ++e) if (s_act[e]) { if (f < 0) f = e; else if (s2 < 0) { s2 = e; break; } }
+    s_first_thing = f; s_second_thing = s2;
+  }
+  __syncthreads();
+  const int first_thing = s_first_thing, second_thing = s_second_thing;
+  const long P = (long)h * w;
+  const int W = 4 * w;
+  for (long blk = (long)blockIdx.x * 256 + threadIdx.x; blk < P; blk += (long)gridDim.x * 256) {
+    const int i = (int)(blk / w), j = (int)(blk % w);
+    Blk4 b4;
+    b4.setup(i, j, h, w);
+    float best[16], v[16];
+    int bi[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { best[e] = -INFINITY; bi[e] = -1; }
+    for (int s = 0; s < ns; ++s) {
+      if (!s_act[s]) continue;
+      b4.eval(masks + (long)s_slot[s] * P, w, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) if (v[e] > best[e]) { best[e] = v[e]; bi[e] = s; }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const uint4 cq = *reinterpret_cast<const uint4*>(cand + (long)(4 * i + a) * W + 4 * j);
+      const unsigned int cds[4] = {cq.x, cq.y, cq.z, cq.w};
+      unsigned short out4[4];
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const int e = a * 4 + bb;
+        float bst = best[e];
+        int b = bi[e];
+        if (first_thing >= 0) {
+          const int own = owner_of(cds[bb], s_rank);
+          const int oe = own == 0xFFFF ? -1 : ns + own;
+          const bool own_active = oe >= 0 && s_act[oe];
+          int ze = !own_active ? first_thing : ((first_thing != oe) ? first_thing : second_thing);
+          float tv = -INFINITY;
+          int te = -1;
+          if (own_active) {
+            tv = b4.eval1(masks + (long)s_slot[oe] * P, w, a, bb);
+            te = oe;
+          }
+          if (ze >= 0 && (0.f > tv || (0.f == tv && ze < te))) { tv = 0.f; te = ze; }
+          if (tv > bst) { bst = tv; b = te; }
+        }
+        out4[bb] = (unsigned short)b;
+        if (b >= 0) atomicAdd(&s_area[b], 1u);
+      }
+      *reinterpret_cast<uint2*>(ids + (long)(4 * i + a) * W + 4 * j) =
+          make_uint2((unsigned int)out4[0] | ((unsigned int)out4[1] << 16), (unsigned int)out4[2] | ((unsigned int)out4[3] << 16));
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Kl; j += 256) if (s_area[j]) atomicAdd(&st->area[j], s_area[j]);
 }
 
 // ---- argmax over the active kept slots of the masked logits ---------------------------------------
 // ids[pixel] = entry of the final list (uncompacted); lowest entry wins ties (torch argmax).
 __global__ void __launch_bounds__(256) fuse_argmax_kernel(const float* __restrict__ masks, int h, int w, int H, int W,
-                                                          FuseState* __restrict__ st, const unsigned short* __restrict__ owner,
+                                                          FuseState* __restrict__ st, const unsigned int* __restrict__ cand,
                                                           unsigned short* __restrict__ ids) {
   if (st->converged) return;
   __shared__ unsigned int s_area[FUSE_MAXN];
+  __shared__ int s_rank[FUSE_MAXN];
   __shared__ int s_first_thing, s_second_thing;
+  for (int j = threadIdx.x; j < FUSE_MAXN; j += 256) s_rank[j] = j < st->n_cand ? st->thing_rank[j] : -1;
   const int Kl = st->Kl, ns = st->n_stuff;
   for (int j = threadIdx.x; j < Kl; j += 256) s_area[j] = 0;
   if (threadIdx.x == 0) {
@@ -238,7 +396,7 @@ __global__ void __launch_bounds__(256) fuse_argmax_kernel(const float* __restric
       if (v > best) { best = v; bi = e; }
     }
     if (first_thing >= 0) {
-      const int own = owner[pix];
+      const int own = owner_of(cand[pix], s_rank);
       const int oe = own == 0xFFFF ? -1 : ns + own;            // entry of the owner (things keep their order)
       const bool own_active = oe >= 0 && st->active[oe];
       // all active things other than the owner carry exactly 0 here (:632-634)
@@ -337,8 +495,11 @@ __global__ void __launch_bounds__(256) fuse_relabel_kernel(const FuseState* __re
 
 // ---- optional: materialise Instances.masks (masked logits of the final kept slots) -------------------
 __global__ void __launch_bounds__(256) fuse_masks_kernel(const float* __restrict__ masks, int h, int w, int H, int W,
-                                                         const FuseState* __restrict__ st, const unsigned short* __restrict__ owner,
+                                                         const FuseState* __restrict__ st, const unsigned int* __restrict__ cand,
                                                          float* __restrict__ out, int cap) {
+  __shared__ int s_rank[FUSE_MAXN];
+  for (int j = threadIdx.x; j < FUSE_MAXN; j += 256) s_rank[j] = j < st->n_cand ? st->thing_rank[j] : -1;
+  __syncthreads();
   const int Kl = st->Kl, ns = st->n_stuff;
   const long P = (long)h * w, HW = (long)H * W;
   const float sys = (float)h / H, sxs = (float)w / W;
@@ -346,7 +507,7 @@ __global__ void __launch_bounds__(256) fuse_masks_kernel(const float* __restrict
   for (long pix = (long)blockIdx.x * 256 + threadIdx.x; pix < HW; pix += (long)gridDim.x * 256) {
     const int y = (int)(pix / W), x = (int)(pix % W);
     const Samp sp = samp_setup(y, x, h, w, sys, sxs, same);
-    const int own = owner[pix];
+    const int own = owner_of(cand[pix], s_rank);
     int c = 0;
     for (int e = 0; e < Kl && c < cap; ++e) {
       if (!st->active[e]) continue;
