@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    ap.add_argument("--inflight", type=int, default=4, help="clips in flight per GPU (independent clips on separate streams)")
     return ap.parse_args()
 
 
@@ -204,41 +205,64 @@ def main():
     T, N, H, W = args.frames, args.slots, args.height, args.width
     sd = synthetic.make_head_state_dict(0)
     cap = synthetic.make_capsule_params(0, N)
-    model = sv.SlotVPSRetriever({**sv.HEAD_KWARGS, "kernel_path": args.kernel_path}, N, sv.FUSION_KWARGS)
-    model.dynamic_mask_head.load_state_dict(sd, strict=True)
-    model.load_capsule_params(cap)
-    model = model.to(dev)
     fusion_logits = synthetic.make_fusion_case(0, N, 8, 8)[0].to(dev)
-    # two distinct clips per rank, alternated; one clip's inputs (178 MB at T=2) exceed the 126 MB L2
-    host_clips = [synthetic.make_features(H, W, T=T, video=10 * rank + i, frame=0) for i in range(2)]
-    dev_clips = [[[f.to(dev) for f in fr] for fr in clip] for clip in host_clips]
-    K, Wm = args.steps, args.warmup
-    pan = torch.empty((K, H, W), dtype=torch.int64, device=dev)
+    K, Wm, M = args.steps, args.warmup, max(1, args.inflight)
+    pan = torch.empty((K, H, W), dtype=torch.int64, device=dev) if world > 1 else None
     L = sv.lib()
 
-    def step(i, feats):
-        return model(feats, (H, W), pos="sine", fusion_logits=fusion_logits, panoptic_out=pan[i % K])
+    # Clips are independent, so M clips are kept in flight per GPU: lane j owns a model instance
+    # (its own workspaces), a resident input clip (178 MB at T=2: larger than the 126 MB L2), a stream and a
+    # CUDA graph of the whole step.  Step i runs on lane i % M.
+    class Lane:
+        pass
+    lanes = []
+    for j in range(M):
+        ln = Lane()
+        ln.model = sv.SlotVPSRetriever({**sv.HEAD_KWARGS, "kernel_path": args.kernel_path}, N, sv.FUSION_KWARGS)
+        ln.model.dynamic_mask_head.load_state_dict(sd, strict=True)
+        ln.model.load_capsule_params(cap)
+        ln.model = ln.model.to(dev)
+        ln.host = synthetic.make_features(H, W, T=T, video=10 * rank + j, frame=0)
+        ln.clip = [[f.to(dev) for f in fr] for fr in ln.host]
+        ln.stream = torch.cuda.Stream()
+        ln.graph = None if args.no_graph else sv.GraphedClip(ln.model, ln.clip, (H, W), pos="sine", fusion_logits=fusion_logits)
+        ln.end = torch.cuda.Event()
+        lanes.append(ln)
+    model = lanes[0].model
+    dev_clips = [ln.clip for ln in lanes]
 
-    graphs = None
-    if not args.no_graph:
-        # one graph per resident clip (static inputs); the id map lands in the graph's static output
-        graphs = [sv.GraphedClip(model, clip, (H, W), pos="sine", fusion_logits=fusion_logits) for clip in dev_clips]
+    def step(i, feats):                      # eager single-stream step (profiling pass)
+        return model(feats, (H, W), pos="sine", fusion_logits=fusion_logits)
 
-    def fast_step(i):
-        if graphs is None:
-            return step(i, dev_clips[i % 2])
-        o = graphs[i % 2].replay()
-        if dist is not None:
+    def lane_step(ln, i):
+        o = ln.graph.replay() if ln.graph is not None else ln.model(ln.clip, (H, W), pos="sine", fusion_logits=fusion_logits)
+        if pan is not None:
             pan[i % K].copy_(o["fusion"].panoptic, non_blocking=True)
         return o
+
+    main = torch.cuda.current_stream()
+    start = torch.cuda.Event()
+
+    def run(n, body):
+        start.record(main)
+        for ln in lanes:
+            ln.stream.wait_event(start)
+        out = None
+        for i in range(n):
+            ln = lanes[i % M]
+            with torch.cuda.stream(ln.stream):
+                out = body(ln, i)
+        for ln in lanes:
+            ln.end.record(ln.stream)
+            main.wait_event(ln.end)
+        return out
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(Wm):
-        fast_step(i)
+    run(max(Wm, M), lane_step)
     barrier()
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
     if rank == 0:
@@ -247,14 +271,13 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(K):
-        out = fast_step(i)
+    out = run(K, lane_step)
     if dist is not None:                                    # one all-gather of the shard's id maps
         gathered = torch.empty((world * K, H, W), dtype=pan.dtype, device=dev)
         dist.all_gather_into_tensor(gathered, pan)
     e1.record()
     barrier()
-    launches = int(L.slotvps_launch_count(0)) if graphs is None else K * graphs[0].launches
+    launches = int(L.slotvps_launch_count(0)) if lanes[0].graph is None else K * lanes[0].graph.launches
     ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([ms], device=dev)
@@ -263,53 +286,45 @@ def main():
     value = world * K * T / (ms * 1e-3)
     meta = out["fusion"].host()
 
+    # single clip in flight (latency view of the same step), for reference
+    single_ms = None
+    if M > 1:
+        keep, lanes[:] = lanes[:], lanes[:1]
+        M1, M = M, 1
+        run(max(2, Wm), lane_step)
+        barrier()
+        e0.record()
+        run(K, lane_step)
+        e1.record()
+        barrier()
+        single_ms = e0.elapsed_time(e1) / K
+        lanes[:] = keep
+        M = M1
+
     # ---- e2e: host buffers in, id map + meta out, every step -----------------------------------------
     e2e = None
     if not args.no_e2e:
-        pinned = [[[f.pin_memory() for f in fr] for fr in clip] for clip in host_clips]
-        stage = dev_clips[0] if graphs is not None else [[torch.empty_like(f, device=dev) for f in fr] for fr in host_clips[0]]
-        h_pan = torch.empty((H, W), dtype=torch.int64).pin_memory()
-        h_meta = torch.empty(4 + 3 * N, dtype=torch.int32).pin_memory()
-        h2d = sum(f.numel() * 4 for fr in host_clips[0] for f in fr)
-        d2h = h_pan.numel() * 8 + h_meta.numel() * 4
+        for ln in lanes:
+            ln.pinned = [[f.pin_memory() for f in fr] for fr in ln.host]
+            ln.h_pan = torch.empty((H, W), dtype=torch.int64).pin_memory()
+            ln.h_meta = torch.empty(4 + 3 * N, dtype=torch.int32).pin_memory()
+        h2d = sum(f.numel() * 4 for fr in lanes[0].host for f in fr)
+        d2h = lanes[0].h_pan.numel() * 8 + lanes[0].h_meta.numel() * 4
 
-        # Double-buffered upload: the copy stream moves clip i+1 into the other static input buffer while the
-        # compute stream runs clip i (both inside the timed region); results are read back every step.
-        bufs = dev_clips if graphs is not None else [stage, [[torch.empty_like(f, device=dev) for f in fr] for fr in host_clips[0]]]
-        copy_stream = torch.cuda.Stream()
-        up_done = [torch.cuda.Event() for _ in range(2)]
-        free = [torch.cuda.Event() for _ in range(2)]
-        main = torch.cuda.current_stream()
-
-        def upload(i):
-            b = i % 2
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(free[b])                 # the step that last read this buffer has finished
-                for t in range(T):
-                    for l in range(4):
-                        bufs[b][t][l].copy_(pinned[i % 2][t][l], non_blocking=True)
-                up_done[b].record(copy_stream)
-
-        def e2e_step(i, last):
-            b = i % 2
-            if not last:
-                upload(i + 1)
-            main.wait_event(up_done[b])
-            o = graphs[b].replay() if graphs is not None else step(i, bufs[b])
-            free[b].record(main)
-            h_pan.copy_(o["fusion"].panoptic, non_blocking=True)
-            h_meta.copy_(o["fusion"].meta, non_blocking=True)
-
-        def e2e_run(n):
-            for b in range(2):
-                free[b].record(main)
-            upload(0)
-            for i in range(n):
-                e2e_step(i, i == n - 1)
-        e2e_run(max(2, Wm))
+        def e2e_step(ln, i):
+            # upload this step's clip from pinned host memory into the lane's input buffers, run, read results back;
+            # the other lanes' uploads / downloads overlap this lane's compute
+            for t in range(T):
+                for l in range(4):
+                    ln.clip[t][l].copy_(ln.pinned[t][l], non_blocking=True)
+            o = lane_step(ln, i)
+            ln.h_pan.copy_(o["fusion"].panoptic, non_blocking=True)
+            ln.h_meta.copy_(o["fusion"].meta, non_blocking=True)
+            return o
+        run(max(2, Wm, M), e2e_step)
         barrier()
         e0.record()
-        e2e_run(K)
+        run(K, e2e_step)
         e1.record()
         barrier()
         ms2 = e0.elapsed_time(e1)
@@ -318,8 +333,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms2 = float(t.item())
         e2e = dict(value=world * K * T / (ms2 * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                   ms_per_step=ms2 / K, pipeline="upload of clip i+1 overlaps compute of clip i (2 static input buffers)")
-
+                   ms_per_step=ms2 / K, pipeline=f"{M} clips in flight: a lane's upload/readback overlaps the other lanes' compute")
     clocks = sampler.stop() if rank == 0 else None     # sampled over the timed region and the e2e region (both under load)
 
     # ---- per-kernel device times (CUDA events on the launching stream) -> roofline ----------------------
@@ -333,7 +347,7 @@ def main():
         torch.cuda.synchronize()
         L.slotvps_profile_begin(torch.cuda.current_stream(dev).cuda_stream)
         for i in range(nprof):
-            step(i, dev_clips[i % 2])
+            step(i, dev_clips[i % len(dev_clips)])
         L.slotvps_profile_end(buf, len(buf))
         rows = [r.split("\t") for r in buf.value.decode().strip().split("\n") if r]
         breakdown = {r[0]: dict(launches_per_step=int(r[1]) / nprof, ms_per_step=float(r[2]) / nprof) for r in rows}
@@ -358,7 +372,27 @@ def main():
         P3 = shapes[3][0] * shapes[3][1]
         ml = [k for k in breakdown if k in ("mask_prep", "feat_rnorm", "mask_logits_tc")]
         if roofline is not None:
-            roofline["hbm_stages"] = {"peak_gbs": pk["hbm_gbs"]}
+            step_ms = single_ms if single_ms else ms / K
+            roofline["share_of_step"] = roofline["ms_per_step"] / step_ms        # vs the single-clip-in-flight step time
+            hb = {"peak_gbs": pk["hbm_gbs"], "peak_source": pk["source"] + " copy bandwidth"}
+            if "mask_tc" in breakdown:      # mask-logit projection: read 4*C*P3 (as 2 fp16 hi/lo planes = same bytes) + write 4*N*P3
+                by = 4 * 256 * P3 + 4 * N * P3
+                t_ms = breakdown["mask_tc"]["ms_per_step"]
+                hb["mask_logits"] = dict(kernel="mask_tc", algorithmic_bytes=by, ms=t_ms, achieved_gbs=by / (t_ms * 1e-3) / 1e9,
+                                         frac=by / (t_ms * 1e-3) / 1e9 / pk["hbm_gbs"])
+            fk = [k for k in breakdown if k.startswith("fuse_") and k != "fuse_tc"]
+            if fk:                          # fusion, exact two-pass form: 2*4*Kept*P3 read + 8*H*W written
+                by = 2 * 4 * meta["k"] * P3 + 8 * H * W
+                t_ms = sum(breakdown[k]["ms_per_step"] for k in fk)
+                hb["panoptic_fusion"] = dict(kernels=fk, kept_slots=meta["k"], algorithmic_bytes=by, ms=t_ms,
+                                             achieved_gbs=by / (t_ms * 1e-3) / 1e9, frac=by / (t_ms * 1e-3) / 1e9 / pk["hbm_gbs"])
+            if "fuse_tc" in breakdown:      # level fusion: read 4*128*P + write 4*256*P (fp32 feature) + 4 fp16 planes, per frame & level
+                px_all = sum(h * w for (h, w) in shapes) * T
+                by = px_all * (4 * 128 + 4 * 256 + 4 * 2 * 256)
+                t_ms = breakdown["fuse_tc"]["ms_per_step"]
+                hb["level_fusion"] = dict(kernel="fuse_tc", algorithmic_bytes=by, ms=t_ms, achieved_gbs=by / (t_ms * 1e-3) / 1e9,
+                                          frac=by / (t_ms * 1e-3) / 1e9 / pk["hbm_gbs"])
+            roofline["hbm_stages"] = hb
 
     # ---- CPU baseline beside it (rank 0, N == 1) ------------------------------------------------------------
     cpu = None
@@ -371,9 +405,10 @@ def main():
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=f"r50_fpn_slotvps retriever, single {H}x{W} clip, T={T}, N={N}, 7 stages (BASELINE configs[1])",
                                 frames_convention="retriever frames/s = T * clips/s; output frames/s = clips/s",
-                                l2="inputs larger than L2 (178 MB/clip), two clips alternated",
+                                l2="inputs larger than L2 (178 MB/clip); one resident clip per lane, lanes alternate",
                                 fusion_logits="designed (random-init heads keep no slot)",
-                                kernel_path=args.kernel_path, cuda_graph=graphs is not None, sharding="clips per rank, one all_gather of id maps" if world > 1 else "single GPU",
+                                kernel_path=args.kernel_path, cuda_graph=not args.no_graph, clips_in_flight=M,
+                                single_clip_in_flight_ms_per_step=single_ms, sharding="clips per rank, one all_gather of id maps" if world > 1 else "single GPU",
                                 kept_slots=meta["k"], fusion_iters=meta["iters"]),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
                     kernel_breakdown_ms_per_step=breakdown)

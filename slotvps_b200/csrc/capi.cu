@@ -1,7 +1,9 @@
 // C ABI of libslotvps_b200.so (see include/slotvps_b200.h) and the host-side orchestration of the
 // retriever hot path: level fusion -> per-stage slot update / pixel attention -> mask logits ->
 // panoptic fusion.  One translation unit; kernels live in the .cuh files next to it.
+#include <stdlib.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -127,6 +129,7 @@ static int dcopy(const float* src, float* dst, long n, cudaStream_t s) {
 // ---- workspace of one head invocation ----------------------------------------------------------------
 struct HeadWs {
   float *slots, *qkv, *mo, *p, *qraw, *qt, *g0, *g1, *G;
+  float *rs_k2, *rs_v2;                 // second LayerNorm-scale buffers (stages alternate in overlapped mode)
   float *rs_k, *rs_v, *Zpart, *a0part, *a1part, *Z, *a0, *a1, *Y, *p2, *hdn, *f, *f2;
   float *tqkv, *L, *av, *ty, *thdn, *tw, *c2, *e1;
   float *pos[SLOTVPS_MAX_LEVELS];       // generated sine embeddings (pos_mode 2)
@@ -154,6 +157,7 @@ static size_t head_ws_layout(const slotvps_head_desc* d, void* base, size_t cap,
   w.p = a.take<float>((size_t)R * C); w.qraw = a.take<float>((size_t)R * C); w.qt = a.take<float>((size_t)R * C);
   w.g0 = a.take<float>(R); w.g1 = a.take<float>(R); w.G = a.take<float>((size_t)R * C);
   w.rs_k = a.take<float>((size_t)T * Pmax); w.rs_v = a.take<float>((size_t)T * Pmax);
+  w.rs_k2 = a.take<float>((size_t)T * Pmax); w.rs_v2 = a.take<float>((size_t)T * Pmax);
   w.Zpart = a.take<float>((size_t)chunks * R * C); w.a0part = a.take<float>((size_t)chunks * R); w.a1part = a.take<float>((size_t)chunks * R);
   w.Z = a.take<float>((size_t)R * C); w.a0 = a.take<float>(R); w.a1 = a.take<float>(R);
   w.Y = a.take<float>((size_t)R * C); w.p2 = a.take<float>((size_t)R * C);
@@ -174,6 +178,42 @@ static size_t head_ws_layout(const slotvps_head_desc* d, void* base, size_t cap,
   if (out) *out = w;
   return align_up(a.off);
 }
+
+// ---- two-stream schedule ---------------------------------------------------------------------------------
+// The slot-side chain of a stage is ~30 short dependent kernels on few SMs; the pixel-side producers
+// (level fusion, LayerNorm statistics) only depend on features.  In overlapped mode they run on an
+// internal side stream with a reduced grid, the attention kernel joins both (events), so the tensor-pipe
+// work hides behind the latency-bound slot chain.  Captured CUDA graphs keep the fork/join structure.
+struct Overlap {
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> ev;
+  int next = 0;
+  int init() {
+    if (!side) SV_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    while (ev.size() < 64) {
+      cudaEvent_t e;
+      SV_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ev.push_back(e);
+    }
+    next = 0;
+    return SLOTVPS_OK;
+  }
+  cudaEvent_t take() { return ev[next++ % ev.size()]; }
+};
+// A small pool of side streams handed out round-robin, created on the first (never captured: callers warm up
+// before capturing) call, so concurrent clips on different caller streams do not serialise on one side stream.
+static thread_local Overlap g_ovs[4];
+static thread_local unsigned g_ov_next = 0;
+static Overlap& overlap_next() { return g_ovs[g_ov_next++ % 4]; }
+static thread_local bool g_last_head_alt = false;   // did the last head_forward leave the finest level in planes_alt?
+constexpr int SIDE_CTAS = 112;           // tensor-core producers leave 36 SMs to the slot-side kernels
+
+struct StagePix {                        // how a stage gets its pixel-side inputs
+  bool overlapped = false;               // true: rs_k/rs_v are produced on the side stream, wait for `ready`
+  cudaEvent_t ready = nullptr, done = nullptr;
+  float *rs_k = nullptr, *rs_v = nullptr;
+  TcWorkspace tc;
+};
 
 // ---- level fusion (dynamic_mask_head.py:172-185), folded: W.cat(up(p),x) = up(Wa.p) + Wb.x ----------
 static int level_fuse_frame(const float* prev, const float* x, const float* conv_w, const float* conv_b, const float* W0,
@@ -204,8 +244,12 @@ static int level_fuse_frame(const float* prev, const float* x, const float* conv
 // (use_tc: the LayerNorm statistics -- 72 % of the contraction's FLOPs -- run on the tensor pipe from the
 //  level's bf16 operand planes, pixel_tc.cuh; the slot-softmax contraction below still runs in fp32)
 static int pixel_attention(const float* x, long x_bs, const float* pos, long pos_bs, const PreparedStage& ps,
-                           const HeadWs& w, int T, int N, int P, bool use_tc, cudaStream_t s) {
-  if (use_tc) {
+                           const HeadWs& w0, const StagePix& px, int T, int N, int P, bool use_tc, cudaStream_t s) {
+  HeadWs w = w0;
+  w.rs_k = px.rs_k; w.rs_v = px.rs_v; w.tc = px.tc;
+  if (px.overlapped) {
+    SV_CHECK_CUDA(cudaStreamWaitEvent(s, px.ready, 0));      // statistics of this stage were produced on the side stream
+  } else if (use_tc) {
     SV_TRY(tc_stats(ps.tc, w.tc, ps.bk_c, ps.bv_c, w.rs_k, w.rs_v, T, P, s));
   } else {
     dim3 gs(ceil_div(P, 32), T);
@@ -242,6 +286,7 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
 #undef SV_ATT
     SV_CHECK_LAUNCH("slot_attn_fp32");
   }
+  if (px.overlapped) SV_CHECK_CUDA(cudaEventRecord(px.done, s));   // planes / rs buffers of this stage may be recycled
   const long nz = (long)T * N * C, na = (long)T * N;
   reduce_attn_parts_kernel<<<(unsigned)((nz + 2 * na + 255) / 256), 256, 0, s>>>(w.Zpart, w.a0part, w.a1part, w.Z, w.a0, w.a1, nz, na, chunks);
   SV_CHECK_LAUNCH("reduce_attn_parts");
@@ -250,7 +295,7 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
 
 // ---- one MaskRCNNHead stage for all frames (dynamic_mask_head.py:291-400) ------------------------------
 static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp, const PreparedStage& ps, const HeadWs& w,
-                     const float* x, long x_bs, const float* pos, long pos_bs, int h, int wd, bool temporal, bool use_tc,
+                     const StagePix& px, const float* x, long x_bs, const float* pos, long pos_bs, int h, int wd, bool temporal, bool use_tc,
                      float* cls_out /*[T][S][N][K] base at this stage*/, long cls_frame_stride,
                      float* emb_out, long emb_frame_stride, cudaStream_t s) {
   const int T = d->n_frames, N = d->n_slots, R = T * N, P = h * wd, F = d->dim_feedforward, TF = d->temporal_dim_feedforward;
@@ -274,7 +319,7 @@ static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp,
   SV_CHECK_LAUNCH("q_post");
   SV_TRY(linear_fast(w.qt, ps.Wk_cT, nullptr, w.G, R, C, C, 0, nullptr, s));     // G = qt . Wk_c  (Wk_cT = Wk_c^T, [c][o])
   // (3) pixel side: Z, a0, a1
-  SV_TRY(pixel_attention(x, x_bs, pos, pos_bs, ps, w, T, N, P, use_tc, s));
+  SV_TRY(pixel_attention(x, x_bs, pos, pos_bs, ps, w, px, T, N, P, use_tc, s));
   // (4) value projection on the pixel-reduced slots, norm1/ReLU, residual, norm2 (:456-459, 374-376)
   SV_TRY(linear_fast(w.Z, ps.Wv_c, nullptr, w.Y, R, C, C, 0, nullptr, s));
   attn_post_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.Y, w.a0, w.a1, w.p, sp.nv_w, sp.nv_b, ps.bv_c, sp.no_w, sp.no_b,
@@ -466,6 +511,22 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
   }
   for (int t = 0; t < T; ++t) SV_TRY(dcopy(init_query[t], w.slots + (long)t * N * C, (long)N * C, s));
   const long cls_fs = (long)S * N * d->num_classes, emb_fs = (long)S * N * C;
+  // Overlapped (two-stream) schedule when every level runs the tensor-core kernels end to end.
+  bool overlap = d->kernel_path == 0 && N <= attn::NROW;
+  for (int l = 0; l < L; ++l) overlap = overlap && tc_supported(d, l) && d->heads_per_level[l] > 0;
+  if (getenv("SLOTVPS_NO_OVERLAP") || g_prof_on) overlap = false;     // per-launch event timing needs one stream
+  cudaStream_t sb = s;
+  cudaEvent_t ev_attn[SLOTVPS_MAX_STAGES] = {nullptr};       // attention of stage i finished (main stream)
+  int last_stage_of_level[SLOTVPS_MAX_LEVELS] = {0};
+  Overlap& g_ov = overlap_next();
+  if (overlap) {
+    for (auto& o : g_ovs) SV_TRY(o.init());
+    sb = g_ov.side;
+    cudaEvent_t fork = g_ov.take();
+    SV_CHECK_CUDA(cudaEventRecord(fork, s));
+    SV_CHECK_CUDA(cudaStreamWaitEvent(sb, fork, 0));
+  }
+  const int side_ctas = overlap ? SIDE_CTAS : 148;
   int stage = 0;
   bool prev_planes = false;
   for (int l = 0; l < L; ++l) {
@@ -473,6 +534,8 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
     const bool use_tc = d->kernel_path == 0 && tc_supported(d, l);
     const bool all_tc = use_tc && N <= attn::NROW;          // no fp32 kernel touches pos at this level
     const bool fuse_tc = use_tc && (l == 0 || prev_planes);  // the coarse GEMM reads the previous level's planes
+    TcWorkspace tcl = w.tc, tcp = w.tc;                      // this level's / the previous level's operand planes
+    if (overlap) { tcl.planes = (l & 1) ? w.tc.planes_alt : w.tc.planes; tcp.planes = (l & 1) ? w.tc.planes : w.tc.planes_alt; }
     const float* pl = nullptr;
     long pls = 0;
     if (d->pos_mode == 1) { pl = pos[l]; pls = pstride[l]; }
@@ -482,7 +545,9 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
       pl = w.pos[l]; pls = 0;
     }
     if (fuse_tc) {
-      // ---- level fusion on the tensor pipe; the epilogue also emits the fp16 operand planes ----
+      // ---- level fusion on the tensor pipe (side stream when overlapped); the epilogue also emits the operand planes ----
+      cudaStream_t s = sb;                                  // shadows the main stream inside this block
+      if (overlap && l >= 2) SV_CHECK_CUDA(cudaStreamWaitEvent(sb, ev_attn[last_stage_of_level[l - 2]], 0));   // planes[l&1] are free again
       const long rows = (long)T * P;
       Ptr8 src;
       for (int t = 0; t < SLOTVPS_MAX_FRAMES; ++t) src.p[t] = t < T ? feats[t * L + l] : nullptr;
@@ -495,33 +560,58 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
         const long rp = (long)T * Pp;
         prm.rows = (int)rp; prm.P = Pp; prm.w = d->w[l - 1]; prm.h = d->h[l - 1]; prm.ksub = 4; prm.a_lo_row = (int)rp;
         prm.y_out = w.ftc.y;
-        SV_TRY(fuse_tc_launch(w.tc.planes, 2 * rp, (int)rp, C, pr.ftc.wa, prm, s));
+        SV_TRY(fuse_tc_launch(tcp.planes, 2 * rp, (int)rp, C, pr.ftc.wa, prm, s, side_ctas));
         memset(&prm, 0, sizeof(prm));
       }
       prm.rows = (int)rows; prm.P = P; prm.w = wd; prm.h = h; prm.ksub = 2; prm.a_lo_row = (int)rows;
       prm.bias = pr.conv_b; prm.y_in = l > 0 ? w.ftc.y : nullptr;
       prm.out = fused_out[l]; prm.out_bs = fstride[l];
-      prm.planes = w.tc.planes; prm.plane_stride = rows;
+      prm.planes = tcl.planes; prm.plane_stride = rows;
       if (d->pos_mode == 1) { prm.pos = pos[l]; prm.pos_bs = pstride[l]; }
       else if (d->pos_mode == 2) {
         pos_tab_kernel<<<ceil_div(128 * (h + wd), 256), 256, 0, s>>>(w.tc.ytab, w.tc.xtab, h, wd);
         SV_CHECK_LAUNCH("pos_tab");
         prm.ytab = w.tc.ytab; prm.xtab = w.tc.xtab;
       }
-      SV_TRY(fuse_tc_launch(w.ftc.in_planes, 2 * rows, (int)rows, CIN, l > 0 ? pr.ftc.wb : pr.ftc.w0, prm, s));
+      SV_TRY(fuse_tc_launch(w.ftc.in_planes, 2 * rows, (int)rows, CIN, l > 0 ? pr.ftc.wb : pr.ftc.w0, prm, s, side_ctas));
     } else {
       for (int t = 0; t < T; ++t)
         SV_TRY(level_fuse_frame(l > 0 ? fused_out[t * L + l - 1] : nullptr, feats[t * L + l], pr.conv_w, pr.conv_b, pr.W0,
                                 fused_out[t * L + l], h, wd, w.ybuf + (long)t * C * (P / 4 + 1), s));
       if (use_tc && d->heads_per_level[l] > 0)
-        SV_TRY(tc_split_level(fused_out[l], fstride[l], pl, pls, d->pos_mode == 2 && all_tc, w.tc, T, h, wd, s));
+        SV_TRY(tc_split_level(fused_out[l], fstride[l], pl, pls, d->pos_mode == 2 && all_tc, tcl, T, h, wd, s));
     }
     prev_planes = fuse_tc || (use_tc && d->heads_per_level[l] > 0);
+    // ---- per-stage pixel inputs; in overlapped mode the statistics of every stage of the level are queued now ----
+    StagePix px[SLOTVPS_MAX_STAGES];
+    for (int j = 0; j < d->heads_per_level[l]; ++j) {
+      const int st = stage + j;
+      StagePix& q = px[j];
+      q.tc = tcl;
+      q.rs_k = (overlap && (st & 1)) ? w.rs_k2 : w.rs_k;
+      q.rs_v = (overlap && (st & 1)) ? w.rs_v2 : w.rs_v;
+      if (overlap) {
+        q.overlapped = true;
+        q.ready = g_ov.take(); q.done = g_ov.take();
+        ev_attn[st] = q.done;
+        cudaStream_t s = sb;
+        if (st >= 2) SV_CHECK_CUDA(cudaStreamWaitEvent(sb, ev_attn[st - 2], 0));     // rs buffers of parity st&1 are free again
+        SV_TRY(tc_stats(pr.st[st].tc, tcl, pr.st[st].bk_c, pr.st[st].bv_c, q.rs_k, q.rs_v, T, P, s, side_ctas));
+        SV_CHECK_CUDA(cudaEventRecord(q.ready, sb));
+      }
+    }
     for (int j = 0; j < d->heads_per_level[l]; ++j, ++stage) {
       const bool temporal = (d->temporal_mask >> stage) & 1;
-      SV_TRY(run_stage(d, stages[stage], pr.st[stage], w, fused_out[l], fstride[l], pl, pls, h, wd, temporal, use_tc,
+      SV_TRY(run_stage(d, stages[stage], pr.st[stage], w, px[j], fused_out[l], fstride[l], pl, pls, h, wd, temporal, use_tc,
                        cls_out + (long)stage * N * d->num_classes, cls_fs, emb_out + (long)stage * N * C, emb_fs, s));
     }
+    last_stage_of_level[l] = stage - 1;
+  }
+  g_last_head_alt = overlap && ((L - 1) & 1);
+  if (overlap) {                                            // join: fused_out / planes written on the side stream
+    cudaEvent_t join = g_ov.take();
+    SV_CHECK_CUDA(cudaEventRecord(join, sb));
+    SV_CHECK_CUDA(cudaStreamWaitEvent(s, join, 0));
   }
   return SLOTVPS_OK;
 }
@@ -634,7 +724,9 @@ int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, s
   g_planes_kernel<<<(unsigned)(((long)mask::NROW * C + 255) / 256), 256, 0, s>>>(e2, ep, N, 1);
   SV_CHECK_LAUNCH("g_planes");
   const long rows = (long)d->n_frames * P;
-  return mask_tc_launch(hw.tc.planes, 2 * rows, rows, (long)frame * P, ep, dn, rn, aff, out, N, P, s);
+  // the finest level used the alternate plane set iff the head call ran the overlapped schedule (recorded by it)
+  const __half* planes = g_last_head_alt ? hw.tc.planes_alt : hw.tc.planes;
+  return mask_tc_launch(planes, 2 * rows, rows, (long)frame * P, ep, dn, rn, aff, out, N, P, s);
 }
 
 // ---- panoptic fusion ----------------------------------------------------------------------------------
@@ -741,7 +833,9 @@ int slotvps_slot_attention(const slotvps_stage_params* sp, const float* slots_p,
   SV_TRY(linear_fast(w.qt, ps.Wk_cT, nullptr, w.G, N, C, C, 0, nullptr, s));
   const bool use_tc = kernel_path == 0 && tc_supported(&d, 0);
   if (use_tc) SV_TRY(tc_split_level(x, 0, pos, 0, false, w.tc, 1, h, wd, s));
-  SV_TRY(pixel_attention(x, 0, pos, 0, ps, w, 1, N, P, use_tc, s));
+  StagePix px;
+  px.rs_k = w.rs_k; px.rs_v = w.rs_v; px.tc = w.tc;
+  SV_TRY(pixel_attention(x, 0, pos, 0, ps, w, px, 1, N, P, use_tc, s));
   SV_TRY(linear(w.Z, ps.Wv_c, nullptr, w.Y, N, C, C, 0, nullptr, s));
   attn_post_kernel<<<ceil_div(N, 8), 256, 0, s>>>(w.Y, w.a0, w.a1, nullptr, sp->nv_w, sp->nv_b, ps.bv_c, sp->no_w, sp->no_b,
                                                    nullptr, nullptr, out, nullptr, N);

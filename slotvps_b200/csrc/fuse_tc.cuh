@@ -265,7 +265,7 @@ struct FuseTcWorkspace {
 };
 
 inline int fuse_tc_launch(const __half* a_planes, long a_rows_total, int a_lo_row, int K, const __half* w_planes, const fuse::Params& prm,
-                          cudaStream_t s) {
+                          cudaStream_t s, int max_ctas = 148) {
   CUtensorMap ma, mw;
   SV_TRY(tc::make_tmap_h16_sw128(&ma, a_planes, (uint64_t)a_rows_total, (uint64_t)K, fuse::TILE_M));
   SV_TRY(tc::make_tmap_h16_sw128(&mw, w_planes, (uint64_t)2 * C, (uint64_t)K, C));
@@ -275,7 +275,7 @@ inline int fuse_tc_launch(const __half* a_planes, long a_rows_total, int a_lo_ro
     attr_done = true;
   }
   const int n_tiles = ceil_div(prm.rows, fuse::TILE_M);
-  const int grid = n_tiles < 148 ? n_tiles : 148;
+  const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
   fuse_tc_kernel<<<grid, fuse::THREADS, fuse::SMEM_BYTES, s>>>(ma, mw, prm);
   SV_CHECK_LAUNCH("fuse_tc");
   return SLOTVPS_OK;

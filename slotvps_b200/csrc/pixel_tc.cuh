@@ -22,6 +22,7 @@ struct TcStageOperands {
 };
 struct TcWorkspace {
   __half* planes = nullptr;      // [4][T*Pmax][256]: x hi, x lo, (x+pos) hi, (x+pos) lo
+  __half* planes_alt = nullptr;  // second plane set: levels alternate so the next level's fusion can overlap this level's stages
   float *ytab = nullptr, *xtab = nullptr;  // separable sine tables [128][hmax], [128][wmax]
   __half* gplanes = nullptr;     // [T][2][112][256] folded query operand G, hi/lo
   long plane_rows = 0;                  // rows allocated per plane (T*Pmax)
@@ -38,6 +39,7 @@ inline void tc_workspace_layout(Arena& a, const slotvps_head_desc* d, TcWorkspac
   w->plane_rows = (long)d->n_frames * Pmax;
   if (d->kernel_path == 0) {
     w->planes = a.take<__half>((size_t)4 * w->plane_rows * C);
+    w->planes_alt = a.take<__half>((size_t)4 * w->plane_rows * C);
     w->ytab = a.take<float>((size_t)128 * hmax);
     w->xtab = a.take<float>((size_t)128 * wmax);
     w->gplanes = a.take<__half>((size_t)d->n_frames * 2 * 112 * C);
@@ -282,7 +284,7 @@ inline int tc_split_level(const float* x, long x_bs, const float* pos, long pos_
 
 // rs_k, rs_v [T][P] from the planes of this level and the stage's weight planes
 inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const float* bk_c, const float* bv_c, float* rs_k, float* rs_v,
-                    int T, int P, cudaStream_t s) {
+                    int T, int P, cudaStream_t s, int max_ctas = 148) {
   CUtensorMap mx, mw;
   const long rows = (long)T * P;
   SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)4 * rows, C, stats::TILE_M));
@@ -294,7 +296,7 @@ inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const flo
   }
   const int tiles_per_frame = ceil_div(P, stats::TILE_M);
   const int n_tiles = T * tiles_per_frame;
-  const int grid = n_tiles < 148 ? n_tiles : 148;
+  const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
   stats_tc_kernel<<<grid, stats::THREADS, stats::SMEM_BYTES, s>>>(mx, mw, bk_c, bv_c, rs_k, rs_v, P, T, (int)rows, tiles_per_frame);
   SV_CHECK_LAUNCH("stats_tc");
   return SLOTVPS_OK;
