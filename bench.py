@@ -199,6 +199,8 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the single JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -277,7 +279,7 @@ def main():
         dist.all_gather_into_tensor(gathered, pan)
     e1.record()
     barrier()
-    launches = int(L.slotvps_launch_count(0)) if lanes[0].graph is None else K * lanes[0].graph.launches
+    launches = world * (int(L.slotvps_launch_count(0)) if lanes[0].graph is None else K * lanes[0].graph.launches)
     ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([ms], device=dev)
