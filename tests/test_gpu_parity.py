@@ -313,3 +313,95 @@ def test_fullsize_clip_properties(dev):
     e6 = rel(a["emb"][1][6], res[1]["emb"][1][6])
     print(f"1024x2048: tensor-core vs fp32 path, stage 0 emb rel {e0:.2e}, stage 6 {e6:.2e}; kept {a['fusion'].host()['k']}")
     assert e0 < 1e-4
+
+
+@pytest.mark.parametrize("heads,temporal", [([0, 0, 0, 1], [0]), ([0, 1, 1, 1], [1, 2]), ([1, 1, 1, 1], [2, 3]),
+                                            ([1, 1, 2, 2], [2, 3, 4, 5])])
+def test_config5_iteration_sweep(dev, heads, temporal):
+    """BASELINE configs[4]: 1..6 retriever iterations via per_dh_num_heads (the combinations SURVEY.md 8d validated
+    on the reference), teacher-free chain vs the fp64 oracle at reduced size."""
+    T, N, shapes = 2, 100, [(4, 8), (8, 16), (16, 32), (32, 64)]
+    S = sum(heads)
+    sd = synthetic.make_head_state_dict(11, per_dh_num_heads=heads, temporal_stages=temporal)
+    cap = synthetic.make_capsule_params(11, N)
+    feats = synthetic.make_features(0, 0, T=T, video=11, shapes=shapes)
+    q = cap["init_mask_query.weight"]
+    cfg = O.HeadConfig(per_dh_num_heads=tuple(heads), temporal_stages=tuple(temporal))
+    pos64 = [[O.sine_position_embedding(*s, dtype=torch.float64) for s in shapes] for _ in range(T)]
+    rc, re_, rf = O.head_forward({k: v.double() for k, v in sd.items()}, [[f.double() for f in fr] for fr in feats], [q.double()] * T, pos64, cfg)
+    head = _mk_head(dev, sd, 0, dh_num_heads=S, per_dh_num_heads=heads, apply_temporal_query_atten_stages=temporal)
+    cl, em, fu = head([[f.to(dev) for f in fr] for fr in feats], [q.to(dev)] * T, None, pos="sine")
+    assert em[0].shape == (S, 1, N, 256) and cl[1].shape == (S, 1, N, 20)
+    for t in range(T):
+        for l in range(4):
+            assert rel(fu[t][l], rf[t][l]) < 1e-5
+        for s in range(S):
+            assert rel(em[t][s], re_[t][s]) < max(3e-5 * 3.5 ** s, 3e-5), (t, s, rel(em[t][s], re_[t][s]))
+    print(f"heads={heads}: last-stage emb rel {rel(em[1][-1], re_[1][-1]):.2e}")
+
+
+@pytest.mark.parametrize("N", [50, 200, 300])
+def test_config5_slot_sweep(dev, N):
+    """BASELINE configs[4]: slot-count sweep (N > 104 runs the fp32 attention kernel with the tensor-core statistics)."""
+    T, shapes = 2, [(4, 8), (8, 16), (16, 32), (32, 64)]
+    sd = synthetic.make_head_state_dict(12)
+    cap = synthetic.make_capsule_params(12, N)
+    feats = synthetic.make_features(0, 0, T=T, video=12, shapes=shapes)
+    q = cap["init_mask_query.weight"]
+    pos64 = [[O.sine_position_embedding(*s, dtype=torch.float64) for s in shapes] for _ in range(T)]
+    rc, re_, rf = O.head_forward({k: v.double() for k, v in sd.items()}, [[f.double() for f in fr] for fr in feats], [q.double()] * T, pos64)
+    head = _mk_head(dev, sd, 0)
+    cl, em, fu = head([[f.to(dev) for f in fr] for fr in feats], [q.to(dev)] * T, None, pos="sine")
+    for s in range(7):
+        assert rel(em[1][s], re_[1][s]) < max(3e-5 * 3.5 ** s, 3e-5), (s, rel(em[1][s], re_[1][s]))
+    print(f"N={N}: stage-0 emb rel {rel(em[1][0], re_[1][0]):.2e}, stage-6 {rel(em[1][6], re_[1][6]):.2e}")
+
+
+def test_config4_viper_shape(dev):
+    """BASELINE configs[3]: VIPER-shaped clip (1080x1920 padded to 1088x1920 -> levels 34x60..272x480, pixel counts
+    that are not multiples of the 128-pixel tile), T=4 (Video Retriever over 400 slots), at 1/4 linear size vs the
+    fp64 oracle, plus the fusion to the UNPADDED target size (non-integer scale)."""
+    T, N = 4, 100
+    shapes = [(9, 15), (18, 30), (36, 60), (72, 120)]           # 1/4-size analogue: same non-multiple-of-128 structure
+    sd = synthetic.make_head_state_dict(13)
+    cap = synthetic.make_capsule_params(13, N)
+    feats = synthetic.make_features(0, 0, T=T, video=13, shapes=shapes)
+    q = cap["init_mask_query.weight"]
+    pos64 = [[O.sine_position_embedding(*s, dtype=torch.float64) for s in shapes] for _ in range(T)]
+    rc, re_, rf = O.head_forward({k: v.double() for k, v in sd.items()}, [[f.double() for f in fr] for fr in feats], [q.double()] * T, pos64)
+    m = sv.SlotVPSRetriever(sv.HEAD_KWARGS, N, sv.FUSION_KWARGS)
+    m.dynamic_mask_head.load_state_dict(sd)
+    m.load_capsule_params(cap)
+    m = m.to(dev)
+    lg, _, _ = synthetic.make_fusion_case(13, N, 8, 8)
+    size = (270, 480)                                           # unpadded size: 72*4 = 288 rows padded, 270 real -> scale 3.75
+    out = m([[f.to(dev) for f in fr] for fr in feats], size, fusion_logits=lg.to(dev))
+    for t in range(T):
+        for s in range(7):
+            assert rel(out["emb"][t][s], re_[t][s]) < max(3e-5 * 3.5 ** s, 3e-5), (t, s)
+    r = O.panoptic_fuse(lg, out["pred_masks"].cpu(), size)
+    got = out["fusion"].panoptic.cpu().numpy()
+    assert got.shape == size
+    diff = got != r.panoptic
+    print(f"VIPER-shaped T=4: stage-6 emb rel {rel(out['emb'][3][6], re_[3][6]):.2e}; fusion mismatches {int(diff.sum())} "
+          f"(outside near-tie {int((diff & ~r.near_tie).sum())})")
+    assert int((diff & ~r.near_tie).sum()) == 0
+
+
+def test_viper_full_size_runs(dev):
+    """Full VIPER shape (levels 34x60 .. 272x480, T=4) runs and is deterministic (no oracle at this size)."""
+    T, N = 4, 100
+    shapes = [(34, 60), (68, 120), (136, 240), (272, 480)]
+    sd = synthetic.make_head_state_dict(0)
+    cap = synthetic.make_capsule_params(0, N)
+    feats = [[f.to(dev) for f in fr] for fr in synthetic.make_features(0, 0, T=T, video=3, shapes=shapes)]
+    m = sv.SlotVPSRetriever(sv.HEAD_KWARGS, N, sv.FUSION_KWARGS)
+    m.dynamic_mask_head.load_state_dict(sd)
+    m.load_capsule_params(cap)
+    m = m.to(dev)
+    lg = synthetic.make_fusion_case(0, N, 8, 8)[0].to(dev)
+    a = m(feats, (1080, 1920), fusion_logits=lg)
+    b = m(feats, (1080, 1920), fusion_logits=lg)
+    assert a["fusion"].panoptic.shape == (1080, 1920) and a["pred_masks"].shape == (N, 272, 480)
+    assert torch.equal(a["fusion"].panoptic, b["fusion"].panoptic) and torch.equal(a["emb"][3], b["emb"][3])
+    assert torch.isfinite(a["pred_masks"]).all()
