@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(FUSE_MAXN) fuse_select_kernel(const float* __r
   __shared__ float s_score[FUSE_MAXN];
   __shared__ int s_cls[FUSE_MAXN];
   __shared__ int s_keep[FUSE_MAXN];
+  __shared__ int s_code[FUSE_MAXN];
   __shared__ int s_cnt[2];
   const int i = threadIdx.x;
   if (i < 2) s_cnt[i] = 0;
@@ -110,12 +111,12 @@ __global__ void __launch_bounds__(FUSE_MAXN) fuse_select_kernel(const float* __r
       if (s_score[j] > sc || (s_score[j] == sc && j > i)) ++rank;
     }
     atomicAdd(&s_cnt[stuff ? 0 : 1], 1);
-    s_keep[i] = 1 + rank + (stuff ? 0 : 100000);
+    s_code[i] = rank + (stuff ? 0 : 100000);     // separate array: other threads are still reading s_keep
   }
   __syncthreads();
   const int ns = s_cnt[0], nc = s_cnt[1];
   if (keep) {
-    int code = s_keep[i] - 1;
+    int code = s_code[i];
     int pos = code >= 100000 ? ns + (code - 100000) : code;
     st->ord[pos] = i; st->cls[pos] = cl; st->score[pos] = sc;
   }

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(attn::THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g,
                const float* __restrict__ g0, const float* __restrict__ g1, const float* __restrict__ rs_k,
                const float* __restrict__ rs_v, float* __restrict__ Zpart, float* __restrict__ a0part,
-               float* __restrict__ a1part, int N, int P, int T, int plane_rows, int tiles_per_frame, int dbg) {
+               float* __restrict__ a1part, const __half* __restrict__ planes, int N, int P, int T, int plane_rows, int tiles_per_frame, int dbg) {
   using namespace attn;
   extern __shared__ uint8_t raw_smem[];
   const uint32_t raw = tc::smem_u32(raw_smem);
@@ -408,31 +408,54 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (lane 0) + L2 prefetchers (lanes 1..31) =====================
+    // The 4-slot ring holds 64 KB in flight.  Optional experiment: the idle lanes touch the NEXT tile's plane rows
+    // with prefetch.global.L2, paced one tile ahead of the producer by the __syncwarp below (see note further down).
+    uint32_t it = 0;
+    auto load_slot = [&](int plane, int c0, int row) {
+      const int s = it % NSLOT;
+      tc::mbar_wait(&empty[s], ((it / NSLOT) & 1) ^ 1);
+      tc::mbar_expect_tx(&full[s], SLOT_BYTES);
+      tc::tma_load_2d(smem + s * SLOT_BYTES, &tmap_x, c0, plane * plane_rows + row, &full[s]);
+      ++it;
+    };
+    auto job_s = [&](int i) {
+      const int row = t * P + (chunk + i * chunks) * TILE_M;
+      for (int ks = 0; ks < 4; ++ks) { load_slot(2, ks * 64, row); load_slot(3, ks * 64, row); }      // (x+pos) hi, lo
+    };
+    auto job_z = [&](int i) {
+      const int row = t * P + (chunk + i * chunks) * TILE_M;
+      for (int mt = 0; mt < 2; ++mt)
+        for (int pl = 0; pl < 2; ++pl) { load_slot(pl, (2 * mt) * 64, row); load_slot(pl, (2 * mt + 1) * 64, row); }   // x hi / lo, 128 channels
+    };
+    auto prefetch_tile = [&](int i) {            // lanes 1..31: 4 planes x 128 rows x 512 B = 2048 lines of 128 B
+      const long row = (long)t * P + (long)(chunk + i * chunks) * TILE_M;
+      const long max_row = (long)T * P;
+      for (int ln = lane - 1; ln < 4 * TILE_M * 4; ln += 31) {
+        const int pl = ln >> 9, r = (ln >> 2) & 127, seg = ln & 3;
+        if (row + r < max_row) {
+          const __half* ptr = planes + ((long)pl * plane_rows + row + r) * C + seg * 64;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        }
+      }
+    };
     if (lane == 0) {
       tc::mbar_expect_tx(gfull, G_BYTES);
       for (int pl = 0; pl < 2; ++pl)
         for (int ks = 0; ks < 4; ++ks)
           tc::tma_load_2d(smem + OFF_G + (pl * 4 + ks) * G_SUB, &tmap_g, ks * 64, (t * 2 + pl) * NROW, gfull);
-      uint32_t it = 0;
-      auto load_slot = [&](int plane, int c0, int row) {
-        const int s = it % NSLOT;
-        tc::mbar_wait(&empty[s], ((it / NSLOT) & 1) ^ 1);
-        tc::mbar_expect_tx(&full[s], SLOT_BYTES);
-        tc::tma_load_2d(smem + s * SLOT_BYTES, &tmap_x, c0, plane * plane_rows + row, &full[s]);
-        ++it;
-      };
-      auto job_s = [&](int i) {
-        const int row = t * P + (chunk + i * chunks) * TILE_M;
-        for (int ks = 0; ks < 4; ++ks) { load_slot(2, ks * 64, row); load_slot(3, ks * 64, row); }      // (x+pos) hi, lo
-      };
-      auto job_z = [&](int i) {
-        const int row = t * P + (chunk + i * chunks) * TILE_M;
-        for (int mt = 0; mt < 2; ++mt)
-          for (int pl = 0; pl < 2; ++pl) { load_slot(pl, (2 * mt) * 64, row); load_slot(pl, (2 * mt + 1) * 64, row); }   // x hi / lo, 128 channels
-      };
       job_s(0);
-      for (int i = 0; i < n_my; ++i) { if (i + 1 < n_my) job_s(i + 1); job_z(i); }
+    }
+    // Measured on B200 (1024x2048, level 3): both an L2 prefetch through the TMA engine and this LSU prefetch made the
+    // kernel SLOWER (0.43 -> 0.51 ms/step): it already streams the planes at ~4.3 TB/s, the extra requests only add
+    // DRAM contention.  Kept for experiments (SLOTVPS_TC_DEBUG bit 3), off by default.
+    const bool do_prefetch = (dbg & 8) != 0;
+    if (do_prefetch && lane != 0 && n_my > 1) prefetch_tile(1);
+    __syncwarp();
+    for (int i = 0; i < n_my; ++i) {
+      if (lane == 0) { if (i + 1 < n_my) job_s(i + 1); job_z(i); }
+      else if (do_prefetch && i + 2 < n_my) prefetch_tile(i + 2);
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -618,7 +641,7 @@ inline int tc_attention(const TcWorkspace& ws, __half* gplanes, const float* G, 
   }
   const int tiles_per_frame = ceil_div(P, attn::TILE_M);
   const int chunks = attn::chunks_for(P, T);
-  attn_tc_kernel<<<dim3(chunks, T), attn::THREADS, attn::SMEM_BYTES, s>>>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, N, P, T,
+  attn_tc_kernel<<<dim3(chunks, T), attn::THREADS, attn::SMEM_BYTES, s>>>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, ws.planes, N, P, T,
                                                                           (int)rows, tiles_per_frame, getenv("SLOTVPS_TC_DEBUG") ? atoi(getenv("SLOTVPS_TC_DEBUG")) : 0);
   SV_CHECK_LAUNCH("attn_tc");
   *chunks_out = chunks;

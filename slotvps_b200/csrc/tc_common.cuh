@@ -48,6 +48,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, int
                : "memory");
 }
 
+// L2 prefetch of a tile (no shared-memory destination): hides the DRAM latency of a later tma_load_2d of the same box
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(m), "r"(c0), "r"(c1) : "memory");
+}
+
 // ---- TMEM ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
