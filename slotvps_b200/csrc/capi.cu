@@ -135,6 +135,9 @@ struct HeadWs {
   float *pos[SLOTVPS_MAX_LEVELS];       // generated sine embeddings (pos_mode 2)
   float *ybuf;                          // coarse conv_trans partial [T][256][P/4]
   float *splitk;                        // split-K partials of the long-K linears [4][R][256]
+  float *tk[SLOTVPS_MAX_STAGES];        // separable-pos key tables per stage: [h][256] then [w][256]
+  float *pg[2];                         // separable-pos slot tables (stage parity): [T][h][112] then [T][w][112]
+  int hmax, wmax;
   TcWorkspace tc;
   FuseTcWorkspace ftc;
   int chunks;
@@ -170,6 +173,13 @@ static size_t head_ws_layout(const slotvps_head_desc* d, void* base, size_t cap,
     w.pos[l] = (d->pos_mode == 2 && l < d->n_levels) ? a.take<float>((size_t)C * d->h[l] * d->w[l]) : nullptr;
   w.ybuf = a.take<float>((size_t)T * C * (Pmax / 4 + 1));
   w.splitk = a.take<float>((size_t)4 * R * C);
+  {
+    int hm = 0, wm = 0;
+    for (int l = 0; l < d->n_levels; ++l) { hm = max(hm, d->h[l]); wm = max(wm, d->w[l]); }
+    w.hmax = hm; w.wmax = wm;
+    for (int i = 0; i < SLOTVPS_MAX_STAGES; ++i) w.tk[i] = (d->kernel_path == 0) ? a.take<float>((size_t)(hm + wm) * C) : nullptr;
+    for (int i = 0; i < 2; ++i) w.pg[i] = (d->kernel_path == 0) ? a.take<float>((size_t)T * (hm + wm) * 112) : nullptr;
+  }
   tc_workspace_layout(a, d, &w.tc);
   if (d->kernel_path == 0) {
     w.ftc.in_planes = a.take<__half>((size_t)2 * T * Pmax * CIN);
@@ -213,6 +223,8 @@ struct StagePix {                        // how a stage gets its pixel-side inpu
   cudaEvent_t ready = nullptr, done = nullptr;
   float *rs_k = nullptr, *rs_v = nullptr;
   TcWorkspace tc;
+  PosSep ps;                             // separable-pos tables (enabled when the level's planes carry x only)
+  float* pg = nullptr;                   // where this stage's pgy|pgx tables go
 };
 
 // ---- level fusion (dynamic_mask_head.py:172-185), folded: W.cat(up(p),x) = up(Wa.p) + Wb.x ----------
@@ -250,7 +262,7 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
   if (px.overlapped) {
     SV_CHECK_CUDA(cudaStreamWaitEvent(s, px.ready, 0));      // statistics of this stage were produced on the side stream
   } else if (use_tc) {
-    SV_TRY(tc_stats(ps.tc, w.tc, ps.bk_c, ps.bv_c, w.rs_k, w.rs_v, T, P, s));
+    SV_TRY(tc_stats(ps.tc, w.tc, ps.bk_c, ps.bv_c, w.rs_k, w.rs_v, T, P, s, 148, px.ps));
   } else {
     dim3 gs(ceil_div(P, 32), T);
     proj_rstd_kernel<<<gs, 256, 0, s>>>(x, x_bs, pos, pos_bs, ps.Wk_c, ps.bk_c, w.rs_k, P);
@@ -260,7 +272,25 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
   }
   int chunks = 0;
   if (use_tc && N <= attn::NROW) {
-    SV_TRY(tc_attention(w.tc, w.tc.gplanes, w.G, w.g0, w.g1, w.rs_k, w.rs_v, w.Zpart, w.a0part, w.a1part, T, N, P, &chunks, s));
+    PosSep pa = px.ps;
+    if (pa.enabled && pa.tky != nullptr) {
+      // pgy[t][row][n] = sum_{c<128} ytab[c][row] G[t][n][c] ; pgx[t][col][n] = sum_{c<128} xtab[c][col] G[t][n][128+c]
+      float* pgy = px.pg;
+      float* pgx = px.pg + (long)T * pa.h * attn::NPAD;
+      GemmArgs g;
+      g.A = w.tc.ytab; g.a_ms = 1; g.a_ks = pa.h;
+      g.B = w.G; g.b_ks = 1; g.b_ns = C; g.b_bs = (long)N * C;
+      g.Cm = pgy; g.c_ms = attn::NPAD; g.c_ns = 1; g.c_bs = (long)pa.h * attn::NPAD;
+      g.M = pa.h; g.N = N; g.K = 128; g.batch = T;
+      SV_TRY(sgemm(g, s));
+      g.A = w.tc.xtab; g.a_ks = pa.w;
+      g.B = w.G + 128;
+      g.Cm = pgx; g.c_bs = (long)pa.w * attn::NPAD;
+      g.M = pa.w;
+      SV_TRY(sgemm(g, s));
+      pa.pgy = pgy; pa.pgx = pgx;
+    }
+    SV_TRY(tc_attention(w.tc, w.tc.gplanes, w.G, w.g0, w.g1, w.rs_k, w.rs_v, w.Zpart, w.a0part, w.a1part, T, N, P, &chunks, s, pa));
   } else {
     const int NB = ceil_div(N, 128);
     chunks = attn_chunks(P, T);
@@ -509,6 +539,20 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
       if (d->pos_mode == 1) SV_REQUIRE(pos[t * L + l] == pos[l] + t * pstride[l], "pos frames of a level must be equally strided");
     }
   }
+  if (const char* pz = getenv("SLOTVPS_POISON")) {          // debugging aid: pre-fill scratch buffers with a finite pattern
+    const int m = atoi(pz);
+    const int pv_ = getenv("SLOTVPS_POISON_BYTE") ? atoi(getenv("SLOTVPS_POISON_BYTE")) : 0x3C;
+    int Pmax = 0;
+    for (int l = 0; l < L; ++l) Pmax = max(Pmax, d->h[l] * d->w[l]);
+    const size_t prow = (size_t)T * Pmax;
+    if ((m & 1) && w.tc.planes) { cudaMemsetAsync(w.tc.planes, pv_, 4 * prow * C * 2, s); cudaMemsetAsync(w.tc.planes_alt, pv_, 4 * prow * C * 2, s); }
+    if ((m & 2) && w.pg[0]) for (int i = 0; i < 2; ++i) cudaMemsetAsync(w.pg[i], 0x3C, (size_t)T * (w.hmax + w.wmax) * 112 * 4, s);
+    if ((m & 4) && w.tk[0]) for (int i = 0; i < SLOTVPS_MAX_STAGES; ++i) cudaMemsetAsync(w.tk[i], 0x3C, (size_t)(w.hmax + w.wmax) * C * 4, s);
+    if ((m & 8) && w.ftc.y) { cudaMemsetAsync(w.ftc.y, 0x3C, (size_t)T * (Pmax / 4 + 1) * C * 4, s); cudaMemsetAsync(w.ftc.in_planes, 0x3C, 2 * prow * CIN * 2, s); }
+    if (m & 16) { cudaMemsetAsync(w.rs_k, 0x3C, prow * 4, s); cudaMemsetAsync(w.rs_v, 0x3C, prow * 4, s); cudaMemsetAsync(w.rs_k2, 0x3C, prow * 4, s); cudaMemsetAsync(w.rs_v2, 0x3C, prow * 4, s); }
+    if ((m & 32) && w.tc.gplanes) cudaMemsetAsync(w.tc.gplanes, 0x3C, (size_t)T * 2 * 112 * C * 2, s);
+    if (m & 64) { cudaMemsetAsync(w.Zpart, 0x3C, (size_t)148 * T * N * C * 4, s); cudaMemsetAsync(w.L, 0x3C, (size_t)T * N * T * N * 4, s); cudaMemsetAsync(w.tqkv, 0x3C, (size_t)T * N * 3 * C * 4, s); }
+  }
   for (int t = 0; t < T; ++t) SV_TRY(dcopy(init_query[t], w.slots + (long)t * N * C, (long)N * C, s));
   const long cls_fs = (long)S * N * d->num_classes, emb_fs = (long)S * N * C;
   // Overlapped (two-stream) schedule when every level runs the tensor-core kernels end to end.
@@ -534,8 +578,10 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
     const bool use_tc = d->kernel_path == 0 && tc_supported(d, l);
     const bool all_tc = use_tc && N <= attn::NROW;          // no fp32 kernel touches pos at this level
     const bool fuse_tc = use_tc && (l == 0 || prev_planes);  // the coarse GEMM reads the previous level's planes
+    const bool pos_sep = use_tc && d->pos_mode != 1;         // sine / no pos: x planes only, pos terms from tables
     TcWorkspace tcl = w.tc, tcp = w.tc;                      // this level's / the previous level's operand planes
     if (overlap) { tcl.planes = (l & 1) ? w.tc.planes_alt : w.tc.planes; tcp.planes = (l & 1) ? w.tc.planes : w.tc.planes_alt; }
+    tcl.ytab = w.tc.ytab_l[l]; tcl.xtab = w.tc.xtab_l[l];      // per-level sine tables
     const float* pl = nullptr;
     long pls = 0;
     if (d->pos_mode == 1) { pl = pos[l]; pls = pstride[l]; }
@@ -566,20 +612,25 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
       prm.rows = (int)rows; prm.P = P; prm.w = wd; prm.h = h; prm.ksub = 2; prm.a_lo_row = (int)rows;
       prm.bias = pr.conv_b; prm.y_in = l > 0 ? w.ftc.y : nullptr;
       prm.out = fused_out[l]; prm.out_bs = fstride[l];
-      prm.planes = tcl.planes; prm.plane_stride = rows;
+      prm.planes = tcl.planes; prm.plane_stride = rows; prm.x_planes_only = pos_sep ? 1 : 0;
       if (d->pos_mode == 1) { prm.pos = pos[l]; prm.pos_bs = pstride[l]; }
       else if (d->pos_mode == 2) {
-        pos_tab_kernel<<<ceil_div(128 * (h + wd), 256), 256, 0, s>>>(w.tc.ytab, w.tc.xtab, h, wd);
+        pos_tab_kernel<<<ceil_div(128 * (h + wd), 256), 256, 0, s>>>(tcl.ytab, tcl.xtab, h, wd);
         SV_CHECK_LAUNCH("pos_tab");
-        prm.ytab = w.tc.ytab; prm.xtab = w.tc.xtab;
+        prm.ytab = tcl.ytab; prm.xtab = tcl.xtab;
       }
       SV_TRY(fuse_tc_launch(w.ftc.in_planes, 2 * rows, (int)rows, CIN, l > 0 ? pr.ftc.wb : pr.ftc.w0, prm, s, side_ctas));
     } else {
       for (int t = 0; t < T; ++t)
         SV_TRY(level_fuse_frame(l > 0 ? fused_out[t * L + l - 1] : nullptr, feats[t * L + l], pr.conv_w, pr.conv_b, pr.W0,
                                 fused_out[t * L + l], h, wd, w.ybuf + (long)t * C * (P / 4 + 1), s));
-      if (use_tc && d->heads_per_level[l] > 0)
+      if (use_tc && d->heads_per_level[l] > 0) {
         SV_TRY(tc_split_level(fused_out[l], fstride[l], pl, pls, d->pos_mode == 2 && all_tc, tcl, T, h, wd, s));
+        if (pos_sep && d->pos_mode == 2 && !all_tc) {          // tables for the key statistics even when pos was materialised
+          pos_tab_kernel<<<ceil_div(128 * (h + wd), 256), 256, 0, s>>>(tcl.ytab, tcl.xtab, h, wd);
+          SV_CHECK_LAUNCH("pos_tab");
+        }
+      }
     }
     prev_planes = fuse_tc || (use_tc && d->heads_per_level[l] > 0);
     // ---- per-stage pixel inputs; in overlapped mode the statistics of every stage of the level are queued now ----
@@ -588,6 +639,26 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
       const int st = stage + j;
       StagePix& q = px[j];
       q.tc = tcl;
+      q.pg = w.pg[st & 1];
+      if (pos_sep) {
+        q.ps.enabled = 1; q.ps.w = wd; q.ps.h = h;
+        if (d->pos_mode == 2) {                               // key tables of this stage (same stream as the planes' producer)
+          cudaStream_t s = sb;
+          float* tky = w.tk[st];
+          float* tkx = w.tk[st] + (long)h * C;
+          GemmArgs g;
+          g.A = tcl.ytab; g.a_ms = 1; g.a_ks = h;
+          g.B = pr.st[st].Wk_c; g.b_ks = 1; g.b_ns = C;
+          g.Cm = tky; g.c_ms = C; g.c_ns = 1;
+          g.M = h; g.N = C; g.K = 128;
+          SV_TRY(sgemm(g, s));
+          g.A = tcl.xtab; g.a_ks = wd;
+          g.B = pr.st[st].Wk_c + 128;
+          g.Cm = tkx; g.M = wd;
+          SV_TRY(sgemm(g, s));
+          q.ps.tky = tky; q.ps.tkx = tkx;
+        }
+      }
       q.rs_k = (overlap && (st & 1)) ? w.rs_k2 : w.rs_k;
       q.rs_v = (overlap && (st & 1)) ? w.rs_v2 : w.rs_v;
       if (overlap) {
@@ -596,7 +667,7 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
         ev_attn[st] = q.done;
         cudaStream_t s = sb;
         if (st >= 2) SV_CHECK_CUDA(cudaStreamWaitEvent(sb, ev_attn[st - 2], 0));     // rs buffers of parity st&1 are free again
-        SV_TRY(tc_stats(pr.st[st].tc, tcl, pr.st[st].bk_c, pr.st[st].bv_c, q.rs_k, q.rs_v, T, P, s, side_ctas));
+        SV_TRY(tc_stats(pr.st[st].tc, tcl, pr.st[st].bk_c, pr.st[st].bv_c, q.rs_k, q.rs_v, T, P, s, side_ctas, q.ps));
         SV_CHECK_CUDA(cudaEventRecord(q.ready, sb));
       }
     }

@@ -39,6 +39,7 @@ struct Params {
   float* out;          // NCHW fp32, frame t at out + t*out_bs, or null
   long out_bs;
   __half* planes;      // 4 planes with stride plane_stride rows, or null
+  int x_planes_only;   // separable pos: only x_hi / x_lo are written (the kernels add pos from tables)
   long plane_stride;
   const float* pos;    // [256][P] per frame (pos_bs) or null
   long pos_bs;
@@ -233,6 +234,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int c = 0; c < 4; ++c) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
           };
           pack(v); store(0, hi); store(1, lo);
+          if (prm.x_planes_only) continue;
           if (prm.pos) {
             const float* ps = prm.pos + (long)t * prm.pos_bs + (long)(j * 32) * prm.P + p;
 #pragma unroll

@@ -23,9 +23,20 @@ struct TcStageOperands {
 struct TcWorkspace {
   __half* planes = nullptr;      // [4][T*Pmax][256]: x hi, x lo, (x+pos) hi, (x+pos) lo
   __half* planes_alt = nullptr;  // second plane set: levels alternate so the next level's fusion can overlap this level's stages
-  float *ytab = nullptr, *xtab = nullptr;  // separable sine tables [128][hmax], [128][wmax]
+  float *ytab = nullptr, *xtab = nullptr;  // separable sine tables [128][h], [128][w] of the CURRENT level
+  float *ytab_l[SLOTVPS_MAX_LEVELS] = {nullptr}, *xtab_l[SLOTVPS_MAX_LEVELS] = {nullptr};   // one pair per level (the side stream runs ahead)
   __half* gplanes = nullptr;     // [T][2][112][256] folded query operand G, hi/lo
   long plane_rows = 0;                  // rows allocated per plane (T*Pmax)
+};
+
+// Separable position embedding (sine, or none): the kernels read only the x planes and add the position terms
+// from small tables in their epilogues instead of streaming separate (x+pos) planes:
+//   Wk_c (x+pos)      = Wk_c x + tky[row] + tkx[col]        tky [h][256], tkx [w][256]      (per stage)
+//   (x+pos) . G_n     = x . G_n + pgy[row][n] + pgx[col][n]  pgy [T][h][112], pgx [T][w][112] (per stage, frame)
+struct PosSep {
+  int enabled = 0, w = 1, h = 1;
+  const float *tky = nullptr, *tkx = nullptr;     // null with enabled: no position embedding at all
+  const float *pgy = nullptr, *pgx = nullptr;
 };
 
 inline void tc_stage_layout(Arena& a, TcStageOperands* o) { o->wplanes = a.take<__half>((size_t)4 * C * C); }
@@ -40,8 +51,8 @@ inline void tc_workspace_layout(Arena& a, const slotvps_head_desc* d, TcWorkspac
   if (d->kernel_path == 0) {
     w->planes = a.take<__half>((size_t)4 * w->plane_rows * C);
     w->planes_alt = a.take<__half>((size_t)4 * w->plane_rows * C);
-    w->ytab = a.take<float>((size_t)128 * hmax);
-    w->xtab = a.take<float>((size_t)128 * wmax);
+    for (int l = 0; l < SLOTVPS_MAX_LEVELS; ++l) { w->ytab_l[l] = a.take<float>((size_t)128 * hmax); w->xtab_l[l] = a.take<float>((size_t)128 * wmax); }
+    w->ytab = w->ytab_l[0]; w->xtab = w->xtab_l[0];
     w->gplanes = a.take<__half>((size_t)d->n_frames * 2 * 112 * C);
   }
 }
@@ -138,7 +149,7 @@ constexpr uint32_t IDESC = tc::make_idesc_f16(128, 256, 0, 0);
 __global__ void __launch_bounds__(stats::THREADS, 1)
 stats_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                 const float* __restrict__ bk_c, const float* __restrict__ bv_c, float* __restrict__ rs_k,
-                float* __restrict__ rs_v, int P, int T, int plane_rows, int tiles_per_frame) {
+                float* __restrict__ rs_v, int P, int T, int plane_rows, int tiles_per_frame, const PosSep ps) {
   using namespace stats;
   extern __shared__ uint8_t raw_smem[];
   const uint32_t raw = tc::smem_u32(raw_smem);
@@ -176,7 +187,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int t = tile / tiles_per_frame, p0 = (tile % tiles_per_frame) * TILE_M;
         const int row = t * P + p0;
         for (int g = 0; g < 2; ++g) {                       // g = 0: keys (x+pos, Wk), g = 1: values (x, Wv)
-          const int aq = g == 0 ? 2 : 0, bq = g == 0 ? 0 : 2;
+          const int aq = (g == 0 && !ps.enabled) ? 2 : 0, bq = g == 0 ? 0 : 2;     // separable pos: keys read the x planes too
           for (int ks = 0; ks < C / KSUB; ++ks, ++it) {
             const int s = it % NSTAGE;
             tc::mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
@@ -230,12 +241,22 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         tc::mbar_wait(&tfull[g], ti & 1);
         tc::tc_fence_after();
         const float* bg = bias + g * C;
+        const bool add_pos = g == 0 && ps.tky != nullptr && p < P;
+        const float4* ty4 = add_pos ? reinterpret_cast<const float4*>(ps.tky + (long)(p / ps.w) * C) : nullptr;
+        const float4* tx4 = add_pos ? reinterpret_cast<const float4*>(ps.tkx + (long)(p % ps.w) * C) : nullptr;
         float ss = 0.f;
 #pragma unroll 1
         for (int j = 0; j < C / 32; ++j) {
           float v[32];
           tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + g * 256 + j * 32, v);
           tc::tmem_ld_wait();
+          if (add_pos) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 a = __ldg(ty4 + j * 8 + c), b = __ldg(tx4 + j * 8 + c);
+              v[4 * c] += a.x + b.x; v[4 * c + 1] += a.y + b.y; v[4 * c + 2] += a.z + b.z; v[4 * c + 3] += a.w + b.w;
+            }
+          }
 #pragma unroll
           for (int c = 0; c < 32; ++c) { float d = v[c] + bg[j * 32 + c]; ss = fmaf(d, d, ss); }
         }
@@ -284,10 +305,12 @@ inline int tc_split_level(const float* x, long x_bs, const float* pos, long pos_
 
 // rs_k, rs_v [T][P] from the planes of this level and the stage's weight planes
 inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const float* bk_c, const float* bv_c, float* rs_k, float* rs_v,
-                    int T, int P, cudaStream_t s, int max_ctas = 148) {
+                    int T, int P, cudaStream_t s, int max_ctas = 148, const PosSep& ps = PosSep()) {
   CUtensorMap mx, mw;
   const long rows = (long)T * P;
-  SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)4 * rows, C, stats::TILE_M));
+  // only the planes that were written are inside the tensor map: a tail tile's rows past the last plane are then
+  // zero-filled by TMA instead of reading stale memory (NaN bit patterns there corrupt the MMA even against zero weights)
+  SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)(ps.enabled ? 2 : 4) * rows, C, stats::TILE_M));
   SV_TRY(tc::make_tmap_h16_sw128(&mw, ops.wplanes, (uint64_t)4 * C, C, C));
   static bool attr_done = false;
   if (!attr_done) {
@@ -297,7 +320,7 @@ inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const flo
   const int tiles_per_frame = ceil_div(P, stats::TILE_M);
   const int n_tiles = T * tiles_per_frame;
   const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
-  stats_tc_kernel<<<grid, stats::THREADS, stats::SMEM_BYTES, s>>>(mx, mw, bk_c, bv_c, rs_k, rs_v, P, T, (int)rows, tiles_per_frame);
+  stats_tc_kernel<<<grid, stats::THREADS, stats::SMEM_BYTES, s>>>(mx, mw, bk_c, bv_c, rs_k, rs_v, P, T, (int)rows, tiles_per_frame, ps);
   SV_CHECK_LAUNCH("stats_tc");
   return SLOTVPS_OK;
 }
@@ -362,7 +385,7 @@ __global__ void __launch_bounds__(attn::THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g,
                const float* __restrict__ g0, const float* __restrict__ g1, const float* __restrict__ rs_k,
                const float* __restrict__ rs_v, float* __restrict__ Zpart, float* __restrict__ a0part,
-               float* __restrict__ a1part, const __half* __restrict__ planes, int N, int P, int T, int plane_rows, int tiles_per_frame, int dbg) {
+               float* __restrict__ a1part, const __half* __restrict__ planes, int N, int P, int T, int plane_rows, int tiles_per_frame, int dbg, const PosSep ps) {
   using namespace attn;
   extern __shared__ uint8_t raw_smem[];
   const uint32_t raw = tc::smem_u32(raw_smem);
@@ -421,7 +444,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     };
     auto job_s = [&](int i) {
       const int row = t * P + (chunk + i * chunks) * TILE_M;
-      for (int ks = 0; ks < 4; ++ks) { load_slot(2, ks * 64, row); load_slot(3, ks * 64, row); }      // (x+pos) hi, lo
+      const int q0 = ps.enabled ? 0 : 2;                                                              // separable pos: S reads the x planes
+      for (int ks = 0; ks < 4; ++ks) { load_slot(q0, ks * 64, row); load_slot(q0 + 1, ks * 64, row); }  // (x+pos) or x: hi, lo
     };
     auto job_z = [&](int i) {
       const int row = t * P + (chunk + i * chunks) * TILE_M;
@@ -564,6 +588,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&sempty[b]);                          // S buffer free for tile i+2
+      if (ps.pgy != nullptr && pv) {                        // + pos . G_n from the separable tables
+        const float4* gy = reinterpret_cast<const float4*>(ps.pgy + ((long)t * ps.h + p / ps.w) * NPAD);
+        const float4* gx = reinterpret_cast<const float4*>(ps.pgx + ((long)t * ps.w + p % ps.w) * NPAD);
+#pragma unroll
+        for (int c = 0; c < NPAD / 4; ++c) {
+          const float4 a = __ldg(gy + c), b = __ldg(gx + c);
+          sv[4 * c] += a.x + b.x; sv[4 * c + 1] += a.y + b.y; sv[4 * c + 2] += a.z + b.z; sv[4 * c + 3] += a.w + b.w;
+        }
+      }
       float mx = -INFINITY;
 #pragma unroll
       for (int n = 0; n < NPAD; ++n) {
@@ -627,12 +660,12 @@ inline int chunks_for(int P, int T) {
 // Zpart/a0part/a1part [chunks][T][N]..., returns the chunk count through *chunks_out
 inline int tc_attention(const TcWorkspace& ws, __half* gplanes, const float* G, const float* g0, const float* g1,
                         const float* rs_k, const float* rs_v, float* Zpart, float* a0part, float* a1part, int T, int N, int P,
-                        int* chunks_out, cudaStream_t s) {
+                        int* chunks_out, cudaStream_t s, const PosSep& ps = PosSep()) {
   g_planes_kernel<<<(unsigned)(((long)T * attn::NROW * C + 255) / 256), 256, 0, s>>>(G, gplanes, N, T);
   SV_CHECK_LAUNCH("g_planes");
   CUtensorMap mx, mg;
   const long rows = (long)T * P;
-  SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)4 * rows, C, attn::TILE_M));
+  SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)(ps.enabled ? 2 : 4) * rows, C, attn::TILE_M));
   SV_TRY(tc::make_tmap_h16_sw128(&mg, gplanes, (uint64_t)T * 2 * attn::NROW, C, attn::NROW));
   static bool attr_done = false;
   if (!attr_done) {
@@ -642,7 +675,7 @@ inline int tc_attention(const TcWorkspace& ws, __half* gplanes, const float* G, 
   const int tiles_per_frame = ceil_div(P, attn::TILE_M);
   const int chunks = attn::chunks_for(P, T);
   attn_tc_kernel<<<dim3(chunks, T), attn::THREADS, attn::SMEM_BYTES, s>>>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, ws.planes, N, P, T,
-                                                                          (int)rows, tiles_per_frame, getenv("SLOTVPS_TC_DEBUG") ? atoi(getenv("SLOTVPS_TC_DEBUG")) : 0);
+                                                                          (int)rows, tiles_per_frame, getenv("SLOTVPS_TC_DEBUG") ? atoi(getenv("SLOTVPS_TC_DEBUG")) : 0, ps);
   SV_CHECK_LAUNCH("attn_tc");
   *chunks_out = chunks;
   return SLOTVPS_OK;

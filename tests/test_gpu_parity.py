@@ -378,7 +378,7 @@ def test_config4_viper_shape(dev):
     out = m([[f.to(dev) for f in fr] for fr in feats], size, fusion_logits=lg.to(dev))
     for t in range(T):
         for s in range(7):
-            assert rel(out["emb"][t][s], re_[t][s]) < max(3e-5 * 3.5 ** s, 3e-5), (t, s)
+            assert rel(out["emb"][t][s], re_[t][s]) < max(3e-5 * 3.5 ** s, 3e-5), (t, s, rel(out["emb"][t][s], re_[t][s]))
     r = O.panoptic_fuse(lg, out["pred_masks"].cpu(), size)
     got = out["fusion"].panoptic.cpu().numpy()
     assert got.shape == size
@@ -405,3 +405,28 @@ def test_viper_full_size_runs(dev):
     assert a["fusion"].panoptic.shape == (1080, 1920) and a["pred_masks"].shape == (N, 272, 480)
     assert torch.equal(a["fusion"].panoptic, b["fusion"].panoptic) and torch.equal(a["emb"][3], b["emb"][3])
     assert torch.isfinite(a["pred_masks"]).all()
+
+
+@pytest.mark.parametrize("pos_kind", ["sine", "tensor", "none"])
+def test_stale_workspace_is_never_read(dev, pos_kind, monkeypatch):
+    """Regression: scratch buffers pre-filled with NaN bit patterns (SLOTVPS_POISON) must not change the result.
+    Pixel counts that are not multiples of the 128-pixel tile make tail tiles reach past the written rows; those
+    rows have to come from TMA zero fill, never from stale memory (a NaN there corrupts the MMA even against zero
+    weights -- found when a T=4 VIPER-shaped clip ran after a larger clip in the same process)."""
+    monkeypatch.setenv("SLOTVPS_POISON", "127")
+    monkeypatch.setenv("SLOTVPS_POISON_BYTE", "255")
+    T, N, shapes = 3, 100, [(9, 15), (18, 30), (36, 60), (72, 120)]
+    sd = synthetic.make_head_state_dict(14)
+    cap = synthetic.make_capsule_params(14, N)
+    feats = synthetic.make_features(0, 0, T=T, video=14, shapes=shapes)
+    q = cap["init_mask_query.weight"]
+    pos64 = None if pos_kind == "none" else [[O.sine_position_embedding(*s, dtype=torch.float64) for s in shapes] for _ in range(T)]
+    rc, re_, rf = O.head_forward({k: v.double() for k, v in sd.items()}, [[f.double() for f in fr] for fr in feats], [q.double()] * T, pos64)
+    head = _mk_head(dev, sd, 0)
+    pos_arg = {"sine": "sine", "none": None,
+               "tensor": None if pos64 is None else [[p.float().to(dev) for p in pp] for pp in pos64]}[pos_kind]
+    cl, em, fu = head([[f.to(dev) for f in fr] for fr in feats], [q.to(dev)] * T, None, pos=pos_arg)
+    for t in range(T):
+        for s in range(7):
+            e = rel(em[t][s], re_[t][s])
+            assert e < max(3e-5 * 3.5 ** s, 3e-5), (pos_kind, t, s, e)
