@@ -578,7 +578,10 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
     const bool use_tc = d->kernel_path == 0 && tc_supported(d, l);
     const bool all_tc = use_tc && N <= attn::NROW;          // no fp32 kernel touches pos at this level
     const bool fuse_tc = use_tc && (l == 0 || prev_planes);  // the coarse GEMM reads the previous level's planes
-    const bool pos_sep = use_tc && d->pos_mode != 1;         // sine / no pos: x planes only, pos terms from tables
+    // Separable-pos mode (x planes only, position terms from tables).  Measured on B200 at 1024x2048: level fusion
+    // gets 0.15 ms/step faster (2 planes instead of 4) but the table loads make the statistics / attention epilogues
+    // 0.19 ms/step slower, so it is opt-in (SLOTVPS_POS_SEP=1); pos == None always uses it (no tables needed).
+    const bool pos_sep = use_tc && d->pos_mode != 1 && (d->pos_mode == 0 || getenv("SLOTVPS_POS_SEP") != nullptr);
     TcWorkspace tcl = w.tc, tcp = w.tc;                      // this level's / the previous level's operand planes
     if (overlap) { tcl.planes = (l & 1) ? w.tc.planes_alt : w.tc.planes; tcp.planes = (l & 1) ? w.tc.planes : w.tc.planes_alt; }
     tcl.ytab = w.tc.ytab_l[l]; tcl.xtab = w.tc.xtab_l[l];      // per-level sine tables

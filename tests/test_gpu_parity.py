@@ -407,7 +407,7 @@ def test_viper_full_size_runs(dev):
     assert torch.isfinite(a["pred_masks"]).all()
 
 
-@pytest.mark.parametrize("pos_kind", ["sine", "tensor", "none"])
+@pytest.mark.parametrize("pos_kind", ["sine", "sine_separable", "tensor", "none"])
 def test_stale_workspace_is_never_read(dev, pos_kind, monkeypatch):
     """Regression: scratch buffers pre-filled with NaN bit patterns (SLOTVPS_POISON) must not change the result.
     Pixel counts that are not multiples of the 128-pixel tile make tail tiles reach past the written rows; those
@@ -415,6 +415,9 @@ def test_stale_workspace_is_never_read(dev, pos_kind, monkeypatch):
     weights -- found when a T=4 VIPER-shaped clip ran after a larger clip in the same process)."""
     monkeypatch.setenv("SLOTVPS_POISON", "127")
     monkeypatch.setenv("SLOTVPS_POISON_BYTE", "255")
+    if pos_kind == "sine_separable":                    # opt-in mode: x planes only, position terms from tables
+        monkeypatch.setenv("SLOTVPS_POS_SEP", "1")
+        pos_kind = "sine"
     T, N, shapes = 3, 100, [(9, 15), (18, 30), (36, 60), (72, 120)]
     sd = synthetic.make_head_state_dict(14)
     cap = synthetic.make_capsule_params(14, N)
