@@ -416,3 +416,83 @@ def clip_forward(P, bn, features, init_query, size, hcfg=HeadConfig(), fcfg=Fusi
     if fuse:
         out["fusion"] = panoptic_fuse(cls[-1][-1, 0], pm, size, fcfg)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Tracker (SURVEY.md 8f "next" rank 1): SimpleTrackHead + the greedy assignment loop of simple_test.
+# ------------------------------------------------------------------------------------------------
+def track_head_embed(fcs, x: torch.Tensor) -> torch.Tensor:
+    """simple_track_head.py:63-79: `num_fcs_query` Linear layers, ReLU between (not after the last).
+    `fcs` = [(weight [C,C], bias [C]), ...]."""
+    x = x.float()
+    for i, (w, b) in enumerate(fcs):
+        x = x @ w.float().t() + b.float()
+        if i < len(fcs) - 1:
+            x = torch.relu(x)
+    return x
+
+
+def track_match_scores(fcs, cur: torch.Tensor, bank: torch.Tensor) -> torch.Tensor:
+    """simple_track_head.py:88-90: [K, 1+M] = [0 | fc(cur) fc(bank)^T]; column 0 is the "new object" entry."""
+    a, b = track_head_embed(fcs, cur), track_head_embed(fcs, bank)
+    return torch.cat([torch.zeros(a.shape[0], 1), a @ b.t()], 1)
+
+
+class TrackerState:
+    """`prev_instances.output_embedding` of the reference (vps_temporal_slots.py:232-237): the raw slot embeddings
+    of every object seen so far in this video; row index = object id."""
+
+    def __init__(self):
+        self.bank: Optional[np.ndarray] = None
+
+    def reset(self):
+        self.bank = None
+
+
+def track_step(fcs, state: TrackerState, embedding: np.ndarray, labels: np.ndarray, stuff_num: int = 11):
+    """vps_temporal_slots.py:322-409.  `embedding` [K,256] and `labels` [K] are the post-processed instances
+    (stuff and things) in the post-processor's order.  Returns (det_obj_ids of the things [n_things] int32 -- the
+    reference's `panoptic_det_obj_ids` -- , ids of all K entries, info)."""
+    emb = np.asarray(embedding, np.float32)
+    K = emb.shape[0]
+    things = np.asarray(labels) > stuff_num - 1
+    info = dict(new=0, matched=0, undone=0, lost=0)
+    if state.bank is None:                                   # :335-342 first frame of the video
+        state.bank = emb.copy()
+        ids = np.arange(K, dtype=np.int64)
+        return ids[things], ids, info
+    score = track_match_scores(fcs, torch.from_numpy(emb), torch.from_numpy(state.bank))
+    logp = torch.log_softmax(score, 1)
+    lik, mid = logp.max(1)                                   # :348-351
+    lik, mid = lik.numpy(), mid.numpy().astype(np.int32)
+    M0 = state.bank.shape[0]
+    bank = [r for r in state.bank]
+    ids = -np.ones(K, np.int32)
+    best = -100.0 * np.ones(M0)
+    best_id = -np.ones(M0, np.int32)
+    for i in range(K):                                       # :359-392
+        if mid[i] == 0:
+            ids[i] = len(bank)
+            bank.append(emb[i])
+            info["new"] += 1
+        else:
+            o = mid[i] - 1
+            if lik[i] > best[o]:
+                ids[i] = o
+                if best_id[o] >= 0:
+                    ids[best_id[o]] = -1
+                    info["undone"] += 1
+                best[o], best_id[o] = lik[i], i
+                bank[o] = emb[i]
+                info["matched"] += 1
+            else:
+                info["lost"] += 1
+    for i in range(K):                                       # :396-404 redundant matches become new objects
+        if ids[i] < 0:
+            ids[i] = len(bank)
+            bank.append(emb[i])
+    state.bank = np.stack(bank).astype(np.float32)
+    info["margin"] = float(np.sort(score.numpy(), 1)[:, -1].min() - 0) if K else 0.0
+    top2 = np.sort(score.numpy(), 1)[:, -2:] if score.shape[1] > 1 else None
+    info["top2_gap"] = float((top2[:, 1] - top2[:, 0]).min()) if top2 is not None and K else float("inf")
+    return ids[things], ids, info

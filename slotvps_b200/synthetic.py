@@ -181,3 +181,54 @@ def make_fusion_case(seed: int, n_slots: int, h: int, w: int, n_stuff: int = 11,
         masks[s, cy, cx] = 30.0
         roles[s] = ("tiny", cls)
     return logits.contiguous(), masks.contiguous(), roles
+
+
+def make_track_params(seed: int, channels: int = 256, num_fcs: int = 2, mode: str = "identity"):
+    """Synthetic SimpleTrackHead weights under the reference's parameter names
+    (simple_track_head.py:44-50: ``fcs_query.{i}.weight/bias``).  ``identity``: identity-dominant layers so that
+    the designed identities of make_track_sequence survive (every branch of the greedy loop is reached);
+    ``random``: dense random layers with an active ReLU (exercises the arithmetic, arbitrary matches)."""
+    g = torch.Generator().manual_seed(50_000 + seed)
+    sd = {}
+    for i in range(num_fcs):
+        if mode == "identity":
+            w = torch.eye(channels) + torch.randn((channels, channels), generator=g) * 0.001
+            b = torch.randn((channels,), generator=g) * 0.002 + (0.1 if i == 0 else -0.1)
+        else:
+            w = torch.randn((channels, channels), generator=g) * 0.08
+            b = torch.randn((channels,), generator=g) * 0.1
+        sd["fcs_query.%d.weight" % i] = w
+        sd["fcs_query.%d.bias" % i] = b
+    return sd
+
+
+def make_track_sequence(seed: int, n_slots: int, frames: int, channels: int = 256, blk: int = 2,
+                        p_new: float = 0.10, p_dup: float = 0.12, amp: float = 10.0, delta: float = 0.04,
+                        noise: float = 0.02):
+    """Per-frame slot embeddings [frames][N,channels] with designed identities.
+
+    Identity j is ``amp`` on its own block of ``blk`` channels and ``-delta`` elsewhere: self dot ~ blk*amp^2,
+    cross dot ~ -2*blk*amp*delta + channels*delta^2 < 0.  A slot re-observing an identity matches its bank row, a
+    slot with an unseen identity prefers the all-zero "new object" column (simple_track_head.py:89), and two slots
+    sharing an identity in one frame reach the undo branch of the greedy loop (vps_temporal_slots.py:373-381)."""
+    g = torch.Generator().manual_seed(60_000 + seed)
+    n_ident = channels // blk
+    protos = -delta * torch.ones((n_ident, channels))
+    for j in range(n_ident):
+        protos[j, j * blk:(j + 1) * blk] = amp
+    order = torch.randperm(n_ident, generator=g).tolist()
+    ident = [order[s % n_ident] for s in range(n_slots)]
+    nxt = n_slots
+    out = []
+    for f in range(frames):
+        if f > 0:
+            for s in range(n_slots):
+                r = float(torch.rand(1, generator=g))
+                if r < p_new and nxt < n_ident:
+                    ident[s] = order[nxt]
+                    nxt += 1
+                elif r < p_new + p_dup:
+                    ident[s] = ident[int(torch.randint(0, n_slots, (1,), generator=g))]
+        e = protos[torch.tensor(ident)] + torch.randn((n_slots, channels), generator=g) * noise
+        out.append(e.contiguous())
+    return out

@@ -132,6 +132,53 @@ def gen_fusion(model, name, seed, N, h, w, **kw):
         masks_nnz=(captured["masks"] != 0).sum((1, 2)).numpy())
 
 
+TRACK_CASES = {
+    # name: seed, N, (h, w), [frames per video], FC mode
+    "track_a": dict(seed=0, N=100, h=32, w=64, videos=[5, 3], mode="identity"),
+    "track_b": dict(seed=1, N=100, h=32, w=64, videos=[4], mode="random"),
+    "track_c": dict(seed=2, N=50, h=24, w=40, videos=[4, 2], mode="identity"),
+}
+
+
+def gen_track(model, name, seed, N, h, w, videos, mode):
+    """Drive the reference's simple_test over consecutive frames (iid = vid*10000 + fid, fid==1 resets the
+    tracker, vps_temporal_slots.py:218-237) with designed logits / masks / slot embeddings per frame, and record
+    panoptic_det_obj_ids and the object bank after every frame."""
+    H, W = 4 * h, 4 * w
+    im = model.image_model
+    im.backbone = _Fn(lambda x: x)
+    im.neck = None
+    model.extract_semantic_feats = lambda x: (torch.zeros(1, 19, H, W), None, [torch.zeros(1, 128, 1, 1)] * 4)
+    model.semantic_trans_ins = lambda f: f
+    model.generate_position_embedding = lambda f: None
+    im.init_mask_query = torch.nn.Embedding(N, 256)
+    model.temporal_track_head.load_state_dict(synthetic.make_track_params(seed, mode=mode))
+    cur = {}
+    im.dynamic_mask_head = _Fn(lambda **k: ([cur["cls"], cur["cls"]], [cur["emb"], cur["emb"]], [[None] * 4, [None] * 4]))
+    model.generate_final_outputs = lambda feats, om, generate_aux_output=False: (feats, cur["masks"][None], [])
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.cuda.current_device = lambda: "cpu"
+    img = torch.zeros(1, 3, H, W)
+    out = {}
+    fidx = 0
+    for v, nf in enumerate(videos):
+        embs = synthetic.make_track_sequence(seed * 10 + v, N, nf)
+        for f in range(nf):
+            logits, masks, _ = synthetic.make_fusion_case(1000 * seed + 100 * v + f, N, h, w)
+            cur["cls"] = logits[None, None].repeat(7, 1, 1, 1)
+            cur["emb"] = embs[f][None, None].repeat(7, 1, 1, 1)
+            cur["masks"] = masks
+            meta = [dict(iid=(v + 1) * 10000 + f + 1, filename="synthetic", ori_shape=(H, W, 3), img_shape=(H, W, 3))]
+            with torch.no_grad():
+                res = model.simple_test(img, meta, rescale=True, ref_img=[img])
+            out["ids_%d" % fidx] = res["panoptic_det_obj_ids"].numpy().astype(np.int64)
+            out["cls_inds_%d" % fidx] = res["panoptic_cls_inds"].numpy()
+            out["bank_sum_%d" % fidx] = model.prev_instances.output_embedding.double().sum(1).numpy()
+            fidx += 1
+    out["videos"] = np.asarray(videos)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
     model, _ = ref_import.build_model(0)
@@ -152,6 +199,10 @@ def main():
         kw = dict(c)
         m3, _ = ref_import.build_model(0, **{"other_config.proposal_num": kw["N"]})
         gen_fusion(m3, name, kw.pop("seed"), kw.pop("N"), kw.pop("h"), kw.pop("w"), **kw)
+        print(name, "done")
+    for name, c in TRACK_CASES.items():
+        m4, _ = ref_import.build_model(0, **{"other_config.proposal_num": c["N"]})
+        gen_track(m4, name, **c)
         print(name, "done")
     print("golden fixtures written to", HERE)
 

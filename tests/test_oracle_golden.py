@@ -107,3 +107,43 @@ def test_panoptic_fusion_bit_exact(golden_dir, name):
     np.testing.assert_allclose(r.masks.astype(np.float64).sum((1, 2)), g["masks_sum"], rtol=1e-9, atol=1e-6)
     np.testing.assert_array_equal(r.panoptic, g["panoptic"])       # bit-identical id map
     assert r.panoptic.dtype == np.int64
+
+
+TRACK_CASES = {
+    "track_a": dict(seed=0, N=100, h=32, w=64, mode="identity"),
+    "track_b": dict(seed=1, N=100, h=32, w=64, mode="random"),
+    "track_c": dict(seed=2, N=50, h=24, w=40, mode="identity"),
+}
+
+
+def track_inputs(seed, N, h, w, videos):
+    """The per-frame inputs tests/golden/make_golden.py::gen_track fed to the reference."""
+    for v, nf in enumerate(videos):
+        embs = synthetic.make_track_sequence(seed * 10 + v, N, int(nf))
+        for f in range(int(nf)):
+            logits, masks, _ = synthetic.make_fusion_case(1000 * seed + 100 * v + f, N, h, w)
+            yield v, f, logits, masks, embs[f]
+
+
+@pytest.mark.parametrize("name", sorted(TRACK_CASES))
+def test_tracker_matches_reference(name):
+    """Oracle tracker (SimpleTrackHead + greedy loop) vs panoptic_det_obj_ids / the object bank the reference's
+    simple_test produced over consecutive frames, including the per-video reset."""
+    c = TRACK_CASES[name]
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    sd = synthetic.make_track_params(c["seed"], mode=c["mode"])
+    fcs = [(sd["fcs_query.%d.weight" % i], sd["fcs_query.%d.bias" % i]) for i in range(2)]
+    st = O.TrackerState()
+    seen = dict(new=0, matched=0, undone=0, lost=0)
+    for i, (v, f, logits, masks, emb) in enumerate(track_inputs(c["seed"], c["N"], c["h"], c["w"], g["videos"])):
+        if f == 0:
+            st.reset()
+        fr = O.panoptic_fuse(logits, masks, (4 * c["h"], 4 * c["w"]))
+        ids, _, info = O.track_step(fcs, st, emb[torch.from_numpy(fr.keep.copy())].numpy(), fr.labels)
+        np.testing.assert_array_equal(fr.cls_inds, g["cls_inds_%d" % i])
+        np.testing.assert_array_equal(ids, g["ids_%d" % i])
+        np.testing.assert_allclose(st.bank.astype(np.float64).sum(1), g["bank_sum_%d" % i], rtol=0, atol=1e-9)
+        for k in seen:
+            seen[k] += info[k]
+    if c["mode"] == "identity":
+        assert all(v > 0 for v in seen.values()), seen     # every branch of the greedy loop was reached
