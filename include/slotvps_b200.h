@@ -159,6 +159,29 @@ int slotvps_panoptic_fuse(const slotvps_fusion_cfg* cfg, const float* pred_logit
  * normalize=True, 128 feats/axis): out [256,h,w].                                           */
 int slotvps_sine_pos(float* out, int h, int w, void* stream);
 
+/* ---- Tracker (first row beyond the retriever path) ------------------------------
+ * SimpleTrackHead.forward (simple_track_head.py:58-92): x_query [k,256], ref_x_query [m,256] ->
+ * match_score [k, 1+m] = [0 | fc(x_query) fc(ref_x_query)^T]; fc = `num_fcs` Linear(256,256) layers with ReLU
+ * between them.  fc_w [num_fcs,256,256] ([out][in], as nn.Linear stores it), fc_b [num_fcs,256].
+ * workspace: (k + m) * 256 floats.                                                                 */
+int slotvps_track_scores(const float* fc_w, const float* fc_b, int num_fcs, const float* x_query, int k,
+                         const float* ref_x_query, int m, float* match_score, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* The per-video tracking loop of simple_test (vps_temporal_slots.py:232-237 reset, :322-409 assignment) with the
+ * object bank (prev_instances.output_embedding) kept in device memory.
+ *   state: opaque device buffer of slotvps_track_state_bytes(capacity, n_slots); capacity = most objects per video.
+ *   slotvps_track_reset: first frame of a video (fid == 1).
+ *   slotvps_track_step:  embedding [N,256] = the head's last-stage slot embeddings of the current frame,
+ *     fusion_meta = the meta written by slotvps_panoptic_fuse for that frame (kept slots, stuff first).
+ *     track_out int32[4 + N] (device): [0]=K' entries, [1]=number of things, [2]=objects in the bank,
+ *     [3]=1 if the bank overflowed `capacity` (ids stay valid, the extra embeddings are not remembered),
+ *     then the object id of every kept entry; the last [1] of them are the reference's panoptic_det_obj_ids. */
+int slotvps_track_state_bytes(int capacity, int n_slots, size_t* bytes);
+int slotvps_track_reset(void* state, size_t state_bytes, void* stream);
+int slotvps_track_step(const float* fc_w, const float* fc_b, int num_fcs, const float* embedding,
+                       const int32_t* fusion_meta, int n_slots, void* state, size_t state_bytes, int capacity,
+                       int32_t* track_out, void* stream);
+
 /* Introspection. */
 const char* slotvps_last_error(void);
 const char* slotvps_version(void);

@@ -11,6 +11,9 @@ from ._lib import build_library, lib, SlotVPSError  # noqa: F401
 from .head import B200DynamicMaskHead  # noqa: F401
 from .retriever import (PanopticFusion, SlotVPSRetriever, FusionOutput, GraphedClip, mask_logits, level_fuse,  # noqa: F401
                         slot_attention, sine_position_embedding)
+from .tracker import B200TrackHead, SlotTracker  # noqa: F401
+
+TRACK_KWARGS = dict(num_fcs_query=2, in_channels_query=256, query_matched_weight=1.0)  # r50_fpn_slotvps.py:90-96
 
 HEAD_KWARGS = dict(  # configs/cityscapes/r50_fpn_slotvps.py:27-54
     dh_dim=256, num_classes=20, dim_feedforward=2048, nhead=8, dropout=0.0, activation="gelu", dh_num_heads=7,

@@ -109,6 +109,10 @@ SYMBOLS = {
     "slotvps_panoptic_fuse": (C.c_int, [C.POINTER(FusionCfg), P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P,
                                         P, C.c_int, P, C.c_size_t, P]),
     "slotvps_sine_pos": (C.c_int, [P, C.c_int, C.c_int, P]),
+    "slotvps_track_scores": (C.c_int, [P, P, C.c_int, P, C.c_int, P, C.c_int, P, P, C.c_size_t, P]),
+    "slotvps_track_state_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "slotvps_track_reset": (C.c_int, [P, C.c_size_t, P]),
+    "slotvps_track_step": (C.c_int, [P, P, C.c_int, P, P, C.c_int, P, C.c_size_t, C.c_int, P, P]),
     "slotvps_last_error": (C.c_char_p, []),
     "slotvps_version": (C.c_char_p, []),
     "slotvps_launch_count": (C.c_int64, [C.c_int]),

@@ -14,6 +14,7 @@
 #include "pixel_tc.cuh"
 #include "fuse_tc.cuh"
 #include "mask_tc.cuh"
+#include "track.cuh"
 
 namespace slotvps {
 thread_local char g_err[512] = "";
@@ -702,6 +703,78 @@ int slotvps_level_fuse(const float* prev, const float* x, const float* conv_w, c
   }
   SV_REQUIRE(h % 2 == 0 && w % 2 == 0, "level must be 2x the previous");
   return level_fuse_frame(prev, x, conv_w, conv_b, nullptr, out, h, w, scratch, s);
+}
+
+// ---- tracker --------------------------------------------------------------------------------------------
+namespace {
+constexpr int TRACK_MAX_CAPACITY = 4000;            // 12 B of shared memory per bank row in track_assign_kernel
+struct TrackLayout { track::State* st; float* bank; float* y_cur; float* y_bank; float* lik; int* mid; size_t bytes; };
+TrackLayout track_layout(void* state, int capacity, int n_slots) {
+  Arena a(state, (size_t)-1);
+  TrackLayout t;
+  t.st = (track::State*)a.take<char>(256);
+  t.bank = a.take<float>((size_t)capacity * C);
+  t.y_cur = a.take<float>((size_t)n_slots * C);
+  t.y_bank = a.take<float>((size_t)capacity * C);
+  t.lik = a.take<float>(n_slots);
+  t.mid = a.take<int>(n_slots);
+  t.bytes = align_up(a.off);
+  return t;
+}
+}  // namespace
+
+int slotvps_track_scores(const float* fc_w, const float* fc_b, int num_fcs, const float* x_query, int k,
+                         const float* ref_x_query, int m, float* match_score, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  SV_REQUIRE(x_query && ref_x_query && match_score && workspace, "null argument");
+  SV_REQUIRE(k > 0 && m > 0 && m <= TRACK_MAX_CAPACITY && num_fcs >= 0 && (num_fcs == 0 || (fc_w && fc_b)), "bad argument");
+  if (workspace_bytes < (size_t)(k + m) * C * sizeof(float)) return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* ya = (float*)workspace; float* yb = ya + (size_t)k * C;
+  track::track_fc_kernel<<<ceil_div(k, track::ROWS), 256, 0, s>>>(x_query, nullptr, nullptr, k, fc_w, fc_b, num_fcs, ya);
+  SV_CHECK_LAUNCH("track_fc");
+  track::track_fc_kernel<<<ceil_div(m, track::ROWS), 256, 0, s>>>(ref_x_query, nullptr, nullptr, m, fc_w, fc_b, num_fcs, yb);
+  SV_CHECK_LAUNCH("track_fc");
+  track::track_score_kernel<<<k, 256, (size_t)(1 + m) * sizeof(float), s>>>(ya, yb, nullptr, k, nullptr, m, nullptr, nullptr, match_score, 1 + m);
+  SV_CHECK_LAUNCH("track_score");
+  return SLOTVPS_OK;
+}
+
+int slotvps_track_state_bytes(int capacity, int n_slots, size_t* bytes) {
+  SV_REQUIRE(bytes && capacity > 0 && capacity <= TRACK_MAX_CAPACITY && n_slots > 0 && n_slots <= 1024, "bad argument");
+  *bytes = track_layout(nullptr, capacity, n_slots).bytes;
+  return SLOTVPS_OK;
+}
+
+int slotvps_track_reset(void* state, size_t state_bytes, void* stream) {
+  SV_REQUIRE(state && state_bytes >= 256, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  track::track_reset_kernel<<<1, 1, 0, s>>>((track::State*)state);
+  SV_CHECK_LAUNCH("track_reset");
+  return SLOTVPS_OK;
+}
+
+int slotvps_track_step(const float* fc_w, const float* fc_b, int num_fcs, const float* embedding, const int32_t* fusion_meta,
+                       int n_slots, void* state, size_t state_bytes, int capacity, int32_t* track_out, void* stream) {
+  SV_REQUIRE(embedding && fusion_meta && state && track_out, "null argument");
+  SV_REQUIRE(capacity > 0 && capacity <= TRACK_MAX_CAPACITY && n_slots > 0 && n_slots <= 1024, "bad argument");
+  SV_REQUIRE(num_fcs >= 0 && (num_fcs == 0 || (fc_w && fc_b)), "bad argument");
+  const TrackLayout t = track_layout(state, capacity, n_slots);
+  if (state_bytes < t.bytes) return fail(SLOTVPS_EWORKSPACE, "tracker state too small%s%s");
+  cudaStream_t s = (cudaStream_t)stream;
+  // Both FC launches and the score launch size their grids for the maxima and exit on the device-side counts
+  // (K' = meta[0], bank rows = State::count), so no count is read back; on the first frame of a video the bank
+  // is empty and the assign kernel ignores lik / mid.
+  track::track_fc_kernel<<<ceil_div(n_slots, track::ROWS), 256, 0, s>>>(embedding, fusion_meta + 4, fusion_meta, n_slots, fc_w, fc_b, num_fcs, t.y_cur);
+  SV_CHECK_LAUNCH("track_fc");
+  track::track_fc_kernel<<<ceil_div(capacity, track::ROWS), 256, 0, s>>>(t.bank, nullptr, &t.st->count, capacity, fc_w, fc_b, num_fcs, t.y_bank);
+  SV_CHECK_LAUNCH("track_fc");
+  track::track_score_kernel<<<n_slots, 256, (size_t)(1 + capacity) * sizeof(float), s>>>(t.y_cur, t.y_bank, fusion_meta, n_slots, &t.st->count, capacity,
+                                                                                        t.lik, t.mid, nullptr, 0);
+  SV_CHECK_LAUNCH("track_score");
+  track::track_assign_kernel<<<1, 256, (size_t)capacity * 12, s>>>(t.st, t.bank, capacity, embedding, fusion_meta, n_slots, t.lik, t.mid, track_out);
+  SV_CHECK_LAUNCH("track_assign");
+  return SLOTVPS_OK;
 }
 
 int slotvps_sine_pos(float* out, int h, int w, void* stream) {

@@ -433,3 +433,79 @@ def test_stale_workspace_is_never_read(dev, pos_kind, monkeypatch):
         for s in range(7):
             e = rel(em[t][s], re_[t][s])
             assert e < max(3e-5 * 3.5 ** s, 3e-5), (pos_kind, t, s, e)
+
+
+# ---- tracker -------------------------------------------------------------------------
+def _track_head(dev, seed, mode):
+    th = sv.B200TrackHead(**sv.TRACK_KWARGS)
+    sd = synthetic.make_track_params(seed, mode=mode)
+    th.load_state_dict(sd, strict=True)               # the reference's parameter names
+    fcs = [(sd["fcs_query.%d.weight" % i], sd["fcs_query.%d.bias" % i]) for i in range(2)]
+    return th.to(dev), fcs
+
+
+@pytest.mark.parametrize("mode", ["identity", "random"])
+@pytest.mark.parametrize("k,m", [(1, 1), (22, 37), (100, 333)])
+def test_track_head_scores(dev, mode, k, m):
+    """SimpleTrackHead.forward: [0 | fc(x) fc(ref)^T] vs the oracle (fp32 CUDA cores, different summation order)."""
+    th, fcs = _track_head(dev, 3, mode)
+    g = torch.Generator().manual_seed(k * 1000 + m)
+    x, r = torch.randn(k, 256, generator=g), torch.randn(m, 256, generator=g)
+    got = th(x.to(dev), r.to(dev))
+    assert isinstance(got, list) and len(got) == 1 and got[0].shape == (k, 1 + m)
+    ref = O.track_match_scores(fcs, x, r)
+    assert float(got[0][:, 0].abs().max()) == 0.0
+    assert rel(got[0], ref) < 2e-6
+    both = th(x.to(dev), [r.to(dev), r[: max(1, m // 2)].to(dev)])     # list of banks, as the reference accepts
+    assert len(both) == 2 and both[1].shape == (k, 1 + max(1, m // 2))
+    with pytest.raises(RuntimeError):
+        th(x, r)                                                     # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("name", ["track_a", "track_b", "track_c"])
+def test_tracker_golden_videos(dev, name, golden_dir):
+    """Fusion + on-device tracker over consecutive frames == the reference's simple_test (golden) and the oracle:
+    det_obj_ids, bank length and bank contents after every frame, including the per-video reset."""
+    from tests.test_oracle_golden import TRACK_CASES, track_inputs
+    c = TRACK_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    th, fcs = _track_head(dev, c["seed"], c["mode"])
+    fz = sv.PanopticFusion(**sv.FUSION_KWARGS)
+    trk = sv.SlotTracker(th, n_slots=c["N"], capacity=256, device=dev)
+    st = O.TrackerState()
+    for i, (v, f, logits, masks, emb) in enumerate(track_inputs(c["seed"], c["N"], c["h"], c["w"], g["videos"])):
+        if f == 0:
+            trk.reset()
+            st.reset()
+        fo = fz.fuse(logits.to(dev), masks.to(dev), (4 * c["h"], 4 * c["w"]))
+        rec = sv.SlotTracker.host(trk.step(emb.to(dev), fo))
+        fr = O.panoptic_fuse(logits, masks, (4 * c["h"], 4 * c["w"]))
+        ids_things, ids_all, _ = O.track_step(fcs, st, emb[torch.from_numpy(fr.keep.copy())].numpy(), fr.labels)
+        np.testing.assert_array_equal(rec["ids"], ids_all)
+        np.testing.assert_array_equal(rec["det_obj_ids"], g["ids_%d" % i])
+        assert rec["bank"] == st.bank.shape[0] == g["bank_sum_%d" % i].shape[0]
+        bank = trk.bank().cpu().numpy()
+        np.testing.assert_array_equal(bank, st.bank)                  # raw embeddings are copied, never recomputed
+        np.testing.assert_allclose(bank.astype(np.float64).sum(1), g["bank_sum_%d" % i], rtol=0, atol=1e-9)
+
+
+def test_tracker_capacity_and_empty(dev):
+    """Bank overflow is reported, not silently dropped; a frame with no kept slot leaves the state untouched."""
+    th, _ = _track_head(dev, 0, "identity")
+    N = 100
+    fz = sv.PanopticFusion(**sv.FUSION_KWARGS)
+    trk = sv.SlotTracker(th, n_slots=N, capacity=8, device=dev)
+    logits, masks, _ = synthetic.make_fusion_case(7, N, 16, 32)
+    fo = fz.fuse(logits.to(dev), masks.to(dev), (64, 128))
+    out = trk.step(synthetic.make_track_sequence(0, N, 1)[0].to(dev), fo)
+    assert int(out[3]) == 1 and int(out[2]) == 8
+    with pytest.raises(RuntimeError):
+        sv.SlotTracker.host(out)
+    trk2 = sv.SlotTracker(th, n_slots=N, capacity=64, device=dev)
+    none = torch.full((N, 20), -4.0)
+    none[:, 19] = 4.0
+    fo0 = fz.fuse(none.to(dev), masks.to(dev), (64, 128))
+    rec = sv.SlotTracker.host(trk2.step(torch.zeros(N, 256, device=dev), fo0))
+    assert rec["k"] == 0 and rec["bank"] == 0
+    rec = sv.SlotTracker.host(trk2.step(synthetic.make_track_sequence(0, N, 1)[0].to(dev), fo))
+    assert rec["ids"].tolist() == list(range(rec["k"]))               # still the "first frame" of the video
