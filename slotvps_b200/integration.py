@@ -8,8 +8,8 @@ before ``build_detector`` runs.  Two levels:
 L1  ``patch_reference(level=1)``: ``MultiScaleDynamicMaskHead`` -> ``B200DynamicMaskHead``.  Everything else,
     including ``simple_test``, runs as in the reference.
 L2  ``patch_reference(level=2)``: additionally re-points ``DETECTORS['VPS_Temporal_Slots']`` at a subclass
-    whose ``generate_final_outputs`` / ``postprocess_panoptic`` / panoptic fusion run on the B200
-    kernels.  The subclass's ``simple_test`` is written here from scratch against the reference's
+    whose ``generate_final_outputs`` / ``postprocess_panoptic`` / panoptic fusion / tracker (SimpleTrackHead
+    scores + greedy id assignment, object bank in device memory) run on the B200 kernels.  The subclass's ``simple_test`` is written here from scratch against the reference's
     sub-module API (no reference lines are copied); it returns the same dict keys / dtypes
     (vps_temporal_slots.py:459-465) that tools/test_vpq.py:41-53 consumes.
 
@@ -19,11 +19,11 @@ from __future__ import annotations
 
 import importlib
 
-import numpy as np
 import torch
 
 from .head import B200DynamicMaskHead
 from .retriever import PanopticFusion, mask_logits
+from .tracker import B200TrackHead, SlotTracker
 
 
 def patch_reference(level: int = 1):
@@ -66,8 +66,6 @@ def make_b200_detector(base, Instances):
             iid = meta["iid"]
             div = 100000 if self.num_classes in (23, 24) else 10000
             first = (iid % div) == 1
-            if first:
-                self.prev_embedding = None
             ref = ref_img[0]
             # reference sub-modules, unchanged: backbone -> neck -> semantic head -> 1x1 conv
             feats = []
@@ -85,16 +83,11 @@ def make_b200_detector(base, Instances):
             h = fo.host()
             if h["k"] == 0:
                 raise ValueError("no slot survives the score/class filter (the reference raises here as well)")
-            thing = h["labels"] > self.stuff_num - 1
-            # tracker (vps_temporal_slots.py:332-409) stays in the reference's host code; it consumes the
-            # kept slots' output embeddings.  First frame of a video: ids are the kept-slot positions.
-            keep = torch.as_tensor(h["keep"], device=emb[-1].device)
-            cur_emb = emb[-1][-1, 0][keep]
-            if self.prev_embedding is None or not hasattr(self, "temporal_track_head"):
-                obj_ids = np.arange(h["k"])[thing]
-            else:
-                obj_ids = self._track(cur_emb, thing)
-            self.prev_embedding = cur_emb if self.prev_embedding is None else self.prev_embedding
+            # tracker (vps_temporal_slots.py:232-237, :332-409): object bank and greedy assignment on the device
+            if first or getattr(self, "_b200_tracker", None) is None:
+                self._b200_tracker = self._make_tracker(emb[-1].device, q.shape[0])
+            rec = SlotTracker.host(self._b200_tracker.step(emb[-1][-1, 0], fo))
+            obj_ids = rec["det_obj_ids"]
             sem = torch.softmax(fcn_output, 1).argmax(1)[:, :H, :W]
             return {
                 "fcn_outputs": sem,
@@ -104,35 +97,15 @@ def make_b200_detector(base, Instances):
                 "panoptic_outputs": fo.panoptic[None, :H, :W],
             }
 
-        def _track(self, cur_emb, thing):
-            """Greedy association against the stored embeddings through the reference's SimpleTrackHead."""
-            score = self.temporal_track_head(cur_emb, self.prev_embedding)[0]
-            logp = torch.log_softmax(score, 1)
-            best, idx = logp.max(1)
-            best, idx = best.cpu().numpy(), idx.cpu().numpy()
-            n_prev = self.prev_embedding.shape[0]
-            ids = -np.ones(len(idx), dtype=np.int64)
-            owner_score = np.full(n_prev, -np.inf)
-            owner = -np.ones(n_prev, dtype=np.int64)
-            extra = []
-            for i, m in enumerate(idx):
-                if m == 0:
-                    ids[i] = n_prev + len(extra); extra.append(i)
-                elif best[i] > owner_score[m - 1]:
-                    if owner[m - 1] >= 0:
-                        ids[owner[m - 1]] = -1
-                    owner[m - 1], owner_score[m - 1], ids[i] = i, best[i], m - 1
-            for i in range(len(ids)):
-                if ids[i] < 0:
-                    ids[i] = n_prev + len(extra); extra.append(i)
-            new = self.prev_embedding.clone()
-            for j in range(n_prev):
-                if owner[j] >= 0:
-                    new[j] = cur_emb[owner[j]]
-            if extra:
-                new = torch.cat([new, cur_emb[torch.as_tensor(extra, device=cur_emb.device)]], 0)
-            self.prev_embedding = new
-            return ids[thing]
+        def _make_tracker(self, device, n_slots):
+            """SlotTracker over the reference's SimpleTrackHead parameters (same names: fcs_query.{i}.weight/bias)."""
+            ref_head = getattr(self, "temporal_track_head", None)
+            n_fc = ref_head.num_fcs_query if ref_head is not None else 0
+            th = B200TrackHead(num_fcs_query=n_fc, in_channels_query=256)
+            if n_fc:
+                th.load_state_dict(ref_head.state_dict(), strict=True)
+            return SlotTracker(th.to(device), n_slots=n_slots, capacity=self.other_config.get("b200_track_capacity", 1024),
+                               device=device)
 
     B200VPSTemporalSlots.__name__ = "VPS_Temporal_Slots"
     return B200VPSTemporalSlots
