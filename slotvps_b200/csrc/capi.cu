@@ -601,7 +601,10 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
       const long rows = (long)T * P;
       Ptr8 src;
       for (int t = 0; t < SLOTVPS_MAX_FRAMES; ++t) src.p[t] = t < T ? feats[t * L + l] : nullptr;
-      split_in_kernel<<<dim3(ceil_div(P, 32), T), 256, 0, s>>>(src, w.ftc.in_planes, rows, P);
+      bool vec4 = P % 4 == 0;
+      for (int t = 0; t < T; ++t) vec4 = vec4 && ((uintptr_t)src.p[t] & 15) == 0;
+      if (vec4) split_in4_kernel<<<dim3(ceil_div(P, 128), T), 256, 0, s>>>(src, w.ftc.in_planes, rows, P);
+      else split_in_kernel<<<dim3(ceil_div(P, 32), T), 256, 0, s>>>(src, w.ftc.in_planes, rows, P);
       SV_CHECK_LAUNCH("split_in");
       fuse::Params prm;
       memset(&prm, 0, sizeof(prm));

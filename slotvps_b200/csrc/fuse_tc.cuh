@@ -70,6 +70,35 @@ __global__ void __launch_bounds__(256) split_in_kernel(Ptr8 src, __half* __restr
     out[rows * (CIN / 2) + o] = __halves2half2(l0, l1);
   }
 }
+// Same conversion without shared memory for P % 4 == 0 and 16-byte aligned frames: a thread owns 4 consecutive
+// pixels x 16 channels (16 coalesced 128-bit loads along the pixel axis) and writes, per pixel, one full 32-byte
+// sector of the hi plane and one of the lo plane (256-bit stores).  Warp w of a block takes channel group w.
+__global__ void __launch_bounds__(256) split_in4_kernel(Ptr8 src, __half* __restrict__ planes, long rows, int P) {
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, t = blockIdx.y;
+  const int p = (blockIdx.x * 32 + lane) * 4;
+  if (p >= P) return;
+  const float* __restrict__ X = src.p[t] + (long)(g * 16) * P + p;
+  float4 x[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) x[c] = __ldg(reinterpret_cast<const float4*>(X + (long)c * P));
+  __half* hi = planes + ((long)t * P + p) * CIN + g * 16;
+  __half* lo = hi + rows * CIN;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t wh[8], wl[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float a = i == 0 ? x[2 * c].x : i == 1 ? x[2 * c].y : i == 2 ? x[2 * c].z : x[2 * c].w;
+      const float b = i == 0 ? x[2 * c + 1].x : i == 1 ? x[2 * c + 1].y : i == 2 ? x[2 * c + 1].z : x[2 * c + 1].w;
+      __half h0, l0, h1, l1;
+      split_bf16(a, h0, l0); split_bf16(b, h1, l1);
+      __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+      wh[c] = *reinterpret_cast<uint32_t*>(&hh); wl[c] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    tc::st_global_v8(hi + (long)i * CIN, wh);
+    tc::st_global_v8(lo + (long)i * CIN, wl);
+  }
+}
 // fp32 weight [256][ld] columns [col0, col0+K) -> fp16 hi/lo planes [2][256][K]
 __global__ void __launch_bounds__(256) conv_planes_kernel(const float* __restrict__ W, int ld, int col0, int K, __half* __restrict__ out) {
   int i = blockIdx.x * 256 + threadIdx.x;
@@ -192,24 +221,24 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] += bias[j * 32 + c];
         if (prm.y_out) {
-          float4* dst = reinterpret_cast<float4*>(prm.y_out + (long)row * C + j * 32);
+          float* dst = prm.y_out + (long)row * C + j * 32;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          for (int c = 0; c < 4; ++c) tc::st_global_v8f(dst + 8 * c, v + 8 * c);
           continue;
         }
         if (prm.y_in) {
-          const float4* a = reinterpret_cast<const float4*>(prm.y_in + (long)i00 * C + j * 32);
-          const float4* b = reinterpret_cast<const float4*>(prm.y_in + (long)i01 * C + j * 32);
-          const float4* cc = reinterpret_cast<const float4*>(prm.y_in + (long)i10 * C + j * 32);
-          const float4* d = reinterpret_cast<const float4*>(prm.y_in + (long)i11 * C + j * 32);
+          const float* a = prm.y_in + (long)i00 * C + j * 32;
+          const float* b = prm.y_in + (long)i01 * C + j * 32;
+          const float* cc = prm.y_in + (long)i10 * C + j * 32;
+          const float* d = prm.y_in + (long)i11 * C + j * 32;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 ya = __ldg(a + c), yb = __ldg(b + c), yc = __ldg(cc + c), yd = __ldg(d + c);
+          for (int c = 0; c < 4; ++c) {
+            float ya[8], yb[8], yc[8], yd[8];
+            tc::ld_global_nc_v8f(a + 8 * c, ya); tc::ld_global_nc_v8f(b + 8 * c, yb);
+            tc::ld_global_nc_v8f(cc + 8 * c, yc); tc::ld_global_nc_v8f(d + 8 * c, yd);
             // same association as F.interpolate: (1-ly)*((1-lx)*v00 + lx*v01) + ly*((1-lx)*v10 + lx*v11), weights pre-multiplied
-            v[4 * c] += w00 * ya.x + w01 * yb.x + w10 * yc.x + w11 * yd.x;
-            v[4 * c + 1] += w00 * ya.y + w01 * yb.y + w10 * yc.y + w11 * yd.y;
-            v[4 * c + 2] += w00 * ya.z + w01 * yb.z + w10 * yc.z + w11 * yd.z;
-            v[4 * c + 3] += w00 * ya.w + w01 * yb.w + w10 * yc.w + w11 * yd.w;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[8 * c + e] += w00 * ya[e] + w01 * yb[e] + w10 * yc[e] + w11 * yd[e];
           }
         }
         if (prm.out) {
@@ -229,9 +258,8 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           };
           auto store = [&](int plane, const uint32_t* w) {
-            uint4* dst = reinterpret_cast<uint4*>(prm.planes + ((long)plane * prm.plane_stride + row) * C + j * 32);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+            __half* dst = prm.planes + ((long)plane * prm.plane_stride + row) * C + j * 32;
+            tc::st_global_v8(dst, w); tc::st_global_v8(dst + 16, w + 8);
           };
           pack(v); store(0, hi); store(1, lo);
           if (prm.x_planes_only) continue;

@@ -161,5 +161,22 @@ inline int make_tmap_h16_sw128(CUtensorMap* m, const void* base, uint64_t rows, 
   return SLOTVPS_OK;
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per thread and request.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+               "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v8f(void* p, const float* w) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[3]), "f"(w[4]),
+               "f"(w[5]), "f"(w[6]), "f"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8f(const void* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+
 }  // namespace tc
 }  // namespace slotvps
