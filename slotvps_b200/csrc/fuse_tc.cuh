@@ -209,6 +209,22 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         i00 = base + y0 * cw + x0; i01 = base + y0 * cw + x1; i10 = base + y1 * cw + x0; i11 = base + y1 * cw + x1;
         w00 = (1.f - ly) * (1.f - lx); w01 = (1.f - ly) * lx; w10 = ly * (1.f - lx); w11 = ly * lx;
       }
+      // cooperative gather (w % 32 == 0: a warp's 32 pixels share one image row and one frame)
+      const bool coop = prm.y_in != nullptr && (prm.w & 31) == 0;
+      int cbase = 0, cy0 = 0, cy1 = 0, ccol = 0, cs0 = 0, cs1 = 0;
+      float cwy0 = 0.f, cwy1 = 0.f, cwx0 = 0.f, cwx1 = 0.f;
+      if (coop) {
+        const int ch = prm.h / 2, cw = prm.w / 2;
+        const float sy = fmaxf((py + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((px + 0.5f) * 0.5f - 0.5f, 0.f);
+        cy0 = (int)sy; cy1 = min(cy0 + 1, ch - 1);
+        cwy1 = sy - cy0; cwy0 = 1.f - cwy1;
+        const int x0 = (int)sx, x1 = min(x0 + 1, cw - 1);
+        cwx1 = sx - x0; cwx0 = 1.f - cwx1;
+        const int first = (px - lane) / 2 - 1;                 // coarse column fetched by lane 0 (clamped below)
+        cs0 = x0 - first; cs1 = x1 - first;
+        ccol = min(max(first + lane, 0), cw - 1);
+        cbase = t * ch * cw;
+      }
       tc::mbar_wait(&tfull[g], u & 1);
       tc::tc_fence_after();
 #pragma unroll 1
@@ -226,7 +242,29 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int c = 0; c < 4; ++c) tc::st_global_v8f(dst + 8 * c, v + 8 * c);
           continue;
         }
-        if (prm.y_in) {
+        if (coop) {
+          // the 32 pixels of this warp lie in one image row: lanes 0..17 fetch the 18 coarse columns the row segment
+          // touches (two coarse rows each, blended vertically), every lane then takes its two columns by shuffle
+          const float* r0 = prm.y_in + (long)(cbase + cy0 * (prm.w / 2) + ccol) * C + j * 32;
+          const float* r1 = prm.y_in + (long)(cbase + cy1 * (prm.w / 2) + ccol) * C + j * 32;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float ta[8], tb[8];
+            if (lane < 18) {
+              tc::ld_global_nc_v8f(r0 + 8 * c, ta); tc::ld_global_nc_v8f(r1 + 8 * c, tb);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) ta[e] = cwy0 * ta[e] + cwy1 * tb[e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) ta[e] = 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float u0 = __shfl_sync(0xffffffffu, ta[e], cs0), u1 = __shfl_sync(0xffffffffu, ta[e], cs1);
+              v[8 * c + e] += cwx0 * u0 + cwx1 * u1;
+            }
+          }
+        } else if (prm.y_in) {
           const float* a = prm.y_in + (long)i00 * C + j * 32;
           const float* b = prm.y_in + (long)i01 * C + j * 32;
           const float* cc = prm.y_in + (long)i10 * C + j * 32;
