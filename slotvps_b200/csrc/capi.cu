@@ -571,7 +571,8 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
     SV_CHECK_CUDA(cudaEventRecord(fork, s));
     SV_CHECK_CUDA(cudaStreamWaitEvent(sb, fork, 0));
   }
-  const int side_ctas = overlap ? SIDE_CTAS : 148;
+  int side_ctas = overlap ? SIDE_CTAS : 148;
+  if (const char* e = overlap ? getenv("SLOTVPS_SIDE_CTAS") : nullptr) { const int v = atoi(e); if (v >= 16 && v <= 148) side_ctas = v; }
   int stage = 0;
   bool prev_planes = false;
   for (int l = 0; l < L; ++l) {
