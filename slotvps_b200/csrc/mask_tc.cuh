@@ -14,7 +14,7 @@ namespace slotvps {
 namespace mask {
 constexpr int TILE_M = 128;
 constexpr int NROW = attn::NROW, NPAD = attn::NPAD;
-constexpr int SLOT_BYTES = 16384, NSLOT = 6;
+constexpr int SLOT_BYTES = 16384, NSLOT = 7;
 constexpr int E_SUB = NROW * 128;
 constexpr int E_BYTES = 2 * 4 * E_SUB;
 constexpr int OFF_E = NSLOT * SLOT_BYTES;
