@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from slotvps_b200.parallel import gather_id_maps, shard_clips
+from slotvps_b200.parallel import WIRE_DTYPE, gather_id_maps, shard_clips
 
 
 def _free_port():
@@ -25,6 +25,8 @@ def _worker(rank, world, port, n_clips, q):
     # stand-in for the per-clip hot path: an id map that encodes the clip index
     local = torch.stack([torch.full((4, 6), c, dtype=torch.int64) for c in mine]) if mine else torch.zeros((0, 4, 6), dtype=torch.int64)
     allmaps = gather_id_maps(local, n_clips, dist)
+    wire = gather_id_maps(local, n_clips, dist, wire_dtype=WIRE_DTYPE)          # int16 on the wire, same ids
+    assert wire.dtype == WIRE_DTYPE and torch.equal(wire.to(torch.int64), allmaps)
     q.put((rank, mine, allmaps[:, 0, 0].tolist()))
     dist.destroy_process_group()
 
