@@ -8,8 +8,14 @@ rows = list(csv.reader(open(sys.argv[1])))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 H = rows[hdr]
 ki, vi, ui = H.index("Kernel Name"), H.index("Metric Value"), H.index("Metric Unit")
+body = [r for r in rows[hdr + 1:] if len(r) > vi]
+# one full step = the launches after the second-to-last fuse_relabel (last kernel of a step) up to the last one
+ends = [i for i, r in enumerate(body) if "fuse_relabel" in r[ki]]
+if len(ends) >= 2 and "--all" not in sys.argv:
+    body = body[ends[-2] + 1:ends[-1] + 1]
+    print(f"# one step: launches {ends[-2] + 1}..{ends[-1]} of the capture")
 agg = collections.defaultdict(lambda: [0, 0.0])
-for r in rows[hdr + 1:]:
+for r in body:
     if len(r) <= vi:
         continue
     name = r[ki].split("(")[0].replace("void ", "").replace("slotvps::", "")[:60]
