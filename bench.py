@@ -415,7 +415,11 @@ def main():
         ml = [k for k in breakdown if k in ("mask_prep", "feat_rnorm", "mask_logits_tc")]
         if roofline is not None:
             step_ms = single_ms if single_ms else ms / K
-            roofline["share_of_step"] = roofline["ms_per_step"] / step_ms        # vs the single-clip-in-flight step time
+            # share of the serialised kernel time of one step (the definition an ncu launch list gives: profiles/
+            # r1_tc_launches_summary.txt) and, separately, of the wall time of a step with one clip in flight (two streams overlap)
+            ktot = sum(v["ms_per_step"] for k, v in breakdown.items() if k != "copy")
+            roofline["share_of_step"] = roofline["ms_per_step"] / ktot
+            roofline["share_of_single_clip_wall_step"] = roofline["ms_per_step"] / step_ms
             hb = {"peak_gbs": pk["hbm_gbs"], "peak_source": pk["source"] + " copy bandwidth"}
             if "mask_tc" in breakdown:      # mask-logit projection: read 4*C*P3 (as 2 fp16 hi/lo planes = same bytes) + write 4*N*P3
                 by = 4 * 256 * P3 + 4 * N * P3
