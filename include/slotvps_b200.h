@@ -87,6 +87,15 @@ int slotvps_prepared_bytes(const slotvps_head_desc* d, size_t* bytes);
 int slotvps_prepare_weights(const slotvps_head_desc* d, const slotvps_stage_params* stages /*[n_stages]*/,
                             const float* conv_trans_w /*[256,384]*/, const float* conv_trans_b /*[256]*/,
                             void* prepared, void* stream);
+/* Same, with the 1x1 input transform of the caller folded into the level fusion:
+ * semantic_trans_ins applies VPS_Capsule.conv_trans (Conv2d(128,128,1) + bias, no norm / activation,
+ * vps_capsule.py:74-79, vps_temporal_slots.py:129-135) to every level before the head.  With
+ * in_trans_w [128,128] / in_trans_b [128] given, slotvps_head_forward takes the UN-transformed semantic-head
+ * features and (W_b T) f + (W_b t + b) replaces W_b (T f + t) + b, which removes that pass (5.7 GFLOP and one
+ * read + write of every input level per frame).  NULL / NULL = slotvps_prepare_weights.                  */
+int slotvps_prepare_weights_ex(const slotvps_head_desc* d, const slotvps_stage_params* stages, const float* conv_w,
+                               const float* conv_b, const float* in_trans_w, const float* in_trans_b, void* prepared,
+                               void* stream);
 
 /* MultiScaleDynamicMaskHead.forward (dynamic_mask_head.py:138-228), bs == 1.
  *   feats[t*n_levels+l] : [128,h_l,w_l]     input features (the reference's features[t][l][0])

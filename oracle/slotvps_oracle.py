@@ -496,3 +496,10 @@ def track_step(fcs, state: TrackerState, embedding: np.ndarray, labels: np.ndarr
     top2 = np.sort(score.numpy(), 1)[:, -2:] if score.shape[1] > 1 else None
     info["top2_gap"] = float((top2[:, 1] - top2[:, 0]).min()) if top2 is not None and K else float("inf")
     return ids[things], ids, info
+
+
+def input_transform(features, weight: torch.Tensor, bias: torch.Tensor):
+    """semantic_trans_ins, vps_temporal_slots.py:129-135: VPS_Capsule.conv_trans (1x1 conv 128->128 + bias, no norm,
+    no activation) on every level.  features T x L x [1,128,h,w]."""
+    w = weight.reshape(weight.shape[0], -1)
+    return [[torch.einsum("oc,bchw->bohw", w.to(f.dtype), f) + bias.to(f.dtype)[None, :, None, None] for f in fr] for fr in features]

@@ -96,6 +96,7 @@ SYMBOLS = {
     "slotvps_head_workspace_bytes": (C.c_int, [C.POINTER(HeadDesc), C.POINTER(C.c_size_t)]),
     "slotvps_prepared_bytes": (C.c_int, [C.POINTER(HeadDesc), C.POINTER(C.c_size_t)]),
     "slotvps_prepare_weights": (C.c_int, [C.POINTER(HeadDesc), C.POINTER(StageParams), P, P, P, P]),
+    "slotvps_prepare_weights_ex": (C.c_int, [C.POINTER(HeadDesc), C.POINTER(StageParams), P, P, P, P, P, P]),
     "slotvps_head_forward": (C.c_int, [C.POINTER(HeadDesc), C.POINTER(StageParams), P, C.POINTER(P), C.POINTER(P),
                                        C.POINTER(P), P, P, C.POINTER(P), P, C.c_size_t, P]),
     "slotvps_level_fuse": (C.c_int, [P, P, P, P, P, C.c_int, C.c_int, P, P]),

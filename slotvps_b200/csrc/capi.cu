@@ -65,7 +65,8 @@ struct PreparedStage {
 };
 struct Prepared {
   float* W0;                            // level-0 folded conv weight [256,128]
-  float *conv_w, *conv_b;               // copies of conv_trans.conv.{weight [256,384], bias [256]}
+  float *conv_w, *conv_b;               // conv_trans.conv.{weight [256,384], bias [256]} (with the input transform folded in)
+  float* conv_b0;                       // bias of level 0 (differs from conv_b only when an input transform is folded)
   FuseTcWeights ftc;                    // fp16 hi/lo planes of the folded conv_trans weights
   PreparedStage st[SLOTVPS_MAX_STAGES];
 };
@@ -74,7 +75,7 @@ static size_t prepared_layout(const slotvps_head_desc* d, void* base, Prepared* 
   Arena a(base, (size_t)-1);
   Prepared p;
   p.W0 = a.take<float>((size_t)C * CIN);
-  p.conv_w = a.take<float>((size_t)C * 3 * CIN); p.conv_b = a.take<float>(C);
+  p.conv_w = a.take<float>((size_t)C * 3 * CIN); p.conv_b = a.take<float>(C); p.conv_b0 = a.take<float>(C);
   p.ftc.w0 = a.take<__half>((size_t)2 * C * CIN); p.ftc.wa = a.take<__half>((size_t)2 * C * C); p.ftc.wb = a.take<__half>((size_t)2 * C * CIN);
   const int S = n_stages_of(d);
   for (int s = 0; s < S; ++s) {
@@ -116,6 +117,28 @@ __global__ void __launch_bounds__(256) fold_w0_kernel(const float* __restrict__ 
   int o = i / CIN, c = i % CIN;
   const float* r = W + (long)o * (3 * CIN);
   W0[i] = (float)((double)r[c] + (double)r[CIN + c] + (double)r[2 * CIN + c]);
+}
+// Fold a 1x1 input transform x = T f + t (VPS_Capsule.conv_trans applied by semantic_trans_ins,
+// vps_temporal_slots.py:129-135) into a conv block acting on x:  W x + b = (W T) f + (W t + b).
+// One block per output row o; W rows have stride ld; in place is allowed (the row is staged first).
+__global__ void __launch_bounds__(CIN) fold_in_trans_kernel(const float* __restrict__ Wsrc, int ld, const float* __restrict__ T,
+                                                            const float* __restrict__ t, const float* __restrict__ b_in,
+                                                            float* __restrict__ Wdst, int ld_dst, float* __restrict__ b_out) {
+  __shared__ float row[CIN];
+  __shared__ double red[CIN];
+  const int o = blockIdx.x, c = threadIdx.x;
+  row[c] = Wsrc[(long)o * ld + c];
+  __syncthreads();
+  double acc = 0.0;
+  for (int k = 0; k < CIN; ++k) acc += (double)row[k] * (double)T[k * CIN + c];
+  red[c] = (double)row[c] * (double)t[c];
+  __syncthreads();
+  Wdst[(long)o * ld_dst + c] = (float)acc;
+  if (c == 0) {
+    double sb = 0.0;
+    for (int k = 0; k < CIN; ++k) sb += red[k];
+    b_out[o] = (float)((double)b_in[o] + sb);
+  }
 }
 __global__ void __launch_bounds__(256) copy_kernel(const float* __restrict__ src, float* __restrict__ dst, long n) {
   long i = (long)blockIdx.x * 256 + threadIdx.x;
@@ -470,8 +493,15 @@ int slotvps_prepared_bytes(const slotvps_head_desc* d, size_t* bytes) {
 
 int slotvps_prepare_weights(const slotvps_head_desc* d, const slotvps_stage_params* stages, const float* conv_w,
                             const float* conv_b, void* prepared, void* stream) {
+  return slotvps_prepare_weights_ex(d, stages, conv_w, conv_b, nullptr, nullptr, prepared, stream);
+}
+
+int slotvps_prepare_weights_ex(const slotvps_head_desc* d, const slotvps_stage_params* stages, const float* conv_w,
+                               const float* conv_b, const float* in_trans_w, const float* in_trans_b, void* prepared,
+                               void* stream) {
   SV_TRY(validate(d));
   SV_REQUIRE(stages && conv_w && conv_b && prepared, "null argument");
+  SV_REQUIRE((in_trans_w == nullptr) == (in_trans_b == nullptr), "in_trans_w and in_trans_b go together");
   cudaStream_t s = (cudaStream_t)stream;
   Prepared p;
   prepared_layout(d, prepared, &p);
@@ -479,11 +509,20 @@ int slotvps_prepare_weights(const slotvps_head_desc* d, const slotvps_stage_para
   SV_CHECK_LAUNCH("fold_w0");
   SV_TRY(dcopy(conv_w, p.conv_w, (long)C * 3 * CIN, s));
   SV_TRY(dcopy(conv_b, p.conv_b, C, s));
+  SV_TRY(dcopy(conv_b, p.conv_b0, C, s));
+  if (in_trans_w) {
+    // the head then takes the UN-transformed semantic-head features: level 0 (W0 = Wa1 + Wa2 + Wb on cat(x,x,x)) and
+    // the x block of the other levels absorb T; each gets its own bias
+    fold_in_trans_kernel<<<C, CIN, 0, s>>>(p.W0, CIN, in_trans_w, in_trans_b, conv_b, p.W0, CIN, p.conv_b0);
+    SV_CHECK_LAUNCH("fold_in_trans");
+    fold_in_trans_kernel<<<C, CIN, 0, s>>>(p.conv_w + 2 * CIN, 3 * CIN, in_trans_w, in_trans_b, conv_b, p.conv_w + 2 * CIN, 3 * CIN, p.conv_b);
+    SV_CHECK_LAUNCH("fold_in_trans");
+  }
   conv_planes_kernel<<<ceil_div(C * CIN, 256), 256, 0, s>>>(p.W0, CIN, 0, CIN, p.ftc.w0);
   SV_CHECK_LAUNCH("conv_planes");
-  conv_planes_kernel<<<ceil_div(C * C, 256), 256, 0, s>>>(conv_w, 3 * CIN, 0, C, p.ftc.wa);
+  conv_planes_kernel<<<ceil_div(C * C, 256), 256, 0, s>>>(p.conv_w, 3 * CIN, 0, C, p.ftc.wa);
   SV_CHECK_LAUNCH("conv_planes");
-  conv_planes_kernel<<<ceil_div(C * CIN, 256), 256, 0, s>>>(conv_w, 3 * CIN, 2 * CIN, CIN, p.ftc.wb);
+  conv_planes_kernel<<<ceil_div(C * CIN, 256), 256, 0, s>>>(p.conv_w, 3 * CIN, 2 * CIN, CIN, p.ftc.wb);
   SV_CHECK_LAUNCH("conv_planes");
   const int S = n_stages_of(d);
   for (int i = 0; i < S; ++i) {
@@ -618,7 +657,7 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
         memset(&prm, 0, sizeof(prm));
       }
       prm.rows = (int)rows; prm.P = P; prm.w = wd; prm.h = h; prm.ksub = 2; prm.a_lo_row = (int)rows;
-      prm.bias = pr.conv_b; prm.y_in = l > 0 ? w.ftc.y : nullptr;
+      prm.bias = l > 0 ? pr.conv_b : pr.conv_b0; prm.y_in = l > 0 ? w.ftc.y : nullptr;
       prm.out = fused_out[l]; prm.out_bs = fstride[l];
       prm.planes = tcl.planes; prm.plane_stride = rows; prm.x_planes_only = pos_sep ? 1 : 0;
       if (d->pos_mode == 1) { prm.pos = pos[l]; prm.pos_bs = pstride[l]; }
@@ -630,7 +669,7 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
       SV_TRY(fuse_tc_launch(w.ftc.in_planes, 2 * rows, (int)rows, CIN, l > 0 ? pr.ftc.wb : pr.ftc.w0, prm, s, side_ctas));
     } else {
       for (int t = 0; t < T; ++t)
-        SV_TRY(level_fuse_frame(l > 0 ? fused_out[t * L + l - 1] : nullptr, feats[t * L + l], pr.conv_w, pr.conv_b, pr.W0,
+        SV_TRY(level_fuse_frame(l > 0 ? fused_out[t * L + l - 1] : nullptr, feats[t * L + l], pr.conv_w, l > 0 ? pr.conv_b : pr.conv_b0, pr.W0,
                                 fused_out[t * L + l], h, wd, w.ybuf + (long)t * C * (P / 4 + 1), s));
       if (use_tc && d->heads_per_level[l] > 0) {
         SV_TRY(tc_split_level(fused_out[l], fstride[l], pl, pls, d->pos_mode == 2 && all_tc, tcl, T, h, wd, s));

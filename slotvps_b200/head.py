@@ -140,6 +140,7 @@ class B200DynamicMaskHead(nn.Module):
             stage += per_dh_num_heads[i]
         self.conv_trans = _ConvParams(trans_in_dim, dh_dim)
         self._prepared = None           # (key, buffer, StageParams array)
+        self._in_trans = None           # (weight [128,128], bias [128]) of a folded 1x1 input transform
         self._last_call = None
         self._ws = {}
         for p in self.parameters():
@@ -182,6 +183,19 @@ class B200DynamicMaskHead(nn.Module):
         d.temporal_mask, d.pos_mode, d.kernel_path = mask, pos_mode, self.kernel_path
         return d
 
+    def fold_input_transform(self, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor]):
+        """Fold the caller's 1x1 input transform (VPS_Capsule.conv_trans, applied by semantic_trans_ins,
+        vps_temporal_slots.py:129-135) into the level fusion: afterwards ``forward`` takes the UN-transformed
+        semantic-head features.  weight [128,128(,1,1)], bias [128]; ``None, None`` removes the fold."""
+        if weight is None:
+            self._in_trans = None
+        else:
+            dev = next(self.parameters()).device
+            w = weight.detach().reshape(128, 128).to(dev, torch.float32).contiguous()
+            b = bias.detach().reshape(128).to(dev, torch.float32).contiguous()
+            self._in_trans = (w, b)
+        self._prepared = None
+
     def _prepare(self, d, device):
         key = (self._param_key(), self.kernel_path)
         if self._prepared is not None and self._prepared[0] == key:
@@ -192,8 +206,12 @@ class B200DynamicMaskHead(nn.Module):
         buf = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
         table = self._stage_table()
         w = self.conv_trans.conv.weight
-        _lib.check(L.slotvps_prepare_weights(C.byref(d), table, w.data_ptr(), self.conv_trans.conv.bias.data_ptr(),
-                                             buf.data_ptr(), _stream_ptr(device)), "slotvps_prepare_weights")
+        if self._in_trans is not None:
+            self._in_trans = tuple(t.to(device) for t in self._in_trans)
+        tw, tb = self._in_trans if self._in_trans is not None else (None, None)
+        _lib.check(L.slotvps_prepare_weights_ex(C.byref(d), table, w.data_ptr(), self.conv_trans.conv.bias.data_ptr(),
+                                                None if tw is None else tw.data_ptr(), None if tb is None else tb.data_ptr(),
+                                                buf.data_ptr(), _stream_ptr(device)), "slotvps_prepare_weights")
         self._prepared = (key, buf, table)
         return buf, table
 

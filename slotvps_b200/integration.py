@@ -67,13 +67,20 @@ def make_b200_detector(base, Instances):
             div = 100000 if self.num_classes in (23, 24) else 10000
             first = (iid % div) == 1
             ref = ref_img[0]
-            # reference sub-modules, unchanged: backbone -> neck -> semantic head -> 1x1 conv
+            # reference sub-modules, unchanged: backbone -> neck -> semantic head.  semantic_trans_ins' 1x1 conv
+            # (VPS_Capsule.conv_trans, :129-135) is folded into the head's level fusion when it is a plain conv + bias.
+            ct = im.conv_trans
+            foldable = (not getattr(ct, "with_norm", False) and not getattr(ct, "with_activatation", False)
+                        and ct.conv.kernel_size == (1, 1) and ct.conv.bias is not None)
+            if foldable and getattr(self, "_b200_folded", None) is not ct.conv.weight:
+                im.dynamic_mask_head.fold_input_transform(ct.conv.weight, ct.conv.bias)
+                self._b200_folded = ct.conv.weight
             feats = []
             for x in (ref, img):
                 y = im.backbone(x)
                 y = im.neck(y) if im.with_neck else y
                 fcn_output, _, fcn_feature = self.extract_semantic_feats(y)
-                feats.append([im.conv_trans(f) for f in fcn_feature])
+                feats.append(list(fcn_feature) if foldable else [ct(f) for f in fcn_feature])
             q = im.init_mask_query.weight
             cls, emb, fused = im.dynamic_mask_head(features=feats, init_masks=[q, q], pad_mask=None, pos="sine",
                                                    query_pos=None, gt_non_void_mask=None)

@@ -232,3 +232,11 @@ def make_track_sequence(seed: int, n_slots: int, frames: int, channels: int = 25
         e = protos[torch.tensor(ident)] + torch.randn((n_slots, channels), generator=g) * noise
         out.append(e.contiguous())
     return out
+
+
+def make_in_trans_params(seed: int, channels: int = 128):
+    """Synthetic VPS_Capsule.conv_trans (ConvModule(128,128,1, activation=None), vps_capsule.py:74-79) under the
+    reference's parameter names: the 1x1 transform semantic_trans_ins applies to every level before the head."""
+    g = torch.Generator().manual_seed(70_000 + seed)
+    return {"conv_trans.conv.weight": torch.randn((channels, channels, 1, 1), generator=g) * (1.2 / channels ** 0.5),
+            "conv_trans.conv.bias": torch.randn((channels,), generator=g) * 0.2}

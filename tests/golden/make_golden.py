@@ -132,6 +132,32 @@ def gen_fusion(model, name, seed, N, h, w, **kw):
         masks_nnz=(captured["masks"] != 0).sum((1, 2)).numpy())
 
 
+def gen_head_intrans(model, name="head_intrans", seed=3, T=2, N=100, shapes=((2, 4), (4, 8), (8, 16), (16, 32))):
+    """semantic_trans_ins (VPS_Capsule.conv_trans on every level, vps_temporal_slots.py:129-135) followed by the head,
+    from UN-transformed features: the golden for the folded input transform."""
+    im = model.image_model
+    head = im.dynamic_mask_head
+    head.load_state_dict(synthetic.make_head_state_dict(seed), strict=True)
+    tp = synthetic.make_in_trans_params(seed)
+    im.conv_trans.conv.weight.data.copy_(tp["conv_trans.conv.weight"])
+    im.conv_trans.conv.bias.data.copy_(tp["conv_trans.conv.bias"])
+    cap = synthetic.make_capsule_params(seed, N)
+    raw = synthetic.make_features(0, 0, T=T, video=seed, frame=0, shapes=list(shapes))
+    q = cap["init_mask_query.weight"]
+    with torch.no_grad():
+        feats = [model.semantic_trans_ins(list(fr)) for fr in raw]
+        pos = [[ref_pos(model, f) for f in feats[t]] for t in range(T)]
+        cls, emb, fused = head(features=feats, init_masks=[q.clone() for _ in range(T)], pad_mask=None, pos=pos,
+                               query_pos=None, gt_non_void_mask=None)
+    out = {}
+    for t in range(T):
+        out[f"cls{t}"] = cls[t].numpy()
+        out[f"emb{t}"] = emb[t].numpy()
+        for l in range(4):
+            out[f"fused{t}_{l}_sample"] = fused[t][l][0][::7, ::3, ::5].contiguous().numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 TRACK_CASES = {
     # name: seed, N, (h, w), [frames per video], FC mode
     "track_a": dict(seed=0, N=100, h=32, w=64, videos=[5, 3], mode="identity"),
@@ -200,6 +226,7 @@ def main():
         m3, _ = ref_import.build_model(0, **{"other_config.proposal_num": kw["N"]})
         gen_fusion(m3, name, kw.pop("seed"), kw.pop("N"), kw.pop("h"), kw.pop("w"), **kw)
         print(name, "done")
+    gen_head_intrans(model)
     for name, c in TRACK_CASES.items():
         m4, _ = ref_import.build_model(0, **{"other_config.proposal_num": c["N"]})
         gen_track(m4, name, **c)

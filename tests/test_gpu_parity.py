@@ -509,3 +509,57 @@ def test_tracker_capacity_and_empty(dev):
     assert rec["k"] == 0 and rec["bank"] == 0
     rec = sv.SlotTracker.host(trk2.step(synthetic.make_track_sequence(0, N, 1)[0].to(dev), fo))
     assert rec["ids"].tolist() == list(range(rec["k"]))               # still the "first frame" of the video
+
+
+# ---- folded input transform ------------------------------------------------------------
+@pytest.mark.parametrize("kernel_path", PATHS)
+def test_folded_input_transform_golden(dev, kernel_path, golden_dir):
+    """head.fold_input_transform(conv_trans) on UN-transformed features == the reference's semantic_trans_ins + head."""
+    from tests.test_oracle_golden import INTRANS_CASE as c
+    gold = np.load(os.path.join(golden_dir, "head_intrans.npz"))
+    sd = synthetic.make_head_state_dict(c["seed"])
+    tp = synthetic.make_in_trans_params(c["seed"])
+    cap = synthetic.make_capsule_params(c["seed"], c["N"])
+    raw = synthetic.make_features(0, 0, T=c["T"], video=c["seed"], frame=0, shapes=c["shapes"])
+    head = _mk_head(dev, sd, kernel_path)
+    head.fold_input_transform(tp["conv_trans.conv.weight"], tp["conv_trans.conv.bias"])
+    q = cap["init_mask_query.weight"].to(dev)
+    cl, em, fu = head([[f.to(dev) for f in fr] for fr in raw], [q] * c["T"], None, pos="sine")
+    for t in range(c["T"]):
+        for l in range(4):
+            assert rel(fu[t][l][0][::7, ::3, ::5], gold[f"fused{t}_{l}_sample"]) < 1e-5
+        for s in range(7):
+            env = max(1e-5 * 3.5 ** s * 3, 2e-5)
+            assert rel(em[t][s], gold[f"emb{t}"][s]) < env and rel(cl[t][s], gold[f"cls{t}"][s]) < env, (t, s)
+    # removing the fold restores the plain head (transformed features in)
+    head.fold_input_transform(None, None)
+    feats = O.input_transform(raw, tp["conv_trans.conv.weight"], tp["conv_trans.conv.bias"])
+    cl2, em2, fu2 = head([[f.to(dev) for f in fr] for fr in feats], [q] * c["T"], None, pos="sine")
+    assert rel(fu2[0][3], fu[0][3]) < 1e-5 and rel(em2[0][0], em[0][0]) < 3e-5
+
+
+def test_folded_input_transform_tensor_core_path(dev):
+    """Same at a size where every level runs the tensor-core kernels (fuse_tc with folded W0 / Wb and per-level bias)."""
+    shapes = [(8, 16), (16, 32), (32, 64), (64, 128)]
+    sd = synthetic.make_head_state_dict(5)
+    tp = synthetic.make_in_trans_params(5)
+    cap = synthetic.make_capsule_params(5, 100)
+    raw = synthetic.make_features(0, 0, T=2, video=5, frame=0, shapes=shapes)
+    feats64 = O.input_transform([[f.double() for f in fr] for fr in raw], tp["conv_trans.conv.weight"].double(), tp["conv_trans.conv.bias"].double())
+    P64 = {k: v.double() for k, v in sd.items()}
+    head = _mk_head(dev, sd, 0)
+    head.fold_input_transform(tp["conv_trans.conv.weight"], tp["conv_trans.conv.bias"])
+    q = cap["init_mask_query.weight"]
+    cl, em, fu = head([[f.to(dev) for f in fr] for fr in raw], [q.to(dev)] * 2, None, pos="sine")
+    W64 = P64["conv_trans.conv.weight"].reshape(256, 384)
+    for t in range(2):
+        prev = None
+        for l in range(4):
+            ref = O.level_fuse(prev, feats64[t][l], W64, P64["conv_trans.conv.bias"])
+            assert rel(fu[t][l], ref) < 1e-5, (t, l, rel(fu[t][l], ref))
+            prev = ref
+    pos64 = [[O.sine_position_embedding(*s, dtype=torch.float64) for s in shapes] for _ in range(2)]
+    rc, re_, _ = O.head_forward(P64, feats64, [q.double()] * 2, pos64)
+    for s in range(7):
+        env = max(1e-5 * 3.5 ** s * 3, 2e-5)
+        assert rel(em[1][s], re_[1][s]) < env, (s, rel(em[1][s], re_[1][s]))

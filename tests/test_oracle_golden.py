@@ -147,3 +147,26 @@ def test_tracker_matches_reference(name):
             seen[k] += info[k]
     if c["mode"] == "identity":
         assert all(v > 0 for v in seen.values()), seen     # every branch of the greedy loop was reached
+
+
+INTRANS_CASE = dict(seed=3, T=2, N=100, shapes=[(2, 4), (4, 8), (8, 16), (16, 32)])
+
+
+def test_input_transform_then_head(golden_dir):
+    """semantic_trans_ins (1x1 conv on every level) + head vs the reference run on UN-transformed features."""
+    c = INTRANS_CASE
+    g = np.load(os.path.join(golden_dir, "head_intrans.npz"))
+    P = synthetic.make_head_state_dict(c["seed"])
+    tp = synthetic.make_in_trans_params(c["seed"])
+    cap = synthetic.make_capsule_params(c["seed"], c["N"])
+    raw = synthetic.make_features(0, 0, T=c["T"], video=c["seed"], frame=0, shapes=c["shapes"])
+    feats = O.input_transform(raw, tp["conv_trans.conv.weight"], tp["conv_trans.conv.bias"])
+    pos = [[O.sine_position_embedding(*s) for s in c["shapes"]] for _ in range(c["T"])]
+    cls, emb, fused = O.head_forward(P, feats, [cap["init_mask_query.weight"]] * c["T"], pos)
+    for t in range(c["T"]):
+        for l in range(4):
+            assert rel_l2(fused[t][l][0][::7, ::3, ::5].numpy(), g[f"fused{t}_{l}_sample"]) < 2e-6
+        for s in range(7):
+            tol = 3e-6 * 3.5 ** s
+            assert rel_l2(emb[t][s].numpy(), g[f"emb{t}"][s]) < tol, (t, s)
+            assert rel_l2(cls[t][s].numpy(), g[f"cls{t}"][s]) < tol, (t, s)
