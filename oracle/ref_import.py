@@ -214,6 +214,31 @@ def import_reference():
     return _CACHE["models"]
 
 
+def import_reference_tools():
+    """The reference's evaluation helper ``tools.dataset.cityscapes_vps.CityscapesVps`` (for get_unified_pan_result,
+    tools/dataset/cityscapes_vps.py:214) with its dataset constants set as the shipped test yaml does
+    (num_seg_classes=19, num_classes=9).  Stubs (names only): easydict, cv2, matplotlib; ``collections.Sequence``."""
+    import_reference()
+    if "tools_cls" not in _CACHE:
+        import collections
+        import collections.abc
+        if not hasattr(collections, "Sequence"):
+            collections.Sequence = collections.abc.Sequence      # removed from `collections` in Python 3.10
+        if "easydict" not in sys.modules:
+            _mod("easydict", EasyDict=AttrDict)
+        for name in ("cv2", "matplotlib", "matplotlib.pyplot"):
+            if name not in sys.modules:
+                try:
+                    __import__(name)
+                except Exception:
+                    _mod(name, use=lambda *a, **k: None)
+        from tools.config.config import config
+        from tools.dataset.cityscapes_vps import CityscapesVps
+        config.dataset.num_seg_classes, config.dataset.num_classes = 19, 9
+        _CACHE["tools_cls"] = CityscapesVps
+    return _CACHE["tools_cls"]
+
+
 def load_config(**overrides):
     cfg = runpy.run_path(os.path.join(REFERENCE_ROOT, CONFIG))
     cfg = to_attr({k: v for k, v in cfg.items() if not k.startswith("__")})

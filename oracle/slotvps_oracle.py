@@ -503,3 +503,81 @@ def input_transform(features, weight: torch.Tensor, bias: torch.Tensor):
     no activation) on every level.  features T x L x [1,128,h,w]."""
     w = weight.reshape(weight.shape[0], -1)
     return [[torch.einsum("oc,bchw->bohw", w.to(f.dtype), f) + bias.to(f.dtype)[None, :, None, None] for f in fr] for fr in features]
+
+
+# ------------------------------------------------------------------------------------------------
+# Consumers of the id map (SURVEY.md 8f rank 3): semantic argmax of simple_test and the per-frame merge
+# CityscapesVps.get_unified_pan_result that produces the evaluation wire format (H x W x 3 uint8).
+# ------------------------------------------------------------------------------------------------
+def semantic_argmax(fcn_output: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+    """vps_temporal_slots.py:440-451: bilinear resize to the image size when needed (align_corners=False), softmax
+    over classes, index of the max.  fcn_output [1,Cs,h,w] -> [1,H,W] int64."""
+    x = fcn_output.float()
+    if tuple(x.shape[-2:]) != tuple(size):
+        x = F.interpolate(x, size=tuple(size), mode="bilinear", align_corners=False)
+    return torch.softmax(x, 1).max(1)[1]
+
+
+def dedup_obj_ids(obj_id: np.ndarray, max_oid: int):
+    """tools/dataset/cityscapes_vps.py:233-244: of several instances carrying one object id the LAST keeps it, the
+    earlier ones (walking backwards) receive fresh ids from a counter that persists over the frames of a call."""
+    obj_id = np.array(obj_id).copy()
+    uniq, cnt = np.unique(obj_id, return_counts=True)
+    if not np.any(cnt > 1):
+        return obj_id, max_oid
+    rev = obj_id[::-1].copy()
+    for red in uniq[cnt > 1]:
+        n = int((obj_id == red).sum())
+        repl = np.full(n, red, dtype=obj_id.dtype)
+        for i in range(1, n):
+            repl[i] = max_oid
+            max_oid += 1
+        rev[rev == red] = repl
+    return rev[::-1], max_oid
+
+
+def unify_pan_result(segs, pans, cls_inds, obj_ids=None, stuff_area_limit: int = 4 * 64 * 64, id_last_stuff: int = 10):
+    """CityscapesVps.get_unified_pan_result, tools/dataset/cityscapes_vps.py:214-302, one [H,W,3] uint8 array per frame
+    (semantic label, instance index from 1, object id + 1).  id_last_stuff = num_seg_classes - num_classes (:250)."""
+    if obj_ids is None:
+        obj_ids = [None] * len(cls_inds)
+    max_oid = 100
+    out = []
+    for seg, pan, cls_ind, obj_id in zip(segs, pans, cls_inds, obj_ids):
+        seg, pan = np.asarray(seg), np.array(pan).copy()
+        if obj_id is not None:
+            obj_id, max_oid = dedup_obj_ids(np.asarray(obj_id), max_oid)
+        pan_seg = pan.copy()
+        if len(cls_ind) == 0:
+            pan[pan > id_last_stuff] = 255
+        pan_ins, pan_obj = pan.copy(), pan.copy()
+        present = np.unique(pan)
+        present = present[present > id_last_stuff]
+        pan_ins[pan_ins <= id_last_stuff] = 0
+        for idx, i in enumerate(present):
+            region = pan == i                       # == (pan_ins == i): values written below never collide with a later id
+            if i == 255:
+                pan_seg[region] = 255
+                pan_ins[region] = 0
+                continue
+            cls, cnt = np.unique(seg[region], return_counts=True)
+            major = cls[np.argmax(cnt)]
+            inst_cls = cls_ind[i - id_last_stuff - 1] + id_last_stuff
+            if major != inst_cls and np.max(cnt) / np.sum(cnt) >= 0.5 and major <= id_last_stuff:
+                pan_seg[region] = major             # the semantic head out-votes the instance: becomes stuff
+                pan_ins[region] = 0
+                pan_obj[region] = 0
+            else:
+                pan_seg[region] = inst_cls
+                pan_ins[region] = idx + 1
+                if obj_id is not None:
+                    pan_obj[region] = obj_id[idx] + 1
+        for v in np.unique(pan_seg):
+            if v <= id_last_stuff:
+                area = pan_seg == v
+                if area.sum() < stuff_area_limit:
+                    pan_seg[area] = 255
+        o = np.zeros(pan.shape + (3,), dtype=np.uint8)
+        o[:, :, 0], o[:, :, 1], o[:, :, 2] = pan_seg.astype(np.uint8), pan_ins.astype(np.uint8), pan_obj.astype(np.uint8)
+        out.append(o)
+    return out

@@ -240,3 +240,57 @@ def make_in_trans_params(seed: int, channels: int = 128):
     g = torch.Generator().manual_seed(70_000 + seed)
     return {"conv_trans.conv.weight": torch.randn((channels, channels, 1, 1), generator=g) * (1.2 / channels ** 0.5),
             "conv_trans.conv.bias": torch.randn((channels,), generator=g) * 0.2}
+
+
+def make_unify_case(seed: int, H: int, W: int, n_inst: int = 12, dup_obj: int = 3, hidden: int = 2,
+                    n_stuff: int = 11, n_sem: int = 19):
+    """One frame of inputs for the id-map merge (get_unified_pan_result): semantic argmax ``seg`` [H,W], panoptic ids
+    ``pan`` [H,W] (stuff label < n_stuff, instance i -> n_stuff + i), ``cls_ind`` [n_inst] (thing class - 10, 1..8)
+    and ``obj_id`` [n_inst].  Designed to reach every branch: instances whose majority semantic class agrees, ones
+    out-voted by a stuff class, ones contradicted by another thing class or by a sub-majority, instances with no pixel
+    (``hidden``: later ones cover them, so position-in-list and id-based indexing differ), duplicate object ids and
+    stuff classes below the area limit."""
+    g = torch.Generator().manual_seed(80_000 + seed)
+    coarse = torch.randn((1, n_stuff, max(2, H // 32), max(2, W // 32)), generator=g)
+    field = torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=False)[0]
+    field[n_stuff - 2:] -= 1.5                                   # two stuff classes end up small
+    pan = field.argmax(0).to(torch.int64)
+    seg = pan.clone()
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    cls_ind = torch.randint(1, n_sem - n_stuff + 1, (n_inst,), generator=g)
+    centres = []
+    for i in range(n_inst):
+        cy, cx = int(torch.randint(0, H, (1,), generator=g)), int(torch.randint(0, W, (1,), generator=g))
+        ry = 3 + int(torch.randint(0, max(4, H // 6), (1,), generator=g))
+        rx = 3 + int(torch.randint(0, max(4, W // 6), (1,), generator=g))
+        centres.append((cy, cx, ry, rx))
+    hidden_idx = [j for j in (2, 5, 7)[:hidden] if j + 1 < n_inst]
+    for j in hidden_idx:
+        centres[j] = centres[j + 1]                              # same ellipse as the next instance, painted before it
+    order = hidden_idx + [i for i in range(n_inst) if i not in hidden_idx]
+    for i in order:
+        cy, cx, ry, rx = centres[i]
+        region = ((yy - cy).float() / ry) ** 2 + ((xx - cx).float() / rx) ** 2 <= 1.0
+        pan[region] = n_stuff + i
+    for i in range(n_inst):
+        region = pan == n_stuff + i
+        if not bool(region.any()):
+            continue
+        mode = i % 4
+        inst_cls = int(cls_ind[i]) + n_stuff - 1
+        if mode == 0 or mode == 1:
+            seg[region] = inst_cls                                # agreement (plus a stuff fringe for mode 1)
+            if mode == 1:
+                seg[region & (xx % 3 == 0)] = 2
+        elif mode == 2:
+            seg[region] = 5                                       # stuff majority >= 0.5: the instance is dropped
+            seg[region & (xx % 4 == 0)] = inst_cls
+        else:
+            other = n_stuff + (int(cls_ind[i]) % (n_sem - n_stuff))
+            seg[region] = other                                   # another thing class: instance label wins
+            seg[region & (yy % 3 == 0)] = 1
+    obj_id = torch.randperm(40, generator=g)[:n_inst].to(torch.int64)
+    for k in range(dup_obj):
+        a, b = int(torch.randint(0, n_inst, (1,), generator=g)), int(torch.randint(0, n_inst, (1,), generator=g))
+        obj_id[a] = obj_id[b]
+    return seg, pan, cls_ind.to(torch.int64), obj_id

@@ -158,6 +158,71 @@ def gen_head_intrans(model, name="head_intrans", seed=3, T=2, N=100, shapes=((2,
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
 
+UNIFY_CASES = {
+    # name: frames (seeds), size, stuff_area_limit, with object ids, frames whose cls_inds are emptied (the 255 path)
+    "unify_a": dict(seeds=[0, 1, 2, 3], H=128, W=256, limit=4096, with_obj=True, empty=[]),
+    "unify_b": dict(seeds=[4, 5, 6], H=96, W=160, limit=4 * 64 * 64, with_obj=True, empty=[1]),
+    "unify_c": dict(seeds=[7, 8], H=64, W=64, limit=512, with_obj=False, empty=[]),
+}
+SEMANTIC_CASES = {"semantic_same": dict(seed=0, h=64, w=128, H=64, W=128), "semantic_up4": dict(seed=1, h=32, w=64, H=128, W=256)}
+
+
+def unify_inputs(seeds, H, W, with_obj, empty, **_):
+    segs, pans, cis, ois = [], [], [], []
+    for j, sd in enumerate(seeds):
+        seg, pan, ci, oi = synthetic.make_unify_case(sd, H, W)
+        segs.append(seg.numpy()); pans.append(pan.numpy())
+        cis.append(np.zeros((0,), np.int64) if j in empty else ci.numpy())
+        ois.append(oi.numpy().astype(np.int32))
+    return segs, pans, cis, (ois if with_obj else None)
+
+
+def gen_unify(name, c):
+    """CityscapesVps.get_unified_pan_result (tools/dataset/cityscapes_vps.py:214) on synthetic frames."""
+    import contextlib
+    import io
+    ds = object.__new__(ref_import.import_reference_tools())
+    segs, pans, cis, ois = unify_inputs(**c)
+    names = ["f%d" % i for i in range(len(segs))]
+    with contextlib.redirect_stdout(io.StringIO()):            # the method prints its whole input
+        res = ds.get_unified_pan_result([x.copy() for x in segs], [x.copy() for x in pans], cis,
+                                        obj_ids=None if ois is None else [x.copy() for x in ois],
+                                        stuff_area_limit=c["limit"], names=names)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **{n: res[n] for n in names})
+
+
+def semantic_input(seed, h, w, **_):
+    g = torch.Generator().manual_seed(90_000 + seed)
+    coarse = torch.randn((1, 19, max(2, h // 8), max(2, w // 8)), generator=g)
+    x = torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=False) * 4.0
+    return x + torch.randn((1, 19, h, w), generator=g) * 0.5
+
+
+def gen_semantic(model, name, c):
+    """The semantic argmax of simple_test (vps_temporal_slots.py:440-451): drive simple_test with a tensor source for
+    the semantic head and keep `fcn_outputs`."""
+    logits, masks, _ = synthetic.make_fusion_case(0, 100, c["H"] // 4, c["W"] // 4)
+    fcn = semantic_input(**c)
+    H, W = c["H"], c["W"]
+    im = model.image_model
+    im.backbone = _Fn(lambda x: x)
+    im.neck = None
+    model.extract_semantic_feats = lambda x: (fcn.clone(), None, [torch.zeros(1, 128, 1, 1)] * 4)
+    model.semantic_trans_ins = lambda f: f
+    model.generate_position_embedding = lambda f: None
+    emb = torch.zeros(7, 1, 100, 256)
+    cls = logits[None, None].repeat(7, 1, 1, 1)
+    im.dynamic_mask_head = _Fn(lambda **k: ([cls, cls], [emb, emb], [[None] * 4, [None] * 4]))
+    model.generate_final_outputs = lambda feats, om, generate_aux_output=False: (feats, masks[None], [])
+    im.init_mask_query = torch.nn.Embedding(100, 256)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    img = torch.zeros(1, 3, H, W)
+    meta = [dict(iid=10001, filename="synthetic", ori_shape=(H, W, 3), img_shape=(H, W, 3))]
+    with torch.no_grad():
+        res = model.simple_test(img, meta, rescale=True, ref_img=[img])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), fcn_outputs=res["fcn_outputs"].numpy().astype(np.uint8))
+
+
 TRACK_CASES = {
     # name: seed, N, (h, w), [frames per video], FC mode
     "track_a": dict(seed=0, N=100, h=32, w=64, videos=[5, 3], mode="identity"),
@@ -227,6 +292,11 @@ def main():
         gen_fusion(m3, name, kw.pop("seed"), kw.pop("N"), kw.pop("h"), kw.pop("w"), **kw)
         print(name, "done")
     gen_head_intrans(model)
+    for name, c in UNIFY_CASES.items():
+        gen_unify(name, c)
+    for name, c in SEMANTIC_CASES.items():
+        m5, _ = ref_import.build_model(0)
+        gen_semantic(m5, name, c)
     for name, c in TRACK_CASES.items():
         m4, _ = ref_import.build_model(0, **{"other_config.proposal_num": c["N"]})
         gen_track(m4, name, **c)

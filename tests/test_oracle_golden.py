@@ -170,3 +170,36 @@ def test_input_transform_then_head(golden_dir):
             tol = 3e-6 * 3.5 ** s
             assert rel_l2(emb[t][s].numpy(), g[f"emb{t}"][s]) < tol, (t, s)
             assert rel_l2(cls[t][s].numpy(), g[f"cls{t}"][s]) < tol, (t, s)
+
+
+def _golden_tables():
+    src = open(spec.origin).read()
+    ns = {"np": np, "torch": torch, "synthetic": synthetic}
+    a, b = src.index("UNIFY_CASES = {"), src.index("def gen_unify")
+    exec(src[a:b], ns)
+    a, b = src.index("def semantic_input"), src.index("def gen_semantic")
+    exec(src[a:b], ns)
+    return ns["UNIFY_CASES"], ns["SEMANTIC_CASES"], ns["unify_inputs"], ns["semantic_input"]
+
+
+UNIFY_CASES, SEMANTIC_CASES, unify_inputs, semantic_input = _golden_tables()
+
+
+@pytest.mark.parametrize("name", sorted(UNIFY_CASES))
+def test_unify_pan_result_bit_exact(golden_dir, name):
+    """Oracle restatement of get_unified_pan_result vs the reference's own output (duplicate object ids with the
+    persistent counter, hidden instances, stuff out-voting, the empty-cls_inds 255 path, small-stuff removal)."""
+    c = UNIFY_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    segs, pans, cis, ois = unify_inputs(**c)
+    out = O.unify_pan_result(segs, pans, cis, ois, c["limit"])
+    for i, o in enumerate(out):
+        np.testing.assert_array_equal(o, g["f%d" % i])
+
+
+@pytest.mark.parametrize("name", sorted(SEMANTIC_CASES))
+def test_semantic_argmax_matches_reference(golden_dir, name):
+    c = SEMANTIC_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))["fcn_outputs"]
+    got = O.semantic_argmax(semantic_input(**c), (c["H"], c["W"])).numpy()
+    np.testing.assert_array_equal(got.astype(np.uint8), g)
