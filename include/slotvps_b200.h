@@ -191,6 +191,25 @@ int slotvps_track_step(const float* fc_w, const float* fc_b, int num_fcs, const 
                        const int32_t* fusion_meta, int n_slots, void* state, size_t state_bytes, int capacity,
                        int32_t* track_out, void* stream);
 
+/* ---- Consumers of the id map ----------------------------------------------------
+ * Semantic prediction of simple_test (vps_temporal_slots.py:440-451): fcn_output [n_classes,h,w] fp32 -> bilinear
+ * resize to (H,W) when the sizes differ (align_corners=False), softmax over classes, first index of the maximum.
+ * out [H,W] int64 (the reference's fcn_outputs[0]).  n_classes <= 32.                                          */
+int slotvps_semantic_argmax(const float* fcn_output, int n_classes, int h, int w, int H, int W, int64_t* out, void* stream);
+/* CityscapesVps.get_unified_pan_result (tools/dataset/cityscapes_vps.py:214-302) for ONE frame, on device:
+ *   seg [H,W] int64 semantic argmax, pan [H,W] int64 panoptic ids (< 256), cls_inds int32[n_inst] (thing class - 10),
+ *   obj_ids int32[n_obj] or NULL / 0 (the reference's obj_ids=None), id_last_stuff = num_seg_classes - num_classes (:250),
+ *   stuff_area_limit as passed by tools/test_vpq.py:169.  pan_2ch [H,W,3] uint8 = (semantic, instance from 1, object id + 1).
+ * The counter for redundant object ids (:219 max_oid) lives in the workspace: slotvps_unify_reset() at the start of
+ * what would be one get_unified_pan_result call, then one slotvps_unify_pan_result() per frame, in order.
+ * status (optional, device int32[2]): [0] sticky error bits (1: id/class out of range, 2: cls_inds too short for an id
+ * present in the map, 4: obj_ids too short -- the reference raises IndexError in the last two cases), [1] max_oid.  */
+int slotvps_unify_workspace_bytes(size_t* bytes);
+int slotvps_unify_reset(void* workspace, size_t workspace_bytes, void* stream);
+int slotvps_unify_pan_result(const int64_t* seg, const int64_t* pan, const int32_t* cls_inds, int n_inst,
+                             const int32_t* obj_ids, int n_obj, int H, int W, int id_last_stuff, int stuff_area_limit,
+                             uint8_t* pan_2ch, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Introspection. */
 const char* slotvps_last_error(void);
 const char* slotvps_version(void);

@@ -12,6 +12,7 @@ from .head import B200DynamicMaskHead  # noqa: F401
 from .retriever import (PanopticFusion, SlotVPSRetriever, FusionOutput, GraphedClip, mask_logits, level_fuse,  # noqa: F401
                         slot_attention, sine_position_embedding)
 from .tracker import B200TrackHead, SlotTracker  # noqa: F401
+from .unify import PanUnifier, get_unified_pan_result, semantic_argmax  # noqa: F401
 
 TRACK_KWARGS = dict(num_fcs_query=2, in_channels_query=256, query_matched_weight=1.0)  # r50_fpn_slotvps.py:90-96
 

@@ -110,6 +110,10 @@ SYMBOLS = {
     "slotvps_panoptic_fuse": (C.c_int, [C.POINTER(FusionCfg), P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P,
                                         P, C.c_int, P, C.c_size_t, P]),
     "slotvps_sine_pos": (C.c_int, [P, C.c_int, C.c_int, P]),
+    "slotvps_semantic_argmax": (C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P]),
+    "slotvps_unify_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),
+    "slotvps_unify_reset": (C.c_int, [P, C.c_size_t, P]),
+    "slotvps_unify_pan_result": (C.c_int, [P, P, P, C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, C.c_size_t, P]),
     "slotvps_track_scores": (C.c_int, [P, P, C.c_int, P, C.c_int, P, C.c_int, P, P, C.c_size_t, P]),
     "slotvps_track_state_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "slotvps_track_reset": (C.c_int, [P, C.c_size_t, P]),

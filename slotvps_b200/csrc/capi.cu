@@ -15,6 +15,7 @@
 #include "fuse_tc.cuh"
 #include "mask_tc.cuh"
 #include "track.cuh"
+#include "unify.cuh"
 
 namespace slotvps {
 thread_local char g_err[512] = "";
@@ -817,6 +818,70 @@ int slotvps_track_step(const float* fc_w, const float* fc_b, int num_fcs, const 
   SV_CHECK_LAUNCH("track_score");
   track::track_assign_kernel<<<1, 256, (size_t)capacity * 12, s>>>(t.st, t.bank, capacity, embedding, fusion_meta, n_slots, t.lik, t.mid, track_out);
   SV_CHECK_LAUNCH("track_assign");
+  return SLOTVPS_OK;
+}
+
+// ---- consumers of the id map ------------------------------------------------------------------------------
+int slotvps_semantic_argmax(const float* fcn_output, int n_classes, int h, int w, int H, int W, int64_t* out, void* stream) {
+  SV_REQUIRE(fcn_output && out, "null argument");
+  SV_REQUIRE(n_classes > 0 && n_classes <= unify::MAXSEM && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long HW = (long)H * W;
+  const int grid = (int)((HW + 255) / 256 < 148 * 8 ? (HW + 255) / 256 : 148 * 8);
+  unify::semantic_argmax_kernel<<<grid, 256, 0, s>>>(fcn_output, n_classes, h, w, H, W, (long long*)out);
+  SV_CHECK_LAUNCH("semantic_argmax");
+  return SLOTVPS_OK;
+}
+
+namespace {
+struct UnifyLayout { unify::State* st; unsigned int* hist; unsigned char* luts; size_t bytes; };
+UnifyLayout unify_layout(void* ws) {
+  Arena a(ws, (size_t)-1);
+  UnifyLayout u;
+  u.st = (unify::State*)a.take<char>(256);
+  u.hist = a.take<unsigned int>((size_t)unify::MAXID * unify::MAXSEM);
+  u.luts = a.take<unsigned char>(3 * unify::MAXID);
+  u.bytes = align_up(a.off);
+  return u;
+}
+}  // namespace
+
+int slotvps_unify_workspace_bytes(size_t* bytes) {
+  SV_REQUIRE(bytes != nullptr, "null out pointer");
+  *bytes = unify_layout(nullptr).bytes;
+  return SLOTVPS_OK;
+}
+
+int slotvps_unify_reset(void* workspace, size_t workspace_bytes, void* stream) {
+  SV_REQUIRE(workspace && workspace_bytes >= unify_layout(nullptr).bytes, "bad workspace");
+  cudaStream_t s = (cudaStream_t)stream;
+  unify::unify_reset_kernel<<<1, 1, 0, s>>>(unify_layout(workspace).st);
+  SV_CHECK_LAUNCH("unify_reset");
+  return SLOTVPS_OK;
+}
+
+int slotvps_unify_pan_result(const int64_t* seg, const int64_t* pan, const int32_t* cls_inds, int n_inst, const int32_t* obj_ids,
+                             int n_obj, int H, int W, int id_last_stuff, int stuff_area_limit, uint8_t* pan_2ch, int32_t* status,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  SV_REQUIRE(seg && pan && pan_2ch && workspace, "null argument");
+  SV_REQUIRE(H > 0 && W > 0 && n_inst >= 0 && n_inst <= unify::MAXID && n_obj >= 0 && n_obj <= unify::MAXID, "bad shape");
+  SV_REQUIRE((n_inst == 0 || cls_inds) && (n_obj == 0 || obj_ids), "null id arrays");
+  SV_REQUIRE(id_last_stuff >= 0 && id_last_stuff < unify::MAXID - 1 && stuff_area_limit >= 0, "bad argument");
+  const UnifyLayout u = unify_layout(workspace);
+  if (workspace_bytes < u.bytes) return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long HW = (long)H * W;
+  SV_CHECK_CUDA(cudaMemsetAsync(u.hist, 0, sizeof(unsigned int) * unify::MAXID * unify::MAXSEM, s));
+  const long chunks = (HW + 2047) / 2048;
+  unify::unify_hist_kernel<<<(int)(chunks < 148 * 4 ? chunks : 148 * 4), 256, 0, s>>>((const long long*)seg, (const long long*)pan, HW, u.hist, u.st);
+  SV_CHECK_LAUNCH("unify_hist");
+  unify::unify_decide_kernel<<<1, unify::MAXID, 0, s>>>(u.hist, cls_inds, n_inst, n_obj > 0 ? obj_ids : nullptr, n_obj, id_last_stuff,
+                                                       (unsigned int)stuff_area_limit, u.st, u.luts);
+  SV_CHECK_LAUNCH("unify_decide");
+  const long quads = (HW + 3) / 4;
+  unify::unify_write_kernel<<<(int)((quads + 255) / 256 < 148 * 8 ? (quads + 255) / 256 : 148 * 8), 256, 0, s>>>((const long long*)pan, HW, u.luts, pan_2ch);
+  SV_CHECK_LAUNCH("unify_write");
+  if (status) SV_CHECK_CUDA(cudaMemcpyAsync(status, u.st, 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
   return SLOTVPS_OK;
 }
 

@@ -24,6 +24,7 @@ import torch
 from .head import B200DynamicMaskHead
 from .retriever import PanopticFusion, mask_logits
 from .tracker import B200TrackHead, SlotTracker
+from .unify import semantic_argmax
 
 
 def patch_reference(level: int = 1):
@@ -95,7 +96,7 @@ def make_b200_detector(base, Instances):
                 self._b200_tracker = self._make_tracker(emb[-1].device, q.shape[0])
             rec = SlotTracker.host(self._b200_tracker.step(emb[-1][-1, 0], fo))
             obj_ids = rec["det_obj_ids"]
-            sem = torch.softmax(fcn_output, 1).argmax(1)[:, :H, :W]
+            sem = semantic_argmax(fcn_output, (H, W))             # :440-451 incl. the bilinear resize when sizes differ
             return {
                 "fcn_outputs": sem,
                 "panoptic_cls_inds": torch.as_tensor(h["cls_inds"]),

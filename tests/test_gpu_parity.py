@@ -563,3 +563,64 @@ def test_folded_input_transform_tensor_core_path(dev):
     for s in range(7):
         env = max(1e-5 * 3.5 ** s * 3, 2e-5)
         assert rel(em[1][s], re_[1][s]) < env, (s, rel(em[1][s], re_[1][s]))
+
+
+# ---- consumers of the id map -------------------------------------------------------------
+@pytest.mark.parametrize("name", ["unify_a", "unify_b", "unify_c"])
+def test_unify_pan_result_golden(dev, name, golden_dir):
+    """get_unified_pan_result on device == the reference's own output, byte for byte, over the frames of a call."""
+    from tests.test_oracle_golden import UNIFY_CASES, unify_inputs
+    c = UNIFY_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    segs, pans, cis, ois = unify_inputs(**c)
+    names = ["f%d" % i for i in range(len(segs))]
+    got = sv.get_unified_pan_result(segs, pans, cis, obj_ids=ois, stuff_area_limit=c["limit"], names=names, device=dev)
+    ref = O.unify_pan_result(segs, pans, cis, ois, c["limit"])
+    for i, n in enumerate(names):
+        assert got[n].dtype == np.uint8 and got[n].shape == g[n].shape
+        np.testing.assert_array_equal(got[n], g[n])
+        np.testing.assert_array_equal(got[n], ref[i])
+
+
+def test_unify_full_size_and_errors(dev):
+    """1024x2048 frames: equals the oracle; ragged tail (H*W not a multiple of 4/8); error reporting."""
+    for seed, (H, W) in [(20, (1024, 2048)), (21, (37, 53))]:
+        seg, pan, ci, oi = synthetic.make_unify_case(seed, H, W, n_inst=40 if H > 100 else 6, dup_obj=5 if H > 100 else 1)
+        got = sv.get_unified_pan_result([seg.to(dev)], [pan.to(dev)], [ci], obj_ids=[oi], stuff_area_limit=4096, names=["x"], device=dev)["x"]
+        ref = O.unify_pan_result([seg.numpy()], [pan.numpy()], [ci.numpy()], [oi.numpy()], 4096)[0]
+        np.testing.assert_array_equal(got, ref)
+    seg, pan, ci, oi = synthetic.make_unify_case(22, 64, 64, n_inst=6, hidden=0)
+    with pytest.raises(IndexError):                    # cls_inds shorter than the ids present: the reference raises too
+        sv.get_unified_pan_result([seg], [pan], [ci[:2]], obj_ids=[oi], names=["x"], device=dev)
+    with pytest.raises(ValueError):
+        sv.get_unified_pan_result([seg], [pan + 300], [ci], obj_ids=[oi], names=["x"], device=dev)
+    with pytest.raises(RuntimeError):                  # no CPU path
+        sv.PanUnifier(dev).frame(seg, pan, ci, oi)
+
+
+@pytest.mark.parametrize("name", ["semantic_same", "semantic_up4"])
+def test_semantic_argmax_golden(dev, name, golden_dir):
+    from tests.test_oracle_golden import SEMANTIC_CASES, semantic_input
+    c = SEMANTIC_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))["fcn_outputs"]
+    x = semantic_input(**c)
+    got = sv.semantic_argmax(x.to(dev), (c["H"], c["W"])).cpu().numpy()
+    assert got.shape == (1, c["H"], c["W"])
+    # pixels whose two largest (resized) logits are closer than 1e-4 may resolve differently (exp rounding); none expected
+    up = torch.nn.functional.interpolate(x, size=(c["H"], c["W"]), mode="bilinear", align_corners=False) if x.shape[-1] != c["W"] else x
+    top2 = up.topk(2, dim=1).values
+    near = ((top2[:, 0] - top2[:, 1]) < 1e-4).numpy()
+    diff = (got.astype(np.uint8) != g)
+    assert int((diff & ~near).sum()) == 0
+    print(f"{name}: mismatches {int(diff.sum())} (near-tie pixels {int(near.sum())})")
+
+
+def test_semantic_argmax_full_size(dev):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 19, 256, 512, generator=g) * 3
+    got = sv.semantic_argmax(x.to(dev), (1024, 2048)).cpu()
+    ref = O.semantic_argmax(x, (1024, 2048))
+    up = torch.nn.functional.interpolate(x, size=(1024, 2048), mode="bilinear", align_corners=False)
+    top2 = up.topk(2, dim=1).values
+    near = (top2[:, 0] - top2[:, 1]) < 1e-4
+    assert int(((got != ref) & ~near).sum()) == 0
