@@ -417,7 +417,7 @@ def main():
             step_ms = single_ms if single_ms else ms / K
             # share of the serialised kernel time of one step (the definition an ncu launch list gives: profiles/
             # r1_tc_launches_summary.txt) and, separately, of the wall time of a step with one clip in flight (two streams overlap)
-            ktot = sum(v["ms_per_step"] for k, v in breakdown.items() if k != "copy")
+            ktot = sum(v["ms_per_step"] for k, v in breakdown.items() if k != "(host gap)")
             roofline["share_of_step"] = roofline["ms_per_step"] / ktot
             roofline["share_of_single_clip_wall_step"] = roofline["ms_per_step"] / step_ms
             hb = {"peak_gbs": pk["hbm_gbs"], "peak_source": pk["source"] + " copy bandwidth"}

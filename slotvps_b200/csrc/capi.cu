@@ -504,6 +504,7 @@ int slotvps_prepare_weights_ex(const slotvps_head_desc* d, const slotvps_stage_p
   SV_REQUIRE(stages && conv_w && conv_b && prepared, "null argument");
   SV_REQUIRE((in_trans_w == nullptr) == (in_trans_b == nullptr), "in_trans_w and in_trans_b go together");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   Prepared p;
   prepared_layout(d, prepared, &p);
   fold_w0_kernel<<<ceil_div(C * CIN, 256), 256, 0, s>>>(conv_w, p.W0);
@@ -564,6 +565,7 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
   SV_REQUIRE(stages && prepared && feats && init_query && cls_out && emb_out && fused_out && workspace, "null argument");
   SV_REQUIRE(d->pos_mode != 1 || pos != nullptr, "pos_mode 1 needs pos tensors");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   const int T = d->n_frames, N = d->n_slots, L = d->n_levels, S = n_stages_of(d);
   HeadWs w;
   if (head_ws_layout(d, workspace, workspace_bytes, &w) > workspace_bytes)
@@ -740,6 +742,7 @@ int slotvps_level_fuse(const float* prev, const float* x, const float* conv_w, c
   SV_REQUIRE(x && conv_w && conv_b && out && h > 0 && w > 0, "bad argument");
   SV_REQUIRE(scratch != nullptr, "scratch of 256*max(128, (h/2)*(w/2)) floats required");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   if (!prev) {
     fold_w0_kernel<<<ceil_div(C * CIN, 256), 256, 0, s>>>(conv_w, scratch);
     SV_CHECK_LAUNCH("fold_w0");
@@ -774,6 +777,7 @@ int slotvps_track_scores(const float* fc_w, const float* fc_b, int num_fcs, cons
   SV_REQUIRE(k > 0 && m > 0 && m <= TRACK_MAX_CAPACITY && num_fcs >= 0 && (num_fcs == 0 || (fc_w && fc_b)), "bad argument");
   if (workspace_bytes < (size_t)(k + m) * C * sizeof(float)) return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   float* ya = (float*)workspace; float* yb = ya + (size_t)k * C;
   track::track_fc_kernel<<<ceil_div(k, track::ROWS), 256, 0, s>>>(x_query, nullptr, nullptr, k, fc_w, fc_b, num_fcs, ya);
   SV_CHECK_LAUNCH("track_fc");
@@ -793,6 +797,7 @@ int slotvps_track_state_bytes(int capacity, int n_slots, size_t* bytes) {
 int slotvps_track_reset(void* state, size_t state_bytes, void* stream) {
   SV_REQUIRE(state && state_bytes >= 256, "bad argument");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   track::track_reset_kernel<<<1, 1, 0, s>>>((track::State*)state);
   SV_CHECK_LAUNCH("track_reset");
   return SLOTVPS_OK;
@@ -806,6 +811,7 @@ int slotvps_track_step(const float* fc_w, const float* fc_b, int num_fcs, const 
   const TrackLayout t = track_layout(state, capacity, n_slots);
   if (state_bytes < t.bytes) return fail(SLOTVPS_EWORKSPACE, "tracker state too small%s%s");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   // Both FC launches and the score launch size their grids for the maxima and exit on the device-side counts
   // (K' = meta[0], bank rows = State::count), so no count is read back; on the first frame of a video the bank
   // is empty and the assign kernel ignores lik / mid.
@@ -826,6 +832,7 @@ int slotvps_semantic_argmax(const float* fcn_output, int n_classes, int h, int w
   SV_REQUIRE(fcn_output && out, "null argument");
   SV_REQUIRE(n_classes > 0 && n_classes <= unify::MAXSEM && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   const long HW = (long)H * W;
   const int grid = (int)((HW + 255) / 256 < 148 * 8 ? (HW + 255) / 256 : 148 * 8);
   unify::semantic_argmax_kernel<<<grid, 256, 0, s>>>(fcn_output, n_classes, h, w, H, W, (long long*)out);
@@ -855,6 +862,7 @@ int slotvps_unify_workspace_bytes(size_t* bytes) {
 int slotvps_unify_reset(void* workspace, size_t workspace_bytes, void* stream) {
   SV_REQUIRE(workspace && workspace_bytes >= unify_layout(nullptr).bytes, "bad workspace");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   unify::unify_reset_kernel<<<1, 1, 0, s>>>(unify_layout(workspace).st);
   SV_CHECK_LAUNCH("unify_reset");
   return SLOTVPS_OK;
@@ -870,6 +878,7 @@ int slotvps_unify_pan_result(const int64_t* seg, const int64_t* pan, const int32
   const UnifyLayout u = unify_layout(workspace);
   if (workspace_bytes < u.bytes) return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   const long HW = (long)H * W;
   SV_CHECK_CUDA(cudaMemsetAsync(u.hist, 0, sizeof(unsigned int) * unify::MAXID * unify::MAXSEM, s));
   const long chunks = (HW + 2047) / 2048;
@@ -888,6 +897,7 @@ int slotvps_unify_pan_result(const int64_t* seg, const int64_t* pan, const int32
 int slotvps_sine_pos(float* out, int h, int w, void* stream) {
   SV_REQUIRE(out && h > 0 && w > 0, "bad argument");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   sine_pos_kernel<<<(unsigned)(((long)C * h * w + 255) / 256), 256, 0, s>>>(out, h, w);
   SV_CHECK_LAUNCH("sine_pos");
   return SLOTVPS_OK;
@@ -932,6 +942,7 @@ int slotvps_mask_logits(const float* feat, const float* emb, const float* bw, co
   SV_REQUIRE(feat && emb && bw && bb && bm && bv && fg_bn && out && workspace, "null argument");
   SV_REQUIRE(n_slots > 0 && h > 0 && w > 0, "bad shape");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   const int P = h * w;
   Arena a(workspace, workspace_bytes);
   float* sc = a.take<float>(C); float* sh = a.take<float>(C);
@@ -964,6 +975,7 @@ int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, s
   const int l = d->n_levels - 1, N = d->n_slots, h = d->h[l], w = d->w[l], P = h * w;
   if (!(d->kernel_path == 0 && tc_supported(d, l) && N <= mask::NROW)) return fail(SLOTVPS_EUNSUPPORTED, "planes unavailable%s%s");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   HeadWs hw;
   if (head_ws_layout(d, head_workspace, head_workspace_bytes, &hw) > head_workspace_bytes) return fail(SLOTVPS_EWORKSPACE, "head workspace too small%s%s");
   Arena a(workspace, workspace_bytes);
@@ -1013,6 +1025,7 @@ int slotvps_panoptic_fuse(const slotvps_fusion_cfg* cfg, const float* pred_logit
   SV_REQUIRE(N > 0 && N <= FUSE_MAXN && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
   SV_REQUIRE(cfg->num_classes >= 2 && cfg->stuff_num >= 0 && cfg->max_iters >= 1, "bad config");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   FuseWs ws;
   if (fuse_ws_layout(N, H, W, workspace, workspace_bytes, &ws) > workspace_bytes)
     return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
@@ -1061,6 +1074,7 @@ int slotvps_slot_attention(const slotvps_stage_params* sp, const float* slots_p,
                            int N, int h, int wd, int kernel_path, void* workspace, size_t workspace_bytes, void* stream) {
   SV_REQUIRE(sp && slots_p && x && out && workspace, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
   slotvps_head_desc d;
   memset(&d, 0, sizeof(d));
   d.n_frames = 1; d.n_slots = N; d.n_levels = 1; d.heads_per_level[0] = 1; d.h[0] = h; d.w[0] = wd;

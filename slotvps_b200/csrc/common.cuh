@@ -43,6 +43,13 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
     if (::slotvps::g_prof_on) ::slotvps::prof_mark(name, s);                           \
   } while (0)
 
+// First statement of an entry point (after `cudaStream_t s`): while profiling, the time the stream sat idle waiting
+// for the host to call us is booked under "(host gap)" instead of inflating the entry point's first kernel.
+#define SV_PROF_ENTRY()                                                                \
+  do {                                                                                 \
+    if (::slotvps::g_prof_on) ::slotvps::prof_mark("(host gap)", s);                   \
+  } while (0)
+
 #define SV_REQUIRE(cond, msg)                                                          \
   do {                                                                                 \
     if (!(cond)) return ::slotvps::fail(SLOTVPS_EINVAL, "%s (%s)", msg, #cond);        \
