@@ -951,7 +951,8 @@ int slotvps_mask_logits(const float* feat, const float* emb, const float* bw, co
   if (!a.ok()) return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
   mask_prep_kernel<<<n_slots, 256, 0, s>>>(emb, bw, bb, bm, bv, fg_bn, sc, sh, e2, dn, aff, n_slots);
   SV_CHECK_LAUNCH("mask_prep");
-  feat_rnorm_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
+  if (P % 4 == 0 && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)rn & 15) == 0) feat_rnorm4_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
+  else feat_rnorm_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
   SV_CHECK_LAUNCH("feat_rnorm");
   GemmArgs g;
   g.A = e2; g.a_ms = C; g.a_ks = 1;
@@ -986,7 +987,8 @@ int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, s
   if (!a.ok()) return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
   mask_prep_kernel<<<N, 256, 0, s>>>(emb, bw, bb, bm, bv, fg_bn, sc, sh, e2, dn, aff, N);
   SV_CHECK_LAUNCH("mask_prep");
-  feat_rnorm_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
+  if (P % 4 == 0 && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)rn & 15) == 0) feat_rnorm4_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
+  else feat_rnorm_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
   SV_CHECK_LAUNCH("feat_rnorm");
   g_planes_kernel<<<(unsigned)(((long)mask::NROW * C + 255) / 256), 256, 0, s>>>(e2, ep, N, 1);
   SV_CHECK_LAUNCH("g_planes");

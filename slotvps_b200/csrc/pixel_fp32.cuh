@@ -277,4 +277,35 @@ __global__ void __launch_bounds__(256) feat_rnorm_kernel(const float* __restrict
   rn[p] = 1.f / fmaxf(sqrtf(s), 1e-12f);
 }
 
+// Same for P % 4 == 0 and a 16-byte aligned x: 4 pixels per thread (128-bit loads along the pixel axis), the 256
+// channels split over 4 thread groups of a block and combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) feat_rnorm4_kernel(const float* __restrict__ x, const float* __restrict__ sc,
+                                                          const float* __restrict__ sh, float* __restrict__ rn, int P) {
+  __shared__ float4 part[4][64];
+  const int q = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int p = (blockIdx.x * 64 + q) * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p < P) {
+#pragma unroll 8
+    for (int c = g * 64; c < g * 64 + 64; ++c) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + (long)c * P + p));
+      const float a = __ldg(sc + c), b = __ldg(sh + c);
+      float t;
+      t = fmaf(a, v.x, b); s.x = fmaf(t, t, s.x);
+      t = fmaf(a, v.y, b); s.y = fmaf(t, t, s.y);
+      t = fmaf(a, v.z, b); s.z = fmaf(t, t, s.z);
+      t = fmaf(a, v.w, b); s.w = fmaf(t, t, s.w);
+    }
+  }
+  part[g][q] = s;
+  __syncthreads();
+  if (g == 0 && p < P) {
+    float4 t = part[0][q];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) { const float4 u = part[k][q]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    *reinterpret_cast<float4*>(rn + p) = make_float4(1.f / fmaxf(sqrtf(t.x), 1e-12f), 1.f / fmaxf(sqrtf(t.y), 1e-12f),
+                                                     1.f / fmaxf(sqrtf(t.z), 1e-12f), 1.f / fmaxf(sqrtf(t.w), 1e-12f));
+  }
+}
+
 }  // namespace slotvps
