@@ -225,6 +225,10 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         ccol = min(max(first + lane, 0), cw - 1);
         cbase = t * ch * cw;
       }
+      if (coop && rv && lane < 18) {                          // first chunk's coarse rows, requested before the accumulator wait
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(prm.y_in + (long)(cbase + cy0 * (prm.w / 2) + ccol) * C + jhalf * 128));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(prm.y_in + (long)(cbase + cy1 * (prm.w / 2) + ccol) * C + jhalf * 128));
+      }
       tc::mbar_wait(&tfull[g], u & 1);
       tc::tc_fence_after();
 #pragma unroll 1
@@ -247,6 +251,10 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // touches (two coarse rows each, blended vertically), every lane then takes its two columns by shuffle
           const float* r0 = prm.y_in + (long)(cbase + cy0 * (prm.w / 2) + ccol) * C + j * 32;
           const float* r1 = prm.y_in + (long)(cbase + cy1 * (prm.w / 2) + ccol) * C + j * 32;
+          if (lane < 18 && j + 1 < jhalf * 4 + 4) {            // next chunk's two 128-byte lines -> L1 while this chunk is processed
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(r0 + 32));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(r1 + 32));
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float ta[8], tb[8];
