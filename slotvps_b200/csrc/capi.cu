@@ -296,7 +296,7 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
     SV_CHECK_LAUNCH("proj_rstd(v)");
   }
   int chunks = 0;
-  if (use_tc && N <= attn::NROW) {
+  if (use_tc) {
     PosSep pa = px.ps;
     if (pa.enabled && pa.tky != nullptr) {
       // pgy[t][row][n] = sum_{c<128} ytab[c][row] G[t][n][c] ; pgx[t][col][n] = sum_{c<128} xtab[c][col] G[t][n][128+c]
@@ -599,7 +599,7 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
   for (int t = 0; t < T; ++t) SV_TRY(dcopy(init_query[t], w.slots + (long)t * N * C, (long)N * C, s));
   const long cls_fs = (long)S * N * d->num_classes, emb_fs = (long)S * N * C;
   // Overlapped (two-stream) schedule when every level runs the tensor-core kernels end to end.
-  bool overlap = d->kernel_path == 0 && N <= attn::NROW;
+  bool overlap = d->kernel_path == 0;
   for (int l = 0; l < L; ++l) overlap = overlap && tc_supported(d, l) && d->heads_per_level[l] > 0;
   if (getenv("SLOTVPS_NO_OVERLAP") || g_prof_on) overlap = false;     // per-launch event timing needs one stream
   cudaStream_t sb = s;
@@ -620,12 +620,12 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
   for (int l = 0; l < L; ++l) {
     const int h = d->h[l], wd = d->w[l], P = h * wd;
     const bool use_tc = d->kernel_path == 0 && tc_supported(d, l);
-    const bool all_tc = use_tc && N <= attn::NROW;          // no fp32 kernel touches pos at this level
+    const bool all_tc = use_tc;                               // no fp32 kernel touches pos at this level
     const bool fuse_tc = use_tc && (l == 0 || prev_planes);  // the coarse GEMM reads the previous level's planes
     // Separable-pos mode (x planes only, position terms from tables).  Measured on B200 at 1024x2048: level fusion
     // gets 0.15 ms/step faster (2 planes instead of 4) but the table loads make the statistics / attention epilogues
     // 0.19 ms/step slower, so it is opt-in (SLOTVPS_POS_SEP=1); pos == None always uses it (no tables needed).
-    const bool pos_sep = use_tc && d->pos_mode != 1 && (d->pos_mode == 0 || getenv("SLOTVPS_POS_SEP") != nullptr);
+    const bool pos_sep = use_tc && d->pos_mode != 1 && (d->pos_mode == 0 || (getenv("SLOTVPS_POS_SEP") != nullptr && N <= attn::NROW));
     TcWorkspace tcl = w.tc, tcp = w.tc;                      // this level's / the previous level's operand planes
     if (overlap) { tcl.planes = (l & 1) ? w.tc.planes_alt : w.tc.planes; tcp.planes = (l & 1) ? w.tc.planes : w.tc.planes_alt; }
     tcl.ytab = w.tc.ytab_l[l]; tcl.xtab = w.tc.xtab_l[l];      // per-level sine tables
@@ -974,7 +974,7 @@ int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, s
   SV_REQUIRE(head_workspace && feat && emb && bw && bb && bm && bv && fg_bn && out && workspace, "null argument");
   SV_REQUIRE(frame >= 0 && frame < d->n_frames, "frame out of range");
   const int l = d->n_levels - 1, N = d->n_slots, h = d->h[l], w = d->w[l], P = h * w;
-  if (!(d->kernel_path == 0 && tc_supported(d, l) && N <= mask::NROW)) return fail(SLOTVPS_EUNSUPPORTED, "planes unavailable%s%s");
+  if (!(d->kernel_path == 0 && tc_supported(d, l))) return fail(SLOTVPS_EUNSUPPORTED, "planes unavailable%s%s");
   cudaStream_t s = (cudaStream_t)stream;
   SV_PROF_ENTRY();
   HeadWs hw;
@@ -990,12 +990,19 @@ int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, s
   if (P % 4 == 0 && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)rn & 15) == 0) feat_rnorm4_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
   else feat_rnorm_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
   SV_CHECK_LAUNCH("feat_rnorm");
-  g_planes_kernel<<<(unsigned)(((long)mask::NROW * C + 255) / 256), 256, 0, s>>>(e2, ep, N, 1);
-  SV_CHECK_LAUNCH("g_planes");
   const long rows = (long)d->n_frames * P;
   // the finest level used the alternate plane set iff the head call ran the overlapped schedule (recorded by it)
   const __half* planes = g_last_head_alt ? hw.tc.planes_alt : hw.tc.planes;
-  return mask_tc_launch(planes, 2 * rows, rows, (long)frame * P, ep, dn, rn, aff, out, N, P, s);
+  // slots are independent here, so N > 104 simply runs the kernel once per group of <= 104 slots
+  const int groups = ceil_div(N, mask::NROW), base = N / groups, extra = N % groups;
+  for (int g = 0, n0 = 0; g < groups; ++g) {
+    const int ng = base + (g < extra ? 1 : 0);
+    g_planes_kernel<<<(unsigned)(((long)mask::NROW * C + 255) / 256), 256, 0, s>>>(e2, ep, ng, 1, n0, N);
+    SV_CHECK_LAUNCH("g_planes");
+    SV_TRY(mask_tc_launch(planes, 2 * rows, rows, (long)frame * P, ep, dn + n0, rn, aff, out + (long)n0 * P, ng, P, s));
+    n0 += ng;
+  }
+  return SLOTVPS_OK;
 }
 
 // ---- panoptic fusion ----------------------------------------------------------------------------------

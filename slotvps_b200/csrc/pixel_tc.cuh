@@ -25,7 +25,8 @@ struct TcWorkspace {
   __half* planes_alt = nullptr;  // second plane set: levels alternate so the next level's fusion can overlap this level's stages
   float *ytab = nullptr, *xtab = nullptr;  // separable sine tables [128][h], [128][w] of the CURRENT level
   float *ytab_l[SLOTVPS_MAX_LEVELS] = {nullptr}, *xtab_l[SLOTVPS_MAX_LEVELS] = {nullptr};   // one pair per level (the side stream runs ahead)
-  __half* gplanes = nullptr;     // [T][2][112][256] folded query operand G, hi/lo
+  __half* gplanes = nullptr;     // [groups][T][2][104][256] folded query operand G, hi/lo (one copy per slot group)
+  float2* ml = nullptr;          // [groups + 1][T*Pmax] per-pixel softmax (max, sum) of each slot group + combined (N > 104 only)
   long plane_rows = 0;                  // rows allocated per plane (T*Pmax)
 };
 
@@ -53,7 +54,9 @@ inline void tc_workspace_layout(Arena& a, const slotvps_head_desc* d, TcWorkspac
     w->planes_alt = a.take<__half>((size_t)4 * w->plane_rows * C);
     for (int l = 0; l < SLOTVPS_MAX_LEVELS; ++l) { w->ytab_l[l] = a.take<float>((size_t)128 * hmax); w->xtab_l[l] = a.take<float>((size_t)128 * wmax); }
     w->ytab = w->ytab_l[0]; w->xtab = w->xtab_l[0];
-    w->gplanes = a.take<__half>((size_t)d->n_frames * 2 * 112 * C);
+    const int groups = (d->n_slots + 103) / 104;
+    w->gplanes = a.take<__half>((size_t)groups * d->n_frames * 2 * 112 * C);
+    if (groups > 1) w->ml = a.take<float2>((size_t)(groups + 1) * w->plane_rows);
   }
 }
 // shapes the tensor-core kernels serve; everything else runs on the fp32 path
@@ -368,25 +371,39 @@ static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(OFF_G % 1024 == 0 && G_SUB % 1024 == 0 && OFF_P % 1024 == 0 && P_SUB % 1024 == 0 && OFF_AUX % 1024 == 0, "swizzle atoms");
 }  // namespace attn
 
-__global__ void __launch_bounds__(256) g_planes_kernel(const float* __restrict__ G, __half* __restrict__ out, int N, int T) {
-  // out [T][2][NROW][256]; rows >= N are zero
+__global__ void __launch_bounds__(256) g_planes_kernel(const float* __restrict__ G, __half* __restrict__ out, int N, int T, int n0 = 0, int Ntot = 0) {
+  // out [T][2][NROW][256] for slots n0 .. n0+N-1 of the Ntot rows of G per frame; rows >= N are zero
+  if (Ntot == 0) Ntot = N;
   long i = (long)blockIdx.x * 256 + threadIdx.x;
   long total = (long)T * attn::NROW * C;
   if (i >= total) return;
   int c = (int)(i % C), n = (int)((i / C) % attn::NROW), t = (int)(i / ((long)C * attn::NROW));
   __half h = __float2half_rn(0.f), l = h;
-  if (n < N) split_bf16(G[((long)t * N + n) * C + c], h, l);
+  if (n < N) split_bf16(G[((long)t * Ntot + n0 + n) * C + c], h, l);
   long o = ((long)t * 2 * attn::NROW + n) * C + c;
   out[o] = h;
   out[o + (long)attn::NROW * C] = l;
 }
 
+// Slot groups (N > 104): the softmax runs over ALL slots of a pixel, so the kernel has three modes.
+//   MODE 0  one group holds every slot: S, softmax, Z in one pass (the shipped N = 100 case).
+//   MODE 1  denominator pass of one group: S only; writes the group's per-pixel (max, sum of exp) to grp.ml_out.
+//   MODE 2  accumulation pass of one group: softmax weights exp(S - M) / L with the COMBINED (M, L) of grp.ml_in.
+struct SlotGroup {
+  int n0 = 0, n_total = 0;              // first slot of the group, slots per frame overall (N of the kernel = slots in the group)
+  const float2* ml_in = nullptr;        // [T*P] combined (M, L)
+  float2* ml_out = nullptr;             // [T*P] this group's (m, l)
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(attn::THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g,
                const float* __restrict__ g0, const float* __restrict__ g1, const float* __restrict__ rs_k,
                const float* __restrict__ rs_v, float* __restrict__ Zpart, float* __restrict__ a0part,
-               float* __restrict__ a1part, const __half* __restrict__ planes, int N, int P, int T, int plane_rows, int tiles_per_frame, int dbg, const PosSep ps) {
+               float* __restrict__ a1part, const __half* __restrict__ planes, int N, int P, int T, int plane_rows, int tiles_per_frame, int dbg, const PosSep ps,
+               const SlotGroup grp) {
   using namespace attn;
+  const int Ntot = MODE == 0 ? N : grp.n_total, n0 = MODE == 0 ? 0 : grp.n0;
   extern __shared__ uint8_t raw_smem[];
   const uint32_t raw = tc::smem_u32(raw_smem);
   uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
@@ -415,7 +432,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     tc::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < NPAD; i += THREADS)
-    gc[i] = i < N ? make_float2(g0[(long)t * N + i], g1[(long)t * N + i]) : make_float2(0.f, 0.f);
+    gc[i] = i < N ? make_float2(g0[(long)t * Ntot + n0 + i], g1[(long)t * Ntot + n0 + i]) : make_float2(0.f, 0.f);
   // aux tile: row 0 = 1.0 (-> a1), row 1 = sigma_v per pixel (rewritten every tile), rows 2..15 = 0.
   // Row r lives at byte r*128 of each 64-pixel half; 16-byte chunk index is XOR-swizzled with (r & 7).
   for (int i = threadIdx.x; i < AUXT_BYTES / 2; i += THREADS) {
@@ -477,7 +494,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     if (do_prefetch && lane != 0 && n_my > 1) prefetch_tile(1);
     __syncwarp();
     for (int i = 0; i < n_my; ++i) {
-      if (lane == 0) { if (i + 1 < n_my) job_s(i + 1); job_z(i); }
+      if (lane == 0) { if (i + 1 < n_my) job_s(i + 1); if (MODE != 1) job_z(i); }
       else if (do_prefetch && i + 2 < n_my) prefetch_tile(i + 2);
       __syncwarp();
     }
@@ -555,8 +572,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         tc::umma_commit(pempty);                            // P may be overwritten once these retire
       };
       issue_s(0);
-      for (int i = 0; i < n_my; ++i) { if (i + 1 < n_my) issue_s(i + 1); issue_z(i); }
-      tc::umma_commit(zfull);
+      for (int i = 0; i < n_my; ++i) { if (i + 1 < n_my) issue_s(i + 1); if (MODE != 1) issue_z(i); }
+      if (MODE != 1) tc::umma_commit(zfull);
     }
   } else {
     // ===================== softmax warps (one pixel per thread) + final epilogue =====================
@@ -606,8 +623,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         mx = fmaxf(mx, s);
       }
       float sum = 0.f;
+      if (MODE == 2) {                                      // the maximum / denominator over ALL slot groups of this pixel
+        const float2 ml = pv ? grp.ml_in[(long)t * P + p] : make_float2(0.f, 1.f);
+        mx = ml.x; sum = ml.y;
 #pragma unroll
-      for (int n = 0; n < NPAD; ++n) { const float e = __expf(sv[n] - mx); sv[n] = e; sum += e; }
+        for (int n = 0; n < NPAD; ++n) sv[n] = __expf(sv[n] - mx);
+      } else {
+#pragma unroll
+        for (int n = 0; n < NPAD; ++n) { const float e = __expf(sv[n] - mx); sv[n] = e; sum += e; }
+      }
+      if (MODE == 1) {
+        if (pv) grp.ml_out[(long)t * P + p] = make_float2(mx, sum);
+        continue;
+      }
       const float sc = pv ? rv / sum : 0.f;                 // A' = A * rs_v
       tc::mbar_wait(pempty, (i & 1) ^ 1);                   // Z(i-1) has finished reading P
 #pragma unroll
@@ -623,9 +651,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       tc::mbar_arrive(pfull);
     }
     // ---- final epilogue: Z^T (lanes = channels) and aux (lanes = slots) -> per-CTA partials ----
+    if (MODE != 1) {
     tc::mbar_wait(zfull, 0);
     tc::tc_fence_after();
-    float* Zp = Zpart + ((long)chunk * T + t) * N * C;
+    float* Zp = Zpart + (((long)chunk * T + t) * Ntot + n0) * C;
     for (int mt = 0; mt < 2; ++mt) {
       const int ch = mt * 128 + r;
       for (int j = 0; j < 4; ++j) {
@@ -640,7 +669,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       float v[32];
       tc::tmem_ld32(tmem_base + lane_addr + TM_AUX, v);     // reads 16 columns past aux (unused)
       tc::tmem_ld_wait();
-      if (r < N) { a1part[((long)chunk * T + t) * N + r] = v[0]; a0part[((long)chunk * T + t) * N + r] = v[1]; }
+      if (r < N) { a1part[((long)chunk * T + t) * Ntot + n0 + r] = v[0]; a0part[((long)chunk * T + t) * Ntot + n0 + r] = v[1]; }
+    }
     }
   }
   tc::tc_fence_before();
@@ -657,27 +687,77 @@ inline int chunks_for(int P, int T) {
 }
 }  // namespace attn
 
-// Zpart/a0part/a1part [chunks][T][N]..., returns the chunk count through *chunks_out
+// combined per-pixel softmax statistics of `groups` slot groups: M = max m_g, L = sum l_g exp(m_g - M)
+__global__ void __launch_bounds__(256) ml_combine_kernel(const float2* __restrict__ ml_g, long stride, int groups, long n, float2* __restrict__ out) {
+  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float M = -INFINITY;
+  for (int g = 0; g < groups; ++g) M = fmaxf(M, ml_g[g * stride + i].x);
+  float L = 0.f;
+  for (int g = 0; g < groups; ++g) { const float2 v = ml_g[g * stride + i]; L += v.y * __expf(v.x - M); }
+  out[i] = make_float2(M, L);
+}
+
+template <int MODE>
+inline int attn_tc_launch(const CUtensorMap& mx, const CUtensorMap& mg, const float* g0, const float* g1, const float* rs_k, const float* rs_v,
+                          float* Zpart, float* a0part, float* a1part, const __half* planes, int N, int P, int T, long rows, int chunks,
+                          const PosSep& ps, const SlotGroup& grp, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    SV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+    attr_done = true;
+  }
+  attn_tc_kernel<MODE><<<dim3(chunks, T), attn::THREADS, attn::SMEM_BYTES, s>>>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, planes, N, P, T,
+                                                                                (int)rows, ceil_div(P, attn::TILE_M),
+                                                                                getenv("SLOTVPS_TC_DEBUG") ? atoi(getenv("SLOTVPS_TC_DEBUG")) : 0, ps, grp);
+  SV_CHECK_LAUNCH(MODE == 0 ? "attn_tc" : MODE == 1 ? "attn_tc(denominators)" : "attn_tc(group)");
+  return SLOTVPS_OK;
+}
+
+// Zpart/a0part/a1part [chunks][T][N]..., returns the chunk count through *chunks_out.
+// N <= 104: one pass.  N > 104: slot groups of <= 104; a denominator pass per group, the per-pixel (max, sum) of
+// the groups are combined, then one accumulation pass per group writes its slots' rows of the partials.
 inline int tc_attention(const TcWorkspace& ws, __half* gplanes, const float* G, const float* g0, const float* g1,
                         const float* rs_k, const float* rs_v, float* Zpart, float* a0part, float* a1part, int T, int N, int P,
                         int* chunks_out, cudaStream_t s, const PosSep& ps = PosSep()) {
-  g_planes_kernel<<<(unsigned)(((long)T * attn::NROW * C + 255) / 256), 256, 0, s>>>(G, gplanes, N, T);
-  SV_CHECK_LAUNCH("g_planes");
   CUtensorMap mx, mg;
   const long rows = (long)T * P;
   SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)(ps.enabled ? 2 : 4) * rows, C, attn::TILE_M));
-  SV_TRY(tc::make_tmap_h16_sw128(&mg, gplanes, (uint64_t)T * 2 * attn::NROW, C, attn::NROW));
-  static bool attr_done = false;
-  if (!attr_done) {
-    SV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-    attr_done = true;
-  }
-  const int tiles_per_frame = ceil_div(P, attn::TILE_M);
   const int chunks = attn::chunks_for(P, T);
-  attn_tc_kernel<<<dim3(chunks, T), attn::THREADS, attn::SMEM_BYTES, s>>>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, ws.planes, N, P, T,
-                                                                          (int)rows, tiles_per_frame, getenv("SLOTVPS_TC_DEBUG") ? atoi(getenv("SLOTVPS_TC_DEBUG")) : 0, ps);
-  SV_CHECK_LAUNCH("attn_tc");
   *chunks_out = chunks;
+  const int groups = ceil_div(N, attn::NROW);
+  const size_t gstride = (size_t)T * 2 * attn::NROW * C;
+  if (groups == 1) {
+    g_planes_kernel<<<(unsigned)(((long)T * attn::NROW * C + 255) / 256), 256, 0, s>>>(G, gplanes, N, T);
+    SV_CHECK_LAUNCH("g_planes");
+    SV_TRY(tc::make_tmap_h16_sw128(&mg, gplanes, (uint64_t)T * 2 * attn::NROW, C, attn::NROW));
+    return attn_tc_launch<0>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, ws.planes, N, P, T, rows, chunks, ps, SlotGroup(), s);
+  }
+  SV_REQUIRE(ws.ml != nullptr && !(ps.enabled && ps.tky), "slot groups need the softmax-statistics workspace and materialised (x+pos) planes");
+  const int base = N / groups, extra = N % groups;
+  int n0 = 0;
+  for (int g = 0; g < groups; ++g) {                       // denominator passes
+    const int ng = base + (g < extra ? 1 : 0);
+    g_planes_kernel<<<(unsigned)(((long)T * attn::NROW * C + 255) / 256), 256, 0, s>>>(G, gplanes + g * gstride, ng, T, n0, N);
+    SV_CHECK_LAUNCH("g_planes");
+    SV_TRY(tc::make_tmap_h16_sw128(&mg, gplanes + g * gstride, (uint64_t)T * 2 * attn::NROW, C, attn::NROW));
+    SlotGroup grp;
+    grp.n0 = n0; grp.n_total = N; grp.ml_out = ws.ml + (size_t)g * ws.plane_rows;
+    SV_TRY(attn_tc_launch<1>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, ws.planes, ng, P, T, rows, chunks, ps, grp, s));
+    n0 += ng;
+  }
+  float2* ml_all = ws.ml + (size_t)groups * ws.plane_rows;
+  ml_combine_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(ws.ml, ws.plane_rows, groups, rows, ml_all);
+  SV_CHECK_LAUNCH("ml_combine");
+  n0 = 0;
+  for (int g = 0; g < groups; ++g) {                       // accumulation passes
+    const int ng = base + (g < extra ? 1 : 0);
+    SV_TRY(tc::make_tmap_h16_sw128(&mg, gplanes + g * gstride, (uint64_t)T * 2 * attn::NROW, C, attn::NROW));
+    SlotGroup grp;
+    grp.n0 = n0; grp.n_total = N; grp.ml_in = ml_all;
+    SV_TRY(attn_tc_launch<2>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, ws.planes, ng, P, T, rows, chunks, ps, grp, s));
+    n0 += ng;
+  }
   return SLOTVPS_OK;
 }
 

@@ -68,7 +68,8 @@ def test_level_fuse(dev, h, w):
 
 @pytest.mark.parametrize("kernel_path", PATHS)
 @pytest.mark.parametrize("N,h,w,use_pos", [(100, 16, 32, True), (100, 32, 64, True), (50, 12, 20, False),
-                                           (128, 24, 40, True), (300, 16, 24, True), (7, 5, 3, True)])
+                                           (128, 24, 40, True), (300, 16, 24, True), (7, 5, 3, True),
+                                           (200, 32, 64, True), (209, 24, 40, False), (512, 16, 32, True)])
 def test_slot_attention_teacher_forced(dev, kernel_path, N, h, w, use_pos):
     """MaskDynamicConv on given inputs (dynamic_mask_head.py:423-461) vs the fp64 oracle."""
     sd = synthetic.make_head_state_dict(5)
@@ -342,7 +343,8 @@ def test_config5_iteration_sweep(dev, heads, temporal):
 
 @pytest.mark.parametrize("N", [50, 200, 300])
 def test_config5_slot_sweep(dev, N):
-    """BASELINE configs[4]: slot-count sweep (N > 104 runs the fp32 attention kernel with the tensor-core statistics)."""
+    """BASELINE configs[4]: slot-count sweep (N > 104 runs the tensor-core attention in slot groups of <= 104:
+    a denominator pass per group, combined per-pixel softmax statistics, an accumulation pass per group)."""
     T, shapes = 2, [(4, 8), (8, 16), (16, 32), (32, 64)]
     sd = synthetic.make_head_state_dict(12)
     cap = synthetic.make_capsule_params(12, N)
@@ -624,3 +626,26 @@ def test_semantic_argmax_full_size(dev):
     top2 = up.topk(2, dim=1).values
     near = (top2[:, 0] - top2[:, 1]) < 1e-4
     assert int(((got != ref) & ~near).sum()) == 0
+
+
+@pytest.mark.parametrize("N", [200, 300])
+def test_slot_groups_whole_clip(dev, N):
+    """N > 104 through the whole tensor-core path at 256x512 (grouped attention + grouped mask logits) vs the fp32 path
+    and the fp64 oracle (mask logits teacher-forced)."""
+    T, H, W = 2, 256, 512
+    sd = synthetic.make_head_state_dict(3)
+    cap = synthetic.make_capsule_params(3, N)
+    feats = [[f.to(dev) for f in fr] for fr in synthetic.make_features(H, W, T=T, video=4, frame=1)]
+    outs = []
+    for kp in (1, 0):
+        m = sv.SlotVPSRetriever({**sv.HEAD_KWARGS, "kernel_path": kp}, N, sv.FUSION_KWARGS)
+        m.dynamic_mask_head.load_state_dict(sd)
+        m.load_capsule_params(cap)
+        outs.append(m.to(dev)(feats, (H, W), fuse=False))
+    a, b = outs
+    e0 = rel(b["emb"][1][0], a["emb"][1][0])
+    print(f"N={N} 256x512: tc-vs-fp32 path stage-0 emb rel {e0:.2e}, stage-6 {rel(b['emb'][1][6], a['emb'][1][6]):.2e}")
+    assert e0 < 3e-5
+    ref = O.mask_logits(b["feats"][1][3][0].double().cpu(), b["emb"][1][-1, 0].double().cpu(), {k: v.double() for k, v in cap.items()})
+    assert b["pred_masks"].shape == (N, H // 4, W // 4)
+    assert rel(b["pred_masks"], ref) < 1e-4
