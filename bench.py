@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
-    ap.add_argument("--inflight", type=int, default=6, help="clips in flight per GPU (independent clips on separate streams)")
+    ap.add_argument("--inflight", type=int, default=8, help="clips in flight per GPU (independent clips on separate streams)")
     return ap.parse_args()
 
 
@@ -237,6 +237,7 @@ def main():
         # clips' kernels, and narrower grids interleave better (measured 64 > 112 > 148); the library default (112)
         # is the single-clip latency optimum.
         os.environ.setdefault("SLOTVPS_SIDE_CTAS", "64")
+        os.environ.setdefault("SLOTVPS_MAIN_CTAS", "64")
     pan = torch.empty((K, H, W), dtype=torch.int64, device=dev) if world > 1 else None
     L = sv.lib()
 
@@ -453,7 +454,7 @@ def main():
                                 frames_convention="retriever frames/s = T * clips/s; output frames/s = clips/s",
                                 l2="inputs larger than L2 (178 MB/clip); one resident clip per lane, lanes alternate",
                                 fusion_logits="designed (random-init heads keep no slot)",
-                                kernel_path=args.kernel_path, cuda_graph=not args.no_graph, clips_in_flight=M, numa_bind=numa, side_stream_ctas=int(os.environ.get("SLOTVPS_SIDE_CTAS", "112")),
+                                kernel_path=args.kernel_path, cuda_graph=not args.no_graph, clips_in_flight=M, numa_bind=numa, side_stream_ctas=int(os.environ.get("SLOTVPS_SIDE_CTAS", "112")), main_stream_ctas=int(os.environ.get("SLOTVPS_MAIN_CTAS", "148")),
                                 single_clip_in_flight_ms_per_step=single_ms, sharding="clips per rank, one all_gather of id maps" if world > 1 else "single GPU",
                                 kept_slots=meta["k"], fusion_iters=meta["iters"]),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,

@@ -148,7 +148,7 @@ inline int mask_tc_launch(const __half* planes, long plane_rows_total, long lo_r
     attr_done = true;
   }
   const int n_tiles = ceil_div(P, mask::TILE_M);
-  const int grid = n_tiles < 148 ? n_tiles : 148;
+  const int grid = n_tiles < main_ctas() ? n_tiles : main_ctas();
   mask_tc_kernel<<<grid, mask::THREADS, mask::SMEM_BYTES, s>>>(mx, me, dn, rn, aff, out, N, P, (int)row0, (int)lo_row);
   SV_CHECK_LAUNCH("mask_tc");
   return SLOTVPS_OK;

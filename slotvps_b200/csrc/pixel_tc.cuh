@@ -678,10 +678,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
+// Total CTAs of one launch of the main-stream tensor-core kernels (attn_tc, mask_tc).  Default: every SM, the
+// single-clip latency optimum; with several clips in flight narrower grids let kernels with different bottlenecks
+// (tensor pipe / HBM / LSU) of different clips run side by side on disjoint SMs (SLOTVPS_MAIN_CTAS, measured 64 > 148).
+inline int main_ctas() {
+  static int v = 0;
+  if (v == 0) { const char* e = getenv("SLOTVPS_MAIN_CTAS"); const int x = e ? atoi(e) : 148; v = (x >= 8 && x <= 148) ? x : 148; }
+  return g_prof_on ? 148 : v;                               // the per-kernel profiling pass times every kernel alone, at full width
+}
 namespace attn {
 inline int chunks_for(int P, int T) {
   int tiles = ceil_div(P, TILE_M);
-  int per = 148 / (T > 0 ? T : 1);
+  int per = main_ctas() / (T > 0 ? T : 1);
   if (per < 1) per = 1;
   return tiles < per ? tiles : per;
 }
