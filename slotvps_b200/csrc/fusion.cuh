@@ -244,10 +244,33 @@ __global__ void __launch_bounds__(256) fuse_count4_kernel(const float* __restric
   __syncthreads();
   const long P = (long)h * w;
   const int W = 4 * w;
+  const float screen_cut = pix_thr > 0.f ? __logf(pix_thr) - 0.05f : -INFINITY;     // margin >> fp32 rounding of the bound
   for (long blk = (long)blockIdx.x * 256 + threadIdx.x; blk < P; blk += (long)gridDim.x * 256) {
     const int i = (int)(blk / w), j = (int)(blk % w);
     Blk4 b4;
     b4.setup(i, j, h, w);
+    // Conservative screen: every output value of the block is a convex combination of the slot's 3x3 source taps,
+    // so p_k <= exp(max tap_k) / sum_j exp(min tap_j).  If that bound stays below pixel_threshold for every thing,
+    // no pixel of the block has a candidate and the three exact passes are skipped (stuff-only regions).
+    {
+      float umax = -INFINITY, m = -INFINITY, ssum = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float* mk = masks + (long)s_ord[k] * P;
+        float tmax = -INFINITY, tmin = INFINITY;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) { const float tv = __ldg(mk + b4.r[a] * w + b4.c[b]); tmax = fmaxf(tmax, tv); tmin = fminf(tmin, tv); }
+        if (k >= ns) umax = fmaxf(umax, tmax);
+        if (tmin > m) { ssum = ssum * __expf(m - tmin) + 1.f; m = tmin; } else ssum += __expf(tmin - m);
+      }
+      if (ns == K || umax - (m + __logf(ssum)) < screen_cut) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          *reinterpret_cast<uint4*>(cand + (long)(4 * i + a) * W + 4 * j) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        continue;
+      }
+    }
     float mx[16], sum[16], v[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) { mx[e] = -INFINITY; sum[e] = 0.f; }
