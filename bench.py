@@ -402,7 +402,7 @@ def main():
                     px_step = sum(hd * h * w for hd, (h, w) in zip(heads, shapes)) * T
                     traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pixels"] * px_step / breakdown[name]["launches_per_step"]
             roofline = dict(kernel=name, bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
-                            executed_mma_tflops=3 * ach if name.endswith("_tc") else None,   # fp16 hi/lo split: 3 MMA products per algorithmic product
+                            executed_mma_tflops=3 * ach if name.endswith("_tc") else None, executed_frac=(3 * ach / peak) if name.endswith("_tc") else None,   # fp16 hi/lo split: 3 MMA products per algorithmic product
                             traffic=traffic, traffic_note="DRAM bytes per launch (ncu, level-3 capture scaled by pixels); the kernel's only large operand is the fp16 plane set it reads (4 x 512 B/pixel)", peak_source=f"{pk['source']} bf16 sustained (kernel timed inside the step)",
                             algorithmic_flops_per_step=fl, ms_per_step=t_ms, share_of_step=t_ms / total,
                             launches_per_step=breakdown[name]["launches_per_step"])
