@@ -274,6 +274,156 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
+// ---- the same statistics on CTA pairs (cta_group::2) ----------------------------------------------------------
+// stats_tc_kernel ingests 96 KB per pipeline stage (32 KB of planes + 64 KB of weight planes) for ~1536 MMA cycles,
+// i.e. it sits at the ~64 B/clk per-SM L2->shared-memory limit.  Here a cluster of two CTAs runs one M = 256 MMA
+// over two pixel tiles and each CTA stages only HALF of the weight tile (128 of the 256 output rows): 64 KB per
+// stage and SM, which also makes room for a third pipeline stage.
+namespace stats2 {
+constexpr int TILE_M = 128, KSUB = 64;
+constexpr int A_BYTES = TILE_M * 128;          // 16 KB  [128 px][64 ch] fp16
+constexpr int B_BYTES = 128 * 128;             // 16 KB  [128 out][64 ch] fp16 : this CTA's half of the weight tile
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // 64 KB
+constexpr int NSTAGE = 3;
+constexpr int AUX_BYTES = 4096;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + AUX_BYTES + 1024;
+constexpr int THREADS = 192;
+constexpr uint32_t IDESC = tc::make_idesc_f16(256, 256, 0, 0);
+}  // namespace stats2
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(stats2::THREADS, 1)
+stats_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                 const float* __restrict__ bk_c, const float* __restrict__ bv_c, float* __restrict__ rs_k,
+                 float* __restrict__ rs_v, int P, int T, int plane_rows, int tiles_per_frame, const PosSep ps) {
+  using namespace stats2;
+  extern __shared__ uint8_t raw_smem[];
+  const uint32_t raw = tc::smem_u32(raw_smem);
+  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
+  uint8_t* aux = smem + NSTAGE * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(aux);                  // [NSTAGE] used on the leader
+  uint64_t* empty = full + NSTAGE;                                    // [NSTAGE] in both CTAs (multicast commit)
+  uint64_t* tfull = empty + NSTAGE;                                   // [2] in both CTAs (multicast commit)
+  uint64_t* tempty = tfull + 2;                                       // [2] on the leader: 256 arrivals (both CTAs' epilogues)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* bias = reinterpret_cast<float*>(aux + 256);                  // [2][256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_tiles = T * tiles_per_frame;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_iter = ((n_tiles + 1) / 2 - pair + n_pairs - 1) / n_pairs;      // identical for both CTAs of the pair
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmap_x);
+    tc::tma_prefetch_desc(&tmap_w);
+    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 256); }
+    tc::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * C; i += THREADS) bias[i] = i < C ? bk_c[i] : bv_c[i - C];
+  if (warp == 1) { tc::tmem_alloc2(tmem_ptr, 512); tc::tmem_relinquish2(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();                                                 // the peer's barriers exist before anything targets them
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs): own pixel tile + own half of the weight tile =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int i = 0; i < n_iter; ++i) {
+        const int tile = (pair + i * n_pairs) * 2 + (int)rank;        // may be n_tiles (odd tail): rows past the data, results dropped
+        const int t = tile / tiles_per_frame, p0 = (tile % tiles_per_frame) * TILE_M;
+        const int row = t * P + p0;
+        for (int g = 0; g < 2; ++g) {
+          const int aq = (g == 0 && !ps.enabled) ? 2 : 0, bq = g == 0 ? 0 : 2;
+          for (int ks = 0; ks < C / KSUB; ++ks, ++it) {
+            const int s = it % NSTAGE;
+            tc::mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
+            uint8_t* st = smem + s * STAGE_BYTES;
+            if (leader) tc::mbar_expect_tx(&full[s], 2 * STAGE_BYTES);           // bytes of both CTAs land on this barrier
+            tc::tma_load_2d_pair(st, &tmap_x, ks * KSUB, aq * plane_rows + row, &full[s]);
+            tc::tma_load_2d_pair(st + A_BYTES, &tmap_x, ks * KSUB, (aq + 1) * plane_rows + row, &full[s]);
+            tc::tma_load_2d_pair(st + 2 * A_BYTES, &tmap_w, ks * KSUB, bq * C + (int)rank * 128, &full[s]);
+            tc::tma_load_2d_pair(st + 2 * A_BYTES + B_BYTES, &tmap_w, ks * KSUB, (bq + 1) * C + (int)rank * 128, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only): M = 256 over both CTAs =====================
+    if (lane == 0 && leader) {
+      uint32_t it = 0;
+      for (int i = 0; i < n_iter; ++i) {
+        for (int g = 0; g < 2; ++g) {
+          tc::mbar_wait(&tempty[g], (i & 1) ^ 1);
+          tc::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + g * 256;
+          for (int ks = 0; ks < C / KSUB; ++ks, ++it) {
+            const int s = it % NSTAGE;
+            tc::mbar_wait(&full[s], (it / NSTAGE) & 1);
+            tc::tc_fence_after();
+            const uint32_t a_hi = tc::smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+            const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+            const uint64_t dah = tc::make_smem_desc_sw128(a_hi, 16, 1024), dal = tc::make_smem_desc_sw128(a_lo, 16, 1024);
+            const uint64_t dbh = tc::make_smem_desc_sw128(b_hi, 16, 1024), dbl = tc::make_smem_desc_sw128(b_lo, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < KSUB / 16; ++k) {
+              tc::umma2_f16(d_tmem, dah + 2 * k, dbh + 2 * k, IDESC, (ks | k) != 0);
+              tc::umma2_f16(d_tmem, dal + 2 * k, dbh + 2 * k, IDESC, 1);
+              tc::umma2_f16(d_tmem, dah + 2 * k, dbl + 2 * k, IDESC, 1);
+            }
+            tc::umma2_commit_multicast(&empty[s], 3);       // slot s is free in both CTAs
+          }
+          tc::umma2_commit_multicast(&tfull[g], 3);         // accumulator g complete in both CTAs' TMEM
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): each drains its own 128 accumulator lanes =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    for (int i = 0; i < n_iter; ++i) {
+      const int tile = (pair + i * n_pairs) * 2 + (int)rank;
+      const int t = tile / tiles_per_frame, p = (tile % tiles_per_frame) * TILE_M + r;
+      const bool valid = tile < n_tiles && p < P;
+      for (int g = 0; g < 2; ++g) {
+        tc::mbar_wait(&tfull[g], i & 1);
+        tc::tc_fence_after();
+        const float* bg = bias + g * C;
+        const bool add_pos = g == 0 && ps.tky != nullptr && valid;
+        const float4* ty4 = add_pos ? reinterpret_cast<const float4*>(ps.tky + (long)(p / ps.w) * C) : nullptr;
+        const float4* tx4 = add_pos ? reinterpret_cast<const float4*>(ps.tkx + (long)(p % ps.w) * C) : nullptr;
+        float ss = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < C / 32; ++j) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + g * 256 + j * 32, v);
+          tc::tmem_ld_wait();
+          if (add_pos) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 a = __ldg(ty4 + j * 8 + c), b = __ldg(tx4 + j * 8 + c);
+              v[4 * c] += a.x + b.x; v[4 * c + 1] += a.y + b.y; v[4 * c + 2] += a.z + b.z; v[4 * c + 3] += a.w + b.w;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { float d = v[c] + bg[j * 32 + c]; ss = fmaf(d, d, ss); }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive_remote(&tempty[g], 0);              // the leader's MMA waits for the epilogues of both CTAs
+        if (valid) (g == 0 ? rs_k : rs_v)[(long)t * P + p] = rsqrtf(ss * (1.f / C) + LN_EPS);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();                                                 // neither CTA leaves while the other may still signal it
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc2(tmem_base, 512); }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------
 inline int tc_prepare_stage(const slotvps_stage_params& sp, const float* Wk_c, const float* bk_c, const float* Wv_c,
                             const float* bv_c, TcStageOperands& o, cudaStream_t s) {
@@ -322,6 +472,21 @@ inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const flo
   }
   const int tiles_per_frame = ceil_div(P, stats::TILE_M);
   const int n_tiles = T * tiles_per_frame;
+  static const int use_pairs = getenv("SLOTVPS_STATS_PAIRS") ? atoi(getenv("SLOTVPS_STATS_PAIRS")) : 1;   // CTA pairs by default
+  if (use_pairs && n_tiles >= 2) {
+    CUtensorMap mw2;
+    SV_TRY(tc::make_tmap_h16_sw128(&mw2, ops.wplanes, (uint64_t)4 * C, C, 128));
+    static bool attr2_done = false;
+    if (!attr2_done) {
+      SV_CHECK_CUDA(cudaFuncSetAttribute(stats_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stats2::SMEM_BYTES));
+      attr2_done = true;
+    }
+    int grid2 = 2 * ((n_tiles + 1) / 2);
+    if (grid2 > (max_ctas & ~1)) grid2 = max_ctas & ~1;
+    stats_tc2_kernel<<<grid2, stats2::THREADS, stats2::SMEM_BYTES, s>>>(mx, mw2, bk_c, bv_c, rs_k, rs_v, P, T, (int)rows, tiles_per_frame, ps);
+    SV_CHECK_LAUNCH("stats_tc");
+    return SLOTVPS_OK;
+  }
   const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
   stats_tc_kernel<<<grid, stats::THREADS, stats::SMEM_BYTES, s>>>(mx, mw, bk_c, bv_c, rs_k, rs_v, P, T, (int)rows, tiles_per_frame, ps);
   SV_CHECK_LAUNCH("stats_tc");
