@@ -388,29 +388,52 @@ def main():
         rows = [r.split("\t") for r in buf.value.decode().strip().split("\n") if r]
         breakdown = {r[0]: dict(launches_per_step=int(r[1]) / nprof, ms_per_step=float(r[2]) / nprof) for r in rows}
         total = sum(v["ms_per_step"] for v in breakdown.values())
-        cand = [(v["ms_per_step"], k) for k, v in breakdown.items() if kernel_flops_per_step(k, args, shapes, heads)]
-        if cand:
-            t_ms, name = max(cand)
+        tj_all = {}
+        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        if os.path.exists(tp):              # DRAM bytes per pixel measured by ncu on the level-3 launches
+            tj_all = json.load(open(tp))
+        px_step = sum(hd * h * w for hd, (h, w) in zip(heads, shapes)) * T            # pixel.stage units of the attention kernels
+        px_all = sum(h * w for (h, w) in shapes) * T                                  # pixels of the level fusion
+
+        def kernel_roofline(name):
+            """Roofline entry of one kernel: its own bound, algorithmic work of all its launches in a step / their time."""
+            t_ms = breakdown[name]["ms_per_step"]
+            nl = breakdown[name]["launches_per_step"]
             fl = kernel_flops_per_step(name, args, shapes, heads)
-            ach = fl / (t_ms * 1e-3) / 1e12
+            if fl:                          # tensor-bound kernels of the attention contraction
+                ach = fl / (t_ms * 1e-3) / 1e12
+                peak = pk["bf16_tflops_sustained"]
+                tj = tj_all.get(name)
+                traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pixels"] * px_step / nl if tj else None
+                return dict(kernel=name, bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
+                            executed_mma_tflops=3 * ach, executed_frac=3 * ach / peak,      # fp16 hi/lo split: 3 MMA products per algorithmic product
+                            traffic=traffic, traffic_note="DRAM bytes per launch (ncu level-3 capture scaled by pixels)",
+                            peak_source=f"{pk['source']} bf16 sustained (kernel timed inside the step)",
+                            algorithmic_flops_per_step=fl, ms_per_step=t_ms, launches_per_step=nl)
+            if name == "fuse_tc":           # level fusion: read 4*128 B + write 4*256 B (fp32 feature) + 4 fp16 planes (2 KB) per pixel
+                by = px_all * (4 * 128 + 4 * 256 + 4 * 2 * 256)
+                ach = by / (t_ms * 1e-3) / 1e9
+                tj = tj_all.get("fuse_tc_main")
+                traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pixels"] * px_all / nl if tj else None
+                return dict(kernel=name, bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
+                            traffic=traffic, traffic_note="DRAM bytes per launch (ncu capture of the level-3 main pass scaled by pixels; coarse passes excluded)",
+                            peak_source=pk["source"] + " copy bandwidth", algorithmic_bytes_per_step=by, ms_per_step=t_ms, launches_per_step=nl)
+            return None
+
+        per_kernel = {k: kernel_roofline(k) for k in breakdown if k in ("stats_tc", "attn_tc", "fuse_tc", "proj_rstd(k)", "proj_rstd(v)", "slot_attn_fp32")}
+        per_kernel = {k: v for k, v in per_kernel.items() if v}
+        if per_kernel:
+            # the dominant kernel = the one with the largest share of the step; the others are listed under "kernels"
+            name = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
+            roofline = dict(per_kernel[name])
+            roofline["kernels"] = per_kernel
             peak = pk["bf16_tflops_sustained"]
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-            if os.path.exists(tp):          # DRAM bytes per pixel measured by ncu on the level-3 launch, scaled to the step's pixels
-                tj = json.load(open(tp)).get(name)
-                if tj:
-                    px_step = sum(hd * h * w for hd, (h, w) in zip(heads, shapes)) * T
-                    traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pixels"] * px_step / breakdown[name]["launches_per_step"]
-            roofline = dict(kernel=name, bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
-                            executed_mma_tflops=3 * ach if name.endswith("_tc") else None, executed_frac=(3 * ach / peak) if name.endswith("_tc") else None,   # fp16 hi/lo split: 3 MMA products per algorithmic product
-                            traffic=traffic, traffic_note="DRAM bytes per launch (ncu, level-3 capture scaled by pixels); the kernel's only large operand is the fp16 plane set it reads (4 x 512 B/pixel)", peak_source=f"{pk['source']} bf16 sustained (kernel timed inside the step)",
-                            algorithmic_flops_per_step=fl, ms_per_step=t_ms, share_of_step=t_ms / total,
-                            launches_per_step=breakdown[name]["launches_per_step"])
             # the whole attention contraction (all its kernels) against the same peak
             names = [k for k in breakdown if k in ("proj_rstd(k)", "proj_rstd(v)", "slot_attn_fp32", "stats_tc", "attn_tc")]
             tt = sum(breakdown[k]["ms_per_step"] for k in names)
             roofline["attention_contraction"] = dict(kernels=names, algorithmic_tflops=per_frame_flops * T / (tt * 1e-3) / 1e12,
-                                                     ms_per_step=tt, frac_of_peak=per_frame_flops * T / (tt * 1e-3) / 1e12 / peak)
+                                                     ms_per_step=tt, frac_of_peak=per_frame_flops * T / (tt * 1e-3) / 1e12 / peak,
+                                                     executed_frac_of_peak=3 * per_frame_flops * T / (tt * 1e-3) / 1e12 / peak)
         # HBM-bound stages: mask logits (read 4*C*P3 + write 4*N*P3) -- SURVEY.md 8d
         P3 = shapes[3][0] * shapes[3][1]
         ml = [k for k in breakdown if k in ("mask_prep", "feat_rnorm", "mask_logits_tc")]
@@ -421,6 +444,8 @@ def main():
             ktot = sum(v["ms_per_step"] for k, v in breakdown.items() if k != "(host gap)")
             roofline["share_of_step"] = roofline["ms_per_step"] / ktot
             roofline["share_of_single_clip_wall_step"] = roofline["ms_per_step"] / step_ms
+            for v in roofline["kernels"].values():
+                v["share_of_step"] = v["ms_per_step"] / ktot
             hb = {"peak_gbs": pk["hbm_gbs"], "peak_source": pk["source"] + " copy bandwidth"}
             if "mask_tc" in breakdown:      # mask-logit projection: read 4*C*P3 (as 2 fp16 hi/lo planes = same bytes) + write 4*N*P3
                 by = 4 * 256 * P3 + 4 * N * P3
