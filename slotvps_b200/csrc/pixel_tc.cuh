@@ -473,7 +473,7 @@ inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const flo
   const int tiles_per_frame = ceil_div(P, stats::TILE_M);
   const int n_tiles = T * tiles_per_frame;
   static const int use_pairs = getenv("SLOTVPS_STATS_PAIRS") ? atoi(getenv("SLOTVPS_STATS_PAIRS")) : 1;   // CTA pairs by default
-  if (use_pairs && n_tiles >= 2) {
+  if (use_pairs && n_tiles >= 2 && max_ctas >= 2) {
     CUtensorMap mw2;
     SV_TRY(tc::make_tmap_h16_sw128(&mw2, ops.wplanes, (uint64_t)4 * C, C, 128));
     static bool attr2_done = false;
