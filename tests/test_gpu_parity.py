@@ -649,3 +649,25 @@ def test_slot_groups_whole_clip(dev, N):
     ref = O.mask_logits(b["feats"][1][3][0].double().cpu(), b["emb"][1][-1, 0].double().cpu(), {k: v.double() for k, v in cap.items()})
     assert b["pred_masks"].shape == (N, H // 4, W // 4)
     assert rel(b["pred_masks"], ref) < 1e-4
+
+
+def test_explicit_pos_tensors_match_sine_mode(dev):
+    """L1 integration passes the reference's PositionEmbeddingSine tensors (pos_mode 1): the level-fusion epilogue then
+    reads them from HBM instead of generating the embedding; results must agree with pos="sine" and with the oracle."""
+    shapes = [(8, 16), (16, 32), (32, 64), (64, 128)]
+    sd = synthetic.make_head_state_dict(9)
+    cap = synthetic.make_capsule_params(9, 100)
+    feats = synthetic.make_features(0, 0, T=2, video=9, frame=0, shapes=shapes)
+    q = cap["init_mask_query.weight"]
+    head = _mk_head(dev, sd, 0)
+    f_dev = [[f.to(dev) for f in fr] for fr in feats]
+    cl_s, em_s, fu_s = head(f_dev, [q.to(dev)] * 2, None, pos="sine")
+    em_s = [e.clone() for e in em_s]
+    pos = [[O.sine_position_embedding(*s).to(dev) for s in shapes] for _ in range(2)]
+    cl_t, em_t, fu_t = head(f_dev, [q.to(dev)] * 2, None, pos=pos)
+    assert rel(em_t[1][0], em_s[1][0]) < 2e-5 and rel(fu_t[1][3], fu_s[1][3]) < 1e-6
+    P64 = {k: v.double() for k, v in sd.items()}
+    pos64 = [[O.sine_position_embedding(*s, dtype=torch.float64) for s in shapes] for _ in range(2)]
+    _, re_, _ = O.head_forward(P64, [[f.double() for f in fr] for fr in feats], [q.double()] * 2, pos64)
+    for s in range(7):
+        assert rel(em_t[1][s], re_[1][s]) < max(1e-5 * 3.5 ** s * 3, 2e-5), (s, rel(em_t[1][s], re_[1][s]))
