@@ -655,7 +655,7 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
         const int Pp = d->h[l - 1] * d->w[l - 1];
         const long rp = (long)T * Pp;
         prm.rows = (int)rp; prm.P = Pp; prm.w = d->w[l - 1]; prm.h = d->h[l - 1]; prm.ksub = 4; prm.a_lo_row = (int)rp;
-        prm.y_out = w.ftc.y;
+        prm.y_out = w.ftc.y; prm.a_split = 1;
         SV_TRY(fuse_tc_launch(tcp.planes, 2 * rp, (int)rp, C, pr.ftc.wa, prm, s, side_ctas));
         memset(&prm, 0, sizeof(prm));
       }

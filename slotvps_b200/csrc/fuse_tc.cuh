@@ -31,6 +31,7 @@ struct Params {
   int P, w;            // pixels per frame and width of THIS resolution
   int ksub;            // K / 64
   int a_lo_row;        // row offset of the lo plane in tmap_a (hi plane at row 0)
+  int a_split;         // A operand stored as 64-channel sub-planes [2][4][a_lo_row][64] (the level planes) instead of [2][rows][K]
   const float* bias;   // [256] or null (coarse)
   // coarse output
   float* y_out;        // [rows][256] or null
@@ -150,8 +151,13 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc::mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
           tc::mbar_expect_tx(&full[s], STAGE_BYTES);
-          tc::tma_load_2d(st, &tmap_a, ks * 64, row, &full[s]);
-          tc::tma_load_2d(st + A_BYTES, &tmap_a, ks * 64, prm.a_lo_row + row, &full[s]);
+          if (prm.a_split) {
+            tc::tma_load_2d(st, &tmap_a, 0, ks * prm.a_lo_row + row, &full[s]);
+            tc::tma_load_2d(st + A_BYTES, &tmap_a, 0, (4 + ks) * prm.a_lo_row + row, &full[s]);
+          } else {
+            tc::tma_load_2d(st, &tmap_a, ks * 64, row, &full[s]);
+            tc::tma_load_2d(st + A_BYTES, &tmap_a, ks * 64, prm.a_lo_row + row, &full[s]);
+          }
           tc::tma_load_2d(st + 2 * A_BYTES, &tmap_w, ks * 64, 0, &full[s]);
           tc::tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmap_w, ks * 64, C, &full[s]);
         }
@@ -304,7 +310,8 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           };
           auto store = [&](int plane, const uint32_t* w) {
-            __half* dst = prm.planes + ((long)plane * prm.plane_stride + row) * C + j * 32;
+            // sub-plane ks = j / 2 of this plane, [rows][64]: the two chunks of a 64-channel group complete one 128-byte row
+            __half* dst = prm.planes + (((long)plane * 4 + (j >> 1)) * prm.plane_stride + row) * 64 + (j & 1) * 32;
             tc::st_global_v8(dst, w); tc::st_global_v8(dst + 16, w + 8);
           };
           pack(v); store(0, hi); store(1, lo);
@@ -343,7 +350,8 @@ struct FuseTcWorkspace {
 inline int fuse_tc_launch(const __half* a_planes, long a_rows_total, int a_lo_row, int K, const __half* w_planes, const fuse::Params& prm,
                           cudaStream_t s, int max_ctas = 148) {
   CUtensorMap ma, mw;
-  SV_TRY(tc::make_tmap_h16_sw128(&ma, a_planes, (uint64_t)a_rows_total, (uint64_t)K, fuse::TILE_M));
+  if (prm.a_split) SV_TRY(tc::make_tmap_h16_sw128(&ma, a_planes, (uint64_t)4 * a_rows_total, 64, fuse::TILE_M));
+  else SV_TRY(tc::make_tmap_h16_sw128(&ma, a_planes, (uint64_t)a_rows_total, (uint64_t)K, fuse::TILE_M));
   SV_TRY(tc::make_tmap_h16_sw128(&mw, w_planes, (uint64_t)2 * C, (uint64_t)K, C));
   static bool attr_done = false;
   if (!attr_done) {

@@ -70,7 +70,7 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const int s = it % NSLOT;
             tc::mbar_wait(&empty[s], ((it / NSLOT) & 1) ^ 1);
             tc::mbar_expect_tx(&full[s], SLOT_BYTES);
-            tc::tma_load_2d(smem + s * SLOT_BYTES, &tmap_x, ks * 64, pl * lo_row + row, &full[s]);
+            tc::tma_load_2d(smem + s * SLOT_BYTES, &tmap_x, 0, (pl * 4 + ks) * lo_row + row, &full[s]);
           }
       }
     }
@@ -140,7 +140,7 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 inline int mask_tc_launch(const __half* planes, long plane_rows_total, long lo_row, long row0, const __half* eplanes, const float* dn,
                           const float* rn, const float* aff, float* out, int N, int P, cudaStream_t s) {
   CUtensorMap mx, me;
-  SV_TRY(tc::make_tmap_h16_sw128(&mx, planes, (uint64_t)plane_rows_total, C, mask::TILE_M));
+  SV_TRY(tc::make_tmap_h16_sw128(&mx, planes, (uint64_t)4 * plane_rows_total, 64, mask::TILE_M));      // ks-major sub-planes [2][4][rows][64]
   SV_TRY(tc::make_tmap_h16_sw128(&me, eplanes, (uint64_t)2 * mask::NROW, C, mask::NROW));
   static bool attr_done = false;
   if (!attr_done) {

@@ -21,7 +21,9 @@ struct TcStageOperands {
   __half* wplanes = nullptr;     // [4][256][256]: Wk_c hi, Wk_c lo, Wv_c hi, Wv_c lo (row-major [out][in])
 };
 struct TcWorkspace {
-  __half* planes = nullptr;      // [4][T*Pmax][256]: x hi, x lo, (x+pos) hi, (x+pos) lo
+  // operand planes x hi, x lo, (x+pos) hi, (x+pos) lo, each stored as four 64-channel sub-planes [4 planes][4 ks][rows][64]:
+  // a [128 px][64 ch] TMA box is then ONE contiguous 16 KB block (whole DRAM pages) instead of 128 rows at a 512-byte pitch
+  __half* planes = nullptr;
   __half* planes_alt = nullptr;  // second plane set: levels alternate so the next level's fusion can overlap this level's stages
   float *ytab = nullptr, *xtab = nullptr;  // separable sine tables [128][h], [128][w] of the CURRENT level
   float *ytab_l[SLOTVPS_MAX_LEVELS] = {nullptr}, *xtab_l[SLOTVPS_MAX_LEVELS] = {nullptr};   // one pair per level (the side stream runs ahead)
@@ -118,12 +120,12 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
   }
   __syncthreads();
   __half2* out = reinterpret_cast<__half2*>(planes);
-  const long plane_stride2 = plane_rows * (C / 2);
+  const long plane_stride2 = 4 * plane_rows * 32;                    // one plane = 4 sub-planes of [rows][64]
 #pragma unroll 4
   for (int i = 0; i < 16; ++i) {
     int idx = tid + i * 256, pp = idx >> 7, cp = idx & 127;
     if (p0 + pp >= P) continue;
-    long o = ((long)t * P + p0 + pp) * (C / 2) + cp;
+    const long o = ((long)(cp >> 5) * plane_rows + (long)t * P + p0 + pp) * 32 + (cp & 31);      // sub-plane ks = cp / 32, 32 half2 per row
     __half h0, l0, h1, l1;
     split_bf16(xs[(2 * cp) * 33 + pp], h0, l0); split_bf16(xs[(2 * cp + 1) * 33 + pp], h1, l1);
     out[o] = __halves2half2(h0, h1);
@@ -196,8 +198,8 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             tc::mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
             uint8_t* st = smem + s * STAGE_BYTES;
             tc::mbar_expect_tx(&full[s], STAGE_BYTES);
-            tc::tma_load_2d(st, &tmap_x, ks * KSUB, aq * plane_rows + row, &full[s]);
-            tc::tma_load_2d(st + A_BYTES, &tmap_x, ks * KSUB, (aq + 1) * plane_rows + row, &full[s]);
+            tc::tma_load_2d(st, &tmap_x, 0, (aq * 4 + ks) * plane_rows + row, &full[s]);
+            tc::tma_load_2d(st + A_BYTES, &tmap_x, 0, ((aq + 1) * 4 + ks) * plane_rows + row, &full[s]);
             tc::tma_load_2d(st + 2 * A_BYTES, &tmap_w, ks * KSUB, bq * C, &full[s]);
             tc::tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmap_w, ks * KSUB, (bq + 1) * C, &full[s]);
           }
@@ -344,8 +346,8 @@ stats_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             tc::mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
             uint8_t* st = smem + s * STAGE_BYTES;
             if (leader) tc::mbar_expect_tx(&full[s], 2 * STAGE_BYTES);           // bytes of both CTAs land on this barrier
-            tc::tma_load_2d_pair(st, &tmap_x, ks * KSUB, aq * plane_rows + row, &full[s]);
-            tc::tma_load_2d_pair(st + A_BYTES, &tmap_x, ks * KSUB, (aq + 1) * plane_rows + row, &full[s]);
+            tc::tma_load_2d_pair(st, &tmap_x, 0, (aq * 4 + ks) * plane_rows + row, &full[s]);
+            tc::tma_load_2d_pair(st + A_BYTES, &tmap_x, 0, ((aq + 1) * 4 + ks) * plane_rows + row, &full[s]);
             tc::tma_load_2d_pair(st + 2 * A_BYTES, &tmap_w, ks * KSUB, bq * C + (int)rank * 128, &full[s]);
             tc::tma_load_2d_pair(st + 2 * A_BYTES + B_BYTES, &tmap_w, ks * KSUB, (bq + 1) * C + (int)rank * 128, &full[s]);
           }
@@ -463,7 +465,7 @@ inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const flo
   const long rows = (long)T * P;
   // only the planes that were written are inside the tensor map: a tail tile's rows past the last plane are then
   // zero-filled by TMA instead of reading stale memory (NaN bit patterns there corrupt the MMA even against zero weights)
-  SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)(ps.enabled ? 2 : 4) * rows, C, stats::TILE_M));
+  SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)(ps.enabled ? 2 : 4) * 4 * rows, 64, stats::TILE_M));
   SV_TRY(tc::make_tmap_h16_sw128(&mw, ops.wplanes, (uint64_t)4 * C, C, C));
   static bool attr_done = false;
   if (!attr_done) {
@@ -621,7 +623,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int s = it % NSLOT;
       tc::mbar_wait(&empty[s], ((it / NSLOT) & 1) ^ 1);
       tc::mbar_expect_tx(&full[s], SLOT_BYTES);
-      tc::tma_load_2d(smem + s * SLOT_BYTES, &tmap_x, c0, plane * plane_rows + row, &full[s]);
+      tc::tma_load_2d(smem + s * SLOT_BYTES, &tmap_x, 0, (plane * 4 + c0 / 64) * plane_rows + row, &full[s]);
       ++it;
     };
     auto job_s = [&](int i) {
@@ -640,7 +642,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       for (int ln = lane - 1; ln < 4 * TILE_M * 4; ln += 31) {
         const int pl = ln >> 9, r = (ln >> 2) & 127, seg = ln & 3;
         if (row + r < max_row) {
-          const __half* ptr = planes + ((long)pl * plane_rows + row + r) * C + seg * 64;
+          const __half* ptr = planes + (((long)pl * 4 + seg) * plane_rows + row + r) * 64;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
         }
       }
@@ -934,7 +936,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int s = NS + itZ % NZ;
       tc::mbar_wait(&empty[s], ((itZ / NZ) & 1) ^ 1);
       tc::mbar_expect_tx(&full[s], SLOT_BYTES);
-      tc::tma_load_2d(smem + s * SLOT_BYTES, &tmap_x, c0, plane * plane_rows + row, &full[s]);
+      tc::tma_load_2d(smem + s * SLOT_BYTES, &tmap_x, 0, (plane * 4 + c0 / 64) * plane_rows + row, &full[s]);
       ++itZ;
     };
     // S operand slots (ring [0, NS)): consumed by the pair MMA the leader issues, so both CTAs' bytes are credited to
@@ -943,7 +945,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int s = itS % NS;
       tc::mbar_wait(&empty[s], ((itS / NS) & 1) ^ 1);
       if (leader) tc::mbar_expect_tx(&full[s], 2 * SLOT_BYTES);
-      tc::tma_load_2d_pair(smem + s * SLOT_BYTES, &tmap_x, c0, plane * plane_rows + row, &full[s]);
+      tc::tma_load_2d_pair(smem + s * SLOT_BYTES, &tmap_x, 0, (plane * 4 + c0 / 64) * plane_rows + row, &full[s]);
       ++itS;
     };
     auto job_s = [&](int i) {
@@ -962,7 +964,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       for (int ln = lane - 1; ln < 4 * TILE_M * 4; ln += 31) {
         const int pl = ln >> 9, r = (ln >> 2) & 127, seg = ln & 3;
         if (row + r < max_row) {
-          const __half* ptr = planes + ((long)pl * plane_rows + row + r) * C + seg * 64;
+          const __half* ptr = planes + (((long)pl * 4 + seg) * plane_rows + row + r) * 64;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
         }
       }
@@ -1219,7 +1221,7 @@ inline int tc_attention(const TcWorkspace& ws, __half* gplanes, const float* G, 
                         int* chunks_out, cudaStream_t s, const PosSep& ps = PosSep()) {
   CUtensorMap mx, mg;
   const long rows = (long)T * P;
-  SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)(ps.enabled ? 2 : 4) * rows, C, attn::TILE_M));
+  SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)(ps.enabled ? 2 : 4) * 4 * rows, 64, attn::TILE_M));
   const int chunks = attn::chunks_for(P, T);
   *chunks_out = chunks;
   const int groups = ceil_div(N, attn::NROW);
