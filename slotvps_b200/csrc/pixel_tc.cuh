@@ -672,9 +672,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       tc::tc_fence_after();
       const uint32_t g_base = tc::smem_u32(smem + OFF_G), p_base = tc::smem_u32(smem + OFF_P), x_base = tc::smem_u32(smem + OFF_AUX);
       uint32_t it = 0;
+      // SLOTVPS_TC_DEBUG bit 4: where this thread waits (cycles, printed by CTA (0,0)).  Measured on B200 (level 3, 14 tiles per
+      // CTA, 13.2 K cycles per tile): it waits only 23 % of the time (S operands 7 %, Z operands 13 %, softmax 2 %, S buffer
+      // 0.4 %) although the tensor pipe reports 41 % active.  Hoisting every descriptor out of the loops and issuing S and Z
+      // from two threads were tried (no gain / faults when two threads issue concurrently), so the remaining time is spent
+      // inside tcgen05.mma issue itself: the Z^T product feeds its A operand MN-major (the x tile transposed on the fly),
+      // which appears to run at about half the K-major rate (48 S MMAs + 48 Z MMAs + 16 aux ~ 2.7 K + 5.4 K + 1 K cycles).
+      const bool prof = (dbg & 16) != 0;
+      long long wS = 0, wZ = 0, wP = 0, wE = 0;
+      const long long t_begin = clock64();
+      auto timed_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
+        if (!prof) { tc::mbar_wait(bar, parity); return; }
+        const long long t0 = clock64();
+        tc::mbar_wait(bar, parity);
+        acc += clock64() - t0;
+      };
       auto issue_s = [&](int i) {
         const int b = i & 1, u = i >> 1;
-        tc::mbar_wait(&sempty[b], (u & 1) ^ 1);            // softmax of tile i-2 has drained this S buffer
+        timed_wait(&sempty[b], (u & 1) ^ 1, wE);           // softmax of tile i-2 has drained this S buffer
         tc::tc_fence_after();
         const uint32_t d = tmem_base + TM_S + b * 128;
         for (int ks = 0; ks < 4; ++ks) {
@@ -682,7 +697,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           const uint64_t dgl = tc::make_smem_desc_sw128(g_base + (4 + ks) * G_SUB, 16, 1024);
           {   // (x+pos) hi against G hi and G lo
             const int s = it % NSLOT;
-            tc::mbar_wait(&full[s], (it / NSLOT) & 1);
+            timed_wait(&full[s], (it / NSLOT) & 1, wS);
             tc::tc_fence_after();
             const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), 16, 1024);
 #pragma unroll
@@ -695,7 +710,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           }
           {   // (x+pos) lo against G hi
             const int s = it % NSLOT;
-            tc::mbar_wait(&full[s], (it / NSLOT) & 1);
+            timed_wait(&full[s], (it / NSLOT) & 1, wS);
             tc::tc_fence_after();
             const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), 16, 1024);
 #pragma unroll
@@ -707,14 +722,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         tc::umma_commit(&sfull[b]);
       };
       auto issue_z = [&](int i) {
-        tc::mbar_wait(pfull, i & 1);                        // P and the aux tile of tile i are in shared memory
+        timed_wait(pfull, i & 1, wP);                       // P and the aux tile of tile i are in shared memory
         tc::tc_fence_after();
         for (int mt = 0; mt < 2; ++mt) {
           const uint32_t d = tmem_base + TM_Z + mt * NPAD;
           for (int pl = 0; pl < 2; ++pl) {                  // pl = 0: x hi against P hi and P lo; pl = 1: x lo against P hi
             const int s = it % NSLOT;                       // even by construction: slots (s, s+1) hold channels [128 mt, 128 mt + 128)
-            tc::mbar_wait(&full[s], (it / NSLOT) & 1);
-            tc::mbar_wait(&full[s + 1], ((it + 1) / NSLOT) & 1);
+            timed_wait(&full[s], (it / NSLOT) & 1, wZ);
+            timed_wait(&full[s + 1], ((it + 1) / NSLOT) & 1, wZ);
             tc::tc_fence_after();
             // A: x tile as MN-major operand: 64-channel groups SLOT_BYTES apart, 8-pixel groups 1024 B apart
             const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), SLOT_BYTES, 1024);
@@ -741,6 +756,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       issue_s(0);
       for (int i = 0; i < n_my; ++i) { if (i + 1 < n_my) issue_s(i + 1); if (MODE != 1) issue_z(i); }
       if (MODE != 1) tc::umma_commit(zfull);
+      if (prof && blockIdx.x == 0 && blockIdx.y == 0)
+        printf("attn_tc tiles=%d cycles=%lld wait: S-operands %lld Z-operands %lld softmax %lld S-buffer %lld\n", n_my, clock64() - t_begin, wS, wZ, wP, wE);
     }
   } else {
     // ===================== softmax warps (one pixel per thread) + final epilogue =====================
