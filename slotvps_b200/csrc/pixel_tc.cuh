@@ -673,13 +673,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const uint32_t g_base = tc::smem_u32(smem + OFF_G), p_base = tc::smem_u32(smem + OFF_P), x_base = tc::smem_u32(smem + OFF_AUX);
       uint32_t it = 0;
       // SLOTVPS_TC_DEBUG bit 4: where this thread waits (cycles, printed by CTA (0,0)).  Measured on B200 (level 3, 14 tiles per
-      // CTA, 13.2 K cycles per tile): it waits only 23 % of the time (S operands 7 %, Z operands 13 %, softmax 2 %, S buffer
-      // 0.4 %) although the tensor pipe reports 41 % active.  Hoisting every descriptor out of the loops and issuing S and Z
-      // from two threads were tried (no gain / faults when two threads issue concurrently), so the remaining time is spent
-      // inside tcgen05.mma issue itself: the Z^T product feeds its A operand MN-major (the x tile transposed on the fly),
-      // which appears to run at about half the K-major rate (48 S MMAs + 48 Z MMAs + 16 aux ~ 2.7 K + 5.4 K + 1 K cycles).
+      // CTA, ~13.3 K cycles per tile): barrier waits 14-23 % (S operands 4-7 %, Z operands 8-13 %, softmax 1-2 %, S buffer
+      // 0.4 %), tcgen05.commit 8 %; the rest is MMA issue.  Hoisting every descriptor out of the loops changed nothing, issuing
+      // S and Z from two threads faulted, and dropping the Z products (timing experiment) shortened the kernel by only 6 %:
+      // the issuing thread and the softmax warps run at about the same per-tile rate, so both have to get faster together.
       const bool prof = (dbg & 16) != 0;
-      long long wS = 0, wZ = 0, wP = 0, wE = 0;
+      long long wS = 0, wZ = 0, wP = 0, wE = 0, tC = 0;
+      auto timed_commit = [&](uint64_t* bar) {
+        if (!prof) { tc::umma_commit(bar); return; }
+        const long long t0 = clock64();
+        tc::umma_commit(bar);
+        tC += clock64() - t0;
+      };
       const long long t_begin = clock64();
       auto timed_wait = [&](uint64_t* bar, uint32_t parity, long long& acc) {
         if (!prof) { tc::mbar_wait(bar, parity); return; }
@@ -705,7 +710,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               tc::umma_bf16(d, da + 2 * k, dgh + 2 * k, IDESC_S, (ks | k) != 0);
               tc::umma_bf16(d, da + 2 * k, dgl + 2 * k, IDESC_S, 1);
             }
-            tc::umma_commit(&empty[s]);
+            timed_commit(&empty[s]);
             ++it;
           }
           {   // (x+pos) lo against G hi
@@ -715,11 +720,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc::umma_bf16(d, da + 2 * k, dgh + 2 * k, IDESC_S, 1);
-            tc::umma_commit(&empty[s]);
+            timed_commit(&empty[s]);
             ++it;
           }
         }
-        tc::umma_commit(&sfull[b]);
+        timed_commit(&sfull[b]);
       };
       auto issue_z = [&](int i) {
         timed_wait(pfull, i & 1, wP);                       // P and the aux tile of tile i are in shared memory
@@ -739,8 +744,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               tc::umma_bf16(d, da + (uint64_t)(k * 128), tc::make_smem_desc_sw128(p_base + poff, 16, 1024), IDESC_Z, (i | pl | k) != 0);
               if (pl == 0) tc::umma_bf16(d, da + (uint64_t)(k * 128), tc::make_smem_desc_sw128(p_base + P_PLANE + poff, 16, 1024), IDESC_Z, 1);
             }
-            tc::umma_commit(&empty[s]);
-            tc::umma_commit(&empty[s + 1]);
+            timed_commit(&empty[s]);
+            timed_commit(&empty[s + 1]);
             it += 2;
           }
         }
@@ -751,13 +756,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           tc::umma_bf16(tmem_base + TM_AUX, tc::make_smem_desc_sw128(p_base + poff, 16, 1024), dx, IDESC_AUX, (i | k) != 0);
           tc::umma_bf16(tmem_base + TM_AUX, tc::make_smem_desc_sw128(p_base + P_PLANE + poff, 16, 1024), dx, IDESC_AUX, 1);
         }
-        tc::umma_commit(pempty);                            // P may be overwritten once these retire
+        timed_commit(pempty);                            // P may be overwritten once these retire
       };
       issue_s(0);
       for (int i = 0; i < n_my; ++i) { if (i + 1 < n_my) issue_s(i + 1); if (MODE != 1) issue_z(i); }
       if (MODE != 1) tc::umma_commit(zfull);
       if (prof && blockIdx.x == 0 && blockIdx.y == 0)
-        printf("attn_tc tiles=%d cycles=%lld wait: S-operands %lld Z-operands %lld softmax %lld S-buffer %lld\n", n_my, clock64() - t_begin, wS, wZ, wP, wE);
+        printf("attn_tc tiles=%d cycles=%lld wait: S-operands %lld Z-operands %lld softmax %lld S-buffer %lld | in tcgen05.commit %lld\n", n_my, clock64() - t_begin, wS, wZ, wP, wE, tC);
     }
   } else {
     // ===================== softmax warps (one pixel per thread) + final epilogue =====================
