@@ -101,3 +101,22 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|import_module\([\"']oracle", src, flags=re.M), \
                     f"{f} imports the oracle"
+
+
+def test_next_row_mirrors_have_no_cpu_path():
+    """Tracker / id-map consumer mirrors keep the reference's names and refuse CPU tensors (no fallback)."""
+    import torch
+    import slotvps_b200 as sv
+    th = sv.B200TrackHead(**sv.TRACK_KWARGS)
+    assert sorted(k for k, _ in th.named_parameters()) == ["fcs_query.0.bias", "fcs_query.0.weight", "fcs_query.1.bias", "fcs_query.1.weight"]
+    with pytest.raises(RuntimeError):
+        th(torch.zeros(3, 256), torch.zeros(4, 256))
+    with pytest.raises(RuntimeError):
+        sv.semantic_argmax(torch.zeros(1, 19, 8, 8), (8, 8))
+    with pytest.raises(NotImplementedError):
+        sv.B200TrackHead(num_fcs_query=2, in_channels_query=128)
+    head = sv.B200DynamicMaskHead(**sv.HEAD_KWARGS)
+    head.fold_input_transform(torch.eye(128).reshape(128, 128, 1, 1), torch.zeros(128))
+    assert head._in_trans is not None and head._prepared is None
+    head.fold_input_transform(None, None)
+    assert head._in_trans is None
