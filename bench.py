@@ -1,25 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- retriever frames/sec @1024x2048 (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config clip|viper|sweep|slots]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one clip: T=2 frames of 4-level 128-ch features at
-1024x2048 -> retriever head (7 stages) -> mask logits -> panoptic fusion -> int64 id map
-(BASELINE.json configs[1]).  Frame convention: retriever frames/s = T * clips/s (the reference
-consumes T=2 frames per call and emits one panoptic frame).
+A "step" is one pass of the hot path over one clip: T frames of 4-level 128-ch features -> retriever head
+(7 stages) -> mask logits -> panoptic fusion -> id map.  Frame convention: retriever frames/s = T * clips/s (the
+reference consumes T=2 frames per call and emits one panoptic frame).
 
-* value      whole-job frames/s with the inputs already resident in HBM (device events).
-* e2e        same metric through the public API with HOST (pinned) input buffers: per step the
-             host->device copy of the clip's features and a device->host read of the id map + meta.
-* roofline   dominant contraction kernel: algorithmic FLOP / CUDA-event time of its launches.
+--config clip   (default) BASELINE configs[1]: one 1024x2048 clip, T=2, N=100, replayed K times per rank.
+--config viper  BASELINE configs[3]: VIPER-shaped 1080x1920 (padded to 1088x1920), T=4, fusion to the unpadded size.
+--config sweep  BASELINE configs[2]: V videos x F frames at 1024x2048, one clip per output frame (frame f pairs with
+                f-1, f=0 with itself: mmdet/datasets/cityscapes_vps.py:262-264), sharded by VIDEO over the ranks (a video's
+                frames stay in order on one rank, as the tracker needs), every frame's features pre-generated in HBM.
+--config slots  BASELINE configs[4]: slot count N in {50,100,200,300} x retriever iterations 1..7 on one GPU (a table).
+
+* value      whole-job frames/s with the inputs already resident in HBM (device events, median of --repeats timed regions).
+* e2e        same metric through the public API with HOST (pinned) input buffers: per step the host->device copy of the
+             clip's features and a device->host read of the id map (narrowed to uint8 on the device: ids < 256) + meta.
+* roofline   the kernel with the largest share of the step, with ITS bound; every kernel is listed under roofline.kernels.
 * cpu_baseline  the CPU oracle (port of the reference's algorithm, oracle/) on this box's host cores.
 
---impl reference times that CPU oracle arm alone (the reference's own CPU implementation cannot
-travel to the GPU box; oracle/ is its pinned restatement on the same torch CPU kernels).
-Synthetic data, random-init weights (no checkpoints/datasets offline).  Random-init heads keep no
-slot above the 0.85 score threshold, so BOTH arms feed designed class logits into the fusion stage
-(`config.fusion_logits`); everything else is computed from the features.
+--impl reference times that CPU arm alone, always at the configuration's full size (the reference's own Python
+implementation cannot travel to the GPU box; oracle/ is its pinned restatement on the same torch CPU kernels).
+Synthetic data, random-init weights (no checkpoints/datasets offline).  Random-init heads keep no slot above the 0.85
+score threshold and produce collapsed masks, so BOTH arms feed a designed (class logits, mask logits) pair with ~30 kept
+slots into the fusion stage (`config.fusion_inputs`); everything else is computed from the features.
 """
 import argparse
 import json
@@ -35,8 +41,11 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "retriever_frames_per_sec_1024x2048"
 UNIT = "frames/s"
+HEADS_DEFAULT = [1, 2, 2, 2]
+# BASELINE configs[4]: per_dh_num_heads / temporal stages for 1..7 retriever iterations
+ITER_CONFIGS = {1: ([0, 0, 0, 1], [0]), 2: ([0, 0, 1, 1], [0, 1]), 3: ([0, 1, 1, 1], [1, 2]), 4: ([1, 1, 1, 1], [2, 3]),
+                5: ([1, 1, 1, 2], [2, 3, 4]), 6: ([1, 1, 2, 2], [2, 3, 4, 5]), 7: ([1, 2, 2, 2], [3, 4, 5, 6])}
 
 
 def parse():
@@ -45,17 +54,54 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--height", type=int, default=1024)
-    ap.add_argument("--width", type=int, default=2048)
-    ap.add_argument("--frames", type=int, default=2)
+    ap.add_argument("--config", default="clip", choices=["clip", "viper", "sweep", "slots"])
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--frames", type=int, default=None)
     ap.add_argument("--slots", type=int, default=100)
+    ap.add_argument("--videos", type=int, default=50, help="--config sweep: number of videos")
+    ap.add_argument("--video-frames", type=int, default=6, help="--config sweep: frames per video")
     ap.add_argument("--kernel-path", type=int, default=0, help="0 auto (tensor-core kernels), 1 force fp32 CUDA-core")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; the median one is reported")
     ap.add_argument("--inflight", type=int, default=8, help="clips in flight per GPU (independent clips on separate streams)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config == "viper":
+        a.height, a.width, a.frames = a.height or 1080, a.width or 1920, a.frames or 4
+    else:
+        a.height, a.width, a.frames = a.height or 1024, a.width or 2048, a.frames or 2
+    return a
+
+
+def metric_name(a):
+    return f"retriever_frames_per_sec_{a.height}x{a.width}"
+
+
+def workload_string(a):
+    """Identical in both arms (the driver compares them)."""
+    if a.config == "viper":
+        return (f"r50_fpn_slotvps retriever, VIPER-shaped {a.height}x{a.width} clip (padded to /32), T={a.frames}, N={a.slots}, "
+                f"7 stages (BASELINE configs[3])")
+    if a.config == "sweep":
+        return (f"r50_fpn_slotvps retriever, Cityscapes-VPS val-shaped sweep: {a.videos} videos x {a.video_frames} frames "
+                f"{a.height}x{a.width}, one T=2 clip per frame, sharded by video (BASELINE configs[2])")
+    if a.config == "slots":
+        return f"r50_fpn_slotvps retriever, slot-count / iteration sweep at {a.height}x{a.width}, T={a.frames} (BASELINE configs[4])"
+    return f"r50_fpn_slotvps retriever, single {a.height}x{a.width} clip, T={a.frames}, N={a.slots}, 7 stages (BASELINE configs[1])"
+
+
+FUSION_CASE = dict(seed=21, n_things=15, near_dup_things=4, tiny=3)      # the case tests/test_gpu_parity.py::test_fullsize_fusion_and_properties checks
+
+
+def fusion_inputs(a, shapes):
+    from slotvps_b200 import synthetic
+    h, w = shapes[-1]
+    kw = dict(FUSION_CASE)
+    lg, pm, _ = synthetic.make_fusion_case(kw.pop("seed"), a.slots, h, w, **kw)
+    return lg, pm
 
 
 def peaks():
@@ -110,103 +156,112 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def algorithmic_flops(args):
-    """attention contraction per frame = sum_l heads_l * P_l * (4 C^2 + 4 N C)."""
-    from slotvps_b200 import synthetic
-    shapes = synthetic.level_shapes(args.height, args.width)
-    heads = [1, 2, 2, 2]
-    C, N = 256, args.slots
-    per_frame = sum(hd * h * w * (4 * C * C + 4 * N * C) for hd, (h, w) in zip(heads, shapes))
-    return per_frame, shapes, heads
-
-
-def kernel_flops_per_step(name, args, shapes, heads):
-    """Algorithmic FLOPs one step (all launches of `name`) performs; None for kernels without a model."""
-    C, N, T = 256, args.slots, args.frames
-    px = sum(hd * h * w for hd, (h, w) in zip(heads, shapes)) * T
-    table = {
-        "proj_rstd(k)": 2 * C * C * px, "proj_rstd(v)": 2 * C * C * px,      # K / V projection (LayerNorm statistics)
-        "slot_attn_fp32": 4 * N * C * px,                                    # slots.keys^T + attn^T.V
-        "stats_tc": 4 * C * C * px,                                          # both projections (their LayerNorm statistics), tcgen05
-        "attn_tc": 4 * N * C * px,                                           # slots.keys^T + softmax + attn^T.V, tcgen05
-    }
-    return table.get(name)
-
-
-def cpu_clip(args, H, W, sd, cap, fusion_logits, video):
+# CPU arm (the oracle port on the host cores): always the configuration's full size
+# ------------------------------------------------------------------------------------------------
+def run_cpu_arm(a, steps, warmup, budget_s):
+    """Time the oracle on the host cores; returns (frames/s, info).  The size is never reduced: when the budget is short
+    the number of clips is."""
     from oracle import slotvps_oracle as O            # CPU baseline leg: the one place bench.py runs oracle/
-    from slotvps_b200 import synthetic
-    feats = synthetic.make_features(H, W, T=args.frames, video=video, frame=0)
-    t0 = time.perf_counter()
-    out = O.clip_forward(sd, cap, feats, cap["init_mask_query.weight"], (H, W), fuse=False)
-    O.panoptic_fuse(fusion_logits, out["pred_masks"], (H, W))
-    return time.perf_counter() - t0
-
-
-def run_cpu_arm(args, steps, warmup, budget_s):
-    """Time the oracle on the host cores over a bounded sample; returns (frames/s @1024x2048-equivalent, info)."""
     from slotvps_b200 import synthetic
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synthetic.make_head_state_dict(0)
-    cap = synthetic.make_capsule_params(0, args.slots)
-    lg, _, _ = synthetic.make_fusion_case(0, args.slots, 8, 8)
-    full_px = args.height * args.width
-    est_full = 11.0 * full_px / (1024 * 2048) * (8.0 / max(1, os.cpu_count() or 1)) ** 0.5   # survey probe: ~11 s/clip on 8 vCPU
-    H, W = args.height, args.width
-    while (steps + warmup) * est_full * (H * W / full_px) > budget_s and H > 128:
-        H, W = H // 2, W // 2
-    times = []
-    for i in range(warmup + steps):
-        dt = cpu_clip(args, H, W, sd, cap, lg, video=100 + i)
-        if i >= warmup:
-            times.append(dt)
+    cap = synthetic.make_capsule_params(0, a.slots)
+    shapes = synthetic.level_shapes(a.height, a.width)
+    lg, pm = fusion_inputs(a, shapes)
+    size = (a.height, a.width)
+
+    def clip(video):
+        feats = synthetic.make_features(a.height, a.width, T=a.frames, video=video, frame=0)
+        t0 = time.perf_counter()
+        O.clip_forward(sd, cap, feats, cap["init_mask_query.weight"], size, fuse=False)      # head + mask logits
+        O.panoptic_fuse(lg, pm, size)                                                        # fusion on the designed pair
+        return time.perf_counter() - t0
+    t_begin = time.perf_counter()
+    times, done_w = [], 0
+    for i in range(warmup):
+        clip(100 + i)
+        done_w += 1
+        if time.perf_counter() - t_begin > 0.3 * budget_s:
+            break
+    for i in range(steps):
+        times.append(clip(200 + i))
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 1:
+            break
     t = statistics.median(times)
-    scale = (H * W) / full_px
-    fps = args.frames / t * scale
-    return fps, dict(kind="port", cores=torch.get_num_threads(),
-                     sample=f"{steps} clip(s) of {H}x{W} T={args.frames} (head+mask logits+fusion, median, {warmup} warm-up); "
-                            f"frames/s scaled by pixel ratio {scale:g} to {args.height}x{args.width}",
-                     sec_per_sample_clip=t), t * (steps + warmup)
+    fps = a.frames / t
+    return fps, dict(kind="port", cores=torch.get_num_threads(), sec_per_clip=t, clips_timed=len(times),
+                     sample=f"{len(times)} clip(s) of {a.height}x{a.width} T={a.frames} at full size (head + mask logits + fusion of the "
+                            f"designed pair; median, {done_w} warm-up); torch CPU kernels on {torch.get_num_threads()} threads")
 
 
 def bind_to_gpu_numa_node(local):
     """Pin this rank's host threads (and, by first touch, its pinned staging buffers) to the NUMA node its GPU hangs
     off, so that N ranks streaming features over PCIe do not all pull from one socket's memory."""
+    info = {}
     try:
         p = torch.cuda.get_device_properties(local)
-        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        bdf = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        info["bdf"] = bdf
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info["node"] = node
         if node < 0:
-            return None
+            info["reason"] = "sysfs reports numa_node = -1 (no NUMA information for this PCI device on this host)"
+            return info
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
         cpus &= os.sched_getaffinity(0)
         if not cpus:
-            return None
+            info["reason"] = "no CPU of that node in this process's affinity mask"
+            return info
         os.sched_setaffinity(0, cpus)
-        return dict(node=node, cpus=len(cpus))
-    except Exception:
-        return None
+        info["cpus"] = len(cpus)
+        return info
+    except Exception as e:
+        info["reason"] = f"{type(e).__name__}: {e}"
+        return info
+
+
+# ------------------------------------------------------------------------------------------------
+# roofline models (SURVEY.md 8d)
+# ------------------------------------------------------------------------------------------------
+def kernel_models(a, shapes, heads, kept):
+    """name -> dict(bound, work per step, unit).  FLOPs / bytes are ALGORITHMIC (reference fp32 layouts)."""
+    C, N, T = 256, a.slots, a.frames
+    px_stage = sum(hd * h * w for hd, (h, w) in zip(heads, shapes)) * T          # pixel.stage units of the attention kernels
+    P = [h * w for (h, w) in shapes]
+    P3 = P[-1]
+    # level fusion on reference-layout bytes: read the 128-ch fp32 input, read the previous level's 256-ch output once
+    # (amortised: P_{l-1} = P_l / 4), write the 256-ch fp32 output
+    fuse_bytes = T * sum(P[l] * (4 * 128 + 4 * 256) + (P[l - 1] * 4 * 256 if l > 0 else 0) for l in range(len(P)))
+    m = {
+        "proj_rstd(k)": ("tensor", 2 * C * C * px_stage), "proj_rstd(v)": ("tensor", 2 * C * C * px_stage),
+        "slot_attn_fp32": ("tensor", 4 * N * C * px_stage),
+        "stats_tc": ("tensor", 4 * C * C * px_stage),                         # both projections (their LayerNorm statistics)
+        "attn_tc": ("tensor", 4 * N * C * px_stage),                          # slots.keys^T + softmax + attn^T.V
+        "fuse_tc": ("hbm", fuse_bytes),
+        "mask_tc": ("hbm", 4 * C * P3 + 4 * N * P3),                          # read the feature once, write pred_masks
+    }
+    return m
 
 
 def main():
-    args = parse()
+    a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    METRIC = metric_name(a)
 
-    if args.impl == "reference":
+    if a.impl == "reference":
         if rank != 0:
             return 0
-        budget = 150.0
-        fps, info, _ = run_cpu_arm(args, args.steps, args.warmup, budget)
-        line = dict(metric=METRIC, value=fps, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=1e3 * info["sec_per_sample_clip"], higher_is_better=True, scaling="weak", vs_baseline=None,
+        fps, info = run_cpu_arm(a, a.steps, a.warmup, 150.0)
+        line = dict(metric=METRIC, value=fps, unit=UNIT, impl="reference", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=1e3 * info["sec_per_clip"], higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32", data="synthetic",
-                    config=dict(workload=f"r50_fpn_slotvps retriever, single {args.height}x{args.width} clip, T={args.frames}, N={args.slots} (BASELINE configs[1])",
-                                fusion_logits="designed (random-init heads keep no slot)"),
+                    config=dict(workload=workload_string(a), fusion_inputs="designed class + mask logits (random-init heads keep no slot)",
+                                clips_timed=info["clips_timed"]),
                     cpu_baseline=dict(value=fps, unit=UNIT, **{k: info[k] for k in ("cores", "kind", "sample")}),
                     e2e=dict(value=fps, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
@@ -227,65 +282,111 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    T, N, H, W = args.frames, args.slots, args.height, args.width
+    if a.config == "slots":
+        return run_slot_sweep(a, dev, rank, world, dist)
+
+    T, N, H, W = a.frames, a.slots, a.height, a.width
+    shapes = synthetic.level_shapes(H, W)
     sd = synthetic.make_head_state_dict(0)
     cap = synthetic.make_capsule_params(0, N)
-    fusion_logits = synthetic.make_fusion_case(0, N, 8, 8)[0].to(dev)
-    K, Wm, M = args.steps, args.warmup, max(1, args.inflight)
+    lg, pm_designed = fusion_inputs(a, shapes)
+    fusion_logits, fusion_masks = lg.to(dev), pm_designed.to(dev)
+    K, Wm, M = a.steps, a.warmup, max(1, a.inflight)
     if M >= 4:
         # throughput mode: with several clips in flight the side-stream producers of one clip co-run with the other
         # clips' kernels, and narrower grids interleave better (measured 64 > 112 > 148); the library default (112)
         # is the single-clip latency optimum.
         os.environ.setdefault("SLOTVPS_SIDE_CTAS", "64")
         os.environ.setdefault("SLOTVPS_MAIN_CTAS", "64")
-    pan = torch.empty((K, H, W), dtype=torch.int64, device=dev) if world > 1 else None
     L = sv.lib()
+    wire_dtype = torch.uint8 if 11 + N <= 256 else torch.int16        # ids < stuff_num + N (vps_temporal_slots.py:428)
+
+    # ---- sweep mode: every frame of this rank's videos resident in HBM, clips = (video, frame) in order --------
+    sweep = None
+    if a.config == "sweep":
+        from slotvps_b200.parallel import shard_clips
+        vids = shard_clips(a.videos, rank, world)                      # shard by VIDEO: the tracker needs a video's frames in order
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        frames = {(v, f): [torch.randn((1, 128, h, w), generator=g, device=dev) for (h, w) in shapes]
+                  for v in vids for f in range(a.video_frames)}
+        clips = [(v, f) for v in vids for f in range(a.video_frames)]
+        # one step per clip of the shard; ranks with one video fewer repeat clips so every rank runs the same number of
+        # steps (the gathers need equal counts) -- `value` counts the real clips only
+        K = -(-a.videos // world) * a.video_frames
+        sweep = dict(frames=frames, clips=clips, vids=vids, real_clips=a.videos * a.video_frames)
 
     # Clips are independent, so M clips are kept in flight per GPU: lane j owns a model instance
-    # (its own workspaces), a resident input clip (178 MB at T=2: larger than the 126 MB L2), a stream and a
+    # (its own workspaces), static input buffers (178 MB at T=2: larger than the 126 MB L2), a stream and a
     # CUDA graph of the whole step.  Step i runs on lane i % M.
     class Lane:
         pass
     lanes = []
+    kw = dict(pos="sine", fusion_logits=fusion_logits, fusion_masks=fusion_masks, want_feats=False)
     for j in range(M):
         ln = Lane()
-        ln.model = sv.SlotVPSRetriever({**sv.HEAD_KWARGS, "kernel_path": args.kernel_path}, N, sv.FUSION_KWARGS)
+        ln.model = sv.SlotVPSRetriever({**sv.HEAD_KWARGS, "kernel_path": a.kernel_path}, N, sv.FUSION_KWARGS)
         ln.model.dynamic_mask_head.load_state_dict(sd, strict=True)
         ln.model.load_capsule_params(cap)
         ln.model = ln.model.to(dev)
         ln.host = synthetic.make_features(H, W, T=T, video=10 * rank + j, frame=0)
         ln.clip = [[f.to(dev) for f in fr] for fr in ln.host]
         ln.stream = torch.cuda.Stream()
-        ln.graph = None if args.no_graph else sv.GraphedClip(ln.model, ln.clip, (H, W), pos="sine", fusion_logits=fusion_logits)
+        ln.graph = None if a.no_graph else sv.GraphedClip(ln.model, ln.clip, (H, W), **kw)
         ln.end = torch.cuda.Event()
         lanes.append(ln)
     model = lanes[0].model
     dev_clips = [ln.clip for ln in lanes]
+    pan_wire = torch.empty((K, H, W), dtype=wire_dtype, device=dev) if world > 1 else None
+    comm = torch.cuda.Stream() if world > 1 else None
+    gathered = [torch.empty((K, H, W), dtype=wire_dtype, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    n_chunks = 4 if K >= 8 else 1
+    bounds = [K * c // n_chunks for c in range(n_chunks + 1)]
 
     def step(i, feats):                      # eager single-stream step (profiling pass)
-        return model(feats, (H, W), pos="sine", fusion_logits=fusion_logits)
+        return model(feats, (H, W), **kw)
 
     def lane_step(ln, i):
-        o = ln.graph.replay() if ln.graph is not None else ln.model(ln.clip, (H, W), pos="sine", fusion_logits=fusion_logits)
-        if pan is not None:
-            pan[i % K].copy_(o["fusion"].panoptic, non_blocking=True)
+        if sweep is not None:                # feed: device-to-device copy of the clip's two frames into the lane's static buffers
+            v, f = sweep["clips"][i % len(sweep["clips"])]
+            cur, ref = sweep["frames"][(v, f)], sweep["frames"][(v, max(f - 1, 0))]
+            for l in range(4):
+                ln.clip[0][l].copy_(ref[l], non_blocking=True)
+                ln.clip[1][l].copy_(cur[l], non_blocking=True)
+        o = ln.graph.replay() if ln.graph is not None else ln.model(ln.clip, (H, W), **kw)
+        if pan_wire is not None:
+            pan_wire[i % K].copy_(o["fusion"].panoptic, non_blocking=True)     # int64 -> 1 byte per pixel for the wire
         return o
 
-    main = torch.cuda.current_stream()
+    main_s = torch.cuda.current_stream()
     start = torch.cuda.Event()
 
-    def run(n, body):
-        start.record(main)
+    def gather_chunk(c):
+        """Rank 0 is the only consumer (it would write the PNG/JSON): a gather of this chunk's id maps on a side stream,
+        issued as soon as the chunk's steps are enqueued, so only the last chunk sits behind the last clip."""
+        comm.wait_stream(main_s)
+        for ln in lanes:
+            comm.wait_stream(ln.stream)
+        with torch.cuda.stream(comm):
+            lo, hi = bounds[c], bounds[c + 1]
+            dist.gather(pan_wire[lo:hi], [g[lo:hi] for g in gathered] if rank == 0 else None, dst=0)
+
+    def run(n, body, collect=False):
+        start.record(main_s)
         for ln in lanes:
             ln.stream.wait_event(start)
-        out = None
+        out, c = None, 0
         for i in range(n):
             ln = lanes[i % M]
             with torch.cuda.stream(ln.stream):
                 out = body(ln, i)
+            if collect and dist is not None and i + 1 == bounds[c + 1]:
+                gather_chunk(c)
+                c += 1
         for ln in lanes:
             ln.end.record(ln.stream)
-            main.wait_event(ln.end)
+            main_s.wait_event(ln.end)
+        if collect and dist is not None:
+            main_s.wait_stream(comm)
         return out
 
     def barrier():
@@ -293,59 +394,71 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(n, body, collect=False, repeats=1):
+        """`repeats` timed regions of n steps each, barrier + synchronize on both sides, max over ranks; all regions."""
+        res = []
+        out = None
+        for _ in range(repeats):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            out = run(n, body, collect)
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if dist is not None:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            res.append(ms)
+        return res, out
+
     run(max(Wm, M), lane_step)
     if dist is not None:
-        from slotvps_b200.parallel import WIRE_DTYPE
-        pan_wire = torch.empty((K, H, W), dtype=WIRE_DTYPE, device=dev)
-        gathered = torch.empty((world * K, H, W), dtype=WIRE_DTYPE, device=dev)
-        dist.all_gather_into_tensor(gathered.view(torch.uint8), pan_wire.view(torch.uint8))     # warm-up: NCCL channel setup stays out of the timed region
+        run(K, lane_step, collect=True)                          # warm-up incl. the gathers: NCCL channel setup stays out of the timed region
     barrier()
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
     if rank == 0:
         sampler.start()
-    L.slotvps_launch_count(1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    out = run(K, lane_step)
-    if dist is not None:                                    # one all-gather of the shard's id maps,
-        pan_wire.copy_(pan)                                 # narrowed to int16 on the wire (ids < stuff_num + N)
-        dist.all_gather_into_tensor(gathered.view(torch.uint8), pan_wire.view(torch.uint8))   # raw bytes: NCCL has no int16
-    e1.record()
-    barrier()
-    launches = world * (int(L.slotvps_launch_count(0)) if lanes[0].graph is None else K * lanes[0].graph.launches)
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world * K * T / (ms * 1e-3)
+    reps, out = timed(K, lane_step, collect=True, repeats=max(1, a.repeats))
+    ms = statistics.median(reps)
+    launches = world * K * lanes[0].graph.launches if lanes[0].graph is not None else 0
+    if lanes[0].graph is None:
+        L.slotvps_launch_count(1)
+        run(K, lane_step)
+        torch.cuda.synchronize()
+        launches = world * int(L.slotvps_launch_count(0))
+    units = sweep["real_clips"] if sweep is not None else world * K          # clips the whole job processed
+    value = units * T / (ms * 1e-3)
     meta = out["fusion"].host()
 
     # single clip in flight (latency view of the same step), for reference
     single_ms = None
-    if M > 1:
+    if M > 1 and sweep is None:
         keep, lanes[:] = lanes[:], lanes[:1]
         M1, M = M, 1
         run(max(2, Wm), lane_step)
-        barrier()
-        e0.record()
-        run(K, lane_step)
-        e1.record()
-        barrier()
-        single_ms = e0.elapsed_time(e1) / K
+        r1, _ = timed(K, lane_step, repeats=3)
+        single_ms = statistics.median(r1) / K
         lanes[:] = keep
         M = M1
 
+    # ---- sweep: per-video tracker pass + bit-identity of a sample of clips (outside the timed region) ------------
+    sweep_info = None
+    if sweep is not None:
+        sweep_info = dict(videos_this_rank=len(sweep["vids"]), clips_this_rank=K,
+                          feed="device-to-device copy of each clip's two frames (178 MB) into the lane's static graph inputs, inside the timed region")
+
     # ---- e2e: host buffers in, id map + meta out, every step -----------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not a.no_e2e and sweep is None:
         for ln in lanes:
             ln.pinned = [[f.pin_memory() for f in fr] for fr in ln.host]
-            ln.h_pan = torch.empty((H, W), dtype=torch.int64).pin_memory()
+            ln.wire = torch.empty((H, W), dtype=wire_dtype, device=dev)
+            ln.h_pan = torch.empty((H, W), dtype=wire_dtype).pin_memory()
             ln.h_meta = torch.empty(4 + 3 * N, dtype=torch.int32).pin_memory()
         h2d = sum(f.numel() * 4 for fr in lanes[0].host for f in fr)
-        d2h = lanes[0].h_pan.numel() * 8 + lanes[0].h_meta.numel() * 4
+        d2h = lanes[0].h_pan.numel() * lanes[0].h_pan.element_size() + lanes[0].h_meta.numel() * 4
 
         def e2e_step(ln, i):
             # upload this step's clip from pinned host memory into the lane's input buffers, run, read results back;
@@ -354,137 +467,211 @@ def main():
                 for l in range(4):
                     ln.clip[t][l].copy_(ln.pinned[t][l], non_blocking=True)
             o = lane_step(ln, i)
-            ln.h_pan.copy_(o["fusion"].panoptic, non_blocking=True)
+            ln.wire.copy_(o["fusion"].panoptic, non_blocking=True)       # ids < 256: 1 byte per pixel over PCIe; the caller widens on the host
+            ln.h_pan.copy_(ln.wire, non_blocking=True)
             ln.h_meta.copy_(o["fusion"].meta, non_blocking=True)
             return o
         run(max(2, Wm, M), e2e_step)
-        barrier()
-        e0.record()
-        run(K, e2e_step)
-        e1.record()
-        barrier()
-        ms2 = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms2], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms2 = float(t.item())
+        r2, _ = timed(K, e2e_step, repeats=max(1, min(3, a.repeats)))
+        ms2 = statistics.median(r2)
         e2e = dict(value=world * K * T / (ms2 * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                   ms_per_step=ms2 / K, pipeline=f"{M} clips in flight: a lane's upload/readback overlaps the other lanes' compute")
+                   ms_per_step=ms2 / K, ms_per_region=r2, h2d_gbs_per_rank=h2d * K / (ms2 * 1e-3) / 1e9,
+                   pipeline=f"{M} clips in flight: a lane's upload/readback overlaps the other lanes' compute",
+                   readback=f"id map as {str(wire_dtype).split('.')[-1]} (ids < stuff_num + N), meta int32[{4 + 3 * N}]")
     clocks = sampler.stop() if rank == 0 else None     # sampled over the timed region and the e2e region (both under load)
 
     # ---- per-kernel device times (CUDA events on the launching stream) -> roofline ----------------------
     roofline, breakdown = None, None
     if rank == 0:
         pk = peaks()
-        per_frame_flops, shapes, heads = algorithmic_flops(args)
-        nprof = min(K, 3)
+        heads = HEADS_DEFAULT
+        nprof = 3
         import ctypes
         buf = ctypes.create_string_buffer(1 << 16)
+        torch.cuda.synchronize()
+        for i in range(2):
+            step(i, dev_clips[i % len(dev_clips)])            # eager warm-up of the single-stream schedule
         torch.cuda.synchronize()
         L.slotvps_profile_begin(torch.cuda.current_stream(dev).cuda_stream)
         for i in range(nprof):
             step(i, dev_clips[i % len(dev_clips)])
         L.slotvps_profile_end(buf, len(buf))
         rows = [r.split("\t") for r in buf.value.decode().strip().split("\n") if r]
-        breakdown = {r[0]: dict(launches_per_step=int(r[1]) / nprof, ms_per_step=float(r[2]) / nprof) for r in rows}
-        total = sum(v["ms_per_step"] for v in breakdown.values())
+        breakdown = {}
+        for r in rows:
+            breakdown[r[0]] = dict(launches_per_step=int(r[1]) / nprof, ms_per_step=float(r[2]) / nprof)
+            if len(r) > 3 and int(r[3]) > 0:
+                breakdown[r[0]]["grid_ctas"] = int(r[3])
         tj_all = {}
-        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-        if os.path.exists(tp):              # DRAM bytes per pixel measured by ncu on the level-3 launches
-            tj_all = json.load(open(tp))
-        px_step = sum(hd * h * w for hd, (h, w) in zip(heads, shapes)) * T            # pixel.stage units of the attention kernels
-        px_all = sum(h * w for (h, w) in shapes) * T                                  # pixels of the level fusion
-
-        def kernel_roofline(name):
-            """Roofline entry of one kernel: its own bound, algorithmic work of all its launches in a step / their time."""
-            t_ms = breakdown[name]["ms_per_step"]
-            nl = breakdown[name]["launches_per_step"]
-            fl = kernel_flops_per_step(name, args, shapes, heads)
-            if fl:                          # tensor-bound kernels of the attention contraction
-                ach = fl / (t_ms * 1e-3) / 1e12
-                peak = pk["bf16_tflops"]              # burst figure: the profiling pass times every kernel alone, with host gaps between launches
+        for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tp):              # DRAM bytes per pixel measured by ncu on the level-3 launches
+                tj_all = json.load(open(tp))
+                tj_all["_file"] = "profiles/" + name
+                break
+        models = kernel_models(a, shapes, heads, meta["k"])
+        px_stage = sum(hd * h * w for hd, (h, w) in zip(heads, shapes)) * T
+        px_all = sum(h * w for (h, w) in shapes) * T
+        ktot = sum(v["ms_per_step"] for k, v in breakdown.items() if k != "(host gap)")
+        per_kernel = {}
+        for name, v in breakdown.items():
+            if name == "(host gap)":
+                continue
+            t_ms, nl = v["ms_per_step"], v["launches_per_step"]
+            ent = dict(kernel=name, ms_per_step=t_ms, launches_per_step=nl, us_per_launch=1e3 * t_ms / max(nl, 1e-9),
+                       share_of_step=t_ms / ktot, grid_ctas=v.get("grid_ctas"))
+            mdl = models.get(name)
+            if mdl is None:
+                ent.update(bound="latency", note="no byte / FLOP model: slot-side or bookkeeping kernel, reported as time per launch")
+            elif mdl[0] == "tensor":
+                ach = mdl[1] / (t_ms * 1e-3) / 1e12
                 tj = tj_all.get(name)
-                traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pixels"] * px_step / nl if tj else None
-                return dict(kernel=name, bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
-                            executed_mma_tflops=3 * ach, executed_frac=3 * ach / peak,      # fp16 hi/lo split: 3 MMA products per algorithmic product
-                            traffic=traffic, traffic_note="DRAM bytes per launch (ncu level-3 capture scaled by pixels)",
-                            peak_source=f"{pk['source']} bf16 burst (kernel timed alone in the per-kernel profiling pass)",
-                            algorithmic_flops_per_step=fl, ms_per_step=t_ms, launches_per_step=nl)
-            if name == "fuse_tc":           # level fusion: read 4*128 B + write 4*256 B (fp32 feature) + 4 fp16 planes (2 KB) per pixel
-                by = px_all * (4 * 128 + 4 * 256 + 4 * 2 * 256)
-                ach = by / (t_ms * 1e-3) / 1e9
-                tj = tj_all.get("fuse_tc_main")
-                traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pixels"] * px_all / nl if tj else None
-                return dict(kernel=name, bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
-                            traffic=traffic, traffic_note="DRAM bytes per launch (ncu capture of the level-3 main pass scaled by pixels; coarse passes excluded)",
-                            peak_source=pk["source"] + " copy bandwidth", algorithmic_bytes_per_step=by, ms_per_step=t_ms, launches_per_step=nl)
-            return None
-
-        per_kernel = {k: kernel_roofline(k) for k in breakdown if k in ("stats_tc", "attn_tc", "fuse_tc", "proj_rstd(k)", "proj_rstd(v)", "slot_attn_fp32")}
-        per_kernel = {k: v for k, v in per_kernel.items() if v}
-        if per_kernel:
-            # the dominant kernel = the one with the largest share of the step; the others are listed under "kernels"
-            name = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
-            roofline = dict(per_kernel[name])
-            roofline["kernels"] = per_kernel
-            peak = pk["bf16_tflops"]              # burst figure: the profiling pass times every kernel alone, with host gaps between launches
-            # the whole attention contraction (all its kernels) against the same peak
-            names = [k for k in breakdown if k in ("proj_rstd(k)", "proj_rstd(v)", "slot_attn_fp32", "stats_tc", "attn_tc")]
+                ent.update(bound="tensor", achieved=ach, peak=pk["bf16_tflops"], unit="TFLOP/s", frac=ach / pk["bf16_tflops"],
+                           executed_mma_tflops=3 * ach, executed_frac=3 * ach / pk["bf16_tflops"],     # fp16 hi/lo split: 3 MMA products per algorithmic product
+                           algorithmic_flops_per_step=mdl[1],
+                           traffic=(tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pixels"] * px_stage / nl if tj else None,
+                           traffic_note=f"DRAM bytes per launch ({tj_all.get('_file')}: ncu level-3 capture scaled by pixels)" if tj else None,
+                           peak_source=f"{pk['source']} bf16 burst (kernel timed alone in the per-kernel profiling pass)")
+            else:
+                ach = mdl[1] / (t_ms * 1e-3) / 1e9
+                tj = tj_all.get("fuse_tc_main" if name == "fuse_tc" else name)
+                scale_px = px_all if name == "fuse_tc" else shapes[-1][0] * shapes[-1][1]
+                traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pixels"] * scale_px if tj else None
+                ent.update(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
+                           algorithmic_bytes_per_step=mdl[1], traffic=traffic,
+                           traffic_over_algorithmic=(traffic / mdl[1]) if traffic else None,
+                           traffic_note=f"DRAM bytes per step ({tj_all.get('_file')}: ncu capture scaled by pixels)" if tj else None,
+                           peak_source=pk["source"] + " copy bandwidth")
+                if name == "fuse_tc":
+                    ent["operand_plane_bytes_per_step"] = px_all * 4 * 2 * 256      # the fp16 hi/lo operand planes it also writes (not algorithmic)
+            per_kernel[name] = ent
+        name = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
+        roofline = dict(per_kernel[name])
+        roofline["kernels"] = per_kernel
+        step_ms = single_ms if single_ms else ms / K
+        roofline["share_of_single_clip_wall_step"] = roofline["ms_per_step"] / step_ms
+        roofline["profile_pass"] = "eager, single stream, 3 steps, every persistent kernel at its full-width grid (grid_ctas per kernel)"
+        # the whole attention contraction (all its kernels) against the bf16 burst peak
+        names = [k for k in breakdown if k in ("proj_rstd(k)", "proj_rstd(v)", "slot_attn_fp32", "stats_tc", "attn_tc")]
+        if names:
+            per_frame_flops = sum(hd * h * w * (4 * 256 * 256 + 4 * N * 256) for hd, (h, w) in zip(heads, shapes))
             tt = sum(breakdown[k]["ms_per_step"] for k in names)
-            roofline["attention_contraction"] = dict(kernels=names, algorithmic_tflops=per_frame_flops * T / (tt * 1e-3) / 1e12,
-                                                     ms_per_step=tt, frac_of_peak=per_frame_flops * T / (tt * 1e-3) / 1e12 / peak,
-                                                     executed_frac_of_peak=3 * per_frame_flops * T / (tt * 1e-3) / 1e12 / peak)
-        # HBM-bound stages: mask logits (read 4*C*P3 + write 4*N*P3) -- SURVEY.md 8d
-        P3 = shapes[3][0] * shapes[3][1]
-        ml = [k for k in breakdown if k in ("mask_prep", "feat_rnorm", "mask_logits_tc")]
-        if roofline is not None:
-            step_ms = single_ms if single_ms else ms / K
-            # share of the serialised kernel time of one step (the definition an ncu launch list gives: profiles/
-            # r1_tc_launches_summary.txt) and, separately, of the wall time of a step with one clip in flight (two streams overlap)
-            ktot = sum(v["ms_per_step"] for k, v in breakdown.items() if k != "(host gap)")
-            roofline["share_of_step"] = roofline["ms_per_step"] / ktot
-            roofline["share_of_single_clip_wall_step"] = roofline["ms_per_step"] / step_ms
-            for v in roofline["kernels"].values():
-                v["share_of_step"] = v["ms_per_step"] / ktot
-            hb = {"peak_gbs": pk["hbm_gbs"], "peak_source": pk["source"] + " copy bandwidth"}
-            if "mask_tc" in breakdown:      # mask-logit projection: read 4*C*P3 (as 2 fp16 hi/lo planes = same bytes) + write 4*N*P3
-                by = 4 * 256 * P3 + 4 * N * P3
-                t_ms = breakdown["mask_tc"]["ms_per_step"]
-                hb["mask_logits"] = dict(kernel="mask_tc", algorithmic_bytes=by, ms=t_ms, achieved_gbs=by / (t_ms * 1e-3) / 1e9,
-                                         frac=by / (t_ms * 1e-3) / 1e9 / pk["hbm_gbs"])
-            fk = [k for k in breakdown if k.startswith("fuse_") and k != "fuse_tc"]
-            if fk:                          # fusion, exact two-pass form: 2*4*Kept*P3 read + 8*H*W written (SURVEY.md 8d)
-                by = 2 * 4 * meta["k"] * P3 + 8 * H * W
-                t_ms = sum(breakdown[k]["ms_per_step"] for k in fk)
-                hb["panoptic_fusion"] = dict(kernels=fk, kept_slots=meta["k"], algorithmic_bytes=by, ms=t_ms,
-                                             achieved_gbs=by / (t_ms * 1e-3) / 1e9, frac=by / (t_ms * 1e-3) / 1e9 / pk["hbm_gbs"])
-            if "fuse_tc" in breakdown:      # level fusion: read 4*128*P + write 4*256*P (fp32 feature) + 4 fp16 planes, per frame & level
-                px_all = sum(h * w for (h, w) in shapes) * T
-                by = px_all * (4 * 128 + 4 * 256 + 4 * 2 * 256)
-                t_ms = breakdown["fuse_tc"]["ms_per_step"]
-                hb["level_fusion"] = dict(kernel="fuse_tc", algorithmic_bytes=by, ms=t_ms, achieved_gbs=by / (t_ms * 1e-3) / 1e9,
-                                          frac=by / (t_ms * 1e-3) / 1e9 / pk["hbm_gbs"])
-            roofline["hbm_stages"] = hb
+            alg = per_frame_flops * T / (tt * 1e-3) / 1e12
+            roofline["attention_contraction"] = dict(kernels=names, algorithmic_tflops=alg, ms_per_step=tt, frac_of_peak=alg / pk["bf16_tflops"],
+                                                     executed_frac_of_peak=3 * alg / pk["bf16_tflops"], peak=pk["bf16_tflops"])
+        hb = {"peak_gbs": pk["hbm_gbs"], "peak_source": pk["source"] + " copy bandwidth"}
+        if "mask_tc" in per_kernel:
+            hb["mask_logits"] = {k: per_kernel["mask_tc"].get(k) for k in ("kernel", "algorithmic_bytes_per_step", "ms_per_step", "achieved", "frac")}
+        fk = [k for k in breakdown if k.startswith("fuse_") and k != "fuse_tc"]
+        if fk:                          # fusion, exact two-pass form: 2*4*Kept*P3 read + 8*H*W written
+            P3 = shapes[-1][0] * shapes[-1][1]
+            by = 2 * 4 * meta["k"] * P3 + 8 * H * W
+            t_ms = sum(breakdown[k]["ms_per_step"] for k in fk)
+            hb["panoptic_fusion"] = dict(kernels=fk, launches_per_step=sum(breakdown[k]["launches_per_step"] for k in fk), kept_slots=meta["k"],
+                                         things=meta["n_things"], algorithmic_bytes=by, ms=t_ms,
+                                         achieved_gbs=by / (t_ms * 1e-3) / 1e9, frac=by / (t_ms * 1e-3) / 1e9 / pk["hbm_gbs"])
+        if "fuse_tc" in per_kernel:
+            hb["level_fusion"] = {k: per_kernel["fuse_tc"].get(k) for k in ("kernel", "algorithmic_bytes_per_step", "ms_per_step", "achieved", "frac",
+                                                                                "traffic", "traffic_over_algorithmic", "operand_plane_bytes_per_step")}
+        roofline["hbm_stages"] = hb
 
     # ---- CPU baseline beside it (rank 0, N == 1) ------------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, info, _ = run_cpu_arm(args, 2, 1, args.cpu_budget_s)
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        fps, info = run_cpu_arm(a, 3, 1, a.cpu_budget_s)
         cpu = dict(value=fps, unit=UNIT, cores=info["cores"], kind=info["kind"], sample=info["sample"])
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=Wm, ms_per_step=ms / K,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=f"r50_fpn_slotvps retriever, single {H}x{W} clip, T={T}, N={N}, 7 stages (BASELINE configs[1])",
+                    timed_regions=dict(repeats=len(reps), ms=reps, median_ms=ms, min_ms=min(reps), max_ms=max(reps),
+                                       value_min=units * T / (max(reps) * 1e-3), value_max=units * T / (min(reps) * 1e-3)),
+                    config=dict(workload=workload_string(a),
                                 frames_convention="retriever frames/s = T * clips/s; output frames/s = clips/s",
-                                l2="inputs larger than L2 (178 MB/clip); one resident clip per lane, lanes alternate",
-                                fusion_logits="designed (random-init heads keep no slot)",
-                                kernel_path=args.kernel_path, cuda_graph=not args.no_graph, clips_in_flight=M, numa_bind=numa, side_stream_ctas=int(os.environ.get("SLOTVPS_SIDE_CTAS", "112")), main_stream_ctas=int(os.environ.get("SLOTVPS_MAIN_CTAS", "148")),
-                                single_clip_in_flight_ms_per_step=single_ms, sharding="clips per rank, one all_gather of id maps" if world > 1 else "single GPU",
-                                kept_slots=meta["k"], fusion_iters=meta["iters"]),
+                                l2="inputs larger than L2 (178 MB/clip at T=2); one resident clip per lane, lanes alternate",
+                                fusion_inputs=f"designed class + mask logits (synthetic.make_fusion_case{tuple(FUSION_CASE.values())}): "
+                                              f"{meta['k']} kept slots, {meta['n_things']} things (random-init heads keep no slot)",
+                                fp32_fused_features="not materialised (L2 integration form: simple_test only consumes the finest level, "
+                                                    "through the fp16 operand planes; want_feats=True restores the head's third return value)",
+                                kernel_path=a.kernel_path, cuda_graph=not a.no_graph, clips_in_flight=M, numa_bind=numa,
+                                side_stream_ctas=int(os.environ.get("SLOTVPS_SIDE_CTAS", "112")), main_stream_ctas=int(os.environ.get("SLOTVPS_MAIN_CTAS", "148")),
+                                single_clip_in_flight_ms_per_step=single_ms,
+                                sharding=(f"clips per rank; id maps ({str(wire_dtype).split('.')[-1]}) gathered to rank 0 in {n_chunks} chunks on a side "
+                                          f"stream while later clips compute") if world > 1 else "single GPU",
+                                kept_slots=meta["k"], fusion_iters=meta["iters"], sweep=sweep_info),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
                     kernel_breakdown_ms_per_step=breakdown)
         print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_slot_sweep(a, dev, rank, world, dist):
+    """BASELINE configs[4]: N in {50,100,200,300} x 1..7 retriever iterations at 1024x2048 on one GPU."""
+    import slotvps_b200 as sv
+    from slotvps_b200 import synthetic
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    T, H, W = a.frames, a.height, a.width
+    shapes = synthetic.level_shapes(H, W)
+    host = synthetic.make_features(H, W, T=T, video=3, frame=0)
+    M = min(4, max(1, a.inflight))
+    clips = [[[f.to(dev) for f in fr] for fr in host] for _ in range(M)]
+    table = []
+    K = max(4, min(a.steps, 8))
+    for N in (50, 100, 200, 300):
+        cap = synthetic.make_capsule_params(0, N)
+        a.slots = N
+        lg, pmd = fusion_inputs(a, shapes)
+        lg, pmd = lg.to(dev), pmd.to(dev)
+        for it in range(1, 8):
+            heads, temporal = ITER_CONFIGS[it]
+            sd = synthetic.make_head_state_dict(0, per_dh_num_heads=heads, temporal_stages=temporal)
+            lanes = []
+            for j in range(M):
+                m = sv.SlotVPSRetriever({**sv.HEAD_KWARGS, "dh_num_heads": it, "per_dh_num_heads": heads,
+                                         "apply_temporal_query_atten_stages": temporal, "kernel_path": a.kernel_path}, N, sv.FUSION_KWARGS)
+                m.dynamic_mask_head.load_state_dict(sd, strict=True)
+                m.load_capsule_params(cap)
+                m = m.to(dev)
+                g = sv.GraphedClip(m, clips[j], (H, W), pos="sine", fusion_logits=lg, fusion_masks=pmd, want_feats=False)
+                lanes.append((g, torch.cuda.Stream()))
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+            def go(n):
+                main_s = torch.cuda.current_stream()
+                for g, s in lanes:
+                    s.wait_stream(main_s)
+                for i in range(n):
+                    g, s = lanes[i % M]
+                    with torch.cuda.stream(s):
+                        g.replay()
+                for g, s in lanes:
+                    main_s.wait_stream(s)
+            go(M)
+            torch.cuda.synchronize()
+            ev0.record()
+            go(K)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / K
+            # one clip in flight
+            ev0.record()
+            for _ in range(K):
+                lanes[0][0].replay()
+            ev1.record()
+            torch.cuda.synchronize()
+            table.append(dict(n_slots=N, iterations=it, per_dh_num_heads=heads, temporal_stages=temporal, ms_per_clip=ms,
+                              frames_per_s=T / (ms * 1e-3), single_clip_ms=ev0.elapsed_time(ev1) / K, launches_per_clip=lanes[0][0].launches))
+            del lanes
+            torch.cuda.empty_cache()
+    line = dict(metric=metric_name(a), value=[r for r in table if r["n_slots"] == 100 and r["iterations"] == 7][0]["frames_per_s"], unit=UNIT,
+                n_gpus=1, steps=K, warmup=M, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=workload_string(a), clips_in_flight=M, value_is="the N=100, 7-iteration row"), table=table)
+    print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -75,6 +75,10 @@ typedef struct slotvps_head_desc {
   int32_t temporal_mask;                       /* bit s set: stage s runs the Video Retriever */
   int32_t pos_mode;                            /* 0: no pos, 1: pos tensors given, 2: sine embedding generated on the fly */
   int32_t kernel_path;                         /* 0: auto (tcgen05 when shapes allow), 1: force fp32 CUDA-core path */
+  int32_t ffn_act;                             /* stage FFN activation (`activation`, r50_fpn_slotvps.py:33 / swinL_fpn_slotvps.py:41):
+                                                  0 = the r50 config's "gelu" (exact erf form), 1 = "relu", 2 = "gelu"          */
+  int32_t temporal_ffn_act;                    /* Video Retriever FFN activation (temporal_query_attention_config.activation,
+                                                  r50 :49 "relu" / swinL :56 "gelu"): 0 = "relu" (r50), 1 = "relu", 2 = "gelu"   */
 } slotvps_head_desc;
 
 /* Bytes of scratch slotvps_head_forward needs for this shape. */
@@ -111,6 +115,31 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
                          float* cls_out, float* emb_out, float* const* fused_out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* slotvps_head_forward with options.  Every field may be 0 / NULL (= slotvps_head_forward).
+ *   stage_slots_in[s*T+t] : [N,256] or NULL.  Teacher forcing for per-stage parity: the slots ENTERING stage s of frame t
+ *                           are taken from here instead of from stage s-1 (dynamic_mask_head.py:210-211 carries them).
+ *   skip_fused_mask       : bit l set = the fp32 NCHW feature of level l (third return value of the reference head) is
+ *                           not written; only allowed for levels that run the tensor-core path (their fp16 operand
+ *                           planes feed everything downstream, incl. slotvps_head_mask_logits).  The L2 integration /
+ *                           SlotVPSRetriever set it: simple_test only consumes the finest level, through the planes.
+ *   feat_bn_scale/shift   : [256] folded feat_bn (eval) of generate_final_outputs (vps_temporal_slots.py:145-149).  When
+ *                           given, the finest level's fusion epilogue also accumulates sum_c (scale*x+shift)^2 per pixel
+ *                           into rnorm_ss [T][P_last] (zeroed by the call), which slotvps_head_mask_logits then uses
+ *                           instead of re-reading the fp32 feature.                                                     */
+typedef struct slotvps_head_opts {
+  const float* const* stage_slots_in;
+  int32_t skip_fused_mask;
+  const float* feat_bn_scale;
+  const float* feat_bn_shift;
+  float* rnorm_ss;
+} slotvps_head_opts;
+int slotvps_head_forward_ex(const slotvps_head_desc* d, const slotvps_stage_params* stages,
+                            const void* prepared,
+                            const float* const* feats, const float* const* pos,
+                            const float* const* init_query,
+                            float* cls_out, float* emb_out, float* const* fused_out,
+                            void* workspace, size_t workspace_bytes, const slotvps_head_opts* opts, void* stream);
+
 /* Level fusion alone (dynamic_mask_head.py:172-185): out = conv_trans(cat(up2x(prev), x)) or,
  * prev == NULL, conv_trans(cat(x,x,x)).  prev [256,h/2,w/2], x [128,h,w], out [256,h,w];
  * scratch: 256*max(128,(h/2)*(w/2)) floats.                                                 */
@@ -144,6 +173,18 @@ int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, s
                              const float* feat, const float* emb,
                              const float* feat_bn_w, const float* feat_bn_b, const float* feat_bn_mean, const float* feat_bn_var,
                              const float* fg_bn, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* BatchNorm2d in eval mode as a per-channel affine (feat_bn of generate_final_outputs, vps_temporal_slots.py:145-149):
+ * scale[c] = w[c] / sqrt(var[c] + 1e-5), shift[c] = b[c] - mean[c] * scale[c].  Feeds slotvps_head_opts.feat_bn_scale/shift. */
+int slotvps_fold_batchnorm(const float* w, const float* b, const float* mean, const float* var, int n,
+                           float* scale, float* shift, void* stream);
+
+/* Same; exactly one of `feat` (per-pixel norm computed from the fp32 feature) and `rnorm_ss` ([T][P_last] squared norms of
+ * feat_bn(x) accumulated by slotvps_head_forward_ex with opts.rnorm_ss) is non-NULL.                                       */
+int slotvps_head_mask_logits_ex(const slotvps_head_desc* d, void* head_workspace, size_t head_workspace_bytes, int frame,
+                                const float* feat, const float* rnorm_ss, const float* emb,
+                                const float* feat_bn_w, const float* feat_bn_b, const float* feat_bn_mean, const float* feat_bn_var,
+                                const float* fg_bn, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Panoptic fusion: PostProcessPanopticInstances.forward (vps_temporal_slots.py:659-807, incl.
  * mask_removal :564-657) + the inline relabel of simple_test (:411-435), entirely on device.

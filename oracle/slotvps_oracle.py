@@ -17,8 +17,8 @@ leg may import this file.  ``slotvps_b200`` never does: the product path has no 
 Parity pinning: the reference ships NO tests, golden vectors or fixtures for this path
 (SURVEY.md section 4), so the oracle is pinned against outputs of the reference itself, imported in
 place by ``oracle/ref_import.py`` and frozen as fixtures by ``tests/golden/make_golden.py``
-(``tests/test_oracle_golden.py`` checks them; ``tests/test_oracle_vs_reference.py`` re-checks
-live whenever ``/root/reference`` is present).
+(``tests/test_oracle_golden.py`` checks them on CPU; ``python tests/golden/make_golden.py --check``
+regenerates every fixture from ``/root/reference`` and compares it with the committed file).
 
 Parameters are passed as a flat ``dict[str, Tensor]`` with the reference's own ``state_dict``
 key names (``head_series_{l}.{j}.*``, ``conv_trans.conv.*``).
@@ -50,6 +50,8 @@ class HeadConfig:
     temporal_stages: Sequence[int] = (3, 4, 5, 6)
     num_cls: int = 2
     num_reg: int = 2
+    activation: str = "gelu"             # stage FFN, r50_fpn_slotvps.py:33 ("relu" in swinL_fpn_slotvps.py:41)
+    temporal_activation: str = "relu"    # Video Retriever FFN, r50 :49 ("gelu" in swinL :56)
 
 
 @dataclass
@@ -79,6 +81,11 @@ def _lin(x, w, b=None):
 
 def _gelu_erf(x):
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def _act(name):
+    """_get_activation_fn, dynamic_mask_head.py:590-597: "relu" -> F.relu, "gelu" -> F.gelu (exact erf form)."""
+    return {"relu": torch.relu, "gelu": _gelu_erf}[name]
 
 
 def sine_position_embedding(h: int, w: int, dtype=torch.float32, num_pos_feats: int = 128,
@@ -161,12 +168,12 @@ def stage_till_ffn(s, x, pos, P, pre, cfg: HeadConfig):
     p = _ln(s + self_attention(s, P, pre, cfg.nhead), P[pre + "norm1.weight"], P[pre + "norm1.bias"])
     r = pixel_attention(p, x, pos, P, pre)
     p = _ln(p + r, P[pre + "norm2.weight"], P[pre + "norm2.bias"])
-    f = _lin(_gelu_erf(_lin(p, P[pre + "linear1.weight"], P[pre + "linear1.bias"])),
+    f = _lin(_act(cfg.activation)(_lin(p, P[pre + "linear1.weight"], P[pre + "linear1.bias"])),
              P[pre + "linear2.weight"], P[pre + "linear2.bias"])
     return _ln(p + f, P[pre + "norm3.weight"], P[pre + "norm3.bias"])
 
 
-def video_retriever(X, P, pre):
+def video_retriever(X, P, pre, activation="relu"):
     """TemporalSlotsHead.forward + SlotsDynamicConv.forward, dynamic_mask_head.py:494-527,550-572.
 
     X [T*N,C] -> [T*N,C] (WITHOUT the outer residual of :317).  softmax_dim="slots" means the
@@ -180,7 +187,7 @@ def video_retriever(X, P, pre):
     a = torch.softmax(q @ k.t(), 0)                         # normalise over l (queries) per key u
     r = torch.relu(_ln(a @ v, P[ii + "norm1.weight"], P[ii + "norm1.bias"]))
     y = _ln(X + r, P[pre + "norm2.weight"], P[pre + "norm2.bias"])
-    f = _lin(torch.relu(_lin(y, P[pre + "linear1.weight"], P[pre + "linear1.bias"])),
+    f = _lin(_act(activation)(_lin(y, P[pre + "linear1.weight"], P[pre + "linear1.bias"])),
              P[pre + "linear2.weight"], P[pre + "linear2.bias"])
     return _ln(y + f, P[pre + "norm3.weight"], P[pre + "norm3.bias"])
 
@@ -200,12 +207,14 @@ def towers(f, P, pre, cfg: HeadConfig):
 
 def head_forward(P: Dict[str, torch.Tensor], features: List[List[torch.Tensor]],
                  init_masks: List[torch.Tensor], pos: Optional[List[List[torch.Tensor]]],
-                 cfg: HeadConfig = HeadConfig(), capture: Optional[dict] = None):
+                 cfg: HeadConfig = HeadConfig(), capture: Optional[dict] = None,
+                 stage_slots_in: Optional[List[Optional[List[torch.Tensor]]]] = None):
     """MultiScaleDynamicMaskHead.forward, dynamic_mask_head.py:138-228 (bs == 1).
 
     features  T x L x [1,128,h_l,w_l];  init_masks T x [N,C];  pos T x L x [1,C,h_l,w_l] | None
     returns ( T x [S,1,N,num_classes],  T x [S,1,N,C],  T x L x [1,C,h_l,w_l] )
     ``capture`` (optional dict) receives per-stage inputs/outputs for teacher-forced parity.
+    ``stage_slots_in[s][t]`` (optional) replaces the slots entering stage s of frame t (teacher forcing).
     """
     T = len(features)
     L = len(cfg.per_dh_num_heads)
@@ -222,13 +231,15 @@ def head_forward(P: Dict[str, torch.Tensor], features: List[List[torch.Tensor]],
         fused.append(x)
         for j in range(cfg.per_dh_num_heads[l]):
             pre = f"head_series_{l}.{j}."
+            if stage_slots_in is not None and stage_slots_in[stage] is not None:
+                slots = [v.to(slots[t].dtype) if v is not None else slots[t] for t, v in enumerate(stage_slots_in[stage])]
             if capture is not None:
                 capture[f"stage{stage}.slots_in"] = [s.clone() for s in slots]
             f = [stage_till_ffn(slots[t], x[t], None if pos is None else pos[t][l][0], P, pre, cfg)
                  for t in range(T)]
             if stage in cfg.temporal_stages:
                 X = torch.cat(f, 0)
-                Y = X + video_retriever(X, P, pre)
+                Y = X + video_retriever(X, P, pre, cfg.temporal_activation)
                 f = list(Y.split(Y.shape[0] // T, 0))
             for t in range(T):
                 c, e = towers(f[t], P, pre, cfg)

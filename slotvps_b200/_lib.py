@@ -80,7 +80,13 @@ class HeadDesc(C.Structure):
         ("heads_per_level", C.c_int32 * MAX_LEVELS), ("h", C.c_int32 * MAX_LEVELS), ("w", C.c_int32 * MAX_LEVELS),
         ("num_classes", C.c_int32), ("dim_feedforward", C.c_int32), ("temporal_dim_feedforward", C.c_int32),
         ("nhead", C.c_int32), ("temporal_mask", C.c_int32), ("pos_mode", C.c_int32), ("kernel_path", C.c_int32),
+        ("ffn_act", C.c_int32), ("temporal_ffn_act", C.c_int32),
     ]
+
+
+class HeadOpts(C.Structure):
+    _fields_ = [("stage_slots_in", C.POINTER(C.c_void_p)), ("skip_fused_mask", C.c_int32), ("feat_bn_scale", C.c_void_p),
+                ("feat_bn_shift", C.c_void_p), ("rnorm_ss", C.c_void_p)]
 
 
 class FusionCfg(C.Structure):
@@ -99,6 +105,10 @@ SYMBOLS = {
     "slotvps_prepare_weights_ex": (C.c_int, [C.POINTER(HeadDesc), C.POINTER(StageParams), P, P, P, P, P, P]),
     "slotvps_head_forward": (C.c_int, [C.POINTER(HeadDesc), C.POINTER(StageParams), P, C.POINTER(P), C.POINTER(P),
                                        C.POINTER(P), P, P, C.POINTER(P), P, C.c_size_t, P]),
+    "slotvps_head_forward_ex": (C.c_int, [C.POINTER(HeadDesc), C.POINTER(StageParams), P, C.POINTER(P), C.POINTER(P),
+                                          C.POINTER(P), P, P, C.POINTER(P), P, C.c_size_t, C.POINTER(HeadOpts), P]),
+    "slotvps_head_mask_logits_ex": (C.c_int, [C.POINTER(HeadDesc), P, C.c_size_t, C.c_int, P, P, P, P, P, P, P, P, P, P, C.c_size_t, P]),
+    "slotvps_fold_batchnorm": (C.c_int, [P, P, P, P, C.c_int, P, P, P]),
     "slotvps_level_fuse": (C.c_int, [P, P, P, P, P, C.c_int, C.c_int, P, P]),
     "slotvps_slot_attention": (C.c_int, [C.POINTER(StageParams), P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, P,
                                          C.c_size_t, P]),

@@ -22,7 +22,8 @@ thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
 thread_local bool g_prof_on = false;
 
-struct ProfRec { const char* name; cudaEvent_t ev; };
+struct ProfRec { const char* name; cudaEvent_t ev; int grid; };
+thread_local int g_prof_grid = 0;           // CTAs of the launch about to be marked (set by the persistent-kernel launchers)
 static thread_local std::vector<ProfRec> g_prof;
 static thread_local std::vector<cudaEvent_t> g_prof_pool;
 void prof_mark(const char* name, cudaStream_t s) {
@@ -30,8 +31,13 @@ void prof_mark(const char* name, cudaStream_t s) {
   if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); }
   else if (cudaEventCreate(&e) != cudaSuccess) return;
   cudaEventRecord(e, s);
-  g_prof.push_back({name, e});
+  g_prof.push_back({name, e, g_prof_grid});
+  g_prof_grid = 0;
 }
+
+// epilogue activation codes of linear_fast / sgemm: 1 relu, 2 exact (erf) GELU
+static int ffn_act_of(const slotvps_head_desc* d) { return d->ffn_act == 1 ? 1 : 2; }                    // default: "gelu" (r50_fpn_slotvps.py:33)
+static int temporal_ffn_act_of(const slotvps_head_desc* d) { return d->temporal_ffn_act == 2 ? 2 : 1; }  // default: "relu" (r50_fpn_slotvps.py:49)
 
 static int n_stages_of(const slotvps_head_desc* d) {
   int s = 0;
@@ -53,6 +59,7 @@ static int validate(const slotvps_head_desc* d) {
     if (l > 0) SV_REQUIRE(d->h[l] == 2 * d->h[l - 1] && d->w[l] == 2 * d->w[l - 1], "each level must be 2x the previous");
   }
   SV_REQUIRE(d->pos_mode >= 0 && d->pos_mode <= 2, "pos_mode");
+  SV_REQUIRE(d->ffn_act >= 0 && d->ffn_act <= 2 && d->temporal_ffn_act >= 0 && d->temporal_ffn_act <= 2, "activation code (0 default, 1 relu, 2 gelu)");
   return SLOTVPS_OK;
 }
 
@@ -323,11 +330,7 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
     const size_t smem = att_fp32_smem_bytes();
 #define SV_ATT(NBV)                                                                                                  \
     {                                                                                                                  \
-      static bool attr_done = false;                                                                                   \
-      if (!attr_done) {                                                                                                \
-        SV_CHECK_CUDA(cudaFuncSetAttribute(slot_attn_fp32_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        attr_done = true;                                                                                              \
-      }                                                                                                                \
+      SV_TRY(ensure_dyn_smem((const void*)slot_attn_fp32_kernel<NBV>, smem));                                         \
       slot_attn_fp32_kernel<NBV><<<ga, 256, smem, s>>>(x, x_bs, pos, pos_bs, w.G, w.g0, w.g1, w.rs_k, w.rs_v, w.Zpart,  \
                                                        w.a0part, w.a1part, N, P, T);                                   \
     }
@@ -352,17 +355,16 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
 static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp, const PreparedStage& ps, const HeadWs& w,
                      const StagePix& px, const float* x, long x_bs, const float* pos, long pos_bs, int h, int wd, bool temporal, bool use_tc,
                      float* cls_out /*[T][S][N][K] base at this stage*/, long cls_frame_stride,
-                     float* emb_out, long emb_frame_stride, cudaStream_t s) {
+                     float* emb_out, long emb_frame_stride, const float* const* slots_in /*[T] or null*/, cudaStream_t s) {
   const int T = d->n_frames, N = d->n_slots, R = T * N, P = h * wd, F = d->dim_feedforward, TF = d->temporal_dim_feedforward;
+  if (slots_in)                                              // teacher forcing: this stage's slots come from the caller
+    for (int t = 0; t < T; ++t)
+      if (slots_in[t]) SV_TRY(dcopy(slots_in[t], w.slots + (long)t * N * C, (long)N * C, s));
   // (1) slot self-attention + norm1  (:346-358)
   SV_TRY(linear_fast(w.slots, sp.in_proj_w, sp.in_proj_b, w.qkv, R, C, 3 * C, 0, nullptr, s));
   {
     size_t smem = (size_t)(2 * N * 33 + 8 * N) * sizeof(float);
-    static size_t attr_smem = 0;
-    if (smem > 48 * 1024 && smem > attr_smem) {
-      SV_CHECK_CUDA(cudaFuncSetAttribute(mha_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_smem = smem;
-    }
+    if (smem > 48 * 1024) SV_TRY(ensure_dyn_smem((const void*)mha_core_kernel, smem));
     mha_core_kernel<<<dim3(d->nhead, T, 4), 256, smem, s>>>(w.qkv, w.mo, N, d->nhead);
     SV_CHECK_LAUNCH("mha_core");
   }
@@ -380,8 +382,8 @@ static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp,
   attn_post_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.Y, w.a0, w.a1, w.p, sp.nv_w, sp.nv_b, ps.bv_c, sp.no_w, sp.no_b,
                                                    sp.norm2_w, sp.norm2_b, nullptr, w.p2, R);
   SV_CHECK_LAUNCH("attn_post");
-  // (5) FFN + norm3 (:379-385), exact GELU
-  SV_TRY(linear_fast(w.p2, sp.lin1_w, sp.lin1_b, w.hdn, R, C, F, 2, nullptr, s));
+  // (5) FFN + norm3 (:379-385); activation = exact GELU (r50 config) or ReLU (swinL config)
+  SV_TRY(linear_fast(w.p2, sp.lin1_w, sp.lin1_b, w.hdn, R, C, F, ffn_act_of(d), nullptr, s));
   SV_TRY(linear_fast(w.hdn, sp.lin2_w, sp.lin2_b, w.qraw, R, F, C, 0, w.p2, s, -1, -1, w.splitk));
   SV_TRY(ln_rows(w.qraw, nullptr, sp.norm3_w, sp.norm3_b, 1, nullptr, w.f, R, 0, s));
   // (6) Video Retriever over the T*N slots of all frames (:308-322, 494-527, 550-572)
@@ -410,7 +412,7 @@ static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp,
     }
     SV_TRY(ln_rows(w.av, nullptr, sp.tq_no_w, sp.tq_no_b, 1, w.f, w.ty, R, 1, s));              // f + relu(LN(av))
     SV_TRY(ln_rows(w.ty, nullptr, sp.tq_norm2_w, sp.tq_norm2_b, 1, nullptr, w.ty, R, 0, s));    // y
-    SV_TRY(linear_fast(w.ty, sp.tq_lin1_w, sp.tq_lin1_b, w.thdn, R, C, TF, 1, nullptr, s));
+    SV_TRY(linear_fast(w.ty, sp.tq_lin1_w, sp.tq_lin1_b, w.thdn, R, C, TF, temporal_ffn_act_of(d), nullptr, s));
     SV_TRY(linear_fast(w.thdn, sp.tq_lin2_w, sp.tq_lin2_b, w.qraw, R, TF, C, 0, w.ty, s, -1, -1, w.splitk));
     SV_TRY(ln_rows(w.qraw, nullptr, sp.tq_norm3_w, sp.tq_norm3_b, 1, w.f, w.f2, R, 0, s));      // X + LN3(...)  (:317)
     fcur = w.f2;
@@ -460,18 +462,19 @@ int slotvps_profile_end(char* buf, size_t cap) {
   SV_CHECK_CUDA(cudaEventSynchronize(g_prof.back().ev));
   std::vector<std::string> names;
   std::vector<double> ms;
-  std::vector<int> cnt;
+  std::vector<int> cnt, grid;
   for (size_t i = 1; i < g_prof.size(); ++i) {
     float t = 0.f;
     SV_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof[i - 1].ev, g_prof[i].ev));
     size_t k = 0;
     for (; k < names.size(); ++k) if (names[k] == g_prof[i].name) break;
-    if (k == names.size()) { names.push_back(g_prof[i].name); ms.push_back(0.0); cnt.push_back(0); }
+    if (k == names.size()) { names.push_back(g_prof[i].name); ms.push_back(0.0); cnt.push_back(0); grid.push_back(0); }
     ms[k] += t; cnt[k] += 1;
+    if (g_prof[i].grid > grid[k]) grid[k] = g_prof[i].grid;
   }
   size_t off = 0;
   for (size_t k = 0; k < names.size(); ++k) {
-    int n = snprintf(buf + off, cap - off, "%s\t%d\t%.6f\n", names[k].c_str(), cnt[k], ms[k]);
+    int n = snprintf(buf + off, cap - off, "%s\t%d\t%.6f\t%d\n", names[k].c_str(), cnt[k], ms[k], grid[k]);
     if (n < 0 || (size_t)n >= cap - off) break;
     off += n;
   }
@@ -561,7 +564,20 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
                          const float* const* feats, const float* const* pos, const float* const* init_query,
                          float* cls_out, float* emb_out, float* const* fused_out, void* workspace,
                          size_t workspace_bytes, void* stream) {
+  return slotvps_head_forward_ex(d, stages, prepared, feats, pos, init_query, cls_out, emb_out, fused_out, workspace, workspace_bytes,
+                                 nullptr, stream);
+}
+
+int slotvps_head_forward_ex(const slotvps_head_desc* d, const slotvps_stage_params* stages, const void* prepared,
+                            const float* const* feats, const float* const* pos, const float* const* init_query,
+                            float* cls_out, float* emb_out, float* const* fused_out, void* workspace,
+                            size_t workspace_bytes, const slotvps_head_opts* opts, void* stream) {
   SV_TRY(validate(d));
+  slotvps_head_opts o;
+  memset(&o, 0, sizeof(o));
+  if (opts) o = *opts;
+  SV_REQUIRE((o.feat_bn_scale == nullptr) == (o.feat_bn_shift == nullptr) && (o.feat_bn_scale == nullptr) == (o.rnorm_ss == nullptr),
+             "feat_bn_scale, feat_bn_shift and rnorm_ss go together");
   SV_REQUIRE(stages && prepared && feats && init_query && cls_out && emb_out && fused_out && workspace, "null argument");
   SV_REQUIRE(d->pos_mode != 1 || pos != nullptr, "pos_mode 1 needs pos tensors");
   cudaStream_t s = (cudaStream_t)stream;
@@ -575,10 +591,12 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
   // frame strides of the caller's fused_out / pos tensors must be uniform per level
   long fstride[SLOTVPS_MAX_LEVELS], pstride[SLOTVPS_MAX_LEVELS];
   for (int l = 0; l < L; ++l) {
-    fstride[l] = T > 1 ? (long)(fused_out[1 * L + l] - fused_out[l]) : 0;
+    const bool skip = (o.skip_fused_mask >> l) & 1;
+    fstride[l] = (T > 1 && !skip) ? (long)(fused_out[1 * L + l] - fused_out[l]) : 0;
     pstride[l] = (d->pos_mode == 1 && T > 1) ? (long)(pos[1 * L + l] - pos[l]) : 0;
     for (int t = 0; t < T; ++t) {
-      SV_REQUIRE(fused_out[t * L + l] == fused_out[l] + t * fstride[l], "fused_out frames of a level must be equally strided");
+      SV_REQUIRE(skip || (fused_out[t * L + l] != nullptr && fused_out[t * L + l] == fused_out[l] + t * fstride[l]),
+                 "fused_out frames of a level must be equally strided");
       if (d->pos_mode == 1) SV_REQUIRE(pos[t * L + l] == pos[l] + t * pstride[l], "pos frames of a level must be equally strided");
     }
   }
@@ -622,6 +640,9 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
     const bool use_tc = d->kernel_path == 0 && tc_supported(d, l);
     const bool all_tc = use_tc;                               // no fp32 kernel touches pos at this level
     const bool fuse_tc = use_tc && (l == 0 || prev_planes);  // the coarse GEMM reads the previous level's planes
+    const bool skip_out = (o.skip_fused_mask >> l) & 1;
+    SV_REQUIRE(!skip_out || (fuse_tc && d->heads_per_level[l] > 0), "skip_fused_mask: level does not run the tensor-core path");
+    SV_REQUIRE(o.rnorm_ss == nullptr || l != L - 1 || fuse_tc, "rnorm_ss needs the tensor-core level fusion on the finest level");
     // Separable-pos mode (x planes only, position terms from tables).  Measured on B200 at 1024x2048: level fusion
     // gets 0.15 ms/step faster (2 planes instead of 4) but the table loads make the statistics / attention epilogues
     // 0.19 ms/step slower, so it is opt-in (SLOTVPS_POS_SEP=1); pos == None always uses it (no tables needed).
@@ -661,7 +682,11 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
       }
       prm.rows = (int)rows; prm.P = P; prm.w = wd; prm.h = h; prm.ksub = 2; prm.a_lo_row = (int)rows;
       prm.bias = l > 0 ? pr.conv_b : pr.conv_b0; prm.y_in = l > 0 ? w.ftc.y : nullptr;
-      prm.out = fused_out[l]; prm.out_bs = fstride[l];
+      prm.out = skip_out ? nullptr : fused_out[l]; prm.out_bs = fstride[l];
+      if (o.rnorm_ss && l == L - 1) {
+        SV_CHECK_CUDA(cudaMemsetAsync(o.rnorm_ss, 0, (size_t)rows * sizeof(float), s));
+        prm.bn_sc = o.feat_bn_scale; prm.bn_sh = o.feat_bn_shift; prm.ss_out = o.rnorm_ss;
+      }
       prm.planes = tcl.planes; prm.plane_stride = rows; prm.x_planes_only = pos_sep ? 1 : 0;
       if (d->pos_mode == 1) { prm.pos = pos[l]; prm.pos_bs = pstride[l]; }
       else if (d->pos_mode == 2) {
@@ -724,7 +749,8 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
     for (int j = 0; j < d->heads_per_level[l]; ++j, ++stage) {
       const bool temporal = (d->temporal_mask >> stage) & 1;
       SV_TRY(run_stage(d, stages[stage], pr.st[stage], w, px[j], fused_out[l], fstride[l], pl, pls, h, wd, temporal, use_tc,
-                       cls_out + (long)stage * N * d->num_classes, cls_fs, emb_out + (long)stage * N * C, emb_fs, s));
+                       cls_out + (long)stage * N * d->num_classes, cls_fs, emb_out + (long)stage * N * C, emb_fs,
+                       o.stage_slots_in ? o.stage_slots_in + (long)stage * T : nullptr, s));
     }
     last_stage_of_level[l] = stage - 1;
   }
@@ -822,6 +848,7 @@ int slotvps_track_step(const float* fc_w, const float* fc_b, int num_fcs, const 
   track::track_score_kernel<<<n_slots, 256, (size_t)(1 + capacity) * sizeof(float), s>>>(t.y_cur, t.y_bank, fusion_meta, n_slots, &t.st->count, capacity,
                                                                                         t.lik, t.mid, nullptr, 0);
   SV_CHECK_LAUNCH("track_score");
+  if ((size_t)capacity * 12 + 4200 > 48 * 1024) SV_TRY(ensure_dyn_smem((const void*)track::track_assign_kernel, (size_t)capacity * 12));
   track::track_assign_kernel<<<1, 256, (size_t)capacity * 12, s>>>(t.st, t.bank, capacity, embedding, fusion_meta, n_slots, t.lik, t.mid, track_out);
   SV_CHECK_LAUNCH("track_assign");
   return SLOTVPS_OK;
@@ -926,6 +953,23 @@ __global__ void __launch_bounds__(256) mask_prep_kernel(const float* __restrict_
   if (c == 0) { float a = 0.f; for (int i = 0; i < 8; ++i) a += red[i]; dn[n] = a; }
 }
 
+// eval-mode BatchNorm as a per-channel affine: scale = w / sqrt(var + eps), shift = b - mean * scale (same expressions as mask_prep_kernel)
+__global__ void __launch_bounds__(256) bn_fold_kernel(const float* __restrict__ bw, const float* __restrict__ bb, const float* __restrict__ bm,
+                                                      const float* __restrict__ bv, float* __restrict__ sc, float* __restrict__ sh, int n) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= n) return;
+  const float s = bw[c] / sqrtf(bv[c] + BN_EPS);
+  sc[c] = s; sh[c] = bb[c] - bm[c] * s;
+}
+int slotvps_fold_batchnorm(const float* w, const float* b, const float* mean, const float* var, int n, float* scale, float* shift, void* stream) {
+  SV_REQUIRE(w && b && mean && var && scale && shift && n > 0, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
+  bn_fold_kernel<<<ceil_div(n, 256), 256, 0, s>>>(w, b, mean, var, scale, shift, n);
+  SV_CHECK_LAUNCH("bn_fold");
+  return SLOTVPS_OK;
+}
+
 int slotvps_mask_logits_workspace_bytes(int n_slots, int h, int w, size_t* bytes) {
   SV_REQUIRE(bytes && n_slots > 0 && h > 0 && w > 0, "bad argument");
   Arena a(nullptr, (size_t)-1);
@@ -970,8 +1014,18 @@ int slotvps_mask_logits(const float* feat, const float* emb, const float* bw, co
 int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, size_t head_workspace_bytes, int frame, const float* feat,
                              const float* emb, const float* bw, const float* bb, const float* bm, const float* bv, const float* fg_bn,
                              float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return slotvps_head_mask_logits_ex(d, head_workspace, head_workspace_bytes, frame, feat, nullptr, emb, bw, bb, bm, bv, fg_bn, out, workspace,
+                                     workspace_bytes, stream);
+}
+
+// feat: the fp32 feature (per-pixel norm computed here), or NULL with rnorm_ss = the per-pixel squared norms the level-fusion
+// epilogue of the preceding slotvps_head_forward_ex accumulated ([T][P]; frame `frame` is used).
+int slotvps_head_mask_logits_ex(const slotvps_head_desc* d, void* head_workspace, size_t head_workspace_bytes, int frame, const float* feat,
+                                const float* rnorm_ss, const float* emb, const float* bw, const float* bb, const float* bm, const float* bv,
+                                const float* fg_bn, float* out, void* workspace, size_t workspace_bytes, void* stream) {
   SV_TRY(validate(d));
-  SV_REQUIRE(head_workspace && feat && emb && bw && bb && bm && bv && fg_bn && out && workspace, "null argument");
+  SV_REQUIRE(head_workspace && emb && bw && bb && bm && bv && fg_bn && out && workspace, "null argument");
+  SV_REQUIRE((feat != nullptr) != (rnorm_ss != nullptr), "exactly one of feat / rnorm_ss");
   SV_REQUIRE(frame >= 0 && frame < d->n_frames, "frame out of range");
   const int l = d->n_levels - 1, N = d->n_slots, h = d->h[l], w = d->w[l], P = h * w;
   if (!(d->kernel_path == 0 && tc_supported(d, l))) return fail(SLOTVPS_EUNSUPPORTED, "planes unavailable%s%s");
@@ -987,9 +1041,14 @@ int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, s
   if (!a.ok()) return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
   mask_prep_kernel<<<N, 256, 0, s>>>(emb, bw, bb, bm, bv, fg_bn, sc, sh, e2, dn, aff, N);
   SV_CHECK_LAUNCH("mask_prep");
-  if (P % 4 == 0 && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)rn & 15) == 0) feat_rnorm4_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
-  else feat_rnorm_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
-  SV_CHECK_LAUNCH("feat_rnorm");
+  const float* rnp = rn;
+  if (feat) {
+    if (P % 4 == 0 && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)rn & 15) == 0) feat_rnorm4_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
+    else feat_rnorm_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
+    SV_CHECK_LAUNCH("feat_rnorm");
+  } else {
+    rnp = rnorm_ss + (long)frame * P;
+  }
   const long rows = (long)d->n_frames * P;
   // the finest level used the alternate plane set iff the head call ran the overlapped schedule (recorded by it)
   const __half* planes = g_last_head_alt ? hw.tc.planes_alt : hw.tc.planes;
@@ -999,7 +1058,7 @@ int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, s
     const int ng = base + (g < extra ? 1 : 0);
     g_planes_kernel<<<(unsigned)(((long)mask::NROW * C + 255) / 256), 256, 0, s>>>(e2, ep, ng, 1, n0, N);
     SV_CHECK_LAUNCH("g_planes");
-    SV_TRY(mask_tc_launch(planes, 2 * rows, rows, (long)frame * P, ep, dn + n0, rn, aff, out + (long)n0 * P, ng, P, s));
+    SV_TRY(mask_tc_launch(planes, 2 * rows, rows, (long)frame * P, ep, dn + n0, rnp, aff, out + (long)n0 * P, ng, P, s, feat ? 0 : 1));
     n0 += ng;
   }
   return SLOTVPS_OK;

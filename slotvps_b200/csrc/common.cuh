@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <vector>
 
 #include "../../include/slotvps_b200.h"
 
@@ -22,6 +23,7 @@ extern thread_local int64_t g_launches;
 // event on its stream right after the kernel; durations are differences of consecutive events.
 void prof_mark(const char* name, cudaStream_t s);
 extern thread_local bool g_prof_on;
+extern thread_local int g_prof_grid;      // grid size (CTAs) of the next marked launch, 0 = not recorded
 
 inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
   snprintf(g_err, sizeof(g_err), fmt, a, b);
@@ -60,6 +62,25 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
     int _r = (expr);                                                                   \
     if (_r != SLOTVPS_OK) return _r;                                                   \
   } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (context) attribute: remember (function, device, bytes)
+// per host thread instead of a process-wide flag, so a second GPU in the same process gets its own call.
+inline int ensure_dyn_smem(const void* fn, size_t bytes) {
+  struct Done { const void* fn; int dev; size_t bytes; };
+  static thread_local std::vector<Done> done;
+  int dev = 0;
+  SV_CHECK_CUDA(cudaGetDevice(&dev));
+  for (auto& d : done)
+    if (d.fn == fn && d.dev == dev) {
+      if (d.bytes >= bytes) return SLOTVPS_OK;
+      SV_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      d.bytes = bytes;
+      return SLOTVPS_OK;
+    }
+  SV_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  done.push_back({fn, dev, bytes});
+  return SLOTVPS_OK;
+}
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }

@@ -26,7 +26,8 @@ constexpr uint32_t IDESC = tc::make_idesc_f16(128, NPAD, 0, 0);
 
 __global__ void __launch_bounds__(mask::THREADS, 1)
 mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e, const float* __restrict__ dn,
-               const float* __restrict__ rn, const float* __restrict__ aff, float* __restrict__ out, int N, int P, int row0, int lo_row) {
+               const float* __restrict__ rn, const float* __restrict__ aff, float* __restrict__ out, int N, int P, int row0, int lo_row,
+               int rn_is_ss) {
   using namespace mask;
   extern __shared__ uint8_t raw_smem[];
   const uint32_t raw = tc::smem_u32(raw_smem);
@@ -113,7 +114,9 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int g = ti & 1, u = ti >> 1;
       const int p = tile * TILE_M + r;
       const bool pv = p < P;
-      const float scale = pv ? __ldg(rn + p) * sg : 0.f;
+      // rn: 1 / max(||feat_bn(x_p)||, 1e-12), or (rn_is_ss) the squared norm left by the level-fusion epilogue
+      const float rnp = pv ? __ldg(rn + p) : 1.f;
+      const float scale = pv ? (rn_is_ss ? 1.f / fmaxf(sqrtf(rnp), 1e-12f) : rnp) * sg : 0.f;
       tc::mbar_wait(&tfull[g], u & 1);
       tc::tc_fence_after();
 #pragma unroll 1
@@ -138,18 +141,15 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
 // planes: the level's x planes (hi at row 0.., lo at lo_row..), frame rows start at row0; eplanes [2][104][256]
 inline int mask_tc_launch(const __half* planes, long plane_rows_total, long lo_row, long row0, const __half* eplanes, const float* dn,
-                          const float* rn, const float* aff, float* out, int N, int P, cudaStream_t s) {
+                          const float* rn, const float* aff, float* out, int N, int P, cudaStream_t s, int rn_is_ss = 0) {
   CUtensorMap mx, me;
   SV_TRY(tc::make_tmap_h16_sw128(&mx, planes, (uint64_t)4 * plane_rows_total, 64, mask::TILE_M));      // ks-major sub-planes [2][4][rows][64]
   SV_TRY(tc::make_tmap_h16_sw128(&me, eplanes, (uint64_t)2 * mask::NROW, C, mask::NROW));
-  static bool attr_done = false;
-  if (!attr_done) {
-    SV_CHECK_CUDA(cudaFuncSetAttribute(mask_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mask::SMEM_BYTES));
-    attr_done = true;
-  }
+  SV_TRY(ensure_dyn_smem((const void*)mask_tc_kernel, mask::SMEM_BYTES));
   const int n_tiles = ceil_div(P, mask::TILE_M);
   const int grid = n_tiles < main_ctas() ? n_tiles : main_ctas();
-  mask_tc_kernel<<<grid, mask::THREADS, mask::SMEM_BYTES, s>>>(mx, me, dn, rn, aff, out, N, P, (int)row0, (int)lo_row);
+  g_prof_grid = grid;
+  mask_tc_kernel<<<grid, mask::THREADS, mask::SMEM_BYTES, s>>>(mx, me, dn, rn, aff, out, N, P, (int)row0, (int)lo_row, rn_is_ss);
   SV_CHECK_LAUNCH("mask_tc");
   return SLOTVPS_OK;
 }

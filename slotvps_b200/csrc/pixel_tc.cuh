@@ -443,11 +443,7 @@ inline int tc_split_level(const float* x, long x_bs, const float* pos, long pos_
   // planes of a level are packed with stride T*P rows, so a tile's rows past the end of a frame/plane are
   // rows of the next frame/plane (finite) or beyond the tensor (TMA zero fill) -- never stale memory
   const long rows = (long)T * P;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SV_CHECK_CUDA(cudaFuncSetAttribute(split_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_SMEM));
-    attr_done = true;
-  }
+  SV_TRY(ensure_dyn_smem((const void*)split_planes_kernel, SPLIT_SMEM));
   if (sine && !pos) {
     pos_tab_kernel<<<ceil_div(128 * (h + w), 256), 256, 0, s>>>(ws.ytab, ws.xtab, h, w);
     SV_CHECK_LAUNCH("pos_tab");
@@ -467,29 +463,23 @@ inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const flo
   // zero-filled by TMA instead of reading stale memory (NaN bit patterns there corrupt the MMA even against zero weights)
   SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)(ps.enabled ? 2 : 4) * 4 * rows, 64, stats::TILE_M));
   SV_TRY(tc::make_tmap_h16_sw128(&mw, ops.wplanes, (uint64_t)4 * C, C, C));
-  static bool attr_done = false;
-  if (!attr_done) {
-    SV_CHECK_CUDA(cudaFuncSetAttribute(stats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stats::SMEM_BYTES));
-    attr_done = true;
-  }
+  SV_TRY(ensure_dyn_smem((const void*)stats_tc_kernel, stats::SMEM_BYTES));
   const int tiles_per_frame = ceil_div(P, stats::TILE_M);
   const int n_tiles = T * tiles_per_frame;
   static const int use_pairs = getenv("SLOTVPS_STATS_PAIRS") ? atoi(getenv("SLOTVPS_STATS_PAIRS")) : 1;   // CTA pairs by default
   if (use_pairs && n_tiles >= 2 && max_ctas >= 2) {
     CUtensorMap mw2;
     SV_TRY(tc::make_tmap_h16_sw128(&mw2, ops.wplanes, (uint64_t)4 * C, C, 128));
-    static bool attr2_done = false;
-    if (!attr2_done) {
-      SV_CHECK_CUDA(cudaFuncSetAttribute(stats_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stats2::SMEM_BYTES));
-      attr2_done = true;
-    }
+    SV_TRY(ensure_dyn_smem((const void*)stats_tc2_kernel, stats2::SMEM_BYTES));
     int grid2 = 2 * ((n_tiles + 1) / 2);
     if (grid2 > (max_ctas & ~1)) grid2 = max_ctas & ~1;
+    g_prof_grid = grid2;
     stats_tc2_kernel<<<grid2, stats2::THREADS, stats2::SMEM_BYTES, s>>>(mx, mw2, bk_c, bv_c, rs_k, rs_v, P, T, (int)rows, tiles_per_frame, ps);
     SV_CHECK_LAUNCH("stats_tc");
     return SLOTVPS_OK;
   }
   const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+  g_prof_grid = grid;
   stats_tc_kernel<<<grid, stats::THREADS, stats::SMEM_BYTES, s>>>(mx, mw, bk_c, bv_c, rs_k, rs_v, P, T, (int)rows, tiles_per_frame, ps);
   SV_CHECK_LAUNCH("stats_tc");
   return SLOTVPS_OK;
@@ -1223,11 +1213,8 @@ template <int MODE>
 inline int attn_tc_launch(const CUtensorMap& mx, const CUtensorMap& mg, const float* g0, const float* g1, const float* rs_k, const float* rs_v,
                           float* Zpart, float* a0part, float* a1part, const __half* planes, int N, int P, int T, long rows, int chunks,
                           const PosSep& ps, const SlotGroup& grp, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    SV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-    attr_done = true;
-  }
+  SV_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<MODE>, attn::SMEM_BYTES));
+  g_prof_grid = chunks * T;
   attn_tc_kernel<MODE><<<dim3(chunks, T), attn::THREADS, attn::SMEM_BYTES, s>>>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, planes, N, P, T,
                                                                                 (int)rows, ceil_div(P, attn::TILE_M),
                                                                                 getenv("SLOTVPS_TC_DEBUG") ? atoi(getenv("SLOTVPS_TC_DEBUG")) : 0, ps, grp);
@@ -1254,11 +1241,8 @@ inline int tc_attention(const TcWorkspace& ws, __half* gplanes, const float* G, 
     static const int use_pairs = getenv("SLOTVPS_ATTN_PAIRS") ? atoi(getenv("SLOTVPS_ATTN_PAIRS")) : 0;
     if (use_pairs && chunks >= 2 && chunks % 2 == 0) {      // CTA pairs along x: S as one M = 256 MMA, G split across the pair
       SV_TRY(tc::make_tmap_h16_sw128(&mg, gplanes, (uint64_t)T * 2 * attn::NROW, C, attn2::NHALF));
-      static bool attr2_done = false;
-      if (!attr2_done) {
-        SV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn2::SMEM_BYTES));
-        attr2_done = true;
-      }
+      SV_TRY(ensure_dyn_smem((const void*)attn_tc2_kernel, attn2::SMEM_BYTES));
+      g_prof_grid = chunks * T;
       attn_tc2_kernel<<<dim3(chunks, T), attn2::THREADS, attn2::SMEM_BYTES, s>>>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, ws.planes, N, P, T,
                                                                                  (int)rows, ceil_div(P, attn::TILE_M), 0, ps, SlotGroup());
       SV_CHECK_LAUNCH("attn_tc");

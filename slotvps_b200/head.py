@@ -52,8 +52,9 @@ class _TemporalParams(nn.Module):
 
     def __init__(self, d_model, dim_feedforward=2048, dropout=0.1, activation="relu", softmax_dim="slots", drop_path=0.):
         super().__init__()
-        if activation != "relu" or softmax_dim != "slots":
-            raise NotImplementedError("B200 Video Retriever supports activation='relu', softmax_dim='slots' (the shipped config)")
+        if activation not in ("relu", "gelu") or softmax_dim != "slots":
+            raise NotImplementedError("B200 Video Retriever supports activation 'relu' (r50 config) / 'gelu' (swinL config), softmax_dim='slots'")
+        self.activation = activation
         self.inst_interact = _RetrieverParams(d_model)
         self.linear1, self.linear2 = nn.Linear(d_model, dim_feedforward), nn.Linear(dim_feedforward, d_model)
         self.norm1, self.norm2, self.norm3 = nn.LayerNorm(d_model), nn.LayerNorm(d_model), nn.LayerNorm(d_model)
@@ -109,7 +110,7 @@ class B200DynamicMaskHead(nn.Module):
         unsupported = []
         if dh_dim != 256: unsupported.append("dh_dim != 256")
         if nhead != 8: unsupported.append("nhead != 8")
-        if activation != "gelu": unsupported.append("activation != 'gelu'")
+        if activation not in ("gelu", "relu"): unsupported.append("activation not in ('gelu', 'relu')")
         if merge_operation != "concat" or trans_in_dim != 384: unsupported.append("merge_operation/trans_in_dim != concat/384")
         if softmax_dim != "slots": unsupported.append("softmax_dim != 'slots'")
         if dropout != 0.0 or drop_path != 0.0: unsupported.append("dropout/drop_path != 0")
@@ -119,6 +120,8 @@ class B200DynamicMaskHead(nn.Module):
             raise NotImplementedError("B200DynamicMaskHead: " + ", ".join(unsupported))
         self.dh_dim, self.trans_in_dim, self.num_classes = dh_dim, trans_in_dim, num_classes
         self.dim_feedforward, self.nhead = dim_feedforward, nhead
+        self.activation = activation                                    # r50 config: "gelu"; swinL config: "relu"
+        self.temporal_activation = (temporal_query_attention_config or {}).get("activation", "relu")
         self.per_dh_num_heads = list(per_dh_num_heads)
         self.feat_num_levels = feat_num_levels
         self.apply_temporal_query_atten_stages = apply_temporal_query_atten_stages
@@ -181,6 +184,8 @@ class B200DynamicMaskHead(nn.Module):
         for s in (self.apply_temporal_query_atten_stages or []):
             mask |= 1 << s
         d.temporal_mask, d.pos_mode, d.kernel_path = mask, pos_mode, self.kernel_path
+        d.ffn_act = {"relu": 1, "gelu": 2}[self.activation]
+        d.temporal_ffn_act = {"relu": 1, "gelu": 2}[self.temporal_activation]
         return d
 
     def fold_input_transform(self, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor]):
@@ -227,10 +232,18 @@ class B200DynamicMaskHead(nn.Module):
 
     # -- forward ------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, features, init_masks, pad_mask, pos=None, query_pos=None, gt_non_void_mask=None):
+    def forward(self, features, init_masks, pad_mask, pos=None, query_pos=None, gt_non_void_mask=None, *,
+                stage_slots_in=None, skip_fused=False, feat_bn=None):
         """dynamic_mask_head.py:138.  features T x L x [1,128,h,w]; init_masks T x [N,256];
         pos T x L x [1,256,h,w] | None | "sine" (generate PositionEmbeddingSine on device).
-        Returns (T x [S,1,N,num_classes], T x [S,1,N,256], T x L x [1,256,h,w])."""
+        Returns (T x [S,1,N,num_classes], T x [S,1,N,256], T x L x [1,256,h,w]).
+
+        Keyword-only extras (not in the reference; slotvps_head_opts of the C ABI):
+        ``stage_slots_in`` S x T x [N,256] | None entries: teacher forcing, the slots entering stage s (parity tests);
+        ``skip_fused``: do not materialise the fp32 fused features (third return value becomes None entries) when every
+        level runs the tensor-core path -- the L2 integration only needs the finest level, through the operand planes;
+        ``feat_bn`` (scale [256], shift [256]): also accumulate the per-pixel squared norm of feat_bn(x) of the finest
+        level (kept in ``self._last_call``) for the mask-logit kernel."""
         assert pad_mask is None
         assert query_pos is None
         assert gt_non_void_mask is None
@@ -266,16 +279,39 @@ class B200DynamicMaskHead(nn.Module):
             pos_ptrs = (C.c_void_p * (T * L))(*[pos_l[l][t].data_ptr() for t in range(T) for l in range(L)])
         else:
             pos_l, pos_ptrs = None, None
-        fused = [torch.empty((T, 1, self.dh_dim) + shapes[l], dtype=torch.float32, device=dev) for l in range(L)]
+        all_tc = self.kernel_path == 0 and all(shapes[l][0] * shapes[l][1] >= 128 and self.per_dh_num_heads[l] > 0 for l in range(L))
+        skip = bool(skip_fused) and all_tc
+        opts = _lib.HeadOpts()
+        keep_alive = []
+        if skip:
+            opts.skip_fused_mask = (1 << L) - 1
+        fused = [None if skip else torch.empty((T, 1, self.dh_dim) + shapes[l], dtype=torch.float32, device=dev) for l in range(L)]
+        rnorm_ss = None
+        if feat_bn is not None and all_tc:
+            sc, sh = (f32c(v) for v in feat_bn)
+            rnorm_ss = torch.empty((T, shapes[-1][0] * shapes[-1][1]), dtype=torch.float32, device=dev)
+            opts.feat_bn_scale, opts.feat_bn_shift, opts.rnorm_ss = sc.data_ptr(), sh.data_ptr(), rnorm_ss.data_ptr()
+            keep_alive += [sc, sh]
+        if stage_slots_in is not None:
+            assert len(stage_slots_in) == S
+            tf = (C.c_void_p * (S * T))()
+            for s_ in range(S):
+                for t in range(T):
+                    v = None if stage_slots_in[s_] is None else stage_slots_in[s_][t]
+                    if v is not None:
+                        v = f32c(v.reshape(N, self.dh_dim).to(dev))
+                        keep_alive.append(v)
+                        tf[s_ * T + t] = v.data_ptr()
+            opts.stage_slots_in = C.cast(tf, C.POINTER(C.c_void_p))
         cls = torch.empty((T, S, 1, N, self.num_classes), dtype=torch.float32, device=dev)
         emb = torch.empty((T, S, 1, N, self.dh_dim), dtype=torch.float32, device=dev)
         feat_ptrs = (C.c_void_p * (T * L))(*[t.data_ptr() for t in feats])
         q_ptrs = (C.c_void_p * T)(*[q.data_ptr() for q in queries])
-        fused_ptrs = (C.c_void_p * (T * L))(*[fused[l][t].data_ptr() for t in range(T) for l in range(L)])
-        _lib.check(_lib.lib().slotvps_head_forward(
+        fused_ptrs = (C.c_void_p * (T * L))(*[None if fused[l] is None else fused[l][t].data_ptr() for t in range(T) for l in range(L)])
+        _lib.check(_lib.lib().slotvps_head_forward_ex(
             C.byref(d), table, prepared.data_ptr(), feat_ptrs, pos_ptrs, q_ptrs, cls.data_ptr(), emb.data_ptr(),
-            fused_ptrs, ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "slotvps_head_forward")
-        del pos_l
-        self._last_call = (d, ws)          # the finest level's operand planes stay valid in ws until the next forward
+            fused_ptrs, ws.data_ptr(), ws.numel(), C.byref(opts), _stream_ptr(dev)), "slotvps_head_forward")
+        del pos_l, keep_alive
+        self._last_call = (d, ws, rnorm_ss)   # the finest level's operand planes stay valid in ws until the next forward
         return ([cls[t] for t in range(T)], [emb[t] for t in range(T)],
-                [[fused[l][t] for l in range(L)] for t in range(T)])
+                [[None if fused[l] is None else fused[l][t] for l in range(L)] for t in range(T)])

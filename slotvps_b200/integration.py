@@ -53,6 +53,45 @@ def make_b200_detector(base, Instances):
                     d[f"{name}.{k}"] = getattr(bn, k)
             return d
 
+        def _feat_bn_affine(self):
+            from . import _lib
+            from .head import _stream_ptr
+            bn = self.image_model.feat_bn
+            key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
+            if getattr(self, "_b200_bn_fold", None) is None or self._b200_bn_fold[0] != key:
+                sc, sh = torch.empty_like(bn.weight.data), torch.empty_like(bn.weight.data)
+                _lib.check(_lib.lib().slotvps_fold_batchnorm(bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                                                             bn.running_var.data_ptr(), 256, sc.data_ptr(), sh.data_ptr(),
+                                                             _stream_ptr(sc.device)), "slotvps_fold_batchnorm")
+                self._b200_bn_fold = (key, sc, sh)
+            return self._b200_bn_fold[1], self._b200_bn_fold[2]
+
+        def _mask_logits_after_head(self, feat, emb, bn, frame):
+            """Mask logits of the current frame: from the operand planes + fused-epilogue norms the head call left behind
+            (tensor-core path), else through the generic fp32 entry on the returned feature."""
+            import ctypes as C
+            from . import _lib
+            from .head import _stream_ptr
+            last = self.image_model.dynamic_mask_head._last_call
+            d, hws, rnorm_ss = last
+            if rnorm_ss is None:
+                return mask_logits(feat[0], emb, bn)
+            l = d.n_levels - 1
+            N, dev = emb.shape[-2], emb.device
+            L = _lib.lib()
+            fg = torch.cat([bn["fg_bn.weight"].reshape(1), bn["fg_bn.bias"].reshape(1), bn["fg_bn.running_mean"].reshape(1),
+                            bn["fg_bn.running_var"].reshape(1)]).float().contiguous()
+            nbytes = C.c_size_t()
+            _lib.check(L.slotvps_mask_logits_workspace_bytes(N, d.h[l], d.w[l], C.byref(nbytes)), "mask_logits_workspace_bytes")
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            out = torch.empty((N, d.h[l], d.w[l]), dtype=torch.float32, device=dev)
+            _lib.check(L.slotvps_head_mask_logits_ex(C.byref(d), hws.data_ptr(), hws.numel(), frame, None, rnorm_ss.data_ptr(),
+                                                     emb.reshape(N, 256).contiguous().data_ptr(), bn["feat_bn.weight"].data_ptr(),
+                                                     bn["feat_bn.bias"].data_ptr(), bn["feat_bn.running_mean"].data_ptr(),
+                                                     bn["feat_bn.running_var"].data_ptr(), fg.data_ptr(), out.data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "slotvps_head_mask_logits_ex")
+            return out
+
         def generate_final_outputs(self, dh_head_input_feats, outputs_masks, generate_aux_output=True):
             """vps_temporal_slots.py:144-194 with generate_aux_output=False (the inference setting)."""
             if generate_aux_output:
@@ -73,9 +112,13 @@ def make_b200_detector(base, Instances):
             ct = im.conv_trans
             foldable = (not getattr(ct, "with_norm", False) and not getattr(ct, "with_activatation", False)
                         and ct.conv.kernel_size == (1, 1) and ct.conv.bias is not None)
-            if foldable and getattr(self, "_b200_folded", None) is not ct.conv.weight:
-                im.dynamic_mask_head.fold_input_transform(ct.conv.weight, ct.conv.bias)
-                self._b200_folded = ct.conv.weight
+            if foldable:
+                # re-fold whenever the transform's parameters change (in-place updates bump ``_version``; a new tensor
+                # changes ``data_ptr``): load_checkpoint / load_state_dict after the first call must not leave stale planes
+                fkey = (ct.conv.weight.data_ptr(), ct.conv.weight._version, ct.conv.bias.data_ptr(), ct.conv.bias._version)
+                if getattr(self, "_b200_folded", None) != fkey:
+                    im.dynamic_mask_head.fold_input_transform(ct.conv.weight, ct.conv.bias)
+                    self._b200_folded = fkey
             feats = []
             for x in (ref, img):
                 y = im.backbone(x)
@@ -83,12 +126,16 @@ def make_b200_detector(base, Instances):
                 fcn_output, _, fcn_feature = self.extract_semantic_feats(y)
                 feats.append(list(fcn_feature) if foldable else [ct(f) for f in fcn_feature])
             q = im.init_mask_query.weight
+            bn = self._bn_dict()
             cls, emb, fused = im.dynamic_mask_head(features=feats, init_masks=[q, q], pad_mask=None, pos="sine",
-                                                   query_pos=None, gt_non_void_mask=None)
+                                                   query_pos=None, gt_non_void_mask=None, skip_fused=True,
+                                                   feat_bn=self._feat_bn_affine())
             H, W = int(meta["ori_shape"][0]), int(meta["ori_shape"][1])
-            pm = mask_logits(fused[-1][-1][0], emb[-1][-1, 0], self._bn_dict())
+            pm = self._mask_logits_after_head(fused[-1][-1], emb[-1][-1, 0], bn, frame=1)
             fo = self.postprocess_panoptic.fuse(cls[-1][-1, 0], pm, (H, W))
             h = fo.host()
+            if not h["converged"]:
+                raise RuntimeError("small-segment filter did not converge within max_iters")
             if h["k"] == 0:
                 raise ValueError("no slot survives the score/class filter (the reference raises here as well)")
             # tracker (vps_temporal_slots.py:232-237, :332-409): object bank and greedy assignment on the device

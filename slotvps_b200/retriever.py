@@ -127,12 +127,18 @@ class PanopticFusion(nn.Module):
     """
 
     def __init__(self, is_thing_map=None, threshold=0.85, output_dir="", debug=False, fraction_threshold=0.03,
-                 pixel_threshold=0.4, apply_mask_removal=True, apply_mask_removal_only_ins=True,
+                 pixel_threshold=0.4, apply_mask_removal=False, apply_mask_removal_only_ins=False,
                  use_mask_low_constant=False, catgories_color=None, filter_small_option='4', num_classes=20,
                  num_stuff=11, max_iters=6):
         super().__init__()
+        # defaults as in the reference (vps_temporal_slots.py:532-536: both mask-removal switches default to False); the
+        # device kernels implement what configs/cityscapes/*_slotvps.py ship (:66-74: both True), anything else raises
         if not (apply_mask_removal and apply_mask_removal_only_ins) or use_mask_low_constant or filter_small_option != '4':
-            raise NotImplementedError("PanopticFusion implements the shipped postprocess_panoptic configuration only")
+            raise NotImplementedError("PanopticFusion implements the shipped postprocess_panoptic configuration only "
+                                      "(apply_mask_removal=True, apply_mask_removal_only_ins=True, use_mask_low_constant=False, "
+                                      "filter_small_option='4')")
+        if not pixel_threshold > 1.0 / 3.0:
+            raise NotImplementedError("pixel_threshold must be > 1/3: the exact two-pass mask_removal keeps at most two candidates per pixel")
         if is_thing_map is not None:
             for c, t in is_thing_map.items():
                 if bool(t) != (c > num_stuff - 1):
@@ -225,43 +231,69 @@ class SlotVPSRetriever(nn.Module):
         bn = self._bn_dict()
         last = self.dynamic_mask_head._last_call
         if last is not None:
-            d, hws = last
-            feat = feat.reshape(256, *feat.shape[-2:])
-            h, w = feat.shape[-2:]
+            d, hws, rnorm_ss = last
+            if feat is not None:
+                feat = feat.reshape(256, *feat.shape[-2:])
+            h, w = d.h[d.n_levels - 1], d.w[d.n_levels - 1]
             N = emb.shape[-2]
+            dev = emb.device
             L = _lib.lib()
             fg_pack = torch.cat([bn["fg_bn.weight"].reshape(1), bn["fg_bn.bias"].reshape(1),
                                  bn["fg_bn.running_mean"].reshape(1), bn["fg_bn.running_var"].reshape(1)]).float().contiguous()
             nbytes = C.c_size_t()
             _lib.check(L.slotvps_mask_logits_workspace_bytes(N, h, w, C.byref(nbytes)), "mask_logits_workspace_bytes")
-            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=feat.device)
-            out = torch.empty((N, h, w), dtype=torch.float32, device=feat.device)
-            rc = L.slotvps_head_mask_logits(C.byref(d), hws.data_ptr(), hws.numel(), frame, feat.contiguous().data_ptr(),
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            out = torch.empty((N, h, w), dtype=torch.float32, device=dev)
+            rc = L.slotvps_head_mask_logits_ex(C.byref(d), hws.data_ptr(), hws.numel(), frame,
+                                            None if rnorm_ss is not None else feat.contiguous().data_ptr(),
+                                            None if rnorm_ss is None else rnorm_ss.data_ptr(),
                                             emb.reshape(N, 256).contiguous().data_ptr(), bn["feat_bn.weight"].data_ptr(),
                                             bn["feat_bn.bias"].data_ptr(), bn["feat_bn.running_mean"].data_ptr(),
                                             bn["feat_bn.running_var"].data_ptr(), fg_pack.data_ptr(), out.data_ptr(),
-                                            ws.data_ptr(), ws.numel(), _stream_ptr(feat.device))
+                                            ws.data_ptr(), ws.numel(), _stream_ptr(dev))
             if rc == 0:
                 return out
-            if rc != -4:
+            if rc != -4 or feat is None:
                 _lib.check(rc, "slotvps_head_mask_logits")
         return mask_logits(feat, emb, bn)
 
+    def _feat_bn_affine(self):
+        """feat_bn (eval) as scale / shift vectors for the level-fusion epilogue (cached per parameter version)."""
+        bn = self.feat_bn
+        key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
+        if getattr(self, "_bn_fold", None) is None or self._bn_fold[0] != key:
+            sc, sh = torch.empty_like(bn.weight.data), torch.empty_like(bn.weight.data)
+            _lib.check(_lib.lib().slotvps_fold_batchnorm(bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                                                         bn.running_var.data_ptr(), 256, sc.data_ptr(), sh.data_ptr(),
+                                                         _stream_ptr(sc.device)), "slotvps_fold_batchnorm")
+            self._bn_fold = (key, sc, sh)
+        return self._bn_fold[1], self._bn_fold[2]
+
     @torch.no_grad()
     def forward(self, features: List[List[torch.Tensor]], size: Tuple[int, int], pos="sine", fuse: bool = True,
-                fusion_logits: Optional[torch.Tensor] = None, panoptic_out: Optional[torch.Tensor] = None):
+                fusion_logits: Optional[torch.Tensor] = None, panoptic_out: Optional[torch.Tensor] = None,
+                want_feats: bool = True, fusion_masks: Optional[torch.Tensor] = None):
         """features T x 4 x [1,128,h,w] (reference frame order: [ref, cur]); size = (H,W) of the image.
         Returns dict(cls, emb, feats, pred_masks [N,h,w], fusion: FusionOutput) -- all on device.
         ``fusion_logits`` [N,num_classes] replaces the head's last-stage class logits at the fusion
-        input (random-init heads keep no slot; benchmarks and tests use designed ones)."""
+        input (random-init heads keep no slot; benchmarks and tests use designed ones).
+        ``want_feats=False`` (what simple_test needs: it only consumes the finest level, vps_temporal_slots.py:297-299):
+        the fp32 fused features (the head's third return value) are not materialised when every level runs the
+        tensor-core path; the mask logits come from the operand planes and the per-pixel norm from the fusion epilogue."""
         T = len(features)
         q = self.init_mask_query.weight
-        cls, emb, feats = self.dynamic_mask_head(features, [q] * T, None, pos=pos)
-        pm = self._mask_logits_after_head(feats[-1][-1][0], emb[-1][-1, 0], T - 1)
+        if want_feats:
+            cls, emb, feats = self.dynamic_mask_head(features, [q] * T, None, pos=pos)
+        else:
+            cls, emb, feats = self.dynamic_mask_head(features, [q] * T, None, pos=pos, skip_fused=True, feat_bn=self._feat_bn_affine())
+        f_last = feats[-1][-1]
+        pm = self._mask_logits_after_head(None if f_last is None else f_last[0], emb[-1][-1, 0], T - 1)
         out = dict(cls=cls, emb=emb, feats=feats, pred_masks=pm)
         if fuse:
             lg = cls[-1][-1, 0] if fusion_logits is None else fusion_logits
-            out["fusion"] = self.postprocess_panoptic.fuse(lg, pm, size, out=panoptic_out)
+            # ``fusion_masks`` [N,h,w]: designed mask logits for the fusion stage (benchmarks: a random-init head's masks are
+            # collapsed, so the fusion would see an unrepresentatively easy input); ``pred_masks`` is still computed and returned
+            out["fusion"] = self.postprocess_panoptic.fuse(lg, pm if fusion_masks is None else fusion_masks, size, out=panoptic_out)
         return out
 
 

@@ -32,6 +32,13 @@ HEAD_CASES = {
     "head_t2_n100": dict(T=2, N=100, shapes=[(2, 4), (4, 8), (8, 16), (16, 32)], seed=0),
     "head_t1_n50": dict(T=1, N=50, shapes=[(3, 5), (6, 10), (12, 20), (24, 40)], seed=1),
     "head_t3_n128": dict(T=3, N=128, shapes=[(2, 3), (4, 6), (8, 12), (16, 24)], seed=2),
+    # every level >= 128 pixels: the tensor-core kernels serve ALL levels, and the per-stage outputs double as
+    # teacher-forcing inputs (stage s enters with the reference's stage s-1 embedding, dynamic_mask_head.py:210-211)
+    "head_t2_n100_big": dict(T=2, N=100, shapes=[(8, 16), (16, 32), (32, 64), (64, 128)], seed=4),
+    # the reference's second shipped config (configs/cityscapes/swinL_fpn_slotvps.py:41,56): ReLU stage FFN, GELU temporal FFN
+    "head_swinl": dict(T=2, N=100, shapes=[(8, 16), (16, 32), (32, 64), (64, 128)], seed=5,
+                       overrides={"dynamic_mask_head.activation": "relu",
+                                  "dynamic_mask_head.temporal_query_attention_config.activation": "gelu"}),
 }
 POS_SHAPES = [(2, 4), (16, 32), (34, 60), (7, 5)]
 FUSION_CASES = {
@@ -48,7 +55,7 @@ def ref_pos(model, feat):
     return model.image_model.position_embedding(nested_tensor_from_tensor_list(feat))
 
 
-def gen_head(model, name, T, N, shapes, seed):
+def gen_head(model, name, T, N, shapes, seed, overrides=None):
     head = model.image_model.dynamic_mask_head
     head.load_state_dict(synthetic.make_head_state_dict(seed), strict=True)
     cap = synthetic.make_capsule_params(seed, N)
@@ -271,6 +278,16 @@ def gen_track(model, name, seed, N, h, w, videos, mode):
 
 
 def main():
+    """No argument: regenerate every fixture.  `--only a,b`: just those head cases.  `--check`: regenerate everything into a
+    temporary directory and compare it with the committed files (bit-identical arrays expected)."""
+    global HERE
+    only = None
+    if "--only" in sys.argv:
+        only = sys.argv[sys.argv.index("--only") + 1].split(",")
+    committed = HERE
+    if "--check" in sys.argv:
+        import tempfile
+        HERE = tempfile.mkdtemp(prefix="golden_check_")
     torch.set_num_threads(8)
     model, _ = ref_import.build_model(0)
     for shp in POS_SHAPES:
@@ -278,13 +295,18 @@ def main():
         np.savez_compressed(os.path.join(HERE, "pos_%dx%d.npz" % shp), pos=p.numpy())
     fused = emb = cap = None
     for name, c in HEAD_CASES.items():
-        if c["N"] != 100:
-            m2, _ = ref_import.build_model(0, **{"other_config.proposal_num": c["N"]})
+        if only and name not in only:
+            continue
+        if c["N"] != 100 or c.get("overrides"):
+            m2, _ = ref_import.build_model(0, **{"other_config.proposal_num": c["N"], **(c.get("overrides") or {})})
         else:
             m2 = model
         f, e, cp = gen_head(m2, name, **c)
         if name == "head_t2_n100":
             fused, emb, cap = f, e, cp
+    if only:
+        print("golden fixtures written to", HERE)
+        return
     gen_masklogit(model, fused, emb, cap)
     for name, c in FUSION_CASES.items():
         kw = dict(c)
@@ -302,6 +324,16 @@ def main():
         gen_track(m4, name, **c)
         print(name, "done")
     print("golden fixtures written to", HERE)
+    if committed != HERE:
+        bad = 0
+        for f in sorted(os.listdir(committed)):
+            if not f.endswith(".npz"):
+                continue
+            a, b = np.load(os.path.join(committed, f)), np.load(os.path.join(HERE, f))
+            same = set(a.files) == set(b.files) and all(np.array_equal(a[k], b[k]) for k in a.files)
+            print(("identical  " if same else "DIFFERENT  ") + f)
+            bad += 0 if same else 1
+        sys.exit(1 if bad else 0)
 
 
 if __name__ == "__main__":

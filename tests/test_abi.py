@@ -37,7 +37,8 @@ def test_struct_layout_matches_header():
     fields = re.findall(r"\*\s*([a-z_0-9]+)", body)
     assert fields == _lib.STAGE_FIELDS
     assert C.sizeof(_lib.StageParams) == 8 * len(fields)
-    assert C.sizeof(_lib.HeadDesc) == 4 * (3 + 12 + 7)
+    assert C.sizeof(_lib.HeadDesc) == 4 * (3 + 12 + 9)
+    assert C.sizeof(_lib.HeadOpts) == 40
     assert C.sizeof(_lib.FusionCfg) == 32
 
 
@@ -76,8 +77,13 @@ def test_head_mirrors_reference_contract():
     assert head.head_series_2[0].temporal_query_head is not None and head.head_series_3[1].temporal_query_head is not None
     with pytest.raises(AssertionError):
         sv.B200DynamicMaskHead(**{**sv.HEAD_KWARGS, "dh_num_heads": 8})
+    # both shipped configs construct: r50 (gelu / relu) and swinL (relu stage FFN, gelu temporal FFN; swinL_fpn_slotvps.py:41,56)
+    swinl = sv.B200DynamicMaskHead(**{**sv.HEAD_KWARGS, "activation": "relu", "temporal_query_attention_config":
+                                      {**sv.HEAD_KWARGS["temporal_query_attention_config"], "activation": "gelu"}})
+    assert swinl._desc(2, 100, [(8, 16), (16, 32), (32, 64), (64, 128)], 2).ffn_act == 1
+    assert swinl._desc(2, 100, [(8, 16), (16, 32), (32, 64), (64, 128)], 2).temporal_ffn_act == 2
     with pytest.raises(NotImplementedError):
-        sv.B200DynamicMaskHead(**{**sv.HEAD_KWARGS, "activation": "relu"})
+        sv.B200DynamicMaskHead(**{**sv.HEAD_KWARGS, "activation": "glu"})
     # error conventions of the reference forward (dynamic_mask_head.py:167,193-195)
     f = [[torch.zeros(1, 128, 2, 2)] * 4]
     with pytest.raises(AssertionError):
@@ -88,7 +94,11 @@ def test_head_mirrors_reference_contract():
 
 def test_fusion_rejects_unshipped_configs():
     with pytest.raises(NotImplementedError):
-        sv.PanopticFusion(apply_mask_removal=False)
+        sv.PanopticFusion(apply_mask_removal=False, apply_mask_removal_only_ins=True)
+    with pytest.raises(NotImplementedError):
+        sv.PanopticFusion()                                  # the reference's own defaults (both switches False) are not the shipped config
+    with pytest.raises(NotImplementedError):
+        sv.PanopticFusion(**{**sv.FUSION_KWARGS, "pixel_threshold": 0.3})
     with pytest.raises(NotImplementedError):
         sv.PanopticFusion(filter_small_option="4_256")
     sv.PanopticFusion(**sv.FUSION_KWARGS)

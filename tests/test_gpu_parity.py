@@ -36,6 +36,22 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
+DRIFT_X = 5.0        # free-running drift allowed relative to the reference arithmetic's own fp32-vs-fp64 drift on the same inputs
+
+
+def fp32_noise(sd, feats, q, T, shapes, e64, cfg=None, pos=True):
+    """Per-stage drift of the fp32 oracle (the reference's arithmetic) against the fp64 oracle on the same inputs: the
+    noise floor every free-running comparison is measured against (instead of a fixed 3.5^s envelope)."""
+    pos32 = [[O.sine_position_embedding(*s) for s in shapes] for _ in range(T)] if pos else None
+    _, e32, _ = O.head_forward(sd, feats, [q] * T, pos32, cfg or O.HeadConfig())
+    S = e32[0].shape[0]
+    return [max(rel(e32[t][s], e64[t][s]) for t in range(T)) for s in range(S)]
+
+
+def drift_ok(drift, noise, s):
+    return drift <= DRIFT_X * max(noise[s], 2e-6)
+
+
 def stage_dict(sd, pre):
     return {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
 
@@ -140,6 +156,8 @@ def test_head_chain_vs_oracle_and_golden(dev, kernel_path, case, golden_dir):
     head = _mk_head(dev, sd, kernel_path)
     cl, em, fu = head([[f.to(dev) for f in fr] for fr in feats], [q.to(dev)] * c["T"], None, pos="sine")
     rows = []
+    noise = fp32_noise(sd, feats, q, c["T"], c["shapes"], re_)
+    gnoise = [max(rel(gold[f"emb{t}"][s], re_[t][s]) for t in range(c["T"])) for s in range(7)]   # the reference itself vs fp64
     for t in range(c["T"]):
         for l in range(4):
             assert rel(fu[t][l], rf[t][l]) < 1e-5
@@ -148,9 +166,9 @@ def test_head_chain_vs_oracle_and_golden(dev, kernel_path, case, golden_dir):
             eg = rel(em[t][s], gold[f"emb{t}"][s])
             cg = rel(cl[t][s], gold[f"cls{t}"][s])
             rows.append((t, s, e64, eg, cg))
-            env = 1e-5 * 3.5 ** s * 3          # 3x the measured fp32-vs-fp64 envelope (3e-6*3.5^s) + headroom
-            assert e64 < max(env, 2e-5), (t, s, e64)
-            assert eg < max(env, 2e-5) and cg < max(env, 2e-5), (t, s, eg, cg)
+            assert drift_ok(e64, noise, s), (t, s, e64, noise[s])
+            # against the reference's golden: both sides carry their own fp32 drift
+            assert eg <= DRIFT_X * max(noise[s], gnoise[s], 2e-6) and cg <= DRIFT_X * max(noise[s], gnoise[s], 2e-6), (t, s, eg, cg)
     print(f"{case} path={kernel_path}: per-stage emb rel vs fp64 oracle (frame 0):",
           " ".join(f"{r[2]:.1e}" for r in rows[:7]), "| vs reference golden:", " ".join(f"{r[3]:.1e}" for r in rows[:7]))
 
@@ -333,12 +351,13 @@ def test_config5_iteration_sweep(dev, heads, temporal):
     head = _mk_head(dev, sd, 0, dh_num_heads=S, per_dh_num_heads=heads, apply_temporal_query_atten_stages=temporal)
     cl, em, fu = head([[f.to(dev) for f in fr] for fr in feats], [q.to(dev)] * T, None, pos="sine")
     assert em[0].shape == (S, 1, N, 256) and cl[1].shape == (S, 1, N, 20)
+    noise = fp32_noise(sd, feats, q, T, shapes, re_, cfg)
     for t in range(T):
         for l in range(4):
             assert rel(fu[t][l], rf[t][l]) < 1e-5
         for s in range(S):
-            assert rel(em[t][s], re_[t][s]) < max(3e-5 * 3.5 ** s, 3e-5), (t, s, rel(em[t][s], re_[t][s]))
-    print(f"heads={heads}: last-stage emb rel {rel(em[1][-1], re_[1][-1]):.2e}")
+            assert drift_ok(rel(em[t][s], re_[t][s]), noise, s), (t, s, rel(em[t][s], re_[t][s]), noise[s])
+    print(f"heads={heads}: last-stage emb rel {rel(em[1][-1], re_[1][-1]):.2e} (fp32 oracle: {noise[-1]:.2e})")
 
 
 @pytest.mark.parametrize("N", [50, 200, 300])
@@ -354,9 +373,10 @@ def test_config5_slot_sweep(dev, N):
     rc, re_, rf = O.head_forward({k: v.double() for k, v in sd.items()}, [[f.double() for f in fr] for fr in feats], [q.double()] * T, pos64)
     head = _mk_head(dev, sd, 0)
     cl, em, fu = head([[f.to(dev) for f in fr] for fr in feats], [q.to(dev)] * T, None, pos="sine")
+    noise = fp32_noise(sd, feats, q, T, shapes, re_)
     for s in range(7):
-        assert rel(em[1][s], re_[1][s]) < max(3e-5 * 3.5 ** s, 3e-5), (s, rel(em[1][s], re_[1][s]))
-    print(f"N={N}: stage-0 emb rel {rel(em[1][0], re_[1][0]):.2e}, stage-6 {rel(em[1][6], re_[1][6]):.2e}")
+        assert drift_ok(rel(em[1][s], re_[1][s]), noise, s), (s, rel(em[1][s], re_[1][s]), noise[s])
+    print(f"N={N}: stage-0 emb rel {rel(em[1][0], re_[1][0]):.2e}, stage-6 {rel(em[1][6], re_[1][6]):.2e} (fp32 oracle: {noise[6]:.2e})")
 
 
 def test_config4_viper_shape(dev):
@@ -378,9 +398,10 @@ def test_config4_viper_shape(dev):
     lg, _, _ = synthetic.make_fusion_case(13, N, 8, 8)
     size = (270, 480)                                           # unpadded size: 72*4 = 288 rows padded, 270 real -> scale 3.75
     out = m([[f.to(dev) for f in fr] for fr in feats], size, fusion_logits=lg.to(dev))
+    noise = fp32_noise(sd, feats, q, T, shapes, re_)
     for t in range(T):
         for s in range(7):
-            assert rel(out["emb"][t][s], re_[t][s]) < max(3e-5 * 3.5 ** s, 3e-5), (t, s, rel(out["emb"][t][s], re_[t][s]))
+            assert drift_ok(rel(out["emb"][t][s], re_[t][s]), noise, s), (t, s, rel(out["emb"][t][s], re_[t][s]), noise[s])
     r = O.panoptic_fuse(lg, out["pred_masks"].cpu(), size)
     got = out["fusion"].panoptic.cpu().numpy()
     assert got.shape == size
@@ -431,10 +452,11 @@ def test_stale_workspace_is_never_read(dev, pos_kind, monkeypatch):
     pos_arg = {"sine": "sine", "none": None,
                "tensor": None if pos64 is None else [[p.float().to(dev) for p in pp] for pp in pos64]}[pos_kind]
     cl, em, fu = head([[f.to(dev) for f in fr] for fr in feats], [q.to(dev)] * T, None, pos=pos_arg)
+    noise = fp32_noise(sd, feats, q, T, shapes, re_, pos=pos64 is not None)
     for t in range(T):
         for s in range(7):
             e = rel(em[t][s], re_[t][s])
-            assert e < max(3e-5 * 3.5 ** s, 3e-5), (pos_kind, t, s, e)
+            assert drift_ok(e, noise, s), (pos_kind, t, s, e, noise[s])
 
 
 # ---- tracker -------------------------------------------------------------------------
@@ -525,14 +547,19 @@ def test_folded_input_transform_golden(dev, kernel_path, golden_dir):
     raw = synthetic.make_features(0, 0, T=c["T"], video=c["seed"], frame=0, shapes=c["shapes"])
     head = _mk_head(dev, sd, kernel_path)
     head.fold_input_transform(tp["conv_trans.conv.weight"], tp["conv_trans.conv.bias"])
+    # noise floor: the fp32 oracle on the transformed features against the reference's golden
+    feats_t = O.input_transform(raw, tp["conv_trans.conv.weight"], tp["conv_trans.conv.bias"])
+    pos32 = [[O.sine_position_embedding(*s) for s in c["shapes"]] for _ in range(c["T"])]
+    _, e32, _ = O.head_forward(sd, feats_t, [cap["init_mask_query.weight"]] * c["T"], pos32)
+    noise = [max(rel(e32[t][s], gold[f"emb{t}"][s]) for t in range(c["T"])) for s in range(7)]
     q = cap["init_mask_query.weight"].to(dev)
     cl, em, fu = head([[f.to(dev) for f in fr] for fr in raw], [q] * c["T"], None, pos="sine")
     for t in range(c["T"]):
         for l in range(4):
             assert rel(fu[t][l][0][::7, ::3, ::5], gold[f"fused{t}_{l}_sample"]) < 1e-5
         for s in range(7):
-            env = max(1e-5 * 3.5 ** s * 3, 2e-5)
-            assert rel(em[t][s], gold[f"emb{t}"][s]) < env and rel(cl[t][s], gold[f"cls{t}"][s]) < env, (t, s)
+            env = DRIFT_X * max(noise[s], 2e-6)
+            assert rel(em[t][s], gold[f"emb{t}"][s]) <= env and rel(cl[t][s], gold[f"cls{t}"][s]) <= env, (t, s)
     # removing the fold restores the plain head (transformed features in)
     head.fold_input_transform(None, None)
     feats = O.input_transform(raw, tp["conv_trans.conv.weight"], tp["conv_trans.conv.bias"])
@@ -562,9 +589,9 @@ def test_folded_input_transform_tensor_core_path(dev):
             prev = ref
     pos64 = [[O.sine_position_embedding(*s, dtype=torch.float64) for s in shapes] for _ in range(2)]
     rc, re_, _ = O.head_forward(P64, feats64, [q.double()] * 2, pos64)
+    noise = fp32_noise(sd, [[f.float() for f in fr] for fr in feats64], q, 2, shapes, re_)
     for s in range(7):
-        env = max(1e-5 * 3.5 ** s * 3, 2e-5)
-        assert rel(em[1][s], re_[1][s]) < env, (s, rel(em[1][s], re_[1][s]))
+        assert drift_ok(rel(em[1][s], re_[1][s]), noise, s), (s, rel(em[1][s], re_[1][s]), noise[s])
 
 
 # ---- consumers of the id map -------------------------------------------------------------
@@ -669,5 +696,160 @@ def test_explicit_pos_tensors_match_sine_mode(dev):
     P64 = {k: v.double() for k, v in sd.items()}
     pos64 = [[O.sine_position_embedding(*s, dtype=torch.float64) for s in shapes] for _ in range(2)]
     _, re_, _ = O.head_forward(P64, [[f.double() for f in fr] for fr in feats], [q.double()] * 2, pos64)
+    noise = fp32_noise(sd, feats, q, 2, shapes, re_)
     for s in range(7):
-        assert rel(em_t[1][s], re_[1][s]) < max(1e-5 * 3.5 ** s * 3, 2e-5), (s, rel(em_t[1][s], re_[1][s]))
+        assert drift_ok(rel(em_t[1][s], re_[1][s]), noise, s), (s, rel(em_t[1][s], re_[1][s]), noise[s])
+
+
+# ---- round 2: parity at the metric's own size, per-stage teacher forcing, drift relative to the reference's own noise ----
+def _teacher_forcing_inputs(q, emb_ref, T):
+    """Slots entering stage s = the checker's stage s-1 embeddings (dynamic_mask_head.py:210-211); stage 0 = init query."""
+    return [[q] * T] + [[emb_ref[t][s, 0] for t in range(T)] for s in range(6)]
+
+
+def _fullsize_parity(dev, shapes, T, seed, paths, label):
+    N = 100
+    sd = synthetic.make_head_state_dict(seed)
+    cap = synthetic.make_capsule_params(seed, N)
+    feats = synthetic.make_features(0, 0, T=T, video=seed, frame=0, shapes=shapes)
+    q = cap["init_mask_query.weight"]
+    P64 = {k: v.double() for k, v in sd.items()}
+    pos32 = [[O.sine_position_embedding(*s) for s in shapes] for _ in range(T)]
+    pos64 = [[p.double() for p in pp] for pp in pos32]
+    torch.set_num_threads(os.cpu_count() or 1)
+    c64, e64, f64 = O.head_forward(P64, [[f.double() for f in fr] for fr in feats], [q.double()] * T, pos64)
+    c32, e32, f32 = O.head_forward(sd, feats, [q] * T, pos32)
+    noise = [max(rel(e32[t][s], e64[t][s]) for t in range(T)) for s in range(7)]     # the fp32 reference arithmetic's own drift
+    forced = _teacher_forcing_inputs(q, e64, T)
+    f_dev = [[f.to(dev) for f in fr] for fr in feats]
+    for kp in paths:
+        head = _mk_head(dev, sd, kp)
+        cl, em, fu = head(f_dev, [q.to(dev)] * T, None, pos="sine")
+        for t in range(T):
+            for l in range(4):
+                e = rel(fu[t][l], f64[t][l])
+                assert e < 1e-5, (label, kp, t, l, e)
+        drift = [max(rel(em[t][s], e64[t][s]) for t in range(T)) for s in range(7)]
+        assert drift[0] < 1e-4, (label, kp, drift[0])
+        for s in range(7):
+            # free-running drift: at most 5x what the reference's own fp32 arithmetic shows against fp64 on the same clip
+            assert drift[s] <= 5 * max(noise[s], 2e-6), (label, kp, s, drift[s], noise[s])
+        # every stage teacher-forced on the fp64 checker's stage inputs: the <= 1e-3 north-star bound, per stage
+        cl_tf, em_tf, _ = head(f_dev, [q.to(dev)] * T, None, pos="sine",
+                               stage_slots_in=[[v.float() for v in st] for st in forced])
+        tf = [max(max(rel(em_tf[t][s], e64[t][s]), rel(cl_tf[t][s], c64[t][s])) for t in range(T)) for s in range(7)]
+        for s in range(7):
+            assert tf[s] < TOL, (label, kp, s, tf[s])
+        # mask logits, teacher-forced on the checker's finest feature / last embedding (through the operand planes on path 0)
+        print(f"{label} path={kp}: fused-feature rel {max(rel(fu[t][l], f64[t][l]) for t in range(T) for l in range(4)):.1e} | "
+              f"teacher-forced per-stage rel vs fp64 oracle: {' '.join(f'{v:.1e}' for v in tf)} | free-running drift: "
+              f"{' '.join(f'{v:.1e}' for v in drift)} | fp32-oracle-vs-fp64 (reference noise): {' '.join(f'{v:.1e}' for v in noise)} | "
+              f"drift/noise max {max(d / max(n, 2e-6) for d, n in zip(drift, noise)):.2f}x")
+    return sd, cap, feats, e64, f64
+
+
+def test_fullsize_head_vs_oracle(dev):
+    """BASELINE configs[1] (1024x2048, T=2, N=100): both kernel paths against the fp64 AND fp32 oracle at the metric's
+    own size -- fused features, stage 0, all 7 stages teacher-forced (<= 1e-3), free-running drift <= 5x the drift the
+    reference's own fp32 arithmetic shows against fp64 on the same clip, and the mask logits teacher-forced."""
+    shapes = synthetic.level_shapes(1024, 2048)
+    sd, cap, feats, e64, f64 = _fullsize_parity(dev, shapes, 2, 31, (0, 1), "1024x2048 T=2")
+    # mask logits through the whole-clip API (operand planes of the finest level), teacher-forced on ITS OWN head outputs
+    N, T = 100, 2
+    m = sv.SlotVPSRetriever(sv.HEAD_KWARGS, N, sv.FUSION_KWARGS)
+    m.dynamic_mask_head.load_state_dict(sd)
+    m.load_capsule_params(cap)
+    m = m.to(dev)
+    f_dev = [[f.to(dev) for f in fr] for fr in feats]
+    a = m(f_dev, (1024, 2048), fuse=False)
+    ref = O.mask_logits(a["feats"][1][3][0].double().cpu(), a["emb"][1][-1, 0].double().cpu(), {k: v.double() for k, v in cap.items()})
+    e = rel(a["pred_masks"], ref)
+    b = m(f_dev, (1024, 2048), fuse=False, want_feats=False)           # L2 form: no fp32 features, norms from the fusion epilogue
+    assert b["feats"][1][3] is None
+    e2 = rel(b["pred_masks"], ref)
+    print(f"1024x2048 mask logits teacher-forced vs fp64 oracle: rel {e:.2e}; without fp32 features (epilogue norms): {e2:.2e}; "
+          f"emb identical: {torch.equal(a['emb'][1], b['emb'][1])}")
+    assert e < 1e-4 and e2 < 1e-4
+    assert torch.equal(a["emb"][1], b["emb"][1]) and torch.equal(a["cls"][0], b["cls"][0])
+
+
+def test_viper_full_size_vs_oracle(dev):
+    """BASELINE configs[3] at its real size (1080x1920 padded to 1088x1920 -> levels 34x60 .. 272x480, pixel counts that
+    are not multiples of the 128-pixel tile; T=4: Video Retriever over 400 slots) against the fp64 / fp32 oracle."""
+    shapes = [(34, 60), (68, 120), (136, 240), (272, 480)]
+    _fullsize_parity(dev, shapes, 4, 32, (0,), "VIPER 1088x1920 T=4")
+
+
+@pytest.mark.parametrize("kernel_path", PATHS)
+@pytest.mark.parametrize("case", ["head_t2_n100_big", "head_swinl"])
+def test_head_big_golden_teacher_forced(dev, kernel_path, case, golden_dir):
+    """Golden cases whose EVERY level has >= 128 pixels (tcgen05 on all levels) against the REFERENCE's own outputs:
+    per stage teacher-forced with the reference's stage s-1 embedding, and free-running within 5x of the drift the fp32
+    oracle shows against the same golden.  `head_swinl` is the reference's second shipped config (ReLU stage FFN, GELU
+    temporal FFN, configs/cityscapes/swinL_fpn_slotvps.py:41,56)."""
+    from tests.test_oracle_golden import HEAD_CASES, head_cfg
+    c = HEAD_CASES[case]
+    gold = np.load(os.path.join(golden_dir, case + ".npz"))
+    T = c["T"]
+    cfg = head_cfg(c)
+    sd = synthetic.make_head_state_dict(c["seed"])
+    cap = synthetic.make_capsule_params(c["seed"], c["N"])
+    feats = synthetic.make_features(0, 0, T=T, video=c["seed"], frame=0, shapes=c["shapes"])
+    q = cap["init_mask_query.weight"]
+    over = dict(activation=cfg.activation,
+                temporal_query_attention_config={**sv.HEAD_KWARGS["temporal_query_attention_config"], "activation": cfg.temporal_activation})
+    head = _mk_head(dev, sd, kernel_path, **over)
+    f_dev = [[f.to(dev) for f in fr] for fr in feats]
+    forced = [[q] * T] + [[torch.from_numpy(gold[f"emb{t}"][s, 0]) for t in range(T)] for s in range(6)]
+    cl, em, fu = head(f_dev, [q.to(dev)] * T, None, pos="sine", stage_slots_in=forced)
+    tf = [max(max(rel(em[t][s], gold[f"emb{t}"][s]), rel(cl[t][s], gold[f"cls{t}"][s])) for t in range(T)) for s in range(7)]
+    for t in range(T):
+        for l in range(4):
+            assert rel(fu[t][l][0][::7, ::3, ::5], gold[f"fused{t}_{l}_sample"]) < 1e-5
+    assert max(tf) < 5e-5, tf                      # ~1e-5 measured; the north-star bound is 1e-3
+    pos32 = [[O.sine_position_embedding(*s) for s in c["shapes"]] for _ in range(T)]
+    _, e32, _ = O.head_forward(sd, feats, [q] * T, pos32, cfg)
+    cl2, em2, _ = head(f_dev, [q.to(dev)] * T, None, pos="sine")
+    noise = [max(rel(e32[t][s], gold[f"emb{t}"][s]) for t in range(T)) for s in range(7)]
+    drift = [max(rel(em2[t][s], gold[f"emb{t}"][s]) for t in range(T)) for s in range(7)]
+    for s in range(7):
+        assert drift[s] <= 5 * max(noise[s], 2e-6), (s, drift[s], noise[s])
+    print(f"{case} path={kernel_path}: teacher-forced per-stage rel vs REFERENCE golden: {' '.join(f'{v:.1e}' for v in tf)} | "
+          f"free-running: {' '.join(f'{v:.1e}' for v in drift)} | fp32 oracle vs golden: {' '.join(f'{v:.1e}' for v in noise)}")
+
+
+def test_postprocess_forward_with_instances(dev):
+    """PostProcessPanopticInstances.forward's SUCCESS path (vps_temporal_slots.py:659-807) with an Instances-like object
+    (structures/instances.py:134-152: boolean / index filtering of every field): the filtered object carries the kept
+    slots' fields in the post-processor's order plus .masks / .probs / .labels, as simple_test consumes them (:313-320)."""
+    class Inst:                                         # the subset of the reference's Instances the call touches
+        def __init__(self, **f):
+            self.__dict__["_f"] = dict(f)
+
+        def __getattr__(self, k):
+            try:
+                return self.__dict__["_f"][k]
+            except KeyError:
+                raise AttributeError(k)
+
+        def __setattr__(self, k, v):
+            self._f[k] = v
+
+        def __getitem__(self, idx):
+            return Inst(**{k: v[idx] for k, v in self._f.items()})
+
+    N, h, w = 100, 24, 40
+    logits, masks, _ = synthetic.make_fusion_case(5, N, h, w, n_things=10, near_dup_things=2, tiny=1)
+    emb = torch.randn(N, 256, generator=torch.Generator().manual_seed(1))
+    inst = Inst(pred_logits=logits.to(dev), pred_masks=masks.to(dev), output_embedding=emb.to(dev),
+                obj_idxes=torch.full((N,), -1, dtype=torch.long, device=dev))
+    fz = sv.PanopticFusion(**sv.FUSION_KWARGS)
+    res = fz(inst, [(4 * h, 4 * w)], id=10001)
+    r = O.panoptic_fuse(logits, masks, (4 * h, 4 * w), want_masks=True)
+    assert res.masks.shape == (len(r.labels), 4 * h, 4 * w)
+    np.testing.assert_array_equal(res.labels.cpu().numpy(), r.labels)
+    np.testing.assert_allclose(res.probs.cpu().numpy(), r.probs, rtol=2e-6)
+    np.testing.assert_array_equal(res.output_embedding.cpu().numpy(), emb[torch.from_numpy(r.keep.copy())].numpy())
+    np.testing.assert_array_equal(res.pred_logits.cpu().numpy(), logits[torch.from_numpy(r.keep.copy())].numpy())
+    assert int(((res.masks.cpu().numpy() != 0) != (r.masks != 0)).sum()) == 0
+    assert float(np.abs(res.masks.cpu().numpy() - r.masks).max()) < 1e-4
