@@ -293,7 +293,7 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
   w.rs_k = px.rs_k; w.rs_v = px.rs_v; w.tc = px.tc;
   if (px.overlapped) {
     SV_CHECK_CUDA(cudaStreamWaitEvent(s, px.ready, 0));      // statistics of this stage were produced on the side stream
-  } else if (use_tc) {
+  } else if (use_tc && !(x != nullptr && getenv("SLOTVPS_TC_DEBUG") && (atoi(getenv("SLOTVPS_TC_DEBUG")) & 64))) {
     SV_TRY(tc_stats(ps.tc, w.tc, ps.bk_c, ps.bv_c, w.rs_k, w.rs_v, T, P, s, 148, px.ps));
   } else {
     dim3 gs(ceil_div(P, 32), T);

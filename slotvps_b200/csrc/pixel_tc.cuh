@@ -524,6 +524,10 @@ constexpr uint32_t IDESC_AUX = tc::make_idesc_f16(128, 16, 0, 0);
 constexpr int TM_S = 0;                            // two S buffers of 128 columns
 constexpr int TM_Z = 256;                          // Z^T: 2 x 112 columns
 constexpr int TM_AUX = 480;                        // 16 columns
+// P = A * rs_v is scaled by 2^7 before the fp16 hi/lo split: fp16 has only 5 exponent bits, so the lo plane of a value
+// below ~0.06 is subnormal (absolute step 6e-8) and softmax weights of ~1/N lose ~2 decimal digits (measured: 5.4e-6
+// instead of 2.5e-6 per stage).  rs_v <= 1/sqrt(eps) = 316, so the scaled value stays below the fp16 maximum.
+constexpr float PSCALE = 128.f, PSCALE_INV = 1.f / 128.f;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(OFF_G % 1024 == 0 && G_SUB % 1024 == 0 && OFF_P % 1024 == 0 && P_SUB % 1024 == 0 && OFF_AUX % 1024 == 0, "swizzle atoms");
 }  // namespace attn
@@ -590,7 +594,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   }
   for (int i = threadIdx.x; i < NPAD; i += THREADS)
     gc[i] = i < N ? make_float2(g0[(long)t * Ntot + n0 + i], g1[(long)t * Ntot + n0 + i]) : make_float2(0.f, 0.f);
-  // aux tile: row 0 = 1.0 (-> a1), row 1 = sigma_v per pixel (rewritten every tile), rows 2..15 = 0.
+  // aux tile: row 0 = 1.0 (-> a1), rows 1 / 2 = sigma_v per pixel as fp16 hi / lo (rewritten every tile), rows 3..15 = 0.
   // Row r lives at byte r*128 of each 64-pixel half; 16-byte chunk index is XOR-swizzled with (r & 7).
   for (int i = threadIdx.x; i < AUXT_BYTES / 2; i += THREADS) {
     int half = i / (AUX_SUB / 2), e = i % (AUX_SUB / 2), r = e / 64;
@@ -762,6 +766,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     uint8_t* p_half = smem + OFF_P + (r >> 6) * P_SUB;      // this pixel's 64-pixel half of P
     const int pc = (r & 63) >> 3, pe = (r & 7) * 2;         // 16-byte chunk and byte offset inside it
     __half* aux_row1 = reinterpret_cast<__half*>(smem + OFF_AUX + (r >> 6) * AUX_SUB + 128 + ((pc ^ 1) * 16) + pe);
+    __half* aux_row2 = reinterpret_cast<__half*>(smem + OFF_AUX + (r >> 6) * AUX_SUB + 256 + ((pc ^ 2) * 16) + pe);
     for (int i = 0; i < n_my; ++i) {
       const int p = (chunk + i * chunks) * TILE_M + r;
       const bool pv = p < P;
@@ -807,6 +812,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         mx = ml.x; sum = ml.y;
 #pragma unroll
         for (int n = 0; n < NPAD; ++n) sv[n] = __expf(sv[n] - mx);
+      } else if (dbg & 32) {
+#pragma unroll
+        for (int n = 0; n < NPAD; ++n) { const float e = expf(sv[n] - mx); sv[n] = e; sum += e; }
       } else {
 #pragma unroll
         for (int n = 0; n < NPAD; ++n) { const float e = __expf(sv[n] - mx); sv[n] = e; sum += e; }
@@ -815,7 +823,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         if (pv) grp.ml_out[(long)t * P + p] = make_float2(mx, sum);
         continue;
       }
-      const float sc = pv ? rv / sum : 0.f;                 // A' = A * rs_v
+      const float sc = pv ? rv / sum * PSCALE : 0.f;        // A' = A * rs_v (scaled, see PSCALE)
       tc::mbar_wait(pempty, (i & 1) ^ 1);                   // Z(i-1) has finished reading P
 #pragma unroll
       for (int n = 0; n < NROW; ++n) {
@@ -825,7 +833,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         *reinterpret_cast<__half*>(p_half + off) = hi;
         *reinterpret_cast<__half*>(p_half + P_PLANE + off) = __float2half_rn(a - __half2float(hi));
       }
-      *aux_row1 = __float2half_rn(pv ? 1.f / rv : 0.f);     // sigma_v
+      {
+        const float sg = pv ? 1.f / rv : 0.f;               // sigma_v, hi + lo
+        const __half sh = __float2half_rn(sg);
+        *aux_row1 = sh;
+        *aux_row2 = __float2half_rn(sg - __half2float(sh));
+      }
       tc::fence_proxy_async();
       tc::mbar_arrive(pfull);
     }
@@ -841,344 +854,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         tc::tmem_ld32(tmem_base + lane_addr + TM_Z + mt * NPAD + j * 32, v);   // last chunk over-reads 16 columns (ignored)
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) { const int n = j * 32 + c; if (n < N) Zp[(long)n * C + ch] = v[c]; }
+        for (int c = 0; c < 32; ++c) { const int n = j * 32 + c; if (n < N) Zp[(long)n * C + ch] = v[c] * PSCALE_INV; }
       }
     }
     {
       float v[32];
       tc::tmem_ld32(tmem_base + lane_addr + TM_AUX, v);     // reads 16 columns past aux (unused)
       tc::tmem_ld_wait();
-      if (r < N) { a1part[((long)chunk * T + t) * Ntot + n0 + r] = v[0]; a0part[((long)chunk * T + t) * Ntot + n0 + r] = v[1]; }
+      if (r < N) {
+        a1part[((long)chunk * T + t) * Ntot + n0 + r] = v[0] * PSCALE_INV;
+        a0part[((long)chunk * T + t) * Ntot + n0 + r] = (v[1] + v[2]) * PSCALE_INV;
+      }
     }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
-}
-
-// ---- CTA-pair form of the attention kernel (experimental, SLOTVPS_ATTN_PAIRS=1) -------------------------------------
-// attn_tc is bounded by the bytes a CTA keeps in flight: G hi/lo (104 KB) and P hi/lo (52 KB) leave a 64 KB TMA ring.
-// Here the S product runs as ONE M = 256 MMA over the two pixel tiles of a CTA pair (cta_group::2) with the slot rows
-// of G split 56 / 56 between the two CTAs' shared memory, which frees room for three more ring slots; softmax, P, the
-// Z^T contraction and the aux product stay per CTA (cta_group::1).
-namespace attn2 {
-constexpr int TILE_M = attn::TILE_M, NROW = attn::NROW, NPAD = attn::NPAD, SLOT_BYTES = attn::SLOT_BYTES;
-constexpr int P_SUB = attn::P_SUB, P_PLANE = attn::P_PLANE, P_BYTES = attn::P_BYTES, AUX_SUB = attn::AUX_SUB, AUXT_BYTES = attn::AUXT_BYTES;
-constexpr int MISC_BYTES = attn::MISC_BYTES, THREADS = attn::THREADS, TM_S = attn::TM_S, TM_Z = attn::TM_Z, TM_AUX = attn::TM_AUX;
-constexpr uint32_t IDESC_Z = attn::IDESC_Z, IDESC_AUX = attn::IDESC_AUX;
-constexpr int NHALF = NPAD / 2;                   // 56 slot rows of G per CTA
-constexpr int NS = 3, NZ = 4, NSLOT = NS + NZ;    // separate rings: S operand slots are pair loads, Z operand slots are local
-constexpr int G_SUB = NHALF * 128;                // 7168: [56 slots][64 ch] fp16
-constexpr int G_BYTES = 2 * 4 * G_SUB;            // 57344
-constexpr int OFF_G = NSLOT * SLOT_BYTES;
-constexpr int OFF_P = OFF_G + G_BYTES;
-constexpr int OFF_AUX = OFF_P + P_BYTES;
-constexpr int OFF_MISC = OFF_AUX + AUXT_BYTES;
-constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
-constexpr uint32_t IDESC_S2 = tc::make_idesc_f16(256, NPAD, 0, 0);
-static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-static_assert(OFF_G % 1024 == 0 && G_SUB % 1024 == 0 && OFF_P % 1024 == 0 && OFF_AUX % 1024 == 0, "swizzle atoms");
-}  // namespace attn2
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(attn2::THREADS, 1)
-attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g,
-               const float* __restrict__ g0, const float* __restrict__ g1, const float* __restrict__ rs_k,
-               const float* __restrict__ rs_v, float* __restrict__ Zpart, float* __restrict__ a0part,
-               float* __restrict__ a1part, const __half* __restrict__ planes, int N, int P, int T, int plane_rows, int tiles_per_frame, int dbg, const PosSep ps,
-               const SlotGroup grp) {
-  using namespace attn2;
-  constexpr int MODE = 0;
-  const uint32_t rank = tc::cluster_ctarank();
-  const bool leader = rank == 0;
-  const int Ntot = MODE == 0 ? N : grp.n_total, n0 = MODE == 0 ? 0 : grp.n0;
-  extern __shared__ uint8_t raw_smem[];
-  const uint32_t raw = tc::smem_u32(raw_smem);
-  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
-  uint8_t* misc = smem + OFF_MISC;
-  uint64_t* full = reinterpret_cast<uint64_t*>(misc);      // [NSLOT]: [0, NS) S ring (waited on by the leader), [NS, NSLOT) Z ring (local)
-  uint64_t* empty = full + NSLOT;                          // [NSLOT]
-  uint64_t* sfull = empty + NSLOT;                         // [2]
-  uint64_t* sempty = sfull + 2;                            // [2]
-  uint64_t* pfull = sempty + 2;                            // [1]
-  uint64_t* pempty = pfull + 1;                            // [1]
-  uint64_t* gfull = pempty + 1;                            // [1]
-  uint64_t* zfull = gfull + 1;                             // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(zfull + 1);
-  float2* gc = reinterpret_cast<float2*>(misc + 256);      // [NPAD] (g0, g1)
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x, chunks = gridDim.x, t = blockIdx.y;
-  // both CTAs of a pair run the same number of iterations (the even chunk's count); a CTA without a tile left
-  // processes rows past the frame with every pixel masked out
-  const int n_my = (tiles_per_frame - (chunk & ~1) + chunks - 1) / chunks;
-
-  if (threadIdx.x == 0) {
-    tc::tma_prefetch_desc(&tmap_x);
-    tc::tma_prefetch_desc(&tmap_g);
-    for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sfull[i], 1); tc::mbar_init(&sempty[i], 256); }
-    tc::mbar_init(pfull, 128); tc::mbar_init(pempty, 1); tc::mbar_init(gfull, 1); tc::mbar_init(zfull, 1);
-    tc::fence_barrier_init();
-  }
-  for (int i = threadIdx.x; i < NPAD; i += THREADS)
-    gc[i] = i < N ? make_float2(g0[(long)t * Ntot + n0 + i], g1[(long)t * Ntot + n0 + i]) : make_float2(0.f, 0.f);
-  // aux tile: row 0 = 1.0 (-> a1), row 1 = sigma_v per pixel (rewritten every tile), rows 2..15 = 0.
-  // Row r lives at byte r*128 of each 64-pixel half; 16-byte chunk index is XOR-swizzled with (r & 7).
-  for (int i = threadIdx.x; i < AUXT_BYTES / 2; i += THREADS) {
-    int half = i / (AUX_SUB / 2), e = i % (AUX_SUB / 2), r = e / 64;
-    reinterpret_cast<__half*>(smem + OFF_AUX + half * AUX_SUB)[e] = __float2half(r == 0 ? 1.f : 0.f);   // constant rows: swizzle-invariant
-  }
-  for (int i = threadIdx.x; i < P_BYTES / 4; i += THREADS) reinterpret_cast<uint32_t*>(smem + OFF_P)[i] = 0u;
-  tc::fence_proxy_async();
-  if (warp == 1) { tc::tmem_alloc2(tmem_ptr, 512); tc::tmem_relinquish2(); }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::cluster_sync();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    // ===================== TMA producer (lane 0) + L2 prefetchers (lanes 1..31) =====================
-    // The 4-slot ring holds 64 KB in flight.  Optional experiment: the idle lanes touch the NEXT tile's plane rows
-    // with prefetch.global.L2, paced one tile ahead of the producer by the __syncwarp below (see note further down).
-    uint32_t itS = 0, itZ = 0;
-    // Z operand slots (ring [NS, NSLOT)): this CTA's own product, local barriers
-    auto load_slot = [&](int plane, int c0, int row) {
-      const int s = NS + itZ % NZ;
-      tc::mbar_wait(&empty[s], ((itZ / NZ) & 1) ^ 1);
-      tc::mbar_expect_tx(&full[s], SLOT_BYTES);
-      tc::tma_load_2d(smem + s * SLOT_BYTES, &tmap_x, 0, (plane * 4 + c0 / 64) * plane_rows + row, &full[s]);
-      ++itZ;
-    };
-    // S operand slots (ring [0, NS)): consumed by the pair MMA the leader issues, so both CTAs' bytes are credited to
-    // the leader's barrier and the slot is released in both CTAs by the leader's multicast commit
-    auto load_slot_pair = [&](int plane, int c0, int row) {
-      const int s = itS % NS;
-      tc::mbar_wait(&empty[s], ((itS / NS) & 1) ^ 1);
-      if (leader) tc::mbar_expect_tx(&full[s], 2 * SLOT_BYTES);
-      tc::tma_load_2d_pair(smem + s * SLOT_BYTES, &tmap_x, 0, (plane * 4 + c0 / 64) * plane_rows + row, &full[s]);
-      ++itS;
-    };
-    auto job_s = [&](int i) {
-      const int row = t * P + (chunk + i * chunks) * TILE_M;
-      const int q0 = ps.enabled ? 0 : 2;                                                              // separable pos: S reads the x planes
-      for (int ks = 0; ks < 4; ++ks) { load_slot_pair(q0, ks * 64, row); load_slot_pair(q0 + 1, ks * 64, row); }  // (x+pos) or x: hi, lo
-    };
-    auto job_z = [&](int i) {
-      const int row = t * P + (chunk + i * chunks) * TILE_M;
-      for (int mt = 0; mt < 2; ++mt)
-        for (int pl = 0; pl < 2; ++pl) { load_slot(pl, (2 * mt) * 64, row); load_slot(pl, (2 * mt + 1) * 64, row); }   // x hi / lo, 128 channels
-    };
-    auto prefetch_tile = [&](int i) {            // lanes 1..31: 4 planes x 128 rows x 512 B = 2048 lines of 128 B
-      const long row = (long)t * P + (long)(chunk + i * chunks) * TILE_M;
-      const long max_row = (long)T * P;
-      for (int ln = lane - 1; ln < 4 * TILE_M * 4; ln += 31) {
-        const int pl = ln >> 9, r = (ln >> 2) & 127, seg = ln & 3;
-        if (row + r < max_row) {
-          const __half* ptr = planes + (((long)pl * 4 + seg) * plane_rows + row + r) * 64;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-        }
-      }
-    };
-    if (lane == 0) {
-      if (leader) tc::mbar_expect_tx(gfull, 2 * G_BYTES);      // each CTA stages its half of the slot rows; both report to the leader
-      for (int pl = 0; pl < 2; ++pl)
-        for (int ks = 0; ks < 4; ++ks)
-          tc::tma_load_2d_pair(smem + OFF_G + (pl * 4 + ks) * G_SUB, &tmap_g, ks * 64, (t * 2 + pl) * NROW + (int)rank * NHALF, gfull);
-      job_s(0);
-    }
-    // Measured on B200 (1024x2048, level 3): both an L2 prefetch through the TMA engine and this LSU prefetch made the
-    // kernel SLOWER (0.43 -> 0.51 ms/step): it already streams the planes at ~4.3 TB/s, the extra requests only add
-    // DRAM contention.  Kept for experiments (SLOTVPS_TC_DEBUG bit 3), off by default.
-    const bool do_prefetch = (dbg & 8) != 0;
-    if (do_prefetch && lane != 0 && n_my > 1) prefetch_tile(1);
-    __syncwarp();
-    for (int i = 0; i < n_my; ++i) {
-      if (lane == 0) { if (i + 1 < n_my) job_s(i + 1); if (MODE != 1) job_z(i); }
-      else if (do_prefetch && i + 2 < n_my) prefetch_tile(i + 2);
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      if (leader) tc::mbar_wait(gfull, 0);
-      tc::tc_fence_after();
-      const uint32_t g_base = tc::smem_u32(smem + OFF_G), p_base = tc::smem_u32(smem + OFF_P), x_base = tc::smem_u32(smem + OFF_AUX);
-      uint32_t itS = 0, itZ = 0;
-      auto issue_s = [&](int i) {
-        if (!leader) return;                                // the leader issues the M = 256 S product for both CTAs
-        const int b = i & 1, u = i >> 1;
-        tc::mbar_wait(&sempty[b], (u & 1) ^ 1);            // softmax of tile i-2 has drained this S buffer
-        tc::tc_fence_after();
-        const uint32_t d = tmem_base + TM_S + b * 128;
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t dgh = tc::make_smem_desc_sw128(g_base + ks * G_SUB, 16, 1024);
-          const uint64_t dgl = tc::make_smem_desc_sw128(g_base + (4 + ks) * G_SUB, 16, 1024);
-          {   // (x+pos) hi against G hi and G lo
-            const int s = itS % NS;
-            tc::mbar_wait(&full[s], (itS / NS) & 1);
-            tc::tc_fence_after();
-            const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), 16, 1024);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              tc::umma2_f16(d, da + 2 * k, dgh + 2 * k, IDESC_S2, (ks | k) != 0);
-              tc::umma2_f16(d, da + 2 * k, dgl + 2 * k, IDESC_S2, 1);
-            }
-            tc::umma2_commit_multicast(&empty[s], 3);
-            ++itS;
-          }
-          {   // (x+pos) lo against G hi
-            const int s = itS % NS;
-            tc::mbar_wait(&full[s], (itS / NS) & 1);
-            tc::tc_fence_after();
-            const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), 16, 1024);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma2_f16(d, da + 2 * k, dgh + 2 * k, IDESC_S2, 1);
-            tc::umma2_commit_multicast(&empty[s], 3);
-            ++itS;
-          }
-        }
-        tc::umma2_commit_multicast(&sfull[b], 3);
-      };
-      auto issue_z = [&](int i) {
-        tc::mbar_wait(pfull, i & 1);                        // P and the aux tile of tile i are in shared memory
-        tc::tc_fence_after();
-        for (int mt = 0; mt < 2; ++mt) {
-          const uint32_t d = tmem_base + TM_Z + mt * NPAD;
-          for (int pl = 0; pl < 2; ++pl) {                  // pl = 0: x hi against P hi and P lo; pl = 1: x lo against P hi
-            const int s = NS + itZ % NZ;                    // NZ even: slots (s, s+1) are adjacent and hold channels [128 mt, 128 mt + 128)
-            tc::mbar_wait(&full[s], (itZ / NZ) & 1);
-            tc::mbar_wait(&full[s + 1], ((itZ + 1) / NZ) & 1);
-            tc::tc_fence_after();
-            // A: x tile as MN-major operand: 64-channel groups SLOT_BYTES apart, 8-pixel groups 1024 B apart
-            const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), SLOT_BYTES, 1024);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {                   // 16 pixels per MMA: A advances 16 rows (2048 B), B 32 B inside its 64-pixel half
-              const uint32_t poff = (k >> 2) * P_SUB + (k & 3) * 32;
-              tc::umma_bf16(d, da + (uint64_t)(k * 128), tc::make_smem_desc_sw128(p_base + poff, 16, 1024), IDESC_Z, (i | pl | k) != 0);
-              if (pl == 0) tc::umma_bf16(d, da + (uint64_t)(k * 128), tc::make_smem_desc_sw128(p_base + P_PLANE + poff, 16, 1024), IDESC_Z, 1);
-            }
-            tc::umma_commit(&empty[s]);
-            tc::umma_commit(&empty[s + 1]);
-            itZ += 2;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {                       // aux[n, :] += (P hi + P lo)[n, px] . (1, sigma_v[px], 0...)
-          const uint32_t poff = (k >> 2) * P_SUB + (k & 3) * 32;
-          const uint64_t dx = tc::make_smem_desc_sw128(x_base + (k >> 2) * AUX_SUB + (k & 3) * 32, 16, 1024);
-          tc::umma_bf16(tmem_base + TM_AUX, tc::make_smem_desc_sw128(p_base + poff, 16, 1024), dx, IDESC_AUX, (i | k) != 0);
-          tc::umma_bf16(tmem_base + TM_AUX, tc::make_smem_desc_sw128(p_base + P_PLANE + poff, 16, 1024), dx, IDESC_AUX, 1);
-        }
-        tc::umma_commit(pempty);                            // P may be overwritten once these retire
-      };
-      issue_s(0);
-      for (int i = 0; i < n_my; ++i) { if (i + 1 < n_my) issue_s(i + 1); if (MODE != 1) issue_z(i); }
-      if (MODE != 1) tc::umma_commit(zfull);
-    }
-  } else {
-    // ===================== softmax warps (one pixel per thread) + final epilogue =====================
-    const int q = warp & 3;
-    const int r = q * 32 + lane;                            // pixel row of the tile == TMEM lane
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint8_t* p_half = smem + OFF_P + (r >> 6) * P_SUB;      // this pixel's 64-pixel half of P
-    const int pc = (r & 63) >> 3, pe = (r & 7) * 2;         // 16-byte chunk and byte offset inside it
-    __half* aux_row1 = reinterpret_cast<__half*>(smem + OFF_AUX + (r >> 6) * AUX_SUB + 128 + ((pc ^ 1) * 16) + pe);
-    for (int i = 0; i < n_my; ++i) {
-      const int p = (chunk + i * chunks) * TILE_M + r;
-      const bool pv = p < P;
-      const float rk = pv ? __ldg(rs_k + (long)t * P + p) : 0.f;
-      const float rv = pv ? __ldg(rs_v + (long)t * P + p) : 0.f;
-      const int b = i & 1;
-      tc::mbar_wait(&sfull[b], (i >> 1) & 1);
-      tc::tc_fence_after();
-      float sv[NPAD];
-      const uint32_t ta = tmem_base + lane_addr + TM_S + b * 128;
-      tc::tmem_ld32(ta, sv);
-      tc::tmem_ld32(ta + 32, sv + 32);
-      tc::tmem_ld32(ta + 64, sv + 64);
-      {
-        float tail[32];
-        tc::tmem_ld32(ta + 96, tail);                       // columns 96..127 (only 96..111 are meaningful)
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 16; ++c) sv[96 + c] = tail[c];
-      }
-      tc::tc_fence_before();
-      tc::mbar_arrive_remote(&sempty[b], 0);                // S buffer free for tile i+2 (the leader waits for both CTAs)
-      if (ps.pgy != nullptr && pv) {                        // + pos . G_n from the separable tables
-        const float4* gy = reinterpret_cast<const float4*>(ps.pgy + ((long)t * ps.h + p / ps.w) * NPAD);
-        const float4* gx = reinterpret_cast<const float4*>(ps.pgx + ((long)t * ps.w + p % ps.w) * NPAD);
-#pragma unroll
-        for (int c = 0; c < NPAD / 4; ++c) {
-          const float4 a = __ldg(gy + c), b = __ldg(gx + c);
-          sv[4 * c] += a.x + b.x; sv[4 * c + 1] += a.y + b.y; sv[4 * c + 2] += a.z + b.z; sv[4 * c + 3] += a.w + b.w;
-        }
-      }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int n = 0; n < NPAD; ++n) {
-        const float2 c = gc[n];
-        const float s = n < N ? fmaf(sv[n] + c.x, rk, c.y) : -INFINITY;
-        sv[n] = s;
-        mx = fmaxf(mx, s);
-      }
-      float sum = 0.f;
-      if (MODE == 2) {                                      // the maximum / denominator over ALL slot groups of this pixel
-        const float2 ml = pv ? grp.ml_in[(long)t * P + p] : make_float2(0.f, 1.f);
-        mx = ml.x; sum = ml.y;
-#pragma unroll
-        for (int n = 0; n < NPAD; ++n) sv[n] = __expf(sv[n] - mx);
-      } else {
-#pragma unroll
-        for (int n = 0; n < NPAD; ++n) { const float e = __expf(sv[n] - mx); sv[n] = e; sum += e; }
-      }
-      if (MODE == 1) {
-        if (pv) grp.ml_out[(long)t * P + p] = make_float2(mx, sum);
-        continue;
-      }
-      const float sc = pv ? rv / sum : 0.f;                 // A' = A * rs_v
-      tc::mbar_wait(pempty, (i & 1) ^ 1);                   // Z(i-1) has finished reading P
-#pragma unroll
-      for (int n = 0; n < NROW; ++n) {
-        const float a = pv ? sv[n] * sc : 0.f;
-        const __half hi = __float2half_rn(a);
-        const int off = n * 128 + ((pc ^ (n & 7)) * 16) + pe;
-        *reinterpret_cast<__half*>(p_half + off) = hi;
-        *reinterpret_cast<__half*>(p_half + P_PLANE + off) = __float2half_rn(a - __half2float(hi));
-      }
-      *aux_row1 = __float2half_rn(pv ? 1.f / rv : 0.f);     // sigma_v
-      tc::fence_proxy_async();
-      tc::mbar_arrive(pfull);
-    }
-    // ---- final epilogue: Z^T (lanes = channels) and aux (lanes = slots) -> per-CTA partials ----
-    if (MODE != 1) {
-    tc::mbar_wait(zfull, 0);
-    tc::tc_fence_after();
-    float* Zp = Zpart + (((long)chunk * T + t) * Ntot + n0) * C;
-    for (int mt = 0; mt < 2; ++mt) {
-      const int ch = mt * 128 + r;
-      for (int j = 0; j < 4; ++j) {
-        float v[32];
-        tc::tmem_ld32(tmem_base + lane_addr + TM_Z + mt * NPAD + j * 32, v);   // last chunk over-reads 16 columns (ignored)
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) { const int n = j * 32 + c; if (n < N) Zp[(long)n * C + ch] = v[c]; }
-      }
-    }
-    {
-      float v[32];
-      tc::tmem_ld32(tmem_base + lane_addr + TM_AUX, v);     // reads 16 columns past aux (unused)
-      tc::tmem_ld_wait();
-      if (r < N) { a1part[((long)chunk * T + t) * Ntot + n0 + r] = v[0]; a0part[((long)chunk * T + t) * Ntot + n0 + r] = v[1]; }
-    }
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::cluster_sync();
-  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc2(tmem_base, 512); }
 }
 
 // Total CTAs of one launch of the main-stream tensor-core kernels (attn_tc, mask_tc).  Default: every SM, the
@@ -1238,16 +930,6 @@ inline int tc_attention(const TcWorkspace& ws, __half* gplanes, const float* G, 
   if (groups == 1) {
     g_planes_kernel<<<(unsigned)(((long)T * attn::NROW * C + 255) / 256), 256, 0, s>>>(G, gplanes, N, T);
     SV_CHECK_LAUNCH("g_planes");
-    static const int use_pairs = getenv("SLOTVPS_ATTN_PAIRS") ? atoi(getenv("SLOTVPS_ATTN_PAIRS")) : 0;
-    if (use_pairs && chunks >= 2 && chunks % 2 == 0) {      // CTA pairs along x: S as one M = 256 MMA, G split across the pair
-      SV_TRY(tc::make_tmap_h16_sw128(&mg, gplanes, (uint64_t)T * 2 * attn::NROW, C, attn2::NHALF));
-      SV_TRY(ensure_dyn_smem((const void*)attn_tc2_kernel, attn2::SMEM_BYTES));
-      g_prof_grid = chunks * T;
-      attn_tc2_kernel<<<dim3(chunks, T), attn2::THREADS, attn2::SMEM_BYTES, s>>>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, ws.planes, N, P, T,
-                                                                                 (int)rows, ceil_div(P, attn::TILE_M), 0, ps, SlotGroup());
-      SV_CHECK_LAUNCH("attn_tc");
-      return SLOTVPS_OK;
-    }
     SV_TRY(tc::make_tmap_h16_sw128(&mg, gplanes, (uint64_t)T * 2 * attn::NROW, C, attn::NROW));
     return attn_tc_launch<0>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, ws.planes, N, P, T, rows, chunks, ps, SlotGroup(), s);
   }
