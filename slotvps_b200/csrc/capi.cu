@@ -14,6 +14,7 @@
 #include "pixel_tc.cuh"
 #include "fuse_tc.cuh"
 #include "mask_tc.cuh"
+#include "slot_tc.cuh"
 #include "track.cuh"
 #include "unify.cuh"
 
@@ -70,6 +71,7 @@ struct PreparedStage {
   float *tq_qkv_w, *tq_qkv_b, *tq_ln_w, *tq_ln_b;   // Video Retriever q|k|v stacked [768,256],[768],[3,256]
   float *tw_w, *tw_ln_w, *tw_ln_b;      // first tower layers cls|reg stacked [512,256],[2,256]
   TcStageOperands tc;                   // tensor-core operand planes (pixel_tc.cuh)
+  slot::SlotTcWeights stc;              // fp16 hi/lo planes of the slot-side linears (slot_tc.cuh), when slot_tc_supported
 };
 struct Prepared {
   float* W0;                            // level-0 folded conv weight [256,128]
@@ -95,6 +97,7 @@ static size_t prepared_layout(const slotvps_head_desc* d, void* base, Prepared* 
     ps.tq_ln_w = a.take<float>(3 * C); ps.tq_ln_b = a.take<float>(3 * C);
     ps.tw_w = a.take<float>((size_t)2 * C * C); ps.tw_ln_w = a.take<float>(2 * C); ps.tw_ln_b = a.take<float>(2 * C);
     tc_stage_layout(a, &ps.tc);
+    if (slot::slot_tc_supported(d)) slot::slot_tc_layout(a, d, &ps.stc);
   }
   if (out) *out = p;
   return align_up(a.off);
@@ -164,6 +167,7 @@ struct HeadWs {
   float *rs_k2, *rs_v2;                 // second LayerNorm-scale buffers (stages alternate in overlapped mode)
   float *rs_k, *rs_v, *Zpart, *a0part, *a1part, *Z, *a0, *a1, *Y, *p2, *hdn, *f, *f2;
   float *tqkv, *L, *av, *ty, *thdn, *tw, *c2, *e1;
+  float *p2buf;                         // post-norm2 rows kept for the FFN residual (slot_post_kernel)
   float *pos[SLOTVPS_MAX_LEVELS];       // generated sine embeddings (pos_mode 2)
   float *ybuf;                          // coarse conv_trans partial [T][256][P/4]
   float *splitk;                        // split-K partials of the long-K linears [4][R][256]
@@ -201,6 +205,7 @@ static size_t head_ws_layout(const slotvps_head_desc* d, void* base, size_t cap,
   w.tqkv = a.take<float>((size_t)R * 3 * C); w.L = a.take<float>((size_t)R * R); w.av = a.take<float>((size_t)R * C);
   w.ty = a.take<float>((size_t)R * C); w.thdn = w.hdn;
   w.tw = a.take<float>((size_t)R * 2 * C); w.c2 = a.take<float>((size_t)R * C); w.e1 = a.take<float>((size_t)R * C);
+  w.p2buf = a.take<float>((size_t)R * C);
   for (int l = 0; l < SLOTVPS_MAX_LEVELS; ++l)
     w.pos[l] = (d->pos_mode == 2 && l < d->n_levels) ? a.take<float>((size_t)C * d->h[l] * d->w[l]) : nullptr;
   w.ybuf = a.take<float>((size_t)T * C * (Pmax / 4 + 1));
@@ -288,7 +293,7 @@ static int level_fuse_frame(const float* prev, const float* x, const float* conv
 // (use_tc: the LayerNorm statistics -- 72 % of the contraction's FLOPs -- run on the tensor pipe from the
 //  level's bf16 operand planes, pixel_tc.cuh; the slot-softmax contraction below still runs in fp32)
 static int pixel_attention(const float* x, long x_bs, const float* pos, long pos_bs, const PreparedStage& ps,
-                           const HeadWs& w0, const StagePix& px, int T, int N, int P, bool use_tc, cudaStream_t s) {
+                           const HeadWs& w0, const StagePix& px, int T, int N, int P, bool use_tc, cudaStream_t s, bool gplanes_ready = false) {
   HeadWs w = w0;
   w.rs_k = px.rs_k; w.rs_v = px.rs_v; w.tc = px.tc;
   if (px.overlapped) {
@@ -322,7 +327,7 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
       SV_TRY(sgemm(g, s));
       pa.pgy = pgy; pa.pgx = pgx;
     }
-    SV_TRY(tc_attention(w.tc, w.tc.gplanes, w.G, w.g0, w.g1, w.rs_k, w.rs_v, w.Zpart, w.a0part, w.a1part, T, N, P, &chunks, s, pa));
+    SV_TRY(tc_attention(w.tc, w.tc.gplanes, w.G, w.g0, w.g1, w.rs_k, w.rs_v, w.Zpart, w.a0part, w.a1part, T, N, P, &chunks, s, pa, gplanes_ready));
   } else {
     const int NB = ceil_div(N, 128);
     chunks = attn_chunks(P, T);
@@ -351,6 +356,110 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
   return SLOTVPS_OK;
 }
 
+// ---- Video Retriever over the T*N slots of all frames (:308-322, 494-527, 550-572): f -> f2 = f + block(f) --------
+static int video_retriever(const slotvps_head_desc* d, const slotvps_stage_params& sp, const PreparedStage& ps, const HeadWs& w, cudaStream_t s) {
+  const int T = d->n_frames, N = d->n_slots, R = T * N, TF = d->temporal_dim_feedforward;
+  SV_REQUIRE(sp.tq_to_q_w != nullptr, "temporal stage without temporal_query_head parameters");
+  SV_TRY(linear_fast(w.f, ps.tq_qkv_w, ps.tq_qkv_b, w.tqkv, R, C, 3 * C, 0, nullptr, s));
+  SV_TRY(ln_rows(w.tqkv, nullptr, ps.tq_ln_w, ps.tq_ln_b, 3, nullptr, w.tqkv, 3 * R, 0, s));   // rows r*3+{q,k,v}
+  {
+    GemmArgs g;                                       // L[l,u] = q_l . k_u
+    g.A = w.tqkv; g.a_ms = 3 * C; g.a_ks = 1;
+    g.B = w.tqkv + C; g.b_ks = 1; g.b_ns = 3 * C;
+    g.Cm = w.L; g.c_ms = R; g.c_ns = 1;
+    g.M = R; g.N = R; g.K = C;
+    SV_TRY(sgemm(g, s));
+  }
+  col_softmax_kernel<<<ceil_div(R, 32), 256, 0, s>>>(w.L, R);
+  SV_CHECK_LAUNCH("col_softmax");
+  {
+    GemmArgs g;                                       // av = A . v
+    g.A = w.L; g.a_ms = R; g.a_ks = 1;
+    g.B = w.tqkv + 2 * C; g.b_ks = 3 * C; g.b_ns = 1;
+    g.Cm = w.av; g.c_ms = C; g.c_ns = 1;
+    g.M = R; g.N = C; g.K = R;
+    SV_TRY(sgemm(g, s));
+  }
+  SV_TRY(ln_rows(w.av, nullptr, sp.tq_no_w, sp.tq_no_b, 1, w.f, w.ty, R, 1, s));              // f + relu(LN(av))
+  SV_TRY(ln_rows(w.ty, nullptr, sp.tq_norm2_w, sp.tq_norm2_b, 1, nullptr, w.ty, R, 0, s));    // y
+  SV_TRY(linear_fast(w.ty, sp.tq_lin1_w, sp.tq_lin1_b, w.thdn, R, C, TF, temporal_ffn_act_of(d), nullptr, s));
+  SV_TRY(linear_fast(w.thdn, sp.tq_lin2_w, sp.tq_lin2_b, w.qraw, R, TF, C, 0, w.ty, s, -1, -1, w.splitk));
+  SV_TRY(ln_rows(w.qraw, nullptr, sp.tq_norm3_w, sp.tq_norm3_b, 1, w.f, w.f2, R, 0, s));      // X + LN3(...)  (:317)
+  return SLOTVPS_OK;
+}
+
+static int pixel_attention(const float* x, long x_bs, const float* pos, long pos_bs, const PreparedStage& ps,
+                           const HeadWs& w0, const StagePix& px, int T, int N, int P, bool use_tc, cudaStream_t s, bool gplanes_ready);
+
+// ---- the same stage with the slot side on the tensor-core slot-update kernels (slot_tc.cuh): N <= 104 ------------
+static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& sp, const PreparedStage& ps, const HeadWs& w,
+                        const StagePix& px, const float* x, long x_bs, const float* pos, long pos_bs, int h, int wd, bool temporal,
+                        float* cls_out, long cls_frame_stride, float* emb_out, long emb_frame_stride, cudaStream_t s) {
+  const int T = d->n_frames, N = d->n_slots, R = T * N, P = h * wd, F = d->dim_feedforward;
+  // (1) slot self-attention core (:346-352): in_proj + 8-head attention on the generic kernels
+  SV_TRY(linear_fast(w.slots, sp.in_proj_w, sp.in_proj_b, w.qkv, R, C, 3 * C, 0, nullptr, s));
+  {
+    size_t smem = (size_t)(2 * N * 33 + 8 * N) * sizeof(float);
+    if (smem > 48 * 1024) SV_TRY(ensure_dyn_smem((const void*)mha_core_kernel, smem));
+    mha_core_kernel<<<dim3(d->nhead, T, 4), 256, smem, s>>>(w.qkv, w.mo, N, d->nhead);
+    SV_CHECK_LAUNCH("mha_core");
+  }
+  // (2) out_proj + norm1, to_q + norm_q, folded key operands G / g0 / g1 and their fp16 planes: one kernel, slots resident
+  {
+    CUtensorMap m_out, m_q, m_wk;
+    SV_TRY(slot::slot_wmap(&m_out, ps.stc.out_proj, C, C));
+    SV_TRY(slot::slot_wmap(&m_q, ps.stc.to_q, C, C));
+    SV_TRY(slot::slot_wmap(&m_wk, ps.stc.wkT, C, C));
+    slot::PreParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.N = N; pp.mo = w.mo; pp.slots = w.slots;
+    pp.out_b = sp.out_proj_b; pp.n1_w = sp.norm1_w; pp.n1_b = sp.norm1_b; pp.q_b = sp.to_q_b;
+    pp.nq_w = sp.nq_w; pp.nq_b = sp.nq_b; pp.nk_w = sp.nk_w; pp.nk_b = sp.nk_b; pp.bk_c = ps.bk_c;
+    pp.p = w.p; pp.G = w.G; pp.g0 = w.g0; pp.g1 = w.g1; pp.gplanes = px.tc.gplanes;
+    SV_TRY(ensure_dyn_smem((const void*)slot::slot_pre_kernel, slot::SMEM_BYTES));
+    slot::slot_pre_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_out, m_q, m_wk, pp);
+    SV_CHECK_LAUNCH("slot_pre");
+  }
+  // (3) pixel side: Z, a0, a1
+  SV_TRY(pixel_attention(x, x_bs, pos, pos_bs, ps, w, px, T, N, P, true, s, true));
+  // (4..7) value projection, norms, FFN [, Video Retriever], towers
+  {
+    CUtensorMap m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg;
+    SV_TRY(slot::slot_wmap(&m_wv, ps.stc.wv, C, C));
+    SV_TRY(slot::slot_wmap(&m_l1, ps.stc.lin1, F, C));
+    SV_TRY(slot::slot_wmap(&m_l2, ps.stc.lin2, C, F));
+    SV_TRY(slot::slot_wmap(&m_tw, ps.stc.tw, 2 * C, C));
+    SV_TRY(slot::slot_wmap(&m_c1, ps.stc.cls1, C, C));
+    SV_TRY(slot::slot_wmap(&m_r1, ps.stc.reg1, C, C));
+    SV_TRY(slot::slot_wmap(&m_lg, ps.stc.logit, d->num_classes, C));
+    slot::PostParams q;
+    memset(&q, 0, sizeof(q));
+    q.N = N; q.F = F; q.act = ffn_act_of(d); q.ncls = d->num_classes;
+    q.Z = w.Z; q.a0 = w.a0; q.a1 = w.a1; q.p = w.p;
+    q.nv_w = sp.nv_w; q.nv_b = sp.nv_b; q.bv_c = ps.bv_c; q.no_w = sp.no_w; q.no_b = sp.no_b; q.n2_w = sp.norm2_w; q.n2_b = sp.norm2_b;
+    q.b1 = sp.lin1_b; q.b2 = sp.lin2_b; q.n3_w = sp.norm3_w; q.n3_b = sp.norm3_b;
+    q.p2buf = w.p2buf; q.f_out = w.f;
+    q.tw_ln_w = ps.tw_ln_w; q.tw_ln_b = ps.tw_ln_b; q.c1_nw = sp.cls1_nw; q.c1_nb = sp.cls1_nb; q.r1_nw = sp.reg1_nw; q.r1_nb = sp.reg1_nb;
+    q.logit_b = sp.logit_b;
+    q.slots_out = w.slots; q.emb_out = emb_out; q.cls_out = cls_out; q.emb_fs = emb_frame_stride; q.cls_fs = cls_frame_stride;
+    SV_TRY(ensure_dyn_smem((const void*)slot::slot_post_kernel, slot::SMEM_BYTES));
+    if (!temporal) {
+      q.phases = 3;
+      slot::slot_post_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg, q);
+      SV_CHECK_LAUNCH("slot_post");
+    } else {
+      q.phases = 1;
+      slot::slot_post_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg, q);
+      SV_CHECK_LAUNCH("slot_post");
+      SV_TRY(video_retriever(d, sp, ps, w, s));
+      q.phases = 2; q.f_in = w.f2;
+      slot::slot_post_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg, q);
+      SV_CHECK_LAUNCH("slot_post(towers)");
+    }
+  }
+  return SLOTVPS_OK;
+}
+
 // ---- one MaskRCNNHead stage for all frames (dynamic_mask_head.py:291-400) ------------------------------
 static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp, const PreparedStage& ps, const HeadWs& w,
                      const StagePix& px, const float* x, long x_bs, const float* pos, long pos_bs, int h, int wd, bool temporal, bool use_tc,
@@ -360,6 +469,9 @@ static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp,
   if (slots_in)                                              // teacher forcing: this stage's slots come from the caller
     for (int t = 0; t < T; ++t)
       if (slots_in[t]) SV_TRY(dcopy(slots_in[t], w.slots + (long)t * N * C, (long)N * C, s));
+  static const int slot_tc_on = getenv("SLOTVPS_SLOT_TC") ? atoi(getenv("SLOTVPS_SLOT_TC")) : 1;
+  if (slot_tc_on && use_tc && slot::slot_tc_supported(d))
+    return run_stage_tc(d, sp, ps, w, px, x, x_bs, pos, pos_bs, h, wd, temporal, cls_out, cls_frame_stride, emb_out, emb_frame_stride, s);
   // (1) slot self-attention + norm1  (:346-358)
   SV_TRY(linear_fast(w.slots, sp.in_proj_w, sp.in_proj_b, w.qkv, R, C, 3 * C, 0, nullptr, s));
   {
@@ -389,32 +501,7 @@ static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp,
   // (6) Video Retriever over the T*N slots of all frames (:308-322, 494-527, 550-572)
   const float* fcur = w.f;
   if (temporal) {
-    SV_REQUIRE(sp.tq_to_q_w != nullptr, "temporal stage without temporal_query_head parameters");
-    SV_TRY(linear_fast(w.f, ps.tq_qkv_w, ps.tq_qkv_b, w.tqkv, R, C, 3 * C, 0, nullptr, s));
-    SV_TRY(ln_rows(w.tqkv, nullptr, ps.tq_ln_w, ps.tq_ln_b, 3, nullptr, w.tqkv, 3 * R, 0, s));   // rows r*3+{q,k,v}
-    {
-      GemmArgs g;                                       // L[l,u] = q_l . k_u
-      g.A = w.tqkv; g.a_ms = 3 * C; g.a_ks = 1;
-      g.B = w.tqkv + C; g.b_ks = 1; g.b_ns = 3 * C;
-      g.Cm = w.L; g.c_ms = R; g.c_ns = 1;
-      g.M = R; g.N = R; g.K = C;
-      SV_TRY(sgemm(g, s));
-    }
-    col_softmax_kernel<<<ceil_div(R, 32), 256, 0, s>>>(w.L, R);
-    SV_CHECK_LAUNCH("col_softmax");
-    {
-      GemmArgs g;                                       // av = A . v
-      g.A = w.L; g.a_ms = R; g.a_ks = 1;
-      g.B = w.tqkv + 2 * C; g.b_ks = 3 * C; g.b_ns = 1;
-      g.Cm = w.av; g.c_ms = C; g.c_ns = 1;
-      g.M = R; g.N = C; g.K = R;
-      SV_TRY(sgemm(g, s));
-    }
-    SV_TRY(ln_rows(w.av, nullptr, sp.tq_no_w, sp.tq_no_b, 1, w.f, w.ty, R, 1, s));              // f + relu(LN(av))
-    SV_TRY(ln_rows(w.ty, nullptr, sp.tq_norm2_w, sp.tq_norm2_b, 1, nullptr, w.ty, R, 0, s));    // y
-    SV_TRY(linear_fast(w.ty, sp.tq_lin1_w, sp.tq_lin1_b, w.thdn, R, C, TF, temporal_ffn_act_of(d), nullptr, s));
-    SV_TRY(linear_fast(w.thdn, sp.tq_lin2_w, sp.tq_lin2_b, w.qraw, R, TF, C, 0, w.ty, s, -1, -1, w.splitk));
-    SV_TRY(ln_rows(w.qraw, nullptr, sp.tq_norm3_w, sp.tq_norm3_b, 1, w.f, w.f2, R, 0, s));      // X + LN3(...)  (:317)
+    SV_TRY(video_retriever(d, sp, ps, w, s));
     fcur = w.f2;
   }
   // (7) towers (:390-400): first layers of cls|reg share the input
@@ -556,6 +643,19 @@ int slotvps_prepare_weights_ex(const slotvps_head_desc* d, const slotvps_stage_p
     SV_TRY(dcopy(sp.cls0_nw, ps.tw_ln_w, C, s)); SV_TRY(dcopy(sp.reg0_nw, ps.tw_ln_w + C, C, s));
     SV_TRY(dcopy(sp.cls0_nb, ps.tw_ln_b, C, s)); SV_TRY(dcopy(sp.reg0_nb, ps.tw_ln_b + C, C, s));
     SV_TRY(tc_prepare_stage(sp, ps.Wk_c, ps.bk_c, ps.Wv_c, ps.bv_c, ps.tc, s));
+    if (slot::slot_tc_supported(d)) {
+      const int F = d->dim_feedforward;
+      SV_TRY(slot::slot_planes(sp.out_proj_w, C, C, ps.stc.out_proj, s));
+      SV_TRY(slot::slot_planes(sp.to_q_w, C, C, ps.stc.to_q, s));
+      SV_TRY(slot::slot_planes(ps.Wk_cT, C, C, ps.stc.wkT, s));
+      SV_TRY(slot::slot_planes(ps.Wv_c, C, C, ps.stc.wv, s));
+      SV_TRY(slot::slot_planes(sp.lin1_w, F, C, ps.stc.lin1, s));
+      SV_TRY(slot::slot_planes(sp.lin2_w, C, F, ps.stc.lin2, s));
+      SV_TRY(slot::slot_planes(ps.tw_w, 2 * C, C, ps.stc.tw, s));
+      SV_TRY(slot::slot_planes(sp.cls1_w, C, C, ps.stc.cls1, s));
+      SV_TRY(slot::slot_planes(sp.reg1_w, C, C, ps.stc.reg1, s));
+      SV_TRY(slot::slot_planes(sp.logit_w, d->num_classes, C, ps.stc.logit, s));
+    }
   }
   return SLOTVPS_OK;
 }

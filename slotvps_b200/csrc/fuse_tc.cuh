@@ -25,6 +25,9 @@ constexpr int AUX_BYTES = 4096;               // barriers, tmem pointer, bias [2
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + AUX_BYTES + 1024;
 constexpr int THREADS = 320;                   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 constexpr uint32_t IDESC = tc::make_idesc_f16(128, 256, 0, 0);
+// conv_trans weight planes carry 2^8 (a weight of ~0.05 would have a subnormal fp16 lo plane: ~1e-6 relative instead of
+// 2.4e-7); the epilogue multiplies the accumulator by 2^-8 (exact)
+constexpr float WSCALE = 256.f, WSCALE_INV = 1.f / 256.f;
 
 struct Params {
   int rows;            // T * P pixel rows of this launch
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(256) conv_planes_kernel(const float* __restric
   if (i >= C * K) return;
   int o = i / K, c = i % K;
   __half h, l;
-  split_bf16(W[(long)o * ld + col0 + c], h, l);
+  split_bf16(W[(long)o * ld + col0 + c] * fuse::WSCALE, h, l);       // scaled: keeps the lo plane out of fp16's subnormal range
   out[i] = h; out[(long)C * K + i] = l;
 }
 
@@ -253,7 +256,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (j == jhalf * 4 + 3) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }      // this warp's half is drained
         if (!rv) continue;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] += bias[j * 32 + c];
+        for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], WSCALE_INV, bias[j * 32 + c]);
         if (prm.y_out) {
           float* dst = prm.y_out + (long)row * C + j * 32;
 #pragma unroll

@@ -919,7 +919,7 @@ inline int attn_tc_launch(const CUtensorMap& mx, const CUtensorMap& mg, const fl
 // the groups are combined, then one accumulation pass per group writes its slots' rows of the partials.
 inline int tc_attention(const TcWorkspace& ws, __half* gplanes, const float* G, const float* g0, const float* g1,
                         const float* rs_k, const float* rs_v, float* Zpart, float* a0part, float* a1part, int T, int N, int P,
-                        int* chunks_out, cudaStream_t s, const PosSep& ps = PosSep()) {
+                        int* chunks_out, cudaStream_t s, const PosSep& ps = PosSep(), bool gplanes_ready = false) {
   CUtensorMap mx, mg;
   const long rows = (long)T * P;
   SV_TRY(tc::make_tmap_h16_sw128(&mx, ws.planes, (uint64_t)(ps.enabled ? 2 : 4) * 4 * rows, 64, attn::TILE_M));
@@ -928,8 +928,10 @@ inline int tc_attention(const TcWorkspace& ws, __half* gplanes, const float* G, 
   const int groups = ceil_div(N, attn::NROW);
   const size_t gstride = (size_t)T * 2 * attn::NROW * C;
   if (groups == 1) {
-    g_planes_kernel<<<(unsigned)(((long)T * attn::NROW * C + 255) / 256), 256, 0, s>>>(G, gplanes, N, T);
-    SV_CHECK_LAUNCH("g_planes");
+    if (!gplanes_ready) {                                     // slot_pre_kernel writes the planes itself
+      g_planes_kernel<<<(unsigned)(((long)T * attn::NROW * C + 255) / 256), 256, 0, s>>>(G, gplanes, N, T);
+      SV_CHECK_LAUNCH("g_planes");
+    }
     SV_TRY(tc::make_tmap_h16_sw128(&mg, gplanes, (uint64_t)T * 2 * attn::NROW, C, attn::NROW));
     return attn_tc_launch<0>(mx, mg, g0, g1, rs_k, rs_v, Zpart, a0part, a1part, ws.planes, N, P, T, rows, chunks, ps, SlotGroup(), s);
   }

@@ -39,6 +39,10 @@ constexpr uint32_t IDESC128 = tc::make_idesc_f16(128, 128, 0, 0);
 constexpr uint32_t IDESC32 = tc::make_idesc_f16(128, 32, 0, 0);
 constexpr int TM_D = 0;                        // main accumulator, 256 columns (towers: 512)
 constexpr int TM_D1 = 256;                     // two 128-column FFN hidden accumulators
+// Weight planes are stored scaled by 2^8: fp16 has 5 exponent bits, so the lo plane of a weight of ~0.05 would be
+// subnormal (absolute step 6e-8, ~1e-6 relative instead of 2.4e-7 -- and for sums of random-sign terms the relative
+// error of the sum equals the per-term one).  Every accumulator read is multiplied by 2^-8 (exact).
+constexpr float WSCALE = 256.f, WSCALE_INV = 1.f / 256.f;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(OFF_HB % 1024 == 0 && OFF_RING % 1024 == 0 && ACT_SUB % 1024 == 0, "swizzle atoms");
 
@@ -48,7 +52,7 @@ __global__ void __launch_bounds__(256) linear_planes_kernel(const float* __restr
   if (i >= (long)Opad * K) return;
   const int o = (int)(i / K);
   __half h = __float2half_rn(0.f), l = h;
-  if (o < O) split_bf16(W[i], h, l);
+  if (o < O) split_bf16(W[i] * WSCALE, h, l);
   out[i] = h;
   out[(long)Opad * K + i] = l;
 }
@@ -141,6 +145,15 @@ __device__ __forceinline__ void ldg32(const float* __restrict__ p, float* v) {  
     v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
   }
 }
+// coherent variant (plain ld.global): rows this kernel wrote earlier itself must not go through the non-coherent path
+__device__ __forceinline__ void ldc32(const float* p, float* v) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 a;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p + 4 * q) : "memory");
+    v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+  }
+}
 __device__ __forceinline__ void stg32(float* p, const float* v) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -168,6 +181,12 @@ __device__ __forceinline__ void load_rows_to_act(uint8_t* smem, const float* __r
 struct Tm {
   uint32_t base;                                // tmem_base + lane quadrant
   __device__ __forceinline__ void ld(int col, float* v) const { tc::tmem_ld32(base + col, v); tc::tmem_ld_wait(); }
+  // raw GEMM output (weights carry WSCALE)
+  __device__ __forceinline__ void ldw(int col, float* v) const {
+    tc::tmem_ld32(base + col, v); tc::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] *= WSCALE_INV;
+  }
   __device__ __forceinline__ void st(int col, const float* v) const { tc::tmem_st32(base + col, v); }
 };
 // variance pass + normalisation constants of 256 TMEM columns holding the final pre-norm values (sum already known)
@@ -245,7 +264,7 @@ slot_pre_kernel(const __grid_constant__ CUtensorMap m_out, const __grid_constant
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
       float v[32], bb[32], rr[32];
-      tm.ld(TM_D + 32 * j, v);
+      tm.ldw(TM_D + 32 * j, v);
       ldg32(P.out_b + 32 * j, bb);
       if (valid) ldg32(P.slots + row + 32 * j, rr);
 #pragma unroll
@@ -273,7 +292,7 @@ slot_pre_kernel(const __grid_constant__ CUtensorMap m_out, const __grid_constant
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
       float v[32], bb[32];
-      tm.ld(TM_D + 32 * j, v);
+      tm.ldw(TM_D + 32 * j, v);
       ldg32(P.q_b + 32 * j, bb);
 #pragma unroll
       for (int c = 0; c < 32; ++c) { v[c] += bb[c]; s += v[c]; }
@@ -309,7 +328,7 @@ slot_pre_kernel(const __grid_constant__ CUtensorMap m_out, const __grid_constant
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
       float v[32];
-      tm.ld(TM_D + 32 * j, v);
+      tm.ldw(TM_D + 32 * j, v);
       if (r < NR) {
         uint32_t hi[16], lo[16];
 #pragma unroll
@@ -470,7 +489,7 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
 #pragma unroll 1
       for (int j = 0; j < 8; ++j) {
         float v[32], gv[32], bv[32], bc[32];
-        tm.ld(TM_D + 32 * j, v);
+        tm.ldw(TM_D + 32 * j, v);
         ldg32(P.nv_w + 32 * j, gv); ldg32(P.nv_b + 32 * j, bv); ldg32(P.bv_c + 32 * j, bc);
 #pragma unroll
         for (int c = 0; c < 32; ++c) { v[c] = gv[c] * fmaf(bc[c], a1r, v[c]) + bv[c] * a0r; s += v[c]; }
@@ -503,7 +522,7 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
           ldg32(P.b1 + c * 128 + 32 * j, bb);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) h[j][e] = act_fn(h[j][e] + bb[e], P.act);
+          for (int e = 0; e < 32; ++e) h[j][e] = act_fn(fmaf(h[j][e], WSCALE_INV, bb[e]), P.act);
         }
         tc::tc_fence_before();
         tc::mbar_arrive(&b->d1free[bf]);
@@ -521,9 +540,9 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
 #pragma unroll 1
       for (int j = 0; j < 8; ++j) {
         float v[32], bb[32], pp[32];
-        tm.ld(TM_D + 32 * j, v);
+        tm.ldw(TM_D + 32 * j, v);
         ldg32(P.b2 + 32 * j, bb);
-        if (valid) ldg32(P.p2buf + row + 32 * j, pp);
+        if (valid) ldc32(P.p2buf + row + 32 * j, pp);
 #pragma unroll
         for (int c = 0; c < 32; ++c) { v[c] = v[c] + bb[c] + (valid ? pp[c] : 0.f); s += v[c]; }
         tm.st(TM_D + 32 * j, v);
@@ -540,15 +559,17 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
     if (ph1) {
       // ---- towers (:390-400): first layers cls0 | reg0 share the input; 512 accumulator columns ----
       wait_d();
-      auto col_sum = [&](int col0) {
+      auto col_sum = [&](int col0) {                              // unscale the raw GEMM output in place, return the row sum
         float s = 0.f;
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
           float v[32];
-          tm.ld(col0 + 32 * j, v);
+          tm.ldw(col0 + 32 * j, v);
 #pragma unroll
           for (int c = 0; c < 32; ++c) s += v[c];
+          tm.st(col0 + 32 * j, v);
         }
+        tc::tmem_st_wait();
         return s;
       };
       float s = col_sum(TM_D);
@@ -561,7 +582,7 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
       wait_d();
       {
         float v[32];
-        tm.ld(TM_D, v);
+        tm.ldw(TM_D, v);
         if (valid) {
           float* dst = P.cls_out + (long)t * P.cls_fs + (long)r * P.ncls;
           for (int c = 0; c < P.ncls; ++c) dst[c] = v[c] + __ldg(P.logit_b + c);
