@@ -413,6 +413,7 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     slot::PreParams pp;
     memset(&pp, 0, sizeof(pp));
     pp.N = N; pp.mo = w.mo; pp.slots = w.slots;
+    pp.dbg = getenv("SLOTVPS_SLOT_DEBUG") ? atoi(getenv("SLOTVPS_SLOT_DEBUG")) : 0;
     pp.out_b = sp.out_proj_b; pp.n1_w = sp.norm1_w; pp.n1_b = sp.norm1_b; pp.q_b = sp.to_q_b;
     pp.nq_w = sp.nq_w; pp.nq_b = sp.nq_b; pp.nk_w = sp.nk_w; pp.nk_b = sp.nk_b; pp.bk_c = ps.bk_c;
     pp.p = w.p; pp.G = w.G; pp.g0 = w.g0; pp.g1 = w.g1; pp.gplanes = px.tc.gplanes;
