@@ -196,14 +196,24 @@ int slotvps_head_mask_logits_ex(const slotvps_head_desc* d, void* head_workspace
  *   (Instances.masks), only the first K' planes are written.                                 */
 typedef struct slotvps_fusion_cfg {
   int32_t num_classes, stuff_num, small_area, max_iters;
-  float threshold, pixel_threshold;   /* compared in fp32, as torch / numpy do (:691, :607)      */
+  float threshold, pixel_threshold;   /* compared in fp32, as torch / numpy do (:691, :607); pixel_threshold must be > 1/3
+                                         (the exact two-pass mask_removal keeps at most two candidates per pixel)          */
   double fraction_threshold;          /* compared in fp64, as numpy does (:621-622)              */
+  int32_t logits_width;               /* columns of pred_logits: 0 or num_classes = with the "no object" column (:688-691),
+                                         num_classes - 1 = without it, no class test (:692-693)                            */
+  int32_t reserved;
 } slotvps_fusion_cfg;
 int slotvps_fusion_workspace_bytes(int n_slots, int H, int W, size_t* bytes);
 int slotvps_panoptic_fuse(const slotvps_fusion_cfg* cfg, const float* pred_logits, const float* pred_masks,
                           int n_slots, int h, int w, int H, int W,
                           int64_t* panoptic, int32_t* meta, float* masks_out, int masks_cap,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* The reference's small-segment loop (:761-792) has no iteration bound; slotvps_panoptic_fuse launches cfg->max_iters
+ * passes (each exits at once after the fixed point).  If meta[3] == 0 afterwards the id map holds the sentinel 255 and
+ * this call runs `iters` more passes from the state left in `workspace` (same cfg / masks / shapes), then relabels.   */
+int slotvps_panoptic_fuse_resume(const slotvps_fusion_cfg* cfg, const float* pred_masks, int n_slots, int h, int w, int H, int W,
+                                 int64_t* panoptic, int32_t* meta, float* masks_out, int masks_cap,
+                                 void* workspace, size_t workspace_bytes, int iters, void* stream);
 
 /* Sine position embedding (PositionEmbeddingSine.forward, position_encoding.py:236-256,
  * normalize=True, 128 feats/axis): out [256,h,w].                                           */

@@ -93,6 +93,7 @@ class FusionCfg(C.Structure):
     _fields_ = [
         ("num_classes", C.c_int32), ("stuff_num", C.c_int32), ("small_area", C.c_int32), ("max_iters", C.c_int32),
         ("threshold", C.c_float), ("pixel_threshold", C.c_float), ("fraction_threshold", C.c_double),
+        ("logits_width", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -119,6 +120,8 @@ SYMBOLS = {
     "slotvps_fusion_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "slotvps_panoptic_fuse": (C.c_int, [C.POINTER(FusionCfg), P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P,
                                         P, C.c_int, P, C.c_size_t, P]),
+    "slotvps_panoptic_fuse_resume": (C.c_int, [C.POINTER(FusionCfg), P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P,
+                                               P, C.c_int, P, C.c_size_t, C.c_int, P]),
     "slotvps_sine_pos": (C.c_int, [P, C.c_int, C.c_int, P]),
     "slotvps_semantic_argmax": (C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P]),
     "slotvps_unify_workspace_bytes": (C.c_int, [C.POINTER(C.c_size_t)]),

@@ -1187,37 +1187,18 @@ int slotvps_fusion_workspace_bytes(int n_slots, int H, int W, size_t* bytes) {
   *bytes = fuse_ws_layout(n_slots, H, W, nullptr, (size_t)-1, nullptr);
   return SLOTVPS_OK;
 }
-int slotvps_panoptic_fuse(const slotvps_fusion_cfg* cfg, const float* pred_logits, const float* pred_masks, int N, int h, int w,
-                          int H, int W, int64_t* panoptic, int32_t* meta, float* masks_out, int masks_cap, void* workspace,
-                          size_t workspace_bytes, void* stream) {
-  SV_REQUIRE(cfg && pred_logits && pred_masks && panoptic && meta && workspace, "null argument");
-  SV_REQUIRE(N > 0 && N <= FUSE_MAXN && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
-  SV_REQUIRE(cfg->num_classes >= 2 && cfg->stuff_num >= 0 && cfg->max_iters >= 1, "bad config");
-  cudaStream_t s = (cudaStream_t)stream;
-  SV_PROF_ENTRY();
-  FuseWs ws;
-  if (fuse_ws_layout(N, H, W, workspace, workspace_bytes, &ws) > workspace_bytes)
-    return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
+static int fuse_iterate(const slotvps_fusion_cfg* cfg, const float* pred_masks, int N, int h, int w, int H, int W, int64_t* panoptic,
+                        int32_t* meta, float* masks_out, int masks_cap, const FuseWs& ws, int iters, cudaStream_t s) {
   const long HW = (long)H * W;
   const int grid = (int)((HW + 255) / 256 < 148 * 16 ? (HW + 255) / 256 : 148 * 16);
-  SV_CHECK_CUDA(cudaMemsetAsync(ws.pair, 0, (size_t)N * N * sizeof(unsigned int), s));
-  SV_CHECK_CUDA(cudaMemsetAsync(meta, 0, (size_t)(4 + 3 * N) * sizeof(int32_t), s));
-  fuse_select_kernel<<<1, FUSE_MAXN, 0, s>>>(pred_logits, N, cfg->num_classes, cfg->stuff_num, cfg->threshold, ws.st);
-  SV_CHECK_LAUNCH("fuse_select");
   const bool x4 = (H == 4 * h && W == 4 * w);              // the shipped case: 1/4-resolution masks
   const long nblk = (long)h * w;
   const int grid4 = (int)((nblk + 255) / 256 < 148 * 8 ? (nblk + 255) / 256 : 148 * 8);
-  if (x4) fuse_count4_kernel<<<grid4, 256, 0, s>>>(pred_masks, h, w, cfg->pixel_threshold, ws.st, ws.pair, ws.cand);
-  else fuse_count_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, cfg->pixel_threshold, ws.st, ws.pair, ws.cand);
-  SV_CHECK_LAUNCH("fuse_count");
-  fuse_greedy_kernel<<<1, 32, 0, s>>>(ws.st, ws.pair, HW, cfg->fraction_threshold);
-  SV_CHECK_LAUNCH("fuse_greedy");
-  for (int it = 0; it < cfg->max_iters; ++it) {
-    if (x4) fuse_argmax4_kernel<<<grid4, 256, 0, s>>>(pred_masks, h, w, ws.st, ws.cand, ws.ids);
-    else fuse_argmax_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, ws.st, ws.cand, ws.ids);
+  FilterArgs fa{cfg->stuff_num, (unsigned)cfg->small_area, N, meta};
+  for (int it = 0; it < iters; ++it) {                      // every pass exits at once when the fixed point was reached
+    if (x4) fuse_argmax4_kernel<<<grid4, 256, 0, s>>>(pred_masks, h, w, ws.st, ws.cand, ws.ids, fa);
+    else fuse_argmax_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, ws.st, ws.cand, ws.ids, fa);
     SV_CHECK_LAUNCH("fuse_argmax");
-    fuse_filter_kernel<<<1, FUSE_MAXN, 0, s>>>(ws.st, cfg->stuff_num, (unsigned)cfg->small_area, N, meta);
-    SV_CHECK_LAUNCH("fuse_filter");
   }
   fuse_relabel_kernel<<<grid, 256, 0, s>>>(ws.st, ws.ids, HW, (long long*)panoptic);
   SV_CHECK_LAUNCH("fuse_relabel");
@@ -1226,6 +1207,51 @@ int slotvps_panoptic_fuse(const slotvps_fusion_cfg* cfg, const float* pred_logit
     SV_CHECK_LAUNCH("fuse_masks");
   }
   return SLOTVPS_OK;
+}
+
+int slotvps_panoptic_fuse(const slotvps_fusion_cfg* cfg, const float* pred_logits, const float* pred_masks, int N, int h, int w,
+                          int H, int W, int64_t* panoptic, int32_t* meta, float* masks_out, int masks_cap, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  SV_REQUIRE(cfg && pred_logits && pred_masks && panoptic && meta && workspace, "null argument");
+  SV_REQUIRE(N > 0 && N <= FUSE_MAXN && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
+  SV_REQUIRE(cfg->num_classes >= 2 && cfg->stuff_num >= 0 && cfg->max_iters >= 1, "bad config");
+  // the exact two-pass mask_removal keeps at most two candidates per pixel: needs pixel_threshold > 1/3
+  SV_REQUIRE(cfg->pixel_threshold > 1.f / 3.f, "pixel_threshold must be > 1/3");
+  cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
+  FuseWs ws;
+  if (fuse_ws_layout(N, H, W, workspace, workspace_bytes, &ws) > workspace_bytes)
+    return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
+  const long HW = (long)H * W;
+  const int grid = (int)((HW + 255) / 256 < 148 * 16 ? (HW + 255) / 256 : 148 * 16);
+  // logits_width == num_classes: the last column is "no object" (:688-691); num_classes - 1 columns: no such test (:692-693)
+  const int width = cfg->logits_width > 0 ? cfg->logits_width : cfg->num_classes;
+  SV_REQUIRE(width == cfg->num_classes || width == cfg->num_classes - 1, "logits_width must be num_classes or num_classes - 1");
+  fuse_select_kernel<<<1, FUSE_MAXN, 0, s>>>(pred_logits, N, width, cfg->stuff_num, cfg->threshold, width == cfg->num_classes ? 1 : 0, ws.st,
+                                             ws.pair, meta);
+  SV_CHECK_LAUNCH("fuse_select");
+  const bool x4 = (H == 4 * h && W == 4 * w);
+  const long nblk = (long)h * w;
+  const int grid4 = (int)((nblk + 255) / 256 < 148 * 8 ? (nblk + 255) / 256 : 148 * 8);
+  if (x4) fuse_count4_kernel<<<grid4, 256, 0, s>>>(pred_masks, h, w, cfg->pixel_threshold, cfg->fraction_threshold, ws.st, ws.pair, ws.cand);
+  else fuse_count_kernel<<<grid, 256, 0, s>>>(pred_masks, h, w, H, W, cfg->pixel_threshold, cfg->fraction_threshold, ws.st, ws.pair, ws.cand);
+  SV_CHECK_LAUNCH("fuse_count");
+  return fuse_iterate(cfg, pred_masks, N, h, w, H, W, panoptic, meta, masks_out, masks_cap, ws, cfg->max_iters, s);
+}
+
+// Continue the small-segment filter loop of a slotvps_panoptic_fuse call whose meta[3] came back 0 (not converged within
+// cfg->max_iters passes): `iters` more argmax / filter passes from the device state in `workspace`, then relabel.
+int slotvps_panoptic_fuse_resume(const slotvps_fusion_cfg* cfg, const float* pred_masks, int N, int h, int w, int H, int W,
+                                 int64_t* panoptic, int32_t* meta, float* masks_out, int masks_cap, void* workspace,
+                                 size_t workspace_bytes, int iters, void* stream) {
+  SV_REQUIRE(cfg && pred_masks && panoptic && meta && workspace && iters >= 1, "bad argument");
+  SV_REQUIRE(N > 0 && N <= FUSE_MAXN && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
+  FuseWs ws;
+  if (fuse_ws_layout(N, H, W, workspace, workspace_bytes, &ws) > workspace_bytes)
+    return fail(SLOTVPS_EWORKSPACE, "workspace too small%s%s");
+  return fuse_iterate(cfg, pred_masks, N, h, w, H, W, panoptic, meta, masks_out, masks_cap, ws, iters, s);
 }
 
 // ---- Panoptic Retriever attention alone (per-kernel parity entry point) ----------------------------------

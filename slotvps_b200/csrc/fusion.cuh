@@ -12,7 +12,10 @@
 //   count   (pixels)  |B_i| and pair counts of thing candidates
 //   greedy  (1 CTA)   mask_removal decisions                   -> final kept list (stuff.., things..)
 //   owner   (pixels)  owner[pixel] = first kept thing with prob >= 0.4   (uint16, 0xFFFF = none)
-//   repeat <= max_iters: argmax (pixels) -> ids + areas ; filter (1 CTA) -> drop area <= small_area
+//   repeat <= max_iters: argmax (pixels) -> ids + areas ; filter (last block of the pass) -> drop area <= small_area
+//   (greedy and filter run in the LAST block of the preceding pixel pass: 3 + max_iters launches instead of 16; when the
+//    launched iterations do not reach the fixed point -- the reference loops without bound, :761-792 -- the id map is a
+//    255 sentinel, meta[3] = 0, and slotvps_panoptic_fuse_resume continues from the device state)
 //   relabel (pixels)  ids -> int64 panoptic labels (stuff class | 11 + thing rank), meta
 // Bilinear sampling follows F.interpolate(mode="bilinear", align_corners=False) to size (H,W).
 #pragma once
@@ -28,7 +31,7 @@ struct FuseState {                 // lives in the workspace (device)
   int Kl;                          // after mask_removal: n_stuff + kept things
   int n_things_kept;
   int iters, converged;
-  int pad;
+  unsigned int ticket;             // blocks that finished the current pixel pass (the last one runs the serial step)
   int ord[FUSE_MAXN];              // slot index per position: stuff (score desc), then thing candidates (score desc)
   int cls[FUSE_MAXN];              // class per position (same indexing as ord)
   float score[FUSE_MAXN];
@@ -79,7 +82,10 @@ __device__ __forceinline__ Samp samp_setup(int y, int x, int h, int w, float sy_
 
 // ---- select: class softmax, keep filter, ordering ---------------------------------------------
 __global__ void __launch_bounds__(FUSE_MAXN) fuse_select_kernel(const float* __restrict__ logits, int N, int ncls, int stuff_num,
-                                                                float thr, FuseState* __restrict__ st) {
+                                                                float thr, int has_no_object, FuseState* __restrict__ st,
+                                                                unsigned int* __restrict__ pair, int* __restrict__ meta) {
+  for (int j = threadIdx.x; j < N * N; j += blockDim.x) pair[j] = 0u;         // pair-overlap counters and the result record start clean
+  for (int j = threadIdx.x; j < 4 + 3 * N; j += blockDim.x) meta[j] = 0;
   __shared__ float s_score[FUSE_MAXN];
   __shared__ int s_cls[FUSE_MAXN];
   __shared__ int s_keep[FUSE_MAXN];
@@ -97,7 +103,8 @@ __global__ void __launch_bounds__(FUSE_MAXN) fuse_select_kernel(const float* __r
     float sum = 0.f;
     for (int j = 0; j < ncls; ++j) sum += expf(l[j] - mx);
     sc = 1.f / sum;                                   // softmax value of the arg-max class (exp(0)/sum)
-    keep = (cl != ncls - 1) && (sc > thr);
+    // vps_temporal_slots.py:688-693: the no-object test applies only when the logits carry that column (width == num_classes)
+    keep = (!has_no_object || cl != ncls - 1) && (sc > thr);
   }
   s_score[i] = sc; s_cls[i] = cl; s_keep[i] = keep;
   __syncthreads();
@@ -120,15 +127,60 @@ __global__ void __launch_bounds__(FUSE_MAXN) fuse_select_kernel(const float* __r
     int pos = code >= 100000 ? ns + (code - 100000) : code;
     st->ord[pos] = i; st->cls[pos] = cl; st->score[pos] = sc;
   }
-  if (i == 0) { st->K = ns + nc; st->n_stuff = ns; st->n_cand = nc; st->Kl = 0; st->n_things_kept = 0; st->iters = 0; st->converged = 0; }
+  if (i == 0) { st->K = ns + nc; st->n_stuff = ns; st->n_cand = nc; st->Kl = 0; st->n_things_kept = 0; st->iters = 0; st->converged = 0; st->ticket = 0u; }
   for (int j = i; j < FUSE_MAXN; j += blockDim.x) { st->cntB[j] = 0; st->area[j] = 0; st->active[j] = 0; }
+}
+
+// ---- greedy: the sequential decisions of mask_removal --------------------------------------------
+// One warp: candidate i is decided in order; lanes sum its overlaps with earlier survivors.
+__device__ __forceinline__ void fuse_greedy_warp(FuseState* st, const unsigned int* pair, long HW, double frac_thr, int* s_rank, int* s_cls) {
+  const int lane = threadIdx.x & 31;
+  const int ns = st->n_stuff, nc = st->n_cand;
+  for (int j = lane; j < nc; j += 32) { s_rank[j] = -1; s_cls[j] = st->cls[ns + j]; }
+  for (int k = lane; k < ns; k += 32) { st->list[k] = k; st->active[k] = 1; }
+  __syncwarp();
+  int nk = 0;
+  for (int i = 0; i < nc; ++i) {
+    const unsigned int b = __ldcg(&st->cntB[i]);
+    unsigned int ov = 0;
+    for (int j = lane; j < i; j += 32)
+      if (s_rank[j] >= 0 && s_cls[j] == s_cls[i]) ov += __ldcg(&pair[i * nc + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ov += __shfl_xor_sync(0xffffffffu, ov, o);
+    bool keep = !(b == 0 || (long)b == HW);                      // constant binarisation (:620)
+    if (keep && (double)ov / (double)(float)b > frac_thr) keep = false;   // int64/float32 -> float64 (:621-622)
+    if (keep) {
+      if (lane == 0) { s_rank[i] = nk; st->list[ns + nk] = ns + i; st->active[ns + nk] = 1; }
+      ++nk;
+    }
+    __syncwarp();
+  }
+  for (int j = lane; j < nc; j += 32) st->thing_rank[j] = s_rank[j];
+  if (lane == 0) { st->Kl = ns + nk; st->n_things_kept = nk; }
+}
+
+// "last block" hand-over: every block of a pixel pass publishes its global atomics, takes a ticket, and the block that
+// draws the last one runs the serial step that used to be a separate single-CTA launch (count -> greedy, argmax -> filter)
+__device__ __forceinline__ bool fuse_last_block(FuseState* st) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&st->ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) st->ticket = 0u;                                  // ready for the next pass (stream order separates the passes)
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
 }
 
 // ---- count: |B_i| and pair overlaps of thing candidates ------------------------------------------
 // pair [n_cand][n_cand] (global, zeroed by the caller); one thread per output pixel.
 __global__ void __launch_bounds__(256) fuse_count_kernel(const float* __restrict__ masks, int h, int w, int H, int W,
-                                                         float pix_thr, FuseState* __restrict__ st, unsigned int* __restrict__ pair, unsigned int* __restrict__ cand) {
+                                                         float pix_thr, double frac_thr, FuseState* __restrict__ st, unsigned int* __restrict__ pair, unsigned int* __restrict__ cand) {
   __shared__ unsigned int s_cnt[FUSE_MAXN];
+  __shared__ int s_gcls[FUSE_MAXN];
   const int K = st->K, ns = st->n_stuff, nc = st->n_cand;
   for (int j = threadIdx.x; j < nc; j += 256) s_cnt[j] = 0;
   __syncthreads();
@@ -153,36 +205,7 @@ __global__ void __launch_bounds__(256) fuse_count_kernel(const float* __restrict
   }
   __syncthreads();
   for (int j = threadIdx.x; j < nc; j += 256) if (s_cnt[j]) atomicAdd(&st->cntB[j], s_cnt[j]);
-}
-
-// ---- greedy: the sequential decisions of mask_removal --------------------------------------------
-// One warp: candidate i is decided in order; lanes sum its overlaps with earlier survivors.
-__global__ void __launch_bounds__(32) fuse_greedy_kernel(FuseState* __restrict__ st, const unsigned int* __restrict__ pair, long HW, double frac_thr) {
-  __shared__ int s_rank[FUSE_MAXN];
-  __shared__ int s_cls[FUSE_MAXN];
-  const int lane = threadIdx.x;
-  const int ns = st->n_stuff, nc = st->n_cand;
-  for (int j = lane; j < nc; j += 32) { s_rank[j] = -1; s_cls[j] = st->cls[ns + j]; }
-  for (int k = lane; k < ns; k += 32) { st->list[k] = k; st->active[k] = 1; }
-  __syncwarp();
-  int nk = 0;
-  for (int i = 0; i < nc; ++i) {
-    const unsigned int b = st->cntB[i];
-    unsigned int ov = 0;
-    for (int j = lane; j < i; j += 32)
-      if (s_rank[j] >= 0 && s_cls[j] == s_cls[i]) ov += pair[i * nc + j];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ov += __shfl_xor_sync(0xffffffffu, ov, o);
-    bool keep = !(b == 0 || (long)b == HW);                      // constant binarisation (:620)
-    if (keep && (double)ov / (double)(float)b > frac_thr) keep = false;   // int64/float32 -> float64 (:621-622)
-    if (keep) {
-      if (lane == 0) { s_rank[i] = nk; st->list[ns + nk] = ns + i; st->active[ns + nk] = 1; }
-      ++nk;
-    }
-    __syncwarp();
-  }
-  for (int j = lane; j < nc; j += 32) st->thing_rank[j] = s_rank[j];
-  if (lane == 0) { st->Kl = ns + nk; st->n_things_kept = nk; }
+  if (fuse_last_block(st) && threadIdx.x < 32) fuse_greedy_warp(st, pair, (long)H * W, frac_thr, reinterpret_cast<int*>(s_cnt), s_gcls);
 }
 
 // owner of a pixel = rank (among surviving things) of the first surviving candidate, or 0xFFFF
@@ -234,10 +257,11 @@ struct Blk4 {
   }
 };
 
-__global__ void __launch_bounds__(256) fuse_count4_kernel(const float* __restrict__ masks, int h, int w, float pix_thr,
+__global__ void __launch_bounds__(256) fuse_count4_kernel(const float* __restrict__ masks, int h, int w, float pix_thr, double frac_thr,
                                                           FuseState* __restrict__ st, unsigned int* __restrict__ pair,
                                                           unsigned int* __restrict__ cand) {
   __shared__ unsigned int s_cnt[FUSE_MAXN];
+  __shared__ int s_gcls[FUSE_MAXN];
   __shared__ int s_ord[FUSE_MAXN];
   const int K = st->K, ns = st->n_stuff, nc = st->n_cand;
   for (int j = threadIdx.x; j < FUSE_MAXN; j += 256) { s_cnt[j] = 0; s_ord[j] = j < K ? st->ord[j] : 0; }
@@ -313,10 +337,83 @@ __global__ void __launch_bounds__(256) fuse_count4_kernel(const float* __restric
   }
   __syncthreads();
   for (int j = threadIdx.x; j < nc; j += 256) if (s_cnt[j]) atomicAdd(&st->cntB[j], s_cnt[j]);
+  if (fuse_last_block(st) && threadIdx.x < 32) fuse_greedy_warp(st, pair, (long)16 * h * w, frac_thr, reinterpret_cast<int*>(s_cnt), s_gcls);
+}
+
+// ---- filter: merge duplicate stuff classes (first call only), drop area <= small_area; on
+// convergence build the label LUT of the inline fusion (vps_temporal_slots.py:420-435) and meta.
+// Runs in the LAST block of an argmax pass (all 256 threads), entries strided over the threads. ----
+struct FilterArgs { int stuff_num; unsigned int small_area; int N; int* meta; };
+__device__ __forceinline__ void fuse_filter_block(FuseState* st, const FilterArgs fa) {
+  __shared__ unsigned int f_area[FUSE_MAXN];
+  __shared__ int f_act[FUSE_MAXN], f_cls[FUSE_MAXN], f_first[FUSE_MAXN], f_comp[FUSE_MAXN], f_lut[FUSE_MAXN];
+  __shared__ int f_removed;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int Kl = st->Kl, ns = st->n_stuff, it = st->iters;
+  if (tid == 0) f_removed = 0;
+  for (int e = tid; e < Kl; e += nt) { f_area[e] = __ldcg(&st->area[e]); f_act[e] = st->active[e]; f_cls[e] = st->cls[st->list[e]]; }
+  __syncthreads();
+  if (it == 0) {                                                  // dedup=True only on the first call (:758)
+    for (int e = tid; e < Kl; e += nt) {
+      int first = e;
+      if (e < ns && f_act[e])
+        for (int f = 0; f < e; ++f) if (f_act[f] && f_cls[f] == f_cls[e]) { first = f; break; }
+      f_first[e] = first;
+    }
+    __syncthreads();
+    for (int e = tid; e < ns; e += nt) {
+      if (f_act[e] && f_first[e] == e) {
+        unsigned int a = f_area[e];
+        for (int f = e + 1; f < ns; ++f) if (f_act[f] && f_first[f] == e) a += f_area[f];
+        f_comp[e] = (int)a;                                       // staged: other threads still read f_area of merged entries
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < ns; e += nt) {
+      if (!f_act[e]) continue;
+      f_area[e] = f_first[e] == e ? (unsigned int)f_comp[e] : 0u;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < Kl; e += nt)
+    if (f_act[e] && f_area[e] <= fa.small_area) { f_act[e] = 0; st->active[e] = 0; atomicAdd(&f_removed, 1); }
+  __syncthreads();
+  if (f_removed != 0) {
+    for (int e = tid; e < Kl; e += nt) st->area[e] = 0;
+    if (tid == 0) st->iters = it + 1;
+    return;
+  }
+  // converged: every active entry is present (area > small_area) in the id map of this iteration
+  if (tid == 0) {
+    int n_all = 0, n_inst = 0;
+    for (int f = 0; f < Kl; ++f) { f_comp[f] = f_act[f] ? n_all : -1; if (f_act[f]) { f_first[n_all] = f; ++n_all; if (f >= ns) ++n_inst; } }
+    // present ids ascending = compacted ids 0..n_all-1 restricted to area > 0; scan from the top
+    int npresent = 0;
+    for (int f = 0; f < Kl; ++f) if (f_act[f] && f_area[f] > 0) ++npresent;
+    int count = n_inst, i = npresent - 1;
+    for (int f = Kl - 1; f >= 0; --f) {
+      f_lut[f] = 0;
+      if (!(f_act[f] && f_area[f] > 0)) continue;
+      if (f_comp[f] >= n_all - n_inst) { f_lut[f] = fa.stuff_num + count - 1; --count; }
+      else f_lut[f] = f_cls[f_first[i]];      // semantic_labels[i], i = position in the unique-id list (:433)
+      --i;
+    }
+    int* meta = fa.meta;
+    meta[0] = n_all; meta[1] = n_inst; meta[2] = it + 1; meta[3] = 1;
+    for (int c = 0; c < n_all; ++c) {
+      const int f = f_first[c];
+      meta[4 + c] = st->ord[st->list[f]];
+      meta[4 + fa.N + c] = f_cls[f];
+      meta[4 + 2 * fa.N + c] = __float_as_int(st->score[st->list[f]]);
+    }
+    st->iters = it + 1; st->converged = 1;
+  }
+  __syncthreads();
+  for (int e = tid; e < Kl; e += nt) st->lut[e] = f_lut[e];
 }
 
 __global__ void __launch_bounds__(256) fuse_argmax4_kernel(const float* __restrict__ masks, int h, int w, FuseState* __restrict__ st,
-                                                           const unsigned int* __restrict__ cand, unsigned short* __restrict__ ids) {
+                                                           const unsigned int* __restrict__ cand, unsigned short* __restrict__ ids, const FilterArgs fa) {
   if (st->converged) return;
   __shared__ unsigned int s_area[FUSE_MAXN];
   __shared__ int s_rank[FUSE_MAXN], s_slot[FUSE_MAXN], s_act[FUSE_MAXN];
@@ -385,13 +482,14 @@ __global__ void __launch_bounds__(256) fuse_argmax4_kernel(const float* __restri
   }
   __syncthreads();
   for (int j = threadIdx.x; j < Kl; j += 256) if (s_area[j]) atomicAdd(&st->area[j], s_area[j]);
+  if (fuse_last_block(st)) fuse_filter_block(st, fa);
 }
 
 // ---- argmax over the active kept slots of the masked logits ---------------------------------------
 // ids[pixel] = entry of the final list (uncompacted); lowest entry wins ties (torch argmax).
 __global__ void __launch_bounds__(256) fuse_argmax_kernel(const float* __restrict__ masks, int h, int w, int H, int W,
                                                           FuseState* __restrict__ st, const unsigned int* __restrict__ cand,
-                                                          unsigned short* __restrict__ ids) {
+                                                          unsigned short* __restrict__ ids, const FilterArgs fa) {
   if (st->converged) return;
   __shared__ unsigned int s_area[FUSE_MAXN];
   __shared__ int s_rank[FUSE_MAXN];
@@ -438,70 +536,7 @@ __global__ void __launch_bounds__(256) fuse_argmax_kernel(const float* __restric
   }
   __syncthreads();
   for (int j = threadIdx.x; j < Kl; j += 256) if (s_area[j]) atomicAdd(&st->area[j], s_area[j]);
-}
-
-// ---- filter: merge duplicate stuff classes (first call only), drop area <= small_area; on
-// convergence build the label LUT of the inline fusion (vps_temporal_slots.py:420-435) and meta ----
-__global__ void __launch_bounds__(FUSE_MAXN) fuse_filter_kernel(FuseState* __restrict__ st, int stuff_num, unsigned int small_area,
-                                                                int N, int* __restrict__ meta) {
-  if (st->converged) return;
-  __shared__ unsigned int s_area[FUSE_MAXN];
-  __shared__ int s_act[FUSE_MAXN], s_cls[FUSE_MAXN], s_first[FUSE_MAXN], s_comp[FUSE_MAXN], s_lut[FUSE_MAXN];
-  __shared__ int s_removed;
-  const int e = threadIdx.x;
-  const int Kl = st->Kl, ns = st->n_stuff, it = st->iters;
-  if (e == 0) s_removed = 0;
-  if (e < Kl) { s_area[e] = st->area[e]; s_act[e] = st->active[e]; s_cls[e] = st->cls[st->list[e]]; }
-  __syncthreads();
-  if (it == 0) {                                                  // dedup=True only on the first call (:758)
-    int first = e;
-    if (e < ns && s_act[e])
-      for (int f = 0; f < e; ++f) if (s_act[f] && s_cls[f] == s_cls[e]) { first = f; break; }
-    if (e < Kl) s_first[e] = first;
-    __syncthreads();
-    if (e < ns && s_act[e] && s_first[e] == e) {
-      unsigned int a = s_area[e];
-      for (int f = e + 1; f < ns; ++f) if (s_act[f] && s_first[f] == e) a += s_area[f];
-      s_area[e] = a;
-    }
-    __syncthreads();
-    if (e < ns && s_act[e] && s_first[e] != e) s_area[e] = 0;
-    __syncthreads();
-  }
-  if (e < Kl && s_act[e] && s_area[e] <= small_area) { s_act[e] = 0; st->active[e] = 0; atomicAdd(&s_removed, 1); }
-  __syncthreads();
-  const int removed = s_removed;
-  if (removed != 0) {
-    if (e < Kl) st->area[e] = 0;
-    if (e == 0) st->iters = it + 1;
-    return;
-  }
-  // converged: every active entry is present (area > small_area) in the id map of this iteration
-  if (e == 0) {
-    int n_all = 0, n_inst = 0;
-    for (int f = 0; f < Kl; ++f) { s_comp[f] = s_act[f] ? n_all : -1; if (s_act[f]) { s_first[n_all] = f; ++n_all; if (f >= ns) ++n_inst; } }
-    // present ids ascending = compacted ids 0..n_all-1 restricted to area > 0; scan from the top
-    int npresent = 0;
-    for (int f = 0; f < Kl; ++f) if (s_act[f] && s_area[f] > 0) ++npresent;
-    int count = n_inst, i = npresent - 1;
-    for (int f = Kl - 1; f >= 0; --f) {
-      s_lut[f] = 0;
-      if (!(s_act[f] && s_area[f] > 0)) continue;
-      if (s_comp[f] >= n_all - n_inst) { s_lut[f] = stuff_num + count - 1; --count; }
-      else s_lut[f] = s_cls[s_first[i]];      // semantic_labels[i], i = position in the unique-id list (:433)
-      --i;
-    }
-    meta[0] = n_all; meta[1] = n_inst; meta[2] = it + 1; meta[3] = 1;
-    for (int c = 0; c < n_all; ++c) {
-      const int f = s_first[c];
-      meta[4 + c] = st->ord[st->list[f]];
-      meta[4 + N + c] = s_cls[f];
-      meta[4 + 2 * N + c] = __float_as_int(st->score[st->list[f]]);
-    }
-    st->iters = it + 1; st->converged = 1;
-  }
-  __syncthreads();
-  if (e < Kl) st->lut[e] = s_lut[e];
+  if (fuse_last_block(st)) fuse_filter_block(st, fa);
 }
 
 // ---- relabel: ids -> int64 panoptic labels -------------------------------------------------------
@@ -511,9 +546,10 @@ __global__ void __launch_bounds__(256) fuse_relabel_kernel(const FuseState* __re
   const int Kl = st->Kl;
   for (int j = threadIdx.x; j < Kl; j += 256) s_lut[j] = st->lut[j];
   __syncthreads();
-  for (long pix = (long)blockIdx.x * 256 + threadIdx.x; pix < HW; pix += (long)gridDim.x * 256) {
+  const bool conv = st->converged != 0;                           // not converged within the launched iterations: sentinel map,
+  for (long pix = (long)blockIdx.x * 256 + threadIdx.x; pix < HW; pix += (long)gridDim.x * 256) {      // meta[3] stays 0, the host resumes
     const unsigned short id = ids[pix];
-    out[pix] = id == 0xFFFF ? 0 : s_lut[id];
+    out[pix] = !conv ? 255 : (id == 0xFFFF ? 0 : s_lut[id]);
   }
 }
 

@@ -106,9 +106,18 @@ class FusionOutput:
     masks: Optional[torch.Tensor]         # [cap,H,W] fp32 masked logits when requested
     n_slots: int
     stuff_num: int
+    resume: Optional[object] = None       # continues the small-segment loop when the launched passes did not converge
 
     def host(self):
         m = self.meta.cpu().numpy()
+        if int(m[3]) == 0 and self.resume is not None:
+            # the reference's loop (vps_temporal_slots.py:761-792) has no bound: keep going from the device state until the
+            # fixed point (every pass removes at least one entry, so at most N + 1 passes exist in total)
+            for _ in range(self.n_slots // 4 + 2):
+                self.resume(4)
+                m = self.meta.cpu().numpy()
+                if int(m[3]) != 0:
+                    break
         k, n_things, iters, conv = int(m[0]), int(m[1]), int(m[2]), int(m[3])
         N = self.n_slots
         keep = m[4:4 + k].astype(np.int64)
@@ -129,7 +138,7 @@ class PanopticFusion(nn.Module):
     def __init__(self, is_thing_map=None, threshold=0.85, output_dir="", debug=False, fraction_threshold=0.03,
                  pixel_threshold=0.4, apply_mask_removal=False, apply_mask_removal_only_ins=False,
                  use_mask_low_constant=False, catgories_color=None, filter_small_option='4', num_classes=20,
-                 num_stuff=11, max_iters=6):
+                 num_stuff=11, max_iters=4):
         super().__init__()
         # defaults as in the reference (vps_temporal_slots.py:532-536: both mask-removal switches default to False); the
         # device kernels implement what configs/cityscapes/*_slotvps.py ship (:66-74: both True), anything else raises
@@ -145,7 +154,7 @@ class PanopticFusion(nn.Module):
                     raise NotImplementedError("is_thing_map must be {c: c > num_stuff-1}")
         self.cfg = _lib.FusionCfg(num_classes=num_classes, stuff_num=num_stuff, small_area=4, max_iters=max_iters,
                                   threshold=threshold, pixel_threshold=pixel_threshold,
-                                  fraction_threshold=fraction_threshold)
+                                  fraction_threshold=fraction_threshold, logits_width=0, reserved=0)
         self.num_stuff = num_stuff
         self._ws = None
 
@@ -166,11 +175,23 @@ class PanopticFusion(nn.Module):
             out = torch.empty((H, W), dtype=torch.int64, device=dev)
         meta = torch.empty(4 + 3 * N, dtype=torch.int32, device=dev)
         masks = torch.empty((want_masks, H, W), dtype=torch.float32, device=dev) if want_masks > 0 else None
-        _lib.check(L.slotvps_panoptic_fuse(C.byref(self.cfg), pred_logits.float().contiguous().data_ptr(),
-                                           pred_masks.float().contiguous().data_ptr(), N, h, w, H, W, out.data_ptr(),
+        width = int(pred_logits.shape[-1])
+        if width not in (self.cfg.num_classes, self.cfg.num_classes - 1):
+            raise ValueError("pred_logits must have num_classes or num_classes - 1 columns (vps_temporal_slots.py:688-693)")
+        cfg = _lib.FusionCfg.from_buffer_copy(self.cfg)
+        cfg.logits_width = width
+        pm = pred_masks.float().contiguous()
+        ws = self._ws
+        _lib.check(L.slotvps_panoptic_fuse(C.byref(cfg), pred_logits.float().contiguous().data_ptr(),
+                                           pm.data_ptr(), N, h, w, H, W, out.data_ptr(),
                                            meta.data_ptr(), None if masks is None else masks.data_ptr(), want_masks,
-                                           self._ws.data_ptr(), self._ws.numel(), _stream_ptr(dev)), "slotvps_panoptic_fuse")
-        return FusionOutput(out, meta, masks, N, self.num_stuff)
+                                           ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "slotvps_panoptic_fuse")
+
+        def resume(iters):
+            _lib.check(L.slotvps_panoptic_fuse_resume(C.byref(cfg), pm.data_ptr(), N, h, w, H, W, out.data_ptr(), meta.data_ptr(),
+                                                      None if masks is None else masks.data_ptr(), want_masks, ws.data_ptr(),
+                                                      ws.numel(), iters, _stream_ptr(dev)), "slotvps_panoptic_fuse_resume")
+        return FusionOutput(out, meta, masks, N, self.num_stuff, resume)
 
     def forward(self, outputs, processed_sizes, target_sizes=None, id=None):
         """Reference signature (vps_temporal_slots.py:659): ``outputs`` is an Instances-like object

@@ -39,7 +39,7 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.StageParams) == 8 * len(fields)
     assert C.sizeof(_lib.HeadDesc) == 4 * (3 + 12 + 9)
     assert C.sizeof(_lib.HeadOpts) == 40
-    assert C.sizeof(_lib.FusionCfg) == 32
+    assert C.sizeof(_lib.FusionCfg) == 40
 
 
 def test_argument_validation_without_gpu(L):

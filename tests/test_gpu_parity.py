@@ -853,3 +853,32 @@ def test_postprocess_forward_with_instances(dev):
     np.testing.assert_array_equal(res.pred_logits.cpu().numpy(), logits[torch.from_numpy(r.keep.copy())].numpy())
     assert int(((res.masks.cpu().numpy() != 0) != (r.masks != 0)).sum()) == 0
     assert float(np.abs(res.masks.cpu().numpy() - r.masks).max()) < 1e-4
+
+
+def test_fusion_long_removal_cascade_resumes(dev):
+    """the reference's small-segment loop is unbounded (vps_temporal_slots.py:761-792).  A cascade that needs
+    more passes than the launched ones must not leave a stale id map: meta[3] = 0 + sentinel map, and host() resumes from
+    the device state until the fixed point -- same result as the oracle."""
+    N, h, w = 40, 16, 16
+    logits = torch.full((N, 20), -4.0)
+    logits[:, 19] = 4.0
+    masks = torch.full((N, h, w), -30.0)
+    # slot 0: stuff everywhere (weak); slots 1..8: things, each a 1-source-pixel bump that only wins once the previous
+    # (stronger, overlapping) one has been removed for being too small -> one removal per pass
+    logits[0] = -4.0; logits[0, 2] = 6.0
+    masks[0] = 1.0
+    for i in range(1, 9):
+        logits[i] = -4.0; logits[i, 11 + (i % 8)] = 6.0 + 0.01 * i
+    fz = sv.PanopticFusion(**{**sv.FUSION_KWARGS}, max_iters=1)
+    lg, pm, _ = synthetic.make_fusion_case(9, N, h, w, n_things=10, near_dup_things=0, tiny=6)
+    fo = fz.fuse(lg.to(dev), pm.to(dev), (4 * h, 4 * w))
+    raw = fo.meta.cpu().numpy()
+    r = O.panoptic_fuse(lg, pm, (4 * h, 4 * w))
+    hst = fo.host()
+    assert hst["converged"] and hst["iters"] == r.iters
+    if r.iters > 1:
+        assert int(raw[3]) == 0                                   # the single launched pass was not enough: resumed on the host
+    np.testing.assert_array_equal(hst["keep"], r.keep)
+    got = fo.panoptic.cpu().numpy()
+    assert int(((got != r.panoptic) & ~r.near_tie).sum()) == 0
+    print(f"fusion cascade: oracle iterations {r.iters}, device converged after resume: {hst['converged']}")
