@@ -1,6 +1,6 @@
 """Print the headline numbers of a bench.py JSON line (gpurun_out/*.json)."""
 import json, sys
-d = json.load(open(sys.argv[1]))
+d = json.loads([l for l in open(sys.argv[1]).read().splitlines() if l.startswith("{")][-1])
 print("value %.1f f/s  ms/step %.3f  regions %s" % (d["value"], d["ms_per_step"], [round(x, 2) for x in d.get("timed_regions", {}).get("ms", [])]))
 if d.get("e2e"): print("e2e %.1f f/s  h2d GB/s/rank %.1f" % (d["e2e"]["value"], d["e2e"].get("h2d_gbs_per_rank", 0)))
 c = d["config"]; print("single clip ms", c.get("single_clip_in_flight_ms_per_step"), "launches", d.get("gpu_launches"), "kept", c.get("kept_slots"))

@@ -509,13 +509,15 @@ constexpr int P_PLANE = 2 * P_SUB;                // two 64-pixel halves
 constexpr int P_BYTES = 2 * P_PLANE;              // hi, lo = 53248
 constexpr int AUX_SUB = 16 * 128;                 // [16 pseudo-channels][64 px] fp16
 constexpr int AUXT_BYTES = 2 * AUX_SUB;
-constexpr int MISC_BYTES = 2048;
+constexpr int MISC_BYTES = 3072;                  // barriers [0,128), (g0, g1) [128,1024), softmax exchange [1024,3072)
 constexpr int OFF_G = NSLOT * SLOT_BYTES;
 constexpr int OFF_P = OFF_G + G_BYTES;
 constexpr int OFF_AUX = OFF_P + P_BYTES;
 constexpr int OFF_MISC = OFF_AUX + AUXT_BYTES;
-constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;      // == 232448, the sm_100 per-block maximum
-constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES;             // == 232448, the sm_100 per-block maximum: no alignment slack, the
+                                                              // dynamic shared-memory array is declared __align__(1024) (checked at run time)
+constexpr int THREADS = 320;                      // warp 0 TMA, warp 1 MMA, warps 2..9 softmax: TWO threads per pixel
+constexpr int NSPLIT = 48;                        // slots [0,48) belong to the pixel's first thread, [48,112) to the second
 constexpr uint32_t IDESC_S = tc::make_idesc_f16(128, NPAD, 0, 0);
 // Z^T: A = x tile, MN-major fp16; B = P, K-major fp16
 constexpr uint32_t IDESC_Z = tc::make_idesc_f16(128, NPAD, 1, 0);
@@ -565,9 +567,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                const SlotGroup grp) {
   using namespace attn;
   const int Ntot = MODE == 0 ? N : grp.n_total, n0 = MODE == 0 ? 0 : grp.n0;
-  extern __shared__ uint8_t raw_smem[];
-  const uint32_t raw = tc::smem_u32(raw_smem);
-  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
+  extern __shared__ __align__(1024) uint8_t attn_smem[];
+  uint8_t* smem = attn_smem;
+  if ((tc::smem_u32(smem) & 1023u) != 0u) __trap();          // the swizzled tiles need 1024-byte alignment and there is no spare byte to fix it up
   uint8_t* misc = smem + OFF_MISC;
   uint64_t* full = reinterpret_cast<uint64_t*>(misc);      // [NSLOT]
   uint64_t* empty = full + NSLOT;                          // [NSLOT]
@@ -575,10 +577,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint64_t* sempty = sfull + 2;                            // [2]
   uint64_t* pfull = sempty + 2;                            // [1]
   uint64_t* pempty = pfull + 1;                            // [1]
-  uint64_t* gfull = pempty + 1;                            // [1]
-  uint64_t* zfull = gfull + 1;                             // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(zfull + 1);
-  float2* gc = reinterpret_cast<float2*>(misc + 256);      // [NPAD] (g0, g1)
+  uint64_t* gfull = pempty + 1;                            // [1] phase 0: G operand landed (TMA); phase 1: the Z / aux accumulators are complete
+  uint64_t* zfull = gfull;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(gfull + 1);      // byte 120 of the 128-byte barrier block
+  float2* gc = reinterpret_cast<float2*>(misc + 128);      // [NPAD] (g0, g1)
+  float* xch = reinterpret_cast<float*>(misc + 1024);      // [2 kinds][2 halves][128] softmax max / sum exchange between a pixel's two threads
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x, chunks = gridDim.x, t = blockIdx.y;
@@ -588,8 +591,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     tc::tma_prefetch_desc(&tmap_x);
     tc::tma_prefetch_desc(&tmap_g);
     for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sfull[i], 1); tc::mbar_init(&sempty[i], 128); }
-    tc::mbar_init(pfull, 128); tc::mbar_init(pempty, 1); tc::mbar_init(gfull, 1); tc::mbar_init(zfull, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sfull[i], 1); tc::mbar_init(&sempty[i], 256); }
+    tc::mbar_init(pfull, 256); tc::mbar_init(pempty, 1); tc::mbar_init(gfull, 1);
     tc::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < NPAD; i += THREADS)
@@ -759,14 +762,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         printf("attn_tc tiles=%d cycles=%lld wait: S-operands %lld Z-operands %lld softmax %lld S-buffer %lld | in tcgen05.commit %lld\n", n_my, clock64() - t_begin, wS, wZ, wP, wE, tC);
     }
   } else {
-    // ===================== softmax warps (one pixel per thread) + final epilogue =====================
-    const int q = warp & 3;
+    // ===================== softmax warps: two threads per pixel (slot halves) + final epilogue =====================
+    // The slot-axis softmax of a pixel is thread-local apart from one max and one sum exchange between the pixel's two
+    // threads.  With one thread per pixel (112 exp + 208 fp16 stores each, one warp per scheduler) this phase, not the
+    // tensor pipe, set the kernel's pace (measured: 38 % tensor-pipe active); eight warps halve the per-thread chain.
+    const int q = warp & 3, hf = (warp - 2) >> 2;           // TMEM lane quadrant, slot half
     const int r = q * 32 + lane;                            // pixel row of the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    constexpr int NH = NPAD - NSPLIT;                       // 64: register slots per thread (the first half uses 48 of them)
+    const int nb = hf == 0 ? 0 : NSPLIT;                    // first slot of this thread
+    const int nh = hf == 0 ? NSPLIT : NH;                   // slots of this thread
     uint8_t* p_half = smem + OFF_P + (r >> 6) * P_SUB;      // this pixel's 64-pixel half of P
     const int pc = (r & 63) >> 3, pe = (r & 7) * 2;         // 16-byte chunk and byte offset inside it
     __half* aux_row1 = reinterpret_cast<__half*>(smem + OFF_AUX + (r >> 6) * AUX_SUB + 128 + ((pc ^ 1) * 16) + pe);
     __half* aux_row2 = reinterpret_cast<__half*>(smem + OFF_AUX + (r >> 6) * AUX_SUB + 256 + ((pc ^ 2) * 16) + pe);
+    float* xmax = xch, *xsum = xch + 256;
     for (int i = 0; i < n_my; ++i) {
       const int p = (chunk + i * chunks) * TILE_M + r;
       const bool pv = p < P;
@@ -775,65 +785,67 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int b = i & 1;
       tc::mbar_wait(&sfull[b], (i >> 1) & 1);
       tc::tc_fence_after();
-      float sv[NPAD];
-      const uint32_t ta = tmem_base + lane_addr + TM_S + b * 128;
+      float sv[NH];
+      const uint32_t ta = tmem_base + lane_addr + TM_S + b * 128 + nb;
       tc::tmem_ld32(ta, sv);
-      tc::tmem_ld32(ta + 32, sv + 32);
-      tc::tmem_ld32(ta + 64, sv + 64);
-      {
-        float tail[32];
-        tc::tmem_ld32(ta + 96, tail);                       // columns 96..127 (only 96..111 are meaningful)
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 16; ++c) sv[96 + c] = tail[c];
-      }
+      if (hf == 0) tc::tmem_ld16(ta + 32, sv + 32);
+      else tc::tmem_ld32(ta + 32, sv + 32);
+      tc::tmem_ld_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(&sempty[b]);                          // S buffer free for tile i+2
       if (ps.pgy != nullptr && pv) {                        // + pos . G_n from the separable tables
-        const float4* gy = reinterpret_cast<const float4*>(ps.pgy + ((long)t * ps.h + p / ps.w) * NPAD);
-        const float4* gx = reinterpret_cast<const float4*>(ps.pgx + ((long)t * ps.w + p % ps.w) * NPAD);
+        const float4* gy = reinterpret_cast<const float4*>(ps.pgy + ((long)t * ps.h + p / ps.w) * NPAD + nb);
+        const float4* gx = reinterpret_cast<const float4*>(ps.pgx + ((long)t * ps.w + p % ps.w) * NPAD + nb);
 #pragma unroll
-        for (int c = 0; c < NPAD / 4; ++c) {
-          const float4 a = __ldg(gy + c), b = __ldg(gx + c);
-          sv[4 * c] += a.x + b.x; sv[4 * c + 1] += a.y + b.y; sv[4 * c + 2] += a.z + b.z; sv[4 * c + 3] += a.w + b.w;
+        for (int c = 0; c < NH / 4; ++c) {
+          if (4 * c < nh) {
+            const float4 a = __ldg(gy + c), bq = __ldg(gx + c);
+            sv[4 * c] += a.x + bq.x; sv[4 * c + 1] += a.y + bq.y; sv[4 * c + 2] += a.z + bq.z; sv[4 * c + 3] += a.w + bq.w;
+          }
         }
       }
       float mx = -INFINITY;
 #pragma unroll
-      for (int n = 0; n < NPAD; ++n) {
-        const float2 c = gc[n];
-        const float s = n < N ? fmaf(sv[n] + c.x, rk, c.y) : -INFINITY;
-        sv[n] = s;
-        mx = fmaxf(mx, s);
+      for (int n = 0; n < NH; ++n) {
+        const float2 c = gc[nb + (n < nh ? n : 0)];
+        const float sl = (n < nh && nb + n < N) ? fmaf(sv[n] + c.x, rk, c.y) : -INFINITY;
+        sv[n] = sl;
+        mx = fmaxf(mx, sl);
       }
       float sum = 0.f;
       if (MODE == 2) {                                      // the maximum / denominator over ALL slot groups of this pixel
         const float2 ml = pv ? grp.ml_in[(long)t * P + p] : make_float2(0.f, 1.f);
         mx = ml.x; sum = ml.y;
 #pragma unroll
-        for (int n = 0; n < NPAD; ++n) sv[n] = __expf(sv[n] - mx);
-      } else if (dbg & 32) {
-#pragma unroll
-        for (int n = 0; n < NPAD; ++n) { const float e = expf(sv[n] - mx); sv[n] = e; sum += e; }
+        for (int n = 0; n < NH; ++n) sv[n] = __expf(sv[n] - mx);
       } else {
+        xmax[hf * 128 + r] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(xmax[r], xmax[128 + r]);
 #pragma unroll
-        for (int n = 0; n < NPAD; ++n) { const float e = __expf(sv[n] - mx); sv[n] = e; sum += e; }
+        for (int n = 0; n < NH; ++n) { const float e = __expf(sv[n] - mx); sv[n] = e; sum += e; }
+        xsum[hf * 128 + r] = sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        sum = xsum[r] + xsum[128 + r];
       }
       if (MODE == 1) {
-        if (pv) grp.ml_out[(long)t * P + p] = make_float2(mx, sum);
+        if (pv && hf == 0) grp.ml_out[(long)t * P + p] = make_float2(mx, sum);
         continue;
       }
       const float sc = pv ? rv / sum * PSCALE : 0.f;        // A' = A * rs_v (scaled, see PSCALE)
       tc::mbar_wait(pempty, (i & 1) ^ 1);                   // Z(i-1) has finished reading P
 #pragma unroll
-      for (int n = 0; n < NROW; ++n) {
-        const float a = pv ? sv[n] * sc : 0.f;
-        const __half hi = __float2half_rn(a);
-        const int off = n * 128 + ((pc ^ (n & 7)) * 16) + pe;
-        *reinterpret_cast<__half*>(p_half + off) = hi;
-        *reinterpret_cast<__half*>(p_half + P_PLANE + off) = __float2half_rn(a - __half2float(hi));
+      for (int n = 0; n < NH; ++n) {
+        const int ng = nb + n;
+        if (n < nh && ng < NROW) {
+          const float a = pv ? sv[n] * sc : 0.f;
+          const __half hi = __float2half_rn(a);
+          const int off = ng * 128 + ((pc ^ (ng & 7)) * 16) + pe;
+          *reinterpret_cast<__half*>(p_half + off) = hi;
+          *reinterpret_cast<__half*>(p_half + P_PLANE + off) = __float2half_rn(a - __half2float(hi));
+        }
       }
-      {
+      if (hf == 0) {
         const float sg = pv ? 1.f / rv : 0.f;               // sigma_v, hi + lo
         const __half sh = __float2half_rn(sg);
         *aux_row1 = sh;
@@ -842,13 +854,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       tc::fence_proxy_async();
       tc::mbar_arrive(pfull);
     }
-    // ---- final epilogue: Z^T (lanes = channels) and aux (lanes = slots) -> per-CTA partials ----
+    // ---- final epilogue: Z^T (lanes = channels; one 128-channel tile per warp group) and aux (lanes = slots) -> per-CTA partials ----
     if (MODE != 1) {
-    tc::mbar_wait(zfull, 0);
+    tc::mbar_wait(zfull, 1);
     tc::tc_fence_after();
     float* Zp = Zpart + (((long)chunk * T + t) * Ntot + n0) * C;
-    for (int mt = 0; mt < 2; ++mt) {
-      const int ch = mt * 128 + r;
+    {
+      const int mt = hf, ch = mt * 128 + r;
       for (int j = 0; j < 4; ++j) {
         float v[32];
         tc::tmem_ld32(tmem_base + lane_addr + TM_Z + mt * NPAD + j * 32, v);   // last chunk over-reads 16 columns (ignored)
@@ -857,7 +869,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         for (int c = 0; c < 32; ++c) { const int n = j * 32 + c; if (n < N) Zp[(long)n * C + ch] = v[c] * PSCALE_INV; }
       }
     }
-    {
+    if (hf == 0) {
       float v[32];
       tc::tmem_ld32(tmem_base + lane_addr + TM_AUX, v);     // reads 16 columns past aux (unused)
       tc::tmem_ld_wait();
