@@ -20,7 +20,7 @@ constexpr int E_BYTES = 2 * 4 * E_SUB;
 constexpr int OFF_E = NSLOT * SLOT_BYTES;
 constexpr int OFF_MISC = OFF_E + E_BYTES;
 constexpr int SMEM_BYTES = OFF_MISC + 2048 + 1024;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;                   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant: 64 / 48 slot columns each)
 constexpr uint32_t IDESC = tc::make_idesc_f16(128, NPAD, 0, 0);
 }  // namespace mask
 
@@ -47,7 +47,7 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     tc::tma_prefetch_desc(&tmap_x);
     tc::tma_prefetch_desc(&tmap_e);
     for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 256); }
     tc::mbar_init(efull, 1);
     tc::fence_barrier_init();
   }
@@ -106,7 +106,7 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
     }
   } else {
-    const int q = warp & 3, r = q * 32 + lane;
+    const int q = warp & 3, r = q * 32 + lane, jh = (warp - 2) >> 2;    // jh: which half of the slot columns this warp stores
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float sg = aff[0], tg = aff[1];
     uint32_t ti = 0;
@@ -120,11 +120,11 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       tc::mbar_wait(&tfull[g], u & 1);
       tc::tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 2 * jh; j < 2 * jh + 2; ++j) {
         float v[32];
         tc::tmem_ld32(tmem_base + lane_addr + g * 128 + j * 32, v);
         tc::tmem_ld_wait();
-        if (j == 3) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }
+        if (j == 2 * jh + 1) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }
         if (!pv) continue;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {

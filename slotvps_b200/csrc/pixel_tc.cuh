@@ -19,6 +19,11 @@ namespace slotvps {
 
 struct TcStageOperands {
   __half* wplanes = nullptr;     // [4][256][256]: Wk_c hi, Wk_c lo, Wv_c hi, Wv_c lo (row-major [out][in])
+  // Triangular form of the same statistics: Wc = Q R (Householder, fp64) => ||Wc u + bc||^2 = ||R u + Q^T bc||^2 with R upper
+  // triangular, so the channels of k-subtile ks only reach the first 64 (ks + 1) outputs: 62.5 % of the MMA work.
+  __half* rplanes = nullptr;     // [4][256][256]: R_k hi, R_k lo, R_v hi, R_v lo
+  float* rbias = nullptr;        // [2][256]: Q_k^T bk_c, Q_v^T bv_c
+  double* qr_scratch = nullptr;  // [2][257][256] fp64 working copies (weights + bias row) of the factorisation
 };
 struct TcWorkspace {
   // operand planes x hi, x lo, (x+pos) hi, (x+pos) lo, each stored as four 64-channel sub-planes [4 planes][4 ks][rows][64]:
@@ -42,7 +47,12 @@ struct PosSep {
   const float *pgy = nullptr, *pgx = nullptr;
 };
 
-inline void tc_stage_layout(Arena& a, TcStageOperands* o) { o->wplanes = a.take<__half>((size_t)4 * C * C); }
+inline void tc_stage_layout(Arena& a, TcStageOperands* o) {
+  o->wplanes = a.take<__half>((size_t)4 * C * C);
+  o->rplanes = a.take<__half>((size_t)4 * C * C);
+  o->rbias = a.take<float>(2 * C);
+  o->qr_scratch = a.take<double>((size_t)2 * (C + 1) * C);
+}
 inline void tc_workspace_layout(Arena& a, const slotvps_head_desc* d, TcWorkspace* w) {
   long Pmax = 0;
   int hmax = 0, wmax = 0;
@@ -426,12 +436,227 @@ stats_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc2(tmem_base, 512); }
 }
 
+// ---- triangular statistics -------------------------------------------------------------------------------------------
+// Householder QR of the centred projection (rows = outputs, columns = input channels) in fp64, one CTA per matrix:
+// A <- H_255 ... H_0 A = R (upper triangular), b <- Q^T b.  Thread c owns column c (and thread 0 the bias, stored as
+// column-vector row 256 of the scratch: scratch[i][c] for i < 256 is A, scratch[256][i] is b_i).
+// blockIdx.x = 0: keys (Wk_c, bk_c), 1: values (Wv_c, bv_c).
+__global__ void __launch_bounds__(256) qr_planes_kernel(const float* __restrict__ Wk, const float* __restrict__ bk, const float* __restrict__ Wv,
+                                                        const float* __restrict__ bv, double* __restrict__ scratch, __half* __restrict__ planes,
+                                                        float* __restrict__ rbias) {
+  const int which = blockIdx.x, c = threadIdx.x;
+  const float* W = which ? Wv : Wk;
+  const float* b = which ? bv : bk;
+  double* A = scratch + (size_t)which * (C + 1) * C;
+  double* bb = A + (size_t)C * C;
+  __shared__ double sv[C];
+  __shared__ double red[8];
+  __shared__ double s_beta;
+  for (int i = 0; i < C; ++i) A[i * C + c] = (double)W[i * C + c];
+  bb[c] = (double)b[c];
+  __syncthreads();
+  for (int j = 0; j < C - 1; ++j) {
+    // v = x + sign(x_0) ||x|| e_0 for x = A[j:, j]
+    const double xj = c >= j ? A[c * C + j] : 0.0;          // thread c holds row c of column j
+    double part = xj * xj;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((c & 31) == 0) red[c >> 5] = part;
+    __syncthreads();
+    double nrm2 = 0.0;
+    for (int i = 0; i < 8; ++i) nrm2 += red[i];
+    const double nrm = sqrt(nrm2);
+    const double x0 = A[j * C + j];
+    const double alpha = x0 >= 0.0 ? -nrm : nrm;
+    sv[c] = c < j ? 0.0 : (c == j ? xj - alpha : xj);
+    if (c == 0) { const double v0 = x0 - alpha; s_beta = (nrm2 - x0 * x0 + v0 * v0); }     // ||v||^2
+    __syncthreads();
+    const double vv = s_beta;
+    if (vv > 0.0) {
+      // column c (>= j) of A, and the bias through thread j's spare time: thread 255 handles b when c == 255
+      if (c >= j) {
+        double dot = 0.0;
+        for (int i = j; i < C; ++i) dot += sv[i] * A[i * C + c];
+        const double f = 2.0 * dot / vv;
+        for (int i = j; i < C; ++i) A[i * C + c] -= f * sv[i];
+      }
+      if (c == 0) {
+        double dot = 0.0;
+        for (int i = j; i < C; ++i) dot += sv[i] * bb[i];
+        const double f = 2.0 * dot / vv;
+        for (int i = j; i < C; ++i) bb[i] -= f * sv[i];
+      }
+    }
+    __syncthreads();
+  }
+  // R (entries below the diagonal are exactly zero by construction) -> fp16 hi / lo planes, Q^T b -> fp32.  Plane row =
+  // accumulator column of the CTA-pair kernel: output o of "ring" o / 64 sits 32 (ring + 1) columns left of the centre
+  // (first half of the ring, rows of CTA 0) or 32 ring columns right of it (second half, CTA 1), so the outputs that are
+  // active for k-subtile ks -- o < 64 (ks + 1) -- occupy the contiguous, centred column range [32 (3 - ks), 256 - 32 (3 - ks)).
+  __half* hi = planes + (size_t)(2 * which) * C * C;
+  __half* lo = hi + (size_t)C * C;
+  for (int o = 0; o < C; ++o) {
+    const int ring = o >> 6, off = o & 63;
+    const int col = off < 32 ? 128 - 32 * (ring + 1) + off : 128 + 32 * ring + (off - 32);
+    double v = c >= o ? A[o * C + c] : 0.0;
+    v = fmin(fmax(v, -65504.0), 65504.0);
+    const __half h = __double2half(v);
+    hi[col * C + c] = h;
+    lo[col * C + c] = __double2half(v - (double)__half2float(h));
+  }
+  {
+    const int ring = c >> 6, off = c & 63;
+    const int col = off < 32 ? 128 - 32 * (ring + 1) + off : 128 + 32 * ring + (off - 32);
+    rbias[which * C + col] = (float)bb[c];
+  }
+}
+
+namespace stats3 {
+constexpr int TILE_M = 128, KSUB = 64;
+constexpr int A_BYTES = TILE_M * 128;          // 16 KB
+constexpr int B_ROWS = 32;                     // weight rows per TMA box
+constexpr int B_BOX = B_ROWS * 128;            // 4 KB
+constexpr int B_BYTES = 128 * 128;             // up to 128 rows of one plane per CTA (half of the active outputs)
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // 64 KB (filled 40 / 48 / 56 / 64 KB)
+constexpr int NSTAGE = 3;
+constexpr int AUX_BYTES = 4096;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + AUX_BYTES + 1024;
+constexpr int THREADS = 192;
+}  // namespace stats3
+
+// The statistics from the triangular factors on CTA pairs (cta_group::2, M = 256 = two pixel tiles).  k-subtiles are visited
+// from the LAST to the first: the first MMA of a tile (N = 256) initialises every accumulator column, the later, narrower
+// ones (N = 192, 128, 64 at column offset 32, 64, 96) only add to theirs.  Each CTA stages its half of the active weight rows.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(stats3::THREADS, 1)
+stats_tri_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_r,
+                 const float* __restrict__ rbias, float* __restrict__ rs_k, float* __restrict__ rs_v, int P, int T, int plane_rows,
+                 int tiles_per_frame, int x_planes_only) {
+  using namespace stats3;
+  extern __shared__ uint8_t raw_smem[];
+  const uint32_t raw = tc::smem_u32(raw_smem);
+  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
+  uint8_t* aux = smem + NSTAGE * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(aux);                  // [NSTAGE] used on the leader
+  uint64_t* empty = full + NSTAGE;                                    // [NSTAGE] in both CTAs (multicast commit)
+  uint64_t* tfull = empty + NSTAGE;                                   // [2] in both CTAs (multicast commit)
+  uint64_t* tempty = tfull + 2;                                       // [2] on the leader: 256 arrivals
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* bias = reinterpret_cast<float*>(aux + 256);                  // [2][256] in accumulator-column order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_tiles = T * tiles_per_frame;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_iter = ((n_tiles + 1) / 2 - pair + n_pairs - 1) / n_pairs;
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmap_x);
+    tc::tma_prefetch_desc(&tmap_r);
+    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 256); }
+    tc::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * C; i += THREADS) bias[i] = rbias[i];
+  if (warp == 1) { tc::tmem_alloc2(tmem_ptr, 512); tc::tmem_relinquish2(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int i = 0; i < n_iter; ++i) {
+        const int tile = (pair + i * n_pairs) * 2 + (int)rank;
+        const int t = tile / tiles_per_frame, p0 = (tile % tiles_per_frame) * TILE_M;
+        const int row = t * P + p0;
+        for (int g = 0; g < 2; ++g) {
+          const int aq = (g == 0 && !x_planes_only) ? 2 : 0, bq = g == 0 ? 0 : 2;
+          for (int ks = C / KSUB - 1; ks >= 0; --ks, ++it) {
+            const int s = it % NSTAGE, nb = ks + 1;                  // nb boxes of 32 weight rows per plane and CTA
+            const int r0 = rank == 0 ? 32 * (3 - ks) : 128;          // first plane row (= accumulator column) of this CTA's active half
+            tc::mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
+            uint8_t* st = smem + s * STAGE_BYTES;
+            if (leader) tc::mbar_expect_tx(&full[s], 2 * (2 * A_BYTES + 2 * nb * B_BOX));
+            tc::tma_load_2d_pair(st, &tmap_x, 0, (aq * 4 + ks) * plane_rows + row, &full[s]);
+            tc::tma_load_2d_pair(st + A_BYTES, &tmap_x, 0, ((aq + 1) * 4 + ks) * plane_rows + row, &full[s]);
+            for (int bx = 0; bx < nb; ++bx) {
+              tc::tma_load_2d_pair(st + 2 * A_BYTES + bx * B_BOX, &tmap_r, ks * KSUB, bq * C + r0 + bx * B_ROWS, &full[s]);
+              tc::tma_load_2d_pair(st + 2 * A_BYTES + B_BYTES + bx * B_BOX, &tmap_r, ks * KSUB, (bq + 1) * C + r0 + bx * B_ROWS, &full[s]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      uint32_t it = 0;
+      for (int i = 0; i < n_iter; ++i) {
+        for (int g = 0; g < 2; ++g) {
+          tc::mbar_wait(&tempty[g], (i & 1) ^ 1);
+          tc::tc_fence_after();
+          for (int ks = C / KSUB - 1; ks >= 0; --ks, ++it) {
+            const int s = it % NSTAGE;
+            const uint32_t idesc = tc::make_idesc_f16(256, 64 * (ks + 1), 0, 0);
+            const uint32_t d_tmem = tmem_base + g * 256 + 32 * (3 - ks);
+            tc::mbar_wait(&full[s], (it / NSTAGE) & 1);
+            tc::tc_fence_after();
+            const uint32_t a_hi = tc::smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+            const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+            const uint64_t dah = tc::make_smem_desc_sw128(a_hi, 16, 1024), dal = tc::make_smem_desc_sw128(a_lo, 16, 1024);
+            const uint64_t dbh = tc::make_smem_desc_sw128(b_hi, 16, 1024), dbl = tc::make_smem_desc_sw128(b_lo, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < KSUB / 16; ++k) {
+              tc::umma2_f16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (ks != C / KSUB - 1 || k != 0) ? 1u : 0u);
+              tc::umma2_f16(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);
+              tc::umma2_f16(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+            }
+            tc::umma2_commit_multicast(&empty[s], 3);
+          }
+          tc::umma2_commit_multicast(&tfull[g], 3);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    for (int i = 0; i < n_iter; ++i) {
+      const int tile = (pair + i * n_pairs) * 2 + (int)rank;
+      const int t = tile / tiles_per_frame, p = (tile % tiles_per_frame) * TILE_M + r;
+      const bool valid = tile < n_tiles && p < P;
+      for (int g = 0; g < 2; ++g) {
+        tc::mbar_wait(&tfull[g], i & 1);
+        tc::tc_fence_after();
+        const float* bg = bias + g * C;
+        float ss = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < C / 32; ++j) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + g * 256 + j * 32, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { float d = v[c] + bg[j * 32 + c]; ss = fmaf(d, d, ss); }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive_remote(&tempty[g], 0);
+        if (valid) (g == 0 ? rs_k : rs_v)[(long)t * P + p] = rsqrtf(ss * (1.f / C) + LN_EPS);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc2(tmem_base, 512); }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------
 inline int tc_prepare_stage(const slotvps_stage_params& sp, const float* Wk_c, const float* bk_c, const float* Wv_c,
                             const float* bv_c, TcStageOperands& o, cudaStream_t s) {
   (void)sp; (void)bk_c; (void)bv_c;
   weight_planes_kernel<<<ceil_div(C * C, 256), 256, 0, s>>>(Wk_c, Wv_c, o.wplanes);
   SV_CHECK_LAUNCH("weight_planes");
+  qr_planes_kernel<<<2, 256, 0, s>>>(Wk_c, bk_c, Wv_c, bv_c, o.qr_scratch, o.rplanes, o.rbias);
+  SV_CHECK_LAUNCH("qr_planes");
   return SLOTVPS_OK;
 }
 
@@ -466,6 +691,18 @@ inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const flo
   SV_TRY(ensure_dyn_smem((const void*)stats_tc_kernel, stats::SMEM_BYTES));
   const int tiles_per_frame = ceil_div(P, stats::TILE_M);
   const int n_tiles = T * tiles_per_frame;
+  static const int use_tri = getenv("SLOTVPS_STATS_TRI") ? atoi(getenv("SLOTVPS_STATS_TRI")) : 1;
+  if (use_tri && ps.tky == nullptr && ops.rplanes != nullptr && n_tiles >= 2 && max_ctas >= 2) {      // triangular factors on CTA pairs
+    CUtensorMap mr;                                                                                   // (no separable position tables in this form)
+    SV_TRY(tc::make_tmap_h16_sw128(&mr, ops.rplanes, (uint64_t)4 * C, C, stats3::B_ROWS));
+    SV_TRY(ensure_dyn_smem((const void*)stats_tri_kernel, stats3::SMEM_BYTES));
+    int grid3 = 2 * ((n_tiles + 1) / 2);
+    if (grid3 > (max_ctas & ~1)) grid3 = max_ctas & ~1;
+    g_prof_grid = grid3;
+    stats_tri_kernel<<<grid3, stats3::THREADS, stats3::SMEM_BYTES, s>>>(mx, mr, ops.rbias, rs_k, rs_v, P, T, (int)rows, tiles_per_frame, ps.enabled);
+    SV_CHECK_LAUNCH("stats_tc");
+    return SLOTVPS_OK;
+  }
   static const int use_pairs = getenv("SLOTVPS_STATS_PAIRS") ? atoi(getenv("SLOTVPS_STATS_PAIRS")) : 1;   // CTA pairs by default
   if (use_pairs && n_tiles >= 2 && max_ctas >= 2) {
     CUtensorMap mw2;
