@@ -526,8 +526,11 @@ def main():
             elif mdl[0] == "tensor":
                 ach = mdl[1] / (t_ms * 1e-3) / 1e12
                 tj = tj_all.get(name)
+                # executed MMA work per algorithmic FLOP: 3 products of the fp16 hi/lo split; the statistics kernel runs on the
+                # triangular (QR) factors, which need only 10/16 of the weight blocks
+                xf = 3 * 0.625 if (name == "stats_tc" and os.environ.get("SLOTVPS_STATS_TRI", "1") != "0") else 3
                 ent.update(bound="tensor", achieved=ach, peak=pk["bf16_tflops"], unit="TFLOP/s", frac=ach / pk["bf16_tflops"],
-                           executed_mma_tflops=3 * ach, executed_frac=3 * ach / pk["bf16_tflops"],     # fp16 hi/lo split: 3 MMA products per algorithmic product
+                           executed_mma_tflops=xf * ach, executed_frac=xf * ach / pk["bf16_tflops"], executed_per_algorithmic=xf,
                            algorithmic_flops_per_step=mdl[1],
                            traffic=(tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["pixels"] * px_stage / nl if tj else None,
                            traffic_note=f"DRAM bytes per launch ({tj_all.get('_file')}: ncu level-3 capture scaled by pixels)" if tj else None,
@@ -557,8 +560,11 @@ def main():
             per_frame_flops = sum(hd * h * w * (4 * 256 * 256 + 4 * N * 256) for hd, (h, w) in zip(heads, shapes))
             tt = sum(breakdown[k]["ms_per_step"] for k in names)
             alg = per_frame_flops * T / (tt * 1e-3) / 1e12
+            ex = sum(per_kernel[k]["executed_mma_tflops"] * breakdown[k]["ms_per_step"] for k in names if "executed_mma_tflops" in per_kernel[k]) / tt
             roofline["attention_contraction"] = dict(kernels=names, algorithmic_tflops=alg, ms_per_step=tt, frac_of_peak=alg / pk["bf16_tflops"],
-                                                     executed_frac_of_peak=3 * alg / pk["bf16_tflops"], peak=pk["bf16_tflops"])
+                                                     executed_mma_tflops=ex, executed_frac_of_peak=ex / pk["bf16_tflops"], peak=pk["bf16_tflops"],
+                                                     note="executed = MMA FLOPs actually issued (3 fp16 hi/lo products per algorithmic product; "
+                                                          "the statistics GEMM runs on triangular QR factors: 0.625 of its weight blocks)")
         hb = {"peak_gbs": pk["hbm_gbs"], "peak_source": pk["source"] + " copy bandwidth"}
         if "mask_tc" in per_kernel:
             hb["mask_logits"] = {k: per_kernel["mask_tc"].get(k) for k in ("kernel", "algorithmic_bytes_per_step", "ms_per_step", "achieved", "frac")}

@@ -528,7 +528,8 @@ constexpr int THREADS = 192;
 // from the LAST to the first: the first MMA of a tile (N = 256) initialises every accumulator column, the later, narrower
 // ones (N = 192, 128, 64 at column offset 32, 64, 96) only add to theirs.  Each CTA stages its half of the active weight rows.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(stats3::THREADS, 1)
-stats_tri_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_r,
+stats_tri_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_r0, const __grid_constant__ CUtensorMap tmap_r1,
+                 const __grid_constant__ CUtensorMap tmap_r2, const __grid_constant__ CUtensorMap tmap_r3,      // boxes of 32, 64, 96, 128 weight rows
                  const float* __restrict__ rbias, float* __restrict__ rs_k, float* __restrict__ rs_v, int P, int T, int plane_rows,
                  int tiles_per_frame, int x_planes_only) {
   using namespace stats3;
@@ -550,7 +551,7 @@ stats_tri_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const int n_iter = ((n_tiles + 1) / 2 - pair + n_pairs - 1) / n_pairs;
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmap_x);
-    tc::tma_prefetch_desc(&tmap_r);
+    tc::tma_prefetch_desc(&tmap_r0); tc::tma_prefetch_desc(&tmap_r1); tc::tma_prefetch_desc(&tmap_r2); tc::tma_prefetch_desc(&tmap_r3);
     for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 256); }
     tc::fence_barrier_init();
@@ -580,10 +581,9 @@ stats_tri_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (leader) tc::mbar_expect_tx(&full[s], 2 * (2 * A_BYTES + 2 * nb * B_BOX));
             tc::tma_load_2d_pair(st, &tmap_x, 0, (aq * 4 + ks) * plane_rows + row, &full[s]);
             tc::tma_load_2d_pair(st + A_BYTES, &tmap_x, 0, ((aq + 1) * 4 + ks) * plane_rows + row, &full[s]);
-            for (int bx = 0; bx < nb; ++bx) {
-              tc::tma_load_2d_pair(st + 2 * A_BYTES + bx * B_BOX, &tmap_r, ks * KSUB, bq * C + r0 + bx * B_ROWS, &full[s]);
-              tc::tma_load_2d_pair(st + 2 * A_BYTES + B_BYTES + bx * B_BOX, &tmap_r, ks * KSUB, (bq + 1) * C + r0 + bx * B_ROWS, &full[s]);
-            }
+            const CUtensorMap* mr = ks == 0 ? &tmap_r0 : ks == 1 ? &tmap_r1 : ks == 2 ? &tmap_r2 : &tmap_r3;     // one box of 32 nb rows per plane
+            tc::tma_load_2d_pair(st + 2 * A_BYTES, mr, ks * KSUB, bq * C + r0, &full[s]);
+            tc::tma_load_2d_pair(st + 2 * A_BYTES + B_BYTES, mr, ks * KSUB, (bq + 1) * C + r0, &full[s]);
           }
         }
       }
@@ -693,13 +693,13 @@ inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const flo
   const int n_tiles = T * tiles_per_frame;
   static const int use_tri = getenv("SLOTVPS_STATS_TRI") ? atoi(getenv("SLOTVPS_STATS_TRI")) : 1;
   if (use_tri && ps.tky == nullptr && ops.rplanes != nullptr && n_tiles >= 2 && max_ctas >= 2) {      // triangular factors on CTA pairs
-    CUtensorMap mr;                                                                                   // (no separable position tables in this form)
-    SV_TRY(tc::make_tmap_h16_sw128(&mr, ops.rplanes, (uint64_t)4 * C, C, stats3::B_ROWS));
+    CUtensorMap mr[4];                                                                                // (no separable position tables in this form)
+    for (int i = 0; i < 4; ++i) SV_TRY(tc::make_tmap_h16_sw128(&mr[i], ops.rplanes, (uint64_t)4 * C, C, stats3::B_ROWS * (i + 1)));
     SV_TRY(ensure_dyn_smem((const void*)stats_tri_kernel, stats3::SMEM_BYTES));
     int grid3 = 2 * ((n_tiles + 1) / 2);
     if (grid3 > (max_ctas & ~1)) grid3 = max_ctas & ~1;
     g_prof_grid = grid3;
-    stats_tri_kernel<<<grid3, stats3::THREADS, stats3::SMEM_BYTES, s>>>(mx, mr, ops.rbias, rs_k, rs_v, P, T, (int)rows, tiles_per_frame, ps.enabled);
+    stats_tri_kernel<<<grid3, stats3::THREADS, stats3::SMEM_BYTES, s>>>(mx, mr[0], mr[1], mr[2], mr[3], ops.rbias, rs_k, rs_v, P, T, (int)rows, tiles_per_frame, ps.enabled);
     SV_CHECK_LAUNCH("stats_tc");
     return SLOTVPS_OK;
   }
