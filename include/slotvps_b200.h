@@ -124,7 +124,7 @@ int slotvps_head_forward(const slotvps_head_desc* d, const slotvps_stage_params*
  *                           SlotVPSRetriever set it: simple_test only consumes the finest level, through the planes.
  *   feat_bn_scale/shift   : [256] folded feat_bn (eval) of generate_final_outputs (vps_temporal_slots.py:145-149).  When
  *                           given, the finest level's fusion epilogue also accumulates sum_c (scale*x+shift)^2 per pixel
- *                           into rnorm_ss [T][P_last] (zeroed by the call), which slotvps_head_mask_logits then uses
+ *                           into rnorm_ss [4][T][P_last] (four 64-channel partial sums), which slotvps_head_mask_logits_ex then uses
  *                           instead of re-reading the fp32 feature.                                                     */
 typedef struct slotvps_head_opts {
   const float* const* stage_slots_in;
@@ -179,7 +179,7 @@ int slotvps_head_mask_logits(const slotvps_head_desc* d, void* head_workspace, s
 int slotvps_fold_batchnorm(const float* w, const float* b, const float* mean, const float* var, int n,
                            float* scale, float* shift, void* stream);
 
-/* Same; exactly one of `feat` (per-pixel norm computed from the fp32 feature) and `rnorm_ss` ([T][P_last] squared norms of
+/* Same; exactly one of `feat` (per-pixel norm computed from the fp32 feature) and `rnorm_ss` ([4][T][P_last] partial squared norms of
  * feat_bn(x) accumulated by slotvps_head_forward_ex with opts.rnorm_ss) is non-NULL.                                       */
 int slotvps_head_mask_logits_ex(const slotvps_head_desc* d, void* head_workspace, size_t head_workspace_bytes, int frame,
                                 const float* feat, const float* rnorm_ss, const float* emb,

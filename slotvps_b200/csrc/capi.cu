@@ -785,7 +785,6 @@ int slotvps_head_forward_ex(const slotvps_head_desc* d, const slotvps_stage_para
       prm.bias = l > 0 ? pr.conv_b : pr.conv_b0; prm.y_in = l > 0 ? w.ftc.y : nullptr;
       prm.out = skip_out ? nullptr : fused_out[l]; prm.out_bs = fstride[l];
       if (o.rnorm_ss && l == L - 1) {
-        SV_CHECK_CUDA(cudaMemsetAsync(o.rnorm_ss, 0, (size_t)rows * sizeof(float), s));
         prm.bn_sc = o.feat_bn_scale; prm.bn_sh = o.feat_bn_shift; prm.ss_out = o.rnorm_ss;
       }
       prm.planes = tcl.planes; prm.plane_stride = rows; prm.x_planes_only = pos_sep ? 1 : 0;
@@ -1148,7 +1147,7 @@ int slotvps_head_mask_logits_ex(const slotvps_head_desc* d, void* head_workspace
     else feat_rnorm_kernel<<<ceil_div(P, 256), 256, 0, s>>>(feat, sc, sh, rn, P);
     SV_CHECK_LAUNCH("feat_rnorm");
   } else {
-    rnp = rnorm_ss + (long)frame * P;
+    rnp = rnorm_ss + (long)frame * P;                        // four partial sums, (long)d->n_frames * P apart
   }
   const long rows = (long)d->n_frames * P;
   // the finest level used the alternate plane set iff the head call ran the overlapped schedule (recorded by it)
@@ -1159,7 +1158,7 @@ int slotvps_head_mask_logits_ex(const slotvps_head_desc* d, void* head_workspace
     const int ng = base + (g < extra ? 1 : 0);
     g_planes_kernel<<<(unsigned)(((long)mask::NROW * C + 255) / 256), 256, 0, s>>>(e2, ep, ng, 1, n0, N);
     SV_CHECK_LAUNCH("g_planes");
-    SV_TRY(mask_tc_launch(planes, 2 * rows, rows, (long)frame * P, ep, dn + n0, rnp, aff, out + (long)n0 * P, ng, P, s, feat ? 0 : 1));
+    SV_TRY(mask_tc_launch(planes, 2 * rows, rows, (long)frame * P, ep, dn + n0, rnp, aff, out + (long)n0 * P, ng, P, s, feat ? 0 : (int)rows));
     n0 += ng;
   }
   return SLOTVPS_OK;

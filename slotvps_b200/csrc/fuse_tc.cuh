@@ -23,7 +23,7 @@ constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 constexpr int NSTAGE = 2;
 constexpr int AUX_BYTES = 4096;               // barriers, tmem pointer, bias [256], feat_bn scale / shift [2][256]
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + AUX_BYTES + 1024;
-constexpr int THREADS = 320;                   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int THREADS = 576;                   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue (four per TMEM lane quadrant, 64 columns each)
 constexpr uint32_t IDESC = tc::make_idesc_f16(128, 256, 0, 0);
 // conv_trans weight planes carry 2^8 (a weight of ~0.05 would have a subnormal fp16 lo plane: ~1e-6 relative instead of
 // 2.4e-7); the epilogue multiplies the accumulator by 2^-8 (exact)
@@ -49,8 +49,8 @@ struct Params {
   long pos_bs;
   const float *ytab, *xtab;   // separable sine tables of this resolution or null
   int h;
-  // optional (finest level): per-pixel sum_c (bn_sc[c] x[c] + bn_sh[c])^2 accumulated into ss_out [rows] (zeroed by the
-  // caller).  The two epilogue warps of a pixel add one partial each: 0 + a + b is order-independent, so it stays deterministic.
+  // optional (finest level): per-pixel sum_c (bn_sc[c] x[c] + bn_sh[c])^2 as four partial sums (one per 64-channel quarter,
+  // written by the four epilogue threads of a pixel) ss_out [4][rows]; the consumer adds them in a fixed order (deterministic).
   const float *bn_sc, *bn_sh;
   float* ss_out;
 };
@@ -141,7 +141,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc::tma_prefetch_desc(&tmap_a);
     tc::tma_prefetch_desc(&tmap_w);
     for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 256); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 512); }
     tc::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < C; i += THREADS) bias[i] = prm.bias ? prm.bias[i] : 0.f;
@@ -201,82 +201,80 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
+    // ===================== epilogue: 16 warps, four threads per pixel, 16-channel units =====================
+    // The epilogue (bias, bilinear gather of the coarse term, two fp16 hi/lo splits, position add, stores) is what bounds
+    // this kernel (ncu, level 3: tensor pipe 10 %, DRAM 25 %, issue slots 33 % busy with 8 epilogue warps); sixteen warps
+    // working on 16-column units keep the register footprint small enough for 576 threads and double the latency hiding.
     const int q = warp & 3;
-    const int jhalf = (warp - 2) >> 2;                      // which half of the 256 output columns this warp drains
+    const int jq = (warp - 2) >> 2;                         // 64-channel quarter of the 256 output columns this warp drains
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const int g = ti & 1, u = ti >> 1;
+      const int g = ti & 1, uu_ = ti >> 1;
       const int row = tile * TILE_M + r;
       const bool rv = row < prm.rows;
       const int t = rv ? row / prm.P : 0, p = rv ? row % prm.P : 0;
+      const int py = p / prm.w, px = p % prm.w;
       // bilinear x2 source taps (align_corners=False): coarse map is (h/2) x (w/2)
       int i00 = 0, i01 = 0, i10 = 0, i11 = 0;
       float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
-      const int py = p / prm.w, px = p % prm.w;
-      if (prm.y_in) {
-        const int ch = prm.h / 2, cw = prm.w / 2;
-        float sy = fmaxf((py + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((px + 0.5f) * 0.5f - 0.5f, 0.f);
-        int y0 = (int)sy, x0 = (int)sx;
-        int y1 = min(y0 + 1, ch - 1), x1 = min(x0 + 1, cw - 1);
-        float ly = sy - y0, lx = sx - x0;
-        const int base = t * ch * cw;
-        i00 = base + y0 * cw + x0; i01 = base + y0 * cw + x1; i10 = base + y1 * cw + x0; i11 = base + y1 * cw + x1;
-        w00 = (1.f - ly) * (1.f - lx); w01 = (1.f - ly) * lx; w10 = ly * (1.f - lx); w11 = ly * lx;
-      }
       // cooperative gather (w % 32 == 0: a warp's 32 pixels share one image row and one frame)
       const bool coop = prm.y_in != nullptr && (prm.w & 31) == 0;
       int cbase = 0, cy0 = 0, cy1 = 0, ccol = 0, cs0 = 0, cs1 = 0;
       float cwy0 = 0.f, cwy1 = 0.f, cwx0 = 0.f, cwx1 = 0.f;
-      if (coop) {
+      if (prm.y_in) {
         const int ch = prm.h / 2, cw = prm.w / 2;
         const float sy = fmaxf((py + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((px + 0.5f) * 0.5f - 0.5f, 0.f);
-        cy0 = (int)sy; cy1 = min(cy0 + 1, ch - 1);
-        cwy1 = sy - cy0; cwy0 = 1.f - cwy1;
-        const int x0 = (int)sx, x1 = min(x0 + 1, cw - 1);
-        cwx1 = sx - x0; cwx0 = 1.f - cwx1;
-        const int first = (px - lane) / 2 - 1;                 // coarse column fetched by lane 0 (clamped below)
-        cs0 = x0 - first; cs1 = x1 - first;
-        ccol = min(max(first + lane, 0), cw - 1);
-        cbase = t * ch * cw;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = min(y0 + 1, ch - 1), x1 = min(x0 + 1, cw - 1);
+        const float ly = sy - y0, lx = sx - x0;
+        const int base = t * ch * cw;
+        if (coop) {
+          cy0 = y0; cy1 = y1; cwy1 = ly; cwy0 = 1.f - ly; cwx1 = lx; cwx0 = 1.f - lx;
+          const int first = (px - lane) / 2 - 1;               // coarse column fetched by lane 0 (clamped below)
+          cs0 = x0 - first; cs1 = x1 - first;
+          ccol = min(max(first + lane, 0), cw - 1);
+          cbase = base;
+        } else {
+          i00 = base + y0 * cw + x0; i01 = base + y0 * cw + x1; i10 = base + y1 * cw + x0; i11 = base + y1 * cw + x1;
+          w00 = (1.f - ly) * (1.f - lx); w01 = (1.f - ly) * lx; w10 = ly * (1.f - lx); w11 = ly * lx;
+        }
       }
-      if (coop && rv && lane < 18) {                          // first chunk's coarse rows, requested before the accumulator wait
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(prm.y_in + (long)(cbase + cy0 * (prm.w / 2) + ccol) * C + jhalf * 128));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(prm.y_in + (long)(cbase + cy1 * (prm.w / 2) + ccol) * C + jhalf * 128));
+      const float* cr0 = coop ? prm.y_in + (long)(cbase + cy0 * (prm.w / 2) + ccol) * C : nullptr;
+      const float* cr1 = coop ? prm.y_in + (long)(cbase + cy1 * (prm.w / 2) + ccol) * C : nullptr;
+      if (coop && rv && lane < 18) {                          // this warp's coarse rows (2 x 256 B), requested before the accumulator wait
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(cr0 + jq * 64));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(cr0 + jq * 64 + 32));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(cr1 + jq * 64));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(cr1 + jq * 64 + 32));
       }
-      tc::mbar_wait(&tfull[g], u & 1);
+      tc::mbar_wait(&tfull[g], uu_ & 1);
       tc::tc_fence_after();
       float ss_part = 0.f;
 #pragma unroll 1
-      for (int j = jhalf * 4; j < jhalf * 4 + 4; ++j) {
-        float v[32];
-        tc::tmem_ld32(tmem_base + lane_addr + g * 256 + j * 32, v);
+      for (int uu = 0; uu < 4; ++uu) {
+        const int u = jq * 4 + uu;                            // 16-channel unit: channels [16 u, 16 u + 16)
+        float v[16];
+        tc::tmem_ld16(tmem_base + lane_addr + g * 256 + u * 16, v);
         tc::tmem_ld_wait();
-        if (j == jhalf * 4 + 3) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }      // this warp's half is drained
+        if (uu == 3) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }      // this warp's quarter is drained
         if (!rv) continue;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], WSCALE_INV, bias[j * 32 + c]);
+        for (int c = 0; c < 16; ++c) v[c] = fmaf(v[c], WSCALE_INV, bias[u * 16 + c]);
         if (prm.y_out) {
-          float* dst = prm.y_out + (long)row * C + j * 32;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tc::st_global_v8f(dst + 8 * c, v + 8 * c);
+          float* dst = prm.y_out + (long)row * C + u * 16;
+          tc::st_global_v8f(dst, v); tc::st_global_v8f(dst + 8, v + 8);
           continue;
         }
         if (coop) {
           // the 32 pixels of this warp lie in one image row: lanes 0..17 fetch the 18 coarse columns the row segment
           // touches (two coarse rows each, blended vertically), every lane then takes its two columns by shuffle
-          const float* r0 = prm.y_in + (long)(cbase + cy0 * (prm.w / 2) + ccol) * C + j * 32;
-          const float* r1 = prm.y_in + (long)(cbase + cy1 * (prm.w / 2) + ccol) * C + j * 32;
-          if (lane < 18 && j + 1 < jhalf * 4 + 4) {            // next chunk's two 128-byte lines -> L1 while this chunk is processed
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(r0 + 32));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(r1 + 32));
-          }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             float ta[8], tb[8];
             if (lane < 18) {
-              tc::ld_global_nc_v8f(r0 + 8 * c, ta); tc::ld_global_nc_v8f(r1 + 8 * c, tb);
+              tc::ld_global_nc_v8f(cr0 + u * 16 + 8 * c, ta); tc::ld_global_nc_v8f(cr1 + u * 16 + 8 * c, tb);
 #pragma unroll
               for (int e = 0; e < 8; ++e) ta[e] = cwy0 * ta[e] + cwy1 * tb[e];
             } else {
@@ -290,12 +288,12 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         } else if (prm.y_in) {
-          const float* a = prm.y_in + (long)i00 * C + j * 32;
-          const float* b = prm.y_in + (long)i01 * C + j * 32;
-          const float* cc = prm.y_in + (long)i10 * C + j * 32;
-          const float* d = prm.y_in + (long)i11 * C + j * 32;
+          const float* a = prm.y_in + (long)i00 * C + u * 16;
+          const float* b = prm.y_in + (long)i01 * C + u * 16;
+          const float* cc = prm.y_in + (long)i10 * C + u * 16;
+          const float* d = prm.y_in + (long)i11 * C + u * 16;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             float ya[8], yb[8], yc[8], yd[8];
             tc::ld_global_nc_v8f(a + 8 * c, ya); tc::ld_global_nc_v8f(b + 8 * c, yb);
             tc::ld_global_nc_v8f(cc + 8 * c, yc); tc::ld_global_nc_v8f(d + 8 * c, yd);
@@ -306,46 +304,42 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         if (prm.ss_out) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) { const float gq = fmaf(bnv[j * 32 + c], v[c], bnv[C + j * 32 + c]); ss_part = fmaf(gq, gq, ss_part); }
-          if (j == jhalf * 4 + 3) atomicAdd(prm.ss_out + row, ss_part);
+          for (int c = 0; c < 16; ++c) { const float gq = fmaf(bnv[u * 16 + c], v[c], bnv[C + u * 16 + c]); ss_part = fmaf(gq, gq, ss_part); }
+          if (uu == 3) prm.ss_out[(long)jq * prm.rows + row] = ss_part;
         }
         if (prm.out) {
-          float* o = prm.out + (long)t * prm.out_bs + (long)(j * 32) * prm.P + p;
+          float* o = prm.out + (long)t * prm.out_bs + (long)(u * 16) * prm.P + p;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) o[(long)c * prm.P] = v[c];
+          for (int c = 0; c < 16; ++c) o[(long)c * prm.P] = v[c];
         }
         if (prm.planes) {
-          uint32_t hi[16], lo[16];
-          auto pack = [&](const float* src) {
+          uint32_t hi[8], lo[8];
+          auto store = [&](int plane) {
+            // sub-plane ks = u / 4 of this plane, [rows][64]: the four units of a 64-channel group complete one 128-byte row
+            __half* dst = prm.planes + (((long)plane * 4 + (u >> 2)) * prm.plane_stride + row) * 64 + (u & 3) * 16;
+            tc::st_global_v8(dst, hi);
+            tc::st_global_v8(dst + (long)4 * prm.plane_stride * 64, lo);       // the lo plane is the next plane
+          };
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              __half h0, l0, h1, l1;
-              split_bf16(src[2 * c], h0, l0); split_bf16(src[2 * c + 1], h1, l1);
-              __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
-              hi[c] = *reinterpret_cast<uint32_t*>(&hh); lo[c] = *reinterpret_cast<uint32_t*>(&ll);
-            }
-          };
-          auto store = [&](int plane, const uint32_t* w) {
-            // sub-plane ks = j / 2 of this plane, [rows][64]: the two chunks of a 64-channel group complete one 128-byte row
-            __half* dst = prm.planes + (((long)plane * 4 + (j >> 1)) * prm.plane_stride + row) * 64 + (j & 1) * 32;
-            tc::st_global_v8(dst, w); tc::st_global_v8(dst + 16, w + 8);
-          };
-          pack(v); store(0, hi); store(1, lo);
+          for (int c = 0; c < 8; ++c) split2(v[2 * c], v[2 * c + 1], hi[c], lo[c]);
+          store(0);
           if (prm.x_planes_only) continue;
           if (prm.pos) {
-            const float* ps = prm.pos + (long)t * prm.pos_bs + (long)(j * 32) * prm.P + p;
+            const float* ps = prm.pos + (long)t * prm.pos_bs + (long)(u * 16) * prm.P + p;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] += __ldg(ps + (long)c * prm.P);
+            for (int c = 0; c < 16; ++c) v[c] += __ldg(ps + (long)c * prm.P);
           } else if (prm.ytab) {
-            if (j < 4) {
+            if (u < 8) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) v[c] += __ldg(prm.ytab + (j * 32 + c) * prm.h + py);
+              for (int c = 0; c < 16; ++c) v[c] += __ldg(prm.ytab + (u * 16 + c) * prm.h + py);
             } else {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) v[c] += __ldg(prm.xtab + ((j - 4) * 32 + c) * prm.w + px);
+              for (int c = 0; c < 16; ++c) v[c] += __ldg(prm.xtab + ((u - 8) * 16 + c) * prm.w + px);
             }
           }
-          pack(v); store(2, hi); store(3, lo);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) split2(v[2 * c], v[2 * c + 1], hi[c], lo[c]);
+          store(2);
         }
       }
     }

@@ -114,8 +114,10 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int g = ti & 1, u = ti >> 1;
       const int p = tile * TILE_M + r;
       const bool pv = p < P;
-      // rn: 1 / max(||feat_bn(x_p)||, 1e-12), or (rn_is_ss) the squared norm left by the level-fusion epilogue
-      const float rnp = pv ? __ldg(rn + p) : 1.f;
+      // rn: 1 / max(||feat_bn(x_p)||, 1e-12), or (rn_is_ss = stride between them) the four partial squared norms left by
+      // the level-fusion epilogue, added in a fixed order
+      float rnp = pv ? __ldg(rn + p) : 1.f;
+      if (rn_is_ss && pv) rnp = (rnp + __ldg(rn + rn_is_ss + p)) + (__ldg(rn + 2L * rn_is_ss + p) + __ldg(rn + 3L * rn_is_ss + p));
       const float scale = pv ? (rn_is_ss ? 1.f / fmaxf(sqrtf(rnp), 1e-12f) : rnp) * sg : 0.f;
       tc::mbar_wait(&tfull[g], u & 1);
       tc::tc_fence_after();

@@ -83,6 +83,14 @@ __device__ __forceinline__ void split_bf16(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
   lo = __float2half_rn(v - __half2float(hi));
 }
+// two fp32 values -> packed fp16 hi pair + lo pair (hi + lo carries 22 bits; clamped to the fp16 range)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __global__ void __launch_bounds__(256) weight_planes_kernel(const float* __restrict__ Wk, const float* __restrict__ Wv,
                                                             __half* __restrict__ out) {
   int i = blockIdx.x * 256 + threadIdx.x;

@@ -130,14 +130,6 @@ __device__ __forceinline__ void prefetch_gemm(const CUtensorMap* m, int opad, in
     }
 }
 
-// two fp32 values -> packed fp16 hi pair + lo pair (hi + lo carries 22 bits; clamped to the fp16 range)
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 f = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
-}
 // 16 fp32 values of row `row`, columns [16 u, 16 u + 16) -> fp16 hi/lo operand planes (K-major, 128-byte swizzle)
 __device__ __forceinline__ void store_operand16(uint8_t* base, int lo_off, int row, int u, const float* v) {
   uint8_t* sub = base + (u >> 2) * ACT_SUB + row * 128;

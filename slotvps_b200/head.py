@@ -289,7 +289,7 @@ class B200DynamicMaskHead(nn.Module):
         rnorm_ss = None
         if feat_bn is not None and all_tc:
             sc, sh = (f32c(v) for v in feat_bn)
-            rnorm_ss = torch.empty((T, shapes[-1][0] * shapes[-1][1]), dtype=torch.float32, device=dev)
+            rnorm_ss = torch.empty((4, T, shapes[-1][0] * shapes[-1][1]), dtype=torch.float32, device=dev)   # four 64-channel partial sums
             opts.feat_bn_scale, opts.feat_bn_shift, opts.rnorm_ss = sc.data_ptr(), sh.data_ptr(), rnorm_ss.data_ptr()
             keep_alive += [sc, sh]
         if stage_slots_in is not None:

@@ -31,9 +31,9 @@ def test_dropin_l2_matches_reference_simple_test():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     os.environ["SLOTVPS_REFERENCE_ROOT"] = REF
-    for m in [k for k in sys.modules if k == "oracle.ref_import"]:
-        del sys.modules[m]
-    from oracle import ref_import                      # checker-side plumbing: stubs for mmcv & co, imports baseline/_ref in place
+    import importlib
+    import oracle.ref_import as ref_import             # checker-side plumbing: stubs for mmcv & co, imports baseline/_ref in place
+    ref_import = importlib.reload(ref_import)          # (re-read SLOTVPS_REFERENCE_ROOT if an earlier test imported the module)
     import slotvps_b200 as sv
     from slotvps_b200 import synthetic
     from slotvps_b200.integration import patch_reference
