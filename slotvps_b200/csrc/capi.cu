@@ -15,6 +15,7 @@
 #include "fuse_tc.cuh"
 #include "mask_tc.cuh"
 #include "slot_tc.cuh"
+#include "slot_cl.cuh"
 #include "track.cuh"
 #include "unify.cuh"
 
@@ -168,6 +169,7 @@ struct HeadWs {
   float *rs_k, *rs_v, *Zpart, *a0part, *a1part, *Z, *a0, *a1, *Y, *p2, *hdn, *f, *f2;
   float *tqkv, *L, *av, *ty, *thdn, *tw, *c2, *e1;
   float *p2buf;                         // post-norm2 rows kept for the FFN residual (slot_post_kernel)
+  float *ffn_part;                      // [F/128][R][256] lin2 partials of the spread FFN (slot_ffn_kernel)
   float *pos[SLOTVPS_MAX_LEVELS];       // generated sine embeddings (pos_mode 2)
   float *ybuf;                          // coarse conv_trans partial [T][256][P/4]
   float *splitk;                        // split-K partials of the long-K linears [4][R][256]
@@ -206,6 +208,7 @@ static size_t head_ws_layout(const slotvps_head_desc* d, void* base, size_t cap,
   w.ty = a.take<float>((size_t)R * C); w.thdn = w.hdn;
   w.tw = a.take<float>((size_t)R * 2 * C); w.c2 = a.take<float>((size_t)R * C); w.e1 = a.take<float>((size_t)R * C);
   w.p2buf = a.take<float>((size_t)R * C);
+  w.ffn_part = a.take<float>((size_t)(d->dim_feedforward / 128 + 1) * R * C);
   for (int l = 0; l < SLOTVPS_MAX_LEVELS; ++l)
     w.pos[l] = (d->pos_mode == 2 && l < d->n_levels) ? a.take<float>((size_t)C * d->h[l] * d->w[l]) : nullptr;
   w.ybuf = a.take<float>((size_t)T * C * (Pmax / 4 + 1));
@@ -396,6 +399,8 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
                         const StagePix& px, const float* x, long x_bs, const float* pos, long pos_bs, int h, int wd, bool temporal,
                         float* cls_out, long cls_frame_stride, float* emb_out, long emb_frame_stride, cudaStream_t s) {
   const int T = d->n_frames, N = d->n_slots, R = T * N, P = h * wd, F = d->dim_feedforward;
+  // cluster form of the slot kernels (slot_cl.cuh): four CTAs per frame, 64 output columns each
+  static const int slot_cl_on = getenv("SLOTVPS_SLOT_CL") ? atoi(getenv("SLOTVPS_SLOT_CL")) : 1;
   // (1) slot self-attention core (:346-352): in_proj + 8-head attention on the generic kernels
   SV_TRY(linear_fast(w.slots, sp.in_proj_w, sp.in_proj_b, w.qkv, R, C, 3 * C, 0, nullptr, s));
   {
@@ -417,9 +422,18 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     pp.out_b = sp.out_proj_b; pp.n1_w = sp.norm1_w; pp.n1_b = sp.norm1_b; pp.q_b = sp.to_q_b;
     pp.nq_w = sp.nq_w; pp.nq_b = sp.nq_b; pp.nk_w = sp.nk_w; pp.nk_b = sp.nk_b; pp.bk_c = ps.bk_c;
     pp.p = w.p; pp.G = w.G; pp.g0 = w.g0; pp.g1 = w.g1; pp.gplanes = px.tc.gplanes;
-    SV_TRY(ensure_dyn_smem((const void*)slot::slot_pre_kernel, slot::SMEM_BYTES));
-    slot::slot_pre_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_out, m_q, m_wk, pp);
-    SV_CHECK_LAUNCH("slot_pre");
+    if (slot_cl_on) {
+      SV_TRY(slot::cl::slot_wmap64(&m_out, ps.stc.out_proj, C, C));
+      SV_TRY(slot::cl::slot_wmap64(&m_q, ps.stc.to_q, C, C));
+      SV_TRY(slot::cl::slot_wmap64(&m_wk, ps.stc.wkT, C, C));
+      SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_pre_cl, slot::cl::SMEM));
+      slot::cl::slot_pre_cl<<<T * slot::cl::CL, slot::THREADS, slot::cl::SMEM, s>>>(m_out, m_q, m_wk, pp);
+      SV_CHECK_LAUNCH("slot_pre");
+    } else {
+      SV_TRY(ensure_dyn_smem((const void*)slot::slot_pre_kernel, slot::SMEM_BYTES));
+      slot::slot_pre_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_out, m_q, m_wk, pp);
+      SV_CHECK_LAUNCH("slot_pre");
+    }
   }
   // (3) pixel side: Z, a0, a1
   SV_TRY(pixel_attention(x, x_bs, pos, pos_bs, ps, w, px, T, N, P, true, s, true));
@@ -436,6 +450,7 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     slot::PostParams q;
     memset(&q, 0, sizeof(q));
     q.N = N; q.F = F; q.act = ffn_act_of(d); q.ncls = d->num_classes;
+    q.dbg = getenv("SLOTVPS_SLOT_DEBUG") ? atoi(getenv("SLOTVPS_SLOT_DEBUG")) : 0;
     q.Z = w.Z; q.a0 = w.a0; q.a1 = w.a1; q.p = w.p;
     q.nv_w = sp.nv_w; q.nv_b = sp.nv_b; q.bv_c = ps.bv_c; q.no_w = sp.no_w; q.no_b = sp.no_b; q.n2_w = sp.norm2_w; q.n2_b = sp.norm2_b;
     q.b1 = sp.lin1_b; q.b2 = sp.lin2_b; q.n3_w = sp.norm3_w; q.n3_b = sp.norm3_b;
@@ -444,16 +459,57 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     q.logit_b = sp.logit_b;
     q.slots_out = w.slots; q.emb_out = emb_out; q.cls_out = cls_out; q.emb_fs = emb_frame_stride; q.cls_fs = cls_frame_stride;
     SV_TRY(ensure_dyn_smem((const void*)slot::slot_post_kernel, slot::SMEM_BYTES));
-    if (!temporal) {
+    static const int ffn_split = getenv("SLOTVPS_FFN_SPLIT") ? atoi(getenv("SLOTVPS_FFN_SPLIT")) : 1;
+    if (slot_cl_on) {
+      CUtensorMap c_wv, c_tw, c_c1, c_lg, c_r1;
+      SV_TRY(slot::cl::slot_wmap64(&c_wv, ps.stc.wv, C, C));
+      SV_TRY(slot::cl::slot_wmap64(&c_tw, ps.stc.tw, 2 * C, C));
+      SV_TRY(slot::cl::slot_wmap64(&c_c1, ps.stc.cls1, C, C));
+      SV_TRY(slot::cl::slot_wmap64(&c_r1, ps.stc.reg1, C, C));
+      SV_TRY(slot::cl::slot_wmap64(&c_lg, ps.stc.logit, d->num_classes, C));
+      SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_post_cl, slot::cl::SMEM));
+      slot::cl::slot_post_cl<<<T * slot::cl::CL, slot::THREADS, slot::cl::SMEM, s>>>(c_wv, q);
+      SV_CHECK_LAUNCH("slot_post");
+      slot::FfnParams fp;
+      fp.N = N; fp.act = q.act; fp.p2 = w.p2buf; fp.b1 = sp.lin1_b; fp.part = w.ffn_part; fp.part_stride = (long)R * C;
+      SV_TRY(ensure_dyn_smem((const void*)slot::slot_ffn_kernel, slot::SMEM_BYTES));
+      slot::slot_ffn_kernel<<<dim3(T, F / 128), slot::THREADS, slot::SMEM_BYTES, s>>>(m_l1, m_l2, fp, F);
+      SV_CHECK_LAUNCH("slot_ffn");
+      slot::slot_norm3_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.ffn_part, (long)R * C, F / 128, w.p2buf, sp.lin2_b, sp.norm3_w, sp.norm3_b, w.f, R);
+      SV_CHECK_LAUNCH("slot_norm3");
+      const float* fcur = w.f;
+      if (temporal) {
+        SV_TRY(video_retriever(d, sp, ps, w, s));
+        fcur = w.f2;
+      }
+      q.f_in = fcur;
+      SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_towers_cl, slot::cl::SMEM));
+      slot::cl::slot_towers_cl<<<T * slot::cl::CL, slot::THREADS, slot::cl::SMEM, s>>>(c_tw, c_c1, c_lg, c_r1, q);
+      SV_CHECK_LAUNCH("slot_towers");
+    } else if (!temporal && !ffn_split) {
       q.phases = 3;
       slot::slot_post_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg, q);
       SV_CHECK_LAUNCH("slot_post");
     } else {
-      q.phases = 1;
+      q.phases = 1; q.ffn_split = ffn_split;
       slot::slot_post_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg, q);
       SV_CHECK_LAUNCH("slot_post");
-      SV_TRY(video_retriever(d, sp, ps, w, s));
-      q.phases = 2; q.f_in = w.f2;
+      if (ffn_split) {
+        // FFN over (frame, hidden chunk) CTAs, then the chunk-ordered reduction + norm3
+        slot::FfnParams fp;
+        fp.N = N; fp.act = q.act; fp.p2 = w.p2buf; fp.b1 = sp.lin1_b; fp.part = w.ffn_part; fp.part_stride = (long)R * C;
+        SV_TRY(ensure_dyn_smem((const void*)slot::slot_ffn_kernel, slot::SMEM_BYTES));
+        slot::slot_ffn_kernel<<<dim3(T, F / 128), slot::THREADS, slot::SMEM_BYTES, s>>>(m_l1, m_l2, fp, F);
+        SV_CHECK_LAUNCH("slot_ffn");
+        slot::slot_norm3_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.ffn_part, (long)R * C, F / 128, w.p2buf, sp.lin2_b, sp.norm3_w, sp.norm3_b, w.f, R);
+        SV_CHECK_LAUNCH("slot_norm3");
+      }
+      const float* fcur = w.f;
+      if (temporal) {
+        SV_TRY(video_retriever(d, sp, ps, w, s));
+        fcur = w.f2;
+      }
+      q.phases = 2; q.f_in = fcur; q.ffn_split = 0;
       slot::slot_post_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg, q);
       SV_CHECK_LAUNCH("slot_post(towers)");
     }

@@ -1,0 +1,512 @@
+// Slot-update kernels, cluster form: the slot side of one retriever stage (dynamic_mask_head.py:342-400) with the
+// frame's N <= 104 slots resident in a CLUSTER of four CTAs instead of one (slot_tc.cuh).
+//
+// Why: a 256 -> 256 linear layer on the 3-product fp16 hi/lo scheme is 6 K tensor-pipe cycles and 256 KB of weights for
+// ONE SM, followed by a LayerNorm epilogue that cannot start before the last column is in; with seven such steps per
+// stage the frame-resident kernels were a 50-90 us latency chain per launch on 2 of 148 SMs.  Here every CTA of the
+// cluster owns 64 of the 256 output columns of every layer:
+//   * its weight slice of a layer is 64 KB = the whole 8-slot TMA ring, so the next layer's weights are in shared
+//     memory before the current epilogue ends (no refill round trips on the critical path);
+//   * the MMAs per layer drop to 48 x (M128 N64 K16) = 1.5 K cycles;
+//   * an epilogue thread owns ONE 16-column unit of its slot row, which stays in registers across the LayerNorm;
+//   * row statistics go CTA-local through shared memory, then across the cluster through distributed shared memory;
+//   * the normalised unit is written as fp16 hi/lo MMA operand into the ACT planes of ALL four CTAs
+//     (st.shared::cluster), so each CTA holds the full K = 256 operand of the next layer.
+// Cluster-wide synchronisation uses two alternating mbarriers per CTA (64 arrivals: one elected lane per epilogue warp of
+// every CTA, release.cluster / acquire.cluster) because the TMA and MMA warps cannot take part in barrier.cluster.
+//
+//   slot_pre_cl     out_proj + residual + norm1 -> to_q + norm_q -> G = (q * gamma_k) Wk_c, g0, g1, fp16 planes of G
+//   slot_post_cl    Wv_c Z, norm_v / norm1 / ReLU, residual, norm2 -> p2      (the FFN runs in slot_ffn_kernel)
+//   slot_towers_cl  cls0 | reg0 -> LN/ReLU -> cls1 -> LN/ReLU -> logits ; reg0 -> LN/ReLU -> reg1 -> LN/ReLU -> next slots
+#pragma once
+#include "slot_tc.cuh"
+
+namespace slotvps {
+namespace slot {
+namespace cl {
+constexpr int CL = 4;                          // CTAs per frame
+constexpr int NCOL = C / CL;                   // 64 output columns per CTA
+constexpr int WT = NCOL * 128;                 // 8 KB weight tile [64 out][64 k] fp16, one plane
+constexpr int NSL = 8;                         // ring slots = one layer slice (4 k-subtiles x hi/lo)
+constexpr int OFF_RING = ACT_BYTES;
+constexpr int OFF_STG = OFF_RING + NSL * WT;   // 16 per-warp staging tiles [32][20] floats
+constexpr int OFF_RED = OFF_STG + EPI_WARPS * 2560;      // CTA-local partial sums [2][4][128] float2
+constexpr int OFF_XCH = OFF_RED + 8192;        // cluster partial sums [2][4 ranks][128] float2
+constexpr int OFF_BAR = OFF_XCH + 8192;
+constexpr int SMEM = OFF_BAR + 1024 + 1024;
+constexpr uint32_t IDESC64 = tc::make_idesc_f16(128, 64, 0, 0);
+static_assert(SMEM <= 232448, "shared memory budget");
+static_assert(OFF_RING % 1024 == 0 && WT % 1024 == 0, "swizzle atoms");
+
+struct Bars {
+  uint64_t full[NSL], empty[NSL];
+  uint64_t dfull, aready;
+  uint64_t xbar[2];                             // cluster rendezvous of the epilogue warps
+  uint32_t tmem_ptr;
+};
+
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cl_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void st_cl_v2f(uint32_t a, float x, float y) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITC_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAITC_DONE;\n\t"
+      "bra WAITC_LOOP;\n\t"
+      "WAITC_DONE:\n\t"
+      "}" ::"r"(tc::smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// ---- TMA producer / MMA issuer: one 64-column slice of a layer -----------------------------------------------------
+__device__ __forceinline__ void prod_slice(uint8_t* smem, Bars* b, uint32_t& it, const CUtensorMap* m, int hi_row, int lo_row) {
+#pragma unroll 1
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll 1
+    for (int pl = 0; pl < 2; ++pl) {
+      const int s = it % NSL;
+      tc::mbar_wait(&b->empty[s], ((it / NSL) & 1) ^ 1);
+      tc::mbar_expect_tx(&b->full[s], WT);
+      tc::tma_load_2d(smem + OFF_RING + s * WT, m, ks * 64, pl ? lo_row : hi_row, &b->full[s]);
+      ++it;
+    }
+}
+__device__ __forceinline__ void mma_slice(uint8_t* smem, Bars* b, uint32_t& it, uint32_t d_tmem, uint32_t act, uint32_t idesc) {
+#pragma unroll 1
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint64_t dah = tc::make_smem_desc_sw128(act + ks * ACT_SUB, 16, 1024);
+    const uint64_t dal = tc::make_smem_desc_sw128(act + ACT_PLANE + ks * ACT_SUB, 16, 1024);
+    {
+      const int s = it % NSL;
+      tc::mbar_wait(&b->full[s], (it / NSL) & 1);
+      tc::tc_fence_after();
+      const uint64_t dbh = tc::make_smem_desc_sw128(tc::smem_u32(smem + OFF_RING + s * WT), 16, 1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        tc::umma_bf16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (ks != 0 || k != 0) ? 1u : 0u);
+        tc::umma_bf16(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);
+      }
+      tc::umma_commit(&b->empty[s]);
+      ++it;
+    }
+    {
+      const int s = it % NSL;
+      tc::mbar_wait(&b->full[s], (it / NSL) & 1);
+      tc::tc_fence_after();
+      const uint64_t dbl = tc::make_smem_desc_sw128(tc::smem_u32(smem + OFF_RING + s * WT), 16, 1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tc::umma_bf16(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+      tc::umma_commit(&b->empty[s]);
+      ++it;
+    }
+  }
+}
+
+// ---- epilogue context --------------------------------------------------------------------------------------------
+// 16 warps; warp e serves TMEM lane quadrant (e & 3) -- slot row 32 (e & 3) + lane -- and the 16-column unit (e >> 2) of the
+// CTA's 64 columns, i.e. unit u = 4 rank + (e >> 2) of the layer's 256.
+struct Ctx {
+  Bars* b;
+  Epi e;                                        // row / lane bookkeeping and the staging tile (read_rows / write_rows)
+  int u;                                        // this thread's unit of the 256 columns
+  uint32_t rank, nred, nx, nsync, nd;
+  float2 *red, *xch;
+  uint32_t act_r[CL], xch_r[CL];                // shared::cluster addresses of every CTA's ACT / XCH base
+  // rendezvous of all epilogue warps of the cluster; also orders this CTA's earlier st.shared::cluster before the peers' reads
+  __device__ __forceinline__ void xsync() {
+    __syncwarp();
+    uint64_t* bar = &b->xbar[nsync & 1];
+    if (e.lane == 0) {
+#pragma unroll
+      for (uint32_t d = 0; d < CL; ++d) tc::mbar_arrive_remote(bar, d);
+    }
+    mbar_wait_cl(bar, (nsync >> 1) & 1);
+    ++nsync;
+  }
+  __device__ __forceinline__ void wait_d() { tc::mbar_wait(&b->dfull, nd & 1); ++nd; tc::tc_fence_after(); }
+  __device__ __forceinline__ void publish() { tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->aready); }
+  // accumulator columns [col0 + 16 qt, +16) of this thread's row, unscaled by the weight scale
+  __device__ __forceinline__ void ld(int col0, float* v) const {
+    tc::tmem_ld16(e.tbase + col0 + 16 * e.qt, v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] *= WSCALE_INV;
+  }
+  // (sum, sum of squares) over this thread's 16 columns -> over the row's 256 columns of the four CTAs
+  __device__ __forceinline__ void row_total(float a, float q, float& ta, float& tq) {
+    float2* rb = red + (nred & 1) * 512;
+    ++nred;
+    rb[e.qt * 128 + e.r] = make_float2(a, q);
+    e.sync();
+    const uint32_t slot = (nx & 1) * 512;
+    ++nx;
+    if (e.qt == 0) {
+      const float2 p0 = rb[e.r], p1 = rb[128 + e.r], p2 = rb[256 + e.r], p3 = rb[384 + e.r];
+      const float s1 = (p0.x + p1.x) + (p2.x + p3.x), s2 = (p0.y + p1.y) + (p2.y + p3.y);
+      const uint32_t off = (slot + rank * 128 + e.r) * 8;
+#pragma unroll
+      for (int d = 0; d < CL; ++d) st_cl_v2f(xch_r[d] + off, s1, s2);
+    }
+    xsync();
+    const float2* xb = xch + slot;
+    const float2 x0 = xb[e.r], x1 = xb[128 + e.r], x2 = xb[256 + e.r], x3 = xb[384 + e.r];
+    ta = (x0.x + x1.x) + (x2.x + x3.x);
+    tq = (x0.y + x1.y) + (x2.y + x3.y);
+  }
+  // LayerNorm of the row whose unit is v (single-pass variance as in slot_tc.cuh), optional ReLU
+  __device__ __forceinline__ void layer_norm(float* v, const float* __restrict__ gw, const float* __restrict__ gb, bool relu) {
+    float sp = 0.f, qp = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { sp += v[c]; qp = fmaf(v[c], v[c], qp); }
+    float s1, s2;
+    row_total(sp, qp, s1, s2);
+    const float mean = s1 * (1.f / C);
+    const float rstd = rsqrtf(fmaxf(s2 * (1.f / C) - mean * mean, 0.f) + LN_EPS);
+    float w[16], bb[16];
+    ldg16(gw + 16 * u, w); ldg16(gb + 16 * u, bb);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      v[c] = (v[c] - mean) * rstd * w[c] + bb[c];
+      if (relu) v[c] = fmaxf(v[c], 0.f);
+    }
+  }
+  // unit -> fp16 hi/lo operand planes of every CTA of the cluster
+  __device__ __forceinline__ void to_act_all(const float* v) const {
+    if (!e.valid) return;
+    const uint32_t off = (u >> 2) * ACT_SUB + e.r * 128;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split2(v[8 * q + 2 * k], v[8 * q + 2 * k + 1], hi[k], lo[k]);
+      const uint32_t phys = off + ((((u & 3) * 2 + q) ^ (e.r & 7))) * 16;
+#pragma unroll
+      for (int d = 0; d < CL; ++d) {
+        st_cl_v4(act_r[d] + phys, hi[0], hi[1], hi[2], hi[3]);
+        st_cl_v4(act_r[d] + ACT_PLANE + phys, lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+  // operand written everywhere -> every CTA's MMA issuer may go
+  __device__ __forceinline__ void publish_all() { xsync(); publish(); }
+};
+
+__device__ __forceinline__ Ctx make_ctx(uint8_t* smem, Bars* b, uint32_t tmem_base, uint32_t rank, int N) {
+  Ctx c;
+  const int we = (threadIdx.x >> 5) - 2;
+  c.b = b; c.rank = rank; c.nred = 0; c.nx = 0; c.nsync = 0; c.nd = 0;
+  c.e.lane = threadIdx.x & 31; c.e.q = (threadIdx.x >> 5) & 3; c.e.qt = we >> 2; c.e.r = c.e.q * 32 + c.e.lane; c.e.N = N;
+  c.e.valid = c.e.r < N;
+  c.e.tbase = tmem_base + ((uint32_t)(c.e.q * 32) << 16);
+  c.e.stg = reinterpret_cast<float*>(smem + OFF_STG) + we * 640;
+  c.e.red = nullptr; c.e.nred = 0;
+  c.u = (int)rank * 4 + c.e.qt;
+  c.red = reinterpret_cast<float2*>(smem + OFF_RED);
+  c.xch = reinterpret_cast<float2*>(smem + OFF_XCH);
+#pragma unroll
+  for (uint32_t d = 0; d < CL; ++d) {
+    c.act_r[d] = mapa(tc::smem_u32(smem + OFF_ACT), d);
+    c.xch_r[d] = mapa(tc::smem_u32(smem + OFF_XCH), d);
+  }
+  return c;
+}
+
+// barriers, TMEM, cluster rendezvous; returns the TMEM base
+__device__ __forceinline__ uint32_t prologue(Bars* b, int warp, uint32_t tmem_cols) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSL; ++i) { tc::mbar_init(&b->full[i], 1); tc::mbar_init(&b->empty[i], 1); }
+    tc::mbar_init(&b->dfull, 1); tc::mbar_init(&b->aready, EPI_THREADS);
+    tc::mbar_init(&b->xbar[0], EPI_WARPS * CL); tc::mbar_init(&b->xbar[1], EPI_WARPS * CL);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) { tc::tmem_alloc(&b->tmem_ptr, tmem_cols); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();                                               // every CTA's barriers exist before a peer targets them
+  tc::tc_fence_after();
+  return b->tmem_ptr;
+}
+__device__ __forceinline__ void epilogue_exit(uint32_t tmem_base, int warp, uint32_t tmem_cols) {
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync();                                               // no CTA leaves while a peer may still write to it
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// =====================================================================================================================
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ CUtensorMap m_q, const __grid_constant__ CUtensorMap m_wk,
+            const PreParams P) {
+  extern __shared__ uint8_t raw_smem[];
+  const uint32_t raw = tc::smem_u32(raw_smem);
+  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
+  Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x / CL, N = P.N;
+  const uint32_t rank = tc::cluster_ctarank();
+  if (threadIdx.x == 0) { tc::tma_prefetch_desc(&m_out); tc::tma_prefetch_desc(&m_q); tc::tma_prefetch_desc(&m_wk); }
+  const uint32_t tmem_base = prologue(b, warp, 64);
+  const int hi_row = (int)rank * NCOL, lo_row = C + (int)rank * NCOL;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      prod_slice(smem, b, it, &m_out, hi_row, lo_row);
+      prod_slice(smem, b, it, &m_q, hi_row, lo_row);
+      prod_slice(smem, b, it, &m_wk, hi_row, lo_row);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint32_t act = tc::smem_u32(smem + OFF_ACT);
+      for (int g = 0; g < 3; ++g) {
+        tc::mbar_wait(&b->aready, g & 1);
+        tc::tc_fence_after();
+        mma_slice(smem, b, it, tmem_base, act, IDESC64);
+        tc::umma_commit(&b->dfull);
+      }
+    }
+  } else {
+    Ctx c = make_ctx(smem, b, tmem_base, rank, N);
+    Epi& e = c.e;
+    const int u = c.u;
+    const long fbase = (long)t * N * C;
+    // A operand of the first GEMM: the self-attention output rows (every CTA builds the full K = 256 operand)
+    load_rows_to_act(smem, P.mo + fbase, N, warp - 2, lane);
+    c.publish();
+    float v[16], add[16];
+    // ---- (1) out_proj + residual + norm1 -> p ----
+    {
+      float bb[16];
+      e.read_rows(P.slots + fbase, u, add);
+      ldg16(P.out_b + 16 * u, bb);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) add[k] += bb[k];
+      prefetch_l1(P.n1_w + 16 * u); prefetch_l1(P.n1_b + 16 * u);
+    }
+    c.wait_d();
+    c.ld(0, v);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] += add[k];
+    c.layer_norm(v, P.n1_w, P.n1_b, false);
+    c.to_act_all(v);
+    e.write_rows(P.p + fbase, u, v);
+    ldg16(P.q_b + 16 * u, add);
+    prefetch_l1(P.nq_w + 16 * u); prefetch_l1(P.nq_b + 16 * u);
+    prefetch_l1(P.nk_w + 16 * u); prefetch_l1(P.nk_b + 16 * u); prefetch_l1(P.bk_c + 16 * u);
+    c.publish_all();
+    // ---- (2) to_q + norm_q -> q; qt = q * gamma_k; g0 = qt . bk_c; g1 = q . beta_k ----
+    c.wait_d();
+    c.ld(0, v);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] += add[k];
+    c.layer_norm(v, P.nq_w, P.nq_b, false);
+    float s0 = 0.f, s1 = 0.f;
+    {
+      float gk[16], bk[16], bc[16];
+      ldg16(P.nk_w + 16 * u, gk); ldg16(P.nk_b + 16 * u, bk); ldg16(P.bk_c + 16 * u, bc);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float qv = v[k], tv = qv * gk[k];
+        s0 = fmaf(tv, bc[k], s0);
+        s1 = fmaf(qv, bk[k], s1);
+        v[k] = tv;
+      }
+    }
+    c.to_act_all(v);
+    c.row_total(s0, s1, s0, s1);                                   // (its rendezvous also covers the operand stores above)
+    if (e.valid && e.qt == 0 && rank == 0) { P.g0[(long)t * N + e.r] = s0; P.g1[(long)t * N + e.r] = s1; }
+    c.publish();
+    // ---- (3) G = qt . Wk_c -> fp32 + fp16 hi/lo planes (the B operand of attn_tc's S product) ----
+    c.wait_d();
+    c.ld(0, v);
+    if (P.G) e.write_rows(P.G + fbase, u, v);
+    {
+      uint32_t* stw = reinterpret_cast<uint32_t*>(e.stg);           // staging as [2 planes][32 rows][10 words] (8 used)
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        hi[k] = 0u; lo[k] = 0u;
+        if (e.valid) split2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        *reinterpret_cast<uint2*>(stw + lane * 10 + k) = make_uint2(hi[k], hi[k + 1]);
+        *reinterpret_cast<uint2*>(stw + 320 + lane * 10 + k) = make_uint2(lo[k], lo[k + 1]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {                            // a row's 16 columns = 32 bytes = 4 lanes x 8 bytes; 8 rows per request
+          const int row = it * 8 + (lane >> 2), gr = e.q * 32 + row, part = lane & 3;
+          if (gr < NR) {
+            const uint2 w2 = *reinterpret_cast<const uint2*>(stw + pl * 320 + row * 10 + part * 2);
+            __half* dst = P.gplanes + (((long)t * 2 + pl) * NR + gr) * C + 16 * u + part * 4;
+            *reinterpret_cast<uint2*>(dst) = w2;
+          }
+        }
+      __syncwarp();
+    }
+  }
+  epilogue_exit(tmem_base, warp, 64);
+}
+
+// =====================================================================================================================
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+slot_post_cl(const __grid_constant__ CUtensorMap m_wv, const PostParams P) {
+  extern __shared__ uint8_t raw_smem[];
+  const uint32_t raw = tc::smem_u32(raw_smem);
+  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
+  Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x / CL, N = P.N;
+  const uint32_t rank = tc::cluster_ctarank();
+  if (threadIdx.x == 0) tc::tma_prefetch_desc(&m_wv);
+  const uint32_t tmem_base = prologue(b, warp, 64);
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      prod_slice(smem, b, it, &m_wv, (int)rank * NCOL, C + (int)rank * NCOL);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      tc::mbar_wait(&b->aready, 0);
+      tc::tc_fence_after();
+      mma_slice(smem, b, it, tmem_base, tc::smem_u32(smem + OFF_ACT), IDESC64);       // Y = Z . Wv_c^T
+      tc::umma_commit(&b->dfull);
+    }
+  } else {
+    Ctx c = make_ctx(smem, b, tmem_base, rank, N);
+    Epi& e = c.e;
+    const int u = c.u;
+    const long fbase = (long)t * N * C;
+    load_rows_to_act(smem, P.Z + fbase, N, warp - 2, lane);
+    c.publish();
+    // ---- value projection of the pixel-reduced slots, norm_v / norm1 / ReLU, residual, norm2 (:456-459, 374-376) ----
+    float v[16], pp[16];
+    e.read_rows(P.p + fbase, u, pp);
+    const float a0r = e.valid ? P.a0[(long)t * N + e.r] : 0.f, a1r = e.valid ? P.a1[(long)t * N + e.r] : 0.f;
+    prefetch_l1(P.nv_w + 16 * u); prefetch_l1(P.nv_b + 16 * u); prefetch_l1(P.bv_c + 16 * u);
+    prefetch_l1(P.no_w + 16 * u); prefetch_l1(P.no_b + 16 * u); prefetch_l1(P.n2_w + 16 * u); prefetch_l1(P.n2_b + 16 * u);
+    c.wait_d();
+    c.ld(0, v);
+    {
+      float gv[16], bv[16], bc[16];
+      ldg16(P.nv_w + 16 * u, gv); ldg16(P.nv_b + 16 * u, bv); ldg16(P.bv_c + 16 * u, bc);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = gv[k] * fmaf(bc[k], a1r, v[k]) + bv[k] * a0r;
+    }
+    c.layer_norm(v, P.no_w, P.no_b, true);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] += pp[k];
+    c.layer_norm(v, P.n2_w, P.n2_b, false);
+    e.write_rows(P.p2buf + fbase, u, v);
+  }
+  epilogue_exit(tmem_base, warp, 64);
+}
+
+// =====================================================================================================================
+// towers (:390-400).  Accumulator columns [0, 64) = cls chain, [64, 128) = first reg layer (kept until the cls chain is done).
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__ CUtensorMap m_c1, const __grid_constant__ CUtensorMap m_lg,
+               const __grid_constant__ CUtensorMap m_r1, const PostParams P) {
+  extern __shared__ uint8_t raw_smem[];
+  const uint32_t raw = tc::smem_u32(raw_smem);
+  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
+  Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x / CL, N = P.N;
+  const uint32_t rank = tc::cluster_ctarank();
+  if (threadIdx.x == 0) { tc::tma_prefetch_desc(&m_tw); tc::tma_prefetch_desc(&m_c1); tc::tma_prefetch_desc(&m_lg); tc::tma_prefetch_desc(&m_r1); }
+  const uint32_t tmem_base = prologue(b, warp, 128);
+  const int hi_row = (int)rank * NCOL, lo_row = C + (int)rank * NCOL;
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      prod_slice(smem, b, it, &m_tw, hi_row, 2 * C + hi_row);                     // cls0 slice  (planes [2][512][256])
+      prod_slice(smem, b, it, &m_tw, C + hi_row, 3 * C + hi_row);                 // reg0 slice
+      prod_slice(smem, b, it, &m_c1, hi_row, lo_row);
+      prod_slice(smem, b, it, &m_lg, 0, TILE_N);                                  // class logits: 32 padded rows used of the 64-row box
+      prod_slice(smem, b, it, &m_r1, hi_row, lo_row);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, na = 0;
+      const uint32_t act = tc::smem_u32(smem + OFF_ACT);
+      auto wait_act = [&]() { tc::mbar_wait(&b->aready, na & 1); ++na; tc::tc_fence_after(); };
+      wait_act();
+      mma_slice(smem, b, it, tmem_base, act, IDESC64);                            // cls0
+      mma_slice(smem, b, it, tmem_base + 64, act, IDESC64);                       // reg0
+      tc::umma_commit(&b->dfull);
+      wait_act();
+      mma_slice(smem, b, it, tmem_base, act, IDESC64);                            // cls1
+      tc::umma_commit(&b->dfull);
+      wait_act();
+      mma_slice(smem, b, it, tmem_base, act, IDESC32);                            // class logits (every CTA; rank 0 stores)
+      tc::umma_commit(&b->dfull);
+      wait_act();
+      mma_slice(smem, b, it, tmem_base, act, IDESC64);                            // reg1
+      tc::umma_commit(&b->dfull);
+    }
+  } else {
+    Ctx c = make_ctx(smem, b, tmem_base, rank, N);
+    Epi& e = c.e;
+    const int u = c.u;
+    const long fbase = (long)t * N * C;
+    load_rows_to_act(smem, P.f_in + fbase, N, warp - 2, lane);
+    c.publish();
+    prefetch_l1(P.tw_ln_w + 16 * u); prefetch_l1(P.tw_ln_b + 16 * u); prefetch_l1(P.tw_ln_w + C + 16 * u); prefetch_l1(P.tw_ln_b + C + 16 * u);
+    prefetch_l1(P.c1_nw + 16 * u); prefetch_l1(P.c1_nb + 16 * u); prefetch_l1(P.r1_nw + 16 * u); prefetch_l1(P.r1_nb + 16 * u);
+    float v[16];
+    c.wait_d();
+    c.ld(0, v);
+    c.layer_norm(v, P.tw_ln_w, P.tw_ln_b, true);                    // c1
+    c.to_act_all(v);
+    c.publish_all();
+    c.wait_d();
+    c.ld(0, v);
+    c.layer_norm(v, P.c1_nw, P.c1_nb, true);                        // c2
+    c.to_act_all(v);
+    c.publish_all();
+    c.wait_d();
+    if (rank == 0 && e.qt == 0) {
+      float lg[2][16];
+      tc::tmem_ld16(e.tbase, lg[0]); tc::tmem_ld16(e.tbase + 16, lg[1]);
+      tc::tmem_ld_wait();
+      if (e.valid) {
+        float* dst = P.cls_out + (long)t * P.cls_fs + (long)e.r * P.ncls;
+        for (int k = 0; k < P.ncls; ++k) dst[k] = lg[k >> 4][k & 15] * WSCALE_INV + __ldg(P.logit_b + k);
+      }
+    }
+    c.ld(64, v);                                                    // first reg layer, parked since the first GEMM
+    c.layer_norm(v, P.tw_ln_w + C, P.tw_ln_b + C, true);            // e1
+    c.to_act_all(v);
+    c.publish_all();
+    c.wait_d();
+    c.ld(0, v);
+    c.layer_norm(v, P.r1_nw, P.r1_nb, true);                        // next-stage slots = this stage's embedding
+    e.write_rows(P.slots_out + fbase, u, v, P.emb_out + (long)t * P.emb_fs);
+  }
+  epilogue_exit(tmem_base, warp, 128);
+}
+
+// tensor map over [2 * Opad][K] fp16 planes, box [64][64]
+inline int slot_wmap64(CUtensorMap* m, const __half* planes, int O, int K) {
+  const int Opad = ceil_div(O, slot::TILE_N) * slot::TILE_N;
+  return tc::make_tmap_h16_sw128(m, planes, (uint64_t)2 * Opad, (uint64_t)K, NCOL);
+}
+
+}  // namespace cl
+}  // namespace slot
+}  // namespace slotvps

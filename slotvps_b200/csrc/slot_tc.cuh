@@ -355,8 +355,12 @@ slot_pre_kernel(const __grid_constant__ CUtensorMap m_out, const __grid_constant
     const long fbase = (long)t * N * C;
     auto publish_act = [&]() { tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->aready); };
     auto to_act = [&](int u, float* v) { if (valid) store_operand16(smem + OFF_ACT, ACT_PLANE, r, u, v); };
+#ifdef SLOTVPS_SLOT_PROFILE
     long long tk[8]; int nk = 0;
     auto mark = [&]() { if (P.dbg && nk < 8) tk[nk++] = clock64(); };
+#else
+    auto mark = []() {};
+#endif
     mark();
     // A operand of the first GEMM: the self-attention output rows
     load_rows_to_act(smem, P.mo + fbase, N, warp - 2, lane);
@@ -438,9 +442,11 @@ slot_pre_kernel(const __grid_constant__ CUtensorMap m_out, const __grid_constant
       __syncwarp();
     }
     mark();
+#ifdef SLOTVPS_SLOT_PROFILE
     if (P.dbg && t == 0 && threadIdx.x == 64)
       printf("slot_pre cycles: load %lld | gemm1 wait %lld | epi1 %lld | gemm2 wait %lld | epi2 %lld | gemm3 wait %lld | epi3 %lld\n", tk[1] - tk[0],
              tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[7] - tk[6]);
+#endif
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -454,6 +460,7 @@ struct PostParams {
   const float *Z, *a0, *a1, *p;
   const float *nv_w, *nv_b, *bv_c, *no_w, *no_b, *n2_w, *n2_b, *b1, *b2, *n3_w, *n3_b;
   float *p2buf, *f_out;                         // [T][N][256] scratch (post-norm2 rows), FFN block output
+  int ffn_split;                                // 1: stop after norm2 (p2buf); the FFN runs in slot_ffn_kernel / slot_norm3_kernel
   // towers
   const float* f_in;                            // [T][N][256] tower input when phase 0 did not just produce it in shared memory
   const float *tw_ln_w, *tw_ln_b, *c1_nw, *c1_nb, *r1_nw, *r1_nb, *logit_b;
@@ -461,7 +468,23 @@ struct PostParams {
   long emb_fs, cls_fs;                          // frame strides of emb_out / cls_out
 };
 
-__device__ __forceinline__ float act_fn(float x, int act) { return act == 1 ? fmaxf(x, 0.f) : gelu_erf(x); }
+// Exact (erf) GELU through the complementary error function: gelu(x) = x/2 * erfc(-x/sqrt(2)), with erfc(z >= 0) from the
+// Chebyshev fit t * exp(-z^2 + P9(t)), t = 1 / (1 + z/2) (fractional error < 1.2e-7 everywhere; W. H. Press et al.).  Against
+// fp64 this is 6.1e-7 absolute / 1.7e-6 relative -- tighter than the fp32 form 0.5 x (1 + erf(x / sqrt 2)) the reference
+// evaluates (6.7e-7 / 5.4e-5, cancellation for x < 0) -- at ~1/3 of erff's instructions: the 2048-wide hidden activation is
+// the largest single item of the slot update (measured 100 K of 176 K FFN cycles per stage with erff).
+__device__ __forceinline__ float gelu_erfc(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.5f, z, 1.f)));
+  float p = 0.17087277f;
+  p = fmaf(p, t, -0.82215223f); p = fmaf(p, t, 1.48851587f); p = fmaf(p, t, -1.13520398f); p = fmaf(p, t, 0.27886807f);
+  p = fmaf(p, t, -0.18628806f); p = fmaf(p, t, 0.09678418f); p = fmaf(p, t, 0.37409196f); p = fmaf(p, t, 1.00002368f);
+  p = fmaf(p, t, -1.26551223f);
+  const float e = t * __expf(fmaf(-z, z, p));             // erfc(|x| / sqrt 2)
+  return 0.5f * x * (x >= 0.f ? 2.f - e : e);
+}
+__device__ __forceinline__ float act_fn(float x, int act) { return act == 1 ? fmaxf(x, 0.f) : gelu_erfc(x); }
 
 __global__ void __launch_bounds__(THREADS, 1)
 slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant__ CUtensorMap m_l1, const __grid_constant__ CUtensorMap m_l2,
@@ -496,11 +519,13 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
       Ring rg;
       if (ph0) {
         prefetch_gemm(&m_wv, C, 0, 2, 0, 4);
-        prefetch_gemm(&m_l1, F_pad, 0, 2, 0, 4);
-        prefetch_gemm(&m_l2, C, 0, 2, 0, 4);
+        if (!P.ffn_split) {
+          prefetch_gemm(&m_l1, F_pad, 0, 2, 0, 4);
+          prefetch_gemm(&m_l2, C, 0, 2, 0, 4);
+        }
         prod_gemm(smem, b, rg, &m_wv, C, 0, 2, 0, 4);
-        prod_gemm(smem, b, rg, &m_l1, F_pad, 0, 1, 0, 4);
-        for (int c = 0; c < NC; ++c) {
+        if (!P.ffn_split) prod_gemm(smem, b, rg, &m_l1, F_pad, 0, 1, 0, 4);
+        for (int c = 0; c < NC && !P.ffn_split; ++c) {
           if (c + 2 < NC) { prefetch_gemm(&m_l1, F_pad, c + 2, 1, 0, 4); prefetch_gemm(&m_l2, C, 0, 2, 2 * (c + 2), 2); }   // two chunks ahead
           else if (ph1 && c + 2 == NC) { prefetch_gemm(&m_tw, 2 * C, 0, 4, 0, 4); prefetch_gemm(&m_c1, C, 0, 2, 0, 4); }
           if (c + 1 < NC) prod_gemm(smem, b, rg, &m_l1, F_pad, c + 1, 1, 0, 4);
@@ -527,6 +552,7 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
         wait_act();                                               // Z rows are in ACT
         mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D, 2, IDESC128, false);      // Y = Z . Wv_c^T
         tc::umma_commit(&b->dfull);
+        if (!P.ffn_split) {
         wait_act();                                               // p2 rows are in ACT, D is drained
         mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D1, 1, IDESC128, false);     // hidden chunk 0
         tc::umma_commit(&b->d1full[0]);
@@ -543,6 +569,7 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
           tc::umma_commit(&b->hfree);
         }
         tc::umma_commit(&b->dfull);
+        }
       }
       if (ph1) {
         wait_act();                                               // tower input rows in ACT (D drained)
@@ -569,11 +596,22 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
     auto wait_d = [&]() { tc::mbar_wait(&b->dfull, nd & 1); ++nd; tc::tc_fence_after(); };
     auto publish_act = [&]() { tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->aready); };
     auto to_act = [&](int u, float* v) { if (valid) store_operand16(smem + OFF_ACT, ACT_PLANE, r, u, v); };
+#ifdef SLOTVPS_SLOT_PROFILE
+    long long tk[16]; int nk = 0; long long w_d1 = 0, w_h = 0, c_ffn = 0;
+    auto mark = [&]() { if (P.dbg && nk < 16) tk[nk++] = clock64(); };
+#define SLOT_PROF(x) x
+#else
+    auto mark = []() {};
+#define SLOT_PROF(x)
+#endif
+    mark();
     if (ph0) {
       load_rows_to_act(smem, P.Z + fbase, N, warp - 2, lane);
       publish_act();
+      mark();
       // ---- value projection of the pixel-reduced slots, norm_v / norm1 / ReLU, residual, norm2 (:456-459, 374-376) ----
       wait_d();
+      mark();
       const float a0r = valid ? P.a0[(long)t * N + r] : 0.f, a1r = valid ? P.a1[(long)t * N + r] : 0.f;
       e.ln_tmem(TM_D, true, [&](int u, float* v) {
         float gv[16], bv[16], bc[16];
@@ -587,14 +625,18 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
         e.read_rows(P.p + fbase, u, pp);
 #pragma unroll
         for (int c = 0; c < 16; ++c) v[c] += pp[c];
-      }, P.n2_w, P.n2_b, false, [&](int u, float* v) { e.write_rows(P.p2buf + fbase, u, v); to_act(u, v); });
+      }, P.n2_w, P.n2_b, false, [&](int u, float* v) { e.write_rows(P.p2buf + fbase, u, v); if (!P.ffn_split) to_act(u, v); });
+      if (!P.ffn_split) {
       e.sync();                                                   // every warp is done with the staging tiles (they alias HB)
       publish_act();
+      mark();
       // ---- FFN: hidden chunks of 128 (:379-382); a thread owns 32 of the chunk's columns ----
       for (int c = 0; c < NC; ++c) {
         const int bf = c & 1;
+        SLOT_PROF(long long t0 = P.dbg ? clock64() : 0;)
         tc::mbar_wait(&b->d1full[bf], (c >> 1) & 1);
         tc::tc_fence_after();
+        SLOT_PROF(long long t1 = P.dbg ? clock64() : 0; w_d1 += t1 - t0;)
         float h[2][16];
 #pragma unroll
         for (int uu = 0; uu < 2; ++uu) tc::tmem_ld16(e.tbase + TM_D1 + bf * 128 + 16 * (qt * 2 + uu), h[uu]);
@@ -608,7 +650,9 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
 #pragma unroll
           for (int k = 0; k < 16; ++k) h[uu][k] = act_fn(fmaf(h[uu][k], WSCALE_INV, bb[k]), P.act);
         }
+        SLOT_PROF(long long t2 = P.dbg ? clock64() : 0; c_ffn += t2 - t1;)
         if (c > 0) tc::mbar_wait(&b->hfree, (c - 1) & 1);         // the MMAs of chunk c-1 have finished reading HB
+        SLOT_PROF(if (P.dbg) w_h += clock64() - t2;)
         if (valid) {
 #pragma unroll
           for (int uu = 0; uu < 2; ++uu) store_operand16(smem + OFF_HB, HB_PLANE, r, qt * 2 + uu, h[uu]);
@@ -617,7 +661,9 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
         tc::mbar_arrive(&b->hfull);
       }
       // ---- linear2 bias + residual + norm3 -> f ----
+      mark();
       wait_d();                                                   // all lin2 MMAs retired: HB is free for the staging tiles again
+      mark();
       e.ln_tmem(TM_D, true, [&](int u, float* v) {
         float bb[16], pp[16];
         e.read_rows(P.p2buf + fbase, u, pp, true);
@@ -626,6 +672,13 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
         for (int c = 0; c < 16; ++c) v[c] = v[c] + bb[c] + pp[c];
       }, P.n3_w, P.n3_b, false, [&](int u, float* v) { e.write_rows(P.f_out + fbase, u, v); if (ph1) to_act(u, v); });
       if (ph1) publish_act();
+      mark();
+#ifdef SLOTVPS_SLOT_PROFILE
+      if (P.dbg && t == 0 && threadIdx.x == 64)
+        printf("slot_post cycles: load %lld | Y wait %lld | epi(attn) %lld | FFN total %lld (wait lin1 %lld, act+split %lld, wait HB free %lld) | lin2 tail %lld | epi(norm3) %lld\n",
+               tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], w_d1, c_ffn, w_h, tk[5] - tk[4], tk[6] - tk[5]);
+#endif
+      }
     } else if (ph1) {
       load_rows_to_act(smem, P.f_in + fbase, N, warp - 2, lane);
       publish_act();
@@ -657,6 +710,132 @@ slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+// ---- FFN of one stage spread over the GPU (:379-385) ---------------------------------------------------------------------
+// One CTA per (frame, 128-wide hidden chunk): the 2 x 3-product GEMMs of the FFN are 100 K tensor-pipe cycles on a single SM
+// (M = 128 x 256 x 2048 x 2 x 3) and the activation another ~60 K issue cycles, so the frame-resident kernel spent 3/4 of a
+// stage here.  Every CTA rebuilds the fp16 operand planes of the frame's post-norm2 rows (106 KB from L2), runs
+// lin1[chunk] -> activation -> lin2[:, chunk] and writes its [N][256] partial; slot_norm3_kernel adds the partials in chunk
+// order (deterministic), the bias and the residual and applies norm3.
+struct FfnParams {
+  int N, act;
+  const float *p2, *b1;                         // [T][N][256] post-norm2 rows, [F] lin1 bias
+  float* part;                                  // [F/128][T][N][256] partial lin2 outputs
+  long part_stride;                             // T * N * 256
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+slot_ffn_kernel(const __grid_constant__ CUtensorMap m_l1, const __grid_constant__ CUtensorMap m_l2, const FfnParams P, const int F_pad) {
+  extern __shared__ uint8_t raw_smem[];
+  const uint32_t raw = tc::smem_u32(raw_smem);
+  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
+  Barriers* b = reinterpret_cast<Barriers*>(smem + OFF_MISC);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x, c = blockIdx.y, N = P.N;
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&m_l1); tc::tma_prefetch_desc(&m_l2);
+    for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&b->full[i], 1); tc::mbar_init(&b->empty[i], 1); }
+    tc::mbar_init(&b->dfull, 1); tc::mbar_init(&b->aready, EPI_THREADS);
+    tc::mbar_init(&b->d1full[0], 1); tc::mbar_init(&b->hfull, EPI_THREADS);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) { tc::tmem_alloc(&b->tmem_ptr, 512); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = b->tmem_ptr;
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring rg;
+      prod_gemm(smem, b, rg, &m_l1, F_pad, c, 1, 0, 4);
+      prod_gemm(smem, b, rg, &m_l2, C, 0, 2, 2 * c, 2);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      Ring rg;
+      const uint32_t act = tc::smem_u32(smem + OFF_ACT), hb = tc::smem_u32(smem + OFF_HB);
+      tc::mbar_wait(&b->aready, 0); tc::tc_fence_after();
+      mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D1, 1, IDESC128, false);       // hidden chunk
+      tc::umma_commit(&b->d1full[0]);
+      tc::mbar_wait(&b->hfull, 0); tc::tc_fence_after();
+      mma_gemm(smem, b, rg, tmem_base, hb, HB_PLANE, 2, TM_D, 2, IDESC128, false);          // partial out = h_c . W2[:, chunk]^T
+      tc::umma_commit(&b->dfull);
+    }
+  } else {
+    Epi e = make_epi(smem, tmem_base, N);
+    const long fbase = (long)t * N * C;
+    load_rows_to_act(smem, P.p2 + fbase, N, warp - 2, lane);
+    tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->aready);
+    float bb[2][16];
+#pragma unroll
+    for (int uu = 0; uu < 2; ++uu) ldg16(P.b1 + c * 128 + 16 * (e.qt * 2 + uu), bb[uu]);
+    tc::mbar_wait(&b->d1full[0], 0);
+    tc::tc_fence_after();
+    float h[2][16];
+#pragma unroll
+    for (int uu = 0; uu < 2; ++uu) tc::tmem_ld16(e.tbase + TM_D1 + 16 * (e.qt * 2 + uu), h[uu]);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int uu = 0; uu < 2; ++uu) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) h[uu][k] = act_fn(fmaf(h[uu][k], WSCALE_INV, bb[uu][k]), P.act);
+      if (e.valid) store_operand16(smem + OFF_HB, HB_PLANE, e.r, e.qt * 2 + uu, h[uu]);
+    }
+    tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->hfull);
+    tc::mbar_wait(&b->dfull, 0);                                   // lin2 retired: HB is free for the staging tiles
+    tc::tc_fence_after();
+    float* dst = P.part + (long)c * P.part_stride + fbase;
+#pragma unroll 1
+    for (int uu = 0; uu < 4; ++uu) {
+      float v[16];
+      e.ld_raw(TM_D, e.qt * 4 + uu, v);
+      e.write_rows(dst, e.qt * 4 + uu, v);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+// f = norm3(p2 + b2 + sum_c part[c]) (:382-385); one warp per slot row, two-pass LayerNorm in registers
+__global__ void __launch_bounds__(256) slot_norm3_kernel(const float* __restrict__ part, long part_stride, int nparts, const float* __restrict__ p2,
+                                                         const float* __restrict__ b2, const float* __restrict__ gw, const float* __restrict__ gb,
+                                                         float* __restrict__ f_out, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[8];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int col = hh * 128 + lane * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int cc = 0; cc < nparts; ++cc) {
+      const float4 q = __ldcg(reinterpret_cast<const float4*>(part + (long)cc * part_stride + (long)row * C + col));
+      a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+    }
+    const float4 r = __ldcg(reinterpret_cast<const float4*>(p2 + (long)row * C + col)), bq = __ldg(reinterpret_cast<const float4*>(b2 + col));
+    v[4 * hh] = a.x + bq.x + r.x; v[4 * hh + 1] = a.y + bq.y + r.y; v[4 * hh + 2] = a.z + bq.z + r.z; v[4 * hh + 3] = a.w + bq.w + r.w;
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sum += v[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.f / C);
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const float dlt = v[k] - mean; sq = fmaf(dlt, dlt, sq); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.f / C) + LN_EPS);
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int col = hh * 128 + lane * 4;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(gw + col)), bq = __ldg(reinterpret_cast<const float4*>(gb + col));
+    float4 o;
+    o.x = (v[4 * hh] - mean) * rstd * w.x + bq.x; o.y = (v[4 * hh + 1] - mean) * rstd * w.y + bq.y;
+    o.z = (v[4 * hh + 2] - mean) * rstd * w.z + bq.z; o.w = (v[4 * hh + 3] - mean) * rstd * w.w + bq.w;
+    *reinterpret_cast<float4*>(f_out + (long)row * C + col) = o;
+  }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
