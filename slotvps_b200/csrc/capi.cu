@@ -399,8 +399,7 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
                         const StagePix& px, const float* x, long x_bs, const float* pos, long pos_bs, int h, int wd, bool temporal,
                         float* cls_out, long cls_frame_stride, float* emb_out, long emb_frame_stride, cudaStream_t s) {
   const int T = d->n_frames, N = d->n_slots, R = T * N, P = h * wd, F = d->dim_feedforward;
-  // cluster form of the slot kernels (slot_cl.cuh): four CTAs per frame, 64 output columns each
-  static const int slot_cl_on = getenv("SLOTVPS_SLOT_CL") ? atoi(getenv("SLOTVPS_SLOT_CL")) : 1;
+  const int grid_cl = T * slot::cl::CL;                   // one cluster of four CTAs per frame (slot_cl.cuh)
   // (1) slot self-attention core (:346-352): in_proj + 8-head attention on the generic kernels
   SV_TRY(linear_fast(w.slots, sp.in_proj_w, sp.in_proj_b, w.qkv, R, C, 3 * C, 0, nullptr, s));
   {
@@ -409,12 +408,12 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     mha_core_kernel<<<dim3(d->nhead, T, 4), 256, smem, s>>>(w.qkv, w.mo, N, d->nhead);
     SV_CHECK_LAUNCH("mha_core");
   }
-  // (2) out_proj + norm1, to_q + norm_q, folded key operands G / g0 / g1 and their fp16 planes: one kernel, slots resident
+  // (2) out_proj + norm1, to_q + norm_q, folded key operands G / g0 / g1 and their fp16 planes
   {
     CUtensorMap m_out, m_q, m_wk;
-    SV_TRY(slot::slot_wmap(&m_out, ps.stc.out_proj, C, C));
-    SV_TRY(slot::slot_wmap(&m_q, ps.stc.to_q, C, C));
-    SV_TRY(slot::slot_wmap(&m_wk, ps.stc.wkT, C, C));
+    SV_TRY(slot::cl::slot_wmap64(&m_out, ps.stc.out_proj, C, C));
+    SV_TRY(slot::cl::slot_wmap64(&m_q, ps.stc.to_q, C, C));
+    SV_TRY(slot::cl::slot_wmap64(&m_wk, ps.stc.wkT, C, C));
     slot::PreParams pp;
     memset(&pp, 0, sizeof(pp));
     pp.N = N; pp.mo = w.mo; pp.slots = w.slots;
@@ -422,97 +421,51 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     pp.out_b = sp.out_proj_b; pp.n1_w = sp.norm1_w; pp.n1_b = sp.norm1_b; pp.q_b = sp.to_q_b;
     pp.nq_w = sp.nq_w; pp.nq_b = sp.nq_b; pp.nk_w = sp.nk_w; pp.nk_b = sp.nk_b; pp.bk_c = ps.bk_c;
     pp.p = w.p; pp.G = w.G; pp.g0 = w.g0; pp.g1 = w.g1; pp.gplanes = px.tc.gplanes;
-    if (slot_cl_on) {
-      SV_TRY(slot::cl::slot_wmap64(&m_out, ps.stc.out_proj, C, C));
-      SV_TRY(slot::cl::slot_wmap64(&m_q, ps.stc.to_q, C, C));
-      SV_TRY(slot::cl::slot_wmap64(&m_wk, ps.stc.wkT, C, C));
-      SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_pre_cl, slot::cl::SMEM));
-      slot::cl::slot_pre_cl<<<T * slot::cl::CL, slot::THREADS, slot::cl::SMEM, s>>>(m_out, m_q, m_wk, pp);
-      SV_CHECK_LAUNCH("slot_pre");
-    } else {
-      SV_TRY(ensure_dyn_smem((const void*)slot::slot_pre_kernel, slot::SMEM_BYTES));
-      slot::slot_pre_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_out, m_q, m_wk, pp);
-      SV_CHECK_LAUNCH("slot_pre");
-    }
+    SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_pre_cl, slot::cl::SMEM));
+    slot::cl::slot_pre_cl<<<grid_cl, slot::THREADS, slot::cl::SMEM, s>>>(m_out, m_q, m_wk, pp);
+    SV_CHECK_LAUNCH("slot_pre");
   }
   // (3) pixel side: Z, a0, a1
   SV_TRY(pixel_attention(x, x_bs, pos, pos_bs, ps, w, px, T, N, P, true, s, true));
-  // (4..7) value projection, norms, FFN [, Video Retriever], towers
+  // (4..7) value projection + norms, FFN, norm3 [, Video Retriever], towers
   {
     CUtensorMap m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg;
-    SV_TRY(slot::slot_wmap(&m_wv, ps.stc.wv, C, C));
+    SV_TRY(slot::cl::slot_wmap64(&m_wv, ps.stc.wv, C, C));
     SV_TRY(slot::slot_wmap(&m_l1, ps.stc.lin1, F, C));
     SV_TRY(slot::slot_wmap(&m_l2, ps.stc.lin2, C, F));
-    SV_TRY(slot::slot_wmap(&m_tw, ps.stc.tw, 2 * C, C));
-    SV_TRY(slot::slot_wmap(&m_c1, ps.stc.cls1, C, C));
-    SV_TRY(slot::slot_wmap(&m_r1, ps.stc.reg1, C, C));
-    SV_TRY(slot::slot_wmap(&m_lg, ps.stc.logit, d->num_classes, C));
+    SV_TRY(slot::cl::slot_wmap64(&m_tw, ps.stc.tw, 2 * C, C));
+    SV_TRY(slot::cl::slot_wmap64(&m_c1, ps.stc.cls1, C, C));
+    SV_TRY(slot::cl::slot_wmap64(&m_r1, ps.stc.reg1, C, C));
+    SV_TRY(slot::cl::slot_wmap64(&m_lg, ps.stc.logit, d->num_classes, C));
     slot::PostParams q;
     memset(&q, 0, sizeof(q));
-    q.N = N; q.F = F; q.act = ffn_act_of(d); q.ncls = d->num_classes;
-    q.dbg = getenv("SLOTVPS_SLOT_DEBUG") ? atoi(getenv("SLOTVPS_SLOT_DEBUG")) : 0;
+    q.N = N; q.ncls = d->num_classes;
     q.Z = w.Z; q.a0 = w.a0; q.a1 = w.a1; q.p = w.p;
     q.nv_w = sp.nv_w; q.nv_b = sp.nv_b; q.bv_c = ps.bv_c; q.no_w = sp.no_w; q.no_b = sp.no_b; q.n2_w = sp.norm2_w; q.n2_b = sp.norm2_b;
-    q.b1 = sp.lin1_b; q.b2 = sp.lin2_b; q.n3_w = sp.norm3_w; q.n3_b = sp.norm3_b;
-    q.p2buf = w.p2buf; q.f_out = w.f;
+    q.p2buf = w.p2buf;
     q.tw_ln_w = ps.tw_ln_w; q.tw_ln_b = ps.tw_ln_b; q.c1_nw = sp.cls1_nw; q.c1_nb = sp.cls1_nb; q.r1_nw = sp.reg1_nw; q.r1_nb = sp.reg1_nb;
     q.logit_b = sp.logit_b;
     q.slots_out = w.slots; q.emb_out = emb_out; q.cls_out = cls_out; q.emb_fs = emb_frame_stride; q.cls_fs = cls_frame_stride;
-    SV_TRY(ensure_dyn_smem((const void*)slot::slot_post_kernel, slot::SMEM_BYTES));
-    static const int ffn_split = getenv("SLOTVPS_FFN_SPLIT") ? atoi(getenv("SLOTVPS_FFN_SPLIT")) : 1;
-    if (slot_cl_on) {
-      CUtensorMap c_wv, c_tw, c_c1, c_lg, c_r1;
-      SV_TRY(slot::cl::slot_wmap64(&c_wv, ps.stc.wv, C, C));
-      SV_TRY(slot::cl::slot_wmap64(&c_tw, ps.stc.tw, 2 * C, C));
-      SV_TRY(slot::cl::slot_wmap64(&c_c1, ps.stc.cls1, C, C));
-      SV_TRY(slot::cl::slot_wmap64(&c_r1, ps.stc.reg1, C, C));
-      SV_TRY(slot::cl::slot_wmap64(&c_lg, ps.stc.logit, d->num_classes, C));
-      SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_post_cl, slot::cl::SMEM));
-      slot::cl::slot_post_cl<<<T * slot::cl::CL, slot::THREADS, slot::cl::SMEM, s>>>(c_wv, q);
-      SV_CHECK_LAUNCH("slot_post");
-      slot::FfnParams fp;
-      fp.N = N; fp.act = q.act; fp.p2 = w.p2buf; fp.b1 = sp.lin1_b; fp.part = w.ffn_part; fp.part_stride = (long)R * C;
-      SV_TRY(ensure_dyn_smem((const void*)slot::slot_ffn_kernel, slot::SMEM_BYTES));
-      slot::slot_ffn_kernel<<<dim3(T, F / 128), slot::THREADS, slot::SMEM_BYTES, s>>>(m_l1, m_l2, fp, F);
-      SV_CHECK_LAUNCH("slot_ffn");
-      slot::slot_norm3_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.ffn_part, (long)R * C, F / 128, w.p2buf, sp.lin2_b, sp.norm3_w, sp.norm3_b, w.f, R);
-      SV_CHECK_LAUNCH("slot_norm3");
-      const float* fcur = w.f;
-      if (temporal) {
-        SV_TRY(video_retriever(d, sp, ps, w, s));
-        fcur = w.f2;
-      }
-      q.f_in = fcur;
-      SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_towers_cl, slot::cl::SMEM));
-      slot::cl::slot_towers_cl<<<T * slot::cl::CL, slot::THREADS, slot::cl::SMEM, s>>>(c_tw, c_c1, c_lg, c_r1, q);
-      SV_CHECK_LAUNCH("slot_towers");
-    } else if (!temporal && !ffn_split) {
-      q.phases = 3;
-      slot::slot_post_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg, q);
-      SV_CHECK_LAUNCH("slot_post");
-    } else {
-      q.phases = 1; q.ffn_split = ffn_split;
-      slot::slot_post_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg, q);
-      SV_CHECK_LAUNCH("slot_post");
-      if (ffn_split) {
-        // FFN over (frame, hidden chunk) CTAs, then the chunk-ordered reduction + norm3
-        slot::FfnParams fp;
-        fp.N = N; fp.act = q.act; fp.p2 = w.p2buf; fp.b1 = sp.lin1_b; fp.part = w.ffn_part; fp.part_stride = (long)R * C;
-        SV_TRY(ensure_dyn_smem((const void*)slot::slot_ffn_kernel, slot::SMEM_BYTES));
-        slot::slot_ffn_kernel<<<dim3(T, F / 128), slot::THREADS, slot::SMEM_BYTES, s>>>(m_l1, m_l2, fp, F);
-        SV_CHECK_LAUNCH("slot_ffn");
-        slot::slot_norm3_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.ffn_part, (long)R * C, F / 128, w.p2buf, sp.lin2_b, sp.norm3_w, sp.norm3_b, w.f, R);
-        SV_CHECK_LAUNCH("slot_norm3");
-      }
-      const float* fcur = w.f;
-      if (temporal) {
-        SV_TRY(video_retriever(d, sp, ps, w, s));
-        fcur = w.f2;
-      }
-      q.phases = 2; q.f_in = fcur; q.ffn_split = 0;
-      slot::slot_post_kernel<<<T, slot::THREADS, slot::SMEM_BYTES, s>>>(m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg, q);
-      SV_CHECK_LAUNCH("slot_post(towers)");
+    SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_post_cl, slot::cl::SMEM));
+    slot::cl::slot_post_cl<<<grid_cl, slot::THREADS, slot::cl::SMEM, s>>>(m_wv, q);
+    SV_CHECK_LAUNCH("slot_post");
+    // FFN over (frame, hidden chunk) CTAs, then the chunk-ordered reduction + residual + norm3
+    slot::FfnParams fp;
+    fp.N = N; fp.act = ffn_act_of(d); fp.p2 = w.p2buf; fp.b1 = sp.lin1_b; fp.part = w.ffn_part; fp.part_stride = (long)R * C;
+    SV_TRY(ensure_dyn_smem((const void*)slot::slot_ffn_kernel, slot::SMEM_BYTES));
+    slot::slot_ffn_kernel<<<dim3(T, F / 128), slot::THREADS, slot::SMEM_BYTES, s>>>(m_l1, m_l2, fp, F);
+    SV_CHECK_LAUNCH("slot_ffn");
+    slot::slot_norm3_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.ffn_part, (long)R * C, F / 128, w.p2buf, sp.lin2_b, sp.norm3_w, sp.norm3_b, w.f, R);
+    SV_CHECK_LAUNCH("slot_norm3");
+    const float* fcur = w.f;
+    if (temporal) {
+      SV_TRY(video_retriever(d, sp, ps, w, s));
+      fcur = w.f2;
     }
+    q.f_in = fcur;
+    SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_towers_cl, slot::cl::SMEM));
+    slot::cl::slot_towers_cl<<<grid_cl, slot::THREADS, slot::cl::SMEM, s>>>(m_tw, m_c1, m_lg, m_r1, q);
+    SV_CHECK_LAUNCH("slot_towers");
   }
   return SLOTVPS_OK;
 }

@@ -190,14 +190,19 @@ __global__ void __launch_bounds__(256) fuse_count_kernel(const float* __restrict
   for (long pix = (long)blockIdx.x * 256 + threadIdx.x; pix < (long)H * W; pix += (long)gridDim.x * 256) {
     const int y = (int)(pix / W), x = (int)(pix % W);
     const Samp sp = samp_setup(y, x, h, w, sys, sxs, same);
-    float mx = -INFINITY;
-    for (int k = 0; k < K; ++k) mx = fmaxf(mx, sp.at(masks + (long)st->ord[k] * P));
-    float sum = 0.f;
-    for (int k = 0; k < K; ++k) sum += expf(sp.at(masks + (long)st->ord[k] * P) - mx);
+    // running-maximum softmax and log-domain threshold, the same arithmetic as fuse_count4_kernel
+    float mx = -INFINITY, sum = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float v = sp.at(masks + (long)st->ord[k] * P);
+      const float dlt = v - mx;
+      const float ex = __expf(-fabsf(dlt));
+      sum = dlt > 0.f ? fmaf(sum, ex, 1.f) : sum + ex;
+      mx = fmaxf(mx, v);
+    }
+    const float cut = mx + logf(pix_thr * sum);
     int c1 = -1, c2 = -1;
     for (int k = ns; k < K; ++k) {
-      float p = expf(sp.at(masks + (long)st->ord[k] * P) - mx) / sum;
-      if (p >= pix_thr) { if (c1 < 0) c1 = k - ns; else if (c2 < 0) c2 = k - ns; }
+      if (sp.at(masks + (long)st->ord[k] * P) >= cut) { if (c1 < 0) c1 = k - ns; else if (c2 < 0) c2 = k - ns; }
     }
     if (c1 >= 0) atomicAdd(&s_cnt[c1], 1u);
     if (c2 >= 0) { atomicAdd(&s_cnt[c2], 1u); atomicAdd(&pair[c1 * nc + c2], 1u); atomicAdd(&pair[c2 * nc + c1], 1u); }
@@ -295,19 +300,24 @@ __global__ void __launch_bounds__(256) fuse_count4_kernel(const float* __restric
         continue;
       }
     }
+    // softmax over the kept slots in one sweep (running maximum, sum rescaled when it moves: one exp per value), then the
+    // threshold test in the log domain: p_k >= thr  <=>  v_k >= max + log(thr * sum).  Against the reference's
+    // exp / divide / compare this moves the decision only for pixels whose p is within ~1e-6 (relative) of the threshold.
     float mx[16], sum[16], v[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) { mx[e] = -INFINITY; sum[e] = 0.f; }
     for (int k = 0; k < K; ++k) {
       b4.eval(masks + (long)s_ord[k] * P, w, v);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) mx[e] = fmaxf(mx[e], v[e]);
+      for (int e = 0; e < 16; ++e) {
+        const float dlt = v[e] - mx[e];
+        const float ex = __expf(-fabsf(dlt));
+        sum[e] = dlt > 0.f ? fmaf(sum[e], ex, 1.f) : sum[e] + ex;
+        mx[e] = fmaxf(mx[e], v[e]);
+      }
     }
-    for (int k = 0; k < K; ++k) {
-      b4.eval(masks + (long)s_ord[k] * P, w, v);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) sum[e] += expf(v[e] - mx[e]);
-    }
+    for (int e = 0; e < 16; ++e) mx[e] += logf(pix_thr * sum[e]);              // the cut: -inf when pix_thr == 0
     unsigned int cd[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) cd[e] = 0xFFFFFFFFu;
@@ -315,8 +325,7 @@ __global__ void __launch_bounds__(256) fuse_count4_kernel(const float* __restric
       b4.eval(masks + (long)s_ord[k] * P, w, v);
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const float p = expf(v[e] - mx[e]) / sum[e];
-        if (p >= pix_thr) {
+        if (v[e] >= mx[e]) {
           const unsigned int c = (unsigned int)(k - ns);
           if ((cd[e] & 0xFFFF) == 0xFFFF) cd[e] = (cd[e] & 0xFFFF0000u) | c;
           else if ((cd[e] >> 16) == 0xFFFF) cd[e] = (cd[e] & 0xFFFFu) | (c << 16);

@@ -33,8 +33,11 @@ constexpr int OFF_STG = OFF_RING + NSL * WT;   // 16 per-warp staging tiles [32]
 constexpr int OFF_RED = OFF_STG + EPI_WARPS * 2560;      // CTA-local partial sums [2][4][128] float2
 constexpr int OFF_XCH = OFF_RED + 8192;        // cluster partial sums [2][4 ranks][128] float2
 constexpr int OFF_BAR = OFF_XCH + 8192;
+constexpr int OFF_RSC = OFF_BAR + 512;            // [128] floats: inverse row scales of the loaded rows
 constexpr int SMEM = OFF_BAR + 1024 + 1024;
+constexpr float INV_L = WSCALE_INV * LSCALE_INV;   // read-back scale of a GEMM on a LayerNorm-output operand
 constexpr uint32_t IDESC64 = tc::make_idesc_f16(128, 64, 0, 0);
+constexpr int CORR = 128;                      // TMEM column offset of the cross-product accumulators
 static_assert(SMEM <= 232448, "shared memory budget");
 static_assert(OFF_RING % 1024 == 0 && WT % 1024 == 0, "swizzle atoms");
 
@@ -69,6 +72,11 @@ __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifdef SLOTVPS_SLOT_PROFILE
+#define CL_MARK(i) tk[i] = clock64()
+#else
+#define CL_MARK(i)
+#endif
 
 // ---- TMA producer / MMA issuer: one 64-column slice of a layer -----------------------------------------------------
 __device__ __forceinline__ void prod_slice(uint8_t* smem, Bars* b, uint32_t& it, const CUtensorMap* m, int hi_row, int lo_row) {
@@ -83,7 +91,11 @@ __device__ __forceinline__ void prod_slice(uint8_t* smem, Bars* b, uint32_t& it,
       ++it;
     }
 }
+// The hi.hi products accumulate at d_tmem, the two cross products (2^-11 of the magnitude) at d_tmem + CORR: the fp32
+// accumulator of the tensor pipe does not round to nearest, so every accumulation step costs up to an ulp of the running
+// sum with a systematic sign; keeping the 32 small steps out of the main sum leaves 16 of the 48.
 __device__ __forceinline__ void mma_slice(uint8_t* smem, Bars* b, uint32_t& it, uint32_t d_tmem, uint32_t act, uint32_t idesc) {
+  const uint32_t d_corr = d_tmem + CORR;
 #pragma unroll 1
   for (int ks = 0; ks < 4; ++ks) {
     const uint64_t dah = tc::make_smem_desc_sw128(act + ks * ACT_SUB, 16, 1024);
@@ -96,7 +108,7 @@ __device__ __forceinline__ void mma_slice(uint8_t* smem, Bars* b, uint32_t& it, 
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         tc::umma_bf16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (ks != 0 || k != 0) ? 1u : 0u);
-        tc::umma_bf16(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);
+        tc::umma_bf16(d_corr, dal + 2 * k, dbh + 2 * k, idesc, (ks != 0 || k != 0) ? 1u : 0u);
       }
       tc::umma_commit(&b->empty[s]);
       ++it;
@@ -107,7 +119,7 @@ __device__ __forceinline__ void mma_slice(uint8_t* smem, Bars* b, uint32_t& it, 
       tc::tc_fence_after();
       const uint64_t dbl = tc::make_smem_desc_sw128(tc::smem_u32(smem + OFF_RING + s * WT), 16, 1024);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tc::umma_bf16(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+      for (int k = 0; k < 4; ++k) tc::umma_bf16(d_corr, dah + 2 * k, dbl + 2 * k, idesc, 1);
       tc::umma_commit(&b->empty[s]);
       ++it;
     }
@@ -137,15 +149,19 @@ struct Ctx {
   }
   __device__ __forceinline__ void wait_d() { tc::mbar_wait(&b->dfull, nd & 1); ++nd; tc::tc_fence_after(); }
   __device__ __forceinline__ void publish() { tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->aready); }
-  // accumulator columns [col0 + 16 qt, +16) of this thread's row, unscaled by the weight scale
-  __device__ __forceinline__ void ld(int col0, float* v) const {
+  // accumulator columns [col0 + 16 qt, +16) of this thread's row (main + cross products) times the inverse operand scales
+  __device__ __forceinline__ void ld(int col0, float* v, float inv) const {
+    float cr[16];
     tc::tmem_ld16(e.tbase + col0 + 16 * e.qt, v);
+    tc::tmem_ld16(e.tbase + CORR + col0 + 16 * e.qt, cr);
     tc::tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] *= WSCALE_INV;
+    for (int c = 0; c < 16; ++c) v[c] = (v[c] + cr[c]) * inv;
   }
-  // (sum, sum of squares) over this thread's 16 columns -> over the row's 256 columns of the four CTAs
-  __device__ __forceinline__ void row_total(float a, float q, float& ta, float& tq) {
+  // (a, q) of this thread's 16 columns -> per-CTA pairs of the four CTAs, in rank order.  CTA-local combine `comb` folds
+  // the four column quarters of a row into one pair; the rendezvous also orders earlier st.shared::cluster of this CTA.
+  template <class Comb>
+  __device__ __forceinline__ void row_gather(float a, float q, Comb&& comb, float2* out) {
     float2* rb = red + (nred & 1) * 512;
     ++nred;
     rb[e.qt * 128 + e.r] = make_float2(a, q);
@@ -153,27 +169,43 @@ struct Ctx {
     const uint32_t slot = (nx & 1) * 512;
     ++nx;
     if (e.qt == 0) {
-      const float2 p0 = rb[e.r], p1 = rb[128 + e.r], p2 = rb[256 + e.r], p3 = rb[384 + e.r];
-      const float s1 = (p0.x + p1.x) + (p2.x + p3.x), s2 = (p0.y + p1.y) + (p2.y + p3.y);
+      const float2 s = comb(rb[e.r], rb[128 + e.r], rb[256 + e.r], rb[384 + e.r]);
       const uint32_t off = (slot + rank * 128 + e.r) * 8;
 #pragma unroll
-      for (int d = 0; d < CL; ++d) st_cl_v2f(xch_r[d] + off, s1, s2);
+      for (int d = 0; d < CL; ++d) st_cl_v2f(xch_r[d] + off, s.x, s.y);
     }
     xsync();
     const float2* xb = xch + slot;
-    const float2 x0 = xb[e.r], x1 = xb[128 + e.r], x2 = xb[256 + e.r], x3 = xb[384 + e.r];
-    ta = (x0.x + x1.x) + (x2.x + x3.x);
-    tq = (x0.y + x1.y) + (x2.y + x3.y);
+    out[0] = xb[e.r]; out[1] = xb[128 + e.r]; out[2] = xb[256 + e.r]; out[3] = xb[384 + e.r];
   }
-  // LayerNorm of the row whose unit is v (single-pass variance as in slot_tc.cuh), optional ReLU
+  // plain sums of two per-thread values over the row's 256 columns
+  __device__ __forceinline__ void row_total(float a, float q, float& ta, float& tq) {
+    float2 x[4];
+    row_gather(a, q, [](float2 p0, float2 p1, float2 p2, float2 p3) {
+      return make_float2((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y)); }, x);
+    ta = (x[0].x + x[1].x) + (x[2].x + x[3].x);
+    tq = (x[0].y + x[1].y) + (x[2].y + x[3].y);
+  }
+  // LayerNorm of the row whose unit is v, optional ReLU.  Mean and CENTRED second moment are combined pairwise
+  // (Chan et al.): per thread over 16 values, per CTA over 4 threads, per row over 4 CTAs -- as accurate as the two-pass
+  // form of the oracle with a single exchange.
   __device__ __forceinline__ void layer_norm(float* v, const float* __restrict__ gw, const float* __restrict__ gb, bool relu) {
-    float sp = 0.f, qp = 0.f;
+    float sp = 0.f;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) { sp += v[c]; qp = fmaf(v[c], v[c], qp); }
-    float s1, s2;
-    row_total(sp, qp, s1, s2);
-    const float mean = s1 * (1.f / C);
-    const float rstd = rsqrtf(fmaxf(s2 * (1.f / C) - mean * mean, 0.f) + LN_EPS);
+    for (int c = 0; c < 16; ++c) sp += v[c];
+    const float m16 = sp * (1.f / 16.f);
+    float m2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { const float dl = v[c] - m16; m2 = fmaf(dl, dl, m2); }
+    float2 x[4];
+    row_gather(m16, m2, [](float2 p0, float2 p1, float2 p2, float2 p3) {        // 4 x (mean, M2) of 16 -> (mean, M2) of 64
+      const float m = 0.25f * ((p0.x + p1.x) + (p2.x + p3.x));
+      const float d0 = p0.x - m, d1 = p1.x - m, d2 = p2.x - m, d3 = p3.x - m;
+      return make_float2(m, ((p0.y + p1.y) + (p2.y + p3.y)) + 16.f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3))); }, x);
+    const float mean = 0.25f * ((x[0].x + x[1].x) + (x[2].x + x[3].x));
+    const float d0 = x[0].x - mean, d1 = x[1].x - mean, d2 = x[2].x - mean, d3 = x[3].x - mean;
+    const float M2 = ((x[0].y + x[1].y) + (x[2].y + x[3].y)) + 64.f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+    const float rstd = rsqrtf(M2 * (1.f / C) + LN_EPS);
     float w[16], bb[16];
     ldg16(gw + 16 * u, w); ldg16(gb + 16 * u, bb);
 #pragma unroll
@@ -182,7 +214,7 @@ struct Ctx {
       if (relu) v[c] = fmaxf(v[c], 0.f);
     }
   }
-  // unit -> fp16 hi/lo operand planes of every CTA of the cluster
+  // LayerNorm-output unit (times LSCALE) -> fp16 hi/lo operand planes of every CTA of the cluster
   __device__ __forceinline__ void to_act_all(const float* v) const {
     if (!e.valid) return;
     const uint32_t off = (u >> 2) * ACT_SUB + e.r * 128;
@@ -190,7 +222,7 @@ struct Ctx {
     for (int q = 0; q < 2; ++q) {
       uint32_t hi[4], lo[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) split2(v[8 * q + 2 * k], v[8 * q + 2 * k + 1], hi[k], lo[k]);
+      for (int k = 0; k < 4; ++k) split2(v[8 * q + 2 * k] * LSCALE, v[8 * q + 2 * k + 1] * LSCALE, hi[k], lo[k]);
       const uint32_t phys = off + ((((u & 3) * 2 + q) ^ (e.r & 7))) * 16;
 #pragma unroll
       for (int d = 0; d < CL; ++d) {
@@ -211,7 +243,6 @@ __device__ __forceinline__ Ctx make_ctx(uint8_t* smem, Bars* b, uint32_t tmem_ba
   c.e.valid = c.e.r < N;
   c.e.tbase = tmem_base + ((uint32_t)(c.e.q * 32) << 16);
   c.e.stg = reinterpret_cast<float*>(smem + OFF_STG) + we * 640;
-  c.e.red = nullptr; c.e.nred = 0;
   c.u = (int)rank * 4 + c.e.qt;
   c.red = reinterpret_cast<float2*>(smem + OFF_RED);
   c.xch = reinterpret_cast<float2*>(smem + OFF_XCH);
@@ -256,7 +287,7 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x / CL, N = P.N;
   const uint32_t rank = tc::cluster_ctarank();
   if (threadIdx.x == 0) { tc::tma_prefetch_desc(&m_out); tc::tma_prefetch_desc(&m_q); tc::tma_prefetch_desc(&m_wk); }
-  const uint32_t tmem_base = prologue(b, warp, 64);
+  const uint32_t tmem_base = prologue(b, warp, 256);
   const int hi_row = (int)rank * NCOL, lo_row = C + (int)rank * NCOL;
 
   if (warp == 0) {
@@ -282,9 +313,15 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
     Epi& e = c.e;
     const int u = c.u;
     const long fbase = (long)t * N * C;
+#ifdef SLOTVPS_SLOT_PROFILE
+    long long tk[12];
+#endif
+    CL_MARK(0);
     // A operand of the first GEMM: the self-attention output rows (every CTA builds the full K = 256 operand)
-    load_rows_to_act(smem, P.mo + fbase, N, warp - 2, lane);
+    float* rsc = reinterpret_cast<float*>(smem + OFF_RSC);
+    load_rows_to_act(smem, P.mo + fbase, N, warp - 2, lane, rsc);
     c.publish();
+    CL_MARK(1);
     float v[16], add[16];
     // ---- (1) out_proj + residual + norm1 -> p ----
     {
@@ -295,20 +332,28 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
       for (int k = 0; k < 16; ++k) add[k] += bb[k];
       prefetch_l1(P.n1_w + 16 * u); prefetch_l1(P.n1_b + 16 * u);
     }
+    e.sync();                                                      // rsc is complete
+    const float inv0 = WSCALE_INV * rsc[e.r];
+    CL_MARK(2);
     c.wait_d();
-    c.ld(0, v);
+    CL_MARK(3);
+    c.ld(0, v, inv0);
 #pragma unroll
     for (int k = 0; k < 16; ++k) v[k] += add[k];
     c.layer_norm(v, P.n1_w, P.n1_b, false);
+    CL_MARK(4);
     c.to_act_all(v);
     e.write_rows(P.p + fbase, u, v);
     ldg16(P.q_b + 16 * u, add);
     prefetch_l1(P.nq_w + 16 * u); prefetch_l1(P.nq_b + 16 * u);
     prefetch_l1(P.nk_w + 16 * u); prefetch_l1(P.nk_b + 16 * u); prefetch_l1(P.bk_c + 16 * u);
+    CL_MARK(5);
     c.publish_all();
+    CL_MARK(6);
     // ---- (2) to_q + norm_q -> q; qt = q * gamma_k; g0 = qt . bk_c; g1 = q . beta_k ----
     c.wait_d();
-    c.ld(0, v);
+    CL_MARK(7);
+    c.ld(0, v, INV_L);
 #pragma unroll
     for (int k = 0; k < 16; ++k) v[k] += add[k];
     c.layer_norm(v, P.nq_w, P.nq_b, false);
@@ -328,9 +373,11 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
     c.row_total(s0, s1, s0, s1);                                   // (its rendezvous also covers the operand stores above)
     if (e.valid && e.qt == 0 && rank == 0) { P.g0[(long)t * N + e.r] = s0; P.g1[(long)t * N + e.r] = s1; }
     c.publish();
+    CL_MARK(8);
     // ---- (3) G = qt . Wk_c -> fp32 + fp16 hi/lo planes (the B operand of attn_tc's S product) ----
     c.wait_d();
-    c.ld(0, v);
+    CL_MARK(9);
+    c.ld(0, v, INV_L);
     if (P.G) e.write_rows(P.G + fbase, u, v);
     {
       uint32_t* stw = reinterpret_cast<uint32_t*>(e.stg);           // staging as [2 planes][32 rows][10 words] (8 used)
@@ -359,8 +406,14 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
         }
       __syncwarp();
     }
+    CL_MARK(10);
+#ifdef SLOTVPS_SLOT_PROFILE
+    if (P.dbg && blockIdx.x == 0 && threadIdx.x == 64)
+      printf("slot_pre_cl cycles: load %lld | prefetch %lld | wait1 %lld | ld+LN1 %lld | emit1 %lld | sync O %lld | wait2 %lld | epi2 %lld | wait3 %lld | epi3 %lld\n",
+             tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[7] - tk[6], tk[8] - tk[7], tk[9] - tk[8], tk[10] - tk[9]);
+#endif
   }
-  epilogue_exit(tmem_base, warp, 64);
+  epilogue_exit(tmem_base, warp, 256);
 }
 
 // =====================================================================================================================
@@ -373,7 +426,7 @@ slot_post_cl(const __grid_constant__ CUtensorMap m_wv, const PostParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x / CL, N = P.N;
   const uint32_t rank = tc::cluster_ctarank();
   if (threadIdx.x == 0) tc::tma_prefetch_desc(&m_wv);
-  const uint32_t tmem_base = prologue(b, warp, 64);
+  const uint32_t tmem_base = prologue(b, warp, 256);
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
@@ -392,7 +445,8 @@ slot_post_cl(const __grid_constant__ CUtensorMap m_wv, const PostParams P) {
     Epi& e = c.e;
     const int u = c.u;
     const long fbase = (long)t * N * C;
-    load_rows_to_act(smem, P.Z + fbase, N, warp - 2, lane);
+    float* rsc = reinterpret_cast<float*>(smem + OFF_RSC);
+    load_rows_to_act(smem, P.Z + fbase, N, warp - 2, lane, rsc);
     c.publish();
     // ---- value projection of the pixel-reduced slots, norm_v / norm1 / ReLU, residual, norm2 (:456-459, 374-376) ----
     float v[16], pp[16];
@@ -400,8 +454,10 @@ slot_post_cl(const __grid_constant__ CUtensorMap m_wv, const PostParams P) {
     const float a0r = e.valid ? P.a0[(long)t * N + e.r] : 0.f, a1r = e.valid ? P.a1[(long)t * N + e.r] : 0.f;
     prefetch_l1(P.nv_w + 16 * u); prefetch_l1(P.nv_b + 16 * u); prefetch_l1(P.bv_c + 16 * u);
     prefetch_l1(P.no_w + 16 * u); prefetch_l1(P.no_b + 16 * u); prefetch_l1(P.n2_w + 16 * u); prefetch_l1(P.n2_b + 16 * u);
+    e.sync();                                                      // rsc is complete
+    const float inv0 = WSCALE_INV * rsc[e.r];
     c.wait_d();
-    c.ld(0, v);
+    c.ld(0, v, inv0);
     {
       float gv[16], bv[16], bc[16];
       ldg16(P.nv_w + 16 * u, gv); ldg16(P.nv_b + 16 * u, bv); ldg16(P.bv_c + 16 * u, bc);
@@ -414,7 +470,7 @@ slot_post_cl(const __grid_constant__ CUtensorMap m_wv, const PostParams P) {
     c.layer_norm(v, P.n2_w, P.n2_b, false);
     e.write_rows(P.p2buf + fbase, u, v);
   }
-  epilogue_exit(tmem_base, warp, 64);
+  epilogue_exit(tmem_base, warp, 256);
 }
 
 // =====================================================================================================================
@@ -429,7 +485,7 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x / CL, N = P.N;
   const uint32_t rank = tc::cluster_ctarank();
   if (threadIdx.x == 0) { tc::tma_prefetch_desc(&m_tw); tc::tma_prefetch_desc(&m_c1); tc::tma_prefetch_desc(&m_lg); tc::tma_prefetch_desc(&m_r1); }
-  const uint32_t tmem_base = prologue(b, warp, 128);
+  const uint32_t tmem_base = prologue(b, warp, 256);
   const int hi_row = (int)rank * NCOL, lo_row = C + (int)rank * NCOL;
   if (warp == 0) {
     if (lane == 0) {
@@ -464,41 +520,47 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
     Epi& e = c.e;
     const int u = c.u;
     const long fbase = (long)t * N * C;
-    load_rows_to_act(smem, P.f_in + fbase, N, warp - 2, lane);
+    float* rsc = reinterpret_cast<float*>(smem + OFF_RSC);
+    load_rows_to_act(smem, P.f_in + fbase, N, warp - 2, lane, rsc);
     c.publish();
     prefetch_l1(P.tw_ln_w + 16 * u); prefetch_l1(P.tw_ln_b + 16 * u); prefetch_l1(P.tw_ln_w + C + 16 * u); prefetch_l1(P.tw_ln_b + C + 16 * u);
     prefetch_l1(P.c1_nw + 16 * u); prefetch_l1(P.c1_nb + 16 * u); prefetch_l1(P.r1_nw + 16 * u); prefetch_l1(P.r1_nb + 16 * u);
     float v[16];
+    e.sync();                                                      // rsc is complete
+    const float inv0 = WSCALE_INV * rsc[e.r];
     c.wait_d();
-    c.ld(0, v);
+    c.ld(0, v, inv0);
     c.layer_norm(v, P.tw_ln_w, P.tw_ln_b, true);                    // c1
     c.to_act_all(v);
     c.publish_all();
     c.wait_d();
-    c.ld(0, v);
+    c.ld(0, v, INV_L);
     c.layer_norm(v, P.c1_nw, P.c1_nb, true);                        // c2
     c.to_act_all(v);
     c.publish_all();
     c.wait_d();
     if (rank == 0 && e.qt == 0) {
-      float lg[2][16];
+      float lg[2][16], lc[2][16];
       tc::tmem_ld16(e.tbase, lg[0]); tc::tmem_ld16(e.tbase + 16, lg[1]);
+      tc::tmem_ld16(e.tbase + CORR, lc[0]); tc::tmem_ld16(e.tbase + CORR + 16, lc[1]);
       tc::tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { lg[0][k] += lc[0][k]; lg[1][k] += lc[1][k]; }
       if (e.valid) {
         float* dst = P.cls_out + (long)t * P.cls_fs + (long)e.r * P.ncls;
-        for (int k = 0; k < P.ncls; ++k) dst[k] = lg[k >> 4][k & 15] * WSCALE_INV + __ldg(P.logit_b + k);
+        for (int k = 0; k < P.ncls; ++k) dst[k] = lg[k >> 4][k & 15] * INV_L + __ldg(P.logit_b + k);
       }
     }
-    c.ld(64, v);                                                    // first reg layer, parked since the first GEMM
+    c.ld(64, v, inv0);                                              // first reg layer, parked since the first GEMM
     c.layer_norm(v, P.tw_ln_w + C, P.tw_ln_b + C, true);            // e1
     c.to_act_all(v);
     c.publish_all();
     c.wait_d();
-    c.ld(0, v);
+    c.ld(0, v, INV_L);
     c.layer_norm(v, P.r1_nw, P.r1_nb, true);                        // next-stage slots = this stage's embedding
     e.write_rows(P.slots_out + fbase, u, v, P.emb_out + (long)t * P.emb_fs);
   }
-  epilogue_exit(tmem_base, warp, 128);
+  epilogue_exit(tmem_base, warp, 256);
 }
 
 // tensor map over [2 * Opad][K] fp16 planes, box [64][64]

@@ -1,17 +1,19 @@
-// Slot-update kernels on the tensor pipe (north_star kernel 2): the slot side of one retriever stage
-// (dynamic_mask_head.py:342-400) with the N <= 104 slots of a frame RESIDENT in one CTA -- activations live in
-// shared memory as fp16 hi/lo MMA operands and in TMEM as fp32 accumulators, the stage's weights stream through
-// a TMA ring, every LayerNorm / GELU / residual runs thread-per-slot-row straight out of TMEM.
+// Slot-update kernels on the tensor pipe (north_star kernel 2), shared pieces: the slot side of one retriever stage
+// (dynamic_mask_head.py:342-400) keeps the N <= 104 slots of a frame on the 128 TMEM lanes of a CTA -- activations live
+// in shared memory as fp16 hi/lo MMA operands and in TMEM as fp32 accumulators, weights stream through a TMA ring, every
+// LayerNorm / GELU / residual runs on slot rows straight out of TMEM.  GEMM scheme: fp16 hi/lo operands, 3 products,
+// fp32 accumulation.
 //
-//   slot_pre_kernel   (after the slot self-attention core):  out_proj + residual + norm1  ->  to_q + norm_q
-//                     -> folded key operands  G = (q*gamma_k) Wk_c, g0, g1  -> fp16 hi/lo planes for attn_tc
-//   slot_post_kernel  (after the pixel attention):  Wv_c Z, norm_v / norm1 / ReLU / residual / norm2  ->  FFN
-//                     256 -> F -> 256 in 128-wide hidden chunks (the hidden activation never leaves the SM)  -> norm3
-//                     [-> Video Retriever on the generic kernels] -> cls / reg towers -> class logits, next-stage slots
+//   slot_cl.cuh       the row-wise layers on a cluster of four CTAs per frame (64 output columns each)
+//   slot_ffn_kernel   the FFN 256 -> F -> 256 over (frame, 128-wide hidden chunk) CTAs   (this file)
+//   slot_norm3_kernel chunk-ordered reduction of the FFN partials + residual + norm3      (this file)
 //
-// One CTA per frame (grid = T), 576 threads: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer,
-// warps 2..17 = epilogue (slot row r = TMEM lane r is shared by four threads, each owning 64 of the 256 columns).  GEMM shape: M = 128 slot rows (lanes),
-// N = 128 output features per weight tile, K = 64 per ring slot; fp16 hi/lo operands, 3 products, fp32 accumulation.
+// Operand scaling.  fp16 has 5 exponent bits: the lo plane of a value below ~0.1 is subnormal (absolute step 6e-8), i.e.
+// the hi/lo pair carries ~1e-6 relative instead of 2^-22 -- and for sums of random-sign terms the relative error of the sum
+// equals the per-term one.  Weight planes are therefore stored times 2^8, LayerNorm outputs are written times 2^4, and rows
+// loaded from global memory (attention outputs, pixel-reduced slots, GELU outputs: anything from 1e-3 to 1e4) get a per-row
+// power of two that puts the row maximum in [512, 1024); the accumulator read-back undoes the scales exactly.  Measured:
+// per-stage teacher-forced error 3.0e-6 -> 1.4e-6 (the fp32 path: 1.36e-6).
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -44,6 +46,8 @@ constexpr int TM_D1 = 256;                     // two 128-column FFN hidden accu
 // subnormal (absolute step 6e-8, ~1e-6 relative instead of 2.4e-7 -- and for sums of random-sign terms the relative
 // error of the sum equals the per-term one).  Every accumulator read is multiplied by 2^-8 (exact).
 constexpr float WSCALE = 256.f, WSCALE_INV = 1.f / 256.f;
+constexpr float LSCALE = 16.f, LSCALE_INV = 1.f / 16.f;      // LayerNorm outputs (|x| <= 16 |gamma| + |beta|) as operands
+constexpr int OFF_RSC = OFF_MISC + 512;        // [128] floats: inverse row scales of the rows loaded by load_rows_to_act
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(OFF_HB % 1024 == 0 && OFF_RING % 1024 == 0 && ACT_SUB % 1024 == 0, "swizzle atoms");
 
@@ -131,30 +135,43 @@ __device__ __forceinline__ void prefetch_gemm(const CUtensorMap* m, int opad, in
 }
 
 // 16 fp32 values of row `row`, columns [16 u, 16 u + 16) -> fp16 hi/lo operand planes (K-major, 128-byte swizzle)
-__device__ __forceinline__ void store_operand16(uint8_t* base, int lo_off, int row, int u, const float* v) {
+__device__ __forceinline__ void store_operand16(uint8_t* base, int lo_off, int row, int u, const float* v, float sc) {
   uint8_t* sub = base + (u >> 2) * ACT_SUB + row * 128;
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) split2(v[8 * q + 2 * e], v[8 * q + 2 * e + 1], hi[e], lo[e]);
+    for (int e = 0; e < 4; ++e) split2(v[8 * q + 2 * e] * sc, v[8 * q + 2 * e + 1] * sc, hi[e], lo[e]);
     const int phys = ((((u & 3) * 2 + q) ^ (row & 7))) * 16;
     *reinterpret_cast<uint4*>(sub + phys) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(sub + lo_off + phys) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
-// fp32 rows [N][256] of one frame -> ACT operand planes; cooperative over the epilogue warps (coalesced row reads,
-// a warp owns a row at a time)
-__device__ __forceinline__ void load_rows_to_act(uint8_t* smem, const float* __restrict__ src, int N, int we, int lane) {
+// power-of-two scale that puts a row maximum m >= 0 into [512, 1024) (capped at 2^40 for tiny rows); inv = its inverse
+__device__ __forceinline__ float row_scale(float m, float& inv) {
+  const int ex = max((__float_as_int(m) >> 23) & 0xFF, 96);
+  inv = __int_as_float((ex - 9) << 23);
+  return __int_as_float((263 - ex) << 23);
+}
+// fp32 rows [N][256] of one frame -> ACT operand planes, each row times its own power of two (inverse -> rsc[row]);
+// cooperative over the epilogue warps (coalesced row reads, a warp owns a row at a time)
+__device__ __forceinline__ void load_rows_to_act(uint8_t* smem, const float* __restrict__ src, int N, int we, int lane, float* rsc) {
   for (int row = we; row < N; row += EPI_WARPS) {
     float4 a[2];
 #pragma unroll
     for (int half = 0; half < 2; ++half) a[half] = __ldg(reinterpret_cast<const float4*>(src + (long)row * C + half * 128 + lane * 4));
+    float m = fmaxf(fmaxf(fmaxf(fabsf(a[0].x), fabsf(a[0].y)), fmaxf(fabsf(a[0].z), fabsf(a[0].w))),
+                    fmaxf(fmaxf(fabsf(a[1].x), fabsf(a[1].y)), fmaxf(fabsf(a[1].z), fabsf(a[1].w))));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float inv;
+    const float sc = row_scale(m, inv);
+    if (lane == 0) rsc[row] = inv;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int col = half * 128 + lane * 4;
       uint32_t h0, l0, h1, l1;
-      split2(a[half].x, a[half].y, h0, l0); split2(a[half].z, a[half].w, h1, l1);
+      split2(a[half].x * sc, a[half].y * sc, h0, l0); split2(a[half].z * sc, a[half].w * sc, h1, l1);
       const int ks = col >> 6, cidx = (col & 63) >> 3;
       uint8_t* dst = smem + OFF_ACT + ks * ACT_SUB + row * 128 + ((cidx ^ (row & 7)) * 16) + (col & 7) * 2;
       *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
@@ -171,32 +188,21 @@ __device__ __forceinline__ void ldg16(const float* __restrict__ p, float* v) {  
 }
 
 // Epilogue context: 16 warps; warp e serves TMEM lane quadrant (e & 3) -- slot rows 32 (e & 3) + lane -- and column
-// quarter (e >> 2) of every 256-column accumulator, so a slot row is shared by four threads (64 columns = 4 units of
-// 16 each) that exchange their partial LayerNorm sums through shared memory.  The epilogues are instruction-bound
-// (~25 fp32 / conversion instructions per element against ~2 tensor-pipe cycles), hence the many warps.  Global row
-// I/O goes through a per-warp staging tile so that every request is coalesced (a thread-per-row access pattern
-// costs ~100 cycles per instruction: 21 K cycles per epilogue were measured with it).
+// quarter (e >> 2) of the accumulator, so a slot row is shared by four threads.  The epilogues are instruction-bound,
+// hence the many warps.  Global row I/O goes through a per-warp staging tile so that every request is coalesced (a
+// thread-per-row access pattern costs ~100 cycles per instruction: 21 K cycles per epilogue were measured with it).
 struct Epi {
   int r, qt, lane, q, N;                        // row, column quarter, lane, lane quadrant
   bool valid;
   uint32_t tbase;                               // tmem_base + lane quadrant
   float* stg;                                   // [32][20] staging tile of this warp
-  float* red;                                   // [2][2][4][128] partial sums / sums of squares (double-buffered)
-  uint32_t nred;
   __device__ __forceinline__ void sync() const { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-  __device__ __forceinline__ float row_sum(float part) {
-    float* rb = red + (nred & 1) * 1024;
-    ++nred;
-    rb[qt * 128 + r] = part;
-    sync();
-    return (rb[r] + rb[128 + r]) + (rb[256 + r] + rb[384 + r]);
-  }
-  // raw accumulator columns of unit u (16 columns), unscaled
-  __device__ __forceinline__ void ld_raw(int col0, int u, float* v) const {
+  // accumulator columns of unit u (16 columns) times `inv` (the product of the inverse operand scales)
+  __device__ __forceinline__ void ld_raw(int col0, int u, float* v, float inv) const {
     tc::tmem_ld16(tbase + col0 + 16 * u, v);
     tc::tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] *= WSCALE_INV;
+    for (int c = 0; c < 16; ++c) v[c] *= inv;
   }
   // v[c] = frame[(32 q + lane) * 256 + 16 u + c] (zeros for rows >= N)
   __device__ __forceinline__ void read_rows(const float* frame, int u, float* v, bool coherent = false) const {
@@ -234,60 +240,6 @@ struct Epi {
     }
     __syncwarp();
   }
-  // partial (sum, sum of squares) of the four threads of a row -> (mean, rstd)
-  __device__ __forceinline__ void row_stats(float sp, float qp, float& mean, float& rstd) {
-    float* rb = red + (nred & 1) * 1024;
-    ++nred;
-    rb[qt * 128 + r] = sp;
-    rb[512 + qt * 128 + r] = qp;
-    sync();
-    const float s1 = (rb[r] + rb[128 + r]) + (rb[256 + r] + rb[384 + r]);
-    const float s2 = (rb[512 + r] + rb[640 + r]) + (rb[768 + r] + rb[896 + r]);
-    mean = s1 * (1.f / C);
-    rstd = rsqrtf(fmaxf(s2 * (1.f / C) - mean * mean, 0.f) + LN_EPS);
-  }
-  // Row LayerNorm over the 256 accumulator columns at col0, 16 columns at a time to stay within the register budget of a
-  // 576-thread CTA.  pre(u, v): raw (unscaled) accumulator values of unit u -> pre-norm values, which are written back
-  // to TMEM while sum / sum of squares are accumulated (single-pass variance: the rows are near-centred pre-norm
-  // activations, so E[x^2] - mean^2 loses < 1e-6 relative); emit(u, v): normalised (optionally rectified) unit.
-  template <class Pre, class Emit>
-  __device__ __forceinline__ void ln_tmem(int col0, bool raw, Pre&& pre, const float* gw, const float* gb, bool relu, Emit&& emit) {
-    float sp = 0.f, qp = 0.f;
-#pragma unroll 1
-    for (int uu = 0; uu < 4; ++uu) {
-      const int u = qt * 4 + uu;
-      float v[16];
-      tc::tmem_ld16(tbase + col0 + 16 * u, v);
-      tc::tmem_ld_wait();
-      if (raw) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] *= WSCALE_INV;
-      }
-      pre(u, v);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) { sp += v[c]; qp = fmaf(v[c], v[c], qp); }
-      tc::tmem_st16(tbase + col0 + 16 * u, v);
-    }
-    tc::tmem_st_wait();
-    float mean, rstd;
-    row_stats(sp, qp, mean, rstd);
-#pragma unroll 1
-    for (int uu = 0; uu < 4; ++uu) {
-      const int u = qt * 4 + uu;
-      float v[16];
-      tc::tmem_ld16(tbase + col0 + 16 * u, v);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(gw + 16 * u) + c4), bb = __ldg(reinterpret_cast<const float4*>(gb + 16 * u) + c4);
-        float* xv = v + 4 * c4;
-        xv[0] = (xv[0] - mean) * rstd * w.x + bb.x; xv[1] = (xv[1] - mean) * rstd * w.y + bb.y;
-        xv[2] = (xv[2] - mean) * rstd * w.z + bb.z; xv[3] = (xv[3] - mean) * rstd * w.w + bb.w;
-        if (relu) { xv[0] = fmaxf(xv[0], 0.f); xv[1] = fmaxf(xv[1], 0.f); xv[2] = fmaxf(xv[2], 0.f); xv[3] = fmaxf(xv[3], 0.f); }
-      }
-      emit(u, v);
-    }
-  }
 };
 __device__ __forceinline__ Epi make_epi(uint8_t* smem, uint32_t tmem_base, int N) {
   Epi e;
@@ -295,9 +247,7 @@ __device__ __forceinline__ Epi make_epi(uint8_t* smem, uint32_t tmem_base, int N
   e.lane = threadIdx.x & 31; e.q = (threadIdx.x >> 5) & 3; e.qt = we >> 2; e.r = e.q * 32 + e.lane; e.N = N;
   e.valid = e.r < N;
   e.tbase = tmem_base + ((uint32_t)(e.q * 32) << 16);
-  e.stg = reinterpret_cast<float*>(smem + OFF_HB) + we * 640;      // 2560 B per warp: [32][20] floats
-  e.red = reinterpret_cast<float*>(smem + OFF_HB + 16 * 2560);      // 8 KB after the staging tiles (HB is idle whenever a LayerNorm runs)
-  e.nred = 0;
+  e.stg = reinterpret_cast<float*>(smem + OFF_HB) + we * 640;      // 2560 B per warp: [32][20] floats (HB is idle when rows are written)
   return e;
 }
 
@@ -309,160 +259,15 @@ struct PreParams {
   __half* gplanes;                              // [T][2][104][256] hi / lo planes of G (rows >= N zero)
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
-slot_pre_kernel(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ CUtensorMap m_q, const __grid_constant__ CUtensorMap m_wk,
-                const PreParams P) {
-  extern __shared__ uint8_t raw_smem[];
-  const uint32_t raw = tc::smem_u32(raw_smem);
-  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
-  Barriers* b = reinterpret_cast<Barriers*>(smem + OFF_MISC);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x, N = P.N;
-  if (threadIdx.x == 0) {
-    tc::tma_prefetch_desc(&m_out); tc::tma_prefetch_desc(&m_q); tc::tma_prefetch_desc(&m_wk);
-    for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&b->full[i], 1); tc::mbar_init(&b->empty[i], 1); }
-    tc::mbar_init(&b->dfull, 1); tc::mbar_init(&b->aready, EPI_THREADS);
-    tc::fence_barrier_init();
-  }
-  if (warp == 1) { tc::tmem_alloc(&b->tmem_ptr, 256); tc::tmem_relinquish(); }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = b->tmem_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      Ring rg;
-      prefetch_gemm(&m_out, C, 0, 2, 0, 4); prefetch_gemm(&m_q, C, 0, 2, 0, 4); prefetch_gemm(&m_wk, C, 0, 2, 0, 4);
-      prod_gemm(smem, b, rg, &m_out, C, 0, 2, 0, 4);
-      prod_gemm(smem, b, rg, &m_q, C, 0, 2, 0, 4);
-      prod_gemm(smem, b, rg, &m_wk, C, 0, 2, 0, 4);
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      Ring rg;
-      const uint32_t act = tc::smem_u32(smem + OFF_ACT);
-      for (int g = 0; g < 3; ++g) {
-        tc::mbar_wait(&b->aready, g & 1);
-        tc::tc_fence_after();
-        mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D, 2, IDESC128, false);
-        tc::umma_commit(&b->dfull);
-      }
-    }
-  } else {
-    Epi e = make_epi(smem, tmem_base, N);
-    const int r = e.r, qt = e.qt;
-    const bool valid = e.valid;
-    const long fbase = (long)t * N * C;
-    auto publish_act = [&]() { tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->aready); };
-    auto to_act = [&](int u, float* v) { if (valid) store_operand16(smem + OFF_ACT, ACT_PLANE, r, u, v); };
-#ifdef SLOTVPS_SLOT_PROFILE
-    long long tk[8]; int nk = 0;
-    auto mark = [&]() { if (P.dbg && nk < 8) tk[nk++] = clock64(); };
-#else
-    auto mark = []() {};
-#endif
-    mark();
-    // A operand of the first GEMM: the self-attention output rows
-    load_rows_to_act(smem, P.mo + fbase, N, warp - 2, lane);
-    publish_act();
-    mark();
-    // ---- (1) out_proj + residual + norm1 -> p ----
-    tc::mbar_wait(&b->dfull, 0);
-    tc::tc_fence_after();
-    mark();
-    e.ln_tmem(TM_D, true, [&](int u, float* v) {
-      float bb[16], rr[16];
-      e.read_rows(P.slots + fbase, u, rr);
-      ldg16(P.out_b + 16 * u, bb);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = v[c] + bb[c] + rr[c];
-    }, P.n1_w, P.n1_b, false, [&](int u, float* v) { e.write_rows(P.p + fbase, u, v); to_act(u, v); });
-    publish_act();
-    mark();
-    // ---- (2) to_q + norm_q -> q; qt = q * gamma_k; g0 = qt . bk_c; g1 = q . beta_k ----
-    tc::mbar_wait(&b->dfull, 1);
-    tc::tc_fence_after();
-    mark();
-    float s0 = 0.f, s1 = 0.f;
-    e.ln_tmem(TM_D, true, [&](int u, float* v) {
-      float bb[16];
-      ldg16(P.q_b + 16 * u, bb);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] += bb[c];
-    }, P.nq_w, P.nq_b, false, [&](int u, float* v) {
-      float gk[16], bk[16], bc[16];
-      ldg16(P.nk_w + 16 * u, gk); ldg16(P.nk_b + 16 * u, bk); ldg16(P.bk_c + 16 * u, bc);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float qv = v[c], tv = qv * gk[c];
-        s0 = fmaf(tv, bc[c], s0);
-        s1 = fmaf(qv, bk[c], s1);
-        v[c] = tv;
-      }
-      to_act(u, v);
-    });
-    s0 = e.row_sum(s0); s1 = e.row_sum(s1);
-    if (valid && qt == 0) { P.g0[(long)t * N + r] = s0; P.g1[(long)t * N + r] = s1; }
-    publish_act();
-    mark();
-    // ---- (3) G = qt . Wk_c -> fp32 + fp16 hi/lo planes (the B operand of attn_tc's S product) ----
-    tc::mbar_wait(&b->dfull, 0);
-    tc::tc_fence_after();
-    mark();
-    uint32_t* stw = reinterpret_cast<uint32_t*>(e.stg);           // staging as [2 planes][32 rows][10 words] (8 used)
-#pragma unroll 1
-    for (int uu = 0; uu < 4; ++uu) {
-      const int u = qt * 4 + uu;
-      float v[16];
-      e.ld_raw(TM_D, u, v);
-      if (P.G) e.write_rows(P.G + fbase, u, v);
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        hi[k] = 0u; lo[k] = 0u;
-        if (valid) split2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
-      }
-#pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        *reinterpret_cast<uint2*>(stw + lane * 10 + k) = make_uint2(hi[k], hi[k + 1]);
-        *reinterpret_cast<uint2*>(stw + 320 + lane * 10 + k) = make_uint2(lo[k], lo[k + 1]);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int pl = 0; pl < 2; ++pl)
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {                          // a row's 16 columns = 32 bytes = 4 lanes x 8 bytes; 8 rows per request
-          const int row = it * 8 + (lane >> 2), gr = e.q * 32 + row, part = lane & 3;
-          if (gr < NR) {
-            const uint2 w2 = *reinterpret_cast<const uint2*>(stw + pl * 320 + row * 10 + part * 2);
-            __half* dst = P.gplanes + (((long)t * 2 + pl) * NR + gr) * C + 16 * u + part * 4;
-            *reinterpret_cast<uint2*>(dst) = w2;
-          }
-        }
-      __syncwarp();
-    }
-    mark();
-#ifdef SLOTVPS_SLOT_PROFILE
-    if (P.dbg && t == 0 && threadIdx.x == 64)
-      printf("slot_pre cycles: load %lld | gemm1 wait %lld | epi1 %lld | gemm2 wait %lld | epi2 %lld | gemm3 wait %lld | epi3 %lld\n", tk[1] - tk[0],
-             tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[7] - tk[6]);
-#endif
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 256); }
-}
 
 // ---- post-attention phase -----------------------------------------------------------------------------------------
 struct PostParams {
-  int N, F, act, phases, ncls, dbg;             // phases: bit 0 = attention epilogue + FFN, bit 1 = towers
-  // phase 0
-  const float *Z, *a0, *a1, *p;
-  const float *nv_w, *nv_b, *bv_c, *no_w, *no_b, *n2_w, *n2_b, *b1, *b2, *n3_w, *n3_b;
-  float *p2buf, *f_out;                         // [T][N][256] scratch (post-norm2 rows), FFN block output
-  int ffn_split;                                // 1: stop after norm2 (p2buf); the FFN runs in slot_ffn_kernel / slot_norm3_kernel
+  int N, ncls;
+  const float *Z, *a0, *a1, *p;                 // pixel-reduced slots [T][N][256], softmax mass / bias terms [T][N], residual rows
+  const float *nv_w, *nv_b, *bv_c, *no_w, *no_b, *n2_w, *n2_b;
+  float* p2buf;                                 // [T][N][256] post-norm2 rows (FFN input and residual)
   // towers
-  const float* f_in;                            // [T][N][256] tower input when phase 0 did not just produce it in shared memory
+  const float* f_in;                            // [T][N][256] tower input
   const float *tw_ln_w, *tw_ln_b, *c1_nw, *c1_nb, *r1_nw, *r1_nb, *logit_b;
   float *slots_out, *emb_out, *cls_out;
   long emb_fs, cls_fs;                          // frame strides of emb_out / cls_out
@@ -486,231 +291,6 @@ __device__ __forceinline__ float gelu_erfc(float x) {
 }
 __device__ __forceinline__ float act_fn(float x, int act) { return act == 1 ? fmaxf(x, 0.f) : gelu_erfc(x); }
 
-__global__ void __launch_bounds__(THREADS, 1)
-slot_post_kernel(const __grid_constant__ CUtensorMap m_wv, const __grid_constant__ CUtensorMap m_l1, const __grid_constant__ CUtensorMap m_l2,
-                 const __grid_constant__ CUtensorMap m_tw, const __grid_constant__ CUtensorMap m_c1, const __grid_constant__ CUtensorMap m_r1,
-                 const __grid_constant__ CUtensorMap m_lg, const PostParams P) {
-  extern __shared__ uint8_t raw_smem[];
-  const uint32_t raw = tc::smem_u32(raw_smem);
-  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
-  Barriers* b = reinterpret_cast<Barriers*>(smem + OFF_MISC);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x, N = P.N;
-  const int NC = P.F / 128;                     // hidden chunks
-  const bool ph0 = P.phases & 1, ph1 = (P.phases & 2) != 0;
-  if (threadIdx.x == 0) {
-    tc::tma_prefetch_desc(&m_wv); tc::tma_prefetch_desc(&m_l1); tc::tma_prefetch_desc(&m_l2);
-    tc::tma_prefetch_desc(&m_tw); tc::tma_prefetch_desc(&m_c1); tc::tma_prefetch_desc(&m_r1); tc::tma_prefetch_desc(&m_lg);
-    for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&b->full[i], 1); tc::mbar_init(&b->empty[i], 1); }
-    tc::mbar_init(&b->dfull, 1); tc::mbar_init(&b->aready, EPI_THREADS);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&b->d1full[i], 1); tc::mbar_init(&b->d1free[i], EPI_THREADS); }
-    tc::mbar_init(&b->hfull, EPI_THREADS); tc::mbar_init(&b->hfree, 1);
-    tc::fence_barrier_init();
-  }
-  if (warp == 1) { tc::tmem_alloc(&b->tmem_ptr, 512); tc::tmem_relinquish(); }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = b->tmem_ptr;
-  const int F_pad = P.F;                        // lin1 planes [2][F][256] (F is a multiple of 128)
-
-  if (warp == 0) {
-    // ===================== TMA producer: the stage's weights in consumption order =====================
-    if (lane == 0) {
-      Ring rg;
-      if (ph0) {
-        prefetch_gemm(&m_wv, C, 0, 2, 0, 4);
-        if (!P.ffn_split) {
-          prefetch_gemm(&m_l1, F_pad, 0, 2, 0, 4);
-          prefetch_gemm(&m_l2, C, 0, 2, 0, 4);
-        }
-        prod_gemm(smem, b, rg, &m_wv, C, 0, 2, 0, 4);
-        if (!P.ffn_split) prod_gemm(smem, b, rg, &m_l1, F_pad, 0, 1, 0, 4);
-        for (int c = 0; c < NC && !P.ffn_split; ++c) {
-          if (c + 2 < NC) { prefetch_gemm(&m_l1, F_pad, c + 2, 1, 0, 4); prefetch_gemm(&m_l2, C, 0, 2, 2 * (c + 2), 2); }   // two chunks ahead
-          else if (ph1 && c + 2 == NC) { prefetch_gemm(&m_tw, 2 * C, 0, 4, 0, 4); prefetch_gemm(&m_c1, C, 0, 2, 0, 4); }
-          if (c + 1 < NC) prod_gemm(smem, b, rg, &m_l1, F_pad, c + 1, 1, 0, 4);
-          prod_gemm(smem, b, rg, &m_l2, C, 0, 2, 2 * c, 2);
-        }
-      }
-      if (ph1) {
-        if (!ph0) { prefetch_gemm(&m_tw, 2 * C, 0, 4, 0, 4); prefetch_gemm(&m_c1, C, 0, 2, 0, 4); }
-        prefetch_gemm(&m_lg, TILE_N, 0, 1, 0, 4); prefetch_gemm(&m_r1, C, 0, 2, 0, 4);
-        prod_gemm(smem, b, rg, &m_tw, 2 * C, 0, 4, 0, 4);
-        prod_gemm(smem, b, rg, &m_c1, C, 0, 2, 0, 4);
-        prod_gemm(smem, b, rg, &m_lg, TILE_N, 0, 1, 0, 4);
-        prod_gemm(smem, b, rg, &m_r1, C, 0, 2, 0, 4);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      Ring rg;
-      const uint32_t act = tc::smem_u32(smem + OFF_ACT), hb = tc::smem_u32(smem + OFF_HB);
-      uint32_t na = 0;                                            // uses of the aready barrier
-      auto wait_act = [&]() { tc::mbar_wait(&b->aready, na & 1); ++na; tc::tc_fence_after(); };
-      if (ph0) {
-        wait_act();                                               // Z rows are in ACT
-        mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D, 2, IDESC128, false);      // Y = Z . Wv_c^T
-        tc::umma_commit(&b->dfull);
-        if (!P.ffn_split) {
-        wait_act();                                               // p2 rows are in ACT, D is drained
-        mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D1, 1, IDESC128, false);     // hidden chunk 0
-        tc::umma_commit(&b->d1full[0]);
-        for (int c = 0; c < NC; ++c) {
-          if (c + 1 < NC) {
-            const int bf = (c + 1) & 1;
-            if (c + 1 >= 2) { tc::mbar_wait(&b->d1free[bf], (((c + 1) >> 1) - 1) & 1); tc::tc_fence_after(); }
-            mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D1 + bf * 128, 1, IDESC128, false);
-            tc::umma_commit(&b->d1full[bf]);
-          }
-          tc::mbar_wait(&b->hfull, c & 1);                        // activated hidden chunk c is in HB
-          tc::tc_fence_after();
-          mma_gemm(smem, b, rg, tmem_base, hb, HB_PLANE, 2, TM_D, 2, IDESC128, c != 0);      // out += h_c . W2[:, chunk]^T
-          tc::umma_commit(&b->hfree);
-        }
-        tc::umma_commit(&b->dfull);
-        }
-      }
-      if (ph1) {
-        wait_act();                                               // tower input rows in ACT (D drained)
-        mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D, 4, IDESC128, false);      // cls0 | reg0 -> 512 columns
-        tc::umma_commit(&b->dfull);
-        wait_act();                                               // c1 in ACT, columns [0,256) drained
-        mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D, 2, IDESC128, false);      // cls1
-        tc::umma_commit(&b->dfull);
-        wait_act();                                               // c2 in ACT
-        mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D, 1, IDESC32, false);       // class logits (32 padded columns)
-        tc::umma_commit(&b->dfull);
-        wait_act();                                               // e1 in ACT
-        mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D, 2, IDESC128, false);      // reg1
-        tc::umma_commit(&b->dfull);
-      }
-    }
-  } else {
-    // ===================== epilogue: 16 warps, four threads per slot row =====================
-    Epi e = make_epi(smem, tmem_base, N);
-    const int r = e.r, qt = e.qt;
-    const bool valid = e.valid;
-    const long fbase = (long)t * N * C;
-    uint32_t nd = 0;                                              // uses of the dfull barrier
-    auto wait_d = [&]() { tc::mbar_wait(&b->dfull, nd & 1); ++nd; tc::tc_fence_after(); };
-    auto publish_act = [&]() { tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->aready); };
-    auto to_act = [&](int u, float* v) { if (valid) store_operand16(smem + OFF_ACT, ACT_PLANE, r, u, v); };
-#ifdef SLOTVPS_SLOT_PROFILE
-    long long tk[16]; int nk = 0; long long w_d1 = 0, w_h = 0, c_ffn = 0;
-    auto mark = [&]() { if (P.dbg && nk < 16) tk[nk++] = clock64(); };
-#define SLOT_PROF(x) x
-#else
-    auto mark = []() {};
-#define SLOT_PROF(x)
-#endif
-    mark();
-    if (ph0) {
-      load_rows_to_act(smem, P.Z + fbase, N, warp - 2, lane);
-      publish_act();
-      mark();
-      // ---- value projection of the pixel-reduced slots, norm_v / norm1 / ReLU, residual, norm2 (:456-459, 374-376) ----
-      wait_d();
-      mark();
-      const float a0r = valid ? P.a0[(long)t * N + r] : 0.f, a1r = valid ? P.a1[(long)t * N + r] : 0.f;
-      e.ln_tmem(TM_D, true, [&](int u, float* v) {
-        float gv[16], bv[16], bc[16];
-        ldg16(P.nv_w + 16 * u, gv); ldg16(P.nv_b + 16 * u, bv); ldg16(P.bv_c + 16 * u, bc);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = gv[c] * fmaf(bc[c], a1r, v[c]) + bv[c] * a0r;
-      }, P.no_w, P.no_b, true, [&](int u, float* v) { tc::tmem_st16(e.tbase + TM_D + 16 * u, v); });     // r = relu(LN(o)) parked in TMEM
-      tc::tmem_st_wait();
-      e.ln_tmem(TM_D, false, [&](int u, float* v) {
-        float pp[16];
-        e.read_rows(P.p + fbase, u, pp);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] += pp[c];
-      }, P.n2_w, P.n2_b, false, [&](int u, float* v) { e.write_rows(P.p2buf + fbase, u, v); if (!P.ffn_split) to_act(u, v); });
-      if (!P.ffn_split) {
-      e.sync();                                                   // every warp is done with the staging tiles (they alias HB)
-      publish_act();
-      mark();
-      // ---- FFN: hidden chunks of 128 (:379-382); a thread owns 32 of the chunk's columns ----
-      for (int c = 0; c < NC; ++c) {
-        const int bf = c & 1;
-        SLOT_PROF(long long t0 = P.dbg ? clock64() : 0;)
-        tc::mbar_wait(&b->d1full[bf], (c >> 1) & 1);
-        tc::tc_fence_after();
-        SLOT_PROF(long long t1 = P.dbg ? clock64() : 0; w_d1 += t1 - t0;)
-        float h[2][16];
-#pragma unroll
-        for (int uu = 0; uu < 2; ++uu) tc::tmem_ld16(e.tbase + TM_D1 + bf * 128 + 16 * (qt * 2 + uu), h[uu]);
-        tc::tmem_ld_wait();
-        tc::tc_fence_before();
-        tc::mbar_arrive(&b->d1free[bf]);
-#pragma unroll
-        for (int uu = 0; uu < 2; ++uu) {
-          float bb[16];
-          ldg16(P.b1 + c * 128 + 16 * (qt * 2 + uu), bb);
-#pragma unroll
-          for (int k = 0; k < 16; ++k) h[uu][k] = act_fn(fmaf(h[uu][k], WSCALE_INV, bb[k]), P.act);
-        }
-        SLOT_PROF(long long t2 = P.dbg ? clock64() : 0; c_ffn += t2 - t1;)
-        if (c > 0) tc::mbar_wait(&b->hfree, (c - 1) & 1);         // the MMAs of chunk c-1 have finished reading HB
-        SLOT_PROF(if (P.dbg) w_h += clock64() - t2;)
-        if (valid) {
-#pragma unroll
-          for (int uu = 0; uu < 2; ++uu) store_operand16(smem + OFF_HB, HB_PLANE, r, qt * 2 + uu, h[uu]);
-        }
-        tc::fence_proxy_async();
-        tc::mbar_arrive(&b->hfull);
-      }
-      // ---- linear2 bias + residual + norm3 -> f ----
-      mark();
-      wait_d();                                                   // all lin2 MMAs retired: HB is free for the staging tiles again
-      mark();
-      e.ln_tmem(TM_D, true, [&](int u, float* v) {
-        float bb[16], pp[16];
-        e.read_rows(P.p2buf + fbase, u, pp, true);
-        ldg16(P.b2 + 16 * u, bb);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = v[c] + bb[c] + pp[c];
-      }, P.n3_w, P.n3_b, false, [&](int u, float* v) { e.write_rows(P.f_out + fbase, u, v); if (ph1) to_act(u, v); });
-      if (ph1) publish_act();
-      mark();
-#ifdef SLOTVPS_SLOT_PROFILE
-      if (P.dbg && t == 0 && threadIdx.x == 64)
-        printf("slot_post cycles: load %lld | Y wait %lld | epi(attn) %lld | FFN total %lld (wait lin1 %lld, act+split %lld, wait HB free %lld) | lin2 tail %lld | epi(norm3) %lld\n",
-               tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], w_d1, c_ffn, w_h, tk[5] - tk[4], tk[6] - tk[5]);
-#endif
-      }
-    } else if (ph1) {
-      load_rows_to_act(smem, P.f_in + fbase, N, warp - 2, lane);
-      publish_act();
-    }
-    if (ph1) {
-      // ---- towers (:390-400): first layers cls0 | reg0 share the input; 512 accumulator columns ----
-      wait_d();
-      auto none = [](int, float*) {};
-      e.ln_tmem(TM_D, true, none, P.tw_ln_w, P.tw_ln_b, true, to_act);
-      publish_act();                                              // c1 -> cls1 GEMM (writes columns [0,256); the reg half stays)
-      wait_d();
-      e.ln_tmem(TM_D, true, none, P.c1_nw, P.c1_nb, true, to_act);
-      publish_act();                                              // c2 -> class logits
-      wait_d();
-      if (qt == 0) {
-        float v[2][16];
-        e.ld_raw(TM_D, 0, v[0]); e.ld_raw(TM_D, 1, v[1]);
-        if (valid) {
-          float* dst = P.cls_out + (long)t * P.cls_fs + (long)r * P.ncls;
-          for (int c = 0; c < P.ncls; ++c) dst[c] = v[c >> 4][c & 15] + __ldg(P.logit_b + c);
-        }
-      }
-      e.ln_tmem(TM_D + 256, true, none, P.tw_ln_w + C, P.tw_ln_b + C, true, to_act);     // reg half of the first tower layer
-      publish_act();                                              // e1 -> reg1 GEMM
-      wait_d();
-      e.ln_tmem(TM_D, true, none, P.r1_nw, P.r1_nb, true, [&](int u, float* v) { e.write_rows(P.slots_out + fbase, u, v, P.emb_out + (long)t * P.emb_fs); });
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
-}
 
 // ---- FFN of one stage spread over the GPU (:379-385) ---------------------------------------------------------------------
 // One CTA per (frame, 128-wide hidden chunk): the 2 x 3-product GEMMs of the FFN are 100 K tensor-pipe cycles on a single SM
@@ -764,31 +344,45 @@ slot_ffn_kernel(const __grid_constant__ CUtensorMap m_l1, const __grid_constant_
   } else {
     Epi e = make_epi(smem, tmem_base, N);
     const long fbase = (long)t * N * C;
-    load_rows_to_act(smem, P.p2 + fbase, N, warp - 2, lane);
+    float* rsc = reinterpret_cast<float*>(smem + OFF_RSC);
+    load_rows_to_act(smem, P.p2 + fbase, N, warp - 2, lane, rsc);
     tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->aready);
     float bb[2][16];
 #pragma unroll
     for (int uu = 0; uu < 2; ++uu) ldg16(P.b1 + c * 128 + 16 * (e.qt * 2 + uu), bb[uu]);
+    e.sync();                                                      // rsc is complete
+    const float inv1 = WSCALE_INV * rsc[e.r];
     tc::mbar_wait(&b->d1full[0], 0);
     tc::tc_fence_after();
     float h[2][16];
 #pragma unroll
     for (int uu = 0; uu < 2; ++uu) tc::tmem_ld16(e.tbase + TM_D1 + 16 * (e.qt * 2 + uu), h[uu]);
     tc::tmem_ld_wait();
+    float m = 0.f;
 #pragma unroll
-    for (int uu = 0; uu < 2; ++uu) {
+    for (int uu = 0; uu < 2; ++uu)
 #pragma unroll
-      for (int k = 0; k < 16; ++k) h[uu][k] = act_fn(fmaf(h[uu][k], WSCALE_INV, bb[uu][k]), P.act);
-      if (e.valid) store_operand16(smem + OFF_HB, HB_PLANE, e.r, e.qt * 2 + uu, h[uu]);
+      for (int k = 0; k < 16; ++k) { h[uu][k] = act_fn(fmaf(h[uu][k], inv1, bb[uu][k]), P.act); m = fmaxf(m, fabsf(h[uu][k])); }
+    // row maximum of the activated chunk over the four threads of the row (lin1 has retired: ACT is free) -> operand scale
+    float* hm = reinterpret_cast<float*>(smem + OFF_ACT);
+    hm[e.qt * 128 + e.r] = m;
+    e.sync();
+    m = fmaxf(fmaxf(hm[e.r], hm[128 + e.r]), fmaxf(hm[256 + e.r], hm[384 + e.r]));
+    float hinv;
+    const float hsc = row_scale(m, hinv);
+    if (e.valid) {
+#pragma unroll
+      for (int uu = 0; uu < 2; ++uu) store_operand16(smem + OFF_HB, HB_PLANE, e.r, e.qt * 2 + uu, h[uu], hsc);
     }
     tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->hfull);
     tc::mbar_wait(&b->dfull, 0);                                   // lin2 retired: HB is free for the staging tiles
     tc::tc_fence_after();
     float* dst = P.part + (long)c * P.part_stride + fbase;
+    const float inv2 = WSCALE_INV * hinv;
 #pragma unroll 1
     for (int uu = 0; uu < 4; ++uu) {
       float v[16];
-      e.ld_raw(TM_D, e.qt * 4 + uu, v);
+      e.ld_raw(TM_D, e.qt * 4 + uu, v, inv2);
       e.write_rows(dst, e.qt * 4 + uu, v);
     }
   }
