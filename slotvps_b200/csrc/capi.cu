@@ -16,6 +16,7 @@
 #include "mask_tc.cuh"
 #include "slot_tc.cuh"
 #include "slot_cl.cuh"
+#include "temporal.cuh"
 #include "track.cuh"
 #include "unify.cuh"
 
@@ -208,7 +209,7 @@ static size_t head_ws_layout(const slotvps_head_desc* d, void* base, size_t cap,
   w.ty = a.take<float>((size_t)R * C); w.thdn = w.hdn;
   w.tw = a.take<float>((size_t)R * 2 * C); w.c2 = a.take<float>((size_t)R * C); w.e1 = a.take<float>((size_t)R * C);
   w.p2buf = a.take<float>((size_t)R * C);
-  w.ffn_part = a.take<float>((size_t)(d->dim_feedforward / 128 + 1) * R * C);
+  w.ffn_part = a.take<float>((size_t)(max(d->dim_feedforward, d->temporal_dim_feedforward) / 128 + 1) * R * C);
   for (int l = 0; l < SLOTVPS_MAX_LEVELS; ++l)
     w.pos[l] = (d->pos_mode == 2 && l < d->n_levels) ? a.take<float>((size_t)C * d->h[l] * d->w[l]) : nullptr;
   w.ybuf = a.take<float>((size_t)T * C * (Pmax / 4 + 1));
@@ -391,6 +392,42 @@ static int video_retriever(const slotvps_head_desc* d, const slotvps_stage_param
   return SLOTVPS_OK;
 }
 
+// The same block on the slot kernels: q|k|v projections + LayerNorms on the frame clusters (slot_cl.cuh), the R x R attention
+// and its two LayerNorms in two fp32 launches (temporal.cuh), the FFN over (frame, hidden chunk) CTAs + reduction/norm3.
+static int video_retriever_tc(const slotvps_head_desc* d, const slotvps_stage_params& sp, const PreparedStage& ps, const HeadWs& w, cudaStream_t s) {
+  const int T = d->n_frames, N = d->n_slots, R = T * N, TF = d->temporal_dim_feedforward;
+  SV_REQUIRE(sp.tq_to_q_w != nullptr, "temporal stage without temporal_query_head parameters");
+  {
+    CUtensorMap m_qkv;
+    SV_TRY(slot::cl::slot_wmap64(&m_qkv, ps.stc.tqkv, 3 * C, C));
+    slot::cl::TqkvParams tp;
+    tp.N = N; tp.f_in = w.f; tp.bias = ps.tq_qkv_b; tp.ln_w = ps.tq_ln_w; tp.ln_b = ps.tq_ln_b; tp.tqkv = w.tqkv;
+    SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_tqkv_cl, slot::cl::SMEM));
+    slot::cl::slot_tqkv_cl<<<T * slot::cl::CL, slot::THREADS, slot::cl::SMEM, s>>>(m_qkv, tp);
+    SV_CHECK_LAUNCH("slot_tqkv");
+  }
+  temporal::tscore_kernel<<<ceil_div(R, temporal::KEYS), temporal::TS_WARPS * 32, 0, s>>>(w.tqkv, w.L, R);
+  SV_CHECK_LAUNCH("tscore");
+  SV_TRY(ensure_dyn_smem((const void*)temporal::tav_kernel, temporal::TAV_SMEM));
+  temporal::tav_kernel<<<ceil_div(R, temporal::TAV_ROWS), temporal::TAV_ROWS * 32, temporal::TAV_SMEM, s>>>(
+      w.L, w.tqkv, w.f, sp.tq_no_w, sp.tq_no_b, sp.tq_norm2_w, sp.tq_norm2_b, w.ty, R);
+  SV_CHECK_LAUNCH("tav");
+  {
+    CUtensorMap m_l1, m_l2;
+    SV_TRY(slot::slot_wmap(&m_l1, ps.stc.tlin1, TF, C));
+    SV_TRY(slot::slot_wmap(&m_l2, ps.stc.tlin2, C, TF));
+    slot::FfnParams fp;
+    fp.N = N; fp.act = temporal_ffn_act_of(d); fp.p2 = w.ty; fp.b1 = sp.tq_lin1_b; fp.part = w.ffn_part; fp.part_stride = (long)R * C;
+    SV_TRY(ensure_dyn_smem((const void*)slot::slot_ffn_kernel, slot::SMEM_BYTES));
+    slot::slot_ffn_kernel<<<dim3(T, TF / 128), slot::THREADS, slot::SMEM_BYTES, s>>>(m_l1, m_l2, fp, TF);
+    SV_CHECK_LAUNCH("slot_ffn");
+    slot::slot_norm3_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.ffn_part, (long)R * C, TF / 128, w.ty, sp.tq_lin2_b, sp.tq_norm3_w, sp.tq_norm3_b,
+                                                           w.f, w.f2, R);                        // X + LN3(...)  (:317)
+    SV_CHECK_LAUNCH("slot_norm3");
+  }
+  return SLOTVPS_OK;
+}
+
 static int pixel_attention(const float* x, long x_bs, const float* pos, long pos_bs, const PreparedStage& ps,
                            const HeadWs& w0, const StagePix& px, int T, int N, int P, bool use_tc, cudaStream_t s, bool gplanes_ready);
 
@@ -455,11 +492,12 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     SV_TRY(ensure_dyn_smem((const void*)slot::slot_ffn_kernel, slot::SMEM_BYTES));
     slot::slot_ffn_kernel<<<dim3(T, F / 128), slot::THREADS, slot::SMEM_BYTES, s>>>(m_l1, m_l2, fp, F);
     SV_CHECK_LAUNCH("slot_ffn");
-    slot::slot_norm3_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.ffn_part, (long)R * C, F / 128, w.p2buf, sp.lin2_b, sp.norm3_w, sp.norm3_b, w.f, R);
+    slot::slot_norm3_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.ffn_part, (long)R * C, F / 128, w.p2buf, sp.lin2_b, sp.norm3_w, sp.norm3_b, nullptr, w.f, R);
     SV_CHECK_LAUNCH("slot_norm3");
     const float* fcur = w.f;
     if (temporal) {
-      SV_TRY(video_retriever(d, sp, ps, w, s));
+      if (R <= temporal::RMAX) SV_TRY(video_retriever_tc(d, sp, ps, w, s));
+      else SV_TRY(video_retriever(d, sp, ps, w, s));
       fcur = w.f2;
     }
     q.f_in = fcur;
@@ -475,7 +513,7 @@ static int run_stage(const slotvps_head_desc* d, const slotvps_stage_params& sp,
                      const StagePix& px, const float* x, long x_bs, const float* pos, long pos_bs, int h, int wd, bool temporal, bool use_tc,
                      float* cls_out /*[T][S][N][K] base at this stage*/, long cls_frame_stride,
                      float* emb_out, long emb_frame_stride, const float* const* slots_in /*[T] or null*/, cudaStream_t s) {
-  const int T = d->n_frames, N = d->n_slots, R = T * N, P = h * wd, F = d->dim_feedforward, TF = d->temporal_dim_feedforward;
+  const int T = d->n_frames, N = d->n_slots, R = T * N, P = h * wd, F = d->dim_feedforward;
   if (slots_in)                                              // teacher forcing: this stage's slots come from the caller
     for (int t = 0; t < T; ++t)
       if (slots_in[t]) SV_TRY(dcopy(slots_in[t], w.slots + (long)t * N * C, (long)N * C, s));
@@ -665,6 +703,12 @@ int slotvps_prepare_weights_ex(const slotvps_head_desc* d, const slotvps_stage_p
       SV_TRY(slot::slot_planes(sp.cls1_w, C, C, ps.stc.cls1, s));
       SV_TRY(slot::slot_planes(sp.reg1_w, C, C, ps.stc.reg1, s));
       SV_TRY(slot::slot_planes(sp.logit_w, d->num_classes, C, ps.stc.logit, s));
+      if (sp.tq_to_q_w) {
+        const int TF = d->temporal_dim_feedforward;
+        SV_TRY(slot::slot_planes(ps.tq_qkv_w, 3 * C, C, ps.stc.tqkv, s));
+        SV_TRY(slot::slot_planes(sp.tq_lin1_w, TF, C, ps.stc.tlin1, s));
+        SV_TRY(slot::slot_planes(sp.tq_lin2_w, C, TF, ps.stc.tlin2, s));
+      }
     }
   }
   return SLOTVPS_OK;

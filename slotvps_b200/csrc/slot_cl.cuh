@@ -45,6 +45,7 @@ struct Bars {
   uint64_t full[NSL], empty[NSL];
   uint64_t dfull, aready;
   uint64_t xbar[2];                             // cluster rendezvous of the epilogue warps
+  uint64_t dq[3];                               // per-layer accumulator barriers where the issuer runs ahead (slot_tqkv_cl)
   uint32_t tmem_ptr;
 };
 
@@ -94,8 +95,9 @@ __device__ __forceinline__ void prod_slice(uint8_t* smem, Bars* b, uint32_t& it,
 // The hi.hi products accumulate at d_tmem, the two cross products (2^-11 of the magnitude) at d_tmem + CORR: the fp32
 // accumulator of the tensor pipe does not round to nearest, so every accumulation step costs up to an ulp of the running
 // sum with a systematic sign; keeping the 32 small steps out of the main sum leaves 16 of the 48.
-__device__ __forceinline__ void mma_slice(uint8_t* smem, Bars* b, uint32_t& it, uint32_t d_tmem, uint32_t act, uint32_t idesc) {
-  const uint32_t d_corr = d_tmem + CORR;
+__device__ __forceinline__ void mma_slice(uint8_t* smem, Bars* b, uint32_t& it, uint32_t d_tmem, uint32_t act, uint32_t idesc,
+                                          uint32_t corr = CORR) {
+  const uint32_t d_corr = d_tmem + corr;
 #pragma unroll 1
   for (int ks = 0; ks < 4; ++ks) {
     const uint64_t dah = tc::make_smem_desc_sw128(act + ks * ACT_SUB, 16, 1024);
@@ -150,10 +152,10 @@ struct Ctx {
   __device__ __forceinline__ void wait_d() { tc::mbar_wait(&b->dfull, nd & 1); ++nd; tc::tc_fence_after(); }
   __device__ __forceinline__ void publish() { tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->aready); }
   // accumulator columns [col0 + 16 qt, +16) of this thread's row (main + cross products) times the inverse operand scales
-  __device__ __forceinline__ void ld(int col0, float* v, float inv) const {
+  __device__ __forceinline__ void ld(int col0, float* v, float inv, int corr = CORR) const {
     float cr[16];
     tc::tmem_ld16(e.tbase + col0 + 16 * e.qt, v);
-    tc::tmem_ld16(e.tbase + CORR + col0 + 16 * e.qt, cr);
+    tc::tmem_ld16(e.tbase + corr + col0 + 16 * e.qt, cr);
     tc::tmem_ld_wait();
 #pragma unroll
     for (int c = 0; c < 16; ++c) v[c] = (v[c] + cr[c]) * inv;
@@ -260,6 +262,7 @@ __device__ __forceinline__ uint32_t prologue(Bars* b, int warp, uint32_t tmem_co
     for (int i = 0; i < NSL; ++i) { tc::mbar_init(&b->full[i], 1); tc::mbar_init(&b->empty[i], 1); }
     tc::mbar_init(&b->dfull, 1); tc::mbar_init(&b->aready, EPI_THREADS);
     tc::mbar_init(&b->xbar[0], EPI_WARPS * CL); tc::mbar_init(&b->xbar[1], EPI_WARPS * CL);
+    for (int i = 0; i < 3; ++i) tc::mbar_init(&b->dq[i], 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) { tc::tmem_alloc(&b->tmem_ptr, tmem_cols); tc::tmem_relinquish(); }
@@ -561,6 +564,66 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
     e.write_rows(P.slots_out + fbase, u, v, P.emb_out + (long)t * P.emb_fs);
   }
   epilogue_exit(tmem_base, warp, 256);
+}
+
+// =====================================================================================================================
+// Video Retriever projections (:494-527): q | k | v = LN_j(f W_j^T + b_j) for the frame's slots -> tqkv rows r*3 + j.
+// The three layers share the operand, so their MMAs run back to back and no operand exchange is needed.
+struct TqkvParams {
+  int N;
+  const float* f_in;                            // [T][N][256]
+  const float *bias, *ln_w, *ln_b;              // [3][256] each
+  float* tqkv;                                  // [T*N][3][256]
+};
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+slot_tqkv_cl(const __grid_constant__ CUtensorMap m_qkv, const TqkvParams P) {
+  extern __shared__ uint8_t raw_smem[];
+  const uint32_t raw = tc::smem_u32(raw_smem);
+  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
+  Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x / CL, N = P.N;
+  const uint32_t rank = tc::cluster_ctarank();
+  if (threadIdx.x == 0) tc::tma_prefetch_desc(&m_qkv);
+  const uint32_t tmem_base = prologue(b, warp, 512);
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int j = 0; j < 3; ++j) prod_slice(smem, b, it, &m_qkv, j * C + (int)rank * NCOL, 3 * C + j * C + (int)rank * NCOL);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      tc::mbar_wait(&b->aready, 0);
+      tc::tc_fence_after();
+      for (int j = 0; j < 3; ++j) {
+        mma_slice(smem, b, it, tmem_base + j * NCOL, tc::smem_u32(smem + OFF_ACT), IDESC64, 256);
+        tc::umma_commit(&b->dq[j]);
+      }
+    }
+  } else {
+    Ctx c = make_ctx(smem, b, tmem_base, rank, N);
+    Epi& e = c.e;
+    const int u = c.u;
+    float* rsc = reinterpret_cast<float*>(smem + OFF_RSC);
+    load_rows_to_act(smem, P.f_in + (long)t * N * C, N, warp - 2, lane, rsc);
+    c.publish();
+    for (int j = 0; j < 3; ++j) { prefetch_l1(P.bias + j * C + 16 * u); prefetch_l1(P.ln_w + j * C + 16 * u); prefetch_l1(P.ln_b + j * C + 16 * u); }
+    e.sync();                                                      // rsc is complete
+    const float inv0 = WSCALE_INV * rsc[e.r];
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+      float v[16], bb[16];
+      ldg16(P.bias + j * C + 16 * u, bb);
+      tc::mbar_wait(&b->dq[j], 0);
+      tc::tc_fence_after();
+      c.ld(j * NCOL, v, inv0, 256);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] += bb[k];
+      c.layer_norm(v, P.ln_w + j * C, P.ln_b + j * C, false);
+      e.write_rows(P.tqkv + ((long)t * N * 3 + j) * C, u, v, nullptr, 3 * C);
+    }
+  }
+  epilogue_exit(tmem_base, warp, 512);
 }
 
 // tensor map over [2 * Opad][K] fp16 planes, box [64][64]

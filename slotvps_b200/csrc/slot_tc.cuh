@@ -225,7 +225,7 @@ struct Epi {
     }
     __syncwarp();
   }
-  __device__ __forceinline__ void write_rows(float* frame, int u, const float* v, float* frame2 = nullptr) const {
+  __device__ __forceinline__ void write_rows(float* frame, int u, const float* v, float* frame2 = nullptr, int ld = C) const {
 #pragma unroll
     for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(stg + lane * 20 + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
     __syncwarp();
@@ -234,8 +234,8 @@ struct Epi {
       const int row = it * 8 + (lane >> 2), gr = q * 32 + row, c4 = (lane & 3) * 4;
       if (gr < N) {
         const float4 a = *reinterpret_cast<const float4*>(stg + row * 20 + c4);
-        *reinterpret_cast<float4*>(frame + (long)gr * C + 16 * u + c4) = a;
-        if (frame2) *reinterpret_cast<float4*>(frame2 + (long)gr * C + 16 * u + c4) = a;
+        *reinterpret_cast<float4*>(frame + (long)gr * ld + 16 * u + c4) = a;
+        if (frame2) *reinterpret_cast<float4*>(frame2 + (long)gr * ld + 16 * u + c4) = a;
       }
     }
     __syncwarp();
@@ -391,10 +391,11 @@ slot_ffn_kernel(const __grid_constant__ CUtensorMap m_l1, const __grid_constant_
   if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
-// f = norm3(p2 + b2 + sum_c part[c]) (:382-385); one warp per slot row, two-pass LayerNorm in registers
+// f = [post +] norm3(p2 + b2 + sum_c part[c]) (:382-385; Video Retriever :317 with post = X); one warp per slot row,
+// two-pass LayerNorm in registers
 __global__ void __launch_bounds__(256) slot_norm3_kernel(const float* __restrict__ part, long part_stride, int nparts, const float* __restrict__ p2,
                                                          const float* __restrict__ b2, const float* __restrict__ gw, const float* __restrict__ gb,
-                                                         float* __restrict__ f_out, int rows) {
+                                                         const float* __restrict__ post, float* __restrict__ f_out, int rows) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   float v[8];
@@ -428,6 +429,10 @@ __global__ void __launch_bounds__(256) slot_norm3_kernel(const float* __restrict
     float4 o;
     o.x = (v[4 * hh] - mean) * rstd * w.x + bq.x; o.y = (v[4 * hh + 1] - mean) * rstd * w.y + bq.y;
     o.z = (v[4 * hh + 2] - mean) * rstd * w.z + bq.z; o.w = (v[4 * hh + 3] - mean) * rstd * w.w + bq.w;
+    if (post) {
+      const float4 pa = __ldcg(reinterpret_cast<const float4*>(post + (long)row * C + col));
+      o.x += pa.x; o.y += pa.y; o.z += pa.z; o.w += pa.w;
+    }
     *reinterpret_cast<float4*>(f_out + (long)row * C + col) = o;
   }
 }
@@ -435,6 +440,7 @@ __global__ void __launch_bounds__(256) slot_norm3_kernel(const float* __restrict
 // ---- host side ----------------------------------------------------------------------------------------------------
 struct SlotTcWeights {                          // fp16 hi/lo planes [2][Opad][K] per linear layer of one stage
   __half *out_proj, *to_q, *wkT, *wv, *lin1, *lin2, *tw, *cls1, *reg1, *logit;
+  __half *tqkv, *tlin1, *tlin2;                 // Video Retriever: q|k|v stacked [2][768][256], FFN [2][TF][256], [2][256][TF]
 };
 inline void slot_tc_layout(Arena& a, const slotvps_head_desc* d, SlotTcWeights* w) {
   const size_t cc = (size_t)2 * C * C;
@@ -442,9 +448,12 @@ inline void slot_tc_layout(Arena& a, const slotvps_head_desc* d, SlotTcWeights* 
   w->lin1 = a.take<__half>((size_t)2 * d->dim_feedforward * C); w->lin2 = a.take<__half>((size_t)2 * C * d->dim_feedforward);
   w->tw = a.take<__half>(2 * cc); w->cls1 = a.take<__half>(cc); w->reg1 = a.take<__half>(cc);
   w->logit = a.take<__half>((size_t)2 * slot::TILE_N * C);
+  w->tqkv = a.take<__half>(3 * cc);
+  w->tlin1 = a.take<__half>((size_t)2 * d->temporal_dim_feedforward * C); w->tlin2 = a.take<__half>((size_t)2 * C * d->temporal_dim_feedforward);
 }
 inline bool slot_tc_supported(const slotvps_head_desc* d) {
-  return d->kernel_path == 0 && d->n_slots <= slot::NR && d->dim_feedforward % 128 == 0 && d->num_classes <= 32;
+  return d->kernel_path == 0 && d->n_slots <= slot::NR && d->dim_feedforward % 128 == 0 && d->temporal_dim_feedforward % 128 == 0 &&
+         d->num_classes <= 32;
 }
 inline int slot_planes(const float* W, int O, int K, __half* out, cudaStream_t s) {
   const int Opad = ceil_div(O, slot::TILE_N) * slot::TILE_N;
