@@ -355,7 +355,7 @@ static int pixel_attention(const float* x, long x_bs, const float* pos, long pos
   }
   if (px.overlapped) SV_CHECK_CUDA(cudaEventRecord(px.done, s));   // planes / rs buffers of this stage may be recycled
   const long nz = (long)T * N * C, na = (long)T * N;
-  reduce_attn_parts_kernel<<<(unsigned)((nz + 2 * na + 255) / 256), 256, 0, s>>>(w.Zpart, w.a0part, w.a1part, w.Z, w.a0, w.a1, nz, na, chunks);
+  reduce_attn_parts_kernel<<<(unsigned)((nz / 4 + 2 * na + 31) / 32), 256, 0, s>>>(w.Zpart, w.a0part, w.a1part, w.Z, w.a0, w.a1, nz, na, chunks);
   SV_CHECK_LAUNCH("reduce_attn_parts");
   return SLOTVPS_OK;
 }
