@@ -171,6 +171,7 @@ struct HeadWs {
   float *tqkv, *L, *av, *ty, *thdn, *tw, *c2, *e1;
   float *p2buf;                         // post-norm2 rows kept for the FFN residual (slot_post_kernel)
   float *ffn_part;                      // [F/128][R][256] lin2 partials of the spread FFN (slot_ffn_kernel)
+  uint8_t *opx;                         // [T][106496] operand image of the slot clusters (slot_cl.cuh)
   float *pos[SLOTVPS_MAX_LEVELS];       // generated sine embeddings (pos_mode 2)
   float *ybuf;                          // coarse conv_trans partial [T][256][P/4]
   float *splitk;                        // split-K partials of the long-K linears [4][R][256]
@@ -210,6 +211,7 @@ static size_t head_ws_layout(const slotvps_head_desc* d, void* base, size_t cap,
   w.tw = a.take<float>((size_t)R * 2 * C); w.c2 = a.take<float>((size_t)R * C); w.e1 = a.take<float>((size_t)R * C);
   w.p2buf = a.take<float>((size_t)R * C);
   w.ffn_part = a.take<float>((size_t)(max(d->dim_feedforward, d->temporal_dim_feedforward) / 128 + 1) * R * C);
+  w.opx = a.take<uint8_t>((size_t)T * slot::ACT_BYTES);
   for (int l = 0; l < SLOTVPS_MAX_LEVELS; ++l)
     w.pos[l] = (d->pos_mode == 2 && l < d->n_levels) ? a.take<float>((size_t)C * d->h[l] * d->w[l]) : nullptr;
   w.ybuf = a.take<float>((size_t)T * C * (Pmax / 4 + 1));
@@ -457,7 +459,7 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     pp.dbg = getenv("SLOTVPS_SLOT_DEBUG") ? atoi(getenv("SLOTVPS_SLOT_DEBUG")) : 0;
     pp.out_b = sp.out_proj_b; pp.n1_w = sp.norm1_w; pp.n1_b = sp.norm1_b; pp.q_b = sp.to_q_b;
     pp.nq_w = sp.nq_w; pp.nq_b = sp.nq_b; pp.nk_w = sp.nk_w; pp.nk_b = sp.nk_b; pp.bk_c = ps.bk_c;
-    pp.p = w.p; pp.G = w.G; pp.g0 = w.g0; pp.g1 = w.g1; pp.gplanes = px.tc.gplanes;
+    pp.p = w.p; pp.G = w.G; pp.g0 = w.g0; pp.g1 = w.g1; pp.gplanes = px.tc.gplanes; pp.opx = w.opx;
     SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_pre_cl, slot::cl::SMEM));
     slot::cl::slot_pre_cl<<<grid_cl, slot::THREADS, slot::cl::SMEM, s>>>(m_out, m_q, m_wk, pp);
     SV_CHECK_LAUNCH("slot_pre");
@@ -479,7 +481,7 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     q.N = N; q.ncls = d->num_classes;
     q.Z = w.Z; q.a0 = w.a0; q.a1 = w.a1; q.p = w.p;
     q.nv_w = sp.nv_w; q.nv_b = sp.nv_b; q.bv_c = ps.bv_c; q.no_w = sp.no_w; q.no_b = sp.no_b; q.n2_w = sp.norm2_w; q.n2_b = sp.norm2_b;
-    q.p2buf = w.p2buf;
+    q.p2buf = w.p2buf; q.opx = w.opx;
     q.tw_ln_w = ps.tw_ln_w; q.tw_ln_b = ps.tw_ln_b; q.c1_nw = sp.cls1_nw; q.c1_nb = sp.cls1_nb; q.r1_nw = sp.reg1_nw; q.r1_nb = sp.reg1_nb;
     q.logit_b = sp.logit_b;
     q.slots_out = w.slots; q.emb_out = emb_out; q.cls_out = cls_out; q.emb_fs = emb_frame_stride; q.cls_fs = cls_frame_stride;

@@ -10,8 +10,9 @@
 //   * the MMAs per layer drop to 48 x (M128 N64 K16) = 1.5 K cycles;
 //   * an epilogue thread owns ONE 16-column unit of its slot row, which stays in registers across the LayerNorm;
 //   * row statistics go CTA-local through shared memory, then across the cluster through distributed shared memory;
-//   * the normalised unit is written as fp16 hi/lo MMA operand into the ACT planes of ALL four CTAs
-//     (st.shared::cluster), so each CTA holds the full K = 256 operand of the next layer.
+//   * the normalised unit is written as fp16 hi/lo MMA operand into the CTA's own ACT planes and into an operand image in
+//     global memory; after a cluster rendezvous every CTA bulk-copies the three foreign k-subtiles from L2, so each CTA
+//     holds the full K = 256 operand of the next layer (distributed shared memory proved too slow for this: 17 B/clk).
 // Cluster-wide synchronisation uses two alternating mbarriers per CTA (64 arrivals: one elected lane per epilogue warp of
 // every CTA, release.cluster / acquire.cluster) because the TMA and MMA warps cannot take part in barrier.cluster.
 //
@@ -46,6 +47,7 @@ struct Bars {
   uint64_t dfull, aready;
   uint64_t xbar[2];                             // cluster rendezvous of the epilogue warps
   uint64_t dq[3];                               // per-layer accumulator barriers where the issuer runs ahead (slot_tqkv_cl)
+  uint64_t opfull;                              // the peers' operand slices have landed (bulk copies from the global image)
   uint32_t tmem_ptr;
 };
 
@@ -72,6 +74,13 @@ __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(tc::smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// 1-D bulk copy global -> this CTA's shared memory, completion bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifdef SLOTVPS_SLOT_PROFILE
 #define CL_MARK(i) tk[i] = clock64()
@@ -137,7 +146,8 @@ struct Ctx {
   int u;                                        // this thread's unit of the 256 columns
   uint32_t rank, nred, nx, nsync, nd;
   float2 *red, *xch;
-  uint32_t act_r[CL], xch_r[CL];                // shared::cluster addresses of every CTA's ACT / XCH base
+  uint32_t xch_r[CL];                           // shared::cluster addresses of every CTA's XCH base
+  uint8_t *smem, *gx;                           // this CTA's shared memory; the frame's operand image in global memory [2][4][104][128 B]
   // rendezvous of all epilogue warps of the cluster; also orders this CTA's earlier st.shared::cluster before the peers' reads
   __device__ __forceinline__ void xsync() {
     __syncwarp();
@@ -216,28 +226,47 @@ struct Ctx {
       if (relu) v[c] = fmaxf(v[c], 0.f);
     }
   }
-  // LayerNorm-output unit (times LSCALE) -> fp16 hi/lo operand planes of every CTA of the cluster
+  // LayerNorm-output unit (times LSCALE) -> fp16 hi/lo operand planes: this CTA's k-subtile (= its rank) in its own shared
+  // memory and in the frame's operand image in global memory, from where the peers fetch it (publish_all).  Distributed
+  // shared memory moves ~17 B/clk per SM -- writing the slice into four CTAs took 8.3 K cycles per layer -- while the L2
+  // path delivers the three foreign slices (80 KB) at the ~64 B/clk ingest rate of an SM.
   __device__ __forceinline__ void to_act_all(const float* v) const {
-    if (!e.valid) return;
-    const uint32_t off = (u >> 2) * ACT_SUB + e.r * 128;
+    if (e.r >= NR) return;
+    const uint32_t off = rank * ACT_SUB + e.r * 128;               // u >> 2 == rank
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      uint32_t hi[4], lo[4];
+      uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+      if (e.valid) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) split2(v[8 * q + 2 * k] * LSCALE, v[8 * q + 2 * k + 1] * LSCALE, hi[k], lo[k]);
-      const uint32_t phys = off + ((((u & 3) * 2 + q) ^ (e.r & 7))) * 16;
-#pragma unroll
-      for (int d = 0; d < CL; ++d) {
-        st_cl_v4(act_r[d] + phys, hi[0], hi[1], hi[2], hi[3]);
-        st_cl_v4(act_r[d] + ACT_PLANE + phys, lo[0], lo[1], lo[2], lo[3]);
+        for (int k = 0; k < 4; ++k) split2(v[8 * q + 2 * k] * LSCALE, v[8 * q + 2 * k + 1] * LSCALE, hi[k], lo[k]);
       }
+      const uint32_t phys = off + ((((u & 3) * 2 + q) ^ (e.r & 7))) * 16;
+      const uint4 h4 = make_uint4(hi[0], hi[1], hi[2], hi[3]), l4 = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<uint4*>(smem + OFF_ACT + phys) = h4;
+      *reinterpret_cast<uint4*>(smem + OFF_ACT + ACT_PLANE + phys) = l4;
+      *reinterpret_cast<uint4*>(gx + phys) = h4;
+      *reinterpret_cast<uint4*>(gx + ACT_PLANE + phys) = l4;
     }
   }
-  // operand written everywhere -> every CTA's MMA issuer may go
-  __device__ __forceinline__ void publish_all() { xsync(); publish(); }
+  // own slice written -> rendezvous -> fetch the peers' slices; the MMA issuer waits for aready and opfull
+  __device__ __forceinline__ void publish_all() {
+    fence_proxy_async_all();                                       // generic writes (shared and global) before async-proxy reads
+    xsync();
+    if (threadIdx.x == 64) {
+      fence_proxy_async_all();
+      tc::mbar_expect_tx(&b->opfull, 6 * ACT_SUB);
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks)
+          if (ks != rank) bulk_g2s(smem + OFF_ACT + pl * ACT_PLANE + ks * ACT_SUB, gx + pl * ACT_PLANE + ks * ACT_SUB, ACT_SUB, &b->opfull);
+    }
+    tc::tc_fence_before();
+    tc::mbar_arrive(&b->aready);
+  }
 };
 
-__device__ __forceinline__ Ctx make_ctx(uint8_t* smem, Bars* b, uint32_t tmem_base, uint32_t rank, int N) {
+__device__ __forceinline__ Ctx make_ctx(uint8_t* smem, Bars* b, uint32_t tmem_base, uint32_t rank, int N, uint8_t* gx) {
   Ctx c;
   const int we = (threadIdx.x >> 5) - 2;
   c.b = b; c.rank = rank; c.nred = 0; c.nx = 0; c.nsync = 0; c.nd = 0;
@@ -249,10 +278,8 @@ __device__ __forceinline__ Ctx make_ctx(uint8_t* smem, Bars* b, uint32_t tmem_ba
   c.red = reinterpret_cast<float2*>(smem + OFF_RED);
   c.xch = reinterpret_cast<float2*>(smem + OFF_XCH);
 #pragma unroll
-  for (uint32_t d = 0; d < CL; ++d) {
-    c.act_r[d] = mapa(tc::smem_u32(smem + OFF_ACT), d);
-    c.xch_r[d] = mapa(tc::smem_u32(smem + OFF_XCH), d);
-  }
+  for (uint32_t d = 0; d < CL; ++d) c.xch_r[d] = mapa(tc::smem_u32(smem + OFF_XCH), d);
+  c.smem = smem; c.gx = gx;
   return c;
 }
 
@@ -263,6 +290,7 @@ __device__ __forceinline__ uint32_t prologue(Bars* b, int warp, uint32_t tmem_co
     tc::mbar_init(&b->dfull, 1); tc::mbar_init(&b->aready, EPI_THREADS);
     tc::mbar_init(&b->xbar[0], EPI_WARPS * CL); tc::mbar_init(&b->xbar[1], EPI_WARPS * CL);
     for (int i = 0; i < 3; ++i) tc::mbar_init(&b->dq[i], 1);
+    tc::mbar_init(&b->opfull, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) { tc::tmem_alloc(&b->tmem_ptr, tmem_cols); tc::tmem_relinquish(); }
@@ -306,13 +334,14 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
       const uint32_t act = tc::smem_u32(smem + OFF_ACT);
       for (int g = 0; g < 3; ++g) {
         tc::mbar_wait(&b->aready, g & 1);
+        if (g > 0) tc::mbar_wait(&b->opfull, (g - 1) & 1);        // the peers' slices of the LayerNorm-output operand
         tc::tc_fence_after();
         mma_slice(smem, b, it, tmem_base, act, IDESC64);
         tc::umma_commit(&b->dfull);
       }
     }
   } else {
-    Ctx c = make_ctx(smem, b, tmem_base, rank, N);
+    Ctx c = make_ctx(smem, b, tmem_base, rank, N, P.opx + (long)t * ACT_BYTES);
     Epi& e = c.e;
     const int u = c.u;
     const long fbase = (long)t * N * C;
@@ -373,9 +402,9 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
       }
     }
     c.to_act_all(v);
-    c.row_total(s0, s1, s0, s1);                                   // (its rendezvous also covers the operand stores above)
+    c.row_total(s0, s1, s0, s1);
     if (e.valid && e.qt == 0 && rank == 0) { P.g0[(long)t * N + e.r] = s0; P.g1[(long)t * N + e.r] = s1; }
-    c.publish();
+    c.publish_all();
     CL_MARK(8);
     // ---- (3) G = qt . Wk_c -> fp32 + fp16 hi/lo planes (the B operand of attn_tc's S product) ----
     c.wait_d();
@@ -444,7 +473,7 @@ slot_post_cl(const __grid_constant__ CUtensorMap m_wv, const PostParams P) {
       tc::umma_commit(&b->dfull);
     }
   } else {
-    Ctx c = make_ctx(smem, b, tmem_base, rank, N);
+    Ctx c = make_ctx(smem, b, tmem_base, rank, N, nullptr);
     Epi& e = c.e;
     const int u = c.u;
     const long fbase = (long)t * N * C;
@@ -503,7 +532,12 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
     if (lane == 0) {
       uint32_t it = 0, na = 0;
       const uint32_t act = tc::smem_u32(smem + OFF_ACT);
-      auto wait_act = [&]() { tc::mbar_wait(&b->aready, na & 1); ++na; tc::tc_fence_after(); };
+      auto wait_act = [&]() {                                       // after the first: also the peers' operand slices
+        tc::mbar_wait(&b->aready, na & 1);
+        if (na > 0) tc::mbar_wait(&b->opfull, (na - 1) & 1);
+        ++na;
+        tc::tc_fence_after();
+      };
       wait_act();
       mma_slice(smem, b, it, tmem_base, act, IDESC64);                            // cls0
       mma_slice(smem, b, it, tmem_base + 64, act, IDESC64);                       // reg0
@@ -519,7 +553,7 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
       tc::umma_commit(&b->dfull);
     }
   } else {
-    Ctx c = make_ctx(smem, b, tmem_base, rank, N);
+    Ctx c = make_ctx(smem, b, tmem_base, rank, N, P.opx + (long)t * ACT_BYTES);
     Epi& e = c.e;
     const int u = c.u;
     const long fbase = (long)t * N * C;
@@ -601,7 +635,7 @@ slot_tqkv_cl(const __grid_constant__ CUtensorMap m_qkv, const TqkvParams P) {
       }
     }
   } else {
-    Ctx c = make_ctx(smem, b, tmem_base, rank, N);
+    Ctx c = make_ctx(smem, b, tmem_base, rank, N, nullptr);
     Epi& e = c.e;
     const int u = c.u;
     float* rsc = reinterpret_cast<float*>(smem + OFF_RSC);

@@ -257,6 +257,7 @@ struct PreParams {
   const float *out_b, *n1_w, *n1_b, *q_b, *nq_w, *nq_b, *nk_w, *nk_b, *bk_c;
   float *p, *G, *g0, *g1;                       // [T][N][256], [T][N][256], [T][N], [T][N]
   __half* gplanes;                              // [T][2][104][256] hi / lo planes of G (rows >= N zero)
+  uint8_t* opx;                                 // [T][106496] operand image exchanged between the CTAs of a frame's cluster
 };
 
 
@@ -271,6 +272,7 @@ struct PostParams {
   const float *tw_ln_w, *tw_ln_b, *c1_nw, *c1_nb, *r1_nw, *r1_nb, *logit_b;
   float *slots_out, *emb_out, *cls_out;
   long emb_fs, cls_fs;                          // frame strides of emb_out / cls_out
+  uint8_t* opx;                                 // [T][106496] operand image exchanged between the CTAs of a frame's cluster
 };
 
 // Exact (erf) GELU through the complementary error function: gelu(x) = x/2 * erfc(-x/sqrt(2)), with erfc(z >= 0) from the
