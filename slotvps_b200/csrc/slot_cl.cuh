@@ -13,8 +13,8 @@
 //   * the normalised unit is written as fp16 hi/lo MMA operand into the CTA's own ACT planes and into an operand image in
 //     global memory; after a cluster rendezvous every CTA bulk-copies the three foreign k-subtiles from L2, so each CTA
 //     holds the full K = 256 operand of the next layer (distributed shared memory proved too slow for this: 17 B/clk).
-// Cluster-wide synchronisation uses two alternating mbarriers per CTA (64 arrivals: one elected lane per epilogue warp of
-// every CTA, release.cluster / acquire.cluster) because the TMA and MMA warps cannot take part in barrier.cluster.
+// Cluster-wide synchronisation uses two alternating mbarriers per CTA (a CTA-local named barrier, then one release.cluster
+// arrival per CTA on every CTA's barrier, acquire.cluster waits) because the TMA and MMA warps cannot take part in barrier.cluster.
 //
 //   slot_pre_cl     out_proj + residual + norm1 -> to_q + norm_q -> G = (q * gamma_k) Wk_c, g0, g1, fp16 planes of G
 //   slot_post_cl    Wv_c Z, norm_v / norm1 / ReLU, residual, norm2 -> p2      (the FFN runs in slot_ffn_kernel)
@@ -148,11 +148,13 @@ struct Ctx {
   float2 *red, *xch;
   uint32_t xch_r[CL];                           // shared::cluster addresses of every CTA's XCH base
   uint8_t *smem, *gx;                           // this CTA's shared memory; the frame's operand image in global memory [2][4][104][128 B]
-  // rendezvous of all epilogue warps of the cluster; also orders this CTA's earlier st.shared::cluster before the peers' reads
+  // rendezvous of the epilogue warps of the whole cluster; also orders this CTA's earlier shared::cluster / global stores
+  // before the peers' reads.  CTA-local named barrier first, then ONE thread arrives on the barrier of every CTA: with one
+  // arrival per warp (64 remote atomics on each barrier) a rendezvous cost 2-2.5 K cycles.
   __device__ __forceinline__ void xsync() {
-    __syncwarp();
+    e.sync();
     uint64_t* bar = &b->xbar[nsync & 1];
-    if (e.lane == 0) {
+    if (threadIdx.x == 64) {
 #pragma unroll
       for (uint32_t d = 0; d < CL; ++d) tc::mbar_arrive_remote(bar, d);
     }
@@ -249,9 +251,7 @@ struct Ctx {
     }
   }
   // own slice written -> rendezvous -> fetch the peers' slices; the MMA issuer waits for aready and opfull
-  __device__ __forceinline__ void publish_all() {
-    fence_proxy_async_all();                                       // generic writes (shared and global) before async-proxy reads
-    xsync();
+  __device__ __forceinline__ void publish_fetch() {
     if (threadIdx.x == 64) {
       fence_proxy_async_all();
       tc::mbar_expect_tx(&b->opfull, 6 * ACT_SUB);
@@ -263,6 +263,11 @@ struct Ctx {
     }
     tc::tc_fence_before();
     tc::mbar_arrive(&b->aready);
+  }
+  __device__ __forceinline__ void publish_all() {
+    fence_proxy_async_all();                                       // generic writes (shared and global) before async-proxy reads
+    xsync();
+    publish_fetch();
   }
 };
 
@@ -288,7 +293,7 @@ __device__ __forceinline__ uint32_t prologue(Bars* b, int warp, uint32_t tmem_co
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSL; ++i) { tc::mbar_init(&b->full[i], 1); tc::mbar_init(&b->empty[i], 1); }
     tc::mbar_init(&b->dfull, 1); tc::mbar_init(&b->aready, EPI_THREADS);
-    tc::mbar_init(&b->xbar[0], EPI_WARPS * CL); tc::mbar_init(&b->xbar[1], EPI_WARPS * CL);
+    tc::mbar_init(&b->xbar[0], CL); tc::mbar_init(&b->xbar[1], CL);
     for (int i = 0; i < 3; ++i) tc::mbar_init(&b->dq[i], 1);
     tc::mbar_init(&b->opfull, 1);
     tc::fence_barrier_init();
@@ -346,7 +351,7 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
     const int u = c.u;
     const long fbase = (long)t * N * C;
 #ifdef SLOTVPS_SLOT_PROFILE
-    long long tk[12];
+    long long tk[20];
 #endif
     CL_MARK(0);
     // A operand of the first GEMM: the self-attention output rows (every CTA builds the full K = 256 operand)
@@ -388,7 +393,9 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
     c.ld(0, v, INV_L);
 #pragma unroll
     for (int k = 0; k < 16; ++k) v[k] += add[k];
+    CL_MARK(11);
     c.layer_norm(v, P.nq_w, P.nq_b, false);
+    CL_MARK(12);
     float s0 = 0.f, s1 = 0.f;
     {
       float gk[16], bk[16], bc[16];
@@ -401,10 +408,17 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
         v[k] = tv;
       }
     }
+    CL_MARK(13);
     c.to_act_all(v);
+    CL_MARK(14);
     c.row_total(s0, s1, s0, s1);
     if (e.valid && e.qt == 0 && rank == 0) { P.g0[(long)t * N + e.r] = s0; P.g1[(long)t * N + e.r] = s1; }
-    c.publish_all();
+    CL_MARK(15);
+    fence_proxy_async_all();
+    CL_MARK(16);
+    c.xsync();
+    CL_MARK(17);
+    c.publish_fetch();
     CL_MARK(8);
     // ---- (3) G = qt . Wk_c -> fp32 + fp16 hi/lo planes (the B operand of attn_tc's S product) ----
     c.wait_d();
@@ -443,6 +457,9 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
     if (P.dbg && blockIdx.x == 0 && threadIdx.x == 64)
       printf("slot_pre_cl cycles: load %lld | prefetch %lld | wait1 %lld | ld+LN1 %lld | emit1 %lld | sync O %lld | wait2 %lld | epi2 %lld | wait3 %lld | epi3 %lld\n",
              tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[7] - tk[6], tk[8] - tk[7], tk[9] - tk[8], tk[10] - tk[9]);
+    if (P.dbg && blockIdx.x == 0 && threadIdx.x == 64)
+      printf("   epi2: ld %lld | layer_norm %lld | gk math %lld | to_act %lld | row_total %lld | fence %lld | xsync %lld | fetch+arrive %lld\n",
+             tk[11] - tk[7], tk[12] - tk[11], tk[13] - tk[12], tk[14] - tk[13], tk[15] - tk[14], tk[16] - tk[15], tk[17] - tk[16], tk[8] - tk[17]);
 #endif
   }
   epilogue_exit(tmem_base, warp, 256);

@@ -156,26 +156,37 @@ __device__ __forceinline__ float row_scale(float m, float& inv) {
 // fp32 rows [N][256] of one frame -> ACT operand planes, each row times its own power of two (inverse -> rsc[row]);
 // cooperative over the epilogue warps (coalesced row reads, a warp owns a row at a time)
 __device__ __forceinline__ void load_rows_to_act(uint8_t* smem, const float* __restrict__ src, int N, int we, int lane, float* rsc) {
-  for (int row = we; row < N; row += EPI_WARPS) {
-    float4 a[2];
+  // four rows per pass: eight 16-byte loads in flight per lane before the first cross-lane maximum
+#pragma unroll 1
+  for (int row0 = we; row0 < N; row0 += 4 * EPI_WARPS) {
+    float4 a[4][2];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) a[half] = __ldg(reinterpret_cast<const float4*>(src + (long)row * C + half * 128 + lane * 4));
-    float m = fmaxf(fmaxf(fmaxf(fabsf(a[0].x), fabsf(a[0].y)), fmaxf(fabsf(a[0].z), fabsf(a[0].w))),
-                    fmaxf(fmaxf(fabsf(a[1].x), fabsf(a[1].y)), fmaxf(fabsf(a[1].z), fabsf(a[1].w))));
+    for (int i = 0; i < 4; ++i) {
+      const int row = min(row0 + i * EPI_WARPS, N - 1);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float inv;
-    const float sc = row_scale(m, inv);
-    if (lane == 0) rsc[row] = inv;
+      for (int half = 0; half < 2; ++half) a[i][half] = __ldg(reinterpret_cast<const float4*>(src + (long)row * C + half * 128 + lane * 4));
+    }
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int col = half * 128 + lane * 4;
-      uint32_t h0, l0, h1, l1;
-      split2(a[half].x * sc, a[half].y * sc, h0, l0); split2(a[half].z * sc, a[half].w * sc, h1, l1);
-      const int ks = col >> 6, cidx = (col & 63) >> 3;
-      uint8_t* dst = smem + OFF_ACT + ks * ACT_SUB + row * 128 + ((cidx ^ (row & 7)) * 16) + (col & 7) * 2;
-      *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
-      *reinterpret_cast<uint2*>(dst + ACT_PLANE) = make_uint2(l0, l1);
+    for (int i = 0; i < 4; ++i) {
+      const int row = row0 + i * EPI_WARPS;
+      if (row >= N) break;
+      float m = fmaxf(fmaxf(fmaxf(fabsf(a[i][0].x), fabsf(a[i][0].y)), fmaxf(fabsf(a[i][0].z), fabsf(a[i][0].w))),
+                      fmaxf(fmaxf(fabsf(a[i][1].x), fabsf(a[i][1].y)), fmaxf(fabsf(a[i][1].z), fabsf(a[i][1].w))));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float inv;
+      const float sc = row_scale(m, inv);
+      if (lane == 0) rsc[row] = inv;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int col = half * 128 + lane * 4;
+        uint32_t h0, l0, h1, l1;
+        split2(a[i][half].x * sc, a[i][half].y * sc, h0, l0); split2(a[i][half].z * sc, a[i][half].w * sc, h1, l1);
+        const int ks = col >> 6, cidx = (col & 63) >> 3;
+        uint8_t* dst = smem + OFF_ACT + ks * ACT_SUB + row * 128 + ((cidx ^ (row & 7)) * 16) + (col & 7) * 2;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(dst + ACT_PLANE) = make_uint2(l0, l1);
+      }
     }
   }
 }
