@@ -211,7 +211,7 @@ static size_t head_ws_layout(const slotvps_head_desc* d, void* base, size_t cap,
   w.tw = a.take<float>((size_t)R * 2 * C); w.c2 = a.take<float>((size_t)R * C); w.e1 = a.take<float>((size_t)R * C);
   w.p2buf = a.take<float>((size_t)R * C);
   w.ffn_part = a.take<float>((size_t)(max(d->dim_feedforward, d->temporal_dim_feedforward) / 128 + 1) * R * C);
-  w.opx = a.take<uint8_t>((size_t)T * slot::ACT_BYTES);
+  w.opx = a.take<uint8_t>((size_t)T * slot::slot_groups(d->n_slots) * slot::ACT_BYTES);
   for (int l = 0; l < SLOTVPS_MAX_LEVELS; ++l)
     w.pos[l] = (d->pos_mode == 2 && l < d->n_levels) ? a.take<float>((size_t)C * d->h[l] * d->w[l]) : nullptr;
   w.ybuf = a.take<float>((size_t)T * C * (Pmax / 4 + 1));
@@ -397,15 +397,15 @@ static int video_retriever(const slotvps_head_desc* d, const slotvps_stage_param
 // The same block on the slot kernels: q|k|v projections + LayerNorms on the frame clusters (slot_cl.cuh), the R x R attention
 // and its two LayerNorms in two fp32 launches (temporal.cuh), the FFN over (frame, hidden chunk) CTAs + reduction/norm3.
 static int video_retriever_tc(const slotvps_head_desc* d, const slotvps_stage_params& sp, const PreparedStage& ps, const HeadWs& w, cudaStream_t s) {
-  const int T = d->n_frames, N = d->n_slots, R = T * N, TF = d->temporal_dim_feedforward;
+  const int T = d->n_frames, N = d->n_slots, R = T * N, TF = d->temporal_dim_feedforward, G = slot::slot_groups(N);
   SV_REQUIRE(sp.tq_to_q_w != nullptr, "temporal stage without temporal_query_head parameters");
   {
     CUtensorMap m_qkv;
     SV_TRY(slot::cl::slot_wmap64(&m_qkv, ps.stc.tqkv, 3 * C, C));
     slot::cl::TqkvParams tp;
-    tp.N = N; tp.f_in = w.f; tp.bias = ps.tq_qkv_b; tp.ln_w = ps.tq_ln_w; tp.ln_b = ps.tq_ln_b; tp.tqkv = w.tqkv;
+    tp.N = N; tp.G = G; tp.f_in = w.f; tp.bias = ps.tq_qkv_b; tp.ln_w = ps.tq_ln_w; tp.ln_b = ps.tq_ln_b; tp.tqkv = w.tqkv;
     SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_tqkv_cl, slot::cl::SMEM));
-    slot::cl::slot_tqkv_cl<<<T * slot::cl::CL, slot::THREADS, slot::cl::SMEM, s>>>(m_qkv, tp);
+    slot::cl::slot_tqkv_cl<<<T * G * slot::cl::CL, slot::THREADS, slot::cl::SMEM, s>>>(m_qkv, tp);
     SV_CHECK_LAUNCH("slot_tqkv");
   }
   temporal::tscore_kernel<<<ceil_div(R, temporal::KEYS), temporal::TS_WARPS * 32, 0, s>>>(w.tqkv, w.L, R);
@@ -419,9 +419,9 @@ static int video_retriever_tc(const slotvps_head_desc* d, const slotvps_stage_pa
     SV_TRY(slot::slot_wmap(&m_l1, ps.stc.tlin1, TF, C));
     SV_TRY(slot::slot_wmap(&m_l2, ps.stc.tlin2, C, TF));
     slot::FfnParams fp;
-    fp.N = N; fp.act = temporal_ffn_act_of(d); fp.p2 = w.ty; fp.b1 = sp.tq_lin1_b; fp.part = w.ffn_part; fp.part_stride = (long)R * C;
+    fp.N = N; fp.G = G; fp.act = temporal_ffn_act_of(d); fp.p2 = w.ty; fp.b1 = sp.tq_lin1_b; fp.part = w.ffn_part; fp.part_stride = (long)R * C;
     SV_TRY(ensure_dyn_smem((const void*)slot::slot_ffn_kernel, slot::SMEM_BYTES));
-    slot::slot_ffn_kernel<<<dim3(T, TF / 128), slot::THREADS, slot::SMEM_BYTES, s>>>(m_l1, m_l2, fp, TF);
+    slot::slot_ffn_kernel<<<dim3(T * G, TF / 128), slot::THREADS, slot::SMEM_BYTES, s>>>(m_l1, m_l2, fp, TF);
     SV_CHECK_LAUNCH("slot_ffn");
     slot::slot_norm3_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.ffn_part, (long)R * C, TF / 128, w.ty, sp.tq_lin2_b, sp.tq_norm3_w, sp.tq_norm3_b,
                                                            w.f, w.f2, R);                        // X + LN3(...)  (:317)
@@ -438,7 +438,8 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
                         const StagePix& px, const float* x, long x_bs, const float* pos, long pos_bs, int h, int wd, bool temporal,
                         float* cls_out, long cls_frame_stride, float* emb_out, long emb_frame_stride, cudaStream_t s) {
   const int T = d->n_frames, N = d->n_slots, R = T * N, P = h * wd, F = d->dim_feedforward;
-  const int grid_cl = T * slot::cl::CL;                   // one cluster of four CTAs per frame (slot_cl.cuh)
+  const int G = slot::slot_groups(N);                     // row groups of <= 104 slots per frame
+  const int grid_cl = T * G * slot::cl::CL;               // one cluster of four CTAs per (frame, group) (slot_cl.cuh)
   // (1) slot self-attention core (:346-352): in_proj + 8-head attention on the generic kernels
   SV_TRY(linear_fast(w.slots, sp.in_proj_w, sp.in_proj_b, w.qkv, R, C, 3 * C, 0, nullptr, s));
   {
@@ -455,17 +456,17 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     SV_TRY(slot::cl::slot_wmap64(&m_wk, ps.stc.wkT, C, C));
     slot::PreParams pp;
     memset(&pp, 0, sizeof(pp));
-    pp.N = N; pp.mo = w.mo; pp.slots = w.slots;
+    pp.N = N; pp.G = G; pp.mo = w.mo; pp.slots = w.slots;
     pp.dbg = getenv("SLOTVPS_SLOT_DEBUG") ? atoi(getenv("SLOTVPS_SLOT_DEBUG")) : 0;
     pp.out_b = sp.out_proj_b; pp.n1_w = sp.norm1_w; pp.n1_b = sp.norm1_b; pp.q_b = sp.to_q_b;
     pp.nq_w = sp.nq_w; pp.nq_b = sp.nq_b; pp.nk_w = sp.nk_w; pp.nk_b = sp.nk_b; pp.bk_c = ps.bk_c;
-    pp.p = w.p; pp.G = w.G; pp.g0 = w.g0; pp.g1 = w.g1; pp.gplanes = px.tc.gplanes; pp.opx = w.opx;
+    pp.p = w.p; pp.Gout = w.G; pp.g0 = w.g0; pp.g1 = w.g1; pp.gplanes = G == 1 ? px.tc.gplanes : nullptr; pp.opx = w.opx;
     SV_TRY(ensure_dyn_smem((const void*)slot::cl::slot_pre_cl, slot::cl::SMEM));
     slot::cl::slot_pre_cl<<<grid_cl, slot::THREADS, slot::cl::SMEM, s>>>(m_out, m_q, m_wk, pp);
     SV_CHECK_LAUNCH("slot_pre");
   }
   // (3) pixel side: Z, a0, a1
-  SV_TRY(pixel_attention(x, x_bs, pos, pos_bs, ps, w, px, T, N, P, true, s, true));
+  SV_TRY(pixel_attention(x, x_bs, pos, pos_bs, ps, w, px, T, N, P, true, s, G == 1));
   // (4..7) value projection + norms, FFN, norm3 [, Video Retriever], towers
   {
     CUtensorMap m_wv, m_l1, m_l2, m_tw, m_c1, m_r1, m_lg;
@@ -478,7 +479,7 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     SV_TRY(slot::cl::slot_wmap64(&m_lg, ps.stc.logit, d->num_classes, C));
     slot::PostParams q;
     memset(&q, 0, sizeof(q));
-    q.N = N; q.ncls = d->num_classes;
+    q.N = N; q.G = G; q.ncls = d->num_classes;
     q.Z = w.Z; q.a0 = w.a0; q.a1 = w.a1; q.p = w.p;
     q.nv_w = sp.nv_w; q.nv_b = sp.nv_b; q.bv_c = ps.bv_c; q.no_w = sp.no_w; q.no_b = sp.no_b; q.n2_w = sp.norm2_w; q.n2_b = sp.norm2_b;
     q.p2buf = w.p2buf; q.opx = w.opx;
@@ -490,9 +491,9 @@ static int run_stage_tc(const slotvps_head_desc* d, const slotvps_stage_params& 
     SV_CHECK_LAUNCH("slot_post");
     // FFN over (frame, hidden chunk) CTAs, then the chunk-ordered reduction + residual + norm3
     slot::FfnParams fp;
-    fp.N = N; fp.act = ffn_act_of(d); fp.p2 = w.p2buf; fp.b1 = sp.lin1_b; fp.part = w.ffn_part; fp.part_stride = (long)R * C;
+    fp.N = N; fp.G = G; fp.act = ffn_act_of(d); fp.p2 = w.p2buf; fp.b1 = sp.lin1_b; fp.part = w.ffn_part; fp.part_stride = (long)R * C;
     SV_TRY(ensure_dyn_smem((const void*)slot::slot_ffn_kernel, slot::SMEM_BYTES));
-    slot::slot_ffn_kernel<<<dim3(T, F / 128), slot::THREADS, slot::SMEM_BYTES, s>>>(m_l1, m_l2, fp, F);
+    slot::slot_ffn_kernel<<<dim3(T * G, F / 128), slot::THREADS, slot::SMEM_BYTES, s>>>(m_l1, m_l2, fp, F);
     SV_CHECK_LAUNCH("slot_ffn");
     slot::slot_norm3_kernel<<<ceil_div(R, 8), 256, 0, s>>>(w.ffn_part, (long)R * C, F / 128, w.p2buf, sp.lin2_b, sp.norm3_w, sp.norm3_b, nullptr, w.f, R);
     SV_CHECK_LAUNCH("slot_norm3");

@@ -320,7 +320,9 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
   const uint32_t raw = tc::smem_u32(raw_smem);
   uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
   Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x / CL, N = P.N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, vf = blockIdx.x / CL;
+  const RowGroup rg = row_group(vf, P.N, P.G);
+  const int t = rg.t, N = rg.n;                 // frame; slot rows of this cluster's group
   const uint32_t rank = tc::cluster_ctarank();
   if (threadIdx.x == 0) { tc::tma_prefetch_desc(&m_out); tc::tma_prefetch_desc(&m_q); tc::tma_prefetch_desc(&m_wk); }
   const uint32_t tmem_base = prologue(b, warp, 256);
@@ -346,10 +348,10 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
       }
     }
   } else {
-    Ctx c = make_ctx(smem, b, tmem_base, rank, N, P.opx + (long)t * ACT_BYTES);
+    Ctx c = make_ctx(smem, b, tmem_base, rank, N, P.opx + (long)vf * ACT_BYTES);
     Epi& e = c.e;
     const int u = c.u;
-    const long fbase = (long)t * N * C;
+    const long fbase = rg.rb * C;
 #ifdef SLOTVPS_SLOT_PROFILE
     long long tk[20];
 #endif
@@ -412,7 +414,7 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
     c.to_act_all(v);
     CL_MARK(14);
     c.row_total(s0, s1, s0, s1);
-    if (e.valid && e.qt == 0 && rank == 0) { P.g0[(long)t * N + e.r] = s0; P.g1[(long)t * N + e.r] = s1; }
+    if (e.valid && e.qt == 0 && rank == 0) { P.g0[rg.rb + e.r] = s0; P.g1[rg.rb + e.r] = s1; }
     CL_MARK(15);
     fence_proxy_async_all();
     CL_MARK(16);
@@ -424,8 +426,8 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
     c.wait_d();
     CL_MARK(9);
     c.ld(0, v, INV_L);
-    if (P.G) e.write_rows(P.G + fbase, u, v);
-    {
+    if (P.Gout) e.write_rows(P.Gout + fbase, u, v);
+    if (P.gplanes) {
       uint32_t* stw = reinterpret_cast<uint32_t*>(e.stg);           // staging as [2 planes][32 rows][10 words] (8 used)
       uint32_t hi[8], lo[8];
 #pragma unroll
@@ -472,7 +474,9 @@ slot_post_cl(const __grid_constant__ CUtensorMap m_wv, const PostParams P) {
   const uint32_t raw = tc::smem_u32(raw_smem);
   uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
   Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x / CL, N = P.N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, vf = blockIdx.x / CL;
+  const RowGroup rg = row_group(vf, P.N, P.G);
+  const int t = rg.t, N = rg.n;                 // frame; slot rows of this cluster's group
   const uint32_t rank = tc::cluster_ctarank();
   if (threadIdx.x == 0) tc::tma_prefetch_desc(&m_wv);
   const uint32_t tmem_base = prologue(b, warp, 256);
@@ -493,14 +497,14 @@ slot_post_cl(const __grid_constant__ CUtensorMap m_wv, const PostParams P) {
     Ctx c = make_ctx(smem, b, tmem_base, rank, N, nullptr);
     Epi& e = c.e;
     const int u = c.u;
-    const long fbase = (long)t * N * C;
+    const long fbase = rg.rb * C;
     float* rsc = reinterpret_cast<float*>(smem + OFF_RSC);
     load_rows_to_act(smem, P.Z + fbase, N, warp - 2, lane, rsc);
     c.publish();
     // ---- value projection of the pixel-reduced slots, norm_v / norm1 / ReLU, residual, norm2 (:456-459, 374-376) ----
     float v[16], pp[16];
     e.read_rows(P.p + fbase, u, pp);
-    const float a0r = e.valid ? P.a0[(long)t * N + e.r] : 0.f, a1r = e.valid ? P.a1[(long)t * N + e.r] : 0.f;
+    const float a0r = e.valid ? P.a0[rg.rb + e.r] : 0.f, a1r = e.valid ? P.a1[rg.rb + e.r] : 0.f;
     prefetch_l1(P.nv_w + 16 * u); prefetch_l1(P.nv_b + 16 * u); prefetch_l1(P.bv_c + 16 * u);
     prefetch_l1(P.no_w + 16 * u); prefetch_l1(P.no_b + 16 * u); prefetch_l1(P.n2_w + 16 * u); prefetch_l1(P.n2_b + 16 * u);
     e.sync();                                                      // rsc is complete
@@ -531,7 +535,9 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
   const uint32_t raw = tc::smem_u32(raw_smem);
   uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
   Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x / CL, N = P.N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, vf = blockIdx.x / CL;
+  const RowGroup rg = row_group(vf, P.N, P.G);
+  const int t = rg.t, N = rg.n;                 // frame; slot rows of this cluster's group
   const uint32_t rank = tc::cluster_ctarank();
   if (threadIdx.x == 0) { tc::tma_prefetch_desc(&m_tw); tc::tma_prefetch_desc(&m_c1); tc::tma_prefetch_desc(&m_lg); tc::tma_prefetch_desc(&m_r1); }
   const uint32_t tmem_base = prologue(b, warp, 256);
@@ -570,10 +576,10 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
       tc::umma_commit(&b->dfull);
     }
   } else {
-    Ctx c = make_ctx(smem, b, tmem_base, rank, N, P.opx + (long)t * ACT_BYTES);
+    Ctx c = make_ctx(smem, b, tmem_base, rank, N, P.opx + (long)vf * ACT_BYTES);
     Epi& e = c.e;
     const int u = c.u;
-    const long fbase = (long)t * N * C;
+    const long fbase = rg.rb * C;
     float* rsc = reinterpret_cast<float*>(smem + OFF_RSC);
     load_rows_to_act(smem, P.f_in + fbase, N, warp - 2, lane, rsc);
     c.publish();
@@ -601,7 +607,7 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < 16; ++k) { lg[0][k] += lc[0][k]; lg[1][k] += lc[1][k]; }
       if (e.valid) {
-        float* dst = P.cls_out + (long)t * P.cls_fs + (long)e.r * P.ncls;
+        float* dst = P.cls_out + (long)t * P.cls_fs + (long)(rg.row0 + e.r) * P.ncls;
         for (int k = 0; k < P.ncls; ++k) dst[k] = lg[k >> 4][k & 15] * INV_L + __ldg(P.logit_b + k);
       }
     }
@@ -612,7 +618,7 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
     c.wait_d();
     c.ld(0, v, INV_L);
     c.layer_norm(v, P.r1_nw, P.r1_nb, true);                        // next-stage slots = this stage's embedding
-    e.write_rows(P.slots_out + fbase, u, v, P.emb_out + (long)t * P.emb_fs);
+    e.write_rows(P.slots_out + fbase, u, v, P.emb_out + (long)t * P.emb_fs + (long)rg.row0 * C);
   }
   epilogue_exit(tmem_base, warp, 256);
 }
@@ -621,7 +627,7 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
 // Video Retriever projections (:494-527): q | k | v = LN_j(f W_j^T + b_j) for the frame's slots -> tqkv rows r*3 + j.
 // The three layers share the operand, so their MMAs run back to back and no operand exchange is needed.
 struct TqkvParams {
-  int N;
+  int N, G;                                     // slots per frame, row groups per frame
   const float* f_in;                            // [T][N][256]
   const float *bias, *ln_w, *ln_b;              // [3][256] each
   float* tqkv;                                  // [T*N][3][256]
@@ -632,7 +638,9 @@ slot_tqkv_cl(const __grid_constant__ CUtensorMap m_qkv, const TqkvParams P) {
   const uint32_t raw = tc::smem_u32(raw_smem);
   uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
   Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x / CL, N = P.N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, vf = blockIdx.x / CL;
+  const RowGroup rg = row_group(vf, P.N, P.G);
+  const int t = rg.t, N = rg.n;                 // frame; slot rows of this cluster's group
   const uint32_t rank = tc::cluster_ctarank();
   if (threadIdx.x == 0) tc::tma_prefetch_desc(&m_qkv);
   const uint32_t tmem_base = prologue(b, warp, 512);
@@ -656,7 +664,7 @@ slot_tqkv_cl(const __grid_constant__ CUtensorMap m_qkv, const TqkvParams P) {
     Epi& e = c.e;
     const int u = c.u;
     float* rsc = reinterpret_cast<float*>(smem + OFF_RSC);
-    load_rows_to_act(smem, P.f_in + (long)t * N * C, N, warp - 2, lane, rsc);
+    load_rows_to_act(smem, P.f_in + rg.rb * C, N, warp - 2, lane, rsc);
     c.publish();
     for (int j = 0; j < 3; ++j) { prefetch_l1(P.bias + j * C + 16 * u); prefetch_l1(P.ln_w + j * C + 16 * u); prefetch_l1(P.ln_b + j * C + 16 * u); }
     e.sync();                                                      // rsc is complete
@@ -671,7 +679,7 @@ slot_tqkv_cl(const __grid_constant__ CUtensorMap m_qkv, const TqkvParams P) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) v[k] += bb[k];
       c.layer_norm(v, P.ln_w + j * C, P.ln_b + j * C, false);
-      e.write_rows(P.tqkv + ((long)t * N * 3 + j) * C, u, v, nullptr, 3 * C);
+      e.write_rows(P.tqkv + (rg.rb * 3 + j) * C, u, v, nullptr, 3 * C);
     }
   }
   epilogue_exit(tmem_base, warp, 512);

@@ -51,6 +51,17 @@ constexpr int OFF_RSC = OFF_MISC + 512;        // [128] floats: inverse row scal
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(OFF_HB % 1024 == 0 && OFF_RING % 1024 == 0 && ACT_SUB % 1024 == 0, "swizzle atoms");
 
+// A frame's N slots are processed as G = ceil(N / 104) groups of per = ceil(N / G) consecutive rows (the last one ragged):
+// every layer of the slot update is row-wise, so a group is simply a "virtual frame" vf = t * G + g.
+struct RowGroup { int t, row0, n; long rb; };   // frame, first slot, slots in the group, first global row (t * N + row0)
+__host__ __device__ __forceinline__ RowGroup row_group(int vf, int N, int G) {
+  RowGroup r;
+  const int per = (N + G - 1) / G, g = vf % G;
+  r.t = vf / G; r.row0 = g * per; r.n = min(per, N - r.row0); r.rb = (long)r.t * N + r.row0;
+  return r;
+}
+inline int slot_groups(int N) { return (N + NR - 1) / NR; }
+
 // fp16 hi/lo weight planes of one nn.Linear for the TMA ring: [2][Opad][K], Opad = ceil(O / 128) * 128 (zero rows)
 __global__ void __launch_bounds__(256) linear_planes_kernel(const float* __restrict__ W, int O, int K, int Opad, __half* __restrict__ out) {
   const long i = (long)blockIdx.x * 256 + threadIdx.x;
@@ -263,10 +274,10 @@ __device__ __forceinline__ Epi make_epi(uint8_t* smem, uint32_t tmem_base, int N
 }
 
 struct PreParams {
-  int N, dbg;
+  int N, G, dbg;                                // slots per frame, row groups per frame (clusters per frame)
   const float *mo, *slots;                      // [T][N][256] MHA output (heads concatenated), slots entering the stage
   const float *out_b, *n1_w, *n1_b, *q_b, *nq_w, *nq_b, *nk_w, *nk_b, *bk_c;
-  float *p, *G, *g0, *g1;                       // [T][N][256], [T][N][256], [T][N], [T][N]
+  float *p, *Gout, *g0, *g1;                    // [T][N][256], [T][N][256], [T][N], [T][N]
   __half* gplanes;                              // [T][2][104][256] hi / lo planes of G (rows >= N zero)
   uint8_t* opx;                                 // [T][106496] operand image exchanged between the CTAs of a frame's cluster
 };
@@ -274,7 +285,7 @@ struct PreParams {
 
 // ---- post-attention phase -----------------------------------------------------------------------------------------
 struct PostParams {
-  int N, ncls;
+  int N, G, ncls;
   const float *Z, *a0, *a1, *p;                 // pixel-reduced slots [T][N][256], softmax mass / bias terms [T][N], residual rows
   const float *nv_w, *nv_b, *bv_c, *no_w, *no_b, *n2_w, *n2_b;
   float* p2buf;                                 // [T][N][256] post-norm2 rows (FFN input and residual)
@@ -312,7 +323,7 @@ __device__ __forceinline__ float act_fn(float x, int act) { return act == 1 ? fm
 // lin1[chunk] -> activation -> lin2[:, chunk] and writes its [N][256] partial; slot_norm3_kernel adds the partials in chunk
 // order (deterministic), the bias and the residual and applies norm3.
 struct FfnParams {
-  int N, act;
+  int N, G, act;
   const float *p2, *b1;                         // [T][N][256] post-norm2 rows, [F] lin1 bias
   float* part;                                  // [F/128][T][N][256] partial lin2 outputs
   long part_stride;                             // T * N * 256
@@ -324,7 +335,9 @@ slot_ffn_kernel(const __grid_constant__ CUtensorMap m_l1, const __grid_constant_
   const uint32_t raw = tc::smem_u32(raw_smem);
   uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
   Barriers* b = reinterpret_cast<Barriers*>(smem + OFF_MISC);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x, c = blockIdx.y, N = P.N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.y;
+  const RowGroup rg = row_group(blockIdx.x, P.N, P.G);
+  const int N = rg.n;
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&m_l1); tc::tma_prefetch_desc(&m_l2);
     for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&b->full[i], 1); tc::mbar_init(&b->empty[i], 1); }
@@ -356,7 +369,7 @@ slot_ffn_kernel(const __grid_constant__ CUtensorMap m_l1, const __grid_constant_
     }
   } else {
     Epi e = make_epi(smem, tmem_base, N);
-    const long fbase = (long)t * N * C;
+    const long fbase = rg.rb * C;
     float* rsc = reinterpret_cast<float*>(smem + OFF_RSC);
     load_rows_to_act(smem, P.p2 + fbase, N, warp - 2, lane, rsc);
     tc::tc_fence_before(); tc::fence_proxy_async(); tc::mbar_arrive(&b->aready);
@@ -465,7 +478,7 @@ inline void slot_tc_layout(Arena& a, const slotvps_head_desc* d, SlotTcWeights* 
   w->tlin1 = a.take<__half>((size_t)2 * d->temporal_dim_feedforward * C); w->tlin2 = a.take<__half>((size_t)2 * C * d->temporal_dim_feedforward);
 }
 inline bool slot_tc_supported(const slotvps_head_desc* d) {
-  return d->kernel_path == 0 && d->n_slots <= slot::NR && d->dim_feedforward % 128 == 0 && d->temporal_dim_feedforward % 128 == 0 &&
+  return d->kernel_path == 0 && d->dim_feedforward % 128 == 0 && d->temporal_dim_feedforward % 128 == 0 &&
          d->num_classes <= 32;
 }
 inline int slot_planes(const float* W, int O, int K, __half* out, cudaStream_t s) {

@@ -12,7 +12,7 @@
 namespace slotvps {
 namespace temporal {
 constexpr int KEYS = 8;                        // key columns per CTA
-constexpr int RMAX = 512;                      // slots per clip held in shared memory (T * N)
+constexpr int RMAX = 1248;                     // slots per clip held in shared memory (T * N): 12 frames x 104, 4 x 312
 
 // Both kernels are latency problems (a few hundred KB out of L2 per CTA, ~1 MFLOP): rows are taken four at a time so that
 // every lane keeps eight 16-byte loads in flight, and the A.v product splits the KEY range over the warps of a CTA (each

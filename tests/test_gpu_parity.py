@@ -379,6 +379,28 @@ def test_config5_slot_sweep(dev, N):
     print(f"N={N}: stage-0 emb rel {rel(em[1][0], re_[1][0]):.2e}, stage-6 {rel(em[1][6], re_[1][6]):.2e} (fp32 oracle: {noise[6]:.2e})")
 
 
+def test_slot_groups_n300_t4(dev):
+    """N = 300, T = 4: the slot-update kernels keep <= 104 slot rows per cluster, so a frame runs as
+    three row groups of 100; the Video Retriever attends over all 1200 slots.  Free-running vs the fp64 oracle within the
+    noise-relative bound, both kernel paths."""
+    T, N, shapes = 4, 300, [(4, 8), (8, 16), (16, 32), (32, 64)]
+    sd = synthetic.make_head_state_dict(14)
+    cap = synthetic.make_capsule_params(14, N)
+    feats = synthetic.make_features(0, 0, T=T, video=14, shapes=shapes)
+    q = cap["init_mask_query.weight"]
+    pos64 = [[O.sine_position_embedding(*s, dtype=torch.float64) for s in shapes] for _ in range(T)]
+    rc, re_, rf = O.head_forward({k: v.double() for k, v in sd.items()}, [[f.double() for f in fr] for fr in feats], [q.double()] * T, pos64)
+    noise = fp32_noise(sd, feats, q, T, shapes, re_)
+    for kp in (0, 1):
+        head = _mk_head(dev, sd, kp)
+        cl, em, fu = head([[f.to(dev) for f in fr] for fr in feats], [q.to(dev)] * T, None, pos="sine")
+        for t in range(T):
+            for s in range(7):
+                assert drift_ok(rel(em[t][s], re_[t][s]), noise, s), (kp, t, s, rel(em[t][s], re_[t][s]), noise[s])
+            assert rel(cl[t][0], rc[t][0]) < 1e-4
+        print(f"N=300 T=4 path={kp}: stage-0 emb rel {rel(em[3][0], re_[3][0]):.2e}, stage-6 {rel(em[3][6], re_[3][6]):.2e} (fp32 oracle: {noise[6]:.2e})")
+
+
 def test_config4_viper_shape(dev):
     """BASELINE configs[3]: VIPER-shaped clip (1080x1920 padded to 1088x1920 -> levels 34x60..272x480, pixel counts
     that are not multiples of the 128-pixel tile), T=4 (Video Retriever over 400 slots), at 1/4 linear size vs the
