@@ -1,30 +1,17 @@
-#!/usr/bin/env python
-"""Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel (device time, share)."""
-import collections
-import csv
-import sys
-
+"""Aggregate the last step of an ncu launch list (ncu --metrics gpu__time_duration.sum --csv) per kernel.
+Usage: python scripts/summarize_launches.py launches.csv"""
+import csv, collections, sys
 rows = list(csv.reader(open(sys.argv[1])))
-hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
-H = rows[hdr]
-ki, vi, ui = H.index("Kernel Name"), H.index("Metric Value"), H.index("Metric Unit")
-body = [r for r in rows[hdr + 1:] if len(r) > vi]
-# one full step = the launches after the second-to-last fuse_relabel (last kernel of a step) up to the last one
-ends = [i for i, r in enumerate(body) if "fuse_relabel" in r[ki]]
-if len(ends) >= 2 and "--all" not in sys.argv:
-    body = body[ends[-2] + 1:ends[-1] + 1]
-    print(f"# one step: launches {ends[-2] + 1}..{ends[-1]} of the capture")
-agg = collections.defaultdict(lambda: [0, 0.0])
-for r in body:
-    if len(r) <= vi:
-        continue
-    name = r[ki].split("(")[0].replace("void ", "").replace("slotvps::", "")[:60]
-    v = float(r[vi].replace(",", ""))
-    v = v / 1e6 if r[ui] == "ns" else v / 1e3 if r[ui] == "us" else v
-    agg[name][0] += 1
-    agg[name][1] += v
-tot = sum(v[1] for v in agg.values())
-print(f"{'kernel':52s} {'launches':>8s} {'ms':>9s} {'share':>7s} {'us/launch':>10s}")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"{k:52s} {v[0]:8d} {v[1]:9.3f} {100 * v[1] / tot:6.1f}% {1e3 * v[1] / v[0]:10.1f}")
-print(f"{'total':52s} {sum(v[0] for v in agg.values()):8d} {tot:9.3f}")
+hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
+hdr = rows[hi]; idx = {h: i for i, h in enumerate(hdr)}
+data = rows[hi + 1:]
+names = [r[idx['Kernel Name']].split('(')[0].replace('slotvps::', '').replace('void ', '') for r in data]
+vals = [float(r[idx['Metric Value']].replace(',', '')) for r in data]
+mi = [i for i, n in enumerate(names) if 'mask_tc' in n]
+L = mi[-1] - mi[-2]                                   # launches per step (mask_tc runs once per step)
+agg = collections.OrderedDict(); tot = 0.0
+for i in range(len(names) - L, len(names)):
+    a = agg.setdefault(names[i], [0, 0.0]); a[0] += 1; a[1] += vals[i] / 1000.0; tot += vals[i] / 1000.0
+print(f"launches per step {L}, serialised kernel time {tot:.1f} us (cold cache, one launch at a time)")
+for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
+    print(f"{n[:44]:44s} x{c:3d} {t:8.1f} us  {t / c:7.1f} us each  {100 * t / tot:5.1f} %")

@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(256) attn_post_kernel(const float* __restrict_
   }
 }
 
-// nn.MultiheadAttention core: qkv [R][768] -> o [R][256]; one CTA per (head, frame); head_dim 32.
+// nn.MultiheadAttention core: qkv [R][768] -> o [R][256]; one CTA per (head, frame, quarter of the query rows); head_dim 32.
+// A latency problem (25 KB of K/V per CTA, ~0.6 MFLOP): K and V come in as 16-byte loads that are all in flight at once,
+// and the score / P.V loops carry four independent accumulation chains.
 __global__ void __launch_bounds__(256) mha_core_kernel(const float* __restrict__ qkv, float* __restrict__ o, int n_slots, int nhead) {
   extern __shared__ float sm[];
   const int hd = blockIdx.x, t = blockIdx.y, D = 32;
@@ -121,34 +123,57 @@ __global__ void __launch_bounds__(256) mha_core_kernel(const float* __restrict__
   float* vs = ks + n_slots * 33;        // [N][33]
   float* ps = vs + n_slots * 33;        // [8 warps][N]
   const float* base = qkv + (long)t * n_slots * 3 * C;
-  for (int i = threadIdx.x; i < n_slots * D; i += blockDim.x) {
-    int j = i / D, d = i % D;
-    ks[j * 33 + d] = base[(long)j * 3 * C + C + hd * D + d];
-    vs[j * 33 + d] = base[(long)j * 3 * C + 2 * C + hd * D + d];
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n_slots * 8; i += 256) {
+    const int j = i >> 3, d4 = (i & 7) * 4;
+    const float4 kk = __ldg(reinterpret_cast<const float4*>(base + (long)j * 3 * C + C + hd * D + d4));
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(base + (long)j * 3 * C + 2 * C + hd * D + d4));
+    float* kd = ks + j * 33 + d4;
+    float* vd = vs + j * 33 + d4;
+    kd[0] = kk.x; kd[1] = kk.y; kd[2] = kk.z; kd[3] = kk.w;
+    vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
   }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* pw = ps + warp * n_slots;
-  const float scale = rsqrtf((float)D);
   // query rows are split over blockIdx.z so that (heads x frames x gridDim.z) CTAs fill the machine
-  for (int i = blockIdx.z * 8 + warp; i < n_slots; i += 8 * gridDim.z) {
-    float qd = base[(long)i * 3 * C + hd * D + lane] * scale;     // lane = dim
+  const int i0 = blockIdx.z * 8 + warp, istep = 8 * gridDim.z;
+  const float scale = rsqrtf((float)D);
+  float qn = i0 < n_slots ? __ldg(base + (long)i0 * 3 * C + hd * D + lane) * scale : 0.f;     // lane = dim
+  __syncthreads();
+  float* pw = ps + warp * n_slots;
+  for (int i = i0; i < n_slots; i += istep) {
+    const float qd = qn;
+    if (i + istep < n_slots) qn = __ldg(base + (long)(i + istep) * 3 * C + hd * D + lane) * scale;
     float mx = -INFINITY;
-    for (int j0 = 0; j0 < n_slots; j0 += 32) {
-      int j = j0 + lane;
-      float sc = 0.f;
+    for (int j0 = 0; j0 < n_slots; j0 += 128) {                     // four key blocks of 32 at a time: independent chains
+      float sc[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* kp[4];
 #pragma unroll
-      for (int d = 0; d < D; ++d) sc = fmaf(__shfl_sync(0xffffffffu, qd, d), j < n_slots ? ks[j * 33 + d] : 0.f, sc);
-      if (j < n_slots) { pw[j] = sc; mx = fmaxf(mx, sc); }
+      for (int b = 0; b < 4; ++b) kp[b] = ks + min(j0 + 32 * b + lane, n_slots - 1) * 33;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float q = __shfl_sync(0xffffffffu, qd, d);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) sc[b] = fmaf(q, kp[b][d], sc[b]);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int j = j0 + 32 * b + lane;
+        if (j < n_slots) { pw[j] = sc[b]; mx = fmaxf(mx, sc[b]); }
+      }
     }
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < n_slots; j += 32) { float e = expf(pw[j] - mx); pw[j] = e; sum += e; }
     sum = warp_sum(sum);
     __syncwarp();
-    float acc = 0.f;
-    for (int j = 0; j < n_slots; ++j) acc = fmaf(pw[j], vs[j * 33 + lane], acc);
-    o[((long)t * n_slots + i) * C + hd * D + lane] = acc / sum;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int j = 0;
+    for (; j + 4 <= n_slots; j += 4) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[b] = fmaf(pw[j + b], vs[(j + b) * 33 + lane], acc[b]);
+    }
+    for (; j < n_slots; ++j) acc[0] = fmaf(pw[j], vs[j * 33 + lane], acc[0]);
+    o[((long)t * n_slots + i) * C + hd * D + lane] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) / sum;
     __syncwarp();
   }
 }

@@ -429,7 +429,8 @@ __global__ void __launch_bounds__(256) slot_norm3_kernel(const float* __restrict
   for (int hh = 0; hh < 2; ++hh) {
     const int col = hh * 128 + lane * 4;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int cc = 0; cc < nparts; ++cc) {
+#pragma unroll 8
+    for (int cc = 0; cc < nparts; ++cc) {                           // chunk order (deterministic); eight loads in flight
       const float4 q = __ldcg(reinterpret_cast<const float4*>(part + (long)cc * part_stride + (long)row * C + col));
       a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
     }
