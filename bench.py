@@ -277,8 +277,9 @@ def main():
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the single JSON line
+        # keep stdout to the single JSON line: NCCL prints its version banner (and anything else it logs) to stdout unless told
+        # otherwise, at every level from VERSION up
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
