@@ -240,13 +240,22 @@ struct Blk4 {
       ly1[a] = sy - y0; ly0[a] = 1.f - ly1[a]; lx1[a] = sx - x0; lx0[a] = 1.f - lx1[a];
     }
   }
-  // v[a*4+b] = value at output pixel (4i+a, 4j+b)
-  __device__ __forceinline__ void eval(const float* __restrict__ m, int w, float* v) const {
-    float t[3][3];
+  // the 3x3 source taps of the block; returns their maximum (every output value of the block is a convex combination of them)
+  __device__ __forceinline__ float taps(const float* __restrict__ m, int w, float (*t)[3]) const {
+    float mx = -INFINITY;
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int b = 0; b < 3; ++b) t[a][b] = __ldg(m + r[a] * w + c[b]);
+      for (int b = 0; b < 3; ++b) { t[a][b] = __ldg(m + r[a] * w + c[b]); mx = fmaxf(mx, t[a][b]); }
+    return mx;
+  }
+  // v[a*4+b] = value at output pixel (4i+a, 4j+b)
+  __device__ __forceinline__ void eval(const float* __restrict__ m, int w, float* v) const {
+    float t[3][3];
+    taps(m, w, t);
+    interp(t, v);
+  }
+  __device__ __forceinline__ void interp(const float (*t)[3], float* v) const {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -281,6 +290,7 @@ __global__ void __launch_bounds__(256) fuse_count4_kernel(const float* __restric
     // Conservative screen: every output value of the block is a convex combination of the slot's 3x3 source taps,
     // so p_k <= exp(max tap_k) / sum_j exp(min tap_j).  If that bound stays below pixel_threshold for every thing,
     // no pixel of the block has a candidate and the three exact passes are skipped (stuff-only regions).
+    float mlow;
     {
       float umax = -INFINITY, m = -INFINITY, ssum = 0.f;
       for (int k = 0; k < K; ++k) {
@@ -293,6 +303,7 @@ __global__ void __launch_bounds__(256) fuse_count4_kernel(const float* __restric
         if (k >= ns) umax = fmaxf(umax, tmax);
         if (tmin > m) { ssum = ssum * __expf(m - tmin) + 1.f; m = tmin; } else ssum += __expf(tmin - m);
       }
+      mlow = m;
       if (ns == K || umax - (m + __logf(ssum)) < screen_cut) {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
@@ -303,11 +314,16 @@ __global__ void __launch_bounds__(256) fuse_count4_kernel(const float* __restric
     // softmax over the kept slots in one sweep (running maximum, sum rescaled when it moves: one exp per value), then the
     // threshold test in the log domain: p_k >= thr  <=>  v_k >= max + log(thr * sum).  Against the reference's
     // exp / divide / compare this moves the decision only for pixels whose p is within ~1e-6 (relative) of the threshold.
-    float mx[16], sum[16], v[16];
+    float mx[16], sum[16], v[16], t[3][3];
 #pragma unroll
     for (int e = 0; e < 16; ++e) { mx[e] = -INFINITY; sum[e] = 0.f; }
+    // A slot whose largest tap lies 20 below `mlow` (= the largest of the slots' smallest taps, a lower bound of the maximum at
+    // every pixel of the block) adds less than e^-20 = 2e-9 of the sum at every pixel -- 27 such slots stay below half an ulp of
+    // the fp32 sum -- so its interpolation and exponentials are skipped; inside an object that is most of the kept slots.
+    const float skip_below = mlow - 20.f;
     for (int k = 0; k < K; ++k) {
-      b4.eval(masks + (long)s_ord[k] * P, w, v);
+      if (b4.taps(masks + (long)s_ord[k] * P, w, t) < skip_below) continue;
+      b4.interp(t, v);
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const float dlt = v[e] - mx[e];
@@ -316,13 +332,15 @@ __global__ void __launch_bounds__(256) fuse_count4_kernel(const float* __restric
         mx[e] = fmaxf(mx[e], v[e]);
       }
     }
+    float cutmin = INFINITY;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) mx[e] += logf(pix_thr * sum[e]);              // the cut: -inf when pix_thr == 0
+    for (int e = 0; e < 16; ++e) { mx[e] += logf(pix_thr * sum[e]); cutmin = fminf(cutmin, mx[e]); }     // the cut: -inf when pix_thr == 0
     unsigned int cd[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) cd[e] = 0xFFFFFFFFu;
     for (int k = ns; k < K; ++k) {
-      b4.eval(masks + (long)s_ord[k] * P, w, v);
+      if (b4.taps(masks + (long)s_ord[k] * P, w, t) < cutmin) continue;       // exact: no value of the block can reach its cut
+      b4.interp(t, v);
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         if (v[e] >= mx[e]) {
