@@ -279,6 +279,9 @@ def main():
     if world > 1:
         # keep stdout to the single JSON line: NCCL prints its version banner (and anything else it logs) to stdout unless told
         # otherwise, at every level from VERSION up
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so a VERSION setting is raised to WARN)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
