@@ -846,9 +846,9 @@ int slotvps_head_forward_ex(const slotvps_head_desc* d, const slotvps_stage_para
       prm.planes = tcl.planes; prm.plane_stride = rows; prm.x_planes_only = pos_sep ? 1 : 0;
       if (d->pos_mode == 1) { prm.pos = pos[l]; prm.pos_bs = pstride[l]; }
       else if (d->pos_mode == 2) {
-        pos_tab_kernel<<<ceil_div(128 * (h + wd), 256), 256, 0, s>>>(tcl.ytab, tcl.xtab, h, wd);
+        pos_tab_kernel<<<ceil_div(128 * (h + wd), 256), 256, 0, s>>>(tcl.ytab, tcl.xtab, h, wd, w.tc.ytabT_l[l]);
         SV_CHECK_LAUNCH("pos_tab");
-        prm.ytab = tcl.ytab; prm.xtab = tcl.xtab;
+        prm.ytab = tcl.ytab; prm.xtab = tcl.xtab; prm.ytabT = w.tc.ytabT_l[l];
       }
       SV_TRY(fuse_tc_launch(w.ftc.in_planes, 2 * rows, (int)rows, CIN, l > 0 ? pr.ftc.wb : pr.ftc.w0, prm, s, side_ctas));
     } else {

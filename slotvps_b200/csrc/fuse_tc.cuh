@@ -48,6 +48,7 @@ struct Params {
   const float* pos;    // [256][P] per frame (pos_bs) or null
   long pos_bs;
   const float *ytab, *xtab;   // separable sine tables of this resolution or null
+  const float* ytabT;         // the row table as [h][128]
   int h;
   // optional (finest level): per-pixel sum_c (bn_sc[c] x[c] + bn_sh[c])^2 as four partial sums (one per 64-channel quarter,
   // written by the four epilogue threads of a pixel) ss_out [4][rows]; the consumer adds them in a fixed order (deterministic).
@@ -329,9 +330,11 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] += __ldg(ps + (long)c * prm.P);
           } else if (prm.ytab) {
-            if (u < 8) {
+            if (u < 8) {                                      // a warp's pixels share the image row: two broadcast 32-byte loads
+              float tb[16];
+              tc::ld_global_nc_v8f(prm.ytabT + py * 128 + u * 16, tb); tc::ld_global_nc_v8f(prm.ytabT + py * 128 + u * 16 + 8, tb + 8);
 #pragma unroll
-              for (int c = 0; c < 16; ++c) v[c] += __ldg(prm.ytab + (u * 16 + c) * prm.h + py);
+              for (int c = 0; c < 16; ++c) v[c] += tb[c];
             } else {
 #pragma unroll
               for (int c = 0; c < 16; ++c) v[c] += __ldg(prm.xtab + ((u - 8) * 16 + c) * prm.w + px);

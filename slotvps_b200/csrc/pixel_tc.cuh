@@ -32,6 +32,7 @@ struct TcWorkspace {
   __half* planes_alt = nullptr;  // second plane set: levels alternate so the next level's fusion can overlap this level's stages
   float *ytab = nullptr, *xtab = nullptr;  // separable sine tables [128][h], [128][w] of the CURRENT level
   float *ytab_l[SLOTVPS_MAX_LEVELS] = {nullptr}, *xtab_l[SLOTVPS_MAX_LEVELS] = {nullptr};   // one pair per level (the side stream runs ahead)
+  float *ytabT_l[SLOTVPS_MAX_LEVELS] = {nullptr};   // row tables transposed [h][128]: a pixel's 16 channels are one 64-byte broadcast load (fuse_tc)
   __half* gplanes = nullptr;     // [groups][T][2][104][256] folded query operand G, hi/lo (one copy per slot group)
   float2* ml = nullptr;          // [groups + 1][T*Pmax] per-pixel softmax (max, sum) of each slot group + combined (N > 104 only)
   long plane_rows = 0;                  // rows allocated per plane (T*Pmax)
@@ -64,7 +65,7 @@ inline void tc_workspace_layout(Arena& a, const slotvps_head_desc* d, TcWorkspac
   if (d->kernel_path == 0) {
     w->planes = a.take<__half>((size_t)4 * w->plane_rows * C);
     w->planes_alt = a.take<__half>((size_t)4 * w->plane_rows * C);
-    for (int l = 0; l < SLOTVPS_MAX_LEVELS; ++l) { w->ytab_l[l] = a.take<float>((size_t)128 * hmax); w->xtab_l[l] = a.take<float>((size_t)128 * wmax); }
+    for (int l = 0; l < SLOTVPS_MAX_LEVELS; ++l) { w->ytab_l[l] = a.take<float>((size_t)128 * hmax); w->xtab_l[l] = a.take<float>((size_t)128 * wmax); w->ytabT_l[l] = a.take<float>((size_t)128 * hmax); }
     w->ytab = w->ytab_l[0]; w->xtab = w->xtab_l[0];
     const int groups = (d->n_slots + 103) / 104;
     w->gplanes = a.take<__half>((size_t)groups * d->n_frames * 2 * 112 * C);
@@ -100,7 +101,8 @@ __global__ void __launch_bounds__(256) weight_planes_kernel(const float* __restr
   split_bf16(Wv[i], h, l); out[2 * C * C + i] = h; out[3 * C * C + i] = l;
 }
 // separable sine tables (position_encoding.py:236-256): channels [0,128) depend on the row, [128,256) on the column
-__global__ void __launch_bounds__(256) pos_tab_kernel(float* __restrict__ ytab, float* __restrict__ xtab, int h, int w) {
+__global__ void __launch_bounds__(256) pos_tab_kernel(float* __restrict__ ytab, float* __restrict__ xtab, int h, int w,
+                                                      float* __restrict__ ytabT = nullptr /* optional [h][128] copy */) {
   int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= 128 * (h + w)) return;
   const bool isy = i < 128 * h;
@@ -109,7 +111,9 @@ __global__ void __launch_bounds__(256) pos_tab_kernel(float* __restrict__ ytab, 
   int ci = j / n, r = j % n;
   float e = (float)(r + 1) / ((float)n + 1e-6f) * 6.283185307179586f;
   float a = e / powf(10000.f, (float)(2 * (ci / 2)) / 128.f);
-  (isy ? ytab : xtab)[j] = (ci & 1) ? cosf(a) : sinf(a);
+  const float val = (ci & 1) ? cosf(a) : sinf(a);
+  (isy ? ytab : xtab)[j] = val;
+  if (isy && ytabT) ytabT[r * 128 + ci] = val;
 }
 // grid (ceil(P/32), T).  pos: tensor [256][P] per frame (pos_bs stride) | tables | none
 constexpr int SPLIT_SMEM = 2 * 256 * 33 * (int)sizeof(float);
