@@ -261,6 +261,41 @@ int slotvps_unify_pan_result(const int64_t* seg, const int64_t* pan, const int32
                              const int32_t* obj_ids, int n_obj, int H, int W, int id_last_stuff, int stuff_area_limit,
                              uint8_t* pan_2ch, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- UPSNetFPN deformable-convolution subnet -------------------------------------
+ * This is the one place on the widened path where the reference HAS a native boundary: the pybind'd
+ * deform_conv_cuda.deform_conv_forward_cuda (mmdet/ops/dcn/src/deform_conv_cuda.cpp:152-245, bound at :688, called from
+ * mmdet/ops/dcn/deform_conv.py:53-58).  slotvps_deform_conv_forward takes the same tensors and the same integer
+ * arguments in the same order: input [B,c_in,H,W], weight [c_out,c_in,kH,kW], offset [B,2*kH*kW*deformable_group,H,W]
+ * (channel 2*tap = dy, 2*tap+1 = dx, tap = ky*kW+kx; deform_conv_cuda_kernel.cu:216-226) -> output [B,c_out,H,W].
+ * The reference's scratch arguments (`columns`, `ones`) become `workspace`; im2col_step only partitions the batch in the
+ * reference and does not change the result, it is accepted and ignored.  Served here: what UPSNetFPN instantiates
+ * (upsnetFPN.py:36-49) -- 3x3, stride 1, padding 1, dilation 1, group 1, deformable_group 1, c_in a multiple of 64 and
+ * c_out a multiple of 32, both <= 256; anything else returns SLOTVPS_EINVAL (the reference op stays available for it).
+ * offset == NULL computes the ordinary 3x3 convolution (all offsets zero).                                           */
+int slotvps_deform_conv_workspace_bytes(int B, int c_in, int H, int W, size_t* bytes);
+int slotvps_deform_conv_forward(const float* input, const float* weight, const float* offset, float* output,
+                                int B, int c_in, int c_out, int H, int W,
+                                int kW, int kH, int dW, int dH, int padW, int padH, int dilationW, int dilationH,
+                                int group, int deformable_group, int im2col_step,
+                                void* workspace, size_t workspace_bytes, void* stream);
+/* The subnet UPSNetFPN applies to every FPN level with shared weights (upsnetFPN.py:36-49, 66-70):
+ * n_layers x [DeformConvWithOffset 3x3 (mmdet/models/utils/deform_conv_with_offset.py: conv_offset = Conv2d(c_in,18,3,
+ * padding=1) with bias, then the bias-free deformable conv) -> GroupNorm(32, c_out) -> ReLU].  Pointers are the module's
+ * own parameters (state_dict keys deform_convs.0.{3i}.conv_offset.{weight,bias}, .{3i}.conv.weight, .{3i+1}.{weight,bias}).
+ * x [B,c_in(0),H,W] -> out [B,c_out(last),H,W] (one entry of the reference's fpn_px list).  Activations stay
+ * pixel-major between the layers; GroupNorm + ReLU of layer i are applied inside the loads of layer i+1.              */
+typedef struct slotvps_dcn_layer {
+  int32_t c_in, c_out;
+  const float *offset_w, *offset_b;   /* conv_offset.weight [18,c_in,3,3], conv_offset.bias [18] */
+  const float *weight;                /* conv.weight [c_out,c_in,3,3] */
+  const float *gn_w, *gn_b;           /* GroupNorm(32, c_out) weight / bias [c_out] */
+} slotvps_dcn_layer;
+int slotvps_dcn_prepared_bytes(const slotvps_dcn_layer* layers, int n_layers, size_t* bytes);
+int slotvps_dcn_prepare(const slotvps_dcn_layer* layers, int n_layers, void* prepared, size_t prepared_bytes, void* stream);
+int slotvps_dcn_workspace_bytes(const slotvps_dcn_layer* layers, int n_layers, int B, int H, int W, size_t* bytes);
+int slotvps_dcn_subnet_forward(const slotvps_dcn_layer* layers, int n_layers, const void* prepared, const float* x, float* out,
+                               int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Introspection. */
 const char* slotvps_last_error(void);
 const char* slotvps_version(void);

@@ -592,3 +592,64 @@ def unify_pan_result(segs, pans, cls_inds, obj_ids=None, stuff_area_limit: int =
         o[:, :, 0], o[:, :, 1], o[:, :, 2] = pan_seg.astype(np.uint8), pan_ins.astype(np.uint8), pan_obj.astype(np.uint8)
         out.append(o)
     return out
+
+
+# ---- UPSNetFPN deformable-convolution subnet ----------------------------------------
+# Pinning: the reference op is CUDA-only, so it cannot run in the build container.  It is compiled UNMODIFIED from its own
+# two source files by oracle/build_ref_dcn.sh into oracle/_ref/deform_conv_cuda.so (sm_100a), run on the B200 by
+# tests/golden/make_golden_dcn.py, and its outputs are frozen as tests/golden/dcn_*.npz; tests/test_oracle_golden.py
+# checks this restatement against them on CPU (and against torchvision.ops.deform_conv2d, an independent implementation).
+def deform_conv(x: torch.Tensor, offset: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """3x3 / stride 1 / padding 1 / dilation 1 deformable convolution, one group, one deformable group.
+
+    ``deformable_im2col_gpu_kernel`` (mmdet/ops/dcn/src/deform_conv_cuda_kernel.cu:190-236) with
+    ``deformable_im2col_bilinear`` (:80-112), then ``weight.flatten(1) @ columns`` (deform_conv_cuda.cpp:214-219).
+    x [B,Cin,H,W], offset [B,18,H,W] (channel 2*tap = dy, 2*tap+1 = dx, tap = 3*ky+kx), weight [Cout,Cin,3,3]."""
+    B, Cin, H, W = x.shape
+    dt = x.dtype
+    flat = x.reshape(B, Cin, H * W)
+    ys = torch.arange(H, dtype=dt).view(1, H, 1)
+    xs = torch.arange(W, dtype=dt).view(1, 1, W)
+    cols = []
+    for tap in range(9):
+        i, j = tap // 3, tap % 3
+        h_im = (ys - 1 + i) + offset[:, 2 * tap].to(dt)               # :222-223 (h_in + i * dilation_h + offset_h)
+        w_im = (xs - 1 + j) + offset[:, 2 * tap + 1].to(dt)
+        inside = (h_im > -1) & (w_im > -1) & (h_im < H) & (w_im < W)  # :224
+        h_low, w_low = torch.floor(h_im), torch.floor(w_im)
+        lh, lw = h_im - h_low, w_im - w_low
+        hh, hw = 1 - lh, 1 - lw
+        h_low, w_low = h_low.long(), w_low.long()
+        h_high, w_high = h_low + 1, w_low + 1
+
+        def corner(hi, wi, ok):
+            idx = (hi.clamp(0, H - 1) * W + wi.clamp(0, W - 1)).view(B, 1, H * W).expand(B, Cin, H * W)
+            v = torch.gather(flat, 2, idx)
+            return v * (ok & inside).view(B, 1, H * W).to(dt)
+        v1 = corner(h_low, w_low, (h_low >= 0) & (w_low >= 0))                     # :93-104
+        v2 = corner(h_low, w_high, (h_low >= 0) & (w_high <= W - 1))
+        v3 = corner(h_high, w_low, (h_high <= H - 1) & (w_low >= 0))
+        v4 = corner(h_high, w_high, (h_high <= H - 1) & (w_high <= W - 1))
+        w1, w2, w3, w4 = (hh * hw), (hh * lw), (lh * hw), (lh * lw)                 # :106
+        f = lambda t: t.view(B, 1, H * W)
+        cols.append(f(w1) * v1 + f(w2) * v2 + f(w3) * v3 + f(w4) * v4)              # :108
+    col = torch.stack(cols, dim=2).reshape(B, Cin * 9, H * W)                        # row c * 9 + tap, as :204 (c_col)
+    out = torch.matmul(weight.reshape(weight.shape[0], -1).to(dt), col)
+    return out.reshape(B, -1, H, W)
+
+
+def deform_conv_with_offset(x, offset_w, offset_b, weight):
+    """DeformConvWithOffset.forward (mmdet/models/utils/deform_conv_with_offset.py:38-39)."""
+    return deform_conv(x, F.conv2d(x, offset_w, offset_b, padding=1), weight)
+
+
+def dcn_subnet(P: Dict[str, torch.Tensor], x: torch.Tensor, n_layers: int = 3, capture: Optional[list] = None) -> torch.Tensor:
+    """``UPSNetFPN.deform_convs[0]`` (upsnetFPN.py:36-49): n x [DeformConvWithOffset -> GroupNorm(32) -> ReLU].
+    P uses the Sequential's own keys ("0.conv_offset.weight", "0.conv.weight", "1.weight", ...).  ``capture`` collects
+    the input of every layer (teacher forcing)."""
+    for i in range(n_layers):
+        if capture is not None:
+            capture.append(x)
+        y = deform_conv_with_offset(x, P[f"{3 * i}.conv_offset.weight"], P[f"{3 * i}.conv_offset.bias"], P[f"{3 * i}.conv.weight"])
+        x = F.relu(F.group_norm(y, 32, P[f"{3 * i + 1}.weight"], P[f"{3 * i + 1}.bias"], 1e-5))
+    return x

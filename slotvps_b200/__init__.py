@@ -5,6 +5,7 @@ Public surface (mirrors of the reference interfaces):
   mask_logits           <- generate_final_outputs       (vps_temporal_slots.py:144)
   PanopticFusion        <- PostProcessPanopticInstances (vps_temporal_slots.py:528) + inline fusion (:411-435)
   SlotVPSRetriever      <- the three chained for one clip
+  B200DeformSubnet      <- UPSNetFPN.deform_convs[0]    (upsnetFPN.py:36-49), deform_conv <- mmdet.ops.dcn.deform_conv
 All compute is hand-written CUDA behind the C ABI of include/slotvps_b200.h; there is no CPU path.
 """
 from ._lib import build_library, lib, SlotVPSError  # noqa: F401
@@ -13,6 +14,7 @@ from .retriever import (PanopticFusion, SlotVPSRetriever, FusionOutput, GraphedC
                         slot_attention, sine_position_embedding)
 from .tracker import B200TrackHead, SlotTracker  # noqa: F401
 from .unify import PanUnifier, get_unified_pan_result, semantic_argmax  # noqa: F401
+from .dcn import B200DeformConvWithOffset, B200DeformSubnet, deform_conv, deform_subnet_levels  # noqa: F401
 
 TRACK_KWARGS = dict(num_fcs_query=2, in_channels_query=256, query_matched_weight=1.0)  # r50_fpn_slotvps.py:90-96
 

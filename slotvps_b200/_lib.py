@@ -97,6 +97,11 @@ class FusionCfg(C.Structure):
     ]
 
 
+class DcnLayer(C.Structure):
+    _fields_ = [("c_in", C.c_int32), ("c_out", C.c_int32), ("offset_w", C.c_void_p), ("offset_b", C.c_void_p),
+                ("weight", C.c_void_p), ("gn_w", C.c_void_p), ("gn_b", C.c_void_p)]
+
+
 # name -> (restype, argtypes): every symbol include/slotvps_b200.h declares
 P = C.c_void_p
 SYMBOLS = {
@@ -131,6 +136,12 @@ SYMBOLS = {
     "slotvps_track_state_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "slotvps_track_reset": (C.c_int, [P, C.c_size_t, P]),
     "slotvps_track_step": (C.c_int, [P, P, C.c_int, P, P, C.c_int, P, C.c_size_t, C.c_int, P, P]),
+    "slotvps_deform_conv_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "slotvps_deform_conv_forward": (C.c_int, [P, P, P, P] + [C.c_int] * 16 + [P, C.c_size_t, P]),
+    "slotvps_dcn_prepared_bytes": (C.c_int, [C.POINTER(DcnLayer), C.c_int, C.POINTER(C.c_size_t)]),
+    "slotvps_dcn_prepare": (C.c_int, [C.POINTER(DcnLayer), C.c_int, P, C.c_size_t, P]),
+    "slotvps_dcn_workspace_bytes": (C.c_int, [C.POINTER(DcnLayer), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "slotvps_dcn_subnet_forward": (C.c_int, [C.POINTER(DcnLayer), C.c_int, P, P, P, C.c_int, C.c_int, C.c_int, P, C.c_size_t, P]),
     "slotvps_last_error": (C.c_char_p, []),
     "slotvps_version": (C.c_char_p, []),
     "slotvps_launch_count": (C.c_int64, [C.c_int]),

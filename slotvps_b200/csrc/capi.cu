@@ -19,6 +19,7 @@
 #include "temporal.cuh"
 #include "track.cuh"
 #include "unify.cuh"
+#include "dcn.cuh"
 
 namespace slotvps {
 thread_local char g_err[512] = "";
@@ -1359,6 +1360,150 @@ int slotvps_slot_attention(const slotvps_stage_params* sp, const float* slots_p,
   attn_post_kernel<<<ceil_div(N, 8), 256, 0, s>>>(w.Y, w.a0, w.a1, nullptr, sp->nv_w, sp->nv_b, ps.bv_c, sp->no_w, sp->no_b,
                                                    nullptr, nullptr, out, nullptr, N);
   SV_CHECK_LAUNCH("attn_post");
+  return SLOTVPS_OK;
+}
+
+// ---- UPSNetFPN deformable-convolution subnet -------------------------------------------------
+namespace {
+int dcn_check_layers(const slotvps_dcn_layer* L, int n) {
+  SV_REQUIRE(L != nullptr && n > 0 && n <= 8, "bad layer list");
+  for (int i = 0; i < n; ++i) {
+    SV_TRY(dcn::validate_layer(L[i]));
+    SV_REQUIRE(i == 0 || L[i].c_in == L[i - 1].c_out, "dcn: c_in of a layer must equal c_out of the previous one");
+  }
+  return SLOTVPS_OK;
+}
+int dcn_cin_max(const slotvps_dcn_layer* L, int n) {
+  int m = 0;
+  for (int i = 0; i < n; ++i) m = L[i].c_in > m ? L[i].c_in : m;
+  return m;
+}
+}  // namespace
+
+int slotvps_dcn_prepared_bytes(const slotvps_dcn_layer* layers, int n_layers, size_t* bytes) {
+  SV_REQUIRE(bytes != nullptr, "null out pointer");
+  SV_TRY(dcn_check_layers(layers, n_layers));
+  *bytes = align_up(dcn::prep_layout(layers, n_layers, nullptr, nullptr));
+  return SLOTVPS_OK;
+}
+
+int slotvps_dcn_prepare(const slotvps_dcn_layer* layers, int n_layers, void* prepared, size_t prepared_bytes, void* stream) {
+  SV_TRY(dcn_check_layers(layers, n_layers));
+  SV_REQUIRE(prepared != nullptr, "null argument");
+  if (prepared_bytes < align_up(dcn::prep_layout(layers, n_layers, nullptr, nullptr))) return fail(SLOTVPS_EWORKSPACE, "dcn: prepared buffer too small%s%s");
+  cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
+  dcn::LayerPrep lp[8];
+  dcn::prep_layout(layers, n_layers, prepared, lp);
+  for (int i = 0; i < n_layers; ++i) {
+    SV_REQUIRE(layers[i].offset_w && layers[i].offset_b && layers[i].weight && layers[i].gn_w && layers[i].gn_b, "dcn: null parameter");
+    const int cin = layers[i].c_in;
+    dcn::offw_prep_kernel<<<ceil_div(dcn::KT * cin * 20, 256), 256, 0, s>>>(layers[i].offset_w, lp[i].offw, cin);
+    SV_CHECK_LAUNCH("dcn_offw_prep");
+    dcn::dcnw_prep_kernel<<<ceil_div(C * dcn::KT * cin, 256), 256, 0, s>>>(layers[i].weight, lp[i].wplanes, layers[i].c_out, cin);
+    SV_CHECK_LAUNCH("dcn_w_prep");
+  }
+  return SLOTVPS_OK;
+}
+
+int slotvps_dcn_workspace_bytes(const slotvps_dcn_layer* layers, int n_layers, int B, int H, int W, size_t* bytes) {
+  SV_REQUIRE(bytes != nullptr, "null out pointer");
+  SV_TRY(dcn_check_layers(layers, n_layers));
+  SV_REQUIRE(B > 0 && H > 0 && W > 0 && (long)B * H * W < (1L << 30), "bad shape");
+  *bytes = align_up(dcn::ws_layout(dcn_cin_max(layers, n_layers), B, H, W, nullptr, nullptr));
+  return SLOTVPS_OK;
+}
+
+int slotvps_dcn_subnet_forward(const slotvps_dcn_layer* layers, int n_layers, const void* prepared, const float* x, float* out,
+                               int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  SV_TRY(dcn_check_layers(layers, n_layers));
+  SV_REQUIRE(prepared && x && out && workspace, "null argument");
+  SV_REQUIRE(B > 0 && H > 0 && W > 0 && (long)B * H * W < (1L << 30), "bad shape");
+  const int cin_max = dcn_cin_max(layers, n_layers);
+  if (workspace_bytes < align_up(dcn::ws_layout(cin_max, B, H, W, nullptr, nullptr))) return fail(SLOTVPS_EWORKSPACE, "dcn: workspace too small%s%s");
+  cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
+  dcn::LayerPrep lp[8];
+  dcn::prep_layout(layers, n_layers, const_cast<void*>(prepared), lp);
+  dcn::Ws w;
+  dcn::ws_layout(cin_max, B, H, W, workspace, &w);
+  const int P = H * W;
+  const long rows = (long)B * P;
+  {
+    const int c0 = layers[0].c_in;
+    dcn::nchw_to_nhwc_kernel<<<dim3(ceil_div(P, 32), ceil_div(c0, 32), B), 256, 0, s>>>(x, w.xT, c0, P);
+    SV_CHECK_LAUNCH("dcn_to_nhwc");
+  }
+  for (int i = 0; i < n_layers; ++i) {
+    const int cin = layers[i].c_in, cout = layers[i].c_out;
+    dcn::Act a;
+    if (i == 0) { a.x = w.xT; a.ld = cin; a.aff = nullptr; }
+    else { a.x = w.y[(i - 1) & 1]; a.ld = C; a.aff = w.aff[(i - 1) & 1]; }
+    dcn::offset_conv_kernel<<<dim3(ceil_div(P, 256), B), 256, 0, s>>>(a, lp[i].offw, layers[i].offset_b, w.off, cin, H, W);
+    SV_CHECK_LAUNCH("dcn_offset_conv");
+    dcn::Off off{w.off, (long)P * dcn::NOFF, dcn::NOFF, 1};
+    SV_TRY(dcn::conv_gemm(a, off, lp[i].wplanes, w.planes, w.y[i & 1], cin, B, H, W, s));
+    dcn::gn_partial_kernel<<<dim3(w.slabs, B), 256, 0, s>>>(w.y[i & 1], w.part, P, cout);
+    SV_CHECK_LAUNCH("dcn_gn_partial");
+    dcn::gn_final_kernel<<<B, 256, 0, s>>>(w.part, w.slabs, B, layers[i].gn_w, layers[i].gn_b, w.aff[i & 1], P, cout);
+    SV_CHECK_LAUNCH("dcn_gn_final");
+  }
+  const int last = n_layers - 1, cout = layers[last].c_out;
+  dcn::act_to_nchw_kernel<<<dim3(ceil_div(P, 32), ceil_div(cout, 32), B), 256, 0, s>>>(w.y[last & 1], w.aff[last & 1], out, P, cout);
+  SV_CHECK_LAUNCH("dcn_to_nchw");
+  (void)rows;
+  return SLOTVPS_OK;
+}
+
+namespace {
+struct DcWs { float *xT, *y; __half *wplanes, *planes; };
+size_t dc_layout(int B, int c_in, int H, int W, void* base, DcWs* o) {
+  Arena a(base, (size_t)-1);
+  const size_t rows = (size_t)B * H * W;
+  DcWs d;
+  d.xT = a.take<float>(rows * c_in);
+  d.y = a.take<float>(rows * C);
+  d.wplanes = a.take<__half>((size_t)2 * C * dcn::KT * c_in);
+  d.planes = a.take<__half>((size_t)2 * rows * dcn::KT * c_in + 64);
+  if (o) *o = d;
+  return a.off;
+}
+}  // namespace
+
+int slotvps_deform_conv_workspace_bytes(int B, int c_in, int H, int W, size_t* bytes) {
+  SV_REQUIRE(bytes != nullptr, "null out pointer");
+  SV_REQUIRE(B > 0 && H > 0 && W > 0 && c_in > 0 && c_in <= C && (long)B * H * W < (1L << 30), "bad shape");
+  *bytes = align_up(dc_layout(B, c_in, H, W, nullptr, nullptr));
+  return SLOTVPS_OK;
+}
+
+int slotvps_deform_conv_forward(const float* input, const float* weight, const float* offset, float* output, int B, int c_in, int c_out,
+                                int H, int W, int kW, int kH, int dW, int dH, int padW, int padH, int dilationW, int dilationH,
+                                int group, int deformable_group, int im2col_step, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)im2col_step;
+  SV_REQUIRE(input && weight && output && workspace, "null argument");
+  SV_REQUIRE(kW == 3 && kH == 3 && dW == 1 && dH == 1 && padW == 1 && padH == 1 && dilationW == 1 && dilationH == 1 && group == 1 &&
+             deformable_group == 1, "deform_conv: only the UPSNetFPN instance (3x3, stride 1, padding 1, dilation 1, one group) is served");
+  slotvps_dcn_layer l;
+  memset(&l, 0, sizeof(l));
+  l.c_in = c_in; l.c_out = c_out;
+  SV_TRY(dcn::validate_layer(l));
+  SV_REQUIRE(B > 0 && H > 0 && W > 0 && (long)B * H * W < (1L << 30), "bad shape");
+  if (workspace_bytes < align_up(dc_layout(B, c_in, H, W, nullptr, nullptr))) return fail(SLOTVPS_EWORKSPACE, "deform_conv: workspace too small%s%s");
+  cudaStream_t s = (cudaStream_t)stream;
+  SV_PROF_ENTRY();
+  DcWs w;
+  dc_layout(B, c_in, H, W, workspace, &w);
+  const int P = H * W;
+  dcn::dcnw_prep_kernel<<<ceil_div(C * dcn::KT * c_in, 256), 256, 0, s>>>(weight, w.wplanes, c_out, c_in);
+  SV_CHECK_LAUNCH("dcn_w_prep");
+  dcn::nchw_to_nhwc_kernel<<<dim3(ceil_div(P, 32), ceil_div(c_in, 32), B), 256, 0, s>>>(input, w.xT, c_in, P);
+  SV_CHECK_LAUNCH("dcn_to_nhwc");
+  dcn::Act a{w.xT, c_in, nullptr};
+  dcn::Off off{offset, (long)P * dcn::NOFF, 1, (long)P};          // NCHW offsets: channel stride P
+  SV_TRY(dcn::conv_gemm(a, off, w.wplanes, w.planes, w.y, c_in, B, H, W, s));
+  dcn::act_to_nchw_kernel<<<dim3(ceil_div(P, 32), ceil_div(c_out, 32), B), 256, 0, s>>>(w.y, nullptr, output, P, c_out);
+  SV_CHECK_LAUNCH("dcn_to_nchw");
   return SLOTVPS_OK;
 }
 

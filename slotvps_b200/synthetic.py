@@ -294,3 +294,30 @@ def make_unify_case(seed: int, H: int, W: int, n_inst: int = 12, dup_obj: int = 
         a, b = int(torch.randint(0, n_inst, (1,), generator=g)), int(torch.randint(0, n_inst, (1,), generator=g))
         obj_id[a] = obj_id[b]
     return seg, pan, cls_ind.to(torch.int64), obj_id
+
+
+def make_dcn_state_dict(seed: int = 0, in_channels: int = 256, out_channels: int = 128, offset_scale: float = 1.0
+                        ) -> Dict[str, torch.Tensor]:
+    """Random-init parameters of ``UPSNetFPN.deform_convs[0]`` (mmdet/models/panoptic/upsnetFPN.py:36-49) under the
+    Sequential's own keys.  The reference zero-initialises ``conv_offset`` (deform_conv_with_offset.py:25-26), which would
+    make every sampling offset zero; here it gets small weights so that the offsets reach ~``offset_scale`` pixels with
+    O(1) inputs (trained checkpoints are unavailable offline), fractional positions, and out-of-map taps at the border."""
+    g = torch.Generator().manual_seed(90_000 + seed)
+    sd: Dict[str, torch.Tensor] = {}
+    chans = [(in_channels, in_channels), (in_channels, out_channels), (out_channels, out_channels)]
+    for i, (cin, cout) in enumerate(chans):
+        n = cin * 9
+        sd[f"{3 * i}.conv_offset.weight"] = _uniform(g, (18, cin, 3, 3), offset_scale * math.sqrt(3.0 / n))
+        sd[f"{3 * i}.conv_offset.bias"] = _uniform(g, (18,), 0.5 * offset_scale)
+        sd[f"{3 * i}.conv.weight"] = _uniform(g, (cout, cin, 3, 3), 1.0 / math.sqrt(n))      # DeformConv.reset_parameters
+        sd[f"{3 * i + 1}.weight"] = 1.0 + _uniform(g, (cout,), 0.1)
+        sd[f"{3 * i + 1}.bias"] = _uniform(g, (cout,), 0.05)
+    return sd
+
+
+def make_fpn_level(seed: int, B: int, channels: int, H: int, W: int) -> torch.Tensor:
+    """One FPN level as the UPSNetFPN subnet sees it: smooth low-frequency structure plus noise, O(1) magnitude."""
+    g = torch.Generator().manual_seed(95_000 + seed)
+    coarse = torch.randn((B, channels, max(H // 8, 1), max(W // 8, 1)), generator=g)
+    x = torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=False)
+    return (x + 0.3 * torch.randn((B, channels, H, W), generator=g)).contiguous()
