@@ -1398,7 +1398,7 @@ int slotvps_dcn_prepare(const slotvps_dcn_layer* layers, int n_layers, void* pre
   for (int i = 0; i < n_layers; ++i) {
     SV_REQUIRE(layers[i].offset_w && layers[i].offset_b && layers[i].weight && layers[i].gn_w && layers[i].gn_b, "dcn: null parameter");
     const int cin = layers[i].c_in;
-    dcn::offw_prep_kernel<<<ceil_div(dcn::KT * cin * 20, 256), 256, 0, s>>>(layers[i].offset_w, lp[i].offw, cin);
+    dcn::offw_planes_kernel<<<ceil_div(C * cin, 256), 256, 0, s>>>(layers[i].offset_w, lp[i].offw, cin);
     SV_CHECK_LAUNCH("dcn_offw_prep");
     dcn::dcnw_prep_kernel<<<ceil_div(C * dcn::KT * cin, 256), 256, 0, s>>>(layers[i].weight, lp[i].wplanes, layers[i].c_out, cin);
     SV_CHECK_LAUNCH("dcn_w_prep");
@@ -1431,27 +1431,29 @@ int slotvps_dcn_subnet_forward(const slotvps_dcn_layer* layers, int n_layers, co
   const long rows = (long)B * P;
   {
     const int c0 = layers[0].c_in;
-    dcn::nchw_to_nhwc_kernel<<<dim3(ceil_div(P, 32), ceil_div(c0, 32), B), 256, 0, s>>>(x, w.xT, c0, P);
+    dcn::nchw_to_nhwc_kernel<<<dim3(ceil_div(P, 32), ceil_div(c0, 32), B), 256, 0, s>>>(x, w.act, c0, P);
     SV_CHECK_LAUNCH("dcn_to_nhwc");
   }
   for (int i = 0; i < n_layers; ++i) {
     const int cin = layers[i].c_in, cout = layers[i].c_out;
-    dcn::Act a;
-    if (i == 0) { a.x = w.xT; a.ld = cin; a.aff = nullptr; }
-    else { a.x = w.y[(i - 1) & 1]; a.ld = C; a.aff = w.aff[(i - 1) & 1]; }
-    dcn::offset_conv_kernel<<<dim3(ceil_div(P, 256), B), 256, 0, s>>>(a, lp[i].offw, layers[i].offset_b, w.off, cin, H, W);
-    SV_CHECK_LAUNCH("dcn_offset_conv");
+    // the activation of this layer once: layer 0 = the input as it is; later = relu(GroupNorm(y)) of the previous layer, compacted to cin columns
+    if (i == 0) dcn::act_planes_kernel<<<dcn::grid_for(rows * (cin / 8)), 256, 0, s>>>(w.act, cin, nullptr, nullptr, w.aplanes, rows, cin, P);
+    else dcn::act_planes_kernel<<<dcn::grid_for(rows * (cin / 8)), 256, 0, s>>>(w.y, C, w.aff, w.act, w.aplanes, rows, cin, P);
+    SV_CHECK_LAUNCH("dcn_act_planes");
+    // conv_offset: one 1x1 GEMM for all 9 taps x 18 outputs, then the 9-tap shift-sum
+    SV_TRY(dcn::gemm(w.aplanes, rows, cin, lp[i].offw, w.z, 176, H, W, s));
+    dcn::offset_shift_kernel<<<(unsigned)((rows * dcn::NOFF + 255) / 256), 256, 0, s>>>(w.z, layers[i].offset_b, w.off, H, W, rows);
+    SV_CHECK_LAUNCH("dcn_offset_shift");
     dcn::Off off{w.off, (long)P * dcn::NOFF, dcn::NOFF, 1};
-    SV_TRY(dcn::conv_gemm(a, off, lp[i].wplanes, w.planes, w.y[i & 1], cin, B, H, W, s));
-    dcn::gn_partial_kernel<<<dim3(w.slabs, B), 256, 0, s>>>(w.y[i & 1], w.part, P, cout);
+    SV_TRY(dcn::conv_gemm(w.act, off, lp[i].wplanes, w.planes, w.y, cin, cout, B, H, W, s));
+    dcn::gn_partial_kernel<<<dim3(w.slabs, B), 256, 0, s>>>(w.y, w.part, P, cout);
     SV_CHECK_LAUNCH("dcn_gn_partial");
-    dcn::gn_final_kernel<<<B, 256, 0, s>>>(w.part, w.slabs, B, layers[i].gn_w, layers[i].gn_b, w.aff[i & 1], P, cout);
+    dcn::gn_final_kernel<<<B, 256, 0, s>>>(w.part, w.slabs, B, layers[i].gn_w, layers[i].gn_b, w.aff, P, cout);
     SV_CHECK_LAUNCH("dcn_gn_final");
   }
-  const int last = n_layers - 1, cout = layers[last].c_out;
-  dcn::act_to_nchw_kernel<<<dim3(ceil_div(P, 32), ceil_div(cout, 32), B), 256, 0, s>>>(w.y[last & 1], w.aff[last & 1], out, P, cout);
+  const int cout = layers[n_layers - 1].c_out;
+  dcn::act_to_nchw_kernel<<<dim3(ceil_div(P, 32), ceil_div(cout, 32), B), 256, 0, s>>>(w.y, w.aff, out, P, cout);
   SV_CHECK_LAUNCH("dcn_to_nchw");
-  (void)rows;
   return SLOTVPS_OK;
 }
 
@@ -1499,9 +1501,8 @@ int slotvps_deform_conv_forward(const float* input, const float* weight, const f
   SV_CHECK_LAUNCH("dcn_w_prep");
   dcn::nchw_to_nhwc_kernel<<<dim3(ceil_div(P, 32), ceil_div(c_in, 32), B), 256, 0, s>>>(input, w.xT, c_in, P);
   SV_CHECK_LAUNCH("dcn_to_nhwc");
-  dcn::Act a{w.xT, c_in, nullptr};
   dcn::Off off{offset, (long)P * dcn::NOFF, 1, (long)P};          // NCHW offsets: channel stride P
-  SV_TRY(dcn::conv_gemm(a, off, w.wplanes, w.planes, w.y, c_in, B, H, W, s));
+  SV_TRY(dcn::conv_gemm(w.xT, off, w.wplanes, w.planes, w.y, c_in, c_out, B, H, W, s));
   dcn::act_to_nchw_kernel<<<dim3(ceil_div(P, 32), ceil_div(c_out, 32), B), 256, 0, s>>>(w.y, nullptr, output, P, c_out);
   SV_CHECK_LAUNCH("dcn_to_nchw");
   return SLOTVPS_OK;

@@ -3,12 +3,19 @@
 // deform_conv_forward_cuda, mmdet/ops/dcn/src/deform_conv_cuda.cpp:152 = bilinear im2col (deform_conv_cuda_kernel.cu:190) to an
 // fp32 column buffer + cuBLAS addmm).
 //
-// First B200 form of this row.  Activations stay pixel-major (NHWC) between the layers, so the four bilinear corners of a tap are
-// contiguous channel runs; GroupNorm + ReLU of layer l are folded into the LOADS of layer l+1 (a per-(image, channel) affine);
-// the sampled columns are written once as fp16 hi/lo operand planes [2][pixels][9 C_in] (the same bytes as the reference's fp32
-// column buffer) and the GEMM runs on tcgen05 through the level-fusion kernel's plain-GEMM mode (fuse_tc_kernel with y_out: TMA
-// A/B stages, 3-product fp16 hi/lo, fp32 accumulation in TMEM).  The 18-channel offset convolution is a direct fp32 kernel.
-// Next: gather straight into the shared-memory A stages (no column planes in HBM), offsets from a tensor-core pass.
+// B200 form of this row.  Activations stay pixel-major (NHWC) between the layers, so the four bilinear corners of a tap are
+// contiguous channel runs.  Per layer:
+//   act_planes   GroupNorm + ReLU of the previous layer (a per-(image, channel) affine) applied ONCE: fp32 activation (in place)
+//                + its fp16 hi/lo operand planes
+//   offset conv  (regular 3x3, 18 outputs) as ONE 1x1 tensor-core GEMM with N = 9 taps x 18 = 162 outputs per pixel
+//                (z[p][tap][o] = W_tap[o] . a[p]) followed by a 9-tap shift-sum -- a regular convolution is a sum of shifted
+//                1x1 convolutions, so nothing is gathered and no column buffer exists for it
+//   im2col       bilinear sampling written once as fp16 hi/lo operand planes [2][pixels][9 C_in] (the same bytes as the
+//                reference's fp32 column buffer)
+//   GEMM         tcgen05 through the level-fusion kernel's plain-GEMM mode (TMA A/B stages, 3-product fp16 hi/lo, fp32
+//                accumulation in TMEM), MMA N = c_out
+//   GroupNorm    statistics of the raw output (slab partials in fp32, combined in double, fixed order)
+// Next: gather straight into the shared-memory A stages (no column planes in HBM).
 #pragma once
 #include "common.cuh"
 #include "fuse_tc.cuh"
@@ -36,13 +43,6 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
-// offset-convolution weights [18][C][3][3] -> [tap][c][20] (18 used; rows padded for 16-byte loads)
-__global__ void __launch_bounds__(256) offw_prep_kernel(const float* __restrict__ w, float* __restrict__ out, int Cn) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= KT * Cn * 20) return;
-  const int o = i % 20, c = (i / 20) % Cn, tap = i / (20 * Cn);
-  out[i] = o < NOFF ? w[((long)o * Cn + c) * KT + tap] : 0.f;
-}
 // deformable-conv weights [C_out][C][3][3] -> fp16 hi/lo planes [2][256][K = 9 C] with k = tap * C + c (rows >= C_out zero), x 2^4
 __global__ void __launch_bounds__(256) dcnw_prep_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cout, int Cn) {
   const long K = (long)KT * Cn, i = (long)blockIdx.x * 256 + threadIdx.x;
@@ -53,75 +53,66 @@ __global__ void __launch_bounds__(256) dcnw_prep_kernel(const float* __restrict_
   out[i] = h; out[(long)C * K + i] = l;
 }
 
-// The activation entering a layer: pixel-major rows of `ld` floats, optionally through the previous layer's GroupNorm + ReLU
-// folded into a per-(image, channel) affine aff[b][2][ld] (scale, shift).
-struct Act {
-  const float* x; int ld; const float* aff;
-};
-__device__ __forceinline__ float4 act4(const Act& a, int b, long pix, int c) {
-  float4 v = __ldg(reinterpret_cast<const float4*>(a.x + pix * a.ld + c));
-  if (a.aff) {
-    const float4 s = __ldg(reinterpret_cast<const float4*>(a.aff + (long)b * 2 * a.ld + c));
-    const float4 t = __ldg(reinterpret_cast<const float4*>(a.aff + (long)b * 2 * a.ld + a.ld + c));
-    v.x = fmaxf(fmaf(v.x, s.x, t.x), 0.f); v.y = fmaxf(fmaf(v.y, s.y, t.y), 0.f);
-    v.z = fmaxf(fmaf(v.z, s.z, t.z), 0.f); v.w = fmaxf(fmaf(v.w, s.w, t.w), 0.f);
-  }
-  return v;
+// offset-convolution weights [18][C][3][3] -> fp16 hi/lo planes [2][256][C] with row n = tap * 18 + o (rows >= 162 zero), x 2^4
+__global__ void __launch_bounds__(256) offw_planes_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cn) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= C * Cn) return;
+  const int n = i / Cn, c = i % Cn, tap = n / NOFF, o = n % NOFF;
+  __half h = __float2half_rn(0.f), l = h;
+  if (n < KT * NOFF) split_bf16(w[((long)o * Cn + c) * KT + tap] * ASCALE, h, l);
+  out[i] = h; out[(long)C * Cn + i] = l;
 }
 
-// conv_offset: regular 3x3 convolution C -> 18, padding 1 (+ bias); one thread per pixel, 32-channel weight tiles in shared memory.
-// off [B][P][18]
-__global__ void __launch_bounds__(256) offset_conv_kernel(const Act a, const float* __restrict__ wt /*[9][C][20]*/, const float* __restrict__ bias,
-                                                          float* __restrict__ off, int Cn, int H, int W) {
-  __shared__ __align__(16) float ws[KT][32][20];
-  const int b = blockIdx.y, P = H * W, p = blockIdx.x * 256 + threadIdx.x;
-  const bool live = p < P;
-  const int y = live ? p / W : 0, x = live ? p % W : 0;
-  float acc[NOFF];
+// The activation entering a layer, materialised once: a[row][c] = relu(src[row][c] * scale[b][c] + shift[b][c]) (aff == null: the
+// values as they are) -> dst fp32 [rows][Cn] (may alias src when ld == Cn; null: not written) and fp16 hi/lo planes [2][rows][Cn] x 2^4.
+// One thread per 8 channels.
+__global__ void __launch_bounds__(256) act_planes_kernel(const float* src, int ld, const float* __restrict__ aff, float* dst,
+                                                         __half* __restrict__ planes, long rows, int Cn, int P) {
+  const int cpr = Cn / 8;
+  const long n = rows * cpr;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    const long row = i / cpr;
+    const int c = (int)(i % cpr) * 8;
+    float v[8];
+    tc::ld_global_nc_v8f(src + row * ld + c, v);
+    if (aff) {
+      const float* sc = aff + (row / P) * 2 * C + c;
 #pragma unroll
-  for (int o = 0; o < NOFF; ++o) acc[o] = bias[o];
-  for (int c0 = 0; c0 < Cn; c0 += 32) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < KT * 32 * 20; i += 256) {
-      const int o = i % 20, c = (i / 20) % 32, tap = i / 640;
-      ws[tap][c][o] = wt[((long)tap * Cn + c0 + c) * 20 + o];
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(v[e], __ldg(sc + e), __ldg(sc + C + e)), 0.f);
     }
-    __syncthreads();
-    if (!live) continue;
-#pragma unroll 1
-    for (int tap = 0; tap < KT; ++tap) {
-      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const long pix = (long)b * P + (long)yy * W + xx;
-#pragma unroll 2
-      for (int c = 0; c < 32; c += 4) {
-        const float4 v = act4(a, b, pix, c0 + c);
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+    if (dst) tc::st_global_v8f(dst + row * Cn + c, v);
+    uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float4* wr = reinterpret_cast<const float4*>(&ws[tap][c + e][0]);
-          const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
-          const float2 w4 = *reinterpret_cast<const float2*>(&ws[tap][c + e][16]);
-          acc[0] = fmaf(vv[e], w0.x, acc[0]); acc[1] = fmaf(vv[e], w0.y, acc[1]); acc[2] = fmaf(vv[e], w0.z, acc[2]); acc[3] = fmaf(vv[e], w0.w, acc[3]);
-          acc[4] = fmaf(vv[e], w1.x, acc[4]); acc[5] = fmaf(vv[e], w1.y, acc[5]); acc[6] = fmaf(vv[e], w1.z, acc[6]); acc[7] = fmaf(vv[e], w1.w, acc[7]);
-          acc[8] = fmaf(vv[e], w2.x, acc[8]); acc[9] = fmaf(vv[e], w2.y, acc[9]); acc[10] = fmaf(vv[e], w2.z, acc[10]); acc[11] = fmaf(vv[e], w2.w, acc[11]);
-          acc[12] = fmaf(vv[e], w3.x, acc[12]); acc[13] = fmaf(vv[e], w3.y, acc[13]); acc[14] = fmaf(vv[e], w3.z, acc[14]); acc[15] = fmaf(vv[e], w3.w, acc[15]);
-          acc[16] = fmaf(vv[e], w4.x, acc[16]); acc[17] = fmaf(vv[e], w4.y, acc[17]);
-        }
-      }
-    }
+    for (int e = 0; e < 4; ++e) split2(v[2 * e] * ASCALE, v[2 * e + 1] * ASCALE, hi[e], lo[e]);
+    *reinterpret_cast<uint4*>(planes + row * Cn + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(planes + (rows + row) * Cn + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
-  if (live) {
-    float* dst = off + ((long)b * P + p) * NOFF;
+}
+
+// off[b][p][o] = bias[o] + sum over the 9 taps of z[b][p + (ky-1) W + (kx-1)][tap * 18 + o], neighbours outside the map skipped
+// (zero padding).  One thread per (pixel, o); z rows are 256 floats.
+__global__ void __launch_bounds__(256) offset_shift_kernel(const float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ off,
+                                                           int H, int W, long rows) {
+  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= rows * NOFF) return;
+  const int o = (int)(i % NOFF);
+  const long row = i / NOFF;
+  const int P = H * W, p = (int)(row % P), y = p / W, x = p % W;
+  float acc = __ldg(bias + o);
 #pragma unroll
-    for (int o = 0; o < NOFF; ++o) dst[o] = acc[o];
+  for (int tap = 0; tap < KT; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    acc += __ldg(z + (row + (long)(tap / 3 - 1) * W + (tap % 3 - 1)) * C + tap * NOFF + o);
   }
+  off[i] = acc;
 }
 
 // bilinear im2col (deform_conv_cuda_kernel.cu:190-236 with deformable_im2col_bilinear :80-112): one item = (pixel, tap, 8 channels);
 // zero outside (-1, H) x (-1, W), corners outside the map contribute zero.  planes [2][rows][9 C] fp16 hi/lo, x 2^4.
 struct Off { const float* p; long bs, ps, cs; };                     // offset (b, pixel, channel) at p[b * bs + pixel * ps + channel * cs]; p == null: regular conv
-__global__ void __launch_bounds__(256) dcn_im2col_kernel(const Act a, const Off off, __half* __restrict__ planes, long rows, int Cn, int H, int W, int B) {
+__global__ void __launch_bounds__(256) dcn_im2col_kernel(const float* __restrict__ act /*[rows][Cn]*/, const Off off, __half* __restrict__ planes, long rows, int Cn,
+                                                         int H, int W, int B) {
   const int cpp = Cn / 8;                                           // 8-channel chunks per (pixel, tap)
   const long P = (long)H * W, n = (long)B * P * KT * cpp, K = (long)KT * Cn;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
@@ -146,10 +137,11 @@ __global__ void __launch_bounds__(256) dcn_im2col_kernel(const Act a, const Off 
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int c = ch + 4 * q;
-        const float4 v1 = (t && lf) ? act4(a, b, base + (long)h_low * W + w_low, c) : z;
-        const float4 v2 = (t && rt) ? act4(a, b, base + (long)h_low * W + w_high, c) : z;
-        const float4 v3 = (bt && lf) ? act4(a, b, base + (long)h_high * W + w_low, c) : z;
-        const float4 v4 = (bt && rt) ? act4(a, b, base + (long)h_high * W + w_high, c) : z;
+        auto ld = [&](long pix) { return __ldg(reinterpret_cast<const float4*>(act + pix * Cn + c)); };
+        const float4 v1 = (t && lf) ? ld(base + (long)h_low * W + w_low) : z;
+        const float4 v2 = (t && rt) ? ld(base + (long)h_low * W + w_high) : z;
+        const float4 v3 = (bt && lf) ? ld(base + (long)h_high * W + w_low) : z;
+        const float4 v4 = (bt && rt) ? ld(base + (long)h_high * W + w_high) : z;
         v[4 * q + 0] = w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
         v[4 * q + 1] = w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
         v[4 * q + 2] = w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
@@ -221,26 +213,30 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(const float* __restric
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
-struct LayerPrep { float* offw; __half* wplanes; };           // [9][C_in][20], [2][256][9 C_in]
+struct LayerPrep { __half *offw, *wplanes; };                 // [2][256][C_in] (162 rows used), [2][256][9 C_in]
 inline size_t prep_layout(const slotvps_dcn_layer* L, int n, void* base, LayerPrep* out) {
   Arena a(base, (size_t)-1);
   for (int i = 0; i < n; ++i) {
     LayerPrep lp;
-    lp.offw = a.take<float>((size_t)KT * L[i].c_in * 20);
+    lp.offw = a.take<__half>((size_t)2 * C * L[i].c_in);
     lp.wplanes = a.take<__half>((size_t)2 * C * KT * L[i].c_in);
     if (out) out[i] = lp;
   }
   return a.off;
 }
-struct Ws { float *xT, *y[2], *off, *aff[2]; __half* planes; double* part; int slabs; };
+// act: fp32 activation entering the current layer [rows][cin]; y: raw conv output [rows][256] (becomes the next activation in place
+// when c_out == 256, else compacted into act); z: offset-GEMM output [rows][256]; aplanes: activation planes [2][rows][cin]
+struct Ws { float *act, *y, *z, *off, *aff; __half *aplanes, *planes; double* part; int slabs; };
 inline size_t ws_layout(int cin_max, int B, int H, int W, void* base, Ws* w) {
   Arena a(base, (size_t)-1);
   const size_t rows = (size_t)B * H * W;
   Ws x;
-  x.xT = a.take<float>(rows * cin_max);
-  x.y[0] = a.take<float>(rows * C); x.y[1] = a.take<float>(rows * C);
+  x.act = a.take<float>(rows * C);
+  x.y = a.take<float>(rows * C);
+  x.z = a.take<float>(rows * C);
   x.off = a.take<float>(rows * NOFF);
-  x.aff[0] = a.take<float>((size_t)B * 2 * C); x.aff[1] = a.take<float>((size_t)B * 2 * C);
+  x.aff = a.take<float>((size_t)B * 2 * C);
+  x.aplanes = a.take<__half>((size_t)2 * rows * cin_max + 64);
   x.planes = a.take<__half>((size_t)2 * rows * KT * cin_max + 64);
   x.slabs = ceil_div(H * W, GN_SLAB);
   x.part = a.take<double>((size_t)x.slabs * B * NG * 2);
@@ -252,18 +248,22 @@ inline int validate_layer(const slotvps_dcn_layer& l) {
   if (l.c_out <= 0 || l.c_out % NG != 0 || l.c_out > C) return fail(SLOTVPS_EINVAL, "dcn: c_out must be a multiple of 32 and <= 256%s%s");
   return SLOTVPS_OK;
 }
-// columns + GEMM of one deformable (off != null) convolution: a -> y [rows][256] raw
-inline int conv_gemm(const Act& a, const Off& off, const __half* wplanes, __half* planes, float* y, int Cn, int B, int H, int W, cudaStream_t s) {
-  const long rows = (long)B * H * W, K = (long)KT * Cn;
-  const long items = rows * KT * (Cn / 8);
-  const int grid = (int)((items + 255) / 256 < 148L * 32 ? (items + 255) / 256 : 148L * 32);
-  dcn_im2col_kernel<<<grid, 256, 0, s>>>(a, off, planes, rows, Cn, H, W, B);
-  SV_CHECK_LAUNCH("dcn_im2col");
+inline int grid_for(long items) { const long g = (items + 255) / 256; return (int)(g < 148L * 32 ? g : 148L * 32); }
+// plain tensor-core GEMM y[rows][256] (first n_out columns) = A[rows][K] . W[n][K]^T / 2^8 with A, W as fp16 hi/lo planes
+inline int gemm(const __half* a_planes, long rows, int K, const __half* w_planes, float* y, int n_out, int H, int W, cudaStream_t s) {
   fuse::Params prm;
   memset(&prm, 0, sizeof(prm));
-  prm.rows = (int)rows; prm.P = H * W; prm.w = W; prm.h = H; prm.ksub = (int)(K / 64); prm.a_lo_row = (int)rows; prm.y_out = y;
-  SV_TRY(fuse_tc_launch(planes, 2 * rows, (int)rows, (int)K, wplanes, prm, s));
-  return SLOTVPS_OK;
+  prm.rows = (int)rows; prm.P = H * W; prm.w = W; prm.h = H; prm.ksub = K / 64; prm.a_lo_row = (int)rows; prm.y_out = y;
+  prm.n_out = n_out >= C ? 0 : n_out;
+  return fuse_tc_launch(a_planes, 2 * rows, (int)rows, K, w_planes, prm, s);
+}
+// columns + GEMM of one deformable (off.p != null) convolution: act [rows][Cn] -> y [rows][256] raw (first c_out columns)
+inline int conv_gemm(const float* act, const Off& off, const __half* wplanes, __half* planes, float* y, int Cn, int c_out, int B, int H, int W,
+                     cudaStream_t s) {
+  const long rows = (long)B * H * W;
+  dcn_im2col_kernel<<<grid_for(rows * KT * (Cn / 8)), 256, 0, s>>>(act, off, planes, rows, Cn, H, W, B);
+  SV_CHECK_LAUNCH("dcn_im2col");
+  return gemm(planes, rows, KT * Cn, wplanes, y, (c_out + 15) / 16 * 16, H, W, s);
 }
 
 }  // namespace dcn

@@ -38,6 +38,7 @@ struct Params {
   const float* bias;   // [256] or null (coarse)
   // coarse output
   float* y_out;        // [rows][256] or null
+  int n_out;           // plain-GEMM mode only: output columns actually computed (multiple of 16, <= 256; 0 = 256): MMA N, weight box rows
   // main outputs
   const float* y_in;   // coarse y [T * P/4][256] or null (level 0)
   float* out;          // NCHW fp32, frame t at out + t*out_bs, or null
@@ -161,7 +162,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int s = it % NSTAGE;
           tc::mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
-          tc::mbar_expect_tx(&full[s], STAGE_BYTES);
+          tc::mbar_expect_tx(&full[s], prm.n_out ? 2 * A_BYTES + 2 * prm.n_out * 128 : STAGE_BYTES);
           if (prm.a_split) {
             tc::tma_load_2d(st, &tmap_a, 0, ks * prm.a_lo_row + row, &full[s]);
             tc::tma_load_2d(st + A_BYTES, &tmap_a, 0, (4 + ks) * prm.a_lo_row + row, &full[s]);
@@ -177,6 +178,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t it = 0, ti = 0;
+      const uint32_t idesc = prm.n_out ? tc::make_idesc_f16(128, prm.n_out, 0, 0) : IDESC;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
         const int g = ti & 1, u = ti >> 1;
         tc::mbar_wait(&tempty[g], (u & 1) ^ 1);
@@ -192,9 +194,9 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t dbh = tc::make_smem_desc_sw128(b_hi, 16, 1024), dbl = tc::make_smem_desc_sw128(b_lo, 16, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            tc::umma_bf16(d_tmem, dah + 2 * k, dbh + 2 * k, IDESC, (ks | k) != 0);
-            tc::umma_bf16(d_tmem, dal + 2 * k, dbh + 2 * k, IDESC, 1);
-            tc::umma_bf16(d_tmem, dah + 2 * k, dbl + 2 * k, IDESC, 1);
+            tc::umma_bf16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (ks | k) != 0);
+            tc::umma_bf16(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);
+            tc::umma_bf16(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
           }
           tc::umma_commit(&empty[s]);
         }
@@ -256,6 +258,10 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll 1
       for (int uu = 0; uu < 4; ++uu) {
         const int u = jq * 4 + uu;                            // 16-channel unit: channels [16 u, 16 u + 16)
+        if (prm.n_out && u * 16 >= prm.n_out) {               // columns the narrowed MMA did not compute
+          if (uu == 3) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }
+          continue;
+        }
         float v[16];
         tc::tmem_ld16(tmem_base + lane_addr + g * 256 + u * 16, v);
         tc::tmem_ld_wait();
@@ -365,7 +371,7 @@ inline int fuse_tc_launch(const __half* a_planes, long a_rows_total, int a_lo_ro
   CUtensorMap ma, mw;
   if (prm.a_split) SV_TRY(tc::make_tmap_h16_sw128(&ma, a_planes, (uint64_t)4 * a_rows_total, 64, fuse::TILE_M));
   else SV_TRY(tc::make_tmap_h16_sw128(&ma, a_planes, (uint64_t)a_rows_total, (uint64_t)K, fuse::TILE_M));
-  SV_TRY(tc::make_tmap_h16_sw128(&mw, w_planes, (uint64_t)2 * C, (uint64_t)K, C));
+  SV_TRY(tc::make_tmap_h16_sw128(&mw, w_planes, (uint64_t)2 * C, (uint64_t)K, prm.n_out ? prm.n_out : C));
   SV_TRY(ensure_dyn_smem((const void*)fuse_tc_kernel, fuse::SMEM_BYTES));
   const int n_tiles = ceil_div(prm.rows, fuse::TILE_M);
   const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
