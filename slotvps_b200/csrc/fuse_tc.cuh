@@ -134,7 +134,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   float* bias = reinterpret_cast<float*>(aux + 256);
   float* bnv = bias + C;                                    // [2][256] feat_bn scale, shift (when prm.ss_out)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // provably warp-uniform
   const int n_tiles = (prm.rows + TILE_M - 1) / TILE_M;
   if (prm.ss_out)
     for (int i = threadIdx.x; i < 2 * C; i += THREADS) bnv[i] = i < C ? prm.bn_sc[i] : prm.bn_sh[i - C];
@@ -151,7 +151,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -176,7 +176,8 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                         // all lanes: warp-uniform issue loop, one elected lane issues (tc::elect_one)
+      const bool el = tc::elect_one();
       uint32_t it = 0, ti = 0;
       const uint32_t idesc = prm.n_out ? tc::make_idesc_f16(128, prm.n_out, 0, 0) : IDESC;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
@@ -192,15 +193,17 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
           const uint64_t dah = tc::make_smem_desc_sw128(a_hi, 16, 1024), dal = tc::make_smem_desc_sw128(a_lo, 16, 1024);
           const uint64_t dbh = tc::make_smem_desc_sw128(b_hi, 16, 1024), dbl = tc::make_smem_desc_sw128(b_lo, 16, 1024);
+          if (el) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tc::umma_bf16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (ks | k) != 0);
-            tc::umma_bf16(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);
-            tc::umma_bf16(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+            for (int k = 0; k < 4; ++k) {
+              tc::umma_bf16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (ks | k) != 0);
+              tc::umma_bf16(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);
+              tc::umma_bf16(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+            }
+            tc::umma_commit(&empty[s]);
           }
-          tc::umma_commit(&empty[s]);
         }
-        tc::umma_commit(&tfull[g]);
+        if (el) tc::umma_commit(&tfull[g]);
       }
     }
   } else {

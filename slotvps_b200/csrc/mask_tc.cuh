@@ -40,7 +40,7 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint64_t* efull = tempty + 2;                            // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(efull + 1);
   float* dsm = reinterpret_cast<float*>(misc + 256);       // [NPAD]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // provably warp-uniform
   const int n_tiles = (P + TILE_M - 1) / TILE_M;
 
   if (threadIdx.x == 0) {
@@ -56,7 +56,7 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -76,7 +76,8 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                         // all lanes: warp-uniform issue loop, one elected lane issues (tc::elect_one)
+      const bool el = tc::elect_one();
       tc::mbar_wait(efull, 0);
       tc::tc_fence_after();
       const uint32_t e_base = tc::smem_u32(smem + OFF_E);
@@ -94,15 +95,17 @@ mask_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             tc::mbar_wait(&full[s], (it / NSLOT) & 1);
             tc::tc_fence_after();
             const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), 16, 1024);
+            if (el) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              tc::umma_bf16(d, da + 2 * k, deh + 2 * k, IDESC, (ks | pl | k) != 0);
-              if (pl == 0) tc::umma_bf16(d, da + 2 * k, del + 2 * k, IDESC, 1);
+              for (int k = 0; k < 4; ++k) {
+                tc::umma_bf16(d, da + 2 * k, deh + 2 * k, IDESC, (ks | pl | k) != 0);
+                if (pl == 0) tc::umma_bf16(d, da + 2 * k, del + 2 * k, IDESC, 1);
+              }
+              tc::umma_commit(&empty[s]);
             }
-            tc::umma_commit(&empty[s]);
           }
         }
-        tc::umma_commit(&tfull[g]);
+        if (el) tc::umma_commit(&tfull[g]);
       }
     }
   } else {

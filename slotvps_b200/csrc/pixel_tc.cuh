@@ -543,7 +543,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(stats3::THREADS, 1)
 stats_tri_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_r0, const __grid_constant__ CUtensorMap tmap_r1,
                  const __grid_constant__ CUtensorMap tmap_r2, const __grid_constant__ CUtensorMap tmap_r3,      // boxes of 32, 64, 96, 128 weight rows
                  const float* __restrict__ rbias, float* __restrict__ rs_k, float* __restrict__ rs_v, int P, int T, int plane_rows,
-                 int tiles_per_frame, int x_planes_only) {
+                 int tiles_per_frame, int x_planes_only, int products) {
   using namespace stats3;
   extern __shared__ uint8_t raw_smem[];
   const uint32_t raw = tc::smem_u32(raw_smem);
@@ -555,7 +555,7 @@ stats_tri_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint64_t* tempty = tfull + 2;                                       // [2] on the leader: 256 arrivals
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
   float* bias = reinterpret_cast<float*>(aux + 256);                  // [2][256] in accumulator-column order
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // provably warp-uniform
   const uint32_t rank = tc::cluster_ctarank();
   const bool leader = rank == 0;
   const int n_tiles = T * tiles_per_frame;
@@ -574,7 +574,7 @@ stats_tri_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   __syncthreads();
   tc::cluster_sync();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -601,7 +601,8 @@ stats_tri_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {                                             // all lanes of the leader CTA's warp: warp-uniform issue loop (tc::elect_one)
+      const bool el = tc::elect_one();
       uint32_t it = 0;
       for (int i = 0; i < n_iter; ++i) {
         for (int g = 0; g < 2; ++g) {
@@ -617,15 +618,17 @@ stats_tri_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
             const uint64_t dah = tc::make_smem_desc_sw128(a_hi, 16, 1024), dal = tc::make_smem_desc_sw128(a_lo, 16, 1024);
             const uint64_t dbh = tc::make_smem_desc_sw128(b_hi, 16, 1024), dbl = tc::make_smem_desc_sw128(b_lo, 16, 1024);
+            if (el) {
 #pragma unroll
-            for (int k = 0; k < KSUB / 16; ++k) {
-              tc::umma2_f16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (ks != C / KSUB - 1 || k != 0) ? 1u : 0u);
-              tc::umma2_f16(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);
-              tc::umma2_f16(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+              for (int k = 0; k < KSUB / 16; ++k) {
+                tc::umma2_f16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (ks != C / KSUB - 1 || k != 0) ? 1u : 0u);
+                if (products >= 2) tc::umma2_f16(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);      // experiment switch; 3 = shipped
+                if (products >= 3) tc::umma2_f16(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+              }
+              tc::umma2_commit_multicast(&empty[s], 3);
             }
-            tc::umma2_commit_multicast(&empty[s], 3);
           }
-          tc::umma2_commit_multicast(&tfull[g], 3);
+          if (el) tc::umma2_commit_multicast(&tfull[g], 3);
         }
       }
     }
@@ -711,7 +714,11 @@ inline int tc_stats(const TcStageOperands& ops, const TcWorkspace& ws, const flo
     int grid3 = 2 * ((n_tiles + 1) / 2);
     if (grid3 > (max_ctas & ~1)) grid3 = max_ctas & ~1;
     g_prof_grid = grid3;
-    stats_tri_kernel<<<grid3, stats3::THREADS, stats3::SMEM_BYTES, s>>>(mx, mr[0], mr[1], mr[2], mr[3], ops.rbias, rs_k, rs_v, P, T, (int)rows, tiles_per_frame, ps.enabled);
+    // measurement switch only: 1 = hi.hi, 2 = hi.hi + lo_x.hi_w, 3 (default, shipped) = + hi_x.lo_w; read per call so one process can compare
+    const char* pe = getenv("SLOTVPS_STATS_PRODUCTS");
+    const int products = pe && atoi(pe) >= 1 && atoi(pe) <= 3 ? atoi(pe) : 3;
+    stats_tri_kernel<<<grid3, stats3::THREADS, stats3::SMEM_BYTES, s>>>(mx, mr[0], mr[1], mr[2], mr[3], ops.rbias, rs_k, rs_v, P, T, (int)rows, tiles_per_frame,
+                                                                        ps.enabled, products);
     SV_CHECK_LAUNCH("stats_tc");
     return SLOTVPS_OK;
   }
@@ -832,7 +839,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   float2* gc = reinterpret_cast<float2*>(misc + 128);      // [NPAD] (g0, g1)
   float* xch = reinterpret_cast<float*>(misc + 1024);      // [2 kinds][2 halves][128] softmax max / sum exchange between a pixel's two threads
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // provably warp-uniform
   const int chunk = blockIdx.x, chunks = gridDim.x, t = blockIdx.y;
   const int n_my = (tiles_per_frame - chunk + chunks - 1) / chunks;       // tiles chunk, chunk+chunks, ...
 
@@ -858,7 +865,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ===================== TMA producer (lane 0) + L2 prefetchers (lanes 1..31) =====================
@@ -912,8 +919,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: warp-uniform loops, one elected lane issues (tc::elect_one) =====================
+    {
+      const bool el = tc::elect_one();
       tc::mbar_wait(gfull, 0);
       tc::tc_fence_after();
       const uint32_t g_base = tc::smem_u32(smem + OFF_G), p_base = tc::smem_u32(smem + OFF_P), x_base = tc::smem_u32(smem + OFF_AUX);
@@ -926,6 +934,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const bool prof = (dbg & 16) != 0;
       long long wS = 0, wZ = 0, wP = 0, wE = 0, tC = 0;
       auto timed_commit = [&](uint64_t* bar) {
+        if (!el) return;
         if (!prof) { tc::umma_commit(bar); return; }
         const long long t0 = clock64();
         tc::umma_commit(bar);
@@ -951,10 +960,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             timed_wait(&full[s], (it / NSLOT) & 1, wS);
             tc::tc_fence_after();
             const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), 16, 1024);
+            if (el) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              tc::umma_bf16(d, da + 2 * k, dgh + 2 * k, IDESC_S, (ks | k) != 0);
-              tc::umma_bf16(d, da + 2 * k, dgl + 2 * k, IDESC_S, 1);
+              for (int k = 0; k < 4; ++k) {
+                tc::umma_bf16(d, da + 2 * k, dgh + 2 * k, IDESC_S, (ks | k) != 0);
+                tc::umma_bf16(d, da + 2 * k, dgl + 2 * k, IDESC_S, 1);
+              }
             }
             timed_commit(&empty[s]);
             ++it;
@@ -964,8 +975,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             timed_wait(&full[s], (it / NSLOT) & 1, wS);
             tc::tc_fence_after();
             const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), 16, 1024);
+            if (el) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_bf16(d, da + 2 * k, dgh + 2 * k, IDESC_S, 1);
+              for (int k = 0; k < 4; ++k) tc::umma_bf16(d, da + 2 * k, dgh + 2 * k, IDESC_S, 1);
+            }
             timed_commit(&empty[s]);
             ++it;
           }
@@ -984,30 +997,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             tc::tc_fence_after();
             // A: x tile as MN-major operand: 64-channel groups SLOT_BYTES apart, 8-pixel groups 1024 B apart
             const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem + s * SLOT_BYTES), SLOT_BYTES, 1024);
+            if (el) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {                   // 16 pixels per MMA: A advances 16 rows (2048 B), B 32 B inside its 64-pixel half
-              const uint32_t poff = (k >> 2) * P_SUB + (k & 3) * 32;
-              tc::umma_bf16(d, da + (uint64_t)(k * 128), tc::make_smem_desc_sw128(p_base + poff, 16, 1024), IDESC_Z, (i | pl | k) != 0);
-              if (pl == 0) tc::umma_bf16(d, da + (uint64_t)(k * 128), tc::make_smem_desc_sw128(p_base + P_PLANE + poff, 16, 1024), IDESC_Z, 1);
+              for (int k = 0; k < 8; ++k) {                 // 16 pixels per MMA: A advances 16 rows (2048 B), B 32 B inside its 64-pixel half
+                const uint32_t poff = (k >> 2) * P_SUB + (k & 3) * 32;
+                tc::umma_bf16(d, da + (uint64_t)(k * 128), tc::make_smem_desc_sw128(p_base + poff, 16, 1024), IDESC_Z, (i | pl | k) != 0);
+                if (pl == 0) tc::umma_bf16(d, da + (uint64_t)(k * 128), tc::make_smem_desc_sw128(p_base + P_PLANE + poff, 16, 1024), IDESC_Z, 1);
+              }
             }
             timed_commit(&empty[s]);
             timed_commit(&empty[s + 1]);
             it += 2;
           }
         }
+        if (el) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {                       // aux[n, :] += (P hi + P lo)[n, px] . (1, sigma_v[px], 0...)
-          const uint32_t poff = (k >> 2) * P_SUB + (k & 3) * 32;
-          const uint64_t dx = tc::make_smem_desc_sw128(x_base + (k >> 2) * AUX_SUB + (k & 3) * 32, 16, 1024);
-          tc::umma_bf16(tmem_base + TM_AUX, tc::make_smem_desc_sw128(p_base + poff, 16, 1024), dx, IDESC_AUX, (i | k) != 0);
-          tc::umma_bf16(tmem_base + TM_AUX, tc::make_smem_desc_sw128(p_base + P_PLANE + poff, 16, 1024), dx, IDESC_AUX, 1);
+          for (int k = 0; k < 8; ++k) {                     // aux[n, :] += (P hi + P lo)[n, px] . (1, sigma_v[px], 0...)
+            const uint32_t poff = (k >> 2) * P_SUB + (k & 3) * 32;
+            const uint64_t dx = tc::make_smem_desc_sw128(x_base + (k >> 2) * AUX_SUB + (k & 3) * 32, 16, 1024);
+            tc::umma_bf16(tmem_base + TM_AUX, tc::make_smem_desc_sw128(p_base + poff, 16, 1024), dx, IDESC_AUX, (i | k) != 0);
+            tc::umma_bf16(tmem_base + TM_AUX, tc::make_smem_desc_sw128(p_base + P_PLANE + poff, 16, 1024), dx, IDESC_AUX, 1);
+          }
         }
         timed_commit(pempty);                            // P may be overwritten once these retire
       };
       issue_s(0);
       for (int i = 0; i < n_my; ++i) { if (i + 1 < n_my) issue_s(i + 1); if (MODE != 1) issue_z(i); }
-      if (MODE != 1) tc::umma_commit(zfull);
-      if (prof && blockIdx.x == 0 && blockIdx.y == 0)
+      if (MODE != 1 && el) tc::umma_commit(zfull);
+      if (prof && el && blockIdx.x == 0 && blockIdx.y == 0)
         printf("attn_tc tiles=%d cycles=%lld wait: S-operands %lld Z-operands %lld softmax %lld S-buffer %lld | in tcgen05.commit %lld\n", n_my, clock64() - t_begin, wS, wZ, wP, wE, tC);
     }
   } else {

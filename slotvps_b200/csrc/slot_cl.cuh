@@ -104,7 +104,8 @@ __device__ __forceinline__ void prod_slice(uint8_t* smem, Bars* b, uint32_t& it,
 // The hi.hi products accumulate at d_tmem, the two cross products (2^-11 of the magnitude) at d_tmem + CORR: the fp32
 // accumulator of the tensor pipe does not round to nearest, so every accumulation step costs up to an ulp of the running
 // sum with a systematic sign; keeping the 32 small steps out of the main sum leaves 16 of the 48.
-__device__ __forceinline__ void mma_slice(uint8_t* smem, Bars* b, uint32_t& it, uint32_t d_tmem, uint32_t act, uint32_t idesc,
+// Runs on ALL lanes of the MMA warp (warp-uniform waits and descriptors); `el` = tc::elect_one() guards the tcgen05 instructions.
+__device__ __forceinline__ void mma_slice(bool el, uint8_t* smem, Bars* b, uint32_t& it, uint32_t d_tmem, uint32_t act, uint32_t idesc,
                                           uint32_t corr = CORR) {
   const uint32_t d_corr = d_tmem + corr;
 #pragma unroll 1
@@ -116,12 +117,14 @@ __device__ __forceinline__ void mma_slice(uint8_t* smem, Bars* b, uint32_t& it, 
       tc::mbar_wait(&b->full[s], (it / NSL) & 1);
       tc::tc_fence_after();
       const uint64_t dbh = tc::make_smem_desc_sw128(tc::smem_u32(smem + OFF_RING + s * WT), 16, 1024);
+      if (el) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        tc::umma_bf16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (ks != 0 || k != 0) ? 1u : 0u);
-        tc::umma_bf16(d_corr, dal + 2 * k, dbh + 2 * k, idesc, (ks != 0 || k != 0) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) {
+          tc::umma_bf16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (ks != 0 || k != 0) ? 1u : 0u);
+          tc::umma_bf16(d_corr, dal + 2 * k, dbh + 2 * k, idesc, (ks != 0 || k != 0) ? 1u : 0u);
+        }
+        tc::umma_commit(&b->empty[s]);
       }
-      tc::umma_commit(&b->empty[s]);
       ++it;
     }
     {
@@ -129,9 +132,11 @@ __device__ __forceinline__ void mma_slice(uint8_t* smem, Bars* b, uint32_t& it, 
       tc::mbar_wait(&b->full[s], (it / NSL) & 1);
       tc::tc_fence_after();
       const uint64_t dbl = tc::make_smem_desc_sw128(tc::smem_u32(smem + OFF_RING + s * WT), 16, 1024);
+      if (el) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tc::umma_bf16(d_corr, dah + 2 * k, dbl + 2 * k, idesc, 1);
-      tc::umma_commit(&b->empty[s]);
+        for (int k = 0; k < 4; ++k) tc::umma_bf16(d_corr, dah + 2 * k, dbl + 2 * k, idesc, 1);
+        tc::umma_commit(&b->empty[s]);
+      }
       ++it;
     }
   }
@@ -303,7 +308,7 @@ __device__ __forceinline__ uint32_t prologue(Bars* b, int warp, uint32_t tmem_co
   __syncthreads();
   tc::cluster_sync();                                               // every CTA's barriers exist before a peer targets them
   tc::tc_fence_after();
-  return b->tmem_ptr;
+  return __shfl_sync(0xffffffffu, b->tmem_ptr, 0);                  // provably warp-uniform (uniform-register descriptors)
 }
 __device__ __forceinline__ void epilogue_exit(uint32_t tmem_base, int warp, uint32_t tmem_cols) {
   tc::tc_fence_before();
@@ -320,7 +325,7 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
   const uint32_t raw = tc::smem_u32(raw_smem);
   uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
   Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, vf = blockIdx.x / CL;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, vf = blockIdx.x / CL;
   const RowGroup rg = row_group(vf, P.N, P.G);
   const int t = rg.t, N = rg.n;                 // frame; slot rows of this cluster's group
   const uint32_t rank = tc::cluster_ctarank();
@@ -336,15 +341,16 @@ slot_pre_cl(const __grid_constant__ CUtensorMap m_out, const __grid_constant__ C
       prod_slice(smem, b, it, &m_wk, hi_row, lo_row);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                             // all lanes: warp-uniform issue loop (see tc::elect_one)
+      const bool el = tc::elect_one();
       uint32_t it = 0;
       const uint32_t act = tc::smem_u32(smem + OFF_ACT);
       for (int g = 0; g < 3; ++g) {
         tc::mbar_wait(&b->aready, g & 1);
         if (g > 0) tc::mbar_wait(&b->opfull, (g - 1) & 1);        // the peers' slices of the LayerNorm-output operand
         tc::tc_fence_after();
-        mma_slice(smem, b, it, tmem_base, act, IDESC64);
-        tc::umma_commit(&b->dfull);
+        mma_slice(el, smem, b, it, tmem_base, act, IDESC64);
+        if (el) tc::umma_commit(&b->dfull);
       }
     }
   } else {
@@ -474,7 +480,7 @@ slot_post_cl(const __grid_constant__ CUtensorMap m_wv, const PostParams P) {
   const uint32_t raw = tc::smem_u32(raw_smem);
   uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
   Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, vf = blockIdx.x / CL;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, vf = blockIdx.x / CL;
   const RowGroup rg = row_group(vf, P.N, P.G);
   const int t = rg.t, N = rg.n;                 // frame; slot rows of this cluster's group
   const uint32_t rank = tc::cluster_ctarank();
@@ -486,12 +492,13 @@ slot_post_cl(const __grid_constant__ CUtensorMap m_wv, const PostParams P) {
       prod_slice(smem, b, it, &m_wv, (int)rank * NCOL, C + (int)rank * NCOL);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                             // all lanes: warp-uniform issue loop (see tc::elect_one)
+      const bool el = tc::elect_one();
       uint32_t it = 0;
       tc::mbar_wait(&b->aready, 0);
       tc::tc_fence_after();
-      mma_slice(smem, b, it, tmem_base, tc::smem_u32(smem + OFF_ACT), IDESC64);       // Y = Z . Wv_c^T
-      tc::umma_commit(&b->dfull);
+      mma_slice(el, smem, b, it, tmem_base, tc::smem_u32(smem + OFF_ACT), IDESC64);       // Y = Z . Wv_c^T
+      if (el) tc::umma_commit(&b->dfull);
     }
   } else {
     Ctx c = make_ctx(smem, b, tmem_base, rank, N, nullptr);
@@ -535,7 +542,7 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
   const uint32_t raw = tc::smem_u32(raw_smem);
   uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
   Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, vf = blockIdx.x / CL;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, vf = blockIdx.x / CL;
   const RowGroup rg = row_group(vf, P.N, P.G);
   const int t = rg.t, N = rg.n;                 // frame; slot rows of this cluster's group
   const uint32_t rank = tc::cluster_ctarank();
@@ -552,7 +559,8 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
       prod_slice(smem, b, it, &m_r1, hi_row, lo_row);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                             // all lanes: warp-uniform issue loop (see tc::elect_one)
+      const bool el = tc::elect_one();
       uint32_t it = 0, na = 0;
       const uint32_t act = tc::smem_u32(smem + OFF_ACT);
       auto wait_act = [&]() {                                       // after the first: also the peers' operand slices
@@ -562,18 +570,18 @@ slot_towers_cl(const __grid_constant__ CUtensorMap m_tw, const __grid_constant__
         tc::tc_fence_after();
       };
       wait_act();
-      mma_slice(smem, b, it, tmem_base, act, IDESC64);                            // cls0
-      mma_slice(smem, b, it, tmem_base + 64, act, IDESC64);                       // reg0
-      tc::umma_commit(&b->dfull);
+      mma_slice(el, smem, b, it, tmem_base, act, IDESC64);                            // cls0
+      mma_slice(el, smem, b, it, tmem_base + 64, act, IDESC64);                       // reg0
+      if (el) tc::umma_commit(&b->dfull);
       wait_act();
-      mma_slice(smem, b, it, tmem_base, act, IDESC64);                            // cls1
-      tc::umma_commit(&b->dfull);
+      mma_slice(el, smem, b, it, tmem_base, act, IDESC64);                            // cls1
+      if (el) tc::umma_commit(&b->dfull);
       wait_act();
-      mma_slice(smem, b, it, tmem_base, act, IDESC32);                            // class logits (every CTA; rank 0 stores)
-      tc::umma_commit(&b->dfull);
+      mma_slice(el, smem, b, it, tmem_base, act, IDESC32);                            // class logits (every CTA; rank 0 stores)
+      if (el) tc::umma_commit(&b->dfull);
       wait_act();
-      mma_slice(smem, b, it, tmem_base, act, IDESC64);                            // reg1
-      tc::umma_commit(&b->dfull);
+      mma_slice(el, smem, b, it, tmem_base, act, IDESC64);                            // reg1
+      if (el) tc::umma_commit(&b->dfull);
     }
   } else {
     Ctx c = make_ctx(smem, b, tmem_base, rank, N, P.opx + (long)vf * ACT_BYTES);
@@ -638,7 +646,7 @@ slot_tqkv_cl(const __grid_constant__ CUtensorMap m_qkv, const TqkvParams P) {
   const uint32_t raw = tc::smem_u32(raw_smem);
   uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
   Bars* b = reinterpret_cast<Bars*>(smem + OFF_BAR);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, vf = blockIdx.x / CL;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, vf = blockIdx.x / CL;
   const RowGroup rg = row_group(vf, P.N, P.G);
   const int t = rg.t, N = rg.n;                 // frame; slot rows of this cluster's group
   const uint32_t rank = tc::cluster_ctarank();
@@ -650,13 +658,14 @@ slot_tqkv_cl(const __grid_constant__ CUtensorMap m_qkv, const TqkvParams P) {
       for (int j = 0; j < 3; ++j) prod_slice(smem, b, it, &m_qkv, j * C + (int)rank * NCOL, 3 * C + j * C + (int)rank * NCOL);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                             // all lanes: warp-uniform issue loop (see tc::elect_one)
+      const bool el = tc::elect_one();
       uint32_t it = 0;
       tc::mbar_wait(&b->aready, 0);
       tc::tc_fence_after();
       for (int j = 0; j < 3; ++j) {
-        mma_slice(smem, b, it, tmem_base + j * NCOL, tc::smem_u32(smem + OFF_ACT), IDESC64, 256);
-        tc::umma_commit(&b->dq[j]);
+        mma_slice(el, smem, b, it, tmem_base + j * NCOL, tc::smem_u32(smem + OFF_ACT), IDESC64, 256);
+        if (el) tc::umma_commit(&b->dq[j]);
       }
     }
   } else {

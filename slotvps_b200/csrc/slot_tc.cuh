@@ -102,7 +102,8 @@ __device__ __forceinline__ void prod_gemm(uint8_t* smem, Barriers* b, Ring& rg, 
     }
 }
 // D[dcol0 + 128 nt ...] (+)= A . W^T for `ntiles` x `nks`; A = hi plane at a_base (k-subtiles ACT_SUB apart), lo plane at + a_lo
-__device__ __forceinline__ void mma_gemm(uint8_t* smem, Barriers* b, Ring& rg, uint32_t tmem_base, uint32_t a_base, uint32_t a_lo, int nks,
+// all lanes of the MMA warp run this (warp-uniform waits and descriptors); `el` = tc::elect_one() guards the tcgen05 instructions
+__device__ __forceinline__ void mma_gemm(bool el, uint8_t* smem, Barriers* b, Ring& rg, uint32_t tmem_base, uint32_t a_base, uint32_t a_lo, int nks,
                                          int dcol0, int ntiles, uint32_t idesc, bool accumulate) {
   for (int nt = 0; nt < ntiles; ++nt) {
     const uint32_t d = tmem_base + dcol0 + nt * TILE_N;
@@ -114,12 +115,14 @@ __device__ __forceinline__ void mma_gemm(uint8_t* smem, Barriers* b, Ring& rg, u
         tc::mbar_wait(&b->full[s], (rg.it / NSLOT) & 1);
         tc::tc_fence_after();
         const uint64_t dbh = tc::make_smem_desc_sw128(tc::smem_u32(smem + OFF_RING + s * W_TILE), 16, 1024);
+        if (el) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          tc::umma_bf16(d, dah + 2 * k, dbh + 2 * k, idesc, (accumulate || ks != 0 || k != 0) ? 1u : 0u);
-          tc::umma_bf16(d, dal + 2 * k, dbh + 2 * k, idesc, 1);
+          for (int k = 0; k < 4; ++k) {
+            tc::umma_bf16(d, dah + 2 * k, dbh + 2 * k, idesc, (accumulate || ks != 0 || k != 0) ? 1u : 0u);
+            tc::umma_bf16(d, dal + 2 * k, dbh + 2 * k, idesc, 1);
+          }
+          tc::umma_commit(&b->empty[s]);
         }
-        tc::umma_commit(&b->empty[s]);
         ++rg.it;
       }
       {
@@ -127,9 +130,11 @@ __device__ __forceinline__ void mma_gemm(uint8_t* smem, Barriers* b, Ring& rg, u
         tc::mbar_wait(&b->full[s], (rg.it / NSLOT) & 1);
         tc::tc_fence_after();
         const uint64_t dbl = tc::make_smem_desc_sw128(tc::smem_u32(smem + OFF_RING + s * W_TILE), 16, 1024);
+        if (el) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc::umma_bf16(d, dah + 2 * k, dbl + 2 * k, idesc, 1);
-        tc::umma_commit(&b->empty[s]);
+          for (int k = 0; k < 4; ++k) tc::umma_bf16(d, dah + 2 * k, dbl + 2 * k, idesc, 1);
+          tc::umma_commit(&b->empty[s]);
+        }
         ++rg.it;
       }
     }
@@ -335,7 +340,7 @@ slot_ffn_kernel(const __grid_constant__ CUtensorMap m_l1, const __grid_constant_
   const uint32_t raw = tc::smem_u32(raw_smem);
   uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
   Barriers* b = reinterpret_cast<Barriers*>(smem + OFF_MISC);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.y;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, c = blockIdx.y;
   const RowGroup rg = row_group(blockIdx.x, P.N, P.G);
   const int N = rg.n;
   if (threadIdx.x == 0) {
@@ -349,7 +354,7 @@ slot_ffn_kernel(const __grid_constant__ CUtensorMap m_l1, const __grid_constant_
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = b->tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, b->tmem_ptr, 0);
   if (warp == 0) {
     if (lane == 0) {
       Ring rg;
@@ -357,15 +362,16 @@ slot_ffn_kernel(const __grid_constant__ CUtensorMap m_l1, const __grid_constant_
       prod_gemm(smem, b, rg, &m_l2, C, 0, 2, 2 * c, 2);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                               // all lanes: warp-uniform issue loop (see tc::elect_one)
+      const bool el = tc::elect_one();
       Ring rg;
       const uint32_t act = tc::smem_u32(smem + OFF_ACT), hb = tc::smem_u32(smem + OFF_HB);
       tc::mbar_wait(&b->aready, 0); tc::tc_fence_after();
-      mma_gemm(smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D1, 1, IDESC128, false);       // hidden chunk
-      tc::umma_commit(&b->d1full[0]);
+      mma_gemm(el, smem, b, rg, tmem_base, act, ACT_PLANE, 4, TM_D1, 1, IDESC128, false);   // hidden chunk
+      if (el) tc::umma_commit(&b->d1full[0]);
       tc::mbar_wait(&b->hfull, 0); tc::tc_fence_after();
-      mma_gemm(smem, b, rg, tmem_base, hb, HB_PLANE, 2, TM_D, 2, IDESC128, false);          // partial out = h_c . W2[:, chunk]^T
-      tc::umma_commit(&b->dfull);
+      mma_gemm(el, smem, b, rg, tmem_base, hb, HB_PLANE, 2, TM_D, 2, IDESC128, false);      // partial out = h_c . W2[:, chunk]^T
+      if (el) tc::umma_commit(&b->dfull);
     }
   } else {
     Epi e = make_epi(smem, tmem_base, N);

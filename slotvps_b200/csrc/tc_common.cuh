@@ -89,6 +89,16 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_maj
          | ((uint32_t)(M >> 4) << 24);   // M / 16
 }
 
+// One lane of a fully converged warp (always the same one).  The MMA-issuing warps run their loops WARP-UNIFORMLY (all 32 lanes
+// wait on the barriers and compute the descriptors) and guard only tcgen05.mma / tcgen05.commit with this predicate: the compiler
+// can then keep descriptors and addresses in uniform registers and emits back-to-back UTCHMMA.  Inside an `if (lane == 0)` region it
+// cannot prove uniformity and wraps every UTCHMMA in an ELECT / BRA.U.ANY loop behind 4-6 R2UR moves (profiles/r2_sass_issue.txt).
+// The warp index must be provably uniform as well: take it through __shfl_sync(0xffffffff, threadIdx.x >> 5, 0).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 // D[tmem] (+)= A[smem] . B[smem]   (one elected thread issues)
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -154,17 +164,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "elect.sync _|P1, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
 
 // ---- host: tensor-map encoding through the driver entry point (no link-time libcuda dependency) -----------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
