@@ -845,6 +845,7 @@ int slotvps_head_forward_ex(const slotvps_head_desc* d, const slotvps_stage_para
         prm.bn_sc = o.feat_bn_scale; prm.bn_sh = o.feat_bn_shift; prm.ss_out = o.rnorm_ss;
       }
       prm.planes = tcl.planes; prm.plane_stride = rows; prm.x_planes_only = pos_sep ? 1 : 0;
+      { static const int ts = getenv("SLOTVPS_FUSE_TMA_STORE") ? atoi(getenv("SLOTVPS_FUSE_TMA_STORE")) : 1; prm.tma_store = ts; }
       if (d->pos_mode == 1) { prm.pos = pos[l]; prm.pos_bs = pstride[l]; }
       else if (d->pos_mode == 2) {
         pos_tab_kernel<<<ceil_div(128 * (h + wd), 256), 256, 0, s>>>(tcl.ytab, tcl.xtab, h, wd, w.tc.ytabT_l[l]);

@@ -23,7 +23,9 @@ constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 constexpr int NSTAGE = 2;
 constexpr int AUX_BYTES = 4096;               // barriers, tmem pointer, bias [256], feat_bn scale / shift [2][256]
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + AUX_BYTES + 1024;
-constexpr int THREADS = 576;                   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue (four per TMEM lane quadrant, 64 columns each)
+constexpr int THREADS = 608;                   // warp 0 TMA loads, warp 1 MMA, warps 2..17 epilogue (four per TMEM lane quadrant), warp 18 TMA stores
+constexpr int EPI_THREADS = 512;
+constexpr int STG_BYTES = TILE_M * 128;        // one staged [128 px][64 ch] fp16 sub-plane tile (16 KB); four of them live in the second stage's space
 constexpr uint32_t IDESC = tc::make_idesc_f16(128, 256, 0, 0);
 // conv_trans weight planes carry 2^8 (a weight of ~0.05 would have a subnormal fp16 lo plane: ~1e-6 relative instead of
 // 2.4e-7); the epilogue multiplies the accumulator by 2^-8 (exact)
@@ -45,6 +47,7 @@ struct Params {
   long out_bs;
   __half* planes;      // 4 planes with stride plane_stride rows, or null
   int x_planes_only;   // separable pos: only x_hi / x_lo are written (the kernels add pos from tables)
+  int tma_store;       // main pass: operand planes leave through shared-memory staging + bulk tensor stores (one pipeline stage instead of two)
   long plane_stride;
   const float* pos;    // [256][P] per frame (pos_bs) or null
   long pos_bs;
@@ -120,7 +123,8 @@ __global__ void __launch_bounds__(256) conv_planes_kernel(const float* __restric
 }
 
 __global__ void __launch_bounds__(fuse::THREADS, 1)
-fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const fuse::Params prm) {
+fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_o,
+               const fuse::Params prm) {
   using namespace fuse;
   extern __shared__ uint8_t raw_smem[];
   const uint32_t raw = tc::smem_u32(raw_smem);
@@ -131,6 +135,12 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tfull = empty + NSTAGE;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* sfull = reinterpret_cast<uint64_t*>(aux + 128);   // [2] staged plane pair (x hi/lo | (x+pos) hi/lo) written: 512 arrivals
+  uint64_t* sempty = sfull + 2;                               // [2] the bulk store has read the pair: 1 arrival
+  // With tma_store the K loop runs on ONE 96 KB stage (the tensor pipe is ~10 % busy in the main pass: the epilogue sets the pace) and
+  // the second stage's space holds the four 16 KB staging tiles.
+  const int nstage = prm.tma_store ? 1 : NSTAGE;
+  uint8_t* stg = smem + STAGE_BYTES;
   float* bias = reinterpret_cast<float*>(aux + 256);
   float* bnv = bias + C;                                    // [2][256] feat_bn scale, shift (when prm.ss_out)
 
@@ -143,7 +153,8 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc::tma_prefetch_desc(&tmap_a);
     tc::tma_prefetch_desc(&tmap_w);
     for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 512); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], EPI_THREADS); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sfull[i], EPI_THREADS); tc::mbar_init(&sempty[i], 1); }
     tc::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < C; i += THREADS) bias[i] = prm.bias ? prm.bias[i] : 0.f;
@@ -159,8 +170,8 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int row = tile * TILE_M;
         for (int ks = 0; ks < prm.ksub; ++ks, ++it) {
-          const int s = it % NSTAGE;
-          tc::mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
+          const int s = it % nstage;
+          tc::mbar_wait(&empty[s], ((it / nstage) & 1) ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
           tc::mbar_expect_tx(&full[s], prm.n_out ? 2 * A_BYTES + 2 * prm.n_out * 128 : STAGE_BYTES);
           if (prm.a_split) {
@@ -186,8 +197,8 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + g * 256;
         for (int ks = 0; ks < prm.ksub; ++ks, ++it) {
-          const int s = it % NSTAGE;
-          tc::mbar_wait(&full[s], (it / NSTAGE) & 1);
+          const int s = it % nstage;
+          tc::mbar_wait(&full[s], (it / nstage) & 1);
           tc::tc_fence_after();
           const uint32_t a_hi = tc::smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
           const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
@@ -206,13 +217,16 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (el) tc::umma_commit(&tfull[g]);
       }
     }
-  } else {
+  } else if (warp < 18) {
     // ===================== epilogue: 16 warps, four threads per pixel, 16-channel units =====================
     // The epilogue (bias, bilinear gather of the coarse term, two fp16 hi/lo splits, position add, stores) is what bounds
     // this kernel (ncu, level 3: tensor pipe 10 %, DRAM 25 %, issue slots 33 % busy with 8 epilogue warps); sixteen warps
     // working on 16-column units keep the register footprint small enough for 576 threads and double the latency hiding.
     const int q = warp & 3;
-    const int jq = (warp - 2) >> 2;                         // 64-channel quarter of the 256 output columns this warp drains
+    // Round uu of a tile: ALL sixteen warps work on the 64-channel quarter uu (warp (q, jq) on its 16-channel unit jq), so a round
+    // completes one [128 px][64 ch] sub-plane tile per operand plane -- the box one bulk tensor store takes from shared memory.
+    const int jq = (warp - 2) >> 2;                         // 16-channel unit of this warp inside the round's 64-channel quarter
+    uint32_t sn = 0;                                        // staged rounds so far (parity of the staging barriers)
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t ti = 0;
@@ -249,18 +263,20 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       const float* cr0 = coop ? prm.y_in + (long)(cbase + cy0 * (prm.w / 2) + ccol) * C : nullptr;
       const float* cr1 = coop ? prm.y_in + (long)(cbase + cy1 * (prm.w / 2) + ccol) * C : nullptr;
-      if (coop && rv && lane < 18) {                          // this warp's coarse rows (2 x 256 B), requested before the accumulator wait
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(cr0 + jq * 64));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(cr0 + jq * 64 + 32));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(cr1 + jq * 64));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(cr1 + jq * 64 + 32));
+      if (coop && rv && lane < 18) {                          // this warp's coarse-row pieces (2 rows x 4 x 64 B), requested before the accumulator wait
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(cr0 + jq * 16 + e * 64));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(cr1 + jq * 16 + e * 64));
+        }
       }
+      const bool staged = prm.tma_store && tile * TILE_M + TILE_M <= prm.rows;      // full tiles leave through the staging buffers
       tc::mbar_wait(&tfull[g], uu_ & 1);
       tc::tc_fence_after();
       float ss_part = 0.f;
 #pragma unroll 1
       for (int uu = 0; uu < 4; ++uu) {
-        const int u = jq * 4 + uu;                            // 16-channel unit: channels [16 u, 16 u + 16)
+        const int u = uu * 4 + jq;                            // 16-channel unit: channels [16 u, 16 u + 16)
         if (prm.n_out && u * 16 >= prm.n_out) {               // columns the narrowed MMA did not compute
           if (uu == 3) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }
           continue;
@@ -325,6 +341,20 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (prm.planes) {
           uint32_t hi[8], lo[8];
           auto store = [&](int plane) {
+            if (staged) {
+              // swizzled [128 px][64 ch] tile (row = 128 bytes, 16-byte chunk c stored at c ^ (row & 7)): what SWIZZLE_128B boxes look like
+              const int pr = plane >> 1;
+              tc::mbar_wait(&sempty[pr], (sn & 1) ^ 1);       // the bulk store of the previous round has read this pair's tiles
+              uint8_t* d0 = stg + plane * STG_BYTES + r * 128;
+              const int c0 = jq * 2, sw = r & 7;
+              *reinterpret_cast<uint4*>(d0 + (((c0) ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(d0 + (((c0 + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              *reinterpret_cast<uint4*>(d0 + STG_BYTES + (((c0) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              *reinterpret_cast<uint4*>(d0 + STG_BYTES + (((c0 + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              tc::fence_proxy_async();
+              tc::mbar_arrive(&sfull[pr]);
+              return;
+            }
             // sub-plane ks = u / 4 of this plane, [rows][64]: the four units of a 64-channel group complete one 128-byte row
             __half* dst = prm.planes + (((long)plane * 4 + (u >> 2)) * prm.plane_stride + row) * 64 + (u & 3) * 16;
             tc::st_global_v8(dst, hi);
@@ -333,7 +363,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int c = 0; c < 8; ++c) split2(v[2 * c], v[2 * c + 1], hi[c], lo[c]);
           store(0);
-          if (prm.x_planes_only) continue;
+          if (prm.x_planes_only) { if (staged) ++sn; continue; }
           if (prm.pos) {
             const float* ps = prm.pos + (long)t * prm.pos_bs + (long)(u * 16) * prm.P + p;
 #pragma unroll
@@ -352,9 +382,36 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int c = 0; c < 8; ++c) split2(v[2 * c], v[2 * c + 1], hi[c], lo[c]);
           store(2);
+          if (staged) ++sn;
         }
       }
     }
+  } else if (prm.tma_store) {
+    // ===================== warp 18: bulk tensor stores of the staged operand-plane tiles =====================
+    const bool el = tc::elect_one();
+    const int npairs = prm.x_planes_only ? 1 : 2;
+    uint32_t sn = 0;
+    if (el) tc::tma_prefetch_desc(&tmap_o);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (tile * TILE_M + TILE_M > prm.rows) continue;        // the partial tile is stored directly by the epilogue threads
+      for (int rd = 0; rd < 4; ++rd, ++sn) {
+        for (int pr = 0; pr < npairs; ++pr) {
+          tc::mbar_wait(&sfull[pr], sn & 1);
+          if (el) {
+#pragma unroll
+            for (int hl = 0; hl < 2; ++hl) {
+              const int plane = pr * 2 + hl;
+              tc::tma_store_2d(&tmap_o, stg + plane * STG_BYTES, 0, (int)((plane * 4 + rd) * prm.plane_stride) + tile * TILE_M);
+            }
+            tc::bulk_commit();
+            tc::bulk_wait_read0();
+            tc::mbar_arrive(&sempty[pr]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (el) tc::bulk_wait0();
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -371,15 +428,18 @@ struct FuseTcWorkspace {
 
 inline int fuse_tc_launch(const __half* a_planes, long a_rows_total, int a_lo_row, int K, const __half* w_planes, const fuse::Params& prm,
                           cudaStream_t s, int max_ctas = 148) {
-  CUtensorMap ma, mw;
+  CUtensorMap ma, mw, mo;
   if (prm.a_split) SV_TRY(tc::make_tmap_h16_sw128(&ma, a_planes, (uint64_t)4 * a_rows_total, 64, fuse::TILE_M));
   else SV_TRY(tc::make_tmap_h16_sw128(&ma, a_planes, (uint64_t)a_rows_total, (uint64_t)K, fuse::TILE_M));
   SV_TRY(tc::make_tmap_h16_sw128(&mw, w_planes, (uint64_t)2 * C, (uint64_t)K, prm.n_out ? prm.n_out : C));
+  if (prm.tma_store && prm.planes)
+    SV_TRY(tc::make_tmap_h16_sw128(&mo, prm.planes, (uint64_t)(prm.x_planes_only ? 2 : 4) * 4 * prm.plane_stride, 64, fuse::TILE_M));
+  else mo = mw;                                                      // unused
   SV_TRY(ensure_dyn_smem((const void*)fuse_tc_kernel, fuse::SMEM_BYTES));
   const int n_tiles = ceil_div(prm.rows, fuse::TILE_M);
   const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
   g_prof_grid = grid;
-  fuse_tc_kernel<<<grid, fuse::THREADS, fuse::SMEM_BYTES, s>>>(ma, mw, prm);
+  fuse_tc_kernel<<<grid, fuse::THREADS, fuse::SMEM_BYTES, s>>>(ma, mw, mo, prm);
   SV_CHECK_LAUNCH("fuse_tc");
   return SLOTVPS_OK;
 }
