@@ -1467,7 +1467,7 @@ size_t dc_layout(int B, int c_in, int H, int W, void* base, DcWs* o) {
   d.xT = a.take<float>(rows * c_in);
   d.y = a.take<float>(rows * C);
   d.wplanes = a.take<__half>((size_t)2 * C * dcn::KT * c_in);
-  d.planes = a.take<__half>((size_t)2 * rows * dcn::KT * c_in + 64);
+  d.planes = a.take<__half>(dcn::use_im2col() ? (size_t)2 * rows * dcn::KT * c_in + 64 : 64);
   if (o) *o = d;
   return a.off;
 }

@@ -19,6 +19,7 @@
 #pragma once
 #include "common.cuh"
 #include "fuse_tc.cuh"
+#include <stdlib.h>
 
 namespace slotvps {
 namespace dcn {
@@ -157,6 +158,200 @@ __global__ void __launch_bounds__(256) dcn_im2col_kernel(const float* __restrict
   }
 }
 
+// ---- implicit-GEMM deformable convolution (no column buffer) ---------------------------------------------------------------
+// y[row][o] = sum_{tap, c} bilinear(act; row, tap, c) * W[o][tap * Cn + c].  One CTA works on tiles of 128 output pixels (the TMEM
+// lanes); the K loop runs over (tap, 64-channel group) stages.  Sixteen GATHER warps build the A operand of a stage directly in
+// shared memory: every thread owns two (pixel, 8-channel) pieces, reads the four bilinear corners as 32-byte loads (a pixel's eight
+// threads cover 256 contiguous bytes per corner), blends them in fp32, splits into fp16 hi / lo and stores the 16-byte chunks in the
+// 128-byte-swizzled K-major layout a TMA box would have produced.  The weight tiles of the stage arrive by TMA, one elected lane
+// issues the three hi/lo products per k-step into one of two TMEM accumulators, and four epilogue warps drain the finished tile
+// (x 2^-8) to y[rows][256] while the next tile is being accumulated.  The sampling geometry (floor, weights, border tests) is
+// evaluated once per (pixel, tap) and reused for the Cn / 64 stages of the tap.
+namespace tcg {
+constexpr int TILE_M = 128;
+constexpr int A_BYTES = TILE_M * 128;                 // [128 px][64 ch] fp16
+constexpr int B_BYTES = C * 128;                      // up to [256 out][64 ch] fp16
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr int NSTAGE = 2;
+constexpr int G_WARPS = 16, E_WARPS = 4;
+constexpr int THREADS = 32 * (2 + E_WARPS + G_WARPS); // 704: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue, warps 6..21 gather
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 4096 + 1024;
+struct Params {
+  const float* act; int Cn;                           // activation [rows][Cn] fp32
+  Off off;                                            // sampling offsets (p == null: regular convolution)
+  float* y;                                           // [rows][256]
+  int rows, P, H, W, n_out;
+};
+}  // namespace tcg
+
+__global__ void __launch_bounds__(tcg::THREADS, 1) dcn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const tcg::Params prm) {
+  using namespace tcg;
+  extern __shared__ uint8_t raw_smem[];
+  const uint32_t raw = tc::smem_u32(raw_smem);
+  uint8_t* smem = raw_smem + ((1024 - (raw & 1023)) & 1023);
+  uint8_t* aux = smem + NSTAGE * STAGE_BYTES;
+  uint64_t* fullb = reinterpret_cast<uint64_t*>(aux);       // [2] weight tiles landed (TMA transaction bytes)
+  uint64_t* fulla = fullb + NSTAGE;                         // [2] gathered A tiles written: one arrival per gather warp
+  uint64_t* empty = fulla + NSTAGE;                         // [2] the MMAs that read the stage have retired
+  uint64_t* tfull = empty + NSTAGE;                         // [2] accumulator complete
+  uint64_t* tempty = tfull + 2;                             // [2] accumulator drained: 128 arrivals
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int n_tiles = (prm.rows + TILE_M - 1) / TILE_M;
+  const int ncs = prm.Cn / 64, nks = KT * ncs;
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmap_w);
+    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&fullb[i], 1); tc::mbar_init(&fulla[i], G_WARPS); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 32 * E_WARPS); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) { tc::tmem_alloc(tmem_ptr, 512); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int ks = 0; ks < nks; ++ks, ++it) {
+          const int s = it % NSTAGE;
+          tc::mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES + 2 * A_BYTES;
+          tc::mbar_expect_tx(&fullb[s], 2 * prm.n_out * 128);
+          tc::tma_load_2d(st, &tmap_w, ks * 64, 0, &fullb[s]);
+          tc::tma_load_2d(st + B_BYTES, &tmap_w, ks * 64, C, &fullb[s]);
+        }
+    }
+  } else if (warp == 1) {
+    const bool el = tc::elect_one();
+    const uint32_t idesc = tc::make_idesc_f16(128, prm.n_out, 0, 0);
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int g = ti & 1, u = ti >> 1;
+      tc::mbar_wait(&tempty[g], (u & 1) ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + g * 256;
+      for (int ks = 0; ks < nks; ++ks, ++it) {
+        const int s = it % NSTAGE;
+        tc::mbar_wait(&fullb[s], (it / NSTAGE) & 1);
+        tc::mbar_wait(&fulla[s], (it / NSTAGE) & 1);
+        tc::tc_fence_after();
+        const uint32_t a_hi = tc::smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+        const uint64_t dah = tc::make_smem_desc_sw128(a_hi, 16, 1024), dal = tc::make_smem_desc_sw128(a_lo, 16, 1024);
+        const uint64_t dbh = tc::make_smem_desc_sw128(b_hi, 16, 1024), dbl = tc::make_smem_desc_sw128(b_lo, 16, 1024);
+        if (el) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc::umma_bf16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (ks | k) != 0);
+            tc::umma_bf16(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);
+            tc::umma_bf16(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+          }
+          tc::umma_commit(&empty[s]);
+        }
+      }
+      if (el) tc::umma_commit(&tfull[g]);
+    }
+  } else if (warp < 2 + E_WARPS) {
+    // ---- epilogue: one thread per pixel row, 32 columns at a time ----
+    const int q = warp & 3, r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int g = ti & 1, u = ti >> 1;
+      const long row = (long)tile * TILE_M + r;
+      tc::mbar_wait(&tfull[g], u & 1);
+      tc::tc_fence_after();
+      for (int j = 0; j < prm.n_out; j += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + lane_addr + g * 256 + j, v);
+        tc::tmem_ld_wait();
+        if (j + 32 >= prm.n_out) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }
+        if (row < prm.rows) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] *= fuse::WSCALE_INV;
+          float* dst = prm.y + row * C + j;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tc::st_global_v8f(dst + 8 * c, v + 8 * c);
+        }
+      }
+    }
+  } else {
+    // ---- gather: thread -> (pixel tg / 8 [+ 64], 8-channel chunk tg % 8) ----
+    const int tg = (warp - 2 - E_WARPS) * 32 + lane, chunk = tg & 7;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int py[2], px[2], pbase[2];                           // pixel coordinates, element offset of the image's first pixel row
+      bool pv[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const long row = (long)tile * TILE_M + (tg >> 3) + 64 * k;
+        pv[k] = row < prm.rows;
+        const int b = pv[k] ? (int)(row / prm.P) : 0, p = pv[k] ? (int)(row % prm.P) : 0;
+        py[k] = p / prm.W; px[k] = p % prm.W; pbase[k] = b * prm.P;
+      }
+      for (int tap = 0; tap < KT; ++tap) {
+        int ci[2][4];                                       // element offsets of the four corners' channel rows (clamped inside the map)
+        float cw[2][4];                                     // corner weights x 2^4, zero where the corner is outside
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          float oh = 0.f, ow = 0.f;
+          if (prm.off.p && pv[k]) {
+            const float* o = prm.off.p + (long)(pbase[k] / prm.P) * prm.off.bs + (long)(py[k] * prm.W + px[k]) * prm.off.ps + (long)(2 * tap) * prm.off.cs;
+            oh = __ldg(o); ow = __ldg(o + prm.off.cs);
+          }
+          const float h_im = (float)(py[k] - 1 + tap / 3) + oh, w_im = (float)(px[k] - 1 + tap % 3) + ow;
+          const bool in = pv[k] && h_im > -1.f && w_im > -1.f && h_im < (float)prm.H && w_im < (float)prm.W;
+          const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im), h_high = h_low + 1, w_high = w_low + 1;
+          const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+          const bool t = in && h_low >= 0, bt = in && h_high <= prm.H - 1, lf = w_low >= 0, rt = w_high <= prm.W - 1;
+          const int hl = min(max(h_low, 0), prm.H - 1), hh_ = min(max(h_high, 0), prm.H - 1);
+          const int wl = min(max(w_low, 0), prm.W - 1), wh = min(max(w_high, 0), prm.W - 1);
+          ci[k][0] = (pbase[k] + hl * prm.W + wl) * prm.Cn; cw[k][0] = (t && lf) ? hh * hw * ASCALE : 0.f;
+          ci[k][1] = (pbase[k] + hl * prm.W + wh) * prm.Cn; cw[k][1] = (t && rt) ? hh * lw * ASCALE : 0.f;
+          ci[k][2] = (pbase[k] + hh_ * prm.W + wl) * prm.Cn; cw[k][2] = (bt && lf) ? lh * hw * ASCALE : 0.f;
+          ci[k][3] = (pbase[k] + hh_ * prm.W + wh) * prm.Cn; cw[k][3] = (bt && rt) ? lh * lw * ASCALE : 0.f;
+        }
+        for (int cs = 0; cs < ncs; ++cs, ++it) {
+          const int s = it % NSTAGE;
+          const float* src = prm.act + cs * 64 + chunk * 8;
+          float c0[2][8], c1[2][8], c2[2][8], c3[2][8];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {                      // all eight corner loads of the thread in flight before the stage is awaited
+            tc::ld_global_nc_v8f(src + ci[k][0], c0[k]); tc::ld_global_nc_v8f(src + ci[k][1], c1[k]);
+            tc::ld_global_nc_v8f(src + ci[k][2], c2[k]); tc::ld_global_nc_v8f(src + ci[k][3], c3[k]);
+          }
+          tc::mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
+          uint8_t* a_hi = smem + s * STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // same association as the reference's (w1 v1 + w2 v2 + w3 v3 + w4 v4), deform_conv_cuda_kernel.cu:108 (weights pre-scaled by 2^4: exact)
+              const float a = cw[k][0] * c0[k][2 * e] + cw[k][1] * c1[k][2 * e] + cw[k][2] * c2[k][2 * e] + cw[k][3] * c3[k][2 * e];
+              const float b = cw[k][0] * c0[k][2 * e + 1] + cw[k][1] * c1[k][2 * e + 1] + cw[k][2] * c2[k][2 * e + 1] + cw[k][3] * c3[k][2 * e + 1];
+              split2(a, b, hi[e], lo[e]);
+            }
+            const int r = (tg >> 3) + 64 * k;
+            const int o = r * 128 + ((chunk ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(a_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(a_hi + A_BYTES + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          tc::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&fulla[s]);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
 // GroupNorm statistics of y [B][P][256] (first Cout channels): slab partials (fp32 over <= 512 pixels, then double), fixed order
 constexpr int GN_SLAB = 512;
 __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ y, double* __restrict__ part /*[slabs][B][32][2]*/, int P, int Cout) {
@@ -212,6 +407,8 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(const float* __restric
   }
 }
 
+// SLOTVPS_DCN_IM2COL=1 keeps the first form (column planes in HBM + plain GEMM) for A/B measurements
+inline bool use_im2col() { static const int v = getenv("SLOTVPS_DCN_IM2COL") ? atoi(getenv("SLOTVPS_DCN_IM2COL")) : 0; return v != 0; }
 // ---- host side ----------------------------------------------------------------------------------------------------
 struct LayerPrep { __half *offw, *wplanes; };                 // [2][256][C_in] (162 rows used), [2][256][9 C_in]
 inline size_t prep_layout(const slotvps_dcn_layer* L, int n, void* base, LayerPrep* out) {
@@ -237,7 +434,7 @@ inline size_t ws_layout(int cin_max, int B, int H, int W, void* base, Ws* w) {
   x.off = a.take<float>(rows * NOFF);
   x.aff = a.take<float>((size_t)B * 2 * C);
   x.aplanes = a.take<__half>((size_t)2 * rows * cin_max + 64);
-  x.planes = a.take<__half>((size_t)2 * rows * KT * cin_max + 64);
+  x.planes = a.take<__half>(use_im2col() ? (size_t)2 * rows * KT * cin_max + 64 : 64);      // column planes: first form only
   x.slabs = ceil_div(H * W, GN_SLAB);
   x.part = a.take<double>((size_t)x.slabs * B * NG * 2);
   if (w) *w = x;
@@ -257,10 +454,27 @@ inline int gemm(const __half* a_planes, long rows, int K, const __half* w_planes
   prm.n_out = n_out >= C ? 0 : n_out;
   return fuse_tc_launch(a_planes, 2 * rows, (int)rows, K, w_planes, prm, s);
 }
+// implicit-GEMM form: act [rows][Cn] -> y [rows][256] raw (first c_out columns), no column planes
+inline int conv_implicit(const float* act, const Off& off, const __half* wplanes, float* y, int Cn, int c_out, int B, int H, int W, cudaStream_t s) {
+  const long rows = (long)B * H * W;
+  tcg::Params prm;
+  prm.act = act; prm.Cn = Cn; prm.off = off; prm.y = y; prm.rows = (int)rows; prm.P = H * W; prm.H = H; prm.W = W;
+  prm.n_out = (c_out + 15) / 16 * 16;
+  CUtensorMap mw;
+  SV_TRY(tc::make_tmap_h16_sw128(&mw, wplanes, (uint64_t)2 * C, (uint64_t)KT * Cn, prm.n_out));
+  SV_TRY(ensure_dyn_smem((const void*)dcn_tc_kernel, tcg::SMEM_BYTES));
+  const int n_tiles = ceil_div((int)rows, tcg::TILE_M);
+  const int grid = n_tiles < 148 ? n_tiles : 148;
+  g_prof_grid = grid;
+  dcn_tc_kernel<<<grid, tcg::THREADS, tcg::SMEM_BYTES, s>>>(mw, prm);
+  SV_CHECK_LAUNCH("dcn_tc");
+  return SLOTVPS_OK;
+}
 // columns + GEMM of one deformable (off.p != null) convolution: act [rows][Cn] -> y [rows][256] raw (first c_out columns)
 inline int conv_gemm(const float* act, const Off& off, const __half* wplanes, __half* planes, float* y, int Cn, int c_out, int B, int H, int W,
                      cudaStream_t s) {
   const long rows = (long)B * H * W;
+  if (!use_im2col()) return conv_implicit(act, off, wplanes, y, Cn, c_out, B, H, W, s);
   dcn_im2col_kernel<<<grid_for(rows * KT * (Cn / 8)), 256, 0, s>>>(act, off, planes, rows, Cn, H, W, B);
   SV_CHECK_LAUNCH("dcn_im2col");
   return gemm(planes, rows, KT * Cn, wplanes, y, (c_out + 15) / 16 * 16, H, W, s);
