@@ -289,6 +289,26 @@ def measure_next_rows(sv, synthetic, lane, kw, size, N, dev, pk):
     b = H * W * (16 + 16 + 3)
     rows["unify_pan_result"] = dict(ms=ms, algorithmic_bytes=b, achieved_gbs=b / (ms * 1e-3) / 1e9, frac=b / (ms * 1e-3) / 1e9 / hbm, bound="hbm",
                                     note="histogram pass + LUT pass each read seg and pan (int64) once; 3 B/px written; includes the host-side argument marshalling of one call")
+    # UPSNetFPN deformable-conv subnet on the clip's four FPN levels (256 channels, T frames as the batch):
+    # the producer side of the head's inputs.  scripts/dcn_bench.py times the reference's own op on the same GPU next to it.
+    T = len(lane.clip)
+    net = sv.B200DeformSubnet()
+    net.load_state_dict(synthetic.make_dcn_state_dict(11, offset_scale=1.5))
+    net = net.to(dev)
+    lv = [(H // 4, W // 4), (H // 8, W // 8), (H // 16, W // 16), (H // 32, W // 32)]
+    xs = [synthetic.make_fpn_level(20 + i, T, 256, h, w).to(dev) for i, (h, w) in enumerate(lv)]
+    def subnet():
+        for x in xs: net(x)
+    ms = med(subnet, n=7, warm=2)
+    px = T * sum(h * w for h, w in lv)
+    fl = px * 2 * 9 * (256 * 256 + 256 * 128 + 128 * 128) + px * 2 * 9 * 18 * (256 + 256 + 128)
+    tf = fl / (ms * 1e-3) / 1e12
+    rows["dcn_subnet"] = dict(ms=ms, algorithmic_gflop=fl / 1e9, achieved_tflops=tf, executed_mma_tflops=3 * tf, peak=float(pk["bf16_tflops"]),
+                              frac=tf / float(pk["bf16_tflops"]), executed_frac=3 * tf / float(pk["bf16_tflops"]), bound="tensor",
+                              note="3 x [3x3 deformable conv + GroupNorm(32) + ReLU], 256->256->128->128, on the four FPN levels of the clip "
+                                   "(implicit GEMM on tcgen05, 3 fp16 hi/lo products per algorithmic product); the reference's own op "
+                                   "compiled for sm_100a takes 32.7 ms for the same work on a B200 (profiles/r2_dcn_bench.json)")
+    del xs, net
     return rows
 
 

@@ -41,6 +41,20 @@ def patch_reference(level: int = 1):
     return cls
 
 
+def patch_upsnet_subnet(detector):
+    """SURVEY 8f rank 4, after ``build_detector`` / ``load_checkpoint``: replace the deformable-conv subnet of the detector's
+    semantic head (``image_model.panopticFPN.deform_convs[0]``, upsnetFPN.py:36-49) by ``B200DeformSubnet`` holding the same
+    parameters (strict state_dict load).  ``UPSNetFPN.forward`` (:66-70) then calls the B200 kernels level by level; the rest of
+    that module (interpolate / concat / conv_pred) stays the reference's.  Inference only (the mirror has no backward)."""
+    from .dcn import B200DeformSubnet
+    fpn = detector.image_model.panopticFPN
+    ref = fpn.deform_convs[0]
+    net = B200DeformSubnet(fpn.in_channels, fpn.out_channels)
+    net.load_state_dict(ref.state_dict(), strict=True)
+    fpn.deform_convs[0] = net.to(next(ref.parameters()).device).eval()
+    return net
+
+
 def make_b200_detector(base, Instances):
     """Subclass of the reference's VPS_Temporal_Slots with the hot path on the B200 kernels."""
 

@@ -101,7 +101,10 @@ def test_abi_rejects_unserved_instances():
     for bad in (dict(k=5), dict(st=2), dict(pad=0), dict(dil=2), dict(group=2), dict(dg=2), dict(cin=100), dict(cout=40), dict(cin=512)):
         assert L.slotvps_deform_conv_forward(*args(**bad)) == -1, bad
         assert L.slotvps_last_error()
-    assert L.slotvps_deform_conv_workspace_bytes(2, 256, 64, 128, C.byref(n)) == 0 and n.value > 2 * 2 * 64 * 128 * 9 * 256 * 2
+    rows = 2 * 64 * 128
+    assert L.slotvps_deform_conv_workspace_bytes(2, 256, 64, 128, C.byref(n)) == 0
+    # pixel-major input + raw output + weight planes, and NO column buffer (the reference's `columns` is rows x 9 x 256 floats)
+    assert rows * (256 + 256) * 4 <= n.value < rows * 9 * 256 * 4
     lay = (_lib.DcnLayer * 2)(_lib.DcnLayer(256, 256, 16, 16, 16, 16, 16), _lib.DcnLayer(128, 128, 16, 16, 16, 16, 16))
     assert L.slotvps_dcn_prepared_bytes(lay, 2, C.byref(n)) == -1             # c_in != previous c_out
 
