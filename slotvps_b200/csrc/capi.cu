@@ -1432,15 +1432,16 @@ int slotvps_dcn_subnet_forward(const slotvps_dcn_layer* layers, int n_layers, co
   const long rows = (long)B * P;
   {
     const int c0 = layers[0].c_in;
-    dcn::nchw_to_nhwc_kernel<<<dim3(ceil_div(P, 32), ceil_div(c0, 32), B), 256, 0, s>>>(x, w.act, c0, P);
+    dcn::nchw_to_nhwc_kernel<<<dim3(ceil_div(P, 32), ceil_div(c0, 32), B), 256, 0, s>>>(x, w.act, c0, P, w.aplanes, rows);   // + layer 0's operand planes
     SV_CHECK_LAUNCH("dcn_to_nhwc");
   }
   for (int i = 0; i < n_layers; ++i) {
     const int cin = layers[i].c_in, cout = layers[i].c_out;
     // the activation of this layer once: layer 0 = the input as it is; later = relu(GroupNorm(y)) of the previous layer, compacted to cin columns
-    if (i == 0) dcn::act_planes_kernel<<<dcn::grid_for(rows * (cin / 8)), 256, 0, s>>>(w.act, cin, nullptr, nullptr, w.aplanes, rows, cin, P);
-    else dcn::act_planes_kernel<<<dcn::grid_for(rows * (cin / 8)), 256, 0, s>>>(w.y, C, w.aff, w.act, w.aplanes, rows, cin, P);
-    SV_CHECK_LAUNCH("dcn_act_planes");
+    if (i > 0) {
+      dcn::act_planes_kernel<<<dcn::grid_for(rows * (cin / 8)), 256, 0, s>>>(w.y, C, w.aff, w.act, w.aplanes, rows, cin, P);
+      SV_CHECK_LAUNCH("dcn_act_planes");
+    }
     // conv_offset: one 1x1 GEMM for all 9 taps x 18 outputs, then the 9-tap shift-sum
     SV_TRY(dcn::gemm(w.aplanes, rows, cin, lp[i].offw, w.z, 176, H, W, s));
     dcn::offset_shift_kernel<<<(unsigned)((rows * dcn::NOFF + 255) / 256), 256, 0, s>>>(w.z, layers[i].offset_b, w.off, H, W, rows);

@@ -29,8 +29,10 @@ constexpr int NG = 32;                         // GroupNorm groups
 constexpr float ASCALE = 16.f;                 // activations and weights both carry 2^4: their product carries fuse::WSCALE = 2^8
 constexpr float GN_EPS = 1e-5f;
 
-// [B][C][P] -> [B][P][C]
-__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Cn, int P) {
+// [B][C][P] -> [B][P][C]; with `planes` also the fp16 hi/lo operand planes [2][B P][C] x 2^4 of the same values (layer 0 of the subnet:
+// saves the separate act_planes pass over the input)
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Cn, int P,
+                                                           __half* __restrict__ planes = nullptr, long rows = 0) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int i = ty; i < 32; i += 8) {
@@ -40,7 +42,16 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int p = p0 + i, c = c0 + tx;
-    if (p < P && c < Cn) y[((long)b * P + p) * Cn + c] = tile[tx][i];
+    if (p < P && c < Cn) {
+      const float v = tile[tx][i];
+      const long o = ((long)b * P + p) * Cn + c;
+      y[o] = v;
+      if (planes) {
+        __half h, l;
+        split_bf16(v * ASCALE, h, l);
+        planes[o] = h; planes[rows * Cn + o] = l;
+      }
+    }
   }
 }
 
@@ -371,14 +382,20 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict
     dst[0] = sa; dst[1] = sq;
   }
 }
-// -> aff [B][2][256]: scale = gamma * rstd, shift = beta - mean * scale (channels >= Cout: 0, 0)
+// -> aff [B][2][256]: scale = gamma * rstd, shift = beta - mean * scale (channels >= Cout: 0, 0).  Thread (stripe = tid / 32, group = tid % 32)
+// adds the slabs stripe, stripe + 8, ... in double; the eight stripes are combined in a fixed order (deterministic).
 __global__ void __launch_bounds__(256) gn_final_kernel(const double* __restrict__ part, int slabs, int B, const float* __restrict__ gw,
                                                        const float* __restrict__ gb, float* __restrict__ aff, int P, int Cout) {
+  __shared__ double ps[8][NG][2];
   __shared__ float mean[NG], rstd[NG];
-  const int b = blockIdx.x, c = threadIdx.x, cpg = Cout / NG;
+  const int b = blockIdx.x, c = threadIdx.x, cpg = Cout / NG, grp = c & 31, stripe = c >> 5;
+  double sa = 0.0, sq = 0.0;
+  for (int s = stripe; s < slabs; s += 8) { const double* src = part + (((long)s * B + b) * NG + grp) * 2; sa += src[0]; sq += src[1]; }
+  ps[stripe][grp][0] = sa; ps[stripe][grp][1] = sq;
+  __syncthreads();
   if (c < NG) {
-    double sa = 0.0, sq = 0.0;
-    for (int s = 0; s < slabs; ++s) { const double* src = part + (((long)s * B + b) * NG + c) * 2; sa += src[0]; sq += src[1]; }
+    sa = 0.0; sq = 0.0;
+    for (int s = 0; s < 8; ++s) { sa += ps[s][c][0]; sq += ps[s][c][1]; }
     const double n = (double)P * cpg, m = sa / n, var = fmax(sq / n - m * m, 0.0);
     mean[c] = (float)m; rstd[c] = (float)(1.0 / sqrt(var + (double)GN_EPS));
   }
@@ -408,7 +425,7 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(const float* __restric
 }
 
 // SLOTVPS_DCN_IM2COL=1 keeps the first form (column planes in HBM + plain GEMM) for A/B measurements
-inline bool use_im2col() { static const int v = getenv("SLOTVPS_DCN_IM2COL") ? atoi(getenv("SLOTVPS_DCN_IM2COL")) : 0; return v != 0; }
+inline bool use_im2col() { const char* e = getenv("SLOTVPS_DCN_IM2COL"); return e && atoi(e) != 0; }     // read per call: one process can compare both
 // ---- host side ----------------------------------------------------------------------------------------------------
 struct LayerPrep { __half *offw, *wplanes; };                 // [2][256][C_in] (162 rows used), [2][256][9 C_in]
 inline size_t prep_layout(const slotvps_dcn_layer* L, int n, void* base, LayerPrep* out) {

@@ -143,6 +143,20 @@ def test_deform_conv_far_offsets_read_zero():
     assert float(_cuda_op(x, torch.full_like(off, -1000.0), w).abs().max()) == 0.0
 
 
+@pytest.mark.gpu
+def test_first_form_matches_implicit_gemm(monkeypatch):
+    """SLOTVPS_DCN_IM2COL=1 (bilinear im2col to fp16 planes in HBM + plain tensor-core GEMM, the A/B baseline of the implicit-GEMM
+    kernel): same operand values, same products -- the two forms agree to accumulation-order noise."""
+    x, off, w = G.op_inputs(9, 2, 256, 128, 21, 37, 2.0)             # 1554 pixels: partial tile
+    a = _cuda_op(x, off, w)
+    monkeypatch.setenv("SLOTVPS_DCN_IM2COL", "1")
+    b = _cuda_op(x, off, w)
+    monkeypatch.delenv("SLOTVPS_DCN_IM2COL")
+    e = rel(a, b)
+    print(f"implicit GEMM vs im2col + GEMM form: rel {e:.2e}")
+    assert e < 2e-6 and rel(a, O.deform_conv(x.double(), off.double(), w.double())) < 1e-5
+
+
 def _subnet(sd, channels=None):
     from slotvps_b200.dcn import B200DeformSubnet
     m = B200DeformSubnet(channels=channels)
