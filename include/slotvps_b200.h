@@ -270,7 +270,8 @@ int slotvps_unify_pan_result(const int64_t* seg, const int64_t* pan, const int32
  * The reference's scratch arguments (`columns`, `ones`) become `workspace`; im2col_step only partitions the batch in the
  * reference and does not change the result, it is accepted and ignored.  Served here: what UPSNetFPN instantiates
  * (upsnetFPN.py:36-49) -- 3x3, stride 1, padding 1, dilation 1, group 1, deformable_group 1, c_in a multiple of 64 and
- * c_out a multiple of 32, both <= 256; anything else returns SLOTVPS_EINVAL (the reference op stays available for it).
+ * c_out a multiple of 32, both <= 256, B*H*W < 2^22 pixels; anything else returns SLOTVPS_EINVAL (the reference op stays available
+ * for it).
  * offset == NULL computes the ordinary 3x3 convolution (all offsets zero).                                           */
 int slotvps_deform_conv_workspace_bytes(int B, int c_in, int H, int W, size_t* bytes);
 int slotvps_deform_conv_forward(const float* input, const float* weight, const float* offset, float* output,

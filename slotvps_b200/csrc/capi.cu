@@ -1410,7 +1410,7 @@ int slotvps_dcn_prepare(const slotvps_dcn_layer* layers, int n_layers, void* pre
 int slotvps_dcn_workspace_bytes(const slotvps_dcn_layer* layers, int n_layers, int B, int H, int W, size_t* bytes) {
   SV_REQUIRE(bytes != nullptr, "null out pointer");
   SV_TRY(dcn_check_layers(layers, n_layers));
-  SV_REQUIRE(B > 0 && H > 0 && W > 0 && (long)B * H * W < (1L << 30), "bad shape");
+  SV_REQUIRE(B > 0 && H > 0 && W > 0 && (long)B * H * W < (1L << 22), "bad shape (the kernels index pixels x channels in 32 bits: B*H*W < 2^22)");
   *bytes = align_up(dcn::ws_layout(dcn_cin_max(layers, n_layers), B, H, W, nullptr, nullptr));
   return SLOTVPS_OK;
 }
@@ -1419,7 +1419,7 @@ int slotvps_dcn_subnet_forward(const slotvps_dcn_layer* layers, int n_layers, co
                                int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
   SV_TRY(dcn_check_layers(layers, n_layers));
   SV_REQUIRE(prepared && x && out && workspace, "null argument");
-  SV_REQUIRE(B > 0 && H > 0 && W > 0 && (long)B * H * W < (1L << 30), "bad shape");
+  SV_REQUIRE(B > 0 && H > 0 && W > 0 && (long)B * H * W < (1L << 22), "bad shape (the kernels index pixels x channels in 32 bits: B*H*W < 2^22)");
   const int cin_max = dcn_cin_max(layers, n_layers);
   if (workspace_bytes < align_up(dcn::ws_layout(cin_max, B, H, W, nullptr, nullptr))) return fail(SLOTVPS_EWORKSPACE, "dcn: workspace too small%s%s");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1476,7 +1476,7 @@ size_t dc_layout(int B, int c_in, int H, int W, void* base, DcWs* o) {
 
 int slotvps_deform_conv_workspace_bytes(int B, int c_in, int H, int W, size_t* bytes) {
   SV_REQUIRE(bytes != nullptr, "null out pointer");
-  SV_REQUIRE(B > 0 && H > 0 && W > 0 && c_in > 0 && c_in <= C && (long)B * H * W < (1L << 30), "bad shape");
+  SV_REQUIRE(B > 0 && H > 0 && W > 0 && c_in > 0 && c_in <= C && (long)B * H * W < (1L << 22), "bad shape (B*H*W < 2^22)");
   *bytes = align_up(dc_layout(B, c_in, H, W, nullptr, nullptr));
   return SLOTVPS_OK;
 }
@@ -1492,7 +1492,7 @@ int slotvps_deform_conv_forward(const float* input, const float* weight, const f
   memset(&l, 0, sizeof(l));
   l.c_in = c_in; l.c_out = c_out;
   SV_TRY(dcn::validate_layer(l));
-  SV_REQUIRE(B > 0 && H > 0 && W > 0 && (long)B * H * W < (1L << 30), "bad shape");
+  SV_REQUIRE(B > 0 && H > 0 && W > 0 && (long)B * H * W < (1L << 22), "bad shape (the kernels index pixels x channels in 32 bits: B*H*W < 2^22)");
   if (workspace_bytes < align_up(dc_layout(B, c_in, H, W, nullptr, nullptr))) return fail(SLOTVPS_EWORKSPACE, "deform_conv: workspace too small%s%s");
   cudaStream_t s = (cudaStream_t)stream;
   SV_PROF_ENTRY();
