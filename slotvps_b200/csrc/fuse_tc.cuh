@@ -122,6 +122,9 @@ __global__ void __launch_bounds__(256) conv_planes_kernel(const float* __restric
   out[i] = h; out[(long)C * K + i] = l;
 }
 
+// MODE (compile time, so that each form keeps only its own state in registers): 0 = plain GEMM to y_out (coarse pass, DCN GEMMs),
+// 1 = main pass with the warp-cooperative gather of the coarse term (w % 32 == 0), 2 = main pass, generic gather / no coarse term.
+template <int MODE>
 __global__ void __launch_bounds__(fuse::THREADS, 1)
 fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_o,
                const fuse::Params prm) {
@@ -240,10 +243,10 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int i00 = 0, i01 = 0, i10 = 0, i11 = 0;
       float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
       // cooperative gather (w % 32 == 0: a warp's 32 pixels share one image row and one frame)
-      const bool coop = prm.y_in != nullptr && (prm.w & 31) == 0;
+      constexpr bool coop = MODE == 1;
       int cbase = 0, cy0 = 0, cy1 = 0, ccol = 0, cs0 = 0, cs1 = 0;
       float cwy0 = 0.f, cwy1 = 0.f, cwx0 = 0.f, cwx1 = 0.f;
-      if (prm.y_in) {
+      if (MODE != 0 && prm.y_in) {
         const int ch = prm.h / 2, cw = prm.w / 2;
         const float sy = fmaxf((py + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((px + 0.5f) * 0.5f - 0.5f, 0.f);
         const int y0 = (int)sy, x0 = (int)sx;
@@ -288,7 +291,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (!rv) continue;
 #pragma unroll
         for (int c = 0; c < 16; ++c) v[c] = fmaf(v[c], WSCALE_INV, bias[u * 16 + c]);
-        if (prm.y_out) {
+        if (MODE == 0) {
           float* dst = prm.y_out + (long)row * C + u * 16;
           tc::st_global_v8f(dst, v); tc::st_global_v8f(dst + 8, v + 8);
           continue;
@@ -313,7 +316,7 @@ fuse_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               v[8 * c + e] += cwx0 * u0 + cwx1 * u1;
             }
           }
-        } else if (prm.y_in) {
+        } else if (MODE == 2 && prm.y_in) {
           const float* a = prm.y_in + (long)i00 * C + u * 16;
           const float* b = prm.y_in + (long)i01 * C + u * 16;
           const float* cc = prm.y_in + (long)i10 * C + u * 16;
@@ -435,11 +438,15 @@ inline int fuse_tc_launch(const __half* a_planes, long a_rows_total, int a_lo_ro
   if (prm.tma_store && prm.planes)
     SV_TRY(tc::make_tmap_h16_sw128(&mo, prm.planes, (uint64_t)(prm.x_planes_only ? 2 : 4) * 4 * prm.plane_stride, 64, fuse::TILE_M));
   else mo = mw;                                                      // unused
-  SV_TRY(ensure_dyn_smem((const void*)fuse_tc_kernel, fuse::SMEM_BYTES));
+  const int mode = prm.y_out ? 0 : (prm.y_in != nullptr && (prm.w & 31) == 0) ? 1 : 2;
+  const void* fn = mode == 0 ? (const void*)fuse_tc_kernel<0> : mode == 1 ? (const void*)fuse_tc_kernel<1> : (const void*)fuse_tc_kernel<2>;
+  SV_TRY(ensure_dyn_smem(fn, fuse::SMEM_BYTES));
   const int n_tiles = ceil_div(prm.rows, fuse::TILE_M);
   const int grid = n_tiles < max_ctas ? n_tiles : max_ctas;
   g_prof_grid = grid;
-  fuse_tc_kernel<<<grid, fuse::THREADS, fuse::SMEM_BYTES, s>>>(ma, mw, mo, prm);
+  if (mode == 0) fuse_tc_kernel<0><<<grid, fuse::THREADS, fuse::SMEM_BYTES, s>>>(ma, mw, mo, prm);
+  else if (mode == 1) fuse_tc_kernel<1><<<grid, fuse::THREADS, fuse::SMEM_BYTES, s>>>(ma, mw, mo, prm);
+  else fuse_tc_kernel<2><<<grid, fuse::THREADS, fuse::SMEM_BYTES, s>>>(ma, mw, mo, prm);
   SV_CHECK_LAUNCH("fuse_tc");
   return SLOTVPS_OK;
 }
