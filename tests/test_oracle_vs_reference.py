@@ -61,3 +61,41 @@ def test_stage_by_stage_teacher_forced(ref_model):
         _, ref_pm, _ = ref_model.generate_final_outputs([f.clone() for f in fused[-1]], emb[-1], generate_aux_output=False)
     pm = O.mask_logits(fused[-1][-1][0], emb[-1][-1, 0], cap)
     assert rel_l2(pm.numpy(), ref_pm[0].numpy()) < 2e-6
+
+
+def test_upsnet_subnet_wiring_against_live_reference(ref_model):
+    """SURVEY 8f rank 4 against the reference's own UPSNetFPN instance (upsnetFPN.py:36-49): the mirror loads the reference
+    subnet's state_dict strictly, `patch_upsnet_subnet` swaps it in place, and everything of the chain EXCEPT the CUDA-only
+    deformable op -- the offset convolutions, GroupNorm(32) eps / grouping, ReLU -- is compared module by module with the oracle
+    (the op itself is pinned by tests/golden/dcn_*.npz, frozen from the reference's compiled op on the B200)."""
+    from slotvps_b200.dcn import B200DeformSubnet
+    from slotvps_b200.integration import patch_upsnet_subnet
+    fpn = ref_model.image_model.panopticFPN
+    seq = fpn.deform_convs[0]
+    sd = synthetic.make_dcn_state_dict(3, fpn.in_channels, fpn.out_channels)
+    assert list(seq.state_dict().keys()) == list(sd.keys())
+    seq.load_state_dict(sd, strict=True)                                    # the synthetic parameters fit the reference module
+    mirror = B200DeformSubnet(fpn.in_channels, fpn.out_channels)
+    mirror.load_state_dict(seq.state_dict(), strict=True)
+    for (k, a), (k2, b) in zip(mirror.state_dict().items(), seq.state_dict().items()):
+        assert k == k2 and torch.equal(a, b)
+    x = synthetic.make_fpn_level(3, 1, fpn.in_channels, 9, 11)
+    cur = x
+    for i in range(3):
+        dc, gn, act = seq[3 * i], seq[3 * i + 1], seq[3 * i + 2]
+        with torch.no_grad():
+            off_ref = dc.conv_offset(cur)                                    # deform_conv_with_offset.py:38-39
+        off = torch.nn.functional.conv2d(cur, sd[f"{3 * i}.conv_offset.weight"], sd[f"{3 * i}.conv_offset.bias"], padding=1)
+        assert rel_l2(off.numpy(), off_ref.numpy()) < 1e-6
+        y = O.deform_conv(cur, off_ref, sd[f"{3 * i}.conv.weight"])
+        with torch.no_grad():
+            want = act(gn(y.clone()))                                       # the reference's own GroupNorm / ReLU modules
+        one = {"0.conv_offset.weight": sd[f"{3 * i}.conv_offset.weight"], "0.conv_offset.bias": sd[f"{3 * i}.conv_offset.bias"],
+               "0.conv.weight": sd[f"{3 * i}.conv.weight"], "1.weight": sd[f"{3 * i + 1}.weight"], "1.bias": sd[f"{3 * i + 1}.bias"]}
+        got = O.dcn_subnet(one, cur, n_layers=1)
+        assert rel_l2(got.numpy(), want.numpy()) < 2e-6, i
+        cur = want
+    net = patch_upsnet_subnet(ref_model)
+    assert fpn.deform_convs[0] is net and isinstance(net, B200DeformSubnet) and not net.training
+    with pytest.raises(Exception):                                           # the mirror has no CPU path
+        fpn.deform_convs[0](x)
