@@ -81,7 +81,9 @@ class B200DeformConvWithOffset(nn.Module):
 class B200DeformSubnet(nn.Sequential):
     """Drop-in for ``UPSNetFPN.deform_convs[0]``: an ``nn.Sequential`` whose entries 0/3/6 are DeformConvWithOffset, 1/4/7
     GroupNorm(32) and 2/5/8 ReLU, so ``load_state_dict(ref.deform_convs[0].state_dict(), strict=True)`` works; ``forward``
-    runs the whole chain in one C-ABI call.  [B,c_in,H,W] -> [B,c_out,H,W]."""
+    runs the whole chain in one C-ABI call.  [B,c_in,H,W] -> [B,c_out,H,W].  One scratch buffer serves every call of the
+    instance (the FPN levels run one after the other on the current stream, as in UPSNetFPN.forward): do not call one instance
+    from several streams at once."""
 
     def __init__(self, in_channels: int = 256, out_channels: int = 128, num_groups: int = 32, channels=None):
         # upsnetFPN.py:37-48; `channels` = explicit [(c_in, c_out), ...] (a single layer for teacher-forced tests)
@@ -92,7 +94,8 @@ class B200DeformSubnet(nn.Sequential):
         super().__init__(*mods)
         self._prepared = None
         self._key = None
-        self._ws = {}
+        self._ws = {}            # (B, H, W, device) -> workspace bytes
+        self._wsbuf = None
 
     def _descs(self):
         n = len(self) // 3
@@ -134,8 +137,12 @@ class B200DeformSubnet(nn.Sequential):
         if wkey not in self._ws:
             nbytes = C.c_size_t()
             _lib.check(_lib.lib().slotvps_dcn_workspace_bytes(arr, n, B, H, W, C.byref(nbytes)), "slotvps_dcn_workspace_bytes")
-            self._ws = {wkey: torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)}     # one shape at a time (largest level: 2.8 GB)
-        ws = self._ws[wkey]
+            self._ws[wkey] = nbytes.value
+        need = self._ws[wkey]
+        if self._wsbuf is None or self._wsbuf.device != x.device or self._wsbuf.numel() < need:
+            self._wsbuf = None                                   # one scratch buffer, grown to the largest level seen (FPN levels share it)
+            self._wsbuf = torch.empty(need, dtype=torch.uint8, device=x.device)
+        ws = self._wsbuf
         out = torch.empty((B, self[3 * (n - 1)].out_channels, H, W), dtype=torch.float32, device=x.device)
         _lib.check(_lib.lib().slotvps_dcn_subnet_forward(arr, n, self._prepared.data_ptr(), x.data_ptr(), out.data_ptr(), B, H, W,
                                                         ws.data_ptr(), ws.numel(), _stream_ptr(x.device)), "slotvps_dcn_subnet_forward")
