@@ -1447,10 +1447,16 @@ int slotvps_dcn_subnet_forward(const slotvps_dcn_layer* layers, int n_layers, co
     dcn::offset_shift_kernel<<<(unsigned)((rows * dcn::NOFF + 255) / 256), 256, 0, s>>>(w.z, layers[i].offset_b, w.off, H, W, rows);
     SV_CHECK_LAUNCH("dcn_offset_shift");
     dcn::Off off{w.off, (long)P * dcn::NOFF, dcn::NOFF, 1};
-    SV_TRY(dcn::conv_gemm(w.act, off, lp[i].wplanes, w.planes, w.y, cin, cout, B, H, W, s));
-    dcn::gn_partial_kernel<<<dim3(w.slabs, B), 256, 0, s>>>(w.y, w.part, P, cout);
-    SV_CHECK_LAUNCH("dcn_gn_partial");
-    dcn::gn_final_kernel<<<B, 256, 0, s>>>(w.part, w.slabs, B, layers[i].gn_w, layers[i].gn_b, w.aff, P, cout);
+    // GroupNorm statistics: from the implicit-GEMM epilogue's per-tile partials when a tile lies in one image, else a pass over y
+    const bool fused_stats = !dcn::use_im2col() && P % 128 == 0;
+    SV_TRY(dcn::conv_gemm(w.act, off, lp[i].wplanes, w.planes, w.y, cin, cout, B, H, W, s, fused_stats ? w.tpart : nullptr));
+    if (fused_stats) {
+      dcn::gn_final_tiles_kernel<<<dim3(B, dcn::NG), 256, 0, s>>>(w.tpart, layers[i].gn_w, layers[i].gn_b, w.aff, P, cout);
+    } else {
+      dcn::gn_partial_kernel<<<dim3(w.slabs, B), 256, 0, s>>>(w.y, w.part, P, cout);
+      SV_CHECK_LAUNCH("dcn_gn_partial");
+      dcn::gn_final_kernel<<<B, 256, 0, s>>>(w.part, w.slabs, B, layers[i].gn_w, layers[i].gn_b, w.aff, P, cout);
+    }
     SV_CHECK_LAUNCH("dcn_gn_final");
   }
   const int cout = layers[n_layers - 1].c_out;

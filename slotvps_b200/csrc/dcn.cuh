@@ -14,7 +14,8 @@
 //                reference's fp32 column buffer)
 //   GEMM         tcgen05 through the level-fusion kernel's plain-GEMM mode (TMA A/B stages, 3-product fp16 hi/lo, fp32
 //                accumulation in TMEM), MMA N = c_out
-//   GroupNorm    statistics of the raw output (slab partials in fp32, combined in double, fixed order)
+//   GroupNorm    statistics of the raw output: per-tile column sums / sums of squares from the implicit-GEMM epilogue (no pass over y),
+//                combined in double per (image, group) in a fixed order; a slab kernel over y where a tile would straddle two images
 // Next: gather straight into the shared-memory A stages (no column planes in HBM).
 #pragma once
 #include "common.cuh"
@@ -186,12 +187,13 @@ constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 constexpr int NSTAGE = 2;
 constexpr int G_WARPS = 16, E_WARPS = 4;
 constexpr int THREADS = 32 * (2 + E_WARPS + G_WARPS); // 704: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue, warps 6..21 gather
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 4096 + 1024;
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 4096 + 8192 + 1024;    // stages, barriers, GroupNorm partials [4][256][2], alignment
 struct Params {
   const float* act; int Cn;                           // activation [rows][Cn] fp32
   Off off;                                            // sampling offsets (p == null: regular convolution)
   float* y;                                           // [rows][256]
   int rows, P, H, W, n_out;
+  float* gn_part;                                     // optional [tiles][256][2]: per-tile column sums and sums of squares of y (GroupNorm statistics)
 };
 }  // namespace tcg
 
@@ -266,9 +268,11 @@ __global__ void __launch_bounds__(tcg::THREADS, 1) dcn_tc_kernel(const __grid_co
       if (el) tc::umma_commit(&tfull[g]);
     }
   } else if (warp < 2 + E_WARPS) {
-    // ---- epilogue: one thread per pixel row, 32 columns at a time ----
+    // ---- epilogue: one thread per pixel row, 32 columns at a time; optionally the tile's column sums / sums of squares (the
+    //      GroupNorm statistics of the raw output: no separate pass over y) ----
     const int q = warp & 3, r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float* gsm = reinterpret_cast<float*>(aux + 4096);          // [4 quadrants][256][2]
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const int g = ti & 1, u = ti >> 1;
@@ -280,13 +284,41 @@ __global__ void __launch_bounds__(tcg::THREADS, 1) dcn_tc_kernel(const __grid_co
         tc::tmem_ld32(tmem_base + lane_addr + g * 256 + j, v);
         tc::tmem_ld_wait();
         if (j + 32 >= prm.n_out) { tc::tc_fence_before(); tc::mbar_arrive(&tempty[g]); }
-        if (row < prm.rows) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] *= fuse::WSCALE_INV;
+        for (int c = 0; c < 32; ++c) v[c] *= fuse::WSCALE_INV;  // rows past the end were gathered as zeros: they add nothing below
+        if (row < prm.rows) {
           float* dst = prm.y + row * C + j;
 #pragma unroll
           for (int c = 0; c < 4; ++c) tc::st_global_v8f(dst + 8 * c, v + 8 * c);
         }
+        if (prm.gn_part) {
+          // transpose-reduce over the warp's 32 rows: after five halving exchanges lane l holds column j + l (31 shuffles per quantity)
+          float w2[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) w2[c] = v[c] * v[c];
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float s1 = up ? v[i] : v[i + off], s2 = up ? w2[i] : w2[i + off];
+              const float r1 = __shfl_xor_sync(0xffffffffu, s1, off), r2 = __shfl_xor_sync(0xffffffffu, s2, off);
+              v[i] = (up ? v[i + off] : v[i]) + r1;
+              w2[i] = (up ? w2[i + off] : w2[i]) + r2;
+            }
+          }
+          gsm[(q * C + j + lane) * 2] = v[0]; gsm[(q * C + j + lane) * 2 + 1] = w2[0];
+        }
+      }
+      if (prm.gn_part) {
+        asm volatile("bar.sync 2, 128;" ::: "memory");          // the four epilogue warps
+        const int t128 = (warp - 2) * 32 + lane;
+        for (int c = t128; c < prm.n_out; c += 128) {
+          const float a = ((gsm[c * 2] + gsm[(C + c) * 2]) + gsm[(2 * C + c) * 2]) + gsm[(3 * C + c) * 2];
+          const float b = ((gsm[c * 2 + 1] + gsm[(C + c) * 2 + 1]) + gsm[(2 * C + c) * 2 + 1]) + gsm[(3 * C + c) * 2 + 1];
+          *reinterpret_cast<float2*>(prm.gn_part + ((long)tile * C + c) * 2) = make_float2(a, b);
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");          // gsm is free for the next tile
       }
     }
   } else {
@@ -404,6 +436,33 @@ __global__ void __launch_bounds__(256) gn_final_kernel(const double* __restrict_
   if (c < Cout) { sc = gw[c] * rstd[c / cpg]; sh = gb[c] - mean[c / cpg] * sc; }
   aff[(long)b * 2 * C + c] = sc; aff[(long)b * 2 * C + C + c] = sh;
 }
+// Same from the per-tile partials of the implicit-GEMM epilogue: part [tiles][256][2] floats, tiles of 128 pixels, P % 128 == 0 (a tile lies
+// in one image).  One block per (image, group): thread t adds the tiles t, t + 256, ... over the group's channels in double, then a
+// fixed-order tree over the 256 threads (deterministic); the group's channels get their affine from the same block.
+__global__ void __launch_bounds__(256) gn_final_tiles_kernel(const float* __restrict__ part, const float* __restrict__ gw,
+                                                             const float* __restrict__ gb, float* __restrict__ aff, int P, int Cout) {
+  __shared__ double ra[256], rq[256];
+  const int b = blockIdx.x, grp = blockIdx.y, t0 = threadIdx.x, cpg = Cout / NG, tpi = P / 128;
+  double sa = 0.0, sq = 0.0;
+  for (int t = t0; t < tpi; t += 256) {
+    const float* src = part + (((long)b * tpi + t) * C + grp * cpg) * 2;
+    for (int e = 0; e < cpg; ++e) { sa += (double)src[2 * e]; sq += (double)src[2 * e + 1]; }
+  }
+  ra[t0] = sa; rq[t0] = sq;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t0 < o) { ra[t0] += ra[t0 + o]; rq[t0] += rq[t0 + o]; }
+    __syncthreads();
+  }
+  const double n = (double)P * cpg, m = ra[0] / n, var = fmax(rq[0] / n - m * m, 0.0);
+  const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)GN_EPS));
+  if (t0 < cpg) {
+    const int c = grp * cpg + t0;
+    const float sc = gw[c] * rstd;
+    aff[(long)b * 2 * C + c] = sc; aff[(long)b * 2 * C + C + c] = gb[c] - mean * sc;
+  }
+  if (grp == 0 && t0 >= Cout && t0 < C) { aff[(long)b * 2 * C + t0] = 0.f; aff[(long)b * 2 * C + C + t0] = 0.f; }     // channels >= Cout: (0, 0)
+}
 // out [B][Cout][P] = relu(y * scale + shift)  (NHWC rows of 256 -> NCHW), or the raw values when aff == null
 __global__ void __launch_bounds__(256) act_to_nchw_kernel(const float* __restrict__ y, const float* __restrict__ aff, float* __restrict__ out, int P, int Cout) {
   __shared__ float tile[32][33];
@@ -440,7 +499,7 @@ inline size_t prep_layout(const slotvps_dcn_layer* L, int n, void* base, LayerPr
 }
 // act: fp32 activation entering the current layer [rows][cin]; y: raw conv output [rows][256] (becomes the next activation in place
 // when c_out == 256, else compacted into act); z: offset-GEMM output [rows][256]; aplanes: activation planes [2][rows][cin]
-struct Ws { float *act, *y, *z, *off, *aff; __half *aplanes, *planes; double* part; int slabs; };
+struct Ws { float *act, *y, *z, *off, *aff, *tpart; __half *aplanes, *planes; double* part; int slabs; };
 inline size_t ws_layout(int cin_max, int B, int H, int W, void* base, Ws* w) {
   Arena a(base, (size_t)-1);
   const size_t rows = (size_t)B * H * W;
@@ -454,6 +513,7 @@ inline size_t ws_layout(int cin_max, int B, int H, int W, void* base, Ws* w) {
   x.planes = a.take<__half>(use_im2col() ? (size_t)2 * rows * KT * cin_max + 64 : 64);      // column planes: first form only
   x.slabs = ceil_div(H * W, GN_SLAB);
   x.part = a.take<double>((size_t)x.slabs * B * NG * 2);
+  x.tpart = a.take<float>((size_t)ceil_div((int)rows, 128) * C * 2);                       // per-tile GroupNorm partials of the implicit-GEMM epilogue
   if (w) *w = x;
   return a.off;
 }
@@ -472,11 +532,13 @@ inline int gemm(const __half* a_planes, long rows, int K, const __half* w_planes
   return fuse_tc_launch(a_planes, 2 * rows, (int)rows, K, w_planes, prm, s);
 }
 // implicit-GEMM form: act [rows][Cn] -> y [rows][256] raw (first c_out columns), no column planes
-inline int conv_implicit(const float* act, const Off& off, const __half* wplanes, float* y, int Cn, int c_out, int B, int H, int W, cudaStream_t s) {
+inline int conv_implicit(const float* act, const Off& off, const __half* wplanes, float* y, int Cn, int c_out, int B, int H, int W, cudaStream_t s,
+                         float* gn_part = nullptr) {
   const long rows = (long)B * H * W;
   tcg::Params prm;
   prm.act = act; prm.Cn = Cn; prm.off = off; prm.y = y; prm.rows = (int)rows; prm.P = H * W; prm.H = H; prm.W = W;
   prm.n_out = (c_out + 15) / 16 * 16;
+  prm.gn_part = gn_part;
   CUtensorMap mw;
   SV_TRY(tc::make_tmap_h16_sw128(&mw, wplanes, (uint64_t)2 * C, (uint64_t)KT * Cn, prm.n_out));
   SV_TRY(ensure_dyn_smem((const void*)dcn_tc_kernel, tcg::SMEM_BYTES));
@@ -489,9 +551,9 @@ inline int conv_implicit(const float* act, const Off& off, const __half* wplanes
 }
 // columns + GEMM of one deformable (off.p != null) convolution: act [rows][Cn] -> y [rows][256] raw (first c_out columns)
 inline int conv_gemm(const float* act, const Off& off, const __half* wplanes, __half* planes, float* y, int Cn, int c_out, int B, int H, int W,
-                     cudaStream_t s) {
+                     cudaStream_t s, float* gn_part = nullptr) {
   const long rows = (long)B * H * W;
-  if (!use_im2col()) return conv_implicit(act, off, wplanes, y, Cn, c_out, B, H, W, s);
+  if (!use_im2col()) return conv_implicit(act, off, wplanes, y, Cn, c_out, B, H, W, s, gn_part);
   dcn_im2col_kernel<<<grid_for(rows * KT * (Cn / 8)), 256, 0, s>>>(act, off, planes, rows, Cn, H, W, B);
   SV_CHECK_LAUNCH("dcn_im2col");
   return gemm(planes, rows, KT * Cn, wplanes, y, (c_out + 15) / 16 * 16, H, W, s);
