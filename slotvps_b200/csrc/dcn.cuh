@@ -5,18 +5,17 @@
 //
 // B200 form of this row.  Activations stay pixel-major (NHWC) between the layers, so the four bilinear corners of a tap are
 // contiguous channel runs.  Per layer:
-//   act_planes   GroupNorm + ReLU of the previous layer (a per-(image, channel) affine) applied ONCE: fp32 activation (in place)
-//                + its fp16 hi/lo operand planes
+//   operand      layer 0: the NCHW -> NHWC pass also writes the fp16 hi/lo operand planes of the input; later layers: act_planes applies
+//                GroupNorm + ReLU of the previous layer (a per-(image, channel) affine) ONCE -> fp32 activation + its operand planes
 //   offset conv  (regular 3x3, 18 outputs) as ONE 1x1 tensor-core GEMM with N = 9 taps x 18 = 162 outputs per pixel
-//                (z[p][tap][o] = W_tap[o] . a[p]) followed by a 9-tap shift-sum -- a regular convolution is a sum of shifted
-//                1x1 convolutions, so nothing is gathered and no column buffer exists for it
-//   im2col       bilinear sampling written once as fp16 hi/lo operand planes [2][pixels][9 C_in] (the same bytes as the
-//                reference's fp32 column buffer)
-//   GEMM         tcgen05 through the level-fusion kernel's plain-GEMM mode (TMA A/B stages, 3-product fp16 hi/lo, fp32
-//                accumulation in TMEM), MMA N = c_out
+//                (z[p][tap][o] = W_tap[o] . a[p]; the level-fusion kernel's plain-GEMM mode) followed by a 9-tap shift-sum -- a regular
+//                convolution is a sum of shifted 1x1 convolutions, so nothing is gathered and no column buffer exists for it
+//   deform conv  dcn_tc_kernel: implicit GEMM -- gather warps build the bilinear-sampled A stages straight in shared memory (fp16 hi/lo,
+//                128-byte swizzle), weights by TMA, 3 hi/lo products per k-step into TMEM, MMA N = c_out; NO column buffer
+//                (SLOTVPS_DCN_IM2COL=1 keeps the first form for A/B runs: bilinear im2col to fp16 planes [2][pixels][9 C_in] in HBM +
+//                the plain tensor-core GEMM; bit-identical results)
 //   GroupNorm    statistics of the raw output: per-tile column sums / sums of squares from the implicit-GEMM epilogue (no pass over y),
 //                combined in double per (image, group) in a fixed order; a slab kernel over y where a tile would straddle two images
-// Next: gather straight into the shared-memory A stages (no column planes in HBM).
 #pragma once
 #include "common.cuh"
 #include "fuse_tc.cuh"
