@@ -195,3 +195,48 @@ def test_dropin_l2_matches_reference_simple_test():
             n_clean += 1
             assert float(l.split("outside near-tie pixels ")[1].split(" %")[0]) < 0.5, l
     assert n_clean >= 3, lines
+
+
+def test_upsnet_forward_with_b200_subnet_matches_reference():
+    """SURVEY 8f rank 4 as a drop-in: the reference's own ``UPSNetFPN.forward`` (upsnetFPN.py:64-85) built from the unchanged
+    config runs UNMODIFIED on the GPU -- its DeformConv modules call the reference's compiled op (oracle/_ref, in place of the
+    extension the reference's setup.py would have built) -- and again after ``patch_upsnet_subnet`` swapped the deformable-conv
+    subnet for the B200 kernels; fcn_output, fcn_score and the four feature levels the head consumes must agree."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import ref_dcn                              # checker: the reference op
+    if not ref_dcn.available():
+        pytest.skip("oracle/_ref/deform_conv_cuda.so not built")
+    os.environ["SLOTVPS_REFERENCE_ROOT"] = REF
+    import importlib
+    import oracle.ref_import as ref_import
+    ref_import = importlib.reload(ref_import)
+    from slotvps_b200 import synthetic
+    from slotvps_b200.dcn import B200DeformSubnet
+    from slotvps_b200.integration import patch_upsnet_subnet
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    model, _ = ref_import.build_model(0)
+    dc_mod = importlib.import_module("mmdet.ops.dcn.deform_conv")
+    dc_mod.deform_conv_cuda = ref_dcn.module()              # the compiled extension deform_conv.py imports (stubbed by ref_import)
+    fpn = model.image_model.panopticFPN
+    fpn.deform_convs[0].load_state_dict(synthetic.make_dcn_state_dict(7, fpn.in_channels, fpn.out_channels, offset_scale=1.0), strict=True)
+    fpn = fpn.to(dev).eval()
+    H, W = 256, 512
+    inputs = [synthetic.make_fpn_level(30 + l, 1, fpn.in_channels, H // (4 << l), W // (4 << l)).to(dev) for l in range(fpn.num_levels)]
+    with torch.no_grad():
+        out_r, score_r, feats_r = fpn([x.clone() for x in inputs])
+    net = patch_upsnet_subnet(model)
+    assert isinstance(fpn.deform_convs[0], B200DeformSubnet) and fpn.deform_convs[0] is net
+    with torch.no_grad():
+        out_b, score_b, feats_b = fpn([x.clone() for x in inputs])
+
+    def rel(a, b):
+        a, b = a.double(), b.double()
+        return float((a - b).norm() / b.norm())
+    errs = [rel(out_b, out_r), rel(score_b, score_r)] + [rel(a, b) for a, b in zip(feats_b, feats_r)]
+    print("UPSNetFPN.forward, reference op vs patch_upsnet_subnet: fcn_output rel %.2e, fcn_score rel %.2e, feature levels %s"
+          % (errs[0], errs[1], " ".join("%.2e" % e for e in errs[2:])))
+    assert out_b.shape == out_r.shape == (1, fpn.num_classes, H, W) and len(feats_b) == len(feats_r) == 4
+    assert max(errs) < 5e-5
